@@ -1,0 +1,225 @@
+/*
+ * vkx.h — C ABI of libvkexp_b200.so: the B200-native DDGI probe update and 1-spp sun-shadow pass.
+ *
+ * This is the drop-in boundary for the hot path of Senryoku/VulkanExp. The reference has no FFI layer: its
+ * Editor calls two C++ classes directly (reference src/IrradianceProbes.hpp:16-129, src/Renderer.hpp:39-86) and
+ * the shaders see one shared descriptor ABI (reference src/RaytracingDescriptors.hpp:8-77). Every entry point
+ * below names the reference interface it replaces. All signatures are plain pointers and sizes; no C++ / torch
+ * types. Every function returns 0 on success and a negative VKX_E_* code on failure (the reference throws from
+ * VK_CHECK, src/vulkan/VkTools.hpp:39-47; the C++ facade in vulkanexp_b200/csrc/host re-throws these codes).
+ *
+ * There is no CPU fallback behind this ABI. If no CUDA device is usable vkx_create fails.
+ *
+ * POD layouts are byte-identical to the reference's (sizes are static_assert'ed in the implementation):
+ *   vkx_vertex        64 B  src/vulkan/Vertex.hpp:8-15
+ *   vkx_material      48 B  src/vulkan/Material.hpp:16-25
+ *   vkx_offset_entry  12 B  src/Renderer.hpp:21-25
+ *   vkx_grid_info     64 B  src/IrradianceProbes.hpp:49-60 (GLSL: src/shaders/ProbeGrid.glsl:4-15)
+ *   vkx_light         32 B  src/Light.hpp:6-9
+ *   vkx_camera       144 B  src/Editor.hpp:58-63
+ */
+#ifndef VKX_H
+#define VKX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VKX_ABI_VERSION 1
+
+/* error codes */
+#define VKX_OK 0
+#define VKX_E_INVALID (-1)  /* bad argument / call order */
+#define VKX_E_CUDA (-2)     /* a CUDA runtime call failed; vkx_last_error has the string */
+#define VKX_E_NOMEM (-3)
+#define VKX_E_UNSUPPORTED (-4) /* e.g. textured materials */
+#define VKX_E_NCCL (-5)
+
+#define VKX_MAX_RAYS_PER_PROBE 256 /* IrradianceProbes::MaxRaysPerProbe, src/IrradianceProbes.hpp:42 */
+#define VKX_INVALID_TEXTURE 0xFFFFFFFFu
+
+/* instance masks, src/shaders/InstanceMasks.glsl:1-3 */
+#define VKX_INSTANCE_STATIC 0x01u
+#define VKX_INSTANCE_DYNAMIC 0x02u
+#define VKX_INSTANCE_SKINNED 0x04u
+
+typedef struct vkx_vertex {
+    float pos[3];
+    float color[3];
+    float normal[3];
+    float tangent[4];
+    float texCoord[2];
+    uint32_t padding;
+} vkx_vertex;
+
+typedef struct vkx_material {
+    float metallicFactor;
+    float roughnessFactor;
+    float baseColorFactor[3];
+    float emissiveFactor[3];
+    uint32_t albedoTexture;
+    uint32_t normalTexture;
+    uint32_t metallicRoughnessTexture;
+    uint32_t emissiveTexture;
+} vkx_material;
+
+typedef struct vkx_offset_entry {
+    uint32_t materialIndex; /* the mesh's defaultMaterialIndex, src/Renderer.cpp:110-114 */
+    uint32_t vertexOffset;  /* in vertices */
+    uint32_t indexOffset;   /* in indices */
+} vkx_offset_entry;
+
+/* One TLAS instance (VkAccelerationStructureInstanceKHR as filled by Renderer::createTLAS, src/Renderer.cpp:532-551). */
+typedef struct vkx_instance {
+    float transform[12];  /* row-major 3x4 object-to-world (VkTransformMatrixKHR) */
+    uint32_t meshEntry;   /* instanceCustomIndex = index into the offset table */
+    uint32_t mask;        /* VKX_INSTANCE_* */
+} vkx_instance;
+
+typedef struct vkx_grid_info {
+    float extentMin[3];
+    float depthSharpness;
+    float extentMax[3];
+    float hysteresis;
+    int32_t resolution[3];
+    uint32_t raysPerProbe;
+    uint32_t colorRes; /* must be 8 */
+    uint32_t depthRes; /* must be 16 */
+    float shadowBias;
+    uint32_t padding;
+} vkx_grid_info;
+
+typedef struct vkx_light {
+    float direction[4];
+    float color[4];
+} vkx_light;
+
+typedef struct vkx_camera {
+    float view[16]; /* column-major, as glm::mat4 */
+    float proj[16];
+    float origin[3];
+    uint32_t frameIndex;
+} vkx_camera;
+
+/* Closest-hit record of the traversal kernels (parity primitive; the reference's RT hardware exposes the same
+ * quantities as gl_HitTEXT, gl_InstanceID/gl_PrimitiveID, hitAttributeEXT and gl_HitKindEXT). */
+typedef struct vkx_hit {
+    float t;           /* < 0: miss */
+    uint32_t instance; /* index into the uploaded instance list */
+    uint32_t primitive;/* triangle index inside the instance's mesh; bit 31 set: back-facing hit */
+    float u, v;        /* barycentrics of vertices 1 and 2 */
+} vkx_hit;
+
+typedef struct vkx_bvh_info {
+    uint32_t numNodes;      /* 8-wide compressed nodes, 80 B each */
+    uint32_t numTriangles;  /* flattened world-space triangles, 48 B each */
+    uint32_t numBinaryNodes;/* inner nodes of the intermediate binary SAH tree */
+    uint32_t depth;         /* depth of the wide tree (root = 1) */
+    float sceneMin[3];
+    float sceneMax[3];
+    float sahCost;          /* sum over wide nodes of area(node)/area(root) (diagnostic) */
+    float buildMs;          /* device time of the last build */
+} vkx_bvh_info;
+
+typedef struct vkx_ctx vkx_ctx;
+
+/* ---- context ---------------------------------------------------------------------------------------------- */
+/* Replaces Device creation + IrradianceProbes::init's device argument (src/IrradianceProbes.cpp:12-13). */
+int vkx_create(int device, vkx_ctx** out);
+void vkx_destroy(vkx_ctx* ctx); /* IrradianceProbes::destroy, src/IrradianceProbes.cpp:596-624 */
+const char* vkx_last_error(vkx_ctx* ctx); /* ctx may be NULL: error of the last failed vkx_create on this thread */
+int vkx_abi_version(void);
+
+/* ---- geometry: Renderer::allocateMeshes + createAccelerationStructures + createTLAS ------------------------ */
+/* Uploads the mesh arenas, the offset table (src/Renderer.cpp:97-126), the material SSBO and the instance list
+ * (one per MeshRendererComponent, already sorted as Renderer::sortRenderers does, src/Renderer.cpp:512-523).
+ * meshIndexCounts[m] = number of indices of mesh entry m (the reference keeps it in VkAccelerationStructure
+ * BuildRangeInfo.primitiveCount, src/Renderer.cpp:294-300). Textured materials are rejected (VKX_E_UNSUPPORTED). */
+int vkx_scene_upload(vkx_ctx* ctx, const vkx_vertex* vertices, size_t numVertices, const uint32_t* indices,
+                     size_t numIndices, const vkx_offset_entry* offsets, const uint32_t* meshIndexCounts,
+                     size_t numMeshes, const vkx_material* materials, size_t numMaterials,
+                     const vkx_instance* instances, size_t numInstances);
+
+/* Deterministic binned-SAH build of the 8-wide compressed BVH on the device (replaces the driver's BLAS/TLAS
+ * build, src/Renderer.cpp:272-449,525-642). Topology is bit-identical to oracle/bvh.cpp. */
+int vkx_bvh_build(vkx_ctx* ctx);
+int vkx_bvh_info_get(vkx_ctx* ctx, vkx_bvh_info* out);
+/* Copies the device BVH back: nodes (80 B each) and triangles (48 B each). Either pointer may be NULL. */
+int vkx_bvh_download(vkx_ctx* ctx, void* nodes, size_t nodesBytes, void* triangles, size_t trianglesBytes);
+
+/* Parity primitive: traces n rays given in host memory (origins/directions: 3 floats each) through the device
+ * BVH. anyHit != 0: terminate-on-first-hit query (shadow rays), out[i].t = 1 if occluded else -1. */
+int vkx_trace(vkx_ctx* ctx, const float* origins, const float* directions, size_t n, float tmin, float tmax,
+              uint32_t cullMask, int anyHit, vkx_hit* out);
+
+/* ---- DDGI: IrradianceProbes ----------------------------------------------------------------------------------- */
+/* IrradianceProbes::init (src/IrradianceProbes.cpp:12-104): allocates both atlases (work + sampled), the state
+ * buffer and the per-chunk ray buffer; atlases and states are zero-initialised. */
+int vkx_probes_init(vkx_ctx* ctx, const vkx_grid_info* grid);
+/* IrradianceProbes::initProbes (src/IrradianceProbes.cpp:357-394) -> probesInit.rgen. orientation = the push
+ * constant mat4 (column-major). */
+int vkx_probes_classify(vkx_ctx* ctx, const float orientation[16]);
+/* IrradianceProbes::update's recorded work (src/IrradianceProbes.cpp:486-576): trace + shade, blend irradiance and
+ * depth, copy borders, publish. probeIndices = the to-update list produced by selectProbesToUpdate
+ * (src/IrradianceProbes.cpp:396-424), host memory; NULL = every probe in linear order ("full-volume update").
+ * Asynchronous on the context's stream unless sync != 0. */
+int vkx_probes_update(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx_light* light, const float orientation[16],
+                      const uint32_t* probeIndices, uint32_t count, int sync);
+/* Readback of the *sampled* atlases (what FinalGather/closest-hit read), packed as the reference formats:
+ * irradiance B10G11R11_UFLOAT_PACK32 [8*rz rows][8*rx*ry cols] u32, depth R16G16_SFLOAT same shape x2, state u32[P].
+ * rays (optional) = the RGBA32F ray buffer of the last update [count][raysPerProbe] (rgb, depth). NULL skips. */
+int vkx_probes_download(vkx_ctx* ctx, uint32_t* irradiance, uint32_t* depth, uint32_t* state, float* rays,
+                        size_t raysCapacityBytes);
+/* Checkpoint/resume of GI state. NULL skips an array. */
+int vkx_probes_upload(vkx_ctx* ctx, const uint32_t* irradiance, const uint32_t* depth, const uint32_t* state);
+/* Debug/parity: pre-pack fp32 blend results of the last update: irr [count][36][3], depth [count][196][2]. */
+int vkx_probes_download_unpacked(vkx_ctx* ctx, float* irr, float* depth);
+/* Hit records (vkx_hit) of the primary rays of the last update, [count][raysPerProbe]; and the shadow-ray
+ * visibility bytes (0 = not traced, 1 = lit, 2 = shadowed). NULL skips. */
+int vkx_probes_download_hits(vkx_ctx* ctx, vkx_hit* hits, uint8_t* shadow);
+/* getComputeTimes/TraceTimes/UpdateTimes/BorderCopyTimes/CopyTimes (src/IrradianceProbes.hpp:68-72), last update:
+ * ms[0] full, ms[1] trace+shade, ms[2] blend (+borders, fused), ms[3] border (0: fused), ms[4] publish. Syncs. */
+int vkx_probes_timings(vkx_ctx* ctx, float ms[5]);
+/* Device pointers for zero-copy consumers (e.g. torch tensors over the sampled atlases). */
+int vkx_probes_device_ptrs(vkx_ctx* ctx, void** irradiance, void** depth, void** state);
+
+/* ---- multi-GPU: probe z-slabs + atlas all-gather (no reference equivalent) -------------------------- */
+/* ncclUniqueId is 128 bytes; create it on rank 0 with vkx_comm_unique_id and broadcast it out of band. */
+int vkx_comm_unique_id(void* id128);
+int vkx_comm_init(vkx_ctx* ctx, int rank, int nranks, const void* id128);
+/* Full-volume update of this rank's z-slab followed by the all-gather of the atlas/state slabs. */
+int vkx_probes_update_sharded(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx_light* light,
+                              const float orientation[16], int sync);
+
+/* ---- sun shadows: DirectLight pass ---------------------------------------------------------------------------- */
+/* Blue-noise slices (RGBA32F = byte/255, src/vulkan/Image.cpp:62-69): [slices][h][w][4]. */
+int vkx_shadow_set_noise(vkx_ctx* ctx, const float* rgba, uint32_t w, uint32_t h, uint32_t slices);
+int vkx_shadow_init(vkx_ctx* ctx, uint32_t width, uint32_t height);
+/* Fixture generator for the G-buffer the raster pass produces (src/shaders/GBuffer.frag:64-68): primary rays
+ * through the same BVH. Fills the device-resident positionDepth / normalMetalness images. */
+int vkx_gbuffer_generate(vkx_ctx* ctx, const vkx_camera* cam);
+/* Or upload a host G-buffer (RGBA32F, [h][w][4]). */
+int vkx_gbuffer_upload(vkx_ctx* ctx, const float* positionDepth, const float* normalMetalness);
+int vkx_gbuffer_download(vkx_ctx* ctx, float* positionDepth, float* normalMetalness);
+/* One frame of directLight.rgen -> directLightFilterX -> directLightFilterY (src/SwapchainManagement.cpp:409-438)
+ * with the history ping-pong of src/Editor.cpp:287-316. */
+int vkx_shadow_frame(vkx_ctx* ctx, const vkx_camera* cur, const vkx_camera* prev, const vkx_light* light, int sync);
+/* stage: 0 = raw 1-spp (directLight.rgen output), 1 = after filter X, 2 = final (after Y + temporal). RGBA32F. */
+int vkx_shadow_download(vkx_ctx* ctx, int stage, float* rgba);
+int vkx_shadow_reset_history(vkx_ctx* ctx);
+/* ms[0] full, ms[1] trace, ms[2] filter X, ms[3] filter Y. */
+int vkx_shadow_timings(vkx_ctx* ctx, float ms[4]);
+
+/* Kernel launch counter since context creation (bench.py's gpu_launches claim). */
+uint64_t vkx_launch_count(vkx_ctx* ctx);
+/* The context's CUDA stream (cudaStream_t) so callers can order torch work after it. */
+void* vkx_stream(vkx_ctx* ctx);
+int vkx_sync(vkx_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VKX_H */

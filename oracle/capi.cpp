@@ -1,0 +1,192 @@
+// TEST INFRASTRUCTURE — C API of the CPU oracle (liboracle.so). Only tests/, __graft_entry__.smoke() and
+// bench.py's cpu_baseline / --impl reference legs may load this library; the product path never does.
+#include <chrono>
+#include <cstring>
+#include <new>
+#include "bvh.h"
+#include "ddgi.h"
+#include "shadow.h"
+#include "packing.h"
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+struct orc_ctx {
+    oddgi::Scene scene;
+    oddgi::Probes probes;
+    oshadow::State shadow;
+};
+
+extern "C" {
+
+orc_ctx* orc_create() { return new (std::nothrow) orc_ctx(); }
+void orc_destroy(orc_ctx* c) { delete c; }
+int orc_max_threads() {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+int orc_scene_upload(orc_ctx* c, const vkx_vertex* v, size_t nv, const uint32_t* idx, size_t ni, const vkx_offset_entry* off,
+                     const uint32_t* counts, size_t nm, const vkx_material* mat, size_t nmat, const vkx_instance* inst, size_t ninst) {
+    oddgi::Scene& s = c->scene;
+    s.vertices.assign(v, v + nv); s.indices.assign(idx, idx + ni); s.offsets.assign(off, off + nm);
+    s.meshIndexCounts.assign(counts, counts + nm); s.materials.assign(mat, mat + nmat); s.instances.assign(inst, inst + ninst);
+    return 0;
+}
+int orc_bvh_build(orc_ctx* c) { oddgi::sceneFinalize(c->scene); return 0; }
+int orc_bvh_info(orc_ctx* c, vkx_bvh_info* out) {
+    const obvh::Bvh& b = c->scene.bvh;
+    std::memset(out, 0, sizeof(*out));
+    out->numNodes = uint32_t(b.nodes.size()); out->numTriangles = uint32_t(b.tris.size());
+    out->numBinaryNodes = b.numBinaryNodes; out->depth = b.depth;
+    for (int a = 0; a < 3; ++a) { out->sceneMin[a] = b.sceneMin[a]; out->sceneMax[a] = b.sceneMax[a]; }
+    return 0;
+}
+int orc_bvh_download(orc_ctx* c, void* nodes, size_t nb, void* tris, size_t tb) {
+    const obvh::Bvh& b = c->scene.bvh;
+    if (nodes) { if (nb < b.nodes.size() * 80) return -1; std::memcpy(nodes, b.nodes.data(), b.nodes.size() * 80); }
+    if (tris) { if (tb < b.tris.size() * 48) return -1; std::memcpy(tris, b.tris.data(), b.tris.size() * 48); }
+    return 0;
+}
+int orc_trace(orc_ctx* c, const float* o, const float* d, size_t n, float tmin, float tmax, uint32_t mask, int any, vkx_hit* out, uint64_t* counters) {
+    obvh::Counters total;
+#pragma omp parallel
+    {
+        obvh::Counters ctr;
+#pragma omp for schedule(dynamic, 256)
+        for (int64_t i = 0; i < int64_t(n); ++i) {
+            if (any) {
+                bool h = obvh::traceAny(c->scene.bvh, o + 3 * i, d + 3 * i, tmin, tmax, mask, &ctr);
+                out[i].t = h ? 1.0f : -1.0f; out[i].instance = 0xFFFFFFFFu; out[i].primitive = 0xFFFFFFFFu; out[i].u = out[i].v = 0.0f;
+            } else obvh::traceClosest(c->scene.bvh, o + 3 * i, d + 3 * i, tmin, tmax, mask, out[i], &ctr);
+        }
+#pragma omp critical
+        { total.nodes += ctr.nodes; total.tris += ctr.tris; total.rays += ctr.rays; }
+    }
+    if (counters) { counters[0] = total.rays; counters[1] = total.nodes; counters[2] = total.tris; }
+    return 0;
+}
+
+int orc_probes_init(orc_ctx* c, const vkx_grid_info* g) { oddgi::probesInit(c->probes, *g); return 0; }
+int orc_probes_classify(orc_ctx* c, const float R[16]) { oddgi::classify(c->scene, c->probes, R); return 0; }
+// returns elapsed seconds of the update in *seconds (trace+shade+blend+border+publish)
+int orc_probes_update(orc_ctx* c, const vkx_grid_info* g, const vkx_light* l, const float R[16], const uint32_t* indices, uint32_t count, int threads, double* seconds) {
+    auto t0 = std::chrono::steady_clock::now();
+    oddgi::update(c->scene, c->probes, *g, *l, R, indices, count, threads);
+    if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return 0;
+}
+int orc_probes_download(orc_ctx* c, uint32_t* irr, uint32_t* dep, uint32_t* state, float* rays, size_t raysCap) {
+    oddgi::Probes& p = c->probes;
+    if (irr) std::memcpy(irr, p.irrSampled.data(), p.irrSampled.size() * 4);
+    if (dep) std::memcpy(dep, p.depSampled.data(), p.depSampled.size() * 4);
+    if (state) std::memcpy(state, p.state.data(), p.state.size() * 4);
+    if (rays) { if (raysCap < p.rays.size() * 4) return -1; std::memcpy(rays, p.rays.data(), p.rays.size() * 4); }
+    return 0;
+}
+int orc_probes_upload(orc_ctx* c, const uint32_t* irr, const uint32_t* dep, const uint32_t* state) {
+    oddgi::Probes& p = c->probes;
+    if (irr) { std::memcpy(p.irrSampled.data(), irr, p.irrSampled.size() * 4); p.irrWork = p.irrSampled; }
+    if (dep) { std::memcpy(p.depSampled.data(), dep, p.depSampled.size() * 4); p.depWork = p.depSampled; }
+    if (state) std::memcpy(p.state.data(), state, p.state.size() * 4);
+    return 0;
+}
+int orc_probes_download_unpacked(orc_ctx* c, float* irr, float* dep) {
+    oddgi::Probes& p = c->probes;
+    if (irr) std::memcpy(irr, p.irrUnpacked.data(), p.irrUnpacked.size() * 4);
+    if (dep) std::memcpy(dep, p.depUnpacked.data(), p.depUnpacked.size() * 4);
+    return 0;
+}
+int orc_probes_download_hits(orc_ctx* c, vkx_hit* hits, uint8_t* shadow) {
+    oddgi::Probes& p = c->probes;
+    if (hits) std::memcpy(hits, p.hits.data(), p.hits.size() * sizeof(vkx_hit));
+    if (shadow) std::memcpy(shadow, p.shadow.data(), p.shadow.size());
+    return 0;
+}
+// counters of the last update: rays (primary + shadow), nodes visited, triangles tested, front hits
+int orc_probes_counters(orc_ctx* c, uint64_t out[4]) {
+    out[0] = c->probes.counters.rays; out[1] = c->probes.counters.nodes; out[2] = c->probes.counters.tris; out[3] = c->probes.frontHits;
+    return 0;
+}
+int orc_ray_directions(const float R[16], uint32_t count, float n, float* out) {
+    std::vector<float> d; oddgi::rayDirections(R, count, n, d); std::memcpy(out, d.data(), d.size() * 4); return 0;
+}
+
+// pure-function KATs
+void orc_spherical_fibonacci(float i, float n, float out[3]) { ovm::vec3 v = oddgi::sphericalFibonacci(i, n); out[0] = v.x; out[1] = v.y; out[2] = v.z; }
+void orc_oct_decode(float x, float y, float out[3]) { ovm::vec3 v = oddgi::octDecode(ovm::V2(x, y)); out[0] = v.x; out[1] = v.y; out[2] = v.z; }
+void orc_sphere_to_oct_uv(const float d[3], float out[2]) { ovm::vec2 v = oddgi::spherePointToOctohedralUV(ovm::V3(d[0], d[1], d[2])); out[0] = v.x; out[1] = v.y; }
+uint32_t orc_pack_r11g11b10(float r, float g, float b) { return opack::packR11G11B10(r, g, b); }
+void orc_unpack_r11g11b10(uint32_t p, float out[3]) { opack::unpackR11G11B10(p, out); }
+uint32_t orc_pack_rg16f(float r, float g) { return opack::packRG16F(r, g); }
+void orc_unpack_rg16f(uint32_t p, float out[2]) { opack::unpackRG16F(p, out); }
+void orc_sky(const float o[3], const float d[3], const vkx_light* l, float out[3]) {
+    ovm::vec3 c = oddgi::sky(ovm::V3(o[0], o[1], o[2]), ovm::V3(d[0], d[1], d[2]), ovm::V3(l->direction[0], l->direction[1], l->direction[2]),
+                             ovm::V3(l->color[0], l->color[1], l->color[2]), l->color[3], true);
+    out[0] = c.x; out[1] = c.y; out[2] = c.z;
+}
+void orc_sample_probes(orc_ctx* c, const float pos[3], const float n[3], const float toCam[3], float out[3]) {
+    ovm::vec3 r = oddgi::sampleProbes(c->probes, ovm::V3(pos[0], pos[1], pos[2]), ovm::V3(n[0], n[1], n[2]), ovm::V3(toCam[0], toCam[1], toCam[2]));
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+void orc_border_source(int T, int x, int y, int out[2]);
+
+// host logic (IrradianceProbes.cpp)
+struct orc_host { oddgi::MsvcRand rng; oddgi::Scheduler sched; };
+orc_host* orc_host_create() { return new orc_host(); }
+void orc_host_destroy(orc_host* h) { delete h; }
+void orc_host_next_orientation(orc_host* h, float out16[16], float Zout[3]) {
+    float Z[3]; oddgi::sphericalRand(h->rng, Z); oddgi::orientationFromZ(Z, out16);
+    if (Zout) { Zout[0] = Z[0]; Zout[1] = Z[1]; Zout[2] = Z[2]; }
+}
+void orc_orientation_from_z(const float Z[3], float out16[16]) { oddgi::orientationFromZ(Z, out16); }
+int orc_host_rand(orc_host* h) { return h->rng.next(); }
+uint32_t orc_host_select(orc_host* h, const uint32_t* state, uint32_t probeCount, uint32_t perUpdate, uint32_t* out) {
+    return oddgi::selectProbesToUpdate(h->sched, state, probeCount, perUpdate, out);
+}
+
+// shadows
+int orc_shadow_set_noise(orc_ctx* c, const float* rgba, uint32_t w, uint32_t h, uint32_t slices) {
+    c->shadow.noise.assign(rgba, rgba + size_t(w) * h * slices * 4); c->shadow.noiseW = w; c->shadow.noiseH = h; c->shadow.noiseSlices = slices; return 0;
+}
+int orc_shadow_init(orc_ctx* c, uint32_t w, uint32_t h) { oshadow::init(c->shadow, w, h); return 0; }
+int orc_gbuffer_generate(orc_ctx* c, const vkx_camera* cam) { oshadow::gbufferGenerate(c->scene, c->shadow, *cam); return 0; }
+int orc_gbuffer_upload(orc_ctx* c, const float* pd, const float* nm) {
+    std::memcpy(c->shadow.positionDepth.data(), pd, c->shadow.positionDepth.size() * 4);
+    std::memcpy(c->shadow.normalMetalness.data(), nm, c->shadow.normalMetalness.size() * 4); return 0;
+}
+int orc_gbuffer_download(orc_ctx* c, float* pd, float* nm) {
+    if (pd) std::memcpy(pd, c->shadow.positionDepth.data(), c->shadow.positionDepth.size() * 4);
+    if (nm) std::memcpy(nm, c->shadow.normalMetalness.data(), c->shadow.normalMetalness.size() * 4);
+    return 0;
+}
+int orc_shadow_frame(orc_ctx* c, const vkx_camera* cur, const vkx_camera* prev, const vkx_light* l, const float* dirOverride, double* seconds) {
+    auto t0 = std::chrono::steady_clock::now();
+    oshadow::frame(c->scene, c->shadow, *cur, *prev, *l, dirOverride);
+    if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return 0;
+}
+int orc_shadow_download(orc_ctx* c, int stage, float* rgba, float* dirs, uint8_t* mask) {
+    const std::vector<float>& src = stage == 0 ? c->shadow.raw : stage == 1 ? c->shadow.filteredX : c->shadow.final_;
+    if (rgba) std::memcpy(rgba, src.data(), src.size() * 4);
+    if (dirs) std::memcpy(dirs, c->shadow.dirs.data(), c->shadow.dirs.size() * 4);
+    if (mask) std::memcpy(mask, c->shadow.mask.data(), c->shadow.mask.size());
+    return 0;
+}
+int orc_shadow_reset_history(orc_ctx* c) {
+    std::fill(c->shadow.final_.begin(), c->shadow.final_.end(), 0.0f); std::fill(c->shadow.previous.begin(), c->shadow.previous.end(), 0.0f); return 0;
+}
+
+} // extern "C"
+
+// border table restated as a formula (checked against the reference's tables in tests/test_oracle_kat.py)
+extern "C" void orc_border_source(int T, int x, int y, int out[2]) {
+    const int L = T - 1;
+    bool bx = (x == 0 || x == L), by = (y == 0 || y == L);
+    if (bx && by) { out[0] = x == 0 ? L - 1 : 1; out[1] = y == 0 ? L - 1 : 1; }
+    else if (bx) { out[0] = x == 0 ? 1 : L - 1; out[1] = L - y; }
+    else { out[0] = L - x; out[1] = y == 0 ? 1 : L - 1; }
+}

@@ -1,0 +1,24 @@
+// TEST INFRASTRUCTURE — part of the CPU oracle. Never linked into, imported or called by the product path.
+#pragma once
+#include <cstdint>
+#include <vector>
+#include "ddgi.h"
+
+namespace oshadow {
+
+struct State {
+    uint32_t w = 0, h = 0;
+    std::vector<float> positionDepth, normalMetalness; // RGBA32F G-buffer
+    std::vector<float> raw, filteredX, final_, previous; // RGBA32F
+    std::vector<float> dirs;   // jittered light direction per pixel (debug / parity)
+    std::vector<uint8_t> mask; // 0 not traced, 1 lit, 2 shadowed
+    std::vector<float> noise;  // [slices][h][w][4]
+    uint32_t noiseW = 0, noiseH = 0, noiseSlices = 0;
+};
+
+void init(State& st, uint32_t w, uint32_t h);
+void gbufferGenerate(const oddgi::Scene& s, State& st, const vkx_camera& cam);
+// dirOverride (optional, [h][w][3]): use these jittered directions instead of computing them (bit-exact mask tests).
+void frame(const oddgi::Scene& s, State& st, const vkx_camera& cur, const vkx_camera& prev, const vkx_light& light, const float* dirOverride);
+
+} // namespace oshadow

@@ -1,0 +1,263 @@
+"""Python reader/writer for the reference's binary `.scene` container and the host-side flattening that turns a
+scene into the arrays the C ABI takes.
+
+This is harness code (fixtures for tests and bench.py); the product's loader is the C++ one in
+csrc/host/Scene.cpp. Both restate reference src/Scene.cpp:710-816 (save), :818-934 (loadScene), :936-961 (transform
+propagation), :1077-1103 (bounds), src/Renderer.cpp:97-126 (offset table) and :512-551 (instance list).
+"""
+from __future__ import annotations
+
+import json
+import struct
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .pods import INSTANCE_DTYPE, INSTANCE_STATIC, INVALID_TEXTURE, MATERIAL_DTYPE, OFFSET_DTYPE, VERTEX_DTYPE
+
+MAGIC = 0x4E454353  # "SCEN"
+CHUNK_JSON = 0x4E4F534A
+CHUNK_BIN = 0x004E4942
+
+IDENTITY16 = [1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0]
+
+
+@dataclass
+class Mesh:
+    name: str
+    material: int
+    vertices: np.ndarray  # VERTEX_DTYPE
+    indices: np.ndarray  # uint32
+
+
+@dataclass
+class Entity:
+    name: str
+    transform: list = field(default_factory=lambda: list(IDENTITY16))  # column-major m[col][row]
+    children: list = field(default_factory=list)
+    mesh_renderer: tuple | None = None  # (meshIndex, materialIndex)
+
+
+@dataclass
+class SceneFile:
+    materials: list = field(default_factory=list)  # glTF-style dicts
+    entities: list = field(default_factory=list)
+    meshes: list = field(default_factory=list)
+    textures: list = field(default_factory=list)
+
+
+def _fmt(v):
+    """Numbers as the reference's JSON writer prints them: std::to_string -> 6 decimals for floats (src/JSON.hpp:27-32)."""
+    if isinstance(v, bool):
+        return "true" if v else "false"
+    if isinstance(v, (int, np.integer)):
+        return str(int(v))
+    if isinstance(v, (float, np.floating)):
+        return "%.6f" % float(v)
+    if isinstance(v, str):
+        return json.dumps(v)
+    if isinstance(v, (list, tuple)):
+        return "[" + ",".join(_fmt(x) for x in v) + "]"
+    if isinstance(v, dict):
+        return "{" + ",".join(json.dumps(k) + ":" + _fmt(x) for k, x in v.items()) + "}"
+    raise TypeError(type(v))
+
+
+def material_json(name, base_color=(1.0, 1.0, 1.0), metallic=0.0, roughness=1.0, emissive=(0.0, 0.0, 0.0)):
+    return {
+        "name": name,
+        "pbrMetallicRoughness": {
+            "baseColorFactor": [float(base_color[0]), float(base_color[1]), float(base_color[2]), 1.0],
+            "metallicFactor": float(metallic),
+            "roughnessFactor": float(roughness),
+        },
+        "emissiveFactor": [float(e) for e in emissive],
+    }
+
+
+def write_scene(path, scene: SceneFile):
+    root = {
+        "materials": scene.materials,
+        "entities": [],
+        "meshes": [],
+        "textures": scene.textures,
+    }
+    for e in scene.entities:
+        ej = {"name": e.name, "transform": [float(x) for x in e.transform], "parent": -1, "children": [int(c) for c in e.children]}
+        if e.mesh_renderer is not None:
+            ej["meshRenderer"] = {"meshIndex": int(e.mesh_renderer[0]), "materialIndex": int(e.mesh_renderer[1])}
+        root["entities"].append(ej)
+    chunks = []
+    for m in scene.meshes:
+        offset = 1 + len(chunks)  # chunk indices count the JSON chunk as 0 (src/Scene.cpp:764-772)
+        root["meshes"].append({"name": m.name, "material": int(m.material), "vertexArray": offset, "indexArray": offset + 1})
+        chunks.append(np.ascontiguousarray(m.vertices, dtype=VERTEX_DTYPE).tobytes())
+        chunks.append(np.ascontiguousarray(m.indices, dtype="<u4").tobytes())
+    js = _fmt(root).encode("utf-8")
+    total = 12 + 8 + len(js) + sum(8 + len(c) for c in chunks)
+    with open(path, "wb") as f:
+        f.write(struct.pack("<III", MAGIC, 0, total))
+        f.write(struct.pack("<II", len(js), CHUNK_JSON))
+        f.write(js)
+        for c in chunks:
+            f.write(struct.pack("<II", len(c), CHUNK_BIN))
+            f.write(c)
+
+
+def _to_f32(x):
+    # Floats were parsed by std::from_chars<float> in the reference (src/JSON.cpp:183-186).
+    return float(np.float32(x))
+
+
+def read_scene(path) -> SceneFile:
+    data = open(path, "rb").read()
+    magic, version, length = struct.unpack_from("<III", data, 0)
+    if magic != MAGIC:
+        raise ValueError("not a .scene file (bad magic)")
+    jlen, jtype = struct.unpack_from("<II", data, 12)
+    if jtype != CHUNK_JSON:
+        raise ValueError("first chunk is not JSON")
+    root = json.loads(data[20 : 20 + jlen].decode("utf-8"))
+    off = 20 + jlen
+    buffers = []
+    while off < length:
+        clen, ctype = struct.unpack_from("<II", data, off)
+        if ctype != CHUNK_BIN:
+            raise ValueError("expected BIN chunk")
+        buffers.append(data[off + 8 : off + 8 + clen])
+        off += 8 + clen
+    s = SceneFile(materials=root.get("materials", []), textures=root.get("textures", []))
+    for e in root["entities"]:
+        mr = e.get("meshRenderer")
+        s.entities.append(
+            Entity(
+                name=e["name"],
+                transform=[_to_f32(x) for x in e["transform"]],
+                children=[int(c) for c in e.get("children", [])],
+                mesh_renderer=(int(mr["meshIndex"]), int(mr["materialIndex"])) if mr else None,
+            )
+        )
+    for m in root["meshes"]:
+        v = np.frombuffer(buffers[m["vertexArray"] - 1], dtype=VERTEX_DTYPE).copy()
+        i = np.frombuffer(buffers[m["indexArray"] - 1], dtype="<u4").copy()
+        s.meshes.append(Mesh(m["name"], int(m.get("material", 0)), v, i))
+    return s
+
+
+def _tex_index(obj, key):
+    t = obj.get(key)
+    if t is None:
+        return INVALID_TEXTURE
+    return int(t.get("index", -1)) & 0xFFFFFFFF
+
+
+def materials_array(materials_json) -> np.ndarray:
+    """parseMaterial, reference src/vulkan/Material.cpp:7-28."""
+    out = np.zeros(len(materials_json), dtype=MATERIAL_DTYPE)
+    for i, m in enumerate(materials_json):
+        pbr = m.get("pbrMetallicRoughness", {})
+        out[i]["baseColorFactor"] = [np.float32(x) for x in pbr.get("baseColorFactor", [1.0, 1.0, 1.0, 1.0])[:3]] if "pbrMetallicRoughness" in m else [1, 1, 1]
+        out[i]["metallicFactor"] = np.float32(pbr.get("metallicFactor", 1.0))
+        out[i]["roughnessFactor"] = np.float32(pbr.get("roughnessFactor", 1.0))
+        out[i]["emissiveFactor"] = [np.float32(x) for x in m.get("emissiveFactor", [0.0, 0.0, 0.0])]
+        out[i]["albedoTexture"] = _tex_index(pbr, "baseColorTexture")
+        out[i]["metallicRoughnessTexture"] = _tex_index(pbr, "metallicRoughnessTexture")
+        out[i]["normalTexture"] = _tex_index(m, "normalTexture")
+        out[i]["emissiveTexture"] = _tex_index(m, "emissiveTexture")
+    return out
+
+
+def _mat4_mul(a, b):
+    """glm mat4 * mat4 in fp32 (column-major flat lists): col_j = ((A0*b0j + A1*b1j) + A2*b2j) + A3*b3j."""
+    a = np.asarray(a, dtype=np.float32).reshape(4, 4)  # a[col][row]
+    b = np.asarray(b, dtype=np.float32).reshape(4, 4)
+    r = np.zeros((4, 4), dtype=np.float32)
+    for j in range(4):
+        acc = a[0] * b[j][0]
+        acc = acc + a[1] * b[j][1]
+        acc = acc + a[2] * b[j][2]
+        acc = acc + a[3] * b[j][3]
+        r[j] = acc
+    return r.reshape(16)
+
+
+def _mat4_mul_vec(m, v):
+    """glm mat4 * vec4: (m0*v0 + m1*v1) + (m2*v2 + m3*v3), fp32."""
+    m = np.asarray(m, dtype=np.float32).reshape(4, 4)
+    v = np.asarray(v, dtype=np.float32)
+    return (m[0] * v[0] + m[1] * v[1]) + (m[2] * v[2] + m[3] * v[3])
+
+
+def flatten(scene: SceneFile) -> dict:
+    """Scene -> the arrays vkx_scene_upload takes, plus the scene bounds used as the probe-grid extents."""
+    n = len(scene.entities)
+    parent = [-1] * n
+    for i, e in enumerate(scene.entities):
+        for c in e.children:
+            parent[c] = i
+    root = next(i for i in range(n) if parent[i] < 0)  # first entity without a parent (src/Scene.cpp:924-928)
+    # Scene::update: globalTransform = parent.globalTransform * child.transform, starting from the root's cached
+    # (identity) globalTransform (src/Scene.cpp:943-954; quirk A.10.2: the root's own local transform is not folded in).
+    glob = [np.array(IDENTITY16, dtype=np.float32) for _ in range(n)]
+    # visitNode accumulation (includes the root's local transform), used for the bounds (src/Scene.cpp:1096-1102)
+    vis = [None] * n
+    stack = [(root, np.array(IDENTITY16, dtype=np.float32), np.array(IDENTITY16, dtype=np.float32))]
+    while stack:
+        i, pg, pv = stack.pop()
+        e = scene.entities[i]
+        if i != root:
+            glob[i] = _mat4_mul(pg, e.transform)
+        vis[i] = _mat4_mul(pv, e.transform)
+        for c in e.children:
+            stack.append((c, glob[i], vis[i]))
+
+    # offset table: tight packing in mesh order (src/Renderer.cpp:97-126)
+    offsets = np.zeros(len(scene.meshes), dtype=OFFSET_DTYPE)
+    counts = np.zeros(len(scene.meshes), dtype=np.uint32)
+    vo = io = 0
+    for mi, m in enumerate(scene.meshes):
+        offsets[mi] = (m.material, vo, io)
+        counts[mi] = len(m.indices)
+        vo += len(m.vertices)
+        io += len(m.indices)
+    vertices = np.concatenate([np.asarray(m.vertices, dtype=VERTEX_DTYPE) for m in scene.meshes]) if scene.meshes else np.zeros(0, VERTEX_DTYPE)
+    indices = np.concatenate([np.asarray(m.indices, dtype=np.uint32) for m in scene.meshes]) if scene.meshes else np.zeros(0, np.uint32)
+
+    # instance list: one per MeshRendererComponent, stable-sorted by (materialIndex, meshIndex) with the entity
+    # array index as final key (src/Renderer.cpp:512-551; SURVEY appendix B decree)
+    rend = [(e.mesh_renderer[1], e.mesh_renderer[0], i) for i, e in enumerate(scene.entities) if e.mesh_renderer is not None]
+    rend.sort()
+    instances = np.zeros(len(rend), dtype=INSTANCE_DTYPE)
+    for k, (_, mesh_index, ei) in enumerate(rend):
+        g = glob[ei].reshape(4, 4)  # g[col][row]
+        rows = np.zeros(12, dtype=np.float32)
+        for r in range(3):
+            for c in range(4):
+                rows[4 * r + c] = g[c][r]
+        instances[k]["transform"] = rows
+        instances[k]["meshEntry"] = mesh_index
+        instances[k]["mask"] = INSTANCE_STATIC
+
+    # bounds: union of (T * meshBounds) with the two-corner transform (src/Bounds.hpp:38-45)
+    bmin = bmax = None
+    for i, e in enumerate(scene.entities):
+        if e.mesh_renderer is None:
+            continue
+        m = scene.meshes[e.mesh_renderer[0]]
+        lo = m.vertices["pos"].min(axis=0)
+        hi = m.vertices["pos"].max(axis=0)
+        a = _mat4_mul_vec(vis[i], [lo[0], lo[1], lo[2], 1.0])[:3]
+        b = _mat4_mul_vec(vis[i], [hi[0], hi[1], hi[2], 1.0])[:3]
+        l2, h2 = np.minimum(a, b), np.maximum(a, b)
+        bmin = l2 if bmin is None else np.minimum(bmin, l2)
+        bmax = h2 if bmax is None else np.maximum(bmax, h2)
+    return {
+        "vertices": vertices,
+        "indices": indices,
+        "offsets": offsets,
+        "mesh_index_counts": counts,
+        "materials": materials_array(scene.materials),
+        "instances": instances,
+        "bounds_min": np.asarray(bmin, dtype=np.float32),
+        "bounds_max": np.asarray(bmax, dtype=np.float32),
+    }
