@@ -175,6 +175,8 @@ int vkx_probes_download(vkx_ctx* ctx, uint32_t* irradiance, uint32_t* depth, uin
                         size_t raysCapacityBytes);
 /* Checkpoint/resume of GI state. NULL skips an array. */
 int vkx_probes_upload(vkx_ctx* ctx, const uint32_t* irradiance, const uint32_t* depth, const uint32_t* state);
+/* Enables the parity side buffers (hit records, shadow flags, unpacked blend results) and forces single-chunk updates. */
+int vkx_probes_debug(vkx_ctx* ctx, int enable);
 /* Debug/parity: pre-pack fp32 blend results of the last update: irr [count][36][3], depth [count][196][2]. */
 int vkx_probes_download_unpacked(vkx_ctx* ctx, float* irr, float* depth);
 /* Hit records (vkx_hit) of the primary rays of the last update, [count][raysPerProbe]; and the shadow-ray
@@ -209,6 +211,8 @@ int vkx_gbuffer_download(vkx_ctx* ctx, float* positionDepth, float* normalMetaln
 int vkx_shadow_frame(vkx_ctx* ctx, const vkx_camera* cur, const vkx_camera* prev, const vkx_light* light, int sync);
 /* stage: 0 = raw 1-spp (directLight.rgen output), 1 = after filter X, 2 = final (after Y + temporal). RGBA32F. */
 int vkx_shadow_download(vkx_ctx* ctx, int stage, float* rgba);
+/* Parity side buffers of the last frame: jittered light directions [h][w][4] floats, mask bytes (0 not traced, 1 lit, 2 shadowed). */
+int vkx_shadow_download_debug(vkx_ctx* ctx, float* dirs4, uint8_t* mask);
 int vkx_shadow_reset_history(vkx_ctx* ctx);
 /* ms[0] full, ms[1] trace, ms[2] filter X, ms[3] filter Y. */
 int vkx_shadow_timings(vkx_ctx* ctx, float ms[4]);

@@ -1,0 +1,71 @@
+"""GPU builder / traversal vs the oracle: BVH topology and hit records must be bit-exact (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from conftest import get_scene, make_pair
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("scene", ["tiny", "court", "cfg1", "cfg2"])
+def test_bvh_topology_bit_exact(oracle_lib, scene):
+    o, g, flat = make_pair(oracle_lib, scene)
+    oi, gi = o.bvh_info(), g.bvh_info()
+    assert (oi.numNodes, oi.numTriangles, oi.numBinaryNodes, oi.depth) == (gi.numNodes, gi.numTriangles, gi.numBinaryNodes, gi.depth)
+    assert list(oi.sceneMin) == list(gi.sceneMin) and list(oi.sceneMax) == list(gi.sceneMax)
+    on, ot = o.bvh_download()
+    gn, gt = g.bvh_download()
+    assert on.tobytes() == gn.tobytes(), "wide nodes differ"
+    assert ot.tobytes() == gt.tobytes(), "triangle order / data differs"
+
+
+def _random_rays(flat, n, seed):
+    rng = np.random.default_rng(seed)
+    lo, hi = flat["bounds_min"], flat["bounds_max"]
+    org = rng.uniform(lo - 0.5, hi + 0.5, size=(n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d = d.astype(np.float32)
+    # axis-aligned and zero-component directions exercise the zero-fix path
+    d[: n // 50] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, size=n // 50)] * rng.choice([-1.0, 1.0], size=(n // 50, 1)).astype(np.float32)
+    return org, d
+
+
+@pytest.mark.parametrize("scene", ["court", "cfg1", "cfg2"])
+def test_closest_hit_bit_exact(oracle_lib, scene):
+    o, g, flat = make_pair(oracle_lib, scene)
+    org, d = _random_rays(flat, 200_000, 7)
+    ho = o.trace(org, d, 0.01, 1000.0, 0x3)
+    hg = g.trace(org, d, 0.01, 1000.0, 0x3)
+    assert (ho["t"] > 0).mean() > 0.3
+    assert ho.tobytes() == hg.tobytes()
+
+
+@pytest.mark.parametrize("scene", ["court", "cfg2"])
+def test_any_hit_bit_exact(oracle_lib, scene):
+    o, g, flat = make_pair(oracle_lib, scene)
+    org, d = _random_rays(flat, 200_000, 11)
+    ho = o.trace(org, d, 0.1, 10000.0, 0xFF, any_hit=True)
+    hg = g.trace(org, d, 0.1, 10000.0, 0xFF, any_hit=True)
+    assert np.array_equal(ho["t"], hg["t"])
+
+
+def test_cull_mask_and_empty_scene(oracle_lib):
+    from vulkanexp_b200._lib import Context
+    from vulkanexp_b200.pods import INSTANCE_DTYPE, MATERIAL_DTYPE, OFFSET_DTYPE, VERTEX_DTYPE
+
+    flat = dict(get_scene("tiny"))
+    inst = flat["instances"].copy()
+    inst["mask"][::2] = 4  # skinned: invisible to probe rays (mask 0x3), visible to shadow rays (0xFF)
+    flat["instances"] = inst
+    o = oracle_lib.Oracle(); o.scene_upload(flat); o.bvh_build()
+    g = Context(0); g.scene_upload(flat); g.bvh_build()
+    org, d = _random_rays(flat, 20_000, 3)
+    for mask in (0x3, 0xFF, 0x4):
+        assert o.trace(org, d, 0.01, 100.0, mask).tobytes() == g.trace(org, d, 0.01, 100.0, mask).tobytes()
+    # empty scene: every ray misses
+    empty = {"vertices": np.zeros(0, VERTEX_DTYPE), "indices": np.zeros(0, np.uint32), "offsets": np.zeros(0, OFFSET_DTYPE),
+             "mesh_index_counts": np.zeros(0, np.uint32), "materials": np.zeros(0, MATERIAL_DTYPE), "instances": np.zeros(0, INSTANCE_DTYPE)}
+    g2 = Context(0); g2.scene_upload(empty); g2.bvh_build()
+    assert g2.bvh_info().numNodes == 1
+    assert (g2.trace(org[:100], d[:100], 0.01, 100.0)["t"] < 0).all()

@@ -1,0 +1,240 @@
+"""ctypes binding of libvkexp_b200.so (the C ABI declared in include/vkx.h).
+
+The library is the product: CUDA kernels for sm_100a behind a C ABI. This module only marshals numpy arrays into
+it. If the shared library is missing the import of `load()` fails loudly; there is no Python or CPU fallback.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .pods import BvhInfo, Camera, GridInfo, HIT_DTYPE, Light, NODE_DTYPE, TRI_DTYPE
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvkexp_b200.so")
+_LIB = None
+
+
+class VkxError(RuntimeError):
+    """Raised for every non-zero return code (the reference throws std::runtime_error from VK_CHECK)."""
+
+    def __init__(self, code, message):
+        super().__init__("vkx error %d: %s" % (code, message))
+        self.code = code
+
+
+def load():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C vulkanexp_b200/csrc`). There is no CPU fallback." % LIB_PATH
+            )
+        lib = C.CDLL(LIB_PATH)
+        lib.vkx_last_error.restype = C.c_char_p
+        lib.vkx_last_error.argtypes = [C.c_void_p]
+        lib.vkx_launch_count.restype = C.c_uint64
+        lib.vkx_launch_count.argtypes = [C.c_void_p]
+        lib.vkx_stream.restype = C.c_void_p
+        lib.vkx_stream.argtypes = [C.c_void_p]
+        lib.vkx_destroy.restype = None
+        lib.vkx_destroy.argtypes = [C.c_void_p]
+        _LIB = lib
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Context:
+    """One per GPU (vkx_ctx). Method names follow the C ABI; see include/vkx.h for the reference call each replaces."""
+
+    def __init__(self, device=0):
+        self.l = load()
+        h = C.c_void_p()
+        rc = self.l.vkx_create(C.c_int(device), C.byref(h))
+        if rc != 0:
+            raise VkxError(rc, self.l.vkx_last_error(None).decode())
+        self.h = h
+        self.grid = None
+        self.count = 0
+        self.sw = self.sh = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.l.vkx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise VkxError(rc, self.l.vkx_last_error(self.h).decode())
+
+    # ---- geometry
+    def scene_upload(self, flat):
+        v, i, o, c, m, inst = (np.ascontiguousarray(flat[k]) for k in ("vertices", "indices", "offsets", "mesh_index_counts", "materials", "instances"))
+        self._check(
+            self.l.vkx_scene_upload(self.h, _p(v), C.c_size_t(len(v)), _p(i), C.c_size_t(len(i)), _p(o), _p(c), C.c_size_t(len(o)), _p(m), C.c_size_t(len(m)), _p(inst), C.c_size_t(len(inst)))
+        )
+
+    def bvh_build(self):
+        self._check(self.l.vkx_bvh_build(self.h))
+
+    def bvh_info(self):
+        info = BvhInfo()
+        self._check(self.l.vkx_bvh_info_get(self.h, C.byref(info)))
+        return info
+
+    def bvh_download(self):
+        info = self.bvh_info()
+        nodes = np.zeros(info.numNodes, dtype=NODE_DTYPE)
+        tris = np.zeros(info.numTriangles, dtype=TRI_DTYPE)
+        self._check(self.l.vkx_bvh_download(self.h, _p(nodes), C.c_size_t(nodes.nbytes), _p(tris), C.c_size_t(tris.nbytes)))
+        return nodes, tris
+
+    def trace(self, origins, dirs, tmin, tmax, mask=0xFF, any_hit=False):
+        o = np.ascontiguousarray(origins, dtype=np.float32)
+        d = np.ascontiguousarray(dirs, dtype=np.float32)
+        out = np.zeros(len(o), dtype=HIT_DTYPE)
+        self._check(self.l.vkx_trace(self.h, _p(o), _p(d), C.c_size_t(len(o)), C.c_float(tmin), C.c_float(tmax), C.c_uint32(mask), C.c_int(int(any_hit)), _p(out)))
+        return out
+
+    # ---- DDGI
+    def probes_init(self, grid: GridInfo):
+        self.grid = grid
+        self._check(self.l.vkx_probes_init(self.h, C.byref(grid)))
+
+    def probes_debug(self, enable=True):
+        self._check(self.l.vkx_probes_debug(self.h, C.c_int(int(enable))))
+
+    def probes_classify(self, R):
+        R = np.ascontiguousarray(R, dtype=np.float32)
+        self._check(self.l.vkx_probes_classify(self.h, _p(R)))
+
+    def probes_update(self, grid, light, R, indices=None, sync=True):
+        R = np.ascontiguousarray(R, dtype=np.float32)
+        self.grid = grid
+        if indices is not None:
+            indices = np.ascontiguousarray(indices, dtype=np.uint32)
+            self.count = len(indices)
+        else:
+            self.count = grid.probe_count
+        self._check(self.l.vkx_probes_update(self.h, C.byref(grid), C.byref(light), _p(R), _p(indices), C.c_uint32(self.count), C.c_int(int(sync))))
+
+    def probes_update_sharded(self, grid, light, R, sync=True):
+        R = np.ascontiguousarray(R, dtype=np.float32)
+        self.grid = grid
+        self._check(self.l.vkx_probes_update_sharded(self.h, C.byref(grid), C.byref(light), _p(R), C.c_int(int(sync))))
+
+    def probes_download(self, rays=False, out=None):
+        (ih, iw), (dh, dw) = self.grid.atlas_shapes()
+        if out is None:
+            irr = np.zeros((ih, iw), dtype=np.uint32)
+            dep = np.zeros((dh, dw), dtype=np.uint32)
+            st = np.zeros(self.grid.probe_count, dtype=np.uint32)
+        else:
+            irr, dep, st = out
+        r = np.zeros((self.count, self.grid.raysPerProbe, 4), dtype=np.float32) if rays else None
+        self._check(self.l.vkx_probes_download(self.h, _p(irr), _p(dep), _p(st), _p(r), C.c_size_t(r.nbytes if rays else 0)))
+        return irr, dep, st, r
+
+    def probes_upload(self, irr=None, dep=None, state=None):
+        a = [np.ascontiguousarray(x, dtype=np.uint32) if x is not None else None for x in (irr, dep, state)]
+        self._check(self.l.vkx_probes_upload(self.h, _p(a[0]), _p(a[1]), _p(a[2])))
+
+    def probes_download_unpacked(self):
+        irr = np.zeros((self.count, 36, 3), dtype=np.float32)
+        dep = np.zeros((self.count, 196, 2), dtype=np.float32)
+        self._check(self.l.vkx_probes_download_unpacked(self.h, _p(irr), _p(dep)))
+        return irr, dep
+
+    def probes_download_hits(self):
+        hits = np.zeros((self.count, self.grid.raysPerProbe), dtype=HIT_DTYPE)
+        sh = np.zeros((self.count, self.grid.raysPerProbe), dtype=np.uint8)
+        self._check(self.l.vkx_probes_download_hits(self.h, _p(hits), _p(sh)))
+        return hits, sh
+
+    def probes_timings(self):
+        ms = (C.c_float * 5)()
+        self._check(self.l.vkx_probes_timings(self.h, ms))
+        return {"full": ms[0], "trace": ms[1], "blend": ms[2], "border": ms[3], "publish": ms[4]}
+
+    def probes_device_ptrs(self):
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._check(self.l.vkx_probes_device_ptrs(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    # ---- multi-GPU
+    @staticmethod
+    def comm_unique_id():
+        buf = (C.c_ubyte * 128)()
+        rc = load().vkx_comm_unique_id(buf)
+        if rc != 0:
+            raise VkxError(rc, "ncclGetUniqueId failed")
+        return bytes(buf)
+
+    def comm_init(self, rank, nranks, unique_id: bytes):
+        buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+        self._check(self.l.vkx_comm_init(self.h, C.c_int(rank), C.c_int(nranks), buf))
+
+    # ---- shadows
+    def shadow_set_noise(self, noise):
+        n = np.ascontiguousarray(noise, dtype=np.float32)
+        self._check(self.l.vkx_shadow_set_noise(self.h, _p(n), C.c_uint32(n.shape[2]), C.c_uint32(n.shape[1]), C.c_uint32(n.shape[0])))
+
+    def shadow_init(self, w, h):
+        self.sw, self.sh = w, h
+        self._check(self.l.vkx_shadow_init(self.h, C.c_uint32(w), C.c_uint32(h)))
+
+    def gbuffer_generate(self, cam: Camera):
+        self._check(self.l.vkx_gbuffer_generate(self.h, C.byref(cam)))
+
+    def gbuffer_upload(self, pd, nm):
+        pd = np.ascontiguousarray(pd, dtype=np.float32)
+        nm = np.ascontiguousarray(nm, dtype=np.float32)
+        self._check(self.l.vkx_gbuffer_upload(self.h, _p(pd), _p(nm)))
+
+    def gbuffer_download(self):
+        pd = np.zeros((self.sh, self.sw, 4), dtype=np.float32)
+        nm = np.zeros((self.sh, self.sw, 4), dtype=np.float32)
+        self._check(self.l.vkx_gbuffer_download(self.h, _p(pd), _p(nm)))
+        return pd, nm
+
+    def shadow_frame(self, cur, prev, light, sync=True):
+        self._check(self.l.vkx_shadow_frame(self.h, C.byref(cur), C.byref(prev), C.byref(light), C.c_int(int(sync))))
+
+    def shadow_download(self, stage=2, out=None):
+        img = out if out is not None else np.zeros((self.sh, self.sw, 4), dtype=np.float32)
+        self._check(self.l.vkx_shadow_download(self.h, C.c_int(stage), _p(img)))
+        return img
+
+    def shadow_download_debug(self):
+        dirs = np.zeros((self.sh, self.sw, 4), dtype=np.float32)
+        mask = np.zeros((self.sh, self.sw), dtype=np.uint8)
+        self._check(self.l.vkx_shadow_download_debug(self.h, _p(dirs), _p(mask)))
+        return dirs[..., :3].copy(), mask
+
+    def shadow_reset_history(self):
+        self._check(self.l.vkx_shadow_reset_history(self.h))
+
+    def shadow_timings(self):
+        ms = (C.c_float * 4)()
+        self._check(self.l.vkx_shadow_timings(self.h, ms))
+        return {"full": ms[0], "trace": ms[1], "filter_x": ms[2], "filter_y": ms[3]}
+
+    # ---- misc
+    def launch_count(self):
+        return int(self.l.vkx_launch_count(self.h))
+
+    def stream(self):
+        return self.l.vkx_stream(self.h)
+
+    def sync(self):
+        self._check(self.l.vkx_sync(self.h))

@@ -1,0 +1,443 @@
+// C ABI of libvkexp_b200.so (include/vkx.h). Host-side orchestration only: every numeric result comes from the CUDA
+// kernels in bvh_build.cu / ddgi.cu / shadow.cu. There is deliberately no CPU fallback: without a usable CUDA device
+// vkx_create fails and nothing else can be called.
+#include "common.cuh"
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <algorithm>
+#include <nccl.h>
+
+static thread_local std::string g_createError;
+
+int vkx_fail(vkx_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    if (ctx) ctx->err = buf; else g_createError = buf;
+    return code;
+}
+
+template <typename T>
+static int upload(vkx_ctx* ctx, T** dst, const T* src, size_t n) {
+    if (*dst) { cudaFree(*dst); *dst = nullptr; }
+    CUDA_TRY(ctx, cudaMalloc(dst, std::max<size_t>(n, 1) * sizeof(T)));
+    if (n) CUDA_TRY(ctx, cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return VKX_OK;
+}
+#define TRY(expr) do { int _rc = (expr); if (_rc != VKX_OK) return _rc; } while (0)
+#define BIND(ctx) do { if (!(ctx)) return VKX_E_INVALID; cudaError_t _e = cudaSetDevice((ctx)->device); if (_e != cudaSuccess) return vkx_fail((ctx), VKX_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(_e)); } while (0)
+
+extern "C" {
+
+int vkx_abi_version(void) { return VKX_ABI_VERSION; }
+
+int vkx_create(int device, vkx_ctx** out) {
+    if (!out) return VKX_E_INVALID;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return vkx_fail(nullptr, VKX_E_CUDA, "no CUDA device available (%s); libvkexp_b200 has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= n) return vkx_fail(nullptr, VKX_E_INVALID, "device %d out of range (%d devices)", device, n);
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return vkx_fail(nullptr, VKX_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    vkx_ctx* ctx = new vkx_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { delete ctx; return vkx_fail(nullptr, VKX_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
+    ctx->smCount = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return vkx_fail(nullptr, VKX_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    for (auto& ev : ctx->sev) cudaEventCreate(&ev);
+    *out = ctx;
+    return VKX_OK;
+}
+
+static void freeProbes(vkx_ctx* ctx) {
+    void* ptrs[] = {ctx->dIrrWork, ctx->dIrrSampled, ctx->dDepWork, ctx->dDepSampled, ctx->dStateWork, ctx->dStateSampled, ctx->dIndicesList, ctx->dDirs, ctx->dRays,
+                    ctx->dHits, ctx->dShadowQueue, ctx->dQueueCount, ctx->dShadowFlags, ctx->dIrrUnpacked, ctx->dDepUnpacked, ctx->dIrrNext, ctx->dDepNext, ctx->dStateNext};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    ctx->dIrrWork = ctx->dIrrSampled = ctx->dDepWork = ctx->dDepSampled = ctx->dStateWork = ctx->dStateSampled = ctx->dIndicesList = nullptr;
+    ctx->dIrrNext = ctx->dDepNext = ctx->dStateNext = nullptr;
+    ctx->dDirs = nullptr; ctx->dRays = nullptr; ctx->dHits = nullptr; ctx->dShadowQueue = nullptr; ctx->dQueueCount = nullptr; ctx->dShadowFlags = nullptr;
+    ctx->dIrrUnpacked = ctx->dDepUnpacked = nullptr;
+    ctx->probesReady = false;
+}
+static void freeShadow(vkx_ctx* ctx) {
+    void* ptrs[] = {ctx->dPosDepth, ctx->dNormalMetal, ctx->dShRaw, ctx->dShX, ctx->dShFinal[0], ctx->dShFinal[1], ctx->dShDirs, ctx->dShMask};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    ctx->dPosDepth = ctx->dNormalMetal = ctx->dShRaw = ctx->dShX = ctx->dShFinal[0] = ctx->dShFinal[1] = ctx->dShDirs = nullptr; ctx->dShMask = nullptr;
+    ctx->shW = ctx->shH = 0;
+}
+
+void vkx_destroy(vkx_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm) ncclCommDestroy(reinterpret_cast<ncclComm_t>(ctx->comm));
+    freeProbes(ctx); freeShadow(ctx);
+    void* ptrs[] = {ctx->dVertices, ctx->dIndices, ctx->dOffsets, ctx->dMeshCounts, ctx->dMaterials, ctx->dInstances, ctx->dWorldToObject, ctx->dInstTriBase, ctx->dNodes, ctx->dTris, ctx->dNoise};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->sev) if (ev) cudaEventDestroy(ev);
+    if (ctx->commStream) cudaStreamDestroy(ctx->commStream);
+    if (ctx->commEvent) cudaEventDestroy(ctx->commEvent);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* vkx_last_error(vkx_ctx* ctx) { return ctx ? ctx->err.c_str() : g_createError.c_str(); }
+uint64_t vkx_launch_count(vkx_ctx* ctx) { return ctx ? ctx->launches : 0; }
+void* vkx_stream(vkx_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int vkx_sync(vkx_ctx* ctx) { BIND(ctx); CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); return VKX_OK; }
+
+// ---------------------------------------------------------------------------------------------------- geometry
+int vkx_scene_upload(vkx_ctx* ctx, const vkx_vertex* vertices, size_t numVertices, const uint32_t* indices, size_t numIndices,
+                     const vkx_offset_entry* offsets, const uint32_t* meshIndexCounts, size_t numMeshes, const vkx_material* materials,
+                     size_t numMaterials, const vkx_instance* instances, size_t numInstances) {
+    BIND(ctx);
+    if ((numVertices && !vertices) || (numIndices && !indices) || (numMeshes && (!offsets || !meshIndexCounts)) || (numMaterials && !materials) || (numInstances && !instances))
+        return vkx_fail(ctx, VKX_E_INVALID, "vkx_scene_upload: null array");
+    if (numInstances >= (1u << 24)) return vkx_fail(ctx, VKX_E_UNSUPPORTED, "more than 2^24 instances");
+    for (size_t m = 0; m < numMaterials; ++m)
+        if (materials[m].albedoTexture != VKX_INVALID_TEXTURE || materials[m].normalTexture != VKX_INVALID_TEXTURE ||
+            materials[m].metallicRoughnessTexture != VKX_INVALID_TEXTURE || materials[m].emissiveTexture != VKX_INVALID_TEXTURE)
+            return vkx_fail(ctx, VKX_E_UNSUPPORTED, "material %zu is textured; texture sampling is implementation-defined in the reference and not supported (SURVEY A.8)", m);
+    for (size_t m = 0; m < numMeshes; ++m) {
+        if (meshIndexCounts[m] % 3 != 0) return vkx_fail(ctx, VKX_E_INVALID, "mesh %zu: index count %u is not a multiple of 3", m, meshIndexCounts[m]);
+        if (size_t(offsets[m].indexOffset) + meshIndexCounts[m] > numIndices) return vkx_fail(ctx, VKX_E_INVALID, "mesh %zu: index range out of bounds", m);
+        if (offsets[m].materialIndex >= numMaterials) return vkx_fail(ctx, VKX_E_INVALID, "mesh %zu: material %u out of range", m, offsets[m].materialIndex);
+        if (offsets[m].vertexOffset > numVertices) return vkx_fail(ctx, VKX_E_INVALID, "mesh %zu: vertex offset out of range", m);
+    }
+    // index validation (a bad index would read out of bounds on the device)
+    {
+        for (size_t m = 0; m < numMeshes; ++m) {
+            uint32_t limit = uint32_t(numVertices) - offsets[m].vertexOffset;
+            for (uint32_t i = 0; i < meshIndexCounts[m]; ++i)
+                if (indices[offsets[m].indexOffset + i] >= limit) return vkx_fail(ctx, VKX_E_INVALID, "mesh %zu: vertex index out of range", m);
+        }
+    }
+    for (size_t v = 0; v < numVertices; ++v)
+        for (int a = 0; a < 3; ++a) if (!std::isfinite(vertices[v].pos[a])) return vkx_fail(ctx, VKX_E_INVALID, "vertex %zu has a non-finite position", v);
+    std::vector<float> w2o(numInstances * 9);
+    ctx->hInstTriBase.assign(numInstances + 1, 0);
+    size_t total = 0;
+    for (size_t k = 0; k < numInstances; ++k) {
+        if (instances[k].meshEntry >= numMeshes) return vkx_fail(ctx, VKX_E_INVALID, "instance %zu: mesh entry out of range", k);
+        ctx->hInstTriBase[k] = uint32_t(total);
+        total += meshIndexCounts[instances[k].meshEntry] / 3;
+        if (total >= (1ull << 29)) return vkx_fail(ctx, VKX_E_UNSUPPORTED, "more than 2^29 instanced triangles");
+        // inverse of the 3x3 part (gl_WorldToObjectEXT), fp32 adjugate / determinant
+        const float* M = instances[k].transform;
+        float a = M[0], b = M[1], c = M[2], d = M[4], e = M[5], f = M[6], g = M[8], h = M[9], i = M[10];
+        float A = e * i - f * h, B = -(d * i - f * g), C = d * h - e * g;
+        float det = a * A + b * B + c * C;
+        float id = 1.0f / det;
+        float* W = &w2o[k * 9];
+        W[0] = A * id; W[1] = -(b * i - c * h) * id; W[2] = (b * f - c * e) * id;
+        W[3] = B * id; W[4] = (a * i - c * g) * id;  W[5] = -(a * f - c * d) * id;
+        W[6] = C * id; W[7] = -(a * h - b * g) * id; W[8] = (a * e - b * d) * id;
+    }
+    ctx->hInstTriBase[numInstances] = uint32_t(total);
+    TRY(upload(ctx, &ctx->dVertices, vertices, numVertices));
+    TRY(upload(ctx, &ctx->dIndices, indices, numIndices));
+    TRY(upload(ctx, &ctx->dOffsets, offsets, numMeshes));
+    TRY(upload(ctx, &ctx->dMeshCounts, meshIndexCounts, numMeshes));
+    TRY(upload(ctx, &ctx->dMaterials, materials, numMaterials));
+    TRY(upload(ctx, &ctx->dInstances, instances, numInstances));
+    TRY(upload(ctx, &ctx->dWorldToObject, w2o.data(), w2o.size()));
+    TRY(upload(ctx, &ctx->dInstTriBase, ctx->hInstTriBase.data(), ctx->hInstTriBase.size()));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->numVertices = numVertices; ctx->numIndices = numIndices; ctx->numMeshes = numMeshes; ctx->numMaterials = numMaterials;
+    ctx->numInstances = numInstances; ctx->numFlatTris = total;
+    ctx->bvhBuilt = false;
+    return VKX_OK;
+}
+
+int vkx_bvh_build(vkx_ctx* ctx) { BIND(ctx); return bvhBuildDevice(ctx); }
+
+int vkx_bvh_info_get(vkx_ctx* ctx, vkx_bvh_info* out) {
+    if (!ctx || !out) return VKX_E_INVALID;
+    if (!ctx->bvhBuilt) return vkx_fail(ctx, VKX_E_INVALID, "BVH not built");
+    *out = ctx->bvh;
+    return VKX_OK;
+}
+
+int vkx_bvh_download(vkx_ctx* ctx, void* nodes, size_t nodesBytes, void* triangles, size_t trianglesBytes) {
+    BIND(ctx);
+    if (!ctx->bvhBuilt) return vkx_fail(ctx, VKX_E_INVALID, "BVH not built");
+    if (nodes) { size_t need = size_t(ctx->bvh.numNodes) * 80; if (nodesBytes < need) return vkx_fail(ctx, VKX_E_INVALID, "node buffer too small"); CUDA_TRY(ctx, cudaMemcpy(nodes, ctx->dNodes, need, cudaMemcpyDeviceToHost)); }
+    if (triangles) { size_t need = size_t(ctx->bvh.numTriangles) * 48; if (trianglesBytes < need) return vkx_fail(ctx, VKX_E_INVALID, "triangle buffer too small"); if (need) CUDA_TRY(ctx, cudaMemcpy(triangles, ctx->dTris, need, cudaMemcpyDeviceToHost)); }
+    return VKX_OK;
+}
+
+int vkx_trace(vkx_ctx* ctx, const float* origins, const float* directions, size_t n, float tmin, float tmax, uint32_t cullMask, int anyHit, vkx_hit* out) {
+    BIND(ctx);
+    if (!ctx->bvhBuilt) return vkx_fail(ctx, VKX_E_INVALID, "BVH not built");
+    if (n && (!origins || !directions || !out)) return vkx_fail(ctx, VKX_E_INVALID, "vkx_trace: null array");
+    return traceHostRays(ctx, origins, directions, n, tmin, tmax, cullMask, anyHit, out);
+}
+
+// ---------------------------------------------------------------------------------------------------- DDGI
+static int checkGrid(vkx_ctx* ctx, const vkx_grid_info* g) {
+    if (!g) return vkx_fail(ctx, VKX_E_INVALID, "null grid");
+    if (g->colorRes != 8 || g->depthRes != 16) return vkx_fail(ctx, VKX_E_INVALID, "colorRes/depthRes must be 8/16 (baked into the reference's shaders)");
+    if (g->resolution[0] < 2 || g->resolution[1] < 2 || g->resolution[2] < 2) return vkx_fail(ctx, VKX_E_INVALID, "grid resolution must be >= 2 on every axis");
+    if (g->raysPerProbe < 1 || g->raysPerProbe > VKX_MAX_RAYS_PER_PROBE) return vkx_fail(ctx, VKX_E_INVALID, "raysPerProbe must be in [1, %d]", VKX_MAX_RAYS_PER_PROBE);
+    return VKX_OK;
+}
+
+static int allocProbeScratch(vkx_ctx* ctx) {
+    // ray-level scratch for one chunk of probes
+    void* old[] = {ctx->dRays, ctx->dHits, ctx->dShadowQueue, ctx->dShadowFlags, ctx->dIrrUnpacked, ctx->dDepUnpacked};
+    for (void* p : old) if (p) cudaFree(p);
+    ctx->dRays = nullptr; ctx->dHits = nullptr; ctx->dShadowQueue = nullptr; ctx->dShadowFlags = nullptr; ctx->dIrrUnpacked = ctx->dDepUnpacked = nullptr;
+    const size_t maxRays = size_t(ctx->chunkProbes) * VKX_MAX_RAYS_PER_PROBE;
+    CUDA_TRY(ctx, cudaMalloc(&ctx->dRays, maxRays * sizeof(float4)));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->dHits, maxRays * sizeof(vkx_hit)));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->dShadowQueue, maxRays * 2 * sizeof(float4)));
+    if (ctx->debugBuffers) {
+        CUDA_TRY(ctx, cudaMalloc(&ctx->dShadowFlags, maxRays));
+        CUDA_TRY(ctx, cudaMalloc(&ctx->dIrrUnpacked, size_t(ctx->probeCount) * 36 * 3 * 4));
+        CUDA_TRY(ctx, cudaMalloc(&ctx->dDepUnpacked, size_t(ctx->probeCount) * 196 * 2 * 4));
+    }
+    return VKX_OK;
+}
+
+int vkx_probes_init(vkx_ctx* ctx, const vkx_grid_info* grid) {
+    BIND(ctx);
+    TRY(checkGrid(ctx, grid));
+    freeProbes(ctx);
+    ctx->grid = *grid;
+    ctx->probeCount = uint32_t(grid->resolution[0]) * uint32_t(grid->resolution[1]) * uint32_t(grid->resolution[2]);
+    ctx->irrW = 8u * uint32_t(grid->resolution[0] * grid->resolution[1]); ctx->irrH = 8u * uint32_t(grid->resolution[2]);
+    ctx->depW = 16u * uint32_t(grid->resolution[0] * grid->resolution[1]); ctx->depH = 16u * uint32_t(grid->resolution[2]);
+    const size_t irrBytes = size_t(ctx->irrW) * ctx->irrH * 4, depBytes = size_t(ctx->depW) * ctx->depH * 4, stBytes = size_t(ctx->probeCount) * 4;
+    uint32_t** bufs[] = {&ctx->dIrrWork, &ctx->dIrrSampled, &ctx->dDepWork, &ctx->dDepSampled, &ctx->dStateWork, &ctx->dStateSampled};
+    const size_t sizes[] = {irrBytes, irrBytes, depBytes, depBytes, stBytes, stBytes};
+    for (int i = 0; i < 6; ++i) { CUDA_TRY(ctx, cudaMalloc(bufs[i], sizes[i])); CUDA_TRY(ctx, cudaMemsetAsync(*bufs[i], 0, sizes[i], ctx->stream)); }
+    CUDA_TRY(ctx, cudaMalloc(&ctx->dIndicesList, stBytes));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->dDirs, 512 * sizeof(float4)));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->dQueueCount, 4));
+    // One chunk holds at most 32768 probes (8.4 M rays: 128 MiB of ray records) so the ray-level scratch stays L2-sized
+    // relative to the atlases; debug buffers force a single chunk.
+    ctx->chunkProbes = ctx->debugBuffers ? ctx->probeCount : std::min<uint32_t>(ctx->probeCount, 32768u);
+    TRY(allocProbeScratch(ctx));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->probesReady = true;
+    ctx->lastCount = 0;
+    return VKX_OK;
+}
+
+int vkx_probes_debug(vkx_ctx* ctx, int enable) {
+    BIND(ctx);
+    ctx->debugBuffers = enable != 0;
+    if (ctx->probesReady) {
+        ctx->chunkProbes = ctx->debugBuffers ? ctx->probeCount : std::min<uint32_t>(ctx->probeCount, 32768u);
+        TRY(allocProbeScratch(ctx));
+    }
+    return VKX_OK;
+}
+
+// mat3(orientation) * sphericalFibonacci(i, n), i in [0, count): traceProbes.rgen:36, irradiance.glsl:52-64. Computed on the
+// host in fp32 (glibc sinf/cosf) once per update: 256 directions shared by every probe, as the reference's rayDirection image.
+static void rayDirections(const float R[16], uint32_t count, float n, float* out) {
+    const float pi = 3.1415926538f;
+    const float PHI = std::sqrt(5.0f) * 0.5f + 0.5f;
+    for (uint32_t k = 0; k < count; ++k) {
+        const float i = float(k);
+        const float ab = i * (PHI - 1.0f);
+        const float phi = 2.0f * pi * (ab - std::floor(ab));
+        const float cosTheta = 1.0f - (2.0f * i + 1.0f) * (1.0f / n);
+        const float sinTheta = std::sqrt(std::min(std::max(1.0f - cosTheta * cosTheta, 0.0f), 1.0f));
+        const float x = std::cos(phi) * sinTheta, y = std::sin(phi) * sinTheta, z = cosTheta;
+        // mat3(R) * v, column-major R
+        out[3 * k + 0] = R[0] * x + R[4] * y + R[8] * z;
+        out[3 * k + 1] = R[1] * x + R[5] * y + R[9] * z;
+        out[3 * k + 2] = R[2] * x + R[6] * y + R[10] * z;
+    }
+}
+
+int vkx_probes_classify(vkx_ctx* ctx, const float orientation[16]) {
+    BIND(ctx);
+    if (!ctx->probesReady || !ctx->bvhBuilt) return vkx_fail(ctx, VKX_E_INVALID, "vkx_probes_classify: probes or BVH not ready");
+    if (!orientation) return vkx_fail(ctx, VKX_E_INVALID, "null orientation");
+    float dirs[512 * 3];
+    rayDirections(orientation, 512, float(ctx->grid.raysPerProbe), dirs);
+    return ddgiClassify(ctx, dirs);
+}
+
+static int uploadFrameInputs(vkx_ctx* ctx, const vkx_grid_info* grid, const float orientation[16]) {
+    TRY(checkGrid(ctx, grid));
+    if (grid->resolution[0] != ctx->grid.resolution[0] || grid->resolution[1] != ctx->grid.resolution[1] || grid->resolution[2] != ctx->grid.resolution[2])
+        return vkx_fail(ctx, VKX_E_INVALID, "grid resolution changed; call vkx_probes_init again (reference quirk A.10.3)");
+    ctx->grid = *grid; // updateUniforms
+    const uint32_t N = grid->raysPerProbe;
+    float dirs[VKX_MAX_RAYS_PER_PROBE * 3];
+    rayDirections(orientation, N, float(N), dirs);
+    float4 d4[VKX_MAX_RAYS_PER_PROBE];
+    for (uint32_t i = 0; i < N; ++i) d4[i] = make_float4(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2], 1.0f);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dDirs, d4, N * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    return VKX_OK;
+}
+
+__global__ void k_iota_list(uint32_t* p, uint32_t first, uint32_t n) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = first + i; }
+
+int vkx_probes_update(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx_light* light, const float orientation[16], const uint32_t* probeIndices, uint32_t count, int sync) {
+    BIND(ctx);
+    if (!ctx->probesReady || !ctx->bvhBuilt) return vkx_fail(ctx, VKX_E_INVALID, "vkx_probes_update: probes or BVH not ready");
+    if (!light || !orientation) return vkx_fail(ctx, VKX_E_INVALID, "null light/orientation");
+    TRY(uploadFrameInputs(ctx, grid, orientation));
+    if (probeIndices) {
+        if (count > ctx->probeCount) return vkx_fail(ctx, VKX_E_INVALID, "more indices than probes");
+        for (uint32_t i = 0; i < count; ++i) if (probeIndices[i] >= ctx->probeCount) return vkx_fail(ctx, VKX_E_INVALID, "probe index %u out of range", probeIndices[i]);
+        if (count) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dIndicesList, probeIndices, size_t(count) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        count = ctx->probeCount;
+        k_iota_list<<<divUp(count, 256), 256, 0, ctx->stream>>>(ctx->dIndicesList, 0, count); LAUNCH_CHECK(ctx);
+    }
+    TRY(ddgiUpdate(ctx, *light, nullptr, count, 0, false));
+    TRY(ddgiPublish(ctx, count));
+    ctx->shardedLast = false;
+    if (sync) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return VKX_OK;
+}
+
+int vkx_probes_download(vkx_ctx* ctx, uint32_t* irradiance, uint32_t* depth, uint32_t* state, float* rays, size_t raysCapacityBytes) {
+    BIND(ctx);
+    if (!ctx->probesReady) return vkx_fail(ctx, VKX_E_INVALID, "probes not initialised");
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (irradiance) CUDA_TRY(ctx, cudaMemcpy(irradiance, ctx->dIrrSampled, size_t(ctx->irrW) * ctx->irrH * 4, cudaMemcpyDeviceToHost));
+    if (depth) CUDA_TRY(ctx, cudaMemcpy(depth, ctx->dDepSampled, size_t(ctx->depW) * ctx->depH * 4, cudaMemcpyDeviceToHost));
+    if (state) CUDA_TRY(ctx, cudaMemcpy(state, ctx->dStateSampled, size_t(ctx->probeCount) * 4, cudaMemcpyDeviceToHost));
+    if (rays) {
+        if (ctx->lastCount > ctx->chunkProbes) return vkx_fail(ctx, VKX_E_INVALID, "ray buffer only holds one chunk; enable vkx_probes_debug before the update");
+        size_t need = size_t(ctx->lastRays) * 16;
+        if (raysCapacityBytes < need) return vkx_fail(ctx, VKX_E_INVALID, "ray buffer too small");
+        if (need) CUDA_TRY(ctx, cudaMemcpy(rays, ctx->dRays, need, cudaMemcpyDeviceToHost));
+    }
+    return VKX_OK;
+}
+
+int vkx_probes_upload(vkx_ctx* ctx, const uint32_t* irradiance, const uint32_t* depth, const uint32_t* state) {
+    BIND(ctx);
+    if (!ctx->probesReady) return vkx_fail(ctx, VKX_E_INVALID, "probes not initialised");
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    const size_t irrBytes = size_t(ctx->irrW) * ctx->irrH * 4, depBytes = size_t(ctx->depW) * ctx->depH * 4, stBytes = size_t(ctx->probeCount) * 4;
+    if (irradiance) { CUDA_TRY(ctx, cudaMemcpy(ctx->dIrrSampled, irradiance, irrBytes, cudaMemcpyHostToDevice)); CUDA_TRY(ctx, cudaMemcpy(ctx->dIrrWork, irradiance, irrBytes, cudaMemcpyHostToDevice)); }
+    if (depth) { CUDA_TRY(ctx, cudaMemcpy(ctx->dDepSampled, depth, depBytes, cudaMemcpyHostToDevice)); CUDA_TRY(ctx, cudaMemcpy(ctx->dDepWork, depth, depBytes, cudaMemcpyHostToDevice)); }
+    if (state) { CUDA_TRY(ctx, cudaMemcpy(ctx->dStateSampled, state, stBytes, cudaMemcpyHostToDevice)); CUDA_TRY(ctx, cudaMemcpy(ctx->dStateWork, state, stBytes, cudaMemcpyHostToDevice)); }
+    return VKX_OK;
+}
+
+int vkx_probes_download_unpacked(vkx_ctx* ctx, float* irr, float* depth) {
+    BIND(ctx);
+    if (!ctx->probesReady || !ctx->debugBuffers || !ctx->dIrrUnpacked) return vkx_fail(ctx, VKX_E_INVALID, "enable vkx_probes_debug before the update");
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (irr) CUDA_TRY(ctx, cudaMemcpy(irr, ctx->dIrrUnpacked, size_t(ctx->lastCount) * 36 * 3 * 4, cudaMemcpyDeviceToHost));
+    if (depth) CUDA_TRY(ctx, cudaMemcpy(depth, ctx->dDepUnpacked, size_t(ctx->lastCount) * 196 * 2 * 4, cudaMemcpyDeviceToHost));
+    return VKX_OK;
+}
+
+int vkx_probes_download_hits(vkx_ctx* ctx, vkx_hit* hits, uint8_t* shadow) {
+    BIND(ctx);
+    if (!ctx->probesReady || !ctx->debugBuffers || !ctx->dShadowFlags) return vkx_fail(ctx, VKX_E_INVALID, "enable vkx_probes_debug before the update");
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (hits) CUDA_TRY(ctx, cudaMemcpy(hits, ctx->dHits, size_t(ctx->lastRays) * sizeof(vkx_hit), cudaMemcpyDeviceToHost));
+    if (shadow) CUDA_TRY(ctx, cudaMemcpy(shadow, ctx->dShadowFlags, size_t(ctx->lastRays), cudaMemcpyDeviceToHost));
+    return VKX_OK;
+}
+
+int vkx_probes_timings(vkx_ctx* ctx, float ms[5]) {
+    BIND(ctx);
+    if (!ms) return VKX_E_INVALID;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 5; ++i) ms[i] = 0.f;
+    if (!ctx->lastCount) return VKX_OK;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms[0], ctx->shardedLast ? ctx->ev[4] : ctx->ev[0], ctx->ev[3]));
+    if (ctx->shardedLast) return VKX_OK; // per-stage split is per chunk in the sharded path; only the total is reported
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms[1], ctx->ev[0], ctx->ev[1]));
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms[2], ctx->ev[1], ctx->ev[2]));
+    ms[3] = 0.f; // borders are written by the blend kernel
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms[4], ctx->ev[2], ctx->ev[3]));
+    return VKX_OK;
+}
+
+int vkx_probes_device_ptrs(vkx_ctx* ctx, void** irradiance, void** depth, void** state) {
+    if (!ctx || !ctx->probesReady) return VKX_E_INVALID;
+    if (irradiance) *irradiance = ctx->dIrrSampled;
+    if (depth) *depth = ctx->dDepSampled;
+    if (state) *state = ctx->dStateSampled;
+    return VKX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------- multi-GPU
+int vkx_comm_unique_id(void* id128) {
+    if (!id128) return VKX_E_INVALID;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId");
+    ncclUniqueId id;
+    if (ncclGetUniqueId(&id) != ncclSuccess) return VKX_E_NCCL;
+    memcpy(id128, &id, 128);
+    return VKX_OK;
+}
+
+int vkx_comm_init(vkx_ctx* ctx, int rank, int nranks, const void* id128) {
+    BIND(ctx);
+    if (nranks < 1 || rank < 0 || rank >= nranks || !id128) return vkx_fail(ctx, VKX_E_INVALID, "bad rank/nranks");
+    ncclUniqueId id; memcpy(&id, id128, 128);
+    ncclComm_t comm;
+    ncclResult_t r = ncclCommInitRank(&comm, nranks, id, rank);
+    if (r != ncclSuccess) return vkx_fail(ctx, VKX_E_NCCL, "ncclCommInitRank: %s", ncclGetErrorString(r));
+    ctx->comm = reinterpret_cast<ncclComm*>(comm); ctx->rank = rank; ctx->nranks = nranks;
+    if (!ctx->commStream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->commStream, cudaStreamNonBlocking));
+    if (!ctx->commEvent) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->commEvent, cudaEventDisableTiming));
+    return VKX_OK;
+}
+
+// Full-volume update, sharded: the z range is cut into K chunks of s*nranks slices; inside chunk k rank r traces and blends
+// the s slices [k*s*n + r*s, k*s*n + (r+1)*s). A chunk's atlas rows are contiguous in memory, so one ncclAllGather per
+// atlas per chunk (on a second stream, overlapped with the next chunk's tracing) assembles the *next* sampled atlases on
+// every rank; they become current by pointer swap at the end. No reduction crosses ranks, so results equal the 1-GPU run.
+int vkx_probes_update_sharded(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx_light* light, const float orientation[16], int sync) {
+    BIND(ctx);
+    if (!ctx->probesReady || !ctx->bvhBuilt) return vkx_fail(ctx, VKX_E_INVALID, "vkx_probes_update_sharded: probes or BVH not ready");
+    if (!light || !orientation) return vkx_fail(ctx, VKX_E_INVALID, "null light/orientation");
+    if (ctx->nranks == 1 || !ctx->comm) return vkx_probes_update(ctx, grid, light, orientation, nullptr, 0, sync);
+    TRY(uploadFrameInputs(ctx, grid, orientation));
+    const uint32_t n = uint32_t(ctx->nranks), rz = uint32_t(ctx->grid.resolution[2]), plane = uint32_t(ctx->grid.resolution[0] * ctx->grid.resolution[1]);
+    if (rz % n != 0) return vkx_fail(ctx, VKX_E_INVALID, "grid z resolution %u is not divisible by %u ranks", rz, n);
+    const size_t irrBytes = size_t(ctx->irrW) * ctx->irrH * 4, depBytes = size_t(ctx->depW) * ctx->depH * 4, stBytes = size_t(ctx->probeCount) * 4;
+    if (!ctx->dIrrNext) { CUDA_TRY(ctx, cudaMalloc(&ctx->dIrrNext, irrBytes)); CUDA_TRY(ctx, cudaMalloc(&ctx->dDepNext, depBytes)); CUDA_TRY(ctx, cudaMalloc(&ctx->dStateNext, stBytes)); }
+    uint32_t s = std::max(1u, rz / (n * 4u));
+    while ((rz / n) % s != 0) --s;
+    const uint32_t K = rz / (n * s);
+    ncclComm_t comm = reinterpret_cast<ncclComm_t>(ctx->comm);
+    cudaStream_t st = ctx->stream, cs = ctx->commStream;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], st));
+    uint32_t total = 0;
+    for (uint32_t k = 0; k < K; ++k) {
+        const uint32_t z0 = k * s * n + uint32_t(ctx->rank) * s;
+        const uint32_t first = z0 * plane, count = s * plane;
+        k_iota_list<<<divUp(count, 256), 256, 0, st>>>(ctx->dIndicesList + total, first, count); LAUNCH_CHECK(ctx);
+        TRY(ddgiUpdate(ctx, *light, nullptr, count, total, false));
+        total += count;
+        CUDA_TRY(ctx, cudaEventRecord(ctx->commEvent, st));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ctx->commEvent, 0));
+        const size_t irrChunk = size_t(8 * s) * ctx->irrW, depChunk = size_t(16 * s) * ctx->depW, stChunk = size_t(s) * plane; // elements per rank
+        const size_t irrOff = size_t(8 * k * s * n) * ctx->irrW, depOff = size_t(16 * k * s * n) * ctx->depW, stOff = size_t(k * s * n) * plane;
+        ncclResult_t r = ncclGroupStart();
+        if (r == ncclSuccess) r = ncclAllGather(ctx->dIrrWork + irrOff + irrChunk * ctx->rank, ctx->dIrrNext + irrOff, irrChunk, ncclUint32, comm, cs);
+        if (r == ncclSuccess) r = ncclAllGather(ctx->dDepWork + depOff + depChunk * ctx->rank, ctx->dDepNext + depOff, depChunk, ncclUint32, comm, cs);
+        if (r == ncclSuccess) r = ncclAllGather(ctx->dStateWork + stOff + stChunk * ctx->rank, ctx->dStateNext + stOff, stChunk, ncclUint32, comm, cs);
+        if (r == ncclSuccess) r = ncclGroupEnd();
+        if (r != ncclSuccess) return vkx_fail(ctx, VKX_E_NCCL, "ncclAllGather: %s", ncclGetErrorString(r));
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->commEvent, cs));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->commEvent, 0));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], st));
+    // publish = swap; the work buffers keep this rank's slices current (they are the only ones it reads as `previous`)
+    std::swap(ctx->dIrrSampled, ctx->dIrrNext); std::swap(ctx->dDepSampled, ctx->dDepNext); std::swap(ctx->dStateSampled, ctx->dStateNext);
+    ctx->lastCount = total; ctx->lastRays = total * ctx->grid.raysPerProbe; ctx->shardedLast = true;
+    if (sync) CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return VKX_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,115 @@
+// C ABI, sun-shadow half (include/vkx.h): host-side orchestration of shadow.cu.
+#include "common.cuh"
+#include <cstring>
+
+#define BIND(ctx) do { if (!(ctx)) return VKX_E_INVALID; cudaError_t _e = cudaSetDevice((ctx)->device); if (_e != cudaSuccess) return vkx_fail((ctx), VKX_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(_e)); } while (0)
+
+extern "C" {
+
+int vkx_shadow_set_noise(vkx_ctx* ctx, const float* rgba, uint32_t w, uint32_t h, uint32_t slices) {
+    BIND(ctx);
+    if (!rgba || !w || !h || !slices) return vkx_fail(ctx, VKX_E_INVALID, "vkx_shadow_set_noise: bad arguments");
+    if (ctx->dNoise) { cudaFree(ctx->dNoise); ctx->dNoise = nullptr; }
+    const size_t bytes = size_t(w) * h * slices * 16;
+    CUDA_TRY(ctx, cudaMalloc(&ctx->dNoise, bytes));
+    CUDA_TRY(ctx, cudaMemcpy(ctx->dNoise, rgba, bytes, cudaMemcpyHostToDevice));
+    ctx->noiseW = w; ctx->noiseH = h; ctx->noiseSlices = slices;
+    return VKX_OK;
+}
+
+int vkx_shadow_init(vkx_ctx* ctx, uint32_t width, uint32_t height) {
+    BIND(ctx);
+    if (!width || !height) return vkx_fail(ctx, VKX_E_INVALID, "vkx_shadow_init: empty image");
+    void* old[] = {ctx->dPosDepth, ctx->dNormalMetal, ctx->dShRaw, ctx->dShX, ctx->dShFinal[0], ctx->dShFinal[1], ctx->dShDirs, ctx->dShMask};
+    for (void* p : old) if (p) cudaFree(p);
+    ctx->dPosDepth = ctx->dNormalMetal = ctx->dShRaw = ctx->dShX = ctx->dShFinal[0] = ctx->dShFinal[1] = ctx->dShDirs = nullptr; ctx->dShMask = nullptr;
+    const size_t px = size_t(width) * height;
+    float4** imgs[] = {&ctx->dPosDepth, &ctx->dNormalMetal, &ctx->dShRaw, &ctx->dShX, &ctx->dShFinal[0], &ctx->dShFinal[1], &ctx->dShDirs};
+    for (float4** p : imgs) { CUDA_TRY(ctx, cudaMalloc(p, px * 16)); CUDA_TRY(ctx, cudaMemsetAsync(*p, 0, px * 16, ctx->stream)); }
+    CUDA_TRY(ctx, cudaMalloc(&ctx->dShMask, px)); CUDA_TRY(ctx, cudaMemsetAsync(ctx->dShMask, 0, px, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->shW = width; ctx->shH = height; ctx->shCur = 0;
+    return VKX_OK;
+}
+
+int vkx_gbuffer_generate(vkx_ctx* ctx, const vkx_camera* cam) {
+    BIND(ctx);
+    if (!cam || !ctx->shW || !ctx->bvhBuilt) return vkx_fail(ctx, VKX_E_INVALID, "vkx_gbuffer_generate: shadow images or BVH not ready");
+    int rc = shadowGBuffer(ctx, *cam);
+    if (rc != VKX_OK) return rc;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return VKX_OK;
+}
+
+int vkx_gbuffer_upload(vkx_ctx* ctx, const float* positionDepth, const float* normalMetalness) {
+    BIND(ctx);
+    if (!ctx->shW || !positionDepth || !normalMetalness) return vkx_fail(ctx, VKX_E_INVALID, "vkx_gbuffer_upload: bad arguments");
+    const size_t bytes = size_t(ctx->shW) * ctx->shH * 16;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpy(ctx->dPosDepth, positionDepth, bytes, cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(ctx->dNormalMetal, normalMetalness, bytes, cudaMemcpyHostToDevice));
+    return VKX_OK;
+}
+
+int vkx_gbuffer_download(vkx_ctx* ctx, float* positionDepth, float* normalMetalness) {
+    BIND(ctx);
+    if (!ctx->shW) return vkx_fail(ctx, VKX_E_INVALID, "shadow images not initialised");
+    const size_t bytes = size_t(ctx->shW) * ctx->shH * 16;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (positionDepth) CUDA_TRY(ctx, cudaMemcpy(positionDepth, ctx->dPosDepth, bytes, cudaMemcpyDeviceToHost));
+    if (normalMetalness) CUDA_TRY(ctx, cudaMemcpy(normalMetalness, ctx->dNormalMetal, bytes, cudaMemcpyDeviceToHost));
+    return VKX_OK;
+}
+
+int vkx_shadow_frame(vkx_ctx* ctx, const vkx_camera* cur, const vkx_camera* prev, const vkx_light* light, int sync) {
+    BIND(ctx);
+    if (!cur || !prev || !light) return vkx_fail(ctx, VKX_E_INVALID, "vkx_shadow_frame: null argument");
+    if (!ctx->shW || !ctx->bvhBuilt) return vkx_fail(ctx, VKX_E_INVALID, "vkx_shadow_frame: shadow images or BVH not ready");
+    if (!ctx->dNoise) return vkx_fail(ctx, VKX_E_INVALID, "vkx_shadow_frame: call vkx_shadow_set_noise first");
+    int rc = shadowFrame(ctx, *cur, *prev, *light);
+    if (rc != VKX_OK) return rc;
+    if (sync) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return VKX_OK;
+}
+
+int vkx_shadow_download(vkx_ctx* ctx, int stage, float* rgba) {
+    BIND(ctx);
+    if (!ctx->shW || !rgba) return vkx_fail(ctx, VKX_E_INVALID, "vkx_shadow_download: bad arguments");
+    const float4* src = stage == 0 ? ctx->dShRaw : stage == 1 ? ctx->dShX : ctx->dShFinal[ctx->shCur];
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpy(rgba, src, size_t(ctx->shW) * ctx->shH * 16, cudaMemcpyDeviceToHost));
+    return VKX_OK;
+}
+
+/* Parity side buffers of the last frame: jittered light directions [h][w][4] and the mask (0 not traced, 1 lit, 2 shadowed). */
+int vkx_shadow_download_debug(vkx_ctx* ctx, float* dirs4, uint8_t* mask) {
+    BIND(ctx);
+    if (!ctx->shW) return vkx_fail(ctx, VKX_E_INVALID, "shadow images not initialised");
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (dirs4) CUDA_TRY(ctx, cudaMemcpy(dirs4, ctx->dShDirs, size_t(ctx->shW) * ctx->shH * 16, cudaMemcpyDeviceToHost));
+    if (mask) CUDA_TRY(ctx, cudaMemcpy(mask, ctx->dShMask, size_t(ctx->shW) * ctx->shH, cudaMemcpyDeviceToHost));
+    return VKX_OK;
+}
+
+int vkx_shadow_reset_history(vkx_ctx* ctx) {
+    BIND(ctx);
+    if (!ctx->shW) return vkx_fail(ctx, VKX_E_INVALID, "shadow images not initialised");
+    const size_t bytes = size_t(ctx->shW) * ctx->shH * 16;
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->dShFinal[0], 0, bytes, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->dShFinal[1], 0, bytes, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return VKX_OK;
+}
+
+int vkx_shadow_timings(vkx_ctx* ctx, float ms[4]) {
+    BIND(ctx);
+    if (!ms) return VKX_E_INVALID;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms[0], ctx->sev[0], ctx->sev[3]));
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms[1], ctx->sev[0], ctx->sev[1]));
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms[2], ctx->sev[1], ctx->sev[2]));
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms[3], ctx->sev[2], ctx->sev[3]));
+    return VKX_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,195 @@
+// Shared declarations of libvkexp_b200: context, error handling, packing helpers.
+// All .cu files are compiled with --fmad=false: every float expression is a sequence of single IEEE-rounded
+// operations in source order, FMAs only where __fmaf_rn is written. This is what makes hit masks / triangle ids /
+// BVH topology bit-identical to oracle/ (compiled with -ffp-contract=off); see DESIGN.md section 4.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "../../include/vkx.h"
+
+static_assert(sizeof(vkx_vertex) == 64, "vkx_vertex");
+static_assert(sizeof(vkx_material) == 48, "vkx_material");
+static_assert(sizeof(vkx_offset_entry) == 12, "vkx_offset_entry");
+static_assert(sizeof(vkx_instance) == 56, "vkx_instance");
+static_assert(sizeof(vkx_grid_info) == 64, "vkx_grid_info");
+static_assert(sizeof(vkx_light) == 32, "vkx_light");
+static_assert(sizeof(vkx_camera) == 144, "vkx_camera");
+static_assert(sizeof(vkx_hit) == 20, "vkx_hit");
+
+struct ncclComm;
+
+struct DeviceScene {
+    const vkx_vertex* vertices;
+    const uint32_t* indices;
+    const vkx_offset_entry* offsets;
+    const vkx_material* materials;
+    const vkx_instance* instances;
+    const float* worldToObject; // 9 floats per instance, W[row][col] row-major = inverse of the 3x3 part
+    const uint4* nodes;         // 5 x uint4 per node
+    const float4* tris;         // 3 x float4 per triangle
+};
+
+struct DeviceProbes {
+    vkx_grid_info grid;
+    uint32_t irrW, irrH, depW, depH, probeCount;
+    const uint32_t* irrSampled;
+    const uint32_t* depSampled;
+    const uint32_t* stateSampled;
+    uint32_t* irrWork;
+    uint32_t* depWork;
+    uint32_t* stateWork;
+};
+
+struct vkx_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    int smCount = 148;
+
+    // scene
+    vkx_vertex* dVertices = nullptr; uint32_t* dIndices = nullptr; vkx_offset_entry* dOffsets = nullptr; uint32_t* dMeshCounts = nullptr;
+    vkx_material* dMaterials = nullptr; vkx_instance* dInstances = nullptr; float* dWorldToObject = nullptr; uint32_t* dInstTriBase = nullptr;
+    size_t numVertices = 0, numIndices = 0, numMeshes = 0, numMaterials = 0, numInstances = 0, numFlatTris = 0;
+    std::vector<uint32_t> hInstTriBase;
+
+    // bvh
+    uint4* dNodes = nullptr; float4* dTris = nullptr;
+    vkx_bvh_info bvh{};
+    bool bvhBuilt = false;
+
+    // probes
+    bool probesReady = false;
+    vkx_grid_info grid{};
+    uint32_t probeCount = 0, irrW = 0, irrH = 0, depW = 0, depH = 0;
+    uint32_t *dIrrWork = nullptr, *dIrrSampled = nullptr, *dDepWork = nullptr, *dDepSampled = nullptr, *dStateWork = nullptr, *dStateSampled = nullptr;
+    uint32_t* dIndicesList = nullptr;   // to-update list [probeCount]
+    float4* dDirs = nullptr;            // rotated ray directions [512]
+    uint32_t chunkProbes = 0;           // probes traced per chunk
+    float4* dRays = nullptr;            // [chunkProbes][N] (rgb, depth)
+    vkx_hit* dHits = nullptr;           // [chunkProbes][N]
+    float4* dShadowQueue = nullptr;     // [chunkProbes*N][2]
+    uint32_t* dQueueCount = nullptr;
+    uint8_t* dShadowFlags = nullptr;    // debug
+    float* dIrrUnpacked = nullptr; float* dDepUnpacked = nullptr; // debug, full count
+    bool debugBuffers = false;
+    uint32_t lastCount = 0, lastRays = 0;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float traceMsAcc = 0.f;
+
+    // multi-GPU
+    ncclComm* comm = nullptr; int rank = 0, nranks = 1;
+    cudaStream_t commStream = nullptr; cudaEvent_t commEvent = nullptr;
+    uint32_t *dIrrNext = nullptr, *dDepNext = nullptr, *dStateNext = nullptr; // all-gather targets (sharded update)
+    bool shardedLast = false;
+
+    // shadows
+    float* dNoise = nullptr; uint32_t noiseW = 0, noiseH = 0, noiseSlices = 0;
+    uint32_t shW = 0, shH = 0;
+    float4 *dPosDepth = nullptr, *dNormalMetal = nullptr, *dShRaw = nullptr, *dShX = nullptr, *dShFinal[2] = {nullptr, nullptr};
+    int shCur = 0; // dShFinal[shCur] = last frame's filtered result
+    float4* dShDirs = nullptr; uint8_t* dShMask = nullptr; // debug
+    cudaEvent_t sev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+int vkx_fail(vkx_ctx* ctx, int code, const char* fmt, ...);
+
+#define CUDA_TRY(ctx, expr)                                                                                  \
+    do {                                                                                                     \
+        cudaError_t _e = (expr);                                                                             \
+        if (_e != cudaSuccess) return vkx_fail((ctx), VKX_E_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+#define LAUNCH_CHECK(ctx)                                                                                    \
+    do {                                                                                                     \
+        (ctx)->launches++;                                                                                   \
+        cudaError_t _e = cudaGetLastError();                                                                 \
+        if (_e != cudaSuccess) return vkx_fail((ctx), VKX_E_CUDA, "%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+    } while (0)
+
+static inline unsigned divUp(size_t a, size_t b) { return unsigned((a + b - 1) / b); }
+
+// ---- implemented in bvh_build.cu
+int bvhBuildDevice(vkx_ctx* ctx);
+// ---- ddgi.cu
+int ddgiClassify(vkx_ctx* ctx, const float* dirs512);
+int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* hostIndices, uint32_t count, uint32_t firstProbe, bool publishAll);
+int ddgiPublish(vkx_ctx* ctx, uint32_t count);
+// ---- trace_api.cu
+int traceHostRays(vkx_ctx* ctx, const float* origins, const float* directions, size_t n, float tmin, float tmax, uint32_t cullMask, int anyHit, vkx_hit* out);
+// ---- shadow.cu
+int shadowGBuffer(vkx_ctx* ctx, const vkx_camera& cam);
+int shadowFrame(vkx_ctx* ctx, const vkx_camera& cur, const vkx_camera& prev, const vkx_light& light);
+
+DeviceScene deviceScene(const vkx_ctx* ctx);
+
+// ---------------------------------------------------------------------------------------------------------------
+// device helpers
+#ifdef __CUDACC__
+#include <cuda_fp16.h>
+
+// Total order on floats as unsigned keys (-0 < +0): min/max through atomicMin/atomicMax on the key.
+__host__ __device__ inline uint32_t okey(float f) {
+#ifdef __CUDA_ARCH__
+    uint32_t b = __float_as_uint(f);
+#else
+    uint32_t b; memcpy(&b, &f, 4);
+#endif
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ inline float unkey(uint32_t k) {
+    uint32_t b = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(b);
+#else
+    float f; memcpy(&f, &b, 4); return f;
+#endif
+}
+
+// ---- atlas texel formats (integer code identical to oracle/packing.h)
+template <int MB>
+__device__ inline uint32_t packUF(float f) {
+    if (!(f > 0.0f)) return 0;
+    const uint32_t maxCode = (31u << MB) - 1u;
+    uint32_t b = __float_as_uint(f);
+    int e = int(b >> 23) - 127;
+    uint32_t m = b & 0x7FFFFFu;
+    if (e > 15) return maxCode;
+    uint32_t code;
+    if (e >= -14) {
+        const int sh = 23 - MB;
+        uint32_t q = m >> sh, rem = m & ((1u << sh) - 1u), half = 1u << (sh - 1);
+        code = (uint32_t(e + 15) << MB) + q;
+        if (rem > half || (rem == half && (q & 1u))) code += 1;
+    } else {
+        int sh = (23 - MB) + (-14 - e);
+        if (sh > 24) return 0;
+        uint32_t full = m | 0x800000u;
+        uint32_t q = full >> sh, rem = full & ((1u << sh) - 1u), half = 1u << (sh - 1);
+        code = q;
+        if (rem > half || (rem == half && (q & 1u))) code += 1;
+    }
+    return code > maxCode ? maxCode : code;
+}
+template <int MB>
+__device__ inline float unpackUF(uint32_t c) {
+    uint32_t e = c >> MB, m = c & ((1u << MB) - 1u);
+    if (e == 0) return float(m) * __uint_as_float(uint32_t(127 - 14 - MB) << 23);
+    if (e == 31) return m ? __uint_as_float(0x7FC00000u) : __uint_as_float(0x7F800000u);
+    return __uint_as_float(((e + 112u) << 23) | (m << (23 - MB)));
+}
+__device__ inline uint32_t packR11G11B10(float r, float g, float b) { return packUF<6>(r) | (packUF<6>(g) << 11) | (packUF<5>(b) << 22); }
+__device__ inline float3 unpackR11G11B10(uint32_t p) {
+    return make_float3(unpackUF<6>(p & 0x7FFu), unpackUF<6>((p >> 11) & 0x7FFu), unpackUF<5>(p >> 22));
+}
+__device__ inline uint32_t packRG16F(float r, float g) {
+    return uint32_t(__half_as_ushort(__float2half_rn(r))) | (uint32_t(__half_as_ushort(__float2half_rn(g))) << 16);
+}
+__device__ inline float2 unpackRG16F(uint32_t p) {
+    return make_float2(__half2float(__ushort_as_half((unsigned short)(p & 0xFFFFu))), __half2float(__ushort_as_half((unsigned short)(p >> 16))));
+}
+
+#endif // __CUDACC__

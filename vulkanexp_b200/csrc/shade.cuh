@@ -1,0 +1,278 @@
+// Device restatement of the reference's shading code for probe rays: sampleProbes (reference
+// src/shaders/irradiance.glsl:145-237), sky (src/shaders/sky.glsl:59-126), pbrMetallicRoughness
+// (src/shaders/pbrMetallicRoughness.glsl:43-84). Compiled with --fmad=false, so the arithmetic is the same
+// sequence of IEEE operations the oracle executes; remaining differences come from libm (exp/pow/sqrt are IEEE,
+// expf/powf are not bit-identical between glibc and CUDA).
+#pragma once
+#include "common.cuh"
+
+struct v3 { float x, y, z; };
+__device__ __forceinline__ v3 mk3(float x, float y, float z) { v3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ v3 mk3(float s) { return mk3(s, s, s); }
+__device__ __forceinline__ v3 operator+(v3 a, v3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ v3 operator-(v3 a, v3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ v3 operator-(v3 a) { return mk3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ v3 operator*(v3 a, v3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ v3 operator/(v3 a, v3 b) { return mk3(a.x / b.x, a.y / b.y, a.z / b.z); }
+__device__ __forceinline__ v3 operator*(v3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ v3 operator*(float s, v3 a) { return mk3(s * a.x, s * a.y, s * a.z); }
+__device__ __forceinline__ v3 operator/(v3 a, float s) { return mk3(a.x / s, a.y / s, a.z / s); }
+__device__ __forceinline__ v3 operator+(v3 a, float s) { return mk3(a.x + s, a.y + s, a.z + s); }
+__device__ __forceinline__ v3 operator-(float s, v3 a) { return mk3(s - a.x, s - a.y, s - a.z); }
+__device__ __forceinline__ float dot3(v3 a, v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ v3 cross3(v3 x, v3 y) { return mk3(x.y * y.z - y.y * x.z, x.z * y.x - y.z * x.x, x.x * y.y - y.x * x.y); }
+__device__ __forceinline__ float len3(v3 v) { return sqrtf(dot3(v, v)); }
+__device__ __forceinline__ v3 norm3(v3 v) { return v * (1.0f / sqrtf(dot3(v, v))); }
+__device__ __forceinline__ float mixf(float x, float y, float a) { return x * (1.0f - a) + y * a; }
+__device__ __forceinline__ v3 mix3(v3 x, v3 y, float a) { return x * (1.0f - a) + y * a; }
+__device__ __forceinline__ v3 mix3(v3 x, v3 y, v3 a) { return x * (1.0f - a) + y * a; }
+__device__ __forceinline__ float maxS(float a, float b) { return a < b ? b : a; } // std::max
+__device__ __forceinline__ float minS(float a, float b) { return b < a ? b : a; } // std::min
+__device__ __forceinline__ float clampS(float x, float lo, float hi) { return minS(maxS(x, lo), hi); }
+__device__ __forceinline__ float signS(float x) { return float((0.0f < x) - (x < 0.0f)); }
+__device__ __forceinline__ v3 abs3(v3 v) { return mk3(fabsf(v.x), fabsf(v.y), fabsf(v.z)); }
+__device__ __forceinline__ v3 reflect3(v3 I, v3 N) { return I - N * dot3(N, I) * 2.0f; }
+
+#define VKX_PI 3.1415926538f
+
+// ---- grid helpers (irradiance.glsl:7-38)
+__device__ __forceinline__ v3 gridCellSize(const vkx_grid_info& g) {
+    return mk3(g.extentMax[0] - g.extentMin[0], g.extentMax[1] - g.extentMin[1], g.extentMax[2] - g.extentMin[2]) /
+           mk3(float(g.resolution[0] - 1), float(g.resolution[1] - 1), float(g.resolution[2] - 1));
+}
+__device__ __forceinline__ v3 probeWorldPos(int ix, int iy, int iz, const vkx_grid_info& g) {
+    return mk3(float(ix), float(iy), float(iz)) * gridCellSize(g) + mk3(g.extentMin[0], g.extentMin[1], g.extentMin[2]);
+}
+__device__ __forceinline__ void probeGridIndex(uint32_t index, const vkx_grid_info& g, int& ix, int& iy, int& iz) {
+    uint32_t rx = uint32_t(g.resolution[0]), ry = uint32_t(g.resolution[1]);
+    ix = int(index % rx); iy = int((index % (rx * ry)) / rx); iz = int(index / (rx * ry));
+}
+
+__device__ __forceinline__ float signNotZero(float k) { return (k >= 0.0f) ? 1.0f : -1.0f; }
+__device__ __forceinline__ v3 octDecode(float ox, float oy) { // irradiance.glsl:107-112
+    v3 v = mk3(ox, oy, 1.0f - fabsf(ox) - fabsf(oy));
+    if (v.z < 0.0f) {
+        float nx = (1.0f - fabsf(v.y)) * signNotZero(v.x);
+        float ny = (1.0f - fabsf(v.x)) * signNotZero(v.y);
+        v.x = nx; v.y = ny;
+    }
+    return norm3(v);
+}
+__device__ __forceinline__ float2 sphereToOctUV(v3 direction) { // irradiance.glsl:119-138
+    v3 octant = mk3(signS(direction.x), signS(direction.y), signS(direction.z));
+    float sum = dot3(direction, octant);
+    v3 o = direction / sum;
+    if (o.z < 0.0f) {
+        v3 a = abs3(o);
+        o.x = octant.x * (1.0f - a.y);
+        o.y = octant.y * (1.0f - a.x);
+    }
+    return make_float2(o.x * 0.5f + 0.5f, o.y * 0.5f + 0.5f);
+}
+
+__device__ __forceinline__ void bilinearSetup(float u, uint32_t size, int& i0, int& i1, float& f) {
+    float x = u * float(size) - 0.5f;
+    float fl = floorf(x);
+    f = x - fl;
+    int isz = int(size), i = int(fl);
+    i0 = ((i % isz) + isz) % isz;
+    i1 = (i0 + 1) % isz;
+}
+
+__device__ __forceinline__ v3 sampleIrradianceTex(const DeviceProbes& p, float u, float v) {
+    int x0, x1, y0, y1; float fx, fy;
+    bilinearSetup(u, p.irrW, x0, x1, fx); bilinearSetup(v, p.irrH, y0, y1, fy);
+    const uint32_t* r0 = p.irrSampled + size_t(y0) * p.irrW; const uint32_t* r1 = p.irrSampled + size_t(y1) * p.irrW;
+    float3 t00 = unpackR11G11B10(__ldg(r0 + x0)), t10 = unpackR11G11B10(__ldg(r0 + x1)), t01 = unpackR11G11B10(__ldg(r1 + x0)), t11 = unpackR11G11B10(__ldg(r1 + x1));
+    float gx = 1.0f - fx, gy = 1.0f - fy;
+    v3 r;
+    r.x = (t00.x * gx + t10.x * fx) * gy + (t01.x * gx + t11.x * fx) * fy;
+    r.y = (t00.y * gx + t10.y * fx) * gy + (t01.y * gx + t11.y * fx) * fy;
+    r.z = (t00.z * gx + t10.z * fx) * gy + (t01.z * gx + t11.z * fx) * fy;
+    return r;
+}
+__device__ __forceinline__ float2 sampleDepthTex(const DeviceProbes& p, float u, float v) {
+    int x0, x1, y0, y1; float fx, fy;
+    bilinearSetup(u, p.depW, x0, x1, fx); bilinearSetup(v, p.depH, y0, y1, fy);
+    const uint32_t* r0 = p.depSampled + size_t(y0) * p.depW; const uint32_t* r1 = p.depSampled + size_t(y1) * p.depW;
+    float2 t00 = unpackRG16F(__ldg(r0 + x0)), t10 = unpackRG16F(__ldg(r0 + x1)), t01 = unpackRG16F(__ldg(r1 + x0)), t11 = unpackRG16F(__ldg(r1 + x1));
+    float gx = 1.0f - fx, gy = 1.0f - fy;
+    return make_float2((t00.x * gx + t10.x * fx) * gy + (t01.x * gx + t11.x * fx) * fy, (t00.y * gx + t10.y * fx) * gy + (t01.y * gx + t11.y * fx) * fy);
+}
+
+__device__ inline v3 sampleProbes(const DeviceProbes& p, v3 position, v3 normal, v3 toCamera) { // irradiance.glsl:145-237
+    const vkx_grid_info& grid = p.grid;
+    const v3 cell = gridCellSize(grid);
+    const v3 acell = abs3(cell);
+    const v3 extentMin = mk3(grid.extentMin[0], grid.extentMin[1], grid.extentMin[2]);
+    const v3 gridCoords = (position - extentMin) / acell;
+    if (gridCoords.x < 0.0f || gridCoords.y < 0.0f || gridCoords.z < 0.0f) return mk3(0.0f);
+    const v3 biasVector = (normal + toCamera) * grid.shadowBias;
+    const v3 biasedPosition = position + biasVector;
+    const int fx = int(gridCoords.x), fy = int(gridCoords.y), fz = int(gridCoords.z);
+    v3 alpha = (position - probeWorldPos(fx, fy, fz, grid)) / acell;
+    alpha = mk3(clampS(alpha.x, 0.0f, 1.0f), clampS(alpha.y, 0.0f, 1.0f), clampS(alpha.z, 0.0f, 1.0f));
+
+    v3 finalColor = mk3(0.0f), fallbackColor = mk3(0.0f);
+    float totalWeight = 0.0f, totalFallbackWeight = 0.0f;
+    const float usx = float(grid.resolution[0] * grid.resolution[1]), usy = float(grid.resolution[2]);
+    const float2 octN = sphereToOctUV(normal);
+    const float cscale = float(grid.colorRes - 2) / float(grid.colorRes), dscale = float(grid.depthRes - 2) / float(grid.depthRes);
+
+    for (int i = 0; i < 8; ++i) {
+        const int ox = i & 1, oy = (i >> 1) & 1, oz = (i >> 2) & 1;
+        const int cx = fx + ox, cy = fy + oy, cz = fz + oz;
+        if (cx > grid.resolution[0] - 1 || cy > grid.resolution[1] - 1 || cz > grid.resolution[2] - 1) continue;
+        const uint32_t li = uint32_t(cx + grid.resolution[0] * cy + grid.resolution[0] * grid.resolution[1] * cz);
+        if (__ldg(p.stateSampled + li) == 0u) continue;
+        const v3 probePosition = probeWorldPos(cx, cy, cz, grid);
+        const v3 directionToProbe = norm3(probePosition - position);
+        const v3 biasedDirectionToProbe = probePosition - biasedPosition;
+        const float2 octD = sphereToOctUV(-norm3(biasedDirectionToProbe));
+        const float lcu = cscale * octN.x, lcv = cscale * octN.y;
+        const float ldu = dscale * octD.x, ldv = dscale * octD.y;
+        const int tile = cy * grid.resolution[0] + cx;
+        const float colorU = (float(int(grid.colorRes) * tile + 1) / float(grid.colorRes) + lcu) / usx;
+        const float colorV = (float(int(grid.colorRes) * cz + 1) / float(grid.colorRes) + lcv) / usy;
+        const float depthU = (float(int(grid.depthRes) * tile + 1) / float(grid.depthRes) + ldu) / usx;
+        const float depthV = (float(int(grid.depthRes) * cz + 1) / float(grid.depthRes) + ldv) / usy;
+        const v3 trilinear = mix3(1.0f - alpha, alpha, mk3(float(ox), float(oy), float(oz)));
+        float weight = 1.0f;
+        const float backfaceweight = maxS(0.0001f, (dot3(directionToProbe, normal) + 1.0f) * 0.5f);
+        weight *= backfaceweight * backfaceweight + 0.2f;
+        float fallbackWeight = weight;
+
+        const float2 depth = sampleDepthTex(p, depthU, depthV);
+        const float mean = depth.x;
+        const float variance = fabsf(depth.x * depth.x - depth.y);
+        const float biasedDistToProbe = len3(probePosition - biasedPosition);
+        const float dd = maxS(biasedDistToProbe - mean, 0.0001f);
+        float chebyshevWeight = variance / (variance + dd * dd);
+        chebyshevWeight = maxS(powf(chebyshevWeight, 3.0f), 0.0f);
+        weight *= (biasedDistToProbe <= mean) ? 1.0f : chebyshevWeight;
+        weight = maxS(0.000001f, weight);
+        const float crushThreshold = 0.2f;
+        if (weight < crushThreshold) weight *= weight * weight * (1.0f / (crushThreshold * crushThreshold));
+        const float tri = trilinear.x * trilinear.y * trilinear.z + 0.001f;
+        weight *= tri;
+        fallbackWeight *= tri;
+
+        v3 color = sampleIrradianceTex(p, colorU, colorV);
+        color = mk3(sqrtf(color.x), sqrtf(color.y), sqrtf(color.z));
+        finalColor = finalColor + weight * color;
+        totalWeight += weight;
+        fallbackColor = fallbackColor + fallbackWeight * color;
+        totalFallbackWeight += fallbackWeight;
+    }
+    if (totalWeight > 1e-3f) finalColor = finalColor * (1.0f / totalWeight);
+    if (totalFallbackWeight > 1e-3f) fallbackColor = fallbackColor * (1.0f / totalFallbackWeight);
+    finalColor = finalColor * finalColor;
+    fallbackColor = fallbackColor * fallbackColor;
+    return mix3(fallbackColor, finalColor, 8.0f * clampS(totalWeight, 0.0f, 1.0f / 8.0f));
+}
+
+// ---- sky.glsl
+__device__ __forceinline__ float skyScale(float fCos) {
+    float x = 1.0f - fCos;
+    return 0.25f * expf(-0.00287f + x * (0.459f + x * (3.83f + x * (-6.80f + x * 5.25f))));
+}
+__device__ inline float traceSphereOutside(v3 center, float radius, v3 origin, v3 direction) {
+    v3 d = origin - center;
+    float a = dot3(direction, direction), b = dot3(direction, d), c = dot3(d, d) - radius * radius;
+    float g = b * b - a * c;
+    if (g > 0.0f) { float dis = (-sqrtf(g) - b) / a; if (dis > 0.0f) return dis; }
+    return -1.0f;
+}
+__device__ inline float traceSphereInside(v3 center, float radius, v3 origin, v3 direction) {
+    v3 oc = center - origin;
+    float docdir = dot3(oc, direction);
+    v3 pc = origin + docdir * direction;
+    float dist = sqrtf(radius * radius - len3(pc - center) * len3(pc - center));
+    if (docdir > 0.0f) return dist - len3(pc - origin);
+    else return dist + len3(pc - origin);
+}
+
+__device__ inline v3 skyColor(v3 rayOrigin, v3 rayDirection, v3 sunPosition, v3 sunColor, float sunBrightnessFactor) { // sky.glsl:59-126, showSun = true
+    const float AvegerageDensityAltitude = 0.25f, InnerRadius = 100000.0f, OuterRadius = 2500.0f + InnerRadius;
+    const float Scale = 1.0f / (OuterRadius - InnerRadius);
+    const float Kr = 0.0025f, Kr4PI = Kr * 4.0f * VKX_PI, Km = 0.0010f, Km4PI = Km * 4.0f * VKX_PI, g = -0.990f;
+    // 1 / pow(w, 4) for w = 0.650, 0.570, 0.475 as glibc's powf evaluates them in fp32
+    const v3 InvWaveLengths = mk3(__uint_as_float(0x40b343f5u), __uint_as_float(0x41179293u), __uint_as_float(0x419d2682u)); // 5.60204554, 9.47328472, 19.6438026
+    sunColor = sunColor * sunBrightnessFactor;
+    const v3 planetCenter = mk3(0.0f, -InnerRadius - 100.0f, 0.0f);
+    v3 position = rayOrigin - planetCenter;
+    float height = len3(position);
+    const v3 lightDir = norm3(sunPosition);
+    if (fabsf(height - InnerRadius) < 1e-3f) { position = position + 1e-2f * norm3(position); height = len3(position); }
+    if (height < OuterRadius) {
+        if (height > InnerRadius) {
+            float planetDistance = traceSphereOutside(mk3(0.0f), InnerRadius, position, rayDirection);
+            if (planetDistance >= 0.0f) return maxS(0.1f, dot3(lightDir, norm3(position + planetDistance * rayDirection))) * mk3(0.05f);
+        } else return mk3(0.0f);
+        const float rayDepth = traceSphereInside(mk3(0.0f), OuterRadius, position, rayDirection);
+        if (isinf(rayDepth) || isnan(rayDepth)) return mk3(0.0f);
+        const float depth = expf(Scale / AvegerageDensityAltitude * (InnerRadius - height));
+        const float startAngle = dot3(rayDirection, position) / height;
+        const float startOffset = depth * skyScale(startAngle);
+        const float sampleLength = rayDepth / 64.0f;
+        const float scaledLength = sampleLength * Scale;
+        const v3 sampleRay = rayDirection * sampleLength;
+        v3 samplePoint = position + 0.5f * sampleRay;
+        v3 color = mk3(0.0f);
+        const v3 kk = InvWaveLengths * Kr4PI + Km4PI;
+        for (uint32_t i = 0; i < 64u; ++i) {
+            const float h = len3(samplePoint);
+            const float dpt = expf(Scale / AvegerageDensityAltitude * (InnerRadius - h));
+            const float lightAngle = dot3(lightDir, samplePoint) / h;
+            const float cameraAngle = dot3(rayDirection, samplePoint) / h;
+            const float scatter = startOffset + dpt * (skyScale(lightAngle) - skyScale(cameraAngle));
+            const v3 e = (-scatter) * kk;
+            const v3 attenuate = mk3(expf(e.x), expf(e.y), expf(e.z));
+            if (isinf(attenuate.x) || isinf(attenuate.y) || isinf(attenuate.z) || isnan(attenuate.x) || isnan(attenuate.y) || isnan(attenuate.z)) continue;
+            color = color + attenuate * (dpt * scaledLength);
+            samplePoint = samplePoint + sampleRay;
+        }
+        const v3 secondary = color * Km * sunColor;
+        color = color * (InvWaveLengths * Kr * sunColor);
+        {
+            const float miecos = dot3(lightDir, -rayDirection);
+            const float miePhase = 1.5f * ((1.0f - g * g) / (2.0f + g * g)) * (1.0f + miecos * miecos) / powf(maxS(1e-3f, 1.0f + g * g - 2.0f * g * miecos), 1.5f);
+            color = color + miePhase * secondary;
+        }
+        if (!(isinf(color.x) || isinf(color.y) || isinf(color.z))) return color;
+    } else {
+        float depth = traceSphereOutside(mk3(0.0f), OuterRadius, position, rayDirection);
+        if (depth > 0.0f) return dot3(lightDir, norm3(position + depth * rayDirection)) * 0.5f * mk3(0.5294117647f, 0.80784313725f, 0.92156862745f);
+    }
+    return mk3(0.0f);
+}
+
+// ---- pbrMetallicRoughness.glsl:43-84
+__device__ inline v3 pbrMetallicRoughness(v3 normal, v3 view, v3 lightColor, v3 lightDirection, v3 albedo, float metalness, float roughness) {
+    const v3 f0 = mk3(0.04f);
+    v3 diffuseColor = albedo * (1.0f - f0);
+    diffuseColor = diffuseColor * (1.0f - metalness);
+    const float alphaRoughness = roughness * roughness;
+    const v3 specularColor = mix3(f0, albedo, metalness);
+    const float reflectance = maxS(maxS(specularColor.x, specularColor.y), specularColor.z);
+    const float reflectance90 = clampS(reflectance * 25.0f, 0.0f, 1.0f);
+    const v3 R0 = specularColor, R90 = mk3(1.0f) * reflectance90;
+    const v3 n = normal, v = view;
+    const v3 l = norm3(lightDirection);
+    const v3 h = norm3(l + v);
+    const float NdotL = clampS(dot3(n, l), 0.001f, 1.0f);
+    const float NdotV = clampS(fabsf(dot3(n, v)), 0.001f, 1.0f);
+    const float NdotH = clampS(dot3(n, h), 0.0f, 1.0f);
+    const float VdotH = clampS(dot3(v, h), 0.0f, 1.0f);
+    const v3 F = R0 + (R90 - R0) * powf(clampS(1.0f - VdotH, 0.0f, 1.0f), 5.0f);
+    const float ar2 = alphaRoughness * alphaRoughness;
+    const float attenuationL = 2.0f * NdotL / (NdotL + sqrtf(ar2 + (1.0f - ar2) * (NdotL * NdotL)));
+    const float attenuationV = 2.0f * NdotV / (NdotV + sqrtf(ar2 + (1.0f - ar2) * (NdotV * NdotV)));
+    const float G = attenuationL * attenuationV;
+    const float a = NdotH * alphaRoughness;
+    const float k = alphaRoughness / ((1.0f - NdotH * NdotH) + a * a);
+    const float D = clampS(k * k * (1.0f / VKX_PI), 0.0f, 4.0f);
+    const v3 diffuseContrib = (1.0f - F) * diffuseColor / VKX_PI;
+    const v3 specContrib = F * G * D / (4.0f * NdotL * NdotV);
+    return NdotL * lightColor * (diffuseContrib + specContrib);
+}

@@ -1,0 +1,156 @@
+// Per-ray traversal of the 8-wide compressed BVH ("BVH spec v1"). Replaces the RT-core
+// traversal behind traceRayEXT in the reference's shaders (reference src/shaders/traceProbes.rgen:43,
+// closesthit.glsl:270-281, directLight.rgen:79-90, probesInit.rgen:45). The float operation sequence per ray is the
+// one oracle/bvh.cpp executes; only the scheduling of rays onto lanes differs.
+#pragma once
+#include "common.cuh"
+
+#define VKX_STACK 48
+
+struct Ray {
+    float ox, oy, oz;
+    float dx, dy, dz;
+    float ix, iy, iz; // 1 / zero-fixed direction
+    uint32_t oct;     // bit 2: dx < 0, bit 1: dy < 0, bit 0: dz < 0
+};
+
+__device__ __forceinline__ float fixZero(float d) { return fabsf(d) < 1e-20f ? copysignf(1e-20f, d) : d; }
+
+__device__ __forceinline__ Ray makeRay(float ox, float oy, float oz, float dx, float dy, float dz) {
+    Ray r;
+    r.ox = ox; r.oy = oy; r.oz = oz; r.dx = dx; r.dy = dy; r.dz = dz;
+    float fx = fixZero(dx), fy = fixZero(dy), fz = fixZero(dz);
+    r.ix = __fdiv_rn(1.0f, fx); r.iy = __fdiv_rn(1.0f, fy); r.iz = __fdiv_rn(1.0f, fz);
+    r.oct = (fx < 0.0f ? 4u : 0u) | (fy < 0.0f ? 2u : 0u) | (fz < 0.0f ? 1u : 0u);
+    return r;
+}
+
+__device__ __forceinline__ float byteToFloat(uint32_t w, int i) { return __uint2float_rn((w >> (8 * i)) & 0xFFu); }
+
+// 8 quantised child boxes of one axis: near plane bytes (n0: slots 0-3, n1: slots 4-7) and far plane bytes.
+struct AxisQ { uint32_t n0, n1, f0, f1; };
+
+// Returns the hit mask of one node: bits 24..31 inner children at priority position, bits 0..23 triangles.
+__device__ __forceinline__ uint32_t intersectNode(const uint4 w0, const uint4 w1, const uint4 w2, const uint4 w3, const uint4 w4,
+                                                   const Ray& r, float tmin, float tmax) {
+    const float px = __uint_as_float(w0.x), py = __uint_as_float(w0.y), pz = __uint_as_float(w0.z);
+    const uint32_t ew = w0.w;
+    const float ax = __fmul_rn(__uint_as_float((ew & 0xFFu) << 23), r.ix);
+    const float ay = __fmul_rn(__uint_as_float(((ew >> 8) & 0xFFu) << 23), r.iy);
+    const float az = __fmul_rn(__uint_as_float(((ew >> 16) & 0xFFu) << 23), r.iz);
+    const float bx = __fmul_rn(__fsub_rn(px, r.ox), r.ix);
+    const float by = __fmul_rn(__fsub_rn(py, r.oy), r.iy);
+    const float bz = __fmul_rn(__fsub_rn(pz, r.oz), r.iz);
+    // words: w2 = qlo.x[0..7] (x,y) qlo.y[0..7] (z,w); w3 = qlo.z, qhi.x; w4 = qhi.y, qhi.z
+    AxisQ qx, qy, qz;
+    if (r.oct & 4u) { qx.n0 = w3.z; qx.n1 = w3.w; qx.f0 = w2.x; qx.f1 = w2.y; } else { qx.n0 = w2.x; qx.n1 = w2.y; qx.f0 = w3.z; qx.f1 = w3.w; }
+    if (r.oct & 2u) { qy.n0 = w4.x; qy.n1 = w4.y; qy.f0 = w2.z; qy.f1 = w2.w; } else { qy.n0 = w2.z; qy.n1 = w2.w; qy.f0 = w4.x; qy.f1 = w4.y; }
+    if (r.oct & 1u) { qz.n0 = w4.z; qz.n1 = w4.w; qz.f0 = w3.x; qz.f1 = w3.y; } else { qz.n0 = w3.x; qz.n1 = w3.y; qz.f0 = w4.z; qz.f1 = w4.w; }
+    uint32_t mask = 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const uint32_t meta4 = h ? w1.w : w1.z;
+        const uint32_t nx = h ? qx.n1 : qx.n0, fx = h ? qx.f1 : qx.f0;
+        const uint32_t ny = h ? qy.n1 : qy.n0, fy = h ? qy.f1 : qy.f0;
+        const uint32_t nz = h ? qz.n1 : qz.n0, fz = h ? qz.f1 : qz.f0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t meta = (meta4 >> (8 * i)) & 0xFFu;
+            if (meta == 0) continue;
+            const float tlx = __fmaf_rn(byteToFloat(nx, i), ax, bx), thx = __fmaf_rn(byteToFloat(fx, i), ax, bx);
+            const float tly = __fmaf_rn(byteToFloat(ny, i), ay, by), thy = __fmaf_rn(byteToFloat(fy, i), ay, by);
+            const float tlz = __fmaf_rn(byteToFloat(nz, i), az, bz), thz = __fmaf_rn(byteToFloat(fz, i), az, bz);
+            const float tn = fmaxf(fmaxf(tlx, tly), fmaxf(tlz, tmin));
+            const float tf = fminf(fminf(thx, thy), fminf(thz, tmax));
+            if (tn <= tf) {
+                uint32_t bits = meta >> 5, idx = meta & 31u;
+                if (idx >= 24u) idx = 24u + ((idx - 24u) ^ r.oct);
+                mask |= bits << idx;
+            }
+        }
+    }
+    return mask;
+}
+
+// Moeller-Trumbore with the fixed operation order of oracle/bvh.cpp::intersectTri.
+__device__ __forceinline__ bool intersectTri(const float4 q0, const float4 q1, const float4 q2, const Ray& r, float& t, float& u, float& v, float& det) {
+    const float v0x = q0.x, v0y = q0.y, v0z = q0.z;
+    const float e1x = q0.w, e1y = q1.x, e1z = q1.y;
+    const float e2x = q1.z, e2y = q1.w, e2z = q2.x;
+    const float px = __fmaf_rn(r.dy, e2z, -__fmul_rn(r.dz, e2y));
+    const float py = __fmaf_rn(r.dz, e2x, -__fmul_rn(r.dx, e2z));
+    const float pz = __fmaf_rn(r.dx, e2y, -__fmul_rn(r.dy, e2x));
+    det = __fmaf_rn(e1x, px, __fmaf_rn(e1y, py, __fmul_rn(e1z, pz)));
+    if (det == 0.0f) return false;
+    const float inv = __fdiv_rn(1.0f, det);
+    const float tx = __fsub_rn(r.ox, v0x), ty = __fsub_rn(r.oy, v0y), tz = __fsub_rn(r.oz, v0z);
+    u = __fmul_rn(__fmaf_rn(tx, px, __fmaf_rn(ty, py, __fmul_rn(tz, pz))), inv);
+    if (!(u >= 0.0f && u <= 1.0f)) return false;
+    const float qx = __fmaf_rn(ty, e1z, -__fmul_rn(tz, e1y));
+    const float qy = __fmaf_rn(tz, e1x, -__fmul_rn(tx, e1z));
+    const float qz = __fmaf_rn(tx, e1y, -__fmul_rn(ty, e1x));
+    v = __fmul_rn(__fmaf_rn(r.dx, qx, __fmaf_rn(r.dy, qy, __fmul_rn(r.dz, qz))), inv);
+    if (!(v >= 0.0f && __fadd_rn(u, v) <= 1.0f)) return false;
+    t = __fmul_rn(__fmaf_rn(e2x, qx, __fmaf_rn(e2y, qy, __fmul_rn(e2z, qz))), inv);
+    return true;
+}
+
+struct HitRec {
+    float t, u, v;
+    uint32_t inst, prim; // prim bit 31: back face
+    bool found;
+};
+
+__device__ __forceinline__ void loadNode(const uint4* __restrict__ nodes, uint32_t idx, uint4& w0, uint4& w1, uint4& w2, uint4& w3, uint4& w4) {
+    const uint4* p = nodes + size_t(idx) * 5;
+    w0 = __ldg(p + 0); w1 = __ldg(p + 1); w2 = __ldg(p + 2); w3 = __ldg(p + 3); w4 = __ldg(p + 4);
+}
+
+// One full traversal. ANY: terminate on first accepted hit, returns true if occluded.
+template <bool ANY>
+__device__ __forceinline__ bool traverse(const uint4* __restrict__ nodes, const float4* __restrict__ tris, const Ray& r, float tmin, float tmax,
+                                         uint32_t cullMask, HitRec& hit) {
+    float tbest = tmax;
+    hit.found = false; hit.inst = 0xFFFFFFFFu; hit.prim = 0xFFFFFFFFu; hit.u = 0.f; hit.v = 0.f; hit.t = -1.0f;
+    uint2 stack[VKX_STACK];
+    int sp = 0;
+    uint2 g = make_uint2(0u, 0x80000000u);
+    for (;;) {
+        uint32_t triBase = 0, triBits = 0;
+        if (g.y & 0xFF000000u) {
+            const uint32_t bit = 31u - uint32_t(__clz(int(g.y)));
+            g.y &= ~(1u << bit);
+            if (g.y & 0xFF000000u) { if (sp < VKX_STACK) stack[sp++] = g; }
+            const uint32_t slot = (bit - 24u) ^ r.oct;
+            const uint32_t rel = uint32_t(__popc(g.y & 0xFFu & ((1u << slot) - 1u)));
+            uint4 w0, w1, w2, w3, w4;
+            loadNode(nodes, g.x + rel, w0, w1, w2, w3, w4);
+            const uint32_t m = intersectNode(w0, w1, w2, w3, w4, r, tmin, tbest);
+            g.x = w1.x; g.y = (m & 0xFF000000u) | (w0.w >> 24);
+            triBase = w1.y; triBits = m & 0x00FFFFFFu;
+        }
+        while (triBits) {
+            const uint32_t b = uint32_t(__ffs(int(triBits))) - 1u;
+            triBits &= triBits - 1u;
+            const float4* tp = tris + size_t(triBase + b) * 3;
+            const float4 q2 = __ldg(tp + 2);
+            const uint32_t instW = __float_as_uint(q2.y), primW = __float_as_uint(q2.z);
+            if (!((instW >> 24) & cullMask)) continue;
+            const float4 q0 = __ldg(tp + 0), q1 = __ldg(tp + 1);
+            float t, u, v, det;
+            if (!intersectTri(q0, q1, q2, r, t, u, v, det)) continue;
+            if (!(t > tmin)) continue;
+            const uint32_t inst = instW & 0x00FFFFFFu, prim = primW & 0x7FFFFFFFu;
+            const bool closer = t < tbest || (hit.found && t == tbest && (inst < hit.inst || (inst == hit.inst && prim < (hit.prim & 0x7FFFFFFFu))));
+            if (!closer) continue;
+            if (ANY) return true;
+            const bool back = (det > 0.0f) == ((primW & 0x80000000u) != 0u);
+            hit.found = true; tbest = t; hit.t = t; hit.inst = inst; hit.prim = prim | (back ? 0x80000000u : 0u); hit.u = u; hit.v = v;
+        }
+        if (!(g.y & 0xFF000000u)) {
+            if (sp == 0) break;
+            g = stack[--sp];
+        }
+    }
+    return hit.found;
+}
