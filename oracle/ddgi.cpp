@@ -594,8 +594,10 @@ void update(const Scene& s, Probes& p, const vkx_grid_info& g, const vkx_light& 
 // ---------------------------------------------------------------- host logic of IrradianceProbes.cpp
 static uint32_t randU32(MsvcRand& r) {
     // glm::detail::compute_rand<1, uint32>: (u16 << 16) | u16, u16 = (u8 << 8) | u8, u8 = rand() % 255
-    // (ext/glm/glm/gtc/random.inl:19-85). Operand evaluation order of `|` is unspecified in C++; decree: left first.
-    uint32_t b3 = uint32_t(r.next() % 255), b2 = uint32_t(r.next() % 255), b1 = uint32_t(r.next() % 255), b0 = uint32_t(r.next() % 255);
+    // (ext/glm/glm/gtc/random.inl:19-85). Operand evaluation order of `|` is unspecified in C++. Decree: the order g++ 13
+    // gives the unmodified GLM headers (right operand first, i.e. the first draw is the lowest byte), which is what
+    // tests/golden/glm_pin.json pins; MSVC's order (the reference's only compiler) cannot be verified here.
+    uint32_t b0 = uint32_t(r.next() % 255), b1 = uint32_t(r.next() % 255), b2 = uint32_t(r.next() % 255), b3 = uint32_t(r.next() % 255);
     return (((b3 << 8) | b2) << 16) | ((b1 << 8) | b0);
 }
 static float linearRand(MsvcRand& r, float Min, float Max) { // random.inl:177-183

@@ -1,0 +1,61 @@
+"""CPU-only: the C ABI library loads and exports every symbol include/vkx.h declares (no compute without a GPU)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "vkx.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vkx_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_the_expected_surface():
+    names = _declared()
+    for must in ("vkx_create", "vkx_scene_upload", "vkx_bvh_build", "vkx_probes_init", "vkx_probes_classify", "vkx_probes_update",
+                 "vkx_probes_download", "vkx_shadow_frame", "vkx_comm_init", "vkx_probes_update_sharded", "vkx_destroy"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol():
+    from vulkanexp_b200 import _lib
+
+    lib = _lib.load()
+    missing = [n for n in _declared() if not hasattr(lib, n)]
+    assert not missing, missing
+    lib.vkx_abi_version.restype = C.c_int
+    assert lib.vkx_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_a_device():
+    """Without a CUDA device vkx_create must fail loudly; with one it must succeed. Either way nothing routes to the oracle."""
+    from vulkanexp_b200 import _lib
+
+    lib = _lib.load()
+    h = C.c_void_p()
+    rc = lib.vkx_create(C.c_int(0), C.byref(h))
+    if rc == 0:
+        lib.vkx_destroy(h)
+    else:
+        assert rc == -2
+        assert b"no CPU fallback" in lib.vkx_last_error(None)
+    # the product sources never reference the oracle
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "vulkanexp_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "liboracle" not in src and "import oracle" not in src and "from oracle" not in src, os.path.join(dirpath, f)
+
+
+def test_pod_sizes_match_the_reference_layouts():
+    from vulkanexp_b200 import pods
+
+    assert pods.VERTEX_DTYPE.itemsize == 64 and pods.VERTEX_DTYPE.fields["normal"][1] == 24 and pods.VERTEX_DTYPE.fields["texCoord"][1] == 52
+    assert pods.MATERIAL_DTYPE.itemsize == 48 and pods.MATERIAL_DTYPE.fields["albedoTexture"][1] == 32
+    assert pods.OFFSET_DTYPE.itemsize == 12
+    assert C.sizeof(pods.GridInfo) == 64 and pods.GridInfo.resolution.offset == 32 and pods.GridInfo.shadowBias.offset == 56
+    assert C.sizeof(pods.Light) == 32 and C.sizeof(pods.Camera) == 144 and pods.Camera.origin.offset == 128
