@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""Benchmark of the DDGI probe update (BASELINE.json metric: probe rays/s and full-volume update ms).
+
+  python bench.py --gpus N --steps K --warmup W            the CUDA path (libvkexp_b200.so through its C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  the CPU transliteration (oracle/) on the host cores
+
+A step is one full-volume DDGI update: every probe of the volume traces raysPerProbe rays (closest hit, shading with
+sun shadow ray and two sampleProbes look-ups, or sky on a miss), blends them into both atlases with hysteresis, writes
+the border texels and publishes. N = 1 runs BASELINE.json configs[1]: 32x16x32 probes x 256 rays on the synthetic
+Sponza-scale scene (the named data/sponza_test.scene is not in the reference checkout). N > 1 is weak scaling: the
+volume becomes 32x16x(32 N) probes over the same scene, every rank traces and blends 16384 probes (z-slices
+interleaved per chunk) and all-gathers its atlas slices over NCCL.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from vulkanexp_b200 import scene_format, synth  # noqa: E402
+from vulkanexp_b200.pods import GridInfo, Light  # noqa: E402
+
+RES = (32, 16, 32)
+RAYS = 256
+NODE_BYTES, TRI_BYTES, HIT_BYTES = 80, 48, 20
+
+
+def workload_name(n):
+    return "DDGI full-volume update, synthetic sponza-scale atrium (265k triangles), %dx%dx%d probes x %d rays" % (RES[0], RES[1], RES[2] * n, RAYS)
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        busy = [x for x in sm if x > 0]
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def orientations(k):
+    """The reference's per-frame random rotations: MSVC-LCG replay of glm::sphericalRand + genBasis. Host-side harness
+    input (the C ABI takes the matrix); computed with the C++ facade's generator so the product path stays oracle-free."""
+    from vulkanexp_b200.host_logic import OrientationGenerator
+
+    gen = OrientationGenerator()
+    gen.next()  # the first draw is consumed by initProbes (reference src/IrradianceProbes.cpp:361)
+    return [gen.next() for _ in range(k)]
+
+
+def cpu_baseline(flat, grid, light, sample_probes, threads=0):
+    """Times the oracle (CPU transliteration) on a bounded sample of the same workload; also returns its traversal counters."""
+    from oracle import pyoracle
+
+    o = pyoracle.Oracle()
+    o.scene_upload(flat)
+    o.bvh_build()
+    o.probes_init(grid)
+    o.probes_upload(state=np.ones(grid.probe_count, dtype=np.uint32))
+    idx = np.linspace(0, grid.probe_count - 1, sample_probes).astype(np.uint32)
+    R = orientations(2)
+    o.probes_update(grid, light, R[0], idx, threads)  # warm-up: fills the atlases so sampleProbes does real work
+    sec = o.probes_update(grid, light, R[1], idx, threads)
+    c = o.probes_counters()
+    rays = len(idx) * grid.raysPerProbe
+    return {
+        "value": rays / sec,
+        "unit": "probe rays/s",
+        "cores": pyoracle.lib().orc_max_threads() if threads <= 0 else threads,
+        "kind": "port",
+        "sample": "%d of %d probes (evenly spaced) x %d rays, one update after one warm-up update, %.2f s" % (len(idx), grid.probe_count, grid.raysPerProbe, sec),
+    }, c, rays
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    flat = scene_format.flatten(synth.make_cfg2())
+    grid = GridInfo.make(flat["bounds_min"], flat["bounds_max"], (RES[0], RES[1], RES[2] * args.gpus), RAYS, hysteresis=0.9)
+    light = Light.default()
+    from oracle import pyoracle
+
+    o = pyoracle.Oracle()
+    o.scene_upload(flat)
+    o.bvh_build()
+    o.probes_init(grid)
+    o.probes_upload(state=np.ones(grid.probe_count, dtype=np.uint32))
+    sample = min(grid.probe_count, args.ref_sample)
+    idx = np.linspace(0, grid.probe_count - 1, sample).astype(np.uint32)
+    Rs = orientations(args.warmup + args.steps)
+    for w in range(args.warmup):
+        o.probes_update(grid, light, Rs[w], idx, 0)
+    total = 0.0
+    for s in range(args.steps):
+        total += o.probes_update(grid, light, Rs[args.warmup + s], idx, 0)
+    rays = sample * RAYS
+    value = rays * args.steps / total
+    cores = pyoracle.lib().orc_max_threads()
+    line = {
+        "impl": "reference", "metric": "ddgi_probe_rays_per_sec", "value": value, "unit": "probe rays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.gpus), "sample": "%d of %d probes per step" % (sample, grid.probe_count)},
+        "cpu_baseline": {"value": value, "unit": "probe rays/s", "cores": cores, "kind": "port",
+                         "sample": "%d of %d probes (evenly spaced) x %d rays per step; the reference itself (Vulkan RT shaders, Windows) cannot run here, so this is its CPU transliteration (oracle/)" % (sample, grid.probe_count, RAYS)},
+        "e2e": {"value": value, "unit": "probe rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "full_volume_update_ms_extrapolated": 1e3 * total / args.steps * grid.probe_count / sample,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="vkx", choices=["vkx", "reference"])
+    ap.add_argument("--ref-sample", type=int, default=1024, help="probes per step of the CPU reference arm")
+    ap.add_argument("--cpu-sample", type=int, default=2048, help="probes of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "vkx" else args.warmup
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from vulkanexp_b200._lib import Context
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = max(world, 1)
+    flat = scene_format.flatten(synth.make_cfg2())
+    grid = GridInfo.make(flat["bounds_min"], flat["bounds_max"], (RES[0], RES[1], RES[2] * n), RAYS, hysteresis=0.0)
+    light = Light.default()
+    ctx = Context(local)
+    ctx.scene_upload(flat)
+    ctx.bvh_build()
+    ctx.probes_init(grid)
+    ctx.probes_upload(state=np.ones(grid.probe_count, dtype=np.uint32))  # every probe active: the named workload traces all of them
+    if world > 1:
+        uid = [Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(rank, world, uid[0])
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    Rs = orientations(args.warmup + args.steps + args.steps)
+    probes_per_rank = grid.probe_count // n
+    rays_per_step_total = grid.probe_count * RAYS
+
+    def step(i, hyst):
+        grid.hysteresis = hyst
+        if world > 1:
+            ctx.probes_update_sharded(grid, light, Rs[i], sync=False)
+        else:
+            ctx.probes_update(grid, light, Rs[i], None, sync=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.sync()
+
+    hyst = 0.0
+    for w in range(args.warmup):
+        step(w, hyst); hyst = min(0.98, hyst + 0.25)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start(); time.sleep(0.3)
+    launches0 = ctx.launch_count()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    kt = {"trace_primary": 0.0, "shade": 0.0, "trace_shadow": 0.0, "blend": 0.0}
+    shadow_rays = 0
+    barrier()
+    for s in range(args.steps):
+        with torch.cuda.stream(stream):
+            flush.fill_(s & 0xFF)  # evict L2 between timed iterations (not timed)
+        starts[s].record(stream)
+        step(args.warmup + s, hyst)
+        ends[s].record(stream)
+        k = ctx.probes_kernel_timings()  # syncs; per-kernel CUDA events recorded inside the library on its launch stream
+        for name in kt:
+            kt[name] += k[name]
+        shadow_rays = k["shadow_rays"]
+    barrier()
+    launches = ctx.launch_count() - launches0
+    step_ms = [a.elapsed_time(b) for a, b in zip(starts, ends)]
+    total_ms = float(sum(step_ms))
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = rays_per_step_total / (ms_per_step * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers: H2D of the to-update list + parameters, D2H of both atlases and the states
+    (ih, iw), (dh, dw) = grid.atlas_shapes()
+    pin_irr = torch.empty((ih, iw), dtype=torch.int32).pin_memory(); pin_dep = torch.empty((dh, dw), dtype=torch.int32).pin_memory(); pin_st = torch.empty(grid.probe_count, dtype=torch.int32).pin_memory()
+    out = (pin_irr.numpy().view(np.uint32), pin_dep.numpy().view(np.uint32), pin_st.numpy().view(np.uint32))
+    pin_idx = torch.arange(grid.probe_count, dtype=torch.int32).pin_memory()
+    idx_np = pin_idx.numpy().view(np.uint32)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        grid.hysteresis = hyst
+        if world > 1:
+            ctx.probes_update_sharded(grid, light, Rs[args.warmup + args.steps + s], sync=False)
+        else:
+            ctx.probes_update(grid, light, Rs[args.warmup + args.steps + s], idx_np, sync=False)
+        ctx.probes_download(out=out)  # synchronous D2H of the step's result
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    if world > 1:
+        t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    h2d = (grid.probe_count * 4 if world == 1 else 0) + 64 + 32 + 64 + RAYS * 16
+    d2h = pin_irr.numel() * 4 + pin_dep.numel() * 4 + pin_st.numel() * 4
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        line = {
+            "metric": "ddgi_probe_rays_per_sec", "value": value, "unit": "probe rays/s", "n_gpus": n, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(n), "probes_per_gpu": probes_per_rank, "rays_per_probe": RAYS, "l2": "256 MiB buffer written between timed steps (flush, untimed)",
+                       "parallelism": "probe z-slices x%d, NCCL all-gather of atlas slices" % n if n > 1 else "single GPU"},
+            "full_volume_update_ms": ms_per_step, "grays_per_sec_per_gpu": value / n / 1e9,
+            "gpu_launches": int(launches), "clocks": clocks,
+            "e2e": {"value": rays_per_step_total / (e2e_ms * 1e-3), "unit": "probe rays/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "what": "vkx_probes_update from host buffers + vkx_probes_download of both atlases and the state words into pinned host memory, every step"},
+            "kernel_ms": {k: v / args.steps for k, v in kt.items()},
+        }
+        if not args.no_cpu_baseline:
+            cb, ctr, sample_rays = cpu_baseline(flat, grid, light, min(args.cpu_sample, grid.probe_count))
+            line["cpu_baseline"] = cb
+            # roofline of the dominant kernel (k_trace_primary): algorithmic bytes per primary ray from the oracle's traversal
+            # counters on the sample (mean 80-byte nodes + 48-byte triangles fetched per ray) + the 20-byte hit record
+            nodes_per_ray = ctr["nodes"] / ctr["rays"]; tris_per_ray = ctr["tris"] / ctr["rays"]
+            b_ray = nodes_per_ray * NODE_BYTES + tris_per_ray * TRI_BYTES + HIT_BYTES
+            dom = max(kt, key=kt.get)
+            rays_launch = probes_per_rank * RAYS if dom != "trace_shadow" else shadow_rays
+            per_unit = {"trace_primary": b_ray, "trace_shadow": b_ray, "shade": 16 + HIT_BYTES + ctr["front"] / sample_rays * (12 + 12 + 36 + 48 + 36 + 512 + 32), "blend": (RAYS * 16 + (36 + 196) * 4 * 2 + (28 + 60) * 4) / RAYS}[dom]
+            achieved = per_unit * rays_launch / (kt[dom] / args.steps * 1e-3) / 1e9
+            line["roofline"] = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                                "peak_source": peak_src, "bytes_per_ray": per_unit, "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,
+                                "front_hit_fraction": ctr["front"] / sample_rays}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

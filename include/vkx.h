@@ -185,6 +185,9 @@ int vkx_probes_download_hits(vkx_ctx* ctx, vkx_hit* hits, uint8_t* shadow);
 /* getComputeTimes/TraceTimes/UpdateTimes/BorderCopyTimes/CopyTimes (src/IrradianceProbes.hpp:68-72), last update:
  * ms[0] full, ms[1] trace+shade, ms[2] blend (+borders, fused), ms[3] border (0: fused), ms[4] publish. Syncs. */
 int vkx_probes_timings(vkx_ctx* ctx, float ms[5]);
+/* Device time of the four kernels of the first chunk of the last update: ms[0] k_trace_primary, ms[1] k_shade,
+ * ms[2] k_trace_shadow, ms[3] k_blend; *probes = probes in that chunk, *shadowRays = shadow rays of the last chunk. Syncs. */
+int vkx_probes_kernel_timings(vkx_ctx* ctx, float ms[4], uint32_t* probes, uint32_t* shadowRays);
 /* Device pointers for zero-copy consumers (e.g. torch tensors over the sampled atlases). */
 int vkx_probes_device_ptrs(vkx_ctx* ctx, void** irradiance, void** depth, void** state);
 
@@ -216,6 +219,14 @@ int vkx_shadow_download_debug(vkx_ctx* ctx, float* dirs4, uint8_t* mask);
 int vkx_shadow_reset_history(vkx_ctx* ctx);
 /* ms[0] full, ms[1] trace, ms[2] filter X, ms[3] filter Y. */
 int vkx_shadow_timings(vkx_ctx* ctx, float ms[4]);
+
+/* ---- host logic of IrradianceProbes.cpp (pure CPU helpers, no device work) ------------------------------------------ */
+/* The per-frame random orientation push constant: glm::sphericalRand(1) + genBasis -> mat4(transpose(mat3(X, Y, Z)))
+ * (src/IrradianceProbes.cpp:347-355, 455-460). *rngState is the MSVC rand() state; the reference never seeds it: start at 1. */
+void vkx_host_next_orientation(uint32_t* rngState, float orientation[16]);
+/* selectProbesToUpdate (src/IrradianceProbes.cpp:396-424). loopIndex / lastUpdateOffset are the function's statics. */
+uint32_t vkx_host_select_probes(uint32_t* loopIndex, uint32_t* lastUpdateOffset, const uint32_t* state, uint32_t probeCount,
+                                uint32_t probesPerUpdate, uint32_t* out);
 
 /* Kernel launch counter since context creation (bench.py's gpu_launches claim). */
 uint64_t vkx_launch_count(vkx_ctx* ctx);

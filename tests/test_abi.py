@@ -59,3 +59,21 @@ def test_pod_sizes_match_the_reference_layouts():
     assert pods.OFFSET_DTYPE.itemsize == 12
     assert C.sizeof(pods.GridInfo) == 64 and pods.GridInfo.resolution.offset == 32 and pods.GridInfo.shadowBias.offset == 56
     assert C.sizeof(pods.Light) == 32 and C.sizeof(pods.Camera) == 144 and pods.Camera.origin.offset == 128
+
+
+def test_host_logic_matches_oracle_and_glm_pin(oracle_lib):
+    """The product's own host logic (csrc/host/HostLogic.cpp) is a second implementation: it must agree bit for bit with
+    the oracle's and with the GLM-generated fixture."""
+    import json
+    import numpy as np
+    from vulkanexp_b200.host_logic import OrientationGenerator, ProbeScheduler
+
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "glm_pin.json")))
+    gen = OrientationGenerator()
+    for e in gold:
+        assert gen.next().view(np.uint32).tolist() == e["M"]
+    rng = np.random.default_rng(9)
+    state = rng.choice([0, 1, 2, 5, 8], size=301).astype(np.uint32)
+    a, b = ProbeScheduler(), oracle_lib.HostLogic()
+    for per in (0, 40, 40, 0, 3, 0):
+        assert a.select(state, per).tolist() == b.select(state, per).tolist()

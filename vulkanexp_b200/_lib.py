@@ -166,6 +166,12 @@ class Context:
         self._check(self.l.vkx_probes_timings(self.h, ms))
         return {"full": ms[0], "trace": ms[1], "blend": ms[2], "border": ms[3], "publish": ms[4]}
 
+    def probes_kernel_timings(self):
+        ms = (C.c_float * 4)()
+        probes, shadow = C.c_uint32(0), C.c_uint32(0)
+        self._check(self.l.vkx_probes_kernel_timings(self.h, ms, C.byref(probes), C.byref(shadow)))
+        return {"trace_primary": ms[0], "shade": ms[1], "trace_shadow": ms[2], "blend": ms[3], "probes": probes.value, "shadow_rays": shadow.value}
+
     def probes_device_ptrs(self):
         a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
         self._check(self.l.vkx_probes_device_ptrs(self.h, C.byref(a), C.byref(b), C.byref(c)))

@@ -47,6 +47,7 @@ int vkx_create(int device, vkx_ctx** out) {
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return vkx_fail(nullptr, VKX_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
     for (auto& ev : ctx->sev) cudaEventCreate(&ev);
+    for (auto& ev : ctx->kev) cudaEventCreate(&ev);
     *out = ctx;
     return VKX_OK;
 }
@@ -78,6 +79,7 @@ void vkx_destroy(vkx_ctx* ctx) {
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->sev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->kev) if (ev) cudaEventDestroy(ev);
     if (ctx->commStream) cudaStreamDestroy(ctx->commStream);
     if (ctx->commEvent) cudaEventDestroy(ctx->commEvent);
     cudaStreamDestroy(ctx->stream);
@@ -358,6 +360,18 @@ int vkx_probes_timings(vkx_ctx* ctx, float ms[5]) {
     CUDA_TRY(ctx, cudaEventElapsedTime(&ms[2], ctx->ev[1], ctx->ev[2]));
     ms[3] = 0.f; // borders are written by the blend kernel
     CUDA_TRY(ctx, cudaEventElapsedTime(&ms[4], ctx->ev[2], ctx->ev[3]));
+    return VKX_OK;
+}
+
+int vkx_probes_kernel_timings(vkx_ctx* ctx, float ms[4], uint32_t* probes, uint32_t* shadowRays) {
+    BIND(ctx);
+    if (!ms) return VKX_E_INVALID;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 4; ++i) ms[i] = 0.f;
+    if (!ctx->lastCount) return VKX_OK;
+    for (int i = 0; i < 4; ++i) CUDA_TRY(ctx, cudaEventElapsedTime(&ms[i], ctx->kev[i], ctx->kev[i + 1]));
+    if (probes) *probes = ctx->kevProbes;
+    if (shadowRays) CUDA_TRY(ctx, cudaMemcpy(shadowRays, ctx->dQueueCount, 4, cudaMemcpyDeviceToHost)); // queue length of the last chunk
     return VKX_OK;
 }
 

@@ -78,7 +78,8 @@ struct vkx_ctx {
     bool debugBuffers = false;
     uint32_t lastCount = 0, lastRays = 0;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    float traceMsAcc = 0.f;
+    cudaEvent_t kev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // per-kernel timing of chunk 0
+    uint32_t kevProbes = 0, kevShadowRays = 0;
 
     // multi-GPU
     ncclComm* comm = nullptr; int rank = 0, nranks = 1;

@@ -350,12 +350,18 @@ int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* /*unused*/,
         const uint32_t* idx = ctx->dIndicesList + listOffset + base;
         TraceParams tp; tp.grid = ctx->grid; tp.tmin = 0.01f; tp.tmax = tmax; tp.raysPerProbe = N; tp.numRays = numRays;
         ShadeParams sp; sp.grid = ctx->grid; sp.light = light; sp.raysPerProbe = N; sp.numRays = numRays;
+        const bool timed = base == 0; // per-kernel events on the first chunk
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->dQueueCount, 0, 4, st));
+        if (timed) { CUDA_TRY(ctx, cudaEventRecord(ctx->kev[0], st)); ctx->kevProbes = n; }
         k_trace_primary<<<divUp(numRays, 128), 128, 0, st>>>(sc, tp, idx, ctx->dDirs, ctx->dHits); LAUNCH_CHECK(ctx);
+        if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[1], st));
         k_shade<<<divUp(numRays, 128), 128, 0, st>>>(sc, pr, sp, idx, ctx->dDirs, ctx->dHits, ctx->dRays, ctx->dShadowQueue, ctx->dQueueCount, ctx->debugBuffers ? ctx->dShadowFlags : nullptr); LAUNCH_CHECK(ctx);
+        if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[2], st));
         k_trace_shadow<<<divUp(numRays, 128), 128, 0, st>>>(sc, light, ctx->dShadowQueue, ctx->dQueueCount, ctx->dRays, ctx->debugBuffers ? ctx->dShadowFlags : nullptr); LAUNCH_CHECK(ctx);
+        if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[3], st));
         if (base + n >= count) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], st));
         k_blend<<<n, 256, 0, st>>>(bp, pr, idx, ctx->dRays, ctx->dDirs, ctx->debugBuffers ? ctx->dIrrUnpacked : nullptr, ctx->debugBuffers ? ctx->dDepUnpacked : nullptr, base); LAUNCH_CHECK(ctx);
+        if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[4], st));
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], st));
     ctx->lastCount = count; ctx->lastRays = count * N;

@@ -1,0 +1,66 @@
+#include "Renderer.hpp"
+#include <algorithm>
+
+namespace vkx {
+
+void check(vkx_ctx* ctx, int rc) {
+    if (rc != VKX_OK) throw Error(rc, std::string("vkx error ") + std::to_string(rc) + ": " + vkx_last_error(ctx));
+}
+
+Device::Device(int index) {
+    int rc = vkx_create(index, &_ctx);
+    if (rc != VKX_OK) throw Error(rc, std::string("vkx_create: ") + vkx_last_error(nullptr));
+}
+Device::~Device() { vkx_destroy(_ctx); }
+
+void Renderer::allocateMeshes() {
+    Vertices.clear(); Indices.clear(); OffsetTable.clear(); MeshIndexCounts.clear();
+    uint32_t vo = 0, io = 0;
+    for (Mesh& m : _scene->getMeshes()) {
+        if (!m.isValid()) continue; // invalid meshes are skipped (reference src/Renderer.cpp:103-105)
+        m.indexIntoOffsetTable = uint32_t(OffsetTable.size());
+        OffsetTable.push_back(OffsetEntry{m.defaultMaterialIndex, vo, io});
+        MeshIndexCounts.push_back(uint32_t(m.indices.size()));
+        Vertices.insert(Vertices.end(), m.vertices.begin(), m.vertices.end());
+        Indices.insert(Indices.end(), m.indices.begin(), m.indices.end());
+        vo += uint32_t(m.vertices.size()); io += uint32_t(m.indices.size());
+    }
+}
+
+void Renderer::createTLAS() {
+    // sortRenderers: by (materialIndex, meshIndex), entity order as the final key (reference src/Renderer.cpp:512-523)
+    struct R { uint32_t material, mesh; int entity; };
+    std::vector<R> rs;
+    const auto& nodes = _scene->getNodes();
+    for (size_t i = 0; i < nodes.size(); ++i) if (nodes[i].hasMeshRenderer) rs.push_back(R{nodes[i].materialIndex, nodes[i].meshIndex, int(i)});
+    std::stable_sort(rs.begin(), rs.end(), [](const R& a, const R& b) { return a.material == b.material ? a.mesh < b.mesh : a.material < b.material; });
+    _instances.clear();
+    for (const R& r : rs) {
+        const Mesh& mesh = _scene->getMeshes().at(r.mesh);
+        if (!mesh.isValid()) continue;
+        vkx_instance inst{};
+        const mat4& g = nodes[size_t(r.entity)].globalTransform; // column-major -> row-major 3x4 (VkTransformMatrixKHR)
+        for (int row = 0; row < 3; ++row) for (int col = 0; col < 4; ++col) inst.transform[4 * row + col] = g.m[col][row];
+        inst.meshEntry = mesh.indexIntoOffsetTable;
+        inst.mask = VKX_INSTANCE_STATIC;
+        _instances.push_back(inst);
+    }
+}
+
+void Renderer::createAccelerationStructures() {
+    createTLAS();
+    std::vector<vkx_material> mats;
+    for (const auto& m : _scene->getMaterials()) mats.push_back(m.properties);
+    vkx_ctx* ctx = _device->ctx();
+    check(ctx, vkx_scene_upload(ctx, Vertices.data(), Vertices.size(), Indices.data(), Indices.size(), OffsetTable.data(), MeshIndexCounts.data(), OffsetTable.size(),
+                                mats.data(), mats.size(), _instances.data(), _instances.size()));
+    check(ctx, vkx_bvh_build(ctx));
+}
+
+vkx_bvh_info Renderer::getTLAS() const {
+    vkx_bvh_info info{};
+    check(_device->ctx(), vkx_bvh_info_get(_device->ctx(), &info));
+    return info;
+}
+
+} // namespace vkx

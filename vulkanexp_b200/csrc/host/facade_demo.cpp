@@ -1,0 +1,39 @@
+// Drives the C++ facade the way Editor::run / initVulkan / mainLoop drive the reference classes:
+//   vkx_facade_demo <scene.scene> <rx> <ry> <rz> <raysPerProbe> <frames> <out.bin>
+// Writes irradiance, depth and state arrays (u32) to out.bin so tests can compare them with the C-ABI path.
+#include <cstdio>
+#include <cstdlib>
+#include "IrradianceProbes.hpp"
+
+int main(int argc, char** argv) {
+    if (argc < 8) { std::fprintf(stderr, "usage: %s scene rx ry rz rays frames out.bin\n", argv[0]); return 2; }
+    try {
+        vkx::Scene scene;
+        if (!scene.load(argv[1])) return 1;
+        scene.update(); // the first Scene::update of the main loop (propagates transforms)
+        vkx::Device device(0);
+        vkx::Renderer renderer; renderer.setDevice(device); renderer.setScene(scene);
+        renderer.allocateMeshes();
+        renderer.createAccelerationStructures();
+        vkx::LightBuffer light;
+        vkx::IrradianceProbes probes;
+        probes.GridParameters.resolution[0] = std::atoi(argv[2]); probes.GridParameters.resolution[1] = std::atoi(argv[3]); probes.GridParameters.resolution[2] = std::atoi(argv[4]);
+        probes.GridParameters.raysPerProbe = unsigned(std::atoi(argv[5]));
+        probes.init(device, scene.getBounds().min, scene.getBounds().max);
+        probes.createPipeline();
+        probes.writeDescriptorSet(renderer, light);
+        probes.initProbes();
+        const int frames = std::atoi(argv[6]);
+        for (int f = 0; f < frames; ++f) probes.update();
+        std::vector<uint32_t> irr, dep, st;
+        probes.download(irr, dep, st);
+        FILE* fp = std::fopen(argv[7], "wb");
+        if (!fp) return 1;
+        std::fwrite(irr.data(), 4, irr.size(), fp); std::fwrite(dep.data(), 4, dep.size(), fp); std::fwrite(st.data(), 4, st.size(), fp);
+        std::fclose(fp);
+        auto info = renderer.getTLAS();
+        std::printf("facade ok: %u nodes, %u triangles, last update %u probes, hysteresis %.4f, compute %.3f ms\n", info.numNodes, info.numTriangles, probes.lastUpdatedProbeCount(),
+                    probes.GridParameters.hysteresis, probes.getComputeTimes().last());
+    } catch (const std::exception& e) { std::fprintf(stderr, "error: %s\n", e.what()); return 1; }
+    return 0;
+}
