@@ -176,6 +176,7 @@ int orc_shadow_download(orc_ctx* c, int stage, float* rgba, float* dirs, uint8_t
     if (mask) std::memcpy(mask, c->shadow.mask.data(), c->shadow.mask.size());
     return 0;
 }
+int orc_shadow_set_history(orc_ctx* c, const float* rgba) { std::memcpy(c->shadow.final_.data(), rgba, c->shadow.final_.size() * 4); return 0; }
 int orc_shadow_reset_history(orc_ctx* c) {
     std::fill(c->shadow.final_.begin(), c->shadow.final_.end(), 0.0f); std::fill(c->shadow.previous.begin(), c->shadow.previous.end(), 0.0f); return 0;
 }

@@ -170,6 +170,10 @@ class Oracle:
         self.l.orc_shadow_download(self.h, C.c_int(stage), _p(img), _p(dirs), _p(mask))
         return img, dirs, mask
 
+    def shadow_set_history(self, img):
+        img = np.ascontiguousarray(img, dtype=np.float32)
+        self.l.orc_shadow_set_history(self.h, _p(img))
+
     def shadow_reset_history(self):
         self.l.orc_shadow_reset_history(self.h)
 
