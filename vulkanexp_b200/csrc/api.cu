@@ -54,10 +54,12 @@ int vkx_create(int device, vkx_ctx** out) {
 
 static void freeProbes(vkx_ctx* ctx) {
     void* ptrs[] = {ctx->dIrrWork, ctx->dIrrSampled, ctx->dDepWork, ctx->dDepSampled, ctx->dStateWork, ctx->dStateSampled, ctx->dIndicesList, ctx->dDirs, ctx->dRays,
-                    ctx->dHits, ctx->dShadowQueue, ctx->dQueueCount, ctx->dShadowFlags, ctx->dIrrUnpacked, ctx->dDepUnpacked, ctx->dIrrNext, ctx->dDepNext, ctx->dStateNext};
+                    ctx->dHits, ctx->dShadowQueue, ctx->dQueueCount, ctx->dShadowFlags, ctx->dIrrUnpacked, ctx->dDepUnpacked, ctx->dIrrNext, ctx->dDepNext, ctx->dStateNext,
+                    ctx->dPerm, ctx->dOrder, ctx->dBlockedOrder, ctx->dBlendW};
     for (void* p : ptrs) if (p) cudaFree(p);
     ctx->dIrrWork = ctx->dIrrSampled = ctx->dDepWork = ctx->dDepSampled = ctx->dStateWork = ctx->dStateSampled = ctx->dIndicesList = nullptr;
     ctx->dIrrNext = ctx->dDepNext = ctx->dStateNext = nullptr;
+    ctx->dPerm = ctx->dOrder = ctx->dBlockedOrder = nullptr; ctx->dBlendW = nullptr; ctx->shardOrderReady = false;
     ctx->dDirs = nullptr; ctx->dRays = nullptr; ctx->dHits = nullptr; ctx->dShadowQueue = nullptr; ctx->dQueueCount = nullptr; ctx->dShadowFlags = nullptr;
     ctx->dIrrUnpacked = ctx->dDepUnpacked = nullptr;
     ctx->probesReady = false;
@@ -82,6 +84,7 @@ void vkx_destroy(vkx_ctx* ctx) {
     for (auto& ev : ctx->kev) if (ev) cudaEventDestroy(ev);
     if (ctx->commStream) cudaStreamDestroy(ctx->commStream);
     if (ctx->commEvent) cudaEventDestroy(ctx->commEvent);
+    if (ctx->hStage) { cudaFreeHost(ctx->hStage); for (auto& e : ctx->stageEvent) if (e) cudaEventDestroy(e); }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -219,6 +222,26 @@ int vkx_probes_init(vkx_ctx* ctx, const vkx_grid_info* grid) {
     CUDA_TRY(ctx, cudaMalloc(&ctx->dIndicesList, stBytes));
     CUDA_TRY(ctx, cudaMalloc(&ctx->dDirs, 512 * sizeof(float4)));
     CUDA_TRY(ctx, cudaMalloc(&ctx->dQueueCount, 4));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->dPerm, VKX_MAX_RAYS_PER_PROBE * 4));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->dOrder, stBytes));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->dBlockedOrder, stBytes));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->dBlendW, size_t(VKX_MAX_RAYS_PER_PROBE) * 288 * 4));
+    { // rank of every probe in 2x2x2-block order (scheduling only: which probes share a warp)
+        const uint32_t rx = uint32_t(grid->resolution[0]), ry = uint32_t(grid->resolution[1]);
+        const uint32_t nbx = (rx + 1) / 2, nby = (ry + 1) / 2;
+        std::vector<std::pair<uint64_t, uint32_t>> keys(ctx->probeCount);
+        for (uint32_t p = 0; p < ctx->probeCount; ++p) {
+            const uint32_t ix = p % rx, iy = (p % (rx * ry)) / rx, iz = p / (rx * ry);
+            const uint64_t block = (ix >> 1) + uint64_t(nbx) * ((iy >> 1) + uint64_t(nby) * (iz >> 1));
+            keys[p] = {(block << 3) | ((iz & 1u) << 2) | ((iy & 1u) << 1) | (ix & 1u), p};
+        }
+        std::sort(keys.begin(), keys.end());
+        ctx->hBlockRank.assign(ctx->probeCount, 0);
+        std::vector<uint32_t> order(ctx->probeCount);
+        for (uint32_t r = 0; r < ctx->probeCount; ++r) { ctx->hBlockRank[keys[r].second] = r; order[r] = keys[r].second; }
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dBlockedOrder, order.data(), stBytes, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     // One chunk holds at most 32768 probes (8.4 M rays: 128 MiB of ray records) so the ray-level scratch stays L2-sized
     // relative to the atlases; debug buffers force a single chunk.
     ctx->chunkProbes = ctx->debugBuffers ? ctx->probeCount : std::min<uint32_t>(ctx->probeCount, 32768u);
@@ -275,9 +298,44 @@ static int uploadFrameInputs(vkx_ctx* ctx, const vkx_grid_info* grid, const floa
     const uint32_t N = grid->raysPerProbe;
     float dirs[VKX_MAX_RAYS_PER_PROBE * 3];
     rayDirections(orientation, N, float(N), dirs);
-    float4 d4[VKX_MAX_RAYS_PER_PROBE];
+    // pinned staging, 4 slots in rotation so that frames can be queued without waiting for the previous one
+    if (!ctx->hStage) { CUDA_TRY(ctx, cudaMallocHost(&ctx->hStage, 4 * sizeof(vkx_ctx::FrameStage))); for (auto& e : ctx->stageEvent) CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); }
+    const int slot = int(ctx->stageCursor++ & 3u);
+    if (ctx->stageUsed[slot]) CUDA_TRY(ctx, cudaEventSynchronize(ctx->stageEvent[slot]));
+    vkx_ctx::FrameStage& fs = ctx->hStage[slot];
+    float4* d4 = fs.dirs;
     for (uint32_t i = 0; i < N; ++i) d4[i] = make_float4(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2], 1.0f);
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dDirs, d4, N * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    // direction order of the frame: Morton curve over the octahedral map, so 4 consecutive entries are neighbours on the sphere
+    std::pair<uint32_t, uint32_t> keys[VKX_MAX_RAYS_PER_PROBE];
+    for (uint32_t i = 0; i < N; ++i) {
+        const float x = dirs[3 * i], y = dirs[3 * i + 1], z = dirs[3 * i + 2];
+        const float l1 = std::fabs(x) + std::fabs(y) + std::fabs(z);
+        float u = l1 > 0.f ? x / l1 : 0.f, v = l1 > 0.f ? y / l1 : 0.f;
+        if (z < 0.f) { const float uu = (1.0f - std::fabs(v)) * (u >= 0.f ? 1.f : -1.f), vv = (1.0f - std::fabs(u)) * (v >= 0.f ? 1.f : -1.f); u = uu; v = vv; }
+        uint32_t qx = uint32_t(std::min(std::max((u * 0.5f + 0.5f) * 65535.0f, 0.0f), 65535.0f)), qy = uint32_t(std::min(std::max((v * 0.5f + 0.5f) * 65535.0f, 0.0f), 65535.0f));
+        auto spread = [](uint32_t a) { a = (a | (a << 8)) & 0x00FF00FFu; a = (a | (a << 4)) & 0x0F0F0F0Fu; a = (a | (a << 2)) & 0x33333333u; a = (a | (a << 1)) & 0x55555555u; return a; };
+        keys[i] = {spread(qx) | (spread(qy) << 1), i};
+    }
+    std::sort(keys, keys + N);
+    uint32_t* perm = fs.perm;
+    for (uint32_t i = 0; i < N; ++i) perm[i] = keys[i].second;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dPerm, perm, N * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->stageEvent[slot], ctx->stream));
+    ctx->stageUsed[slot] = true;
+    return VKX_OK;
+}
+
+// position -> slot order for a host-provided to-update list: slots sorted by the 2x2x2-block rank of their probe (O(P))
+static int uploadOrder(vkx_ctx* ctx, const uint32_t* probeIndices, uint32_t count, uint32_t listOffset) {
+    std::vector<uint32_t>& mark = ctx->hMark; std::vector<uint32_t>& order = ctx->hOrder;
+    mark.assign(ctx->probeCount, 0u); order.resize(count);
+    bool dup = false;
+    for (uint32_t s = 0; s < count; ++s) { uint32_t& m = mark[ctx->hBlockRank[probeIndices[s]]]; if (m) dup = true; m = s + 1; }
+    if (dup) { for (uint32_t s = 0; s < count; ++s) order[s] = s; }
+    else { uint32_t n = 0; for (uint32_t r = 0; r < ctx->probeCount; ++r) if (mark[r]) order[n++] = mark[r] - 1; }
+    // pageable source: cudaMemcpyAsync stages it before returning, and the vector is owned by the context
+    if (count) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dOrder + listOffset, order.data(), size_t(count) * 4, cudaMemcpyHostToDevice, ctx->stream));
     return VKX_OK;
 }
 
@@ -292,10 +350,13 @@ int vkx_probes_update(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx_light* 
         if (count > ctx->probeCount) return vkx_fail(ctx, VKX_E_INVALID, "more indices than probes");
         for (uint32_t i = 0; i < count; ++i) if (probeIndices[i] >= ctx->probeCount) return vkx_fail(ctx, VKX_E_INVALID, "probe index %u out of range", probeIndices[i]);
         if (count) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dIndicesList, probeIndices, size_t(count) * 4, cudaMemcpyHostToDevice, ctx->stream));
+        TRY(uploadOrder(ctx, probeIndices, count, 0));
     } else {
         count = ctx->probeCount;
         k_iota_list<<<divUp(count, 256), 256, 0, ctx->stream>>>(ctx->dIndicesList, 0, count); LAUNCH_CHECK(ctx);
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dOrder, ctx->dBlockedOrder, size_t(count) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     }
+    ctx->shardOrderReady = false;
     TRY(ddgiUpdate(ctx, *light, nullptr, count, 0, false));
     TRY(ddgiPublish(ctx, count));
     ctx->shardedLast = false;
@@ -431,6 +492,7 @@ int vkx_probes_update_sharded(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx
         const uint32_t z0 = k * s * n + uint32_t(ctx->rank) * s;
         const uint32_t first = z0 * plane, count = s * plane;
         k_iota_list<<<divUp(count, 256), 256, 0, st>>>(ctx->dIndicesList + total, first, count); LAUNCH_CHECK(ctx);
+        if (!ctx->shardOrderReady) { std::vector<uint32_t> idx(count); for (uint32_t i = 0; i < count; ++i) idx[i] = first + i; TRY(uploadOrder(ctx, idx.data(), count, total)); }
         TRY(ddgiUpdate(ctx, *light, nullptr, count, total, false));
         total += count;
         CUDA_TRY(ctx, cudaEventRecord(ctx->commEvent, st));
@@ -444,6 +506,7 @@ int vkx_probes_update_sharded(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx
         if (r == ncclSuccess) r = ncclGroupEnd();
         if (r != ncclSuccess) return vkx_fail(ctx, VKX_E_NCCL, "ncclAllGather: %s", ncclGetErrorString(r));
     }
+    ctx->shardOrderReady = true;
     CUDA_TRY(ctx, cudaEventRecord(ctx->commEvent, cs));
     CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->commEvent, 0));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], st));

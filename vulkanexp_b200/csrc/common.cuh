@@ -68,6 +68,14 @@ struct vkx_ctx {
     uint32_t *dIrrWork = nullptr, *dIrrSampled = nullptr, *dDepWork = nullptr, *dDepSampled = nullptr, *dStateWork = nullptr, *dStateSampled = nullptr;
     uint32_t* dIndicesList = nullptr;   // to-update list [probeCount]
     float4* dDirs = nullptr;            // rotated ray directions [512]
+    uint32_t* dPerm = nullptr;          // direction sort permutation of the frame [256]
+    uint32_t* dOrder = nullptr;         // [probeCount] position -> slot of the to-update list (2x2x2 probe blocks)
+    uint32_t* dBlockedOrder = nullptr;  // cached order for the full-volume list
+    float* dBlendW = nullptr;           // per-frame blend weight table [256][288]
+    std::vector<uint32_t> hBlockRank;   // probe linear index -> rank in 2x2x2-block order
+    std::vector<uint32_t> hMark, hOrder; // scratch of uploadOrder
+    struct FrameStage { float4 dirs[VKX_MAX_RAYS_PER_PROBE]; uint32_t perm[VKX_MAX_RAYS_PER_PROBE]; };
+    FrameStage* hStage = nullptr; cudaEvent_t stageEvent[4] = {nullptr, nullptr, nullptr, nullptr}; bool stageUsed[4] = {false, false, false, false}; uint32_t stageCursor = 0;
     uint32_t chunkProbes = 0;           // probes traced per chunk
     float4* dRays = nullptr;            // [chunkProbes][N] (rgb, depth)
     vkx_hit* dHits = nullptr;           // [chunkProbes][N]
@@ -85,7 +93,7 @@ struct vkx_ctx {
     ncclComm* comm = nullptr; int rank = 0, nranks = 1;
     cudaStream_t commStream = nullptr; cudaEvent_t commEvent = nullptr;
     uint32_t *dIrrNext = nullptr, *dDepNext = nullptr, *dStateNext = nullptr; // all-gather targets (sharded update)
-    bool shardedLast = false;
+    bool shardedLast = false, shardOrderReady = false;
 
     // shadows
     float* dNoise = nullptr; uint32_t noiseW = 0, noiseH = 0, noiseSlices = 0;

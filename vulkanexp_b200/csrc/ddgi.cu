@@ -15,17 +15,36 @@
 
 namespace {
 
+// Thread -> ray mapping shared by the trace and shade kernels. A warp handles a tile of 8 probes x 4 directions: the 8 probes are
+// a 2x2x2 block of the grid (`order` lists slots block by block) and the 4 directions are neighbours on the sphere (`perm`
+// sorts the frame's direction table along a Morton curve of the octahedral map). Rays of a warp are then near-parallel with
+// nearby origins, instead of 32 consecutive spherical-Fibonacci directions of one probe. Results are stored by (slot, ray), so
+// the mapping changes scheduling only.
+struct RayMap {
+    uint32_t count, raysPerProbe, numDirGroups, numThreads;
+    const uint32_t* order; // [count] position -> slot
+    const uint32_t* perm;  // [raysPerProbe] position -> ray index
+};
+__device__ __forceinline__ bool mapRay(const RayMap& m, uint32_t t, uint32_t& slot, uint32_t& ray) {
+    const uint32_t tile = t >> 5, lane = t & 31u;
+    const uint32_t pg = tile / m.numDirGroups, dg = tile - pg * m.numDirGroups;
+    const uint32_t j = pg * 8u + (lane & 7u), k = dg * 4u + (lane >> 3);
+    if (j >= m.count || k >= m.raysPerProbe) return false;
+    slot = __ldg(m.order + j); ray = __ldg(m.perm + k);
+    return true;
+}
+
 struct TraceParams {
     vkx_grid_info grid;
     float tmin, tmax;
     uint32_t raysPerProbe, numRays; // numRays = chunk probes * raysPerProbe
 };
 
-__global__ void __launch_bounds__(128) k_trace_primary(DeviceScene sc, TraceParams tp, const uint32_t* __restrict__ probeIndices,
+__global__ void __launch_bounds__(128) k_trace_primary(DeviceScene sc, TraceParams tp, RayMap rm, const uint32_t* __restrict__ probeIndices,
                                                        const float4* __restrict__ dirs, vkx_hit* __restrict__ hits) {
-    const uint32_t ri = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ri >= tp.numRays) return;
-    const uint32_t slot = ri / tp.raysPerProbe, ray = ri - slot * tp.raysPerProbe;
+    uint32_t slot, ray;
+    if (!mapRay(rm, blockIdx.x * blockDim.x + threadIdx.x, slot, ray)) return;
+    const uint32_t ri = slot * tp.raysPerProbe + ray;
     int ix, iy, iz; probeGridIndex(__ldg(probeIndices + slot), tp.grid, ix, iy, iz);
     const v3 o = probeWorldPos(ix, iy, iz, tp.grid);
     const float4 d = __ldg(dirs + ray);
@@ -42,12 +61,12 @@ struct ShadeParams {
     uint32_t raysPerProbe, numRays;
 };
 
-__global__ void __launch_bounds__(128) k_shade(DeviceScene sc, DeviceProbes pr, ShadeParams sp, const uint32_t* __restrict__ probeIndices,
+__global__ void __launch_bounds__(128) k_shade(DeviceScene sc, DeviceProbes pr, ShadeParams sp, RayMap rm, const uint32_t* __restrict__ probeIndices,
                                                const float4* __restrict__ dirs, const vkx_hit* __restrict__ hits, float4* __restrict__ rays,
                                                float4* __restrict__ queue, uint32_t* __restrict__ queueCount, uint8_t* __restrict__ shadowFlags) {
-    const uint32_t ri = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ri >= sp.numRays) return;
-    const uint32_t slot = ri / sp.raysPerProbe, ray = ri - slot * sp.raysPerProbe;
+    uint32_t slot, ray;
+    if (!mapRay(rm, blockIdx.x * blockDim.x + threadIdx.x, slot, ray)) return;
+    const uint32_t ri = slot * sp.raysPerProbe + ray;
     int ix, iy, iz; probeGridIndex(__ldg(probeIndices + slot), sp.grid, ix, iy, iz);
     const v3 origin = probeWorldPos(ix, iy, iz, sp.grid);
     const float4 d4 = __ldg(dirs + ray);
@@ -134,112 +153,174 @@ __device__ __forceinline__ void borderSource(int T, int x, int y, int& sx, int& 
 
 struct BlendParams {
     vkx_grid_info grid;
-    uint32_t raysPerProbe;
+    uint32_t raysPerProbe, count;
     float gridCellLen;   // length(probeGridCellSize)
-    int intSharpness;    // > 0: depthSharpness is this small integer (pow by repeated multiplication)
 };
 
-// One CTA per updated probe. Threads 0..195: depth texels, 196..231: irradiance texels. Accumulation order over rays is
-// sequential (i = 0..N-1) with separate multiply and add, like the oracle, so packed texels agree bit for bit whenever
-// the ray records do.
-__global__ void __launch_bounds__(256) k_blend(BlendParams bp, DeviceProbes pr, const uint32_t* __restrict__ probeIndices, const float4* __restrict__ rays,
-                                               const float4* __restrict__ dirs, float* __restrict__ irrUnpacked, float* __restrict__ depUnpacked, uint32_t slotBase) {
-    __shared__ float4 sRay[VKX_MAX_RAYS_PER_PROBE];
-    __shared__ float4 sDir[VKX_MAX_RAYS_PER_PROBE];
-    __shared__ uint32_t sIrr[64];
-    __shared__ uint32_t sDep[256];
-    __shared__ uint32_t sMaxChange;
-    __shared__ uint32_t sOutOfRange;
-    const uint32_t slot = blockIdx.x, tid = threadIdx.x, N = bp.raysPerProbe;
-    const uint32_t linearIndex = __ldg(probeIndices + slot);
-    int ix, iy, iz; probeGridIndex(linearIndex, bp.grid, ix, iy, iz);
-    for (uint32_t i = tid; i < N; i += blockDim.x) { sRay[i] = rays[size_t(slot) * N + i]; sDir[i] = __ldg(dirs + i); }
-    if (tid == 0) { sMaxChange = 0u; sOutOfRange = 0u; }
-    __syncthreads();
-    const float hysteresis = bp.grid.hysteresis;
-    const float cellLen = bp.gridCellLen;
-    const int tile = iy * bp.grid.resolution[0] + ix;
-    if (tid < 196) { // ---- depth texel (probesUpdate.glsl, DEPTH)
-        const int lx = int(tid % 14u), ly = int(tid / 14u);
+// Per-frame weight table shared by every probe (the texel directions are fixed and all probes use the same rotated ray
+// directions): W[ray][col], col 0..195 depth texels pow(max(0, dot), sharpness), col 224..259 irradiance texels max(0, dot)
+// (probesUpdate.glsl:60,75,80). Same arithmetic as evaluating the weight inside the blend loop.
+#define BLEND_COLS 288
+#define BLEND_IRR_COL0 224
+#define BLEND_P 8
+__global__ void __launch_bounds__(BLEND_COLS) k_blend_weights(float depthSharpness, uint32_t N, const float4* __restrict__ dirs, float* __restrict__ W) {
+    const uint32_t i = blockIdx.x, col = threadIdx.x;
+    const float4 dd = __ldg(dirs + i);
+    float w = 0.0f;
+    if (col < 196u) {
+        const int lx = int(col % 14u), ly = int(col / 14u);
         const v3 td = octDecode(0.142857f * (float(lx) - 6.5f), 0.142857f * (float(ly) - 6.5f));
-        float r0 = 0.f, r1 = 0.f, rw = 0.f;
-        const float sharp = bp.grid.depthSharpness;
-        const int ip = bp.intSharpness;
-        for (uint32_t i = 0; i < N; ++i) {
-            const float4 rd = sRay[i]; const float4 dd = sDir[i];
-            float depth = minS(cellLen, rd.w);
-            if (depth < 0.0f) depth = cellLen;
-            const float c = maxS(0.0f, td.x * dd.x + td.y * dd.y + td.z * dd.z);
-            float weight;
-            if (ip > 0) { // c^ip by square-and-multiply (exact-integer exponent fast path; <= 2 ulp from powf)
-                float b = c; int e = ip; weight = 1.0f;
-                while (e) { if (e & 1) weight = weight * b; b = b * b; e >>= 1; }
-            } else weight = powf(c, sharp);
-            r0 = r0 + weight * depth;
-            r1 = r1 + weight * depth * depth;
-            rw = rw + weight;
-        }
-        if (rw > 1e-3f) { r0 = r0 / rw; r1 = r1 / rw; }
-        const size_t gi = size_t(16 * iz + 1 + ly) * pr.depW + size_t(16 * tile + 1 + lx);
-        const float2 prev = unpackRG16F(pr.depWork[gi]);
-        const float o0 = mixf(r0, prev.x, hysteresis), o1 = mixf(r1, prev.y, hysteresis);
-        sDep[(ly + 1) * 16 + (lx + 1)] = packRG16F(o0, o1);
-        if (depUnpacked) { float* up = depUnpacked + (size_t(slotBase + slot) * 196 + tid) * 2; up[0] = o0; up[1] = o1; }
-    } else if (tid < 232) { // ---- irradiance texel (probesUpdate.glsl, IRRADIANCE)
-        const uint32_t t = tid - 196u;
+        w = powf(maxS(0.0f, td.x * dd.x + td.y * dd.y + td.z * dd.z), depthSharpness);
+    } else if (col >= BLEND_IRR_COL0 && col < BLEND_IRR_COL0 + 36u) {
+        const uint32_t t = col - BLEND_IRR_COL0;
         const int lx = int(t % 6u), ly = int(t / 6u);
         const v3 td = octDecode(0.33333f * (float(lx) - 2.5f), 0.33333f * (float(ly) - 2.5f));
-        float r0 = 0.f, r1 = 0.f, r2 = 0.f, rw = 0.f; uint32_t outOfRange = 0;
-        for (uint32_t i = 0; i < N; ++i) {
-            const float4 rd = sRay[i]; const float4 dd = sDir[i];
-            if (rd.w < 0.0f || rd.w > cellLen) ++outOfRange;
-            const float weight = maxS(0.0f, td.x * dd.x + td.y * dd.y + td.z * dd.z);
-            r0 = r0 + weight * rd.x; r1 = r1 + weight * rd.y; r2 = r2 + weight * rd.z; rw = rw + weight;
+        w = maxS(0.0f, td.x * dd.x + td.y * dd.y + td.z * dd.z);
+    }
+    W[size_t(i) * BLEND_COLS + col] = w;
+}
+
+// One CTA blends BLEND_P probes: their ray records are staged in shared memory, thread `col` owns one texel of every probe, so each
+// weight is loaded once and applied to BLEND_P probes from registers. Accumulation over rays is sequential (i = 0..N-1) with separate
+// multiply and add, like the oracle, so packed texels agree bit for bit whenever the ray records do. Warps 0-6: depth texels,
+// warps 7-8: irradiance texels (warp-uniform roles).
+__global__ void __launch_bounds__(BLEND_COLS) k_blend(BlendParams bp, DeviceProbes pr, const uint32_t* __restrict__ probeIndices, const float4* __restrict__ rays,
+                                                      const float* __restrict__ W, float* __restrict__ irrUnpacked, float* __restrict__ depUnpacked, uint32_t slotBase) {
+    __shared__ float4 sRay[BLEND_P][VKX_MAX_RAYS_PER_PROBE]; // (r, g, b, clamped depth)
+    __shared__ uint32_t sDep[BLEND_P][256];
+    __shared__ uint32_t sIrr[BLEND_P][64];
+    __shared__ uint32_t sMaxChange[BLEND_P];
+    __shared__ uint32_t sOutOfRange[BLEND_P];
+    __shared__ uint32_t sLinear[BLEND_P];
+    const uint32_t tid = threadIdx.x, N = bp.raysPerProbe;
+    const uint32_t slot0 = blockIdx.x * BLEND_P;
+    const uint32_t np = min(uint32_t(BLEND_P), bp.count - slot0);
+    const float cellLen = bp.gridCellLen;
+    if (tid < BLEND_P) { sMaxChange[tid] = 0u; sOutOfRange[tid] = 0u; sLinear[tid] = tid < np ? __ldg(probeIndices + slot0 + tid) : 0u; }
+    __syncthreads();
+    // stage ray records; count out-of-range rays per probe (probesUpdate.glsl:74) and clamp depths (:78-79) once per ray
+    for (uint32_t e = tid; e < BLEND_P * N; e += BLEND_COLS) {
+        const uint32_t p = e / N, i = e - p * N;
+        float4 rd = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p < np) {
+            rd = rays[size_t(slot0 + p) * N + i];
+            if (rd.w < 0.0f || rd.w > cellLen) atomicAdd(&sOutOfRange[p], 1u);
+            float depth = minS(cellLen, rd.w);
+            if (depth < 0.0f) depth = cellLen;
+            rd.w = depth;
         }
-        if (rw > 1e-3f) { r0 = r0 / rw; r1 = r1 / rw; r2 = r2 / rw; }
-        const size_t gi = size_t(8 * iz + 1 + ly) * pr.irrW + size_t(8 * tile + 1 + lx);
-        const float3 prev = unpackR11G11B10(pr.irrWork[gi]);
-        const float maxChange = maxS(maxS(fabsf(r0 - prev.x), fabsf(r1 - prev.y)), fabsf(r2 - prev.z));
-        const float o0 = mixf(r0, prev.x, hysteresis), o1 = mixf(r1, prev.y, hysteresis), o2 = mixf(r2, prev.z, hysteresis);
-        sIrr[(ly + 1) * 8 + (lx + 1)] = packR11G11B10(o0, o1, o2);
-        if (irrUnpacked) { float* up = irrUnpacked + (size_t(slotBase + slot) * 36 + t) * 3; up[0] = o0; up[1] = o1; up[2] = o2; }
-        atomicMax(&sMaxChange, __float_as_uint(maxChange)); // probesUpdate.glsl:106-107 (non-negative floats order as uints)
-        if (t == 0) sOutOfRange = outOfRange;
+        sRay[p][i] = rd;
     }
     __syncthreads();
-    if (tid == 0) { // state machine, probesUpdate.glsl:110-119 (decree A.5.3: full max over the 36 texels)
+    const float hysteresis = bp.grid.hysteresis;
+    const float* Wc = W + tid;
+    if (tid < 224u) { // ---- depth texels (warps 0..6; lanes >= 196 idle)
+        if (tid < 196u) {
+            float a0[BLEND_P], a1[BLEND_P], rw = 0.0f;
+#pragma unroll
+            for (int p = 0; p < BLEND_P; ++p) { a0[p] = 0.0f; a1[p] = 0.0f; }
+#pragma unroll 4
+            for (uint32_t i = 0; i < N; ++i) {
+                const float w = __ldg(Wc + size_t(i) * BLEND_COLS);
+#pragma unroll
+                for (int p = 0; p < BLEND_P; ++p) {
+                    const float d = sRay[p][i].w;
+                    const float t = w * d;
+                    a0[p] = a0[p] + t;
+                    a1[p] = a1[p] + t * d;
+                }
+                rw = rw + w;
+            }
+            const int lx = int(tid % 14u), ly = int(tid / 14u);
+#pragma unroll
+            for (int p = 0; p < BLEND_P; ++p) {
+                if (uint32_t(p) >= np) break;
+                float r0 = a0[p], r1 = a1[p];
+                if (rw > 1e-3f) { r0 = r0 / rw; r1 = r1 / rw; }
+                int ix, iy, iz; probeGridIndex(sLinear[p], bp.grid, ix, iy, iz);
+                const int tile = iy * bp.grid.resolution[0] + ix;
+                const size_t gi = size_t(16 * iz + 1 + ly) * pr.depW + size_t(16 * tile + 1 + lx);
+                const float2 prev = unpackRG16F(pr.depWork[gi]);
+                const float o0 = mixf(r0, prev.x, hysteresis), o1 = mixf(r1, prev.y, hysteresis);
+                sDep[p][(ly + 1) * 16 + (lx + 1)] = packRG16F(o0, o1);
+                if (depUnpacked) { float* up = depUnpacked + (size_t(slotBase + slot0 + p) * 196 + tid) * 2; up[0] = o0; up[1] = o1; }
+            }
+        }
+    } else if (tid < BLEND_IRR_COL0 + 36u) { // ---- irradiance texels (warps 7..8)
+        const uint32_t t = tid - BLEND_IRR_COL0;
+        float a0[BLEND_P], a1[BLEND_P], a2[BLEND_P], rw = 0.0f;
+#pragma unroll
+        for (int p = 0; p < BLEND_P; ++p) { a0[p] = 0.0f; a1[p] = 0.0f; a2[p] = 0.0f; }
+#pragma unroll 2
+        for (uint32_t i = 0; i < N; ++i) {
+            const float w = __ldg(Wc + size_t(i) * BLEND_COLS);
+#pragma unroll
+            for (int p = 0; p < BLEND_P; ++p) {
+                const float4 rd = sRay[p][i];
+                a0[p] = a0[p] + w * rd.x; a1[p] = a1[p] + w * rd.y; a2[p] = a2[p] + w * rd.z;
+            }
+            rw = rw + w;
+        }
+        const int lx = int(t % 6u), ly = int(t / 6u);
+#pragma unroll
+        for (int p = 0; p < BLEND_P; ++p) {
+            if (uint32_t(p) >= np) break;
+            float r0 = a0[p], r1 = a1[p], r2 = a2[p];
+            if (rw > 1e-3f) { r0 = r0 / rw; r1 = r1 / rw; r2 = r2 / rw; }
+            int ix, iy, iz; probeGridIndex(sLinear[p], bp.grid, ix, iy, iz);
+            const int tile = iy * bp.grid.resolution[0] + ix;
+            const size_t gi = size_t(8 * iz + 1 + ly) * pr.irrW + size_t(8 * tile + 1 + lx);
+            const float3 prev = unpackR11G11B10(pr.irrWork[gi]);
+            const float maxChange = maxS(maxS(fabsf(r0 - prev.x), fabsf(r1 - prev.y)), fabsf(r2 - prev.z));
+            const float o0 = mixf(r0, prev.x, hysteresis), o1 = mixf(r1, prev.y, hysteresis), o2 = mixf(r2, prev.z, hysteresis);
+            sIrr[p][(ly + 1) * 8 + (lx + 1)] = packR11G11B10(o0, o1, o2);
+            if (irrUnpacked) { float* up = irrUnpacked + (size_t(slotBase + slot0 + p) * 36 + t) * 3; up[0] = o0; up[1] = o1; up[2] = o2; }
+            atomicMax(&sMaxChange[p], __float_as_uint(maxChange)); // probesUpdate.glsl:106-107 (non-negative floats order as uints)
+        }
+    }
+    __syncthreads();
+    if (tid < np) { // state machine, probesUpdate.glsl:110-119 (decree A.5.3: full max over the 36 texels)
+        const uint32_t linearIndex = sLinear[tid];
         uint32_t st = pr.stateWork[linearIndex];
-        if (sOutOfRange >= N) st = 8;
+        if (sOutOfRange[tid] >= N) st = 8;
         else {
-            const float maxChange = __uint_as_float(sMaxChange);
+            const float maxChange = __uint_as_float(sMaxChange[tid]);
             if (maxChange < 0.02f / float(st)) st = min(st + 1u, 8u);
             else if (maxChange > 0.04f / float(st)) st = max(st - 1u, 1u);
             else if (maxChange > 0.25f) st = 1;
         }
         pr.stateWork[linearIndex] = st;
     }
-    // ---- borders (probesCopyBorders.comp) from the shared tiles
-    if (tid < 60) { // depth border texels: 4 corners + 4 x 14
-        int x, y;
-        if (tid < 16) { x = int(tid); y = 0; } else if (tid < 32) { x = int(tid) - 16; y = 15; } else if (tid < 46) { x = 0; y = int(tid) - 32 + 1; } else { x = 15; y = int(tid) - 46 + 1; }
-        int sx, sy; borderSource(16, x, y, sx, sy);
-        sDep[y * 16 + x] = sDep[sy * 16 + sx];
-    } else if (tid >= 64 && tid < 92) { // irradiance border texels: 28
-        const int b = int(tid) - 64; int x, y;
-        if (b < 8) { x = b; y = 0; } else if (b < 16) { x = b - 8; y = 7; } else if (b < 22) { x = 0; y = b - 16 + 1; } else { x = 7; y = b - 22 + 1; }
-        int sx, sy; borderSource(8, x, y, sx, sy);
-        sIrr[y * 8 + x] = sIrr[sy * 8 + sx];
+    // ---- borders (probesCopyBorders.comp) from the shared tiles: 60 depth + 28 irradiance texels per probe
+    for (uint32_t e = tid; e < np * 88u; e += BLEND_COLS) {
+        const uint32_t p = e / 88u, b = e - p * 88u;
+        int x, y, sx, sy;
+        if (b < 60u) {
+            if (b < 16u) { x = int(b); y = 0; } else if (b < 32u) { x = int(b) - 16; y = 15; } else if (b < 46u) { x = 0; y = int(b) - 32 + 1; } else { x = 15; y = int(b) - 46 + 1; }
+            borderSource(16, x, y, sx, sy);
+            sDep[p][y * 16 + x] = sDep[p][sy * 16 + sx];
+        } else {
+            const int c = int(b) - 60;
+            if (c < 8) { x = c; y = 0; } else if (c < 16) { x = c - 8; y = 7; } else if (c < 22) { x = 0; y = c - 16 + 1; } else { x = 7; y = c - 22 + 1; }
+            borderSource(8, x, y, sx, sy);
+            sIrr[p][y * 8 + x] = sIrr[p][sy * 8 + sx];
+        }
     }
     __syncthreads();
-    // ---- vectorised tile stores: depth 16 rows x 64 B (4 x uint4), irradiance 8 rows x 32 B (2 x uint4)
-    if (tid < 64) {
-        const int row = int(tid >> 2), q = int(tid & 3);
-        uint4 v = *reinterpret_cast<const uint4*>(&sDep[row * 16 + q * 4]);
-        *reinterpret_cast<uint4*>(pr.depWork + size_t(16 * iz + row) * pr.depW + size_t(16 * tile + q * 4)) = v;
-    } else if (tid < 80) {
-        const int k = int(tid) - 64; const int row = k >> 1, q = k & 1;
-        uint4 v = *reinterpret_cast<const uint4*>(&sIrr[row * 8 + q * 4]);
-        *reinterpret_cast<uint4*>(pr.irrWork + size_t(8 * iz + row) * pr.irrW + size_t(8 * tile + q * 4)) = v;
+    // ---- vectorised tile stores: per probe depth 16 rows x 64 B (64 uint4), irradiance 8 rows x 32 B (16 uint4)
+    for (uint32_t e = tid; e < np * 80u; e += BLEND_COLS) {
+        const uint32_t p = e / 80u, k = e - p * 80u;
+        int ix, iy, iz; probeGridIndex(sLinear[p], bp.grid, ix, iy, iz);
+        const int tile = iy * bp.grid.resolution[0] + ix;
+        if (k < 64u) {
+            const int row = int(k >> 2), q = int(k & 3u);
+            const uint4 v = *reinterpret_cast<const uint4*>(&sDep[p][row * 16 + q * 4]);
+            *reinterpret_cast<uint4*>(pr.depWork + size_t(16 * iz + row) * pr.depW + size_t(16 * tile + q * 4)) = v;
+        } else {
+            const int kk = int(k) - 64; const int row = kk >> 1, q = kk & 1;
+            const uint4 v = *reinterpret_cast<const uint4*>(&sIrr[p][row * 8 + q * 4]);
+            *reinterpret_cast<uint4*>(pr.irrWork + size_t(8 * iz + row) * pr.irrW + size_t(8 * tile + q * 4)) = v;
+        }
     }
 }
 
@@ -341,26 +422,28 @@ int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* /*unused*/,
     const float tmax = sqrtf(ex * ex + ey * ey + ez * ez); // traceProbes.rgen:33
     const float cx = ex / float(ctx->grid.resolution[0] - 1), cy = ey / float(ctx->grid.resolution[1] - 1), cz = ez / float(ctx->grid.resolution[2] - 1);
     BlendParams bp; bp.grid = ctx->grid; bp.raysPerProbe = N; bp.gridCellLen = sqrtf(cx * cx + cy * cy + cz * cz);
-    const float sh = ctx->grid.depthSharpness;
-    bp.intSharpness = (sh >= 1.0f && sh <= 64.0f && sh == floorf(sh)) ? int(sh) : 0;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
+    k_blend_weights<<<N, BLEND_COLS, 0, st>>>(ctx->grid.depthSharpness, N, ctx->dDirs, ctx->dBlendW); LAUNCH_CHECK(ctx);
     for (uint32_t base = 0; base < count; base += ctx->chunkProbes) {
         const uint32_t n = std::min(ctx->chunkProbes, count - base);
         const uint32_t numRays = n * N;
         const uint32_t* idx = ctx->dIndicesList + listOffset + base;
+        RayMap rm; rm.count = n; rm.raysPerProbe = N; rm.numDirGroups = (N + 3u) / 4u; rm.order = ctx->dOrder + listOffset + base; rm.perm = ctx->dPerm;
+        rm.numThreads = ((n + 7u) / 8u) * rm.numDirGroups * 32u;
         TraceParams tp; tp.grid = ctx->grid; tp.tmin = 0.01f; tp.tmax = tmax; tp.raysPerProbe = N; tp.numRays = numRays;
         ShadeParams sp; sp.grid = ctx->grid; sp.light = light; sp.raysPerProbe = N; sp.numRays = numRays;
         const bool timed = base == 0; // per-kernel events on the first chunk
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->dQueueCount, 0, 4, st));
         if (timed) { CUDA_TRY(ctx, cudaEventRecord(ctx->kev[0], st)); ctx->kevProbes = n; }
-        k_trace_primary<<<divUp(numRays, 128), 128, 0, st>>>(sc, tp, idx, ctx->dDirs, ctx->dHits); LAUNCH_CHECK(ctx);
+        k_trace_primary<<<divUp(rm.numThreads, 128), 128, 0, st>>>(sc, tp, rm, idx, ctx->dDirs, ctx->dHits); LAUNCH_CHECK(ctx);
         if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[1], st));
-        k_shade<<<divUp(numRays, 128), 128, 0, st>>>(sc, pr, sp, idx, ctx->dDirs, ctx->dHits, ctx->dRays, ctx->dShadowQueue, ctx->dQueueCount, ctx->debugBuffers ? ctx->dShadowFlags : nullptr); LAUNCH_CHECK(ctx);
+        k_shade<<<divUp(rm.numThreads, 128), 128, 0, st>>>(sc, pr, sp, rm, idx, ctx->dDirs, ctx->dHits, ctx->dRays, ctx->dShadowQueue, ctx->dQueueCount, ctx->debugBuffers ? ctx->dShadowFlags : nullptr); LAUNCH_CHECK(ctx);
         if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[2], st));
         k_trace_shadow<<<divUp(numRays, 128), 128, 0, st>>>(sc, light, ctx->dShadowQueue, ctx->dQueueCount, ctx->dRays, ctx->debugBuffers ? ctx->dShadowFlags : nullptr); LAUNCH_CHECK(ctx);
         if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[3], st));
         if (base + n >= count) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], st));
-        k_blend<<<n, 256, 0, st>>>(bp, pr, idx, ctx->dRays, ctx->dDirs, ctx->debugBuffers ? ctx->dIrrUnpacked : nullptr, ctx->debugBuffers ? ctx->dDepUnpacked : nullptr, base); LAUNCH_CHECK(ctx);
+        bp.count = n;
+        k_blend<<<divUp(n, BLEND_P), BLEND_COLS, 0, st>>>(bp, pr, idx, ctx->dRays, ctx->dBlendW, ctx->debugBuffers ? ctx->dIrrUnpacked : nullptr, ctx->debugBuffers ? ctx->dDepUnpacked : nullptr, base); LAUNCH_CHECK(ctx);
         if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[4], st));
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], st));
