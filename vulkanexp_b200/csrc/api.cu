@@ -221,7 +221,7 @@ int vkx_probes_init(vkx_ctx* ctx, const vkx_grid_info* grid) {
     for (int i = 0; i < 6; ++i) { CUDA_TRY(ctx, cudaMalloc(bufs[i], sizes[i])); CUDA_TRY(ctx, cudaMemsetAsync(*bufs[i], 0, sizes[i], ctx->stream)); }
     CUDA_TRY(ctx, cudaMalloc(&ctx->dIndicesList, stBytes));
     CUDA_TRY(ctx, cudaMalloc(&ctx->dDirs, 512 * sizeof(float4)));
-    CUDA_TRY(ctx, cudaMalloc(&ctx->dQueueCount, 4));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->dQueueCount, 16));
     CUDA_TRY(ctx, cudaMalloc(&ctx->dPerm, VKX_MAX_RAYS_PER_PROBE * 4));
     CUDA_TRY(ctx, cudaMalloc(&ctx->dOrder, stBytes));
     CUDA_TRY(ctx, cudaMalloc(&ctx->dBlockedOrder, stBytes));

@@ -191,14 +191,17 @@ __device__ inline float unpackUF(uint32_t c) {
     return __uint_as_float(((e + 112u) << 23) | (m << (23 - MB)));
 }
 __device__ inline uint32_t packR11G11B10(float r, float g, float b) { return packUF<6>(r) | (packUF<6>(g) << 11) | (packUF<5>(b) << 22); }
+// Decode through binary16: an unsigned 5e6m / 5e5m float is a half with the low mantissa bits zero (exact, including denormals,
+// inf and NaN), so one shift + one F2F per channel replaces the branchy integer decode. Same values as unpackUF<>.
 __device__ inline float3 unpackR11G11B10(uint32_t p) {
-    return make_float3(unpackUF<6>(p & 0x7FFu), unpackUF<6>((p >> 11) & 0x7FFu), unpackUF<5>(p >> 22));
+    return make_float3(__half2float(__ushort_as_half((unsigned short)((p & 0x7FFu) << 4))), __half2float(__ushort_as_half((unsigned short)(((p >> 11) & 0x7FFu) << 4))),
+                       __half2float(__ushort_as_half((unsigned short)((p >> 22) << 5))));
 }
 __device__ inline uint32_t packRG16F(float r, float g) {
     return uint32_t(__half_as_ushort(__float2half_rn(r))) | (uint32_t(__half_as_ushort(__float2half_rn(g))) << 16);
 }
 __device__ inline float2 unpackRG16F(uint32_t p) {
-    return make_float2(__half2float(__ushort_as_half((unsigned short)(p & 0xFFFFu))), __half2float(__ushort_as_half((unsigned short)(p >> 16))));
+    return __half22float2(*reinterpret_cast<const __half2*>(&p));
 }
 
 #endif // __CUDACC__

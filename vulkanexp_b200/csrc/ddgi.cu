@@ -11,6 +11,7 @@
 //   k_publish        work -> sampled for the updated probes (the reference copies both whole atlases)
 #include "common.cuh"
 #include "traverse.cuh"
+#include "ptrace.cuh"
 #include "shade.cuh"
 
 namespace {
@@ -40,19 +41,31 @@ struct TraceParams {
     uint32_t raysPerProbe, numRays; // numRays = chunk probes * raysPerProbe
 };
 
+struct PrimarySrc {
+    TraceParams tp; RayMap rm; const uint32_t* probeIndices; const float4* dirs; vkx_hit* hits;
+    uint32_t ri;
+    __device__ __forceinline__ bool load(uint32_t item, Ray& r, float& tmin, float& tmax, uint32_t& cullMask) {
+        uint32_t slot, ray;
+        if (!mapRay(rm, item, slot, ray)) return false;
+        ri = slot * tp.raysPerProbe + ray;
+        int ix, iy, iz; probeGridIndex(__ldg(probeIndices + slot), tp.grid, ix, iy, iz);
+        const v3 o = probeWorldPos(ix, iy, iz, tp.grid);
+        const float4 d = __ldg(dirs + ray);
+        r = makeRay(o.x, o.y, o.z, d.x, d.y, d.z);
+        tmin = tp.tmin; tmax = tp.tmax; cullMask = VKX_INSTANCE_STATIC | VKX_INSTANCE_DYNAMIC;
+        return true;
+    }
+    __device__ __forceinline__ void store(uint32_t, const HitRec& h, bool) {
+        vkx_hit out; out.t = h.t; out.instance = h.inst; out.primitive = h.prim; out.u = h.u; out.v = h.v;
+        hits[ri] = out;
+    }
+};
+
+// Persistent warps; see ptrace.cuh.
 __global__ void __launch_bounds__(128) k_trace_primary(DeviceScene sc, TraceParams tp, RayMap rm, const uint32_t* __restrict__ probeIndices,
-                                                       const float4* __restrict__ dirs, vkx_hit* __restrict__ hits) {
-    uint32_t slot, ray;
-    if (!mapRay(rm, blockIdx.x * blockDim.x + threadIdx.x, slot, ray)) return;
-    const uint32_t ri = slot * tp.raysPerProbe + ray;
-    int ix, iy, iz; probeGridIndex(__ldg(probeIndices + slot), tp.grid, ix, iy, iz);
-    const v3 o = probeWorldPos(ix, iy, iz, tp.grid);
-    const float4 d = __ldg(dirs + ray);
-    const Ray r = makeRay(o.x, o.y, o.z, d.x, d.y, d.z);
-    HitRec h;
-    traverse<false>(sc.nodes, sc.tris, r, tp.tmin, tp.tmax, VKX_INSTANCE_STATIC | VKX_INSTANCE_DYNAMIC, h);
-    vkx_hit out; out.t = h.t; out.instance = h.inst; out.primitive = h.prim; out.u = h.u; out.v = h.v;
-    hits[ri] = out;
+                                                       const float4* __restrict__ dirs, vkx_hit* __restrict__ hits, uint32_t* __restrict__ counter) {
+    PrimarySrc src; src.tp = tp; src.rm = rm; src.probeIndices = probeIndices; src.dirs = dirs; src.hits = hits; src.ri = 0;
+    persistentTrace<false>(sc.nodes, sc.tris, src, rm.numThreads, counter);
 }
 
 struct ShadeParams {
@@ -129,17 +142,27 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene sc, DeviceProbes pr, 
     queue[2 * size_t(qi) + 1] = make_float4(lit.x, lit.y, lit.z, 0.0f);
 }
 
+struct ShadowSrc {
+    vkx_light light; const float4* queue; float4* rays; uint8_t* shadowFlags; uint32_t count;
+    uint32_t ri; float lx, ly, lz;
+    __device__ __forceinline__ bool load(uint32_t item, Ray& r, float& tmin, float& tmax, uint32_t& cullMask) {
+        if (item >= count) return false;
+        const float4 q0 = queue[2 * size_t(item)], q1 = queue[2 * size_t(item) + 1];
+        ri = __float_as_uint(q0.w); lx = q1.x; ly = q1.y; lz = q1.z;
+        r = makeRay(q0.x, q0.y, q0.z, light.direction[0], light.direction[1], light.direction[2]);
+        tmin = 0.1f; tmax = 10000.0f; cullMask = 0xFFu; // closesthit.glsl:270-281
+        return true;
+    }
+    __device__ __forceinline__ void store(uint32_t, const HitRec& h, bool) {
+        if (!h.found) { float4 rec = rays[ri]; rec.x = lx; rec.y = ly; rec.z = lz; rays[ri] = rec; }
+        if (shadowFlags) shadowFlags[ri] = h.found ? 2 : 1;
+    }
+};
+
 __global__ void __launch_bounds__(128) k_trace_shadow(DeviceScene sc, vkx_light light, const float4* __restrict__ queue, const uint32_t* __restrict__ queueCount,
-                                                      float4* __restrict__ rays, uint8_t* __restrict__ shadowFlags) {
-    const uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (qi >= *queueCount) return;
-    const float4 q0 = queue[2 * size_t(qi)], q1 = queue[2 * size_t(qi) + 1];
-    const uint32_t ri = __float_as_uint(q0.w);
-    const Ray r = makeRay(q0.x, q0.y, q0.z, light.direction[0], light.direction[1], light.direction[2]);
-    HitRec h;
-    const bool shadowed = traverse<true>(sc.nodes, sc.tris, r, 0.1f, 10000.0f, 0xFFu, h); // closesthit.glsl:270-281
-    if (!shadowed) { float4 rec = rays[ri]; rec.x = q1.x; rec.y = q1.y; rec.z = q1.z; rays[ri] = rec; }
-    if (shadowFlags) shadowFlags[ri] = shadowed ? 2 : 1;
+                                                      float4* __restrict__ rays, uint8_t* __restrict__ shadowFlags, uint32_t* __restrict__ counter) {
+    ShadowSrc src; src.light = light; src.queue = queue; src.rays = rays; src.shadowFlags = shadowFlags; src.count = *queueCount; src.ri = 0; src.lx = src.ly = src.lz = 0.f;
+    persistentTrace<true>(sc.nodes, sc.tris, src, src.count, counter);
 }
 
 // ------------------------------------------------------------------------------------------------ blend
@@ -422,6 +445,9 @@ int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* /*unused*/,
     const float tmax = sqrtf(ex * ex + ey * ey + ez * ez); // traceProbes.rgen:33
     const float cx = ex / float(ctx->grid.resolution[0] - 1), cy = ey / float(ctx->grid.resolution[1] - 1), cz = ez / float(ctx->grid.resolution[2] - 1);
     BlendParams bp; bp.grid = ctx->grid; bp.raysPerProbe = N; bp.gridCellLen = sqrtf(cx * cx + cy * cy + cz * cz);
+    static int blocksPerSm = 0;
+    if (!blocksPerSm) { int a = 0, b = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_trace_primary, 128, 0); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace_shadow, 128, 0); blocksPerSm = std::max(1, std::min(a, b)); }
+    const unsigned persistentBlocks = unsigned(ctx->smCount * blocksPerSm);
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
     k_blend_weights<<<N, BLEND_COLS, 0, st>>>(ctx->grid.depthSharpness, N, ctx->dDirs, ctx->dBlendW); LAUNCH_CHECK(ctx);
     for (uint32_t base = 0; base < count; base += ctx->chunkProbes) {
@@ -433,13 +459,13 @@ int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* /*unused*/,
         TraceParams tp; tp.grid = ctx->grid; tp.tmin = 0.01f; tp.tmax = tmax; tp.raysPerProbe = N; tp.numRays = numRays;
         ShadeParams sp; sp.grid = ctx->grid; sp.light = light; sp.raysPerProbe = N; sp.numRays = numRays;
         const bool timed = base == 0; // per-kernel events on the first chunk
-        CUDA_TRY(ctx, cudaMemsetAsync(ctx->dQueueCount, 0, 4, st));
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->dQueueCount, 0, 16, st)); // [0] shadow queue length, [1] primary work counter, [2] shadow work counter
         if (timed) { CUDA_TRY(ctx, cudaEventRecord(ctx->kev[0], st)); ctx->kevProbes = n; }
-        k_trace_primary<<<divUp(rm.numThreads, 128), 128, 0, st>>>(sc, tp, rm, idx, ctx->dDirs, ctx->dHits); LAUNCH_CHECK(ctx);
+        k_trace_primary<<<persistentBlocks, 128, 0, st>>>(sc, tp, rm, idx, ctx->dDirs, ctx->dHits, ctx->dQueueCount + 1); LAUNCH_CHECK(ctx);
         if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[1], st));
         k_shade<<<divUp(rm.numThreads, 128), 128, 0, st>>>(sc, pr, sp, rm, idx, ctx->dDirs, ctx->dHits, ctx->dRays, ctx->dShadowQueue, ctx->dQueueCount, ctx->debugBuffers ? ctx->dShadowFlags : nullptr); LAUNCH_CHECK(ctx);
         if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[2], st));
-        k_trace_shadow<<<divUp(numRays, 128), 128, 0, st>>>(sc, light, ctx->dShadowQueue, ctx->dQueueCount, ctx->dRays, ctx->debugBuffers ? ctx->dShadowFlags : nullptr); LAUNCH_CHECK(ctx);
+        k_trace_shadow<<<persistentBlocks, 128, 0, st>>>(sc, light, ctx->dShadowQueue, ctx->dQueueCount, ctx->dRays, ctx->debugBuffers ? ctx->dShadowFlags : nullptr, ctx->dQueueCount + 2); LAUNCH_CHECK(ctx);
         if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[3], st));
         if (base + n >= count) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], st));
         bp.count = n;

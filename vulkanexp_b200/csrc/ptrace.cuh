@@ -1,0 +1,99 @@
+// Persistent-thread traversal with warp-level ray replacement ("dynamic fetch"): warps stay resident, and a lane whose ray has
+// terminated takes the next ray from the work list instead of idling until the slowest ray of its warp finishes. Measured
+// motivation (profiles/r01a): with one ray per thread 11 of 32 lanes were active in the node test because traversal lengths
+// inside a warp differ by 3x. The per-ray operation sequence is unchanged (it is the one of traverse<> in traverse.cuh);
+// only the assignment of rays to lanes is dynamic.
+//
+// Work distribution: each warp owns a private chunk of PT_CHUNK consecutive work items taken from a global counter with one
+// atomicAdd per chunk; idle lanes take consecutive items of the chunk, so rays that are neighbours in the (coherent) work
+// order still run in the same warp.
+#pragma once
+#include "traverse.cuh"
+
+#define PT_CHUNK 256u
+#define PT_REFILL_MIN 8 // fetch when at least this many lanes are idle (or all remaining lanes are idle)
+
+// Src must provide:
+//   __device__ bool load(uint32_t item, Ray& r, float& tmin, float& tmax, uint32_t& cullMask);   false: item is padding
+//   __device__ void store(uint32_t item, const HitRec& h, bool anyHit);
+template <bool ANY, class Src>
+__device__ __forceinline__ void persistentTrace(const uint4* __restrict__ nodes, const float4* __restrict__ tris, Src& src, uint32_t total, uint32_t* __restrict__ counter) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned ltMask = (1u << lane) - 1u;
+    uint2 stack[VKX_STACK];
+    int sp = 0;
+    uint2 g = make_uint2(0u, 0u);
+    Ray r; float tmin = 0.f, tbest = 0.f; uint32_t cullMask = 0, item = 0;
+    HitRec hit; hit.found = false; hit.t = -1.0f; hit.u = hit.v = 0.f; hit.inst = hit.prim = 0xFFFFFFFFu;
+    bool active = false;
+    uint32_t cur = 0, end = 0; // this warp's chunk (warp-uniform)
+    bool more = true;
+    for (;;) {
+        const unsigned idle = __ballot_sync(0xFFFFFFFFu, !active);
+        const int nIdle = __popc(idle);
+        if (nIdle == 32 && !more) break;
+        if (more && (nIdle >= PT_REFILL_MIN)) {
+            if (cur >= end) { // take a new chunk
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(counter, PT_CHUNK);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                cur = base; end = min(base + PT_CHUNK, total);
+                if (base >= total) { more = false; cur = end = 0; }
+            }
+            if (more) {
+                const uint32_t avail = end - cur;
+                const uint32_t rank = uint32_t(__popc(idle & ltMask));
+                if (!active && rank < avail) {
+                    const uint32_t it = cur + rank;
+                    float tmax;
+                    if (src.load(it, r, tmin, tmax, cullMask)) {
+                        item = it; tbest = tmax; sp = 0; g = make_uint2(0u, 0x80000000u);
+                        hit.found = false; hit.t = -1.0f; hit.u = hit.v = 0.f; hit.inst = hit.prim = 0xFFFFFFFFu;
+                        active = true;
+                    }
+                }
+                cur += min(uint32_t(nIdle), avail);
+            }
+        }
+        if (active) { // one node step + its triangles (same order as traverse<>)
+            uint32_t triBase = 0, triBits = 0;
+            bool done = false;
+            if (g.y & 0xFF000000u) {
+                const uint32_t bit = 31u - uint32_t(__clz(int(g.y)));
+                g.y &= ~(1u << bit);
+                if (g.y & 0xFF000000u) { if (sp < VKX_STACK) stack[sp++] = g; }
+                const uint32_t slot = (bit - 24u) ^ r.oct;
+                const uint32_t rel = uint32_t(__popc(g.y & 0xFFu & ((1u << slot) - 1u)));
+                uint4 w0, w1, w2, w3, w4;
+                loadNode(nodes, g.x + rel, w0, w1, w2, w3, w4);
+                const uint32_t m = intersectNode(w0, w1, w2, w3, w4, r, tmin, tbest);
+                g.x = w1.x; g.y = (m & 0xFF000000u) | (w0.w >> 24);
+                triBase = w1.y; triBits = m & 0x00FFFFFFu;
+            }
+            while (triBits) {
+                const uint32_t b = uint32_t(__ffs(int(triBits))) - 1u;
+                triBits &= triBits - 1u;
+                const float4* tp = tris + size_t(triBase + b) * 3;
+                const float4 q2 = __ldg(tp + 2);
+                const uint32_t instW = __float_as_uint(q2.y), primW = __float_as_uint(q2.z);
+                if (!((instW >> 24) & cullMask)) continue;
+                const float4 q0 = __ldg(tp + 0), q1 = __ldg(tp + 1);
+                float t, u, v, det;
+                if (!intersectTri(q0, q1, q2, r, t, u, v, det)) continue;
+                if (!(t > tmin)) continue;
+                const uint32_t inst = instW & 0x00FFFFFFu, prim = primW & 0x7FFFFFFFu;
+                const bool closer = t < tbest || (hit.found && t == tbest && (inst < hit.inst || (inst == hit.inst && prim < (hit.prim & 0x7FFFFFFFu))));
+                if (!closer) continue;
+                hit.found = true;
+                if (ANY) { done = true; break; }
+                const bool back = (det > 0.0f) == ((primW & 0x80000000u) != 0u);
+                tbest = t; hit.t = t; hit.inst = inst; hit.prim = prim | (back ? 0x80000000u : 0u); hit.u = u; hit.v = v;
+            }
+            if (!done && !(g.y & 0xFF000000u)) {
+                if (sp == 0) done = true;
+                else g = stack[--sp];
+            }
+            if (done) { src.store(item, hit, ANY); active = false; }
+        }
+    }
+}

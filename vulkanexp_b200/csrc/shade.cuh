@@ -70,13 +70,17 @@ __device__ __forceinline__ float2 sphereToOctUV(v3 direction) { // irradiance.gl
     return make_float2(o.x * 0.5f + 0.5f, o.y * 0.5f + 0.5f);
 }
 
+// REPEAT addressing without integer division: atlas/noise coordinates produced on this path lie in [-1, 2*size), where one
+// conditional add/subtract equals the oracle's ((i % size) + size) % size.
 __device__ __forceinline__ void bilinearSetup(float u, uint32_t size, int& i0, int& i1, float& f) {
     float x = u * float(size) - 0.5f;
     float fl = floorf(x);
     f = x - fl;
-    int isz = int(size), i = int(fl);
-    i0 = ((i % isz) + isz) % isz;
-    i1 = (i0 + 1) % isz;
+    const int isz = int(size);
+    int i = int(fl);
+    if (i < 0 || i >= isz) { i %= isz; if (i < 0) i += isz; } // rare general case
+    i0 = i;
+    i1 = (i0 + 1 == isz) ? 0 : i0 + 1;
 }
 
 __device__ __forceinline__ v3 sampleIrradianceTex(const DeviceProbes& p, float u, float v) {
@@ -148,7 +152,7 @@ __device__ inline v3 sampleProbes(const DeviceProbes& p, v3 position, v3 normal,
         const float biasedDistToProbe = len3(probePosition - biasedPosition);
         const float dd = maxS(biasedDistToProbe - mean, 0.0001f);
         float chebyshevWeight = variance / (variance + dd * dd);
-        chebyshevWeight = maxS(powf(chebyshevWeight, 3.0f), 0.0f);
+        chebyshevWeight = maxS(chebyshevWeight * chebyshevWeight * chebyshevWeight, 0.0f); // pow(x, 3.0): within 2 ulp of powf
         weight *= (biasedDistToProbe <= mean) ? 1.0f : chebyshevWeight;
         weight = maxS(0.000001f, weight);
         const float crushThreshold = 0.2f;
