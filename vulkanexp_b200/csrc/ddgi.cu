@@ -122,9 +122,10 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene sc, DeviceProbes pr, 
     diffuseColor = diffuseColor * (1.0f - metalness);
     const v3 specularColor = mix3(f0, albedo, metalness);
     const v3 reflectDir = reflect3(direction, normal);
-    const v3 reflection = sampleProbes(pr, position, reflectDir, -direction);
+    v3 reflection, indirectLight;
+    const GridConsts gc = makeGridConsts(sp.grid);
+    sampleProbes2(pr, gc, position, reflectDir, normal, -direction, reflection, indirectLight);
     color = color + specularColor * reflection;
-    const v3 indirectLight = sampleProbes(pr, position, normal, -direction);
     color = color + indirectLight * diffuseColor;
     rays[ri] = make_float4(color.x, color.y, color.z, h.t); // value if the sun is occluded
     // direct term, applied by k_trace_shadow if the shadow ray escapes
