@@ -54,14 +54,14 @@ int vkx_create(int device, vkx_ctx** out) {
 
 static void freeProbes(vkx_ctx* ctx) {
     void* ptrs[] = {ctx->dIrrWork, ctx->dIrrSampled, ctx->dDepWork, ctx->dDepSampled, ctx->dStateWork, ctx->dStateSampled, ctx->dIndicesList, ctx->dDirs, ctx->dRays,
-                    ctx->dHits, ctx->dShadowQueue, ctx->dQueueCount, ctx->dShadowFlags, ctx->dIrrUnpacked, ctx->dDepUnpacked, ctx->dIrrNext, ctx->dDepNext, ctx->dStateNext,
+                    ctx->dHits, ctx->dShadowQueue, ctx->dQueueCount, ctx->dShadowFlags, ctx->dIrrUnpacked, ctx->dDepUnpacked, ctx->dMissQueue, ctx->dFrontQueue, ctx->dIrrNext, ctx->dDepNext, ctx->dStateNext,
                     ctx->dPerm, ctx->dOrder, ctx->dBlockedOrder, ctx->dBlendW};
     for (void* p : ptrs) if (p) cudaFree(p);
     ctx->dIrrWork = ctx->dIrrSampled = ctx->dDepWork = ctx->dDepSampled = ctx->dStateWork = ctx->dStateSampled = ctx->dIndicesList = nullptr;
     ctx->dIrrNext = ctx->dDepNext = ctx->dStateNext = nullptr;
     ctx->dPerm = ctx->dOrder = ctx->dBlockedOrder = nullptr; ctx->dBlendW = nullptr; ctx->shardOrderReady = false;
     ctx->dDirs = nullptr; ctx->dRays = nullptr; ctx->dHits = nullptr; ctx->dShadowQueue = nullptr; ctx->dQueueCount = nullptr; ctx->dShadowFlags = nullptr;
-    ctx->dIrrUnpacked = ctx->dDepUnpacked = nullptr;
+    ctx->dIrrUnpacked = ctx->dDepUnpacked = nullptr; ctx->dMissQueue = ctx->dFrontQueue = nullptr;
     ctx->probesReady = false;
 }
 static void freeShadow(vkx_ctx* ctx) {
@@ -192,13 +192,16 @@ static int checkGrid(vkx_ctx* ctx, const vkx_grid_info* g) {
 
 static int allocProbeScratch(vkx_ctx* ctx) {
     // ray-level scratch for one chunk of probes
-    void* old[] = {ctx->dRays, ctx->dHits, ctx->dShadowQueue, ctx->dShadowFlags, ctx->dIrrUnpacked, ctx->dDepUnpacked};
+    void* old[] = {ctx->dRays, ctx->dHits, ctx->dShadowQueue, ctx->dShadowFlags, ctx->dIrrUnpacked, ctx->dDepUnpacked, ctx->dMissQueue, ctx->dFrontQueue};
     for (void* p : old) if (p) cudaFree(p);
+    ctx->dMissQueue = ctx->dFrontQueue = nullptr;
     ctx->dRays = nullptr; ctx->dHits = nullptr; ctx->dShadowQueue = nullptr; ctx->dShadowFlags = nullptr; ctx->dIrrUnpacked = ctx->dDepUnpacked = nullptr;
     const size_t maxRays = size_t(ctx->chunkProbes) * VKX_MAX_RAYS_PER_PROBE;
     CUDA_TRY(ctx, cudaMalloc(&ctx->dRays, maxRays * sizeof(float4)));
     CUDA_TRY(ctx, cudaMalloc(&ctx->dHits, maxRays * sizeof(vkx_hit)));
     CUDA_TRY(ctx, cudaMalloc(&ctx->dShadowQueue, maxRays * 2 * sizeof(float4)));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->dMissQueue, maxRays * 4));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->dFrontQueue, maxRays * 4));
     if (ctx->debugBuffers) {
         CUDA_TRY(ctx, cudaMalloc(&ctx->dShadowFlags, maxRays));
         CUDA_TRY(ctx, cudaMalloc(&ctx->dIrrUnpacked, size_t(ctx->probeCount) * 36 * 3 * 4));
@@ -221,7 +224,7 @@ int vkx_probes_init(vkx_ctx* ctx, const vkx_grid_info* grid) {
     for (int i = 0; i < 6; ++i) { CUDA_TRY(ctx, cudaMalloc(bufs[i], sizes[i])); CUDA_TRY(ctx, cudaMemsetAsync(*bufs[i], 0, sizes[i], ctx->stream)); }
     CUDA_TRY(ctx, cudaMalloc(&ctx->dIndicesList, stBytes));
     CUDA_TRY(ctx, cudaMalloc(&ctx->dDirs, 512 * sizeof(float4)));
-    CUDA_TRY(ctx, cudaMalloc(&ctx->dQueueCount, 16));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->dQueueCount, 32));
     CUDA_TRY(ctx, cudaMalloc(&ctx->dPerm, VKX_MAX_RAYS_PER_PROBE * 4));
     CUDA_TRY(ctx, cudaMalloc(&ctx->dOrder, stBytes));
     CUDA_TRY(ctx, cudaMalloc(&ctx->dBlockedOrder, stBytes));

@@ -80,7 +80,8 @@ struct vkx_ctx {
     float4* dRays = nullptr;            // [chunkProbes][N] (rgb, depth)
     vkx_hit* dHits = nullptr;           // [chunkProbes][N]
     float4* dShadowQueue = nullptr;     // [chunkProbes*N][2]
-    uint32_t* dQueueCount = nullptr;
+    uint32_t* dQueueCount = nullptr;    // 8 counters, see ddgiUpdate
+    uint32_t* dMissQueue = nullptr; uint32_t* dFrontQueue = nullptr; // ray indices sorted by what they need next
     uint8_t* dShadowFlags = nullptr;    // debug
     float* dIrrUnpacked = nullptr; float* dDepUnpacked = nullptr; // debug, full count
     bool debugBuffers = false;
