@@ -25,7 +25,9 @@ __device__ __forceinline__ Ray makeRay(float ox, float oy, float oz, float dx, f
     return r;
 }
 
-__device__ __forceinline__ float byteToFloat(uint32_t w, int i) { return __uint2float_rn((w >> (8 * i)) & 0xFFu); }
+// float(byte i of w), exactly, without the conversion (XU) pipe: PRMT builds 0x4B0000qq = 2^23 + q, one FADD removes 2^23.
+// (profiles/r01c: I2F.U8 saturated the XU pipe at 94 % in the node test.)
+__device__ __forceinline__ float byteToFloat(uint32_t w, int i) { return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u + uint32_t(i))), 8388608.0f); }
 
 // 8 quantised child boxes of one axis: near plane bytes (n0: slots 0-3, n1: slots 4-7) and far plane bytes.
 struct AxisQ { uint32_t n0, n1, f0, f1; };
