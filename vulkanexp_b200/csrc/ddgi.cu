@@ -77,7 +77,7 @@ struct PrimarySrc {
 };
 
 // Persistent warps; see ptrace.cuh.
-__global__ void __launch_bounds__(128) k_trace_primary(DeviceScene sc, TraceParams tp, RayMap rm, const uint32_t* __restrict__ probeIndices,
+__global__ void __launch_bounds__(128, 8) k_trace_primary(DeviceScene sc, TraceParams tp, RayMap rm, const uint32_t* __restrict__ probeIndices,
                                                        const float4* __restrict__ dirs, vkx_hit* __restrict__ hits, float4* __restrict__ rays,
                                                        uint32_t* __restrict__ missQueue, uint32_t* __restrict__ frontQueue, uint32_t* __restrict__ counters) {
     PrimarySrc src; src.tp = tp; src.rm = rm; src.probeIndices = probeIndices; src.dirs = dirs; src.hits = hits; src.ri = 0;
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(128) k_shade_miss(ShadeParams sp, const uint32
 }
 
 // closesthit.glsl:143-288 (NO_REFLECTION, untextured) over the dense front-hit queue; appends the shadow rays
-__global__ void __launch_bounds__(128) k_shade_front(DeviceScene sc, DeviceProbes pr, ShadeParams sp, const uint32_t* __restrict__ probeIndices,
+__global__ void __launch_bounds__(128, 6) k_shade_front(DeviceScene sc, DeviceProbes pr, ShadeParams sp, const uint32_t* __restrict__ probeIndices,
                                                      const float4* __restrict__ dirs, const vkx_hit* __restrict__ hits, const uint32_t* __restrict__ frontQueue,
                                                      uint32_t* __restrict__ counters, float4* __restrict__ rays, float4* __restrict__ queue) {
     const uint32_t n = counters[4];
@@ -181,7 +181,7 @@ struct ShadowSrc {
     }
 };
 
-__global__ void __launch_bounds__(128) k_trace_shadow(DeviceScene sc, vkx_light light, const float4* __restrict__ queue, const uint32_t* __restrict__ queueCount,
+__global__ void __launch_bounds__(128, 8) k_trace_shadow(DeviceScene sc, vkx_light light, const float4* __restrict__ queue, const uint32_t* __restrict__ queueCount,
                                                       float4* __restrict__ rays, uint8_t* __restrict__ shadowFlags, uint32_t* __restrict__ counter) {
     ShadowSrc src; src.light = light; src.queue = queue; src.rays = rays; src.shadowFlags = shadowFlags; src.count = *queueCount; src.ri = 0; src.lx = src.ly = src.lz = 0.f;
     persistentTrace<true>(sc.nodes, sc.tris, src, src.count, counter);

@@ -1,0 +1,34 @@
+"""Probe-volume sharding plan (host logic of vkx_probes_update_sharded, csrc/api.cu).
+
+The z range of the grid is cut into K chunks of s*nranks slices; inside chunk k rank r owns slices
+[k*s*n + r*s, k*s*n + (r+1)*s). A chunk's atlas rows are contiguous, so one all-gather per atlas per chunk assembles
+the next sampled atlases on every rank while the following chunk is traced. Probes are independent within a frame
+(reference src/shaders/irradiance.glsl:15-17,32-38: linear index and atlas row are monotone in z), so no reduction
+crosses ranks and the result equals the single-GPU update bit for bit.
+"""
+
+
+def chunk_plan(rz: int, nranks: int):
+    """(slices per rank per chunk, number of chunks); mirrors the C++ choice (about 4 chunks when rz allows)."""
+    if rz % nranks != 0:
+        raise ValueError("grid z resolution %d is not divisible by %d ranks" % (rz, nranks))
+    s = max(1, rz // (nranks * 4))
+    while (rz // nranks) % s != 0:
+        s -= 1
+    return s, rz // (nranks * s)
+
+
+def rank_slices(rz: int, nranks: int, rank: int):
+    """z-slices owned by `rank`, chunk by chunk: list of (z0, z1)."""
+    s, K = chunk_plan(rz, nranks)
+    return [(k * s * nranks + rank * s, k * s * nranks + (rank + 1) * s) for k in range(K)]
+
+
+def rank_probe_indices(resolution, nranks: int, rank: int):
+    """Linear probe indices traced by `rank`, in chunk order."""
+    rx, ry, rz = resolution
+    plane = rx * ry
+    out = []
+    for z0, z1 in rank_slices(rz, nranks, rank):
+        out.extend(range(z0 * plane, z1 * plane))
+    return out
