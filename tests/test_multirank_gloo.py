@@ -23,12 +23,12 @@ def test_chunk_plan_partitions_the_volume():
                 with pytest.raises(ValueError):
                     chunk_plan(rz, n)
                 continue
-            s, K = chunk_plan(rz, n)
+            s, K = chunk_plan(rz, n, 2048)
             assert s * n * K == rz
-            owned = sorted(z for r in range(n) for (a, b) in rank_slices(rz, n, r) for z in range(a, b))
+            owned = sorted(z for r in range(n) for (a, b) in rank_slices(rz, n, r, 2048) for z in range(a, b))
             assert owned == list(range(rz))
             for k in range(K):  # within a chunk, ranks own consecutive equal blocks -> plain all-gather layout
-                blocks = [rank_slices(rz, n, r)[k] for r in range(n)]
+                blocks = [rank_slices(rz, n, r, 2048)[k] for r in range(n)]
                 assert all(blocks[r][1] == blocks[r + 1][0] for r in range(n - 1)) and len({b - a for a, b in blocks}) == 1
 
 
@@ -58,12 +58,12 @@ def _worker(rank, world, port, out_dir):
     gen = OrientationGenerator()
     rx, ry, rz = grid.resolution
     plane = rx * ry
-    s, K = chunk_plan(rz, world)
+    s, K = chunk_plan(rz, world, 4096)  # small plane value -> 2 chunks in this tiny test
     for frame in range(3):
         R = gen.next()
         grid.hysteresis = 0.4 * frame
         # every rank holds the previous frame's full sampled atlases; trace + blend own slices only
-        idx = np.array([p for (z0, z1) in rank_slices(rz, world, rank) for p in range(z0 * plane, z1 * plane)], dtype=np.uint32)
+        idx = np.array([p for (z0, z1) in rank_slices(rz, world, rank, 4096) for p in range(z0 * plane, z1 * plane)], dtype=np.uint32)
         o.probes_update(grid, light, R, idx, 1)
         irr, dep, st, _ = o.probes_download()
         nirr, ndep, nst = np.zeros_like(irr), np.zeros_like(dep), np.zeros_like(st)

@@ -1,0 +1,29 @@
+"""Sun-shadow pass timing (BASELINE.json configs[2]): synthetic dungeon-like scene, 3840x2160, 1 spp + X/Y depth-aware
+Gaussian + temporal accumulation, camera path of 16 frames. Prints one JSON line (secondary metric; bench.py is the contract)."""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from vulkanexp_b200 import scene_format, synth
+from vulkanexp_b200._lib import Context
+from vulkanexp_b200.pods import Light, make_camera
+
+W, H = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (3840, 2160)
+s = synth.make_cfg3(); flat = scene_format.flatten(s)
+g = Context(0); g.scene_upload(flat); g.bvh_build()
+info = g.bvh_info()
+g.shadow_set_noise(synth.blue_noise_like(64, 64)); g.shadow_init(W, H)
+light = Light.default()
+cams = [make_camera((-20.0 + 1.2 * f, 2.2, -18.0 + 0.9 * f), (0.0 + 0.5 * f, 1.5, 0.0), aspect=W / H, frame_index=f) for f in range(16)]
+prev = cams[0]; ms = []; gb = []
+for f, cam in enumerate(cams):
+    t0 = time.perf_counter(); g.gbuffer_generate(cam); gb.append((time.perf_counter() - t0) * 1e3)
+    g.shadow_frame(cam, prev, light)
+    ms.append(g.shadow_timings()); prev = cam
+pd, _ = g.gbuffer_download()
+steady = ms[4:]
+avg = {k: float(np.mean([m[k] for m in steady])) for k in steady[0]}
+px = W * H
+print(json.dumps({"metric": "sun_shadow_pass_ms", "value": avg["full"], "unit": "ms", "width": W, "height": H, "triangles": int(info.numTriangles), "stages_ms": avg,
+                  "gbuffer_fixture_ms": float(np.mean(gb[4:])), "geometry_pixels": float((pd[..., 3] > 0).mean()),
+                  "filter_bytes_per_px": 48 + 64, "filter_gbs": px * (48 + 64) / ((avg["filter_x"] + avg["filter_y"]) * 1e-3) / 1e9,
+                  "shadow_rays_per_s": px * float((pd[..., 3] > 0).mean()) / (avg["trace"] * 1e-3)}))

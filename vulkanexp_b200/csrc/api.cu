@@ -484,9 +484,11 @@ int vkx_probes_update_sharded(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx
     if (rz % n != 0) return vkx_fail(ctx, VKX_E_INVALID, "grid z resolution %u is not divisible by %u ranks", rz, n);
     const size_t irrBytes = size_t(ctx->irrW) * ctx->irrH * 4, depBytes = size_t(ctx->depW) * ctx->depH * 4, stBytes = size_t(ctx->probeCount) * 4;
     if (!ctx->dIrrNext) { CUDA_TRY(ctx, cudaMalloc(&ctx->dIrrNext, irrBytes)); CUDA_TRY(ctx, cudaMalloc(&ctx->dDepNext, depBytes)); CUDA_TRY(ctx, cudaMalloc(&ctx->dStateNext, stBytes)); }
-    uint32_t s = std::max(1u, rz / (n * 4u));
-    while ((rz / n) % s != 0) --s;
-    const uint32_t K = rz / (n * s);
+    // chunks of at least ~8192 probes per rank (smaller launches do not fill the persistent kernels), at most 4 chunks
+    const uint32_t slicesPerRank = rz / n;
+    uint32_t K = std::min(4u, std::max(1u, (slicesPerRank * plane) / 8192u));
+    while (slicesPerRank % K != 0) --K;
+    const uint32_t s = slicesPerRank / K;
     ncclComm_t comm = reinterpret_cast<ncclComm_t>(ctx->comm);
     cudaStream_t st = ctx->stream, cs = ctx->commStream;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], st));

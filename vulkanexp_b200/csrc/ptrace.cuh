@@ -10,7 +10,7 @@
 #pragma once
 #include "traverse.cuh"
 
-#define PT_CHUNK 256u
+#define PT_CHUNK 64u
 #define PT_REFILL_MIN 8 // fetch when at least this many lanes are idle (or all remaining lanes are idle)
 
 // Src must provide:

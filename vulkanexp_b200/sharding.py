@@ -8,19 +8,21 @@ crosses ranks and the result equals the single-GPU update bit for bit.
 """
 
 
-def chunk_plan(rz: int, nranks: int):
-    """(slices per rank per chunk, number of chunks); mirrors the C++ choice (about 4 chunks when rz allows)."""
+def chunk_plan(rz: int, nranks: int, plane: int = 512):
+    """(slices per rank per chunk, number of chunks); mirrors the C++ choice: chunks of at least ~8192 probes per rank,
+    at most 4 chunks. `plane` = rx*ry probes per z-slice."""
     if rz % nranks != 0:
         raise ValueError("grid z resolution %d is not divisible by %d ranks" % (rz, nranks))
-    s = max(1, rz // (nranks * 4))
-    while (rz // nranks) % s != 0:
-        s -= 1
-    return s, rz // (nranks * s)
+    per_rank = rz // nranks
+    k = min(4, max(1, (per_rank * plane) // 8192))
+    while per_rank % k != 0:
+        k -= 1
+    return per_rank // k, k
 
 
-def rank_slices(rz: int, nranks: int, rank: int):
+def rank_slices(rz: int, nranks: int, rank: int, plane: int = 512):
     """z-slices owned by `rank`, chunk by chunk: list of (z0, z1)."""
-    s, K = chunk_plan(rz, nranks)
+    s, K = chunk_plan(rz, nranks, plane)
     return [(k * s * nranks + rank * s, k * s * nranks + (rank + 1) * s) for k in range(K)]
 
 
@@ -29,6 +31,6 @@ def rank_probe_indices(resolution, nranks: int, rank: int):
     rx, ry, rz = resolution
     plane = rx * ry
     out = []
-    for z0, z1 in rank_slices(rz, nranks, rank):
+    for z0, z1 in rank_slices(rz, nranks, rank, plane):
         out.extend(range(z0 * plane, z1 * plane))
     return out
