@@ -49,6 +49,7 @@ def _compare_update(o, g, frame):
     irr_flip = float((io != ig).mean())
     dep_flip = float((do != dg).mean())
     st_diff = float((sto != stg).mean())
+    print("frame %d max rel err: rays %.2e, irradiance %.2e, depth %.2e" % (frame, e.max(), rel_err(uio, uig).max(), rel_err(udo, udg).max()))
     return irr_flip, dep_flip, st_diff
 
 

@@ -13,36 +13,9 @@
 #include "traverse.cuh"
 #include "ptrace.cuh"
 #include "shade.cuh"
+#include "ddgi_common.cuh"
 
 namespace {
-
-// Thread -> ray mapping shared by the trace and shade kernels. A warp handles a tile of 8 probes x 4 directions: the 8 probes are
-// a 2x2x2 block of the grid (`order` lists slots block by block) and the 4 directions are neighbours on the sphere (`perm`
-// sorts the frame's direction table along a Morton curve of the octahedral map). Rays of a warp are then near-parallel with
-// nearby origins, instead of 32 consecutive spherical-Fibonacci directions of one probe. Results are stored by (slot, ray), so
-// the mapping changes scheduling only.
-struct RayMap {
-    uint32_t count, raysPerProbe, numDirGroups, numThreads;
-    const uint32_t* order; // [count] position -> slot
-    const uint32_t* perm;  // [raysPerProbe] position -> ray index
-};
-__device__ __forceinline__ bool mapRay(const RayMap& m, uint32_t t, uint32_t& slot, uint32_t& ray) {
-    const uint32_t tile = t >> 5, lane = t & 31u;
-    const uint32_t pg = tile / m.numDirGroups, dg = tile - pg * m.numDirGroups;
-    const uint32_t j = pg * 8u + (lane & 7u), k = dg * 4u + (lane >> 3);
-    if (j >= m.count || k >= m.raysPerProbe) return false;
-    slot = __ldg(m.order + j); ray = __ldg(m.perm + k);
-    return true;
-}
-
-__device__ __forceinline__ uint32_t warpAppend(uint32_t* counter) { // warp-aggregated queue slot allocation
-    const unsigned m = __activemask();
-    const int lane = threadIdx.x & 31, leader = __ffs(int(m)) - 1;
-    uint32_t base = 0;
-    if (lane == leader) base = atomicAdd(counter, uint32_t(__popc(m)));
-    base = __shfl_sync(m, base, leader);
-    return base + uint32_t(__popc(m & ((1u << lane) - 1u)));
-}
 
 struct TraceParams {
     vkx_grid_info grid;
@@ -83,85 +56,6 @@ __global__ void __launch_bounds__(128, 8) k_trace_primary(DeviceScene sc, TraceP
     PrimarySrc src; src.tp = tp; src.rm = rm; src.probeIndices = probeIndices; src.dirs = dirs; src.hits = hits; src.ri = 0;
     src.rays = rays; src.missQueue = missQueue; src.frontQueue = frontQueue; src.counters = counters;
     persistentTrace<false>(sc.nodes, sc.tris, src, rm.numThreads, counters + 1);
-}
-
-struct ShadeParams {
-    vkx_grid_info grid;
-    vkx_light light;
-    uint32_t raysPerProbe, numRays;
-};
-
-// miss.rmiss + sky.glsl over the dense miss queue
-__global__ void __launch_bounds__(128) k_shade_miss(ShadeParams sp, const uint32_t* __restrict__ probeIndices, const float4* __restrict__ dirs,
-                                                    const uint32_t* __restrict__ queue, const uint32_t* __restrict__ counters, float4* __restrict__ rays, uint8_t* __restrict__ shadowFlags) {
-    const uint32_t n = counters[3];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t ri = queue[i];
-        const uint32_t slot = ri / sp.raysPerProbe, ray = ri - slot * sp.raysPerProbe;
-        int ix, iy, iz; probeGridIndex(__ldg(probeIndices + slot), sp.grid, ix, iy, iz);
-        const v3 origin = probeWorldPos(ix, iy, iz, sp.grid);
-        const float4 d4 = __ldg(dirs + ray);
-        const v3 c = skyColor(origin, mk3(d4.x, d4.y, d4.z), mk3(sp.light.direction[0], sp.light.direction[1], sp.light.direction[2]),
-                              mk3(sp.light.color[0], sp.light.color[1], sp.light.color[2]), sp.light.color[3]);
-        rays[ri] = make_float4(c.x, c.y, c.z, -1.0f);
-        if (shadowFlags) shadowFlags[ri] = 0;
-    }
-}
-
-// closesthit.glsl:143-288 (NO_REFLECTION, untextured) over the dense front-hit queue; appends the shadow rays
-__global__ void __launch_bounds__(128, 6) k_shade_front(DeviceScene sc, DeviceProbes pr, ShadeParams sp, const uint32_t* __restrict__ probeIndices,
-                                                     const float4* __restrict__ dirs, const vkx_hit* __restrict__ hits, const uint32_t* __restrict__ frontQueue,
-                                                     uint32_t* __restrict__ counters, float4* __restrict__ rays, float4* __restrict__ queue) {
-    const uint32_t n = counters[4];
-    const GridConsts gc = makeGridConsts(sp.grid);
-    const v3 lightDir = mk3(sp.light.direction[0], sp.light.direction[1], sp.light.direction[2]);
-    const v3 lightColor = mk3(sp.light.color[0], sp.light.color[1], sp.light.color[2]);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t ri = frontQueue[i];
-        const uint32_t slot = ri / sp.raysPerProbe, ray = ri - slot * sp.raysPerProbe;
-        int ix, iy, iz; probeGridIndex(__ldg(probeIndices + slot), sp.grid, ix, iy, iz);
-        const v3 origin = probeWorldPos(ix, iy, iz, sp.grid);
-        const float4 d4 = __ldg(dirs + ray);
-        const v3 direction = mk3(d4.x, d4.y, d4.z);
-        const vkx_hit h = hits[ri];
-        const float u = h.u, v = h.v;
-        const float bx = 1.0f - u - v, by = u, bz = v;
-        const v3 position = direction * h.t + origin;
-        const uint32_t meshEntry = __ldg(&sc.instances[h.instance].meshEntry);
-        const vkx_offset_entry oe = sc.offsets[meshEntry];
-        const uint32_t prim = h.primitive & 0x7FFFFFFFu;
-        v3 n3[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const uint32_t vi = oe.vertexOffset + __ldg(sc.indices + oe.indexOffset + 3 * prim + c);
-            const float* nn = sc.vertices[vi].normal;
-            n3[c] = mk3(__ldg(nn), __ldg(nn + 1), __ldg(nn + 2));
-        }
-        const vkx_material m = sc.materials[oe.materialIndex];
-        const v3 tsn = norm3(n3[0] * bx + n3[1] * by + n3[2] * bz);
-        const float* W = sc.worldToObject + size_t(h.instance) * 9; // W[row][col]
-        // vec3(tsn * worldToObject): component j = dot(tsn, column j)
-        const v3 normal = norm3(mk3(dot3(tsn, mk3(W[0], W[3], W[6])), dot3(tsn, mk3(W[1], W[4], W[7])), dot3(tsn, mk3(W[2], W[5], W[8]))));
-        const v3 albedo = mk3(m.baseColorFactor[0], m.baseColorFactor[1], m.baseColorFactor[2]);
-        const float metalness = m.metallicFactor, roughness = m.roughnessFactor;
-        v3 color = mk3(0.0f) + mk3(m.emissiveFactor[0], m.emissiveFactor[1], m.emissiveFactor[2]);
-        const v3 f0 = mk3(0.04f);
-        v3 diffuseColor = albedo * (1.0f - f0);
-        diffuseColor = diffuseColor * (1.0f - metalness);
-        const v3 specularColor = mix3(f0, albedo, metalness);
-        const v3 reflectDir = reflect3(direction, normal);
-        v3 reflection, indirectLight;
-        sampleProbes2(pr, gc, position, reflectDir, normal, -direction, reflection, indirectLight);
-        color = color + specularColor * reflection;
-        color = color + indirectLight * diffuseColor;
-        rays[ri] = make_float4(color.x, color.y, color.z, h.t); // value if the sun is occluded
-        // direct term, applied by k_trace_shadow if the shadow ray escapes
-        v3 lit = color + pbrMetallicRoughness(normal, norm3(-direction), lightColor, lightDir, albedo, metalness, roughness);
-        if (lightDir.y < 0.0f) lit = lit * (1.0f - clampS(-lightDir.y, 0.0f, 0.1f) / 0.1f);
-        const uint32_t qi = warpAppend(counters);
-        queue[2 * size_t(qi)] = make_float4(position.x, position.y, position.z, __uint_as_float(ri));
-        queue[2 * size_t(qi) + 1] = make_float4(lit.x, lit.y, lit.z, 0.0f);
-    }
 }
 
 struct ShadowSrc {
@@ -486,8 +380,8 @@ int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* /*unused*/,
         k_trace_primary<<<persistentBlocks, 128, 0, st>>>(sc, tp, rm, idx, ctx->dDirs, ctx->dHits, ctx->dRays, ctx->dMissQueue, ctx->dFrontQueue, ctx->dQueueCount); LAUNCH_CHECK(ctx);
         if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[1], st));
         const unsigned shadeBlocks = std::min<unsigned>(divUp(numRays, 128), unsigned(ctx->smCount) * 16u);
-        k_shade_miss<<<shadeBlocks, 128, 0, st>>>(sp, idx, ctx->dDirs, ctx->dMissQueue, ctx->dQueueCount, ctx->dRays, ctx->debugBuffers ? ctx->dShadowFlags : nullptr); LAUNCH_CHECK(ctx);
-        k_shade_front<<<shadeBlocks, 128, 0, st>>>(sc, pr, sp, idx, ctx->dDirs, ctx->dHits, ctx->dFrontQueue, ctx->dQueueCount, ctx->dRays, ctx->dShadowQueue); LAUNCH_CHECK(ctx);
+        launchShadeMiss(shadeBlocks, st, sp, idx, ctx->dDirs, ctx->dMissQueue, ctx->dQueueCount, ctx->dRays); LAUNCH_CHECK(ctx);
+        launchShadeFront(shadeBlocks, st, sc, pr, sp, idx, ctx->dDirs, ctx->dHits, ctx->dFrontQueue, ctx->dQueueCount, ctx->dRays, ctx->dShadowQueue); LAUNCH_CHECK(ctx);
         if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[2], st));
         if (ctx->debugBuffers) CUDA_TRY(ctx, cudaMemsetAsync(ctx->dShadowFlags, 0, numRays, st));
         k_trace_shadow<<<persistentBlocks, 128, 0, st>>>(sc, light, ctx->dShadowQueue, ctx->dQueueCount, ctx->dRays, ctx->debugBuffers ? ctx->dShadowFlags : nullptr, ctx->dQueueCount + 2); LAUNCH_CHECK(ctx);

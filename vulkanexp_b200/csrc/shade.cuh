@@ -43,6 +43,19 @@ __device__ __forceinline__ v3 gridCellSize(const vkx_grid_info& g) {
 __device__ __forceinline__ v3 probeWorldPos(int ix, int iy, int iz, const vkx_grid_info& g) {
     return mk3(float(ix), float(iy), float(iz)) * gridCellSize(g) + mk3(g.extentMin[0], g.extentMin[1], g.extentMin[2]);
 }
+// Exact versions (explicit _rn intrinsics: immune to the translation unit's fmad / prec-div flags). Probe origins and hit
+// positions feed traversal, whose results must stay bit-identical to the oracle.
+__device__ __forceinline__ v3 gridCellSizeExact(const vkx_grid_info& g) {
+    return mk3(__fdiv_rn(__fsub_rn(g.extentMax[0], g.extentMin[0]), float(g.resolution[0] - 1)), __fdiv_rn(__fsub_rn(g.extentMax[1], g.extentMin[1]), float(g.resolution[1] - 1)),
+               __fdiv_rn(__fsub_rn(g.extentMax[2], g.extentMin[2]), float(g.resolution[2] - 1)));
+}
+__device__ __forceinline__ v3 probeWorldPosExact(int ix, int iy, int iz, const vkx_grid_info& g) {
+    const v3 c = gridCellSizeExact(g);
+    return mk3(__fadd_rn(__fmul_rn(float(ix), c.x), g.extentMin[0]), __fadd_rn(__fmul_rn(float(iy), c.y), g.extentMin[1]), __fadd_rn(__fmul_rn(float(iz), c.z), g.extentMin[2]));
+}
+__device__ __forceinline__ v3 pointOnRayExact(v3 origin, v3 direction, float t) { // direction * t + origin
+    return mk3(__fadd_rn(__fmul_rn(direction.x, t), origin.x), __fadd_rn(__fmul_rn(direction.y, t), origin.y), __fadd_rn(__fmul_rn(direction.z, t), origin.z));
+}
 __device__ __forceinline__ void probeGridIndex(uint32_t index, const vkx_grid_info& g, int& ix, int& iy, int& iz) {
     uint32_t rx = uint32_t(g.resolution[0]), ry = uint32_t(g.resolution[1]);
     ix = int(index % rx); iy = int((index % (rx * ry)) / rx); iz = int(index / (rx * ry));
@@ -115,7 +128,7 @@ struct GridConsts {
 __device__ __forceinline__ bool isPow2f(float x) { return (__float_as_uint(x) & 0x007FFFFFu) == 0u && x > 0.0f; }
 __device__ __forceinline__ GridConsts makeGridConsts(const vkx_grid_info& grid) {
     GridConsts c;
-    c.cell = gridCellSize(grid); c.acell = abs3(c.cell);
+    c.cell = gridCellSizeExact(grid); c.acell = abs3(c.cell);
     c.extentMin = mk3(grid.extentMin[0], grid.extentMin[1], grid.extentMin[2]);
     c.usx = float(grid.resolution[0] * grid.resolution[1]); c.usy = float(grid.resolution[2]);
     c.pow2x = isPow2f(c.usx); c.pow2y = isPow2f(c.usy);
@@ -194,7 +207,8 @@ __device__ __forceinline__ v3 finishProbes(ProbeAccum a) {
 // resultA = sampleProbes(position, normalA, toCamera), resultB = sampleProbes(position, normalB, toCamera)
 __device__ inline void sampleProbes2(const DeviceProbes& p, const GridConsts& gc, v3 position, v3 normalA, v3 normalB, v3 toCamera, v3& resultA, v3& resultB) {
     const vkx_grid_info& grid = p.grid;
-    const v3 gridCoords = (position - gc.extentMin) / gc.acell;
+    // exact quotient: int(gridCoords) selects the 8 probes
+    const v3 gridCoords = mk3(__fdiv_rn(__fsub_rn(position.x, gc.extentMin.x), gc.acell.x), __fdiv_rn(__fsub_rn(position.y, gc.extentMin.y), gc.acell.y), __fdiv_rn(__fsub_rn(position.z, gc.extentMin.z), gc.acell.z));
     resultA = mk3(0.0f); resultB = mk3(0.0f);
     if (gridCoords.x < 0.0f || gridCoords.y < 0.0f || gridCoords.z < 0.0f) return;
     const v3 biasedA = position + (normalA + toCamera) * grid.shadowBias;
