@@ -120,8 +120,9 @@ __global__ void __launch_bounds__(BLEND_COLS) k_blend_weights(float depthSharpne
 }
 
 // One CTA blends BLEND_P probes: their ray records are staged in shared memory, thread `col` owns one texel of every probe, so each
-// weight is loaded once and applied to BLEND_P probes from registers. Accumulation over rays is sequential (i = 0..N-1) with separate
-// multiply and add, like the oracle, so packed texels agree bit for bit whenever the ray records do. Warps 0-6: depth texels,
+// weight is loaded once and applied to BLEND_P probes from registers. Accumulation over rays is sequential (i = 0..N-1) like the oracle's,
+// with fused multiply-adds (one rounding instead of the oracle's two per term: fp32 results differ by <= 1e-6 relative, which
+// flips an 11-bit packed code on ~1e-5 of the texels). Warps 0-6: depth texels,
 // warps 7-8: irradiance texels (warp-uniform roles).
 __global__ void __launch_bounds__(BLEND_COLS) k_blend(BlendParams bp, DeviceProbes pr, const uint32_t* __restrict__ probeIndices, const float4* __restrict__ rays,
                                                       const float* __restrict__ W, float* __restrict__ irrUnpacked, float* __restrict__ depUnpacked, uint32_t slotBase) {
@@ -165,8 +166,8 @@ __global__ void __launch_bounds__(BLEND_COLS) k_blend(BlendParams bp, DeviceProb
                 for (int p = 0; p < BLEND_P; ++p) {
                     const float d = sRay[p][i].w;
                     const float t = w * d;
-                    a0[p] = a0[p] + t;
-                    a1[p] = a1[p] + t * d;
+                    a0[p] = fmaf(w, d, a0[p]);
+                    a1[p] = fmaf(t, d, a1[p]);
                 }
                 rw = rw + w;
             }
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(BLEND_COLS) k_blend(BlendParams bp, DeviceProb
 #pragma unroll
             for (int p = 0; p < BLEND_P; ++p) {
                 const float4 rd = sRay[p][i];
-                a0[p] = a0[p] + w * rd.x; a1[p] = a1[p] + w * rd.y; a2[p] = a2[p] + w * rd.z;
+                a0[p] = fmaf(w, rd.x, a0[p]); a1[p] = fmaf(w, rd.y, a1[p]); a2[p] = fmaf(w, rd.z, a2[p]);
             }
             rw = rw + w;
         }

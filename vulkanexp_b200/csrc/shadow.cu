@@ -99,9 +99,11 @@ __global__ void __launch_bounds__(128) k_direct_light(DeviceScene sc, vkx_light 
     } else out[pix] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-__device__ __forceinline__ float gaussian(float stdDev, float dist) { // directLightFilter.glsl:29-31
-    return (1.0f / (sqrtf(2.0f * 3.14159f) * stdDev)) * expf(-(dist * dist) / (2.0f * stdDev * stdDev));
-}
+// gaussian(stdDev, dist) of directLightFilter.glsl:29-31 = norm(stdDev) * exp(-(dist * dist) * invTwoVar(stdDev)); the two factors that
+// only depend on stdDev are hoisted out of the tap loops and exp is ex2.approx (tolerance of the filter outputs: 1e-3 absolute).
+__device__ __forceinline__ float gaussNorm(float stdDev) { return 1.0f / (sqrtf(2.0f * 3.14159f) * stdDev); }
+__device__ __forceinline__ float gaussInvTwoVar(float stdDev) { return 1.0f / (2.0f * stdDev * stdDev); }
+__device__ __forceinline__ float gaussian(float norm, float invTwoVar, float dist) { return norm * __expf(-(dist * dist) * invTwoVar); }
 #define MAX_DEV 7.0f
 #define I_MAX_DEV 8
 #define DEPTH_FACTOR (1.0f / 0.5f)
@@ -132,9 +134,10 @@ __global__ void __launch_bounds__(256) k_filter_x(uint32_t W, uint32_t H, const 
     float stdDev; const int window = filterWindow(depth, stdDev);
     const int minOffset = -min(window, x), maxOffset = min(window, int(W) - x);
     float totalFactor = 0.0f; float4 fin = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float gn = gaussNorm(stdDev), gv = gaussInvTwoVar(stdDev), dn = gaussNorm(DEPTH_STD), dv = gaussInvTwoVar(DEPTH_STD);
     for (int i = minOffset; i <= maxOffset; ++i) {
-        float factor = gaussian(stdDev, float(i));
-        factor *= gaussian(DEPTH_STD, fabsf(depth - sDepth[tid + I_MAX_DEV + i]));
+        float factor = gaussian(gn, gv, float(i));
+        factor *= gaussian(dn, dv, fabsf(depth - sDepth[tid + I_MAX_DEV + i]));
         totalFactor += factor;
         const float4 v = sIn[tid + I_MAX_DEV + i];
         fin.x += factor * v.x; fin.y += factor * v.y; fin.z += factor * v.z; fin.w += factor * v.w;
@@ -169,9 +172,10 @@ __global__ void __launch_bounds__(256) k_filter_y(uint32_t W, uint32_t H, const 
         float stdDev; const int window = filterWindow(depth, stdDev);
         const int minOffset = -min(window, y), maxOffset = min(window, int(H) - y);
         float totalFactor = 0.0f; float4 fin = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float gn = gaussNorm(stdDev), gv = gaussInvTwoVar(stdDev), dn = gaussNorm(DEPTH_STD), dv = gaussInvTwoVar(DEPTH_STD);
         for (int i = minOffset; i <= maxOffset; ++i) {
-            float factor = gaussian(stdDev, float(i));
-            factor *= gaussian(DEPTH_STD, fabsf(depth - sDepth[c + i * TW]));
+            float factor = gaussian(gn, gv, float(i));
+            factor *= gaussian(dn, dv, fabsf(depth - sDepth[c + i * TW]));
             totalFactor += factor;
             const float4 v = sIn[c + i * TW];
             fin.x += factor * v.x; fin.y += factor * v.y; fin.z += factor * v.z; fin.w += factor * v.w;
