@@ -106,9 +106,10 @@ int orc_probes_download_hits(orc_ctx* c, vkx_hit* hits, uint8_t* shadow) {
     if (shadow) std::memcpy(shadow, p.shadow.data(), p.shadow.size());
     return 0;
 }
-// counters of the last update: rays (primary + shadow), nodes visited, triangles tested, front hits
-int orc_probes_counters(orc_ctx* c, uint64_t out[4]) {
+// counters of the last update: primary rays, nodes visited, triangles tested, front hits, shadow rays, nodes, triangles
+int orc_probes_counters(orc_ctx* c, uint64_t out[7]) {
     out[0] = c->probes.counters.rays; out[1] = c->probes.counters.nodes; out[2] = c->probes.counters.tris; out[3] = c->probes.frontHits;
+    out[4] = c->probes.shadowCounters.rays; out[5] = c->probes.shadowCounters.nodes; out[6] = c->probes.shadowCounters.tris;
     return 0;
 }
 int orc_ray_directions(const float R[16], uint32_t count, float n, float* out) {

@@ -405,7 +405,7 @@ void classify(const Scene& s, Probes& p, const float orientation[16]) {
 
 // ---------------------------------------------------------------- traceProbes.rgen + closesthit.glsl + miss.rmiss
 static vec4 shadeRay(const Scene& s, const Probes& p, const vkx_light& light, vec3 origin, vec3 direction, float tmax,
-                     vkx_hit& hit, uint8_t& shadowFlag, obvh::Counters* ctr, uint64_t& front) {
+                     vkx_hit& hit, uint8_t& shadowFlag, obvh::Counters* ctr, obvh::Counters* sctr, uint64_t& front) {
     const float tmin = 0.01f; // traceProbes.rgen:27
     shadowFlag = 0;
     vec3 lightDir = V3(light.direction[0], light.direction[1], light.direction[2]);
@@ -445,7 +445,7 @@ static vec4 shadeRay(const Scene& s, const Probes& p, const vkx_light& light, ve
     vec3 indirectLight = sampleProbes(p, position, normal, -direction); // :248
     color += indirectLight * diffuseColor;
     // shadow ray :252-281 (tmin 0.1, tmax 10000, cull mask 0xFF, un-normalised light direction)
-    bool isShadowed = obvh::traceAny(s.bvh, &position.x, &lightDir.x, 0.1f, 10000.0f, 0xFFu, ctr);
+    bool isShadowed = obvh::traceAny(s.bvh, &position.x, &lightDir.x, 0.1f, 10000.0f, 0xFFu, sctr);
     shadowFlag = isShadowed ? 2 : 1;
     if (!isShadowed) {
         vec4 pbr = pbrMetallicRoughness(normal, normalize(-direction), lightColor, lightDir, albedo, metalness, roughness);
@@ -485,11 +485,11 @@ void update(const Scene& s, Probes& p, const vkx_grid_info& g, const vkx_light& 
 #else
     (void)threads;
 #endif
-    obvh::Counters total; uint64_t frontTotal = 0;
+    obvh::Counters total, stotal; uint64_t frontTotal = 0;
     // ---- trace + shade (traceProbes.rgen)
 #pragma omp parallel
     {
-        obvh::Counters ctr; uint64_t front = 0;
+        obvh::Counters ctr, sctr; uint64_t front = 0;
 #pragma omp for schedule(dynamic, 4)
         for (int64_t slot = 0; slot < int64_t(count); ++slot) {
             ivec3 probeIndex = probeLinearIndexToGridIndex(indices[slot], grid);
@@ -497,14 +497,14 @@ void update(const Scene& s, Probes& p, const vkx_grid_info& g, const vkx_light& 
             for (uint32_t r = 0; r < N; ++r) {
                 vec3 direction = V3(p.dirs[3 * r], p.dirs[3 * r + 1], p.dirs[3 * r + 2]);
                 size_t ri = size_t(slot) * N + r;
-                vec4 c = shadeRay(s, p, light, origin, direction, tmax, p.hits[ri], p.shadow[ri], &ctr, front);
+                vec4 c = shadeRay(s, p, light, origin, direction, tmax, p.hits[ri], p.shadow[ri], &ctr, &sctr, front);
                 p.rays[4 * ri + 0] = c.x; p.rays[4 * ri + 1] = c.y; p.rays[4 * ri + 2] = c.z; p.rays[4 * ri + 3] = c.w;
             }
         }
 #pragma omp critical
-        { total.nodes += ctr.nodes; total.tris += ctr.tris; total.rays += ctr.rays; frontTotal += front; }
+        { total.nodes += ctr.nodes; total.tris += ctr.tris; total.rays += ctr.rays; stotal.nodes += sctr.nodes; stotal.tris += sctr.tris; stotal.rays += sctr.rays; frontTotal += front; }
     }
-    p.counters = total; p.frontHits = frontTotal;
+    p.counters = total; p.shadowCounters = stotal; p.frontHits = frontTotal;
 
     // ---- blend (probesUpdate.glsl), decrees A.5.1-3
     float gridCellSize = length(probeGridCellSize(grid));

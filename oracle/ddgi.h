@@ -33,7 +33,8 @@ struct Probes {
     std::vector<float> irrUnpacked; // [count][36][3]  post-hysteresis fp32
     std::vector<float> depUnpacked; // [count][196][2]
     std::vector<float> dirs;        // [N][3] rotated ray directions of the last update
-    obvh::Counters counters;        // primary + shadow traversal counters of the last update
+    obvh::Counters counters;        // traversal counters of the primary rays of the last update
+    obvh::Counters shadowCounters;  // ... and of the shadow rays
     uint64_t frontHits = 0;
 };
 

@@ -130,9 +130,9 @@ class Oracle:
         return hits, sh
 
     def probes_counters(self):
-        c = np.zeros(4, dtype=np.uint64)
+        c = np.zeros(7, dtype=np.uint64)
         self.l.orc_probes_counters(self.h, _p(c))
-        return {"rays": int(c[0]), "nodes": int(c[1]), "tris": int(c[2]), "front": int(c[3])}
+        return {"rays": int(c[0]), "nodes": int(c[1]), "tris": int(c[2]), "front": int(c[3]), "shadow_rays": int(c[4]), "shadow_nodes": int(c[5]), "shadow_tris": int(c[6])}
 
     # shadows
     def shadow_set_noise(self, noise):

@@ -83,15 +83,16 @@ __device__ __forceinline__ float2 sphereToOctUV(v3 direction) { // irradiance.gl
     return make_float2(o.x * 0.5f + 0.5f, o.y * 0.5f + 0.5f);
 }
 
-// REPEAT addressing without integer division: atlas/noise coordinates produced on this path lie in [-1, 2*size), where one
-// conditional add/subtract equals the oracle's ((i % size) + size) % size.
+// REPEAT addressing without integer division or branches: atlas/noise coordinates produced on this path lie in [-size, 2*size)
+// (uv in [-1, 2)), where one conditional add/subtract equals the oracle's ((i % size) + size) % size.
 __device__ __forceinline__ void bilinearSetup(float u, uint32_t size, int& i0, int& i1, float& f) {
     float x = u * float(size) - 0.5f;
     float fl = floorf(x);
     f = x - fl;
     const int isz = int(size);
     int i = int(fl);
-    if (i < 0 || i >= isz) { i %= isz; if (i < 0) i += isz; } // rare general case
+    i += (i < 0) ? isz : 0;
+    i -= (i >= isz) ? isz : 0;
     i0 = i;
     i1 = (i0 + 1 == isz) ? 0 : i0 + 1;
 }
@@ -160,26 +161,31 @@ __device__ __forceinline__ float2 sphereToOctUVxy(v3 direction) {
 // This evaluates both in one pass; per call the arithmetic is the sequence of irradiance.glsl:145-237.
 struct ProbeAccum { v3 finalColor, fallbackColor; float totalWeight, totalFallbackWeight; };
 
-__device__ __forceinline__ void sampleProbesOne(const DeviceProbes& p, const GridConsts& gc, ProbeAccum& acc, v3 normal, float2 octN, v3 biasedPosition,
-                                                v3 probePosition, v3 directionToProbe, float tri, int tile, int cz) {
-    const v3 biasedDirectionToProbe = probePosition - biasedPosition;
-    const float bd2 = dot3(biasedDirectionToProbe, biasedDirectionToProbe);
-    const float bsq = sqrtf(bd2);
-    const float2 octD = sphereToOctUVxy(-(biasedDirectionToProbe * (1.0f / bsq)));
-    const float lcu = gc.cscale * octN.x, lcv = gc.cscale * octN.y;
-    const float ldu = gc.dscale * octD.x, ldv = gc.dscale * octD.y;
-    const float colorU = divScale(float(8 * tile + 1) * 0.125f + lcu, gc.usx, gc.invUsx, gc.pow2x);
-    const float colorV = divScale(float(8 * cz + 1) * 0.125f + lcv, gc.usy, gc.invUsy, gc.pow2y);
-    const float depthU = divScale(float(16 * tile + 1) * 0.0625f + ldu, gc.usx, gc.invUsx, gc.pow2x);
-    const float depthV = divScale(float(16 * cz + 1) * 0.0625f + ldv, gc.usy, gc.invUsy, gc.pow2y);
+struct BilinearTaps { int o00, o10, o01, o11; float fx, fy; }; // texel offsets + weights of one bilinear fetch
+__device__ __forceinline__ BilinearTaps makeTaps(float u, float v, uint32_t w, uint32_t h) {
+    int x0, x1, y0, y1; BilinearTaps t;
+    bilinearSetup(u, w, x0, x1, t.fx); bilinearSetup(v, h, y0, y1, t.fy);
+    t.o00 = y0 * int(w) + x0; t.o10 = y0 * int(w) + x1; t.o01 = y1 * int(w) + x0; t.o11 = y1 * int(w) + x1;
+    return t;
+}
+__device__ __forceinline__ float2 lerpDepth(const BilinearTaps& t, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    const float2 t00 = unpackRG16F(a), t10 = unpackRG16F(b), t01 = unpackRG16F(c), t11 = unpackRG16F(d);
+    const float gx = 1.0f - t.fx, gy = 1.0f - t.fy;
+    return make_float2((t00.x * gx + t10.x * t.fx) * gy + (t01.x * gx + t11.x * t.fx) * t.fy, (t00.y * gx + t10.y * t.fx) * gy + (t01.y * gx + t11.y * t.fx) * t.fy);
+}
+__device__ __forceinline__ v3 lerpIrradiance(const BilinearTaps& t, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    const float3 t00 = unpackR11G11B10(a), t10 = unpackR11G11B10(b), t01 = unpackR11G11B10(c), t11 = unpackR11G11B10(d);
+    const float gx = 1.0f - t.fx, gy = 1.0f - t.fy;
+    return mk3((t00.x * gx + t10.x * t.fx) * gy + (t01.x * gx + t11.x * t.fx) * t.fy, (t00.y * gx + t10.y * t.fx) * gy + (t01.y * gx + t11.y * t.fx) * t.fy,
+               (t00.z * gx + t10.z * t.fx) * gy + (t01.z * gx + t11.z * t.fx) * t.fy);
+}
+__device__ __forceinline__ void accumulateProbe(ProbeAccum& acc, v3 normal, v3 directionToProbe, float tri, float biasedDistToProbe, float2 depth, v3 color) {
     float weight = 1.0f;
     const float backfaceweight = maxS(0.0001f, (dot3(directionToProbe, normal) + 1.0f) * 0.5f);
     weight *= backfaceweight * backfaceweight + 0.2f;
     float fallbackWeight = weight;
-    const float2 depth = sampleDepthTex(p, depthU, depthV);
     const float mean = depth.x;
     const float variance = fabsf(depth.x * depth.x - depth.y);
-    const float biasedDistToProbe = bsq; // length(probePosition - biasedPosition)
     const float dd = maxS(biasedDistToProbe - mean, 0.0001f);
     float chebyshevWeight = variance / (variance + dd * dd);
     chebyshevWeight = maxS(chebyshevWeight * chebyshevWeight * chebyshevWeight, 0.0f); // pow(x, 3.0): within 2 ulp of powf
@@ -189,12 +195,32 @@ __device__ __forceinline__ void sampleProbesOne(const DeviceProbes& p, const Gri
     if (weight < crushThreshold) weight *= weight * weight * (1.0f / (crushThreshold * crushThreshold));
     weight *= tri;
     fallbackWeight *= tri;
-    v3 color = sampleIrradianceTex(p, colorU, colorV);
     color = mk3(sqrtf(color.x), sqrtf(color.y), sqrtf(color.z));
     acc.finalColor = acc.finalColor + weight * color;
     acc.totalWeight += weight;
     acc.fallbackColor = acc.fallbackColor + fallbackWeight * color;
     acc.totalFallbackWeight += fallbackWeight;
+}
+
+// One probe, both sampleProbes calls: all 16 atlas texels (2 x (4 depth + 4 irradiance)) are requested before any is used, so
+// the loads overlap instead of forming four dependent round trips to L2.
+__device__ __forceinline__ void sampleProbePair(const DeviceProbes& p, const GridConsts& gc, ProbeAccum& accA, ProbeAccum& accB, v3 normalA, v3 normalB, float2 octA, float2 octB,
+                                                v3 biasedA, v3 biasedB, v3 probePosition, v3 directionToProbe, float tri, int tile, int cz) {
+    const v3 bA = probePosition - biasedA, bB = probePosition - biasedB;
+    const float lenA = sqrtf(dot3(bA, bA)), lenB = sqrtf(dot3(bB, bB));
+    const float2 octDA = sphereToOctUVxy(-(bA * (1.0f / lenA))), octDB = sphereToOctUVxy(-(bB * (1.0f / lenB)));
+    const float cu0 = float(8 * tile + 1) * 0.125f, cv0 = float(8 * cz + 1) * 0.125f, du0 = float(16 * tile + 1) * 0.0625f, dv0 = float(16 * cz + 1) * 0.0625f;
+    const BilinearTaps tcA = makeTaps(divScale(cu0 + gc.cscale * octA.x, gc.usx, gc.invUsx, gc.pow2x), divScale(cv0 + gc.cscale * octA.y, gc.usy, gc.invUsy, gc.pow2y), p.irrW, p.irrH);
+    const BilinearTaps tcB = makeTaps(divScale(cu0 + gc.cscale * octB.x, gc.usx, gc.invUsx, gc.pow2x), divScale(cv0 + gc.cscale * octB.y, gc.usy, gc.invUsy, gc.pow2y), p.irrW, p.irrH);
+    const BilinearTaps tdA = makeTaps(divScale(du0 + gc.dscale * octDA.x, gc.usx, gc.invUsx, gc.pow2x), divScale(dv0 + gc.dscale * octDA.y, gc.usy, gc.invUsy, gc.pow2y), p.depW, p.depH);
+    const BilinearTaps tdB = makeTaps(divScale(du0 + gc.dscale * octDB.x, gc.usx, gc.invUsx, gc.pow2x), divScale(dv0 + gc.dscale * octDB.y, gc.usy, gc.invUsy, gc.pow2y), p.depW, p.depH);
+    const uint32_t* D = p.depSampled; const uint32_t* C = p.irrSampled;
+    const uint32_t dA0 = __ldg(D + tdA.o00), dA1 = __ldg(D + tdA.o10), dA2 = __ldg(D + tdA.o01), dA3 = __ldg(D + tdA.o11);
+    const uint32_t dB0 = __ldg(D + tdB.o00), dB1 = __ldg(D + tdB.o10), dB2 = __ldg(D + tdB.o01), dB3 = __ldg(D + tdB.o11);
+    const uint32_t cA0 = __ldg(C + tcA.o00), cA1 = __ldg(C + tcA.o10), cA2 = __ldg(C + tcA.o01), cA3 = __ldg(C + tcA.o11);
+    const uint32_t cB0 = __ldg(C + tcB.o00), cB1 = __ldg(C + tcB.o10), cB2 = __ldg(C + tcB.o01), cB3 = __ldg(C + tcB.o11);
+    accumulateProbe(accA, normalA, directionToProbe, tri, lenA, lerpDepth(tdA, dA0, dA1, dA2, dA3), lerpIrradiance(tcA, cA0, cA1, cA2, cA3));
+    accumulateProbe(accB, normalB, directionToProbe, tri, lenB, lerpDepth(tdB, dB0, dB1, dB2, dB3), lerpIrradiance(tcB, cB0, cB1, cB2, cB3));
 }
 __device__ __forceinline__ v3 finishProbes(ProbeAccum a) {
     if (a.totalWeight > 1e-3f) a.finalColor = a.finalColor * (1.0f / a.totalWeight);
@@ -232,8 +258,7 @@ __device__ inline void sampleProbes2(const DeviceProbes& p, const GridConsts& gc
         const v3 trilinear = mix3(1.0f - alpha, alpha, mk3(float(ox), float(oy), float(oz)));
         const float tri = trilinear.x * trilinear.y * trilinear.z + 0.001f;
         const int tile = cy * gc.rx + cx;
-        sampleProbesOne(p, gc, accA, normalA, octA, biasedA, probePosition, directionToProbe, tri, tile, cz);
-        sampleProbesOne(p, gc, accB, normalB, octB, biasedB, probePosition, directionToProbe, tri, tile, cz);
+        sampleProbePair(p, gc, accA, accB, normalA, normalB, octA, octB, biasedA, biasedB, probePosition, directionToProbe, tri, tile, cz);
     }
     resultA = finishProbes(accA);
     resultB = finishProbes(accB);
