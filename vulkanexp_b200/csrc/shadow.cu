@@ -56,9 +56,19 @@ __device__ __forceinline__ v3 rotateAxis(v3 p, v3 axis, float angle) { // common
     return mix3(dot3(axis, p) * axis, p, cosf(angle)) + cross3(axis, p) * sinf(angle);
 }
 
+// general REPEAT wrap (uv = pixel / 64 is far outside [0, 1), unlike the atlas coordinates bilinearSetup() handles)
+__device__ __forceinline__ void bilinearSetupRepeat(float u, uint32_t size, int& i0, int& i1, float& f) {
+    const float x = u * float(size) - 0.5f;
+    const float fl = floorf(x);
+    f = x - fl;
+    const int isz = int(size), i = int(fl);
+    i0 = ((i % isz) + isz) % isz;
+    i1 = (i0 + 1) % isz;
+}
+
 __device__ __forceinline__ float4 sampleNoise(const float* __restrict__ tex, uint32_t nw, uint32_t nh, float u, float v) { // linear, REPEAT
     int x0, x1, y0, y1; float fx, fy;
-    bilinearSetup(u, nw, x0, x1, fx); bilinearSetup(v, nh, y0, y1, fy);
+    bilinearSetupRepeat(u, nw, x0, x1, fx); bilinearSetupRepeat(v, nh, y0, y1, fy);
     const float4* t = reinterpret_cast<const float4*>(tex);
     const float4 t00 = __ldg(t + size_t(y0) * nw + x0), t10 = __ldg(t + size_t(y0) * nw + x1), t01 = __ldg(t + size_t(y1) * nw + x0), t11 = __ldg(t + size_t(y1) * nw + x1);
     const float gx = 1.0f - fx, gy = 1.0f - fy;

@@ -29,6 +29,11 @@ __device__ __forceinline__ Ray makeRay(float ox, float oy, float oz, float dx, f
 // (profiles/r01c: I2F.U8 saturated the XU pipe at 94 % in the node test.)
 __device__ __forceinline__ float byteToFloat(uint32_t w, int i) { return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u + uint32_t(i))), 8388608.0f); }
 
+// Same value through the conversion pipe (I2F.U8). The node test needs 48 byte->float conversions; splitting them between the XU pipe
+// (this) and the ALU/FMA pipes (byteToFloat) balances the pipes: profiles/r01c (all I2F): XU 94 % busy; r01f (all PRMT+FADD): 2.2x more
+// instructions in the child loop at the same run time.
+__device__ __forceinline__ float byteToFloatXU(uint32_t w, int i) { return __uint2float_rn((w >> (8 * i)) & 0xFFu); }
+
 // 8 quantised child boxes of one axis: near plane bytes (n0: slots 0-3, n1: slots 4-7) and far plane bytes.
 struct AxisQ { uint32_t n0, n1, f0, f1; };
 
@@ -59,9 +64,9 @@ __device__ __forceinline__ uint32_t intersectNode(const uint4 w0, const uint4 w1
         for (int i = 0; i < 4; ++i) {
             const uint32_t meta = (meta4 >> (8 * i)) & 0xFFu;
             if (meta == 0) continue;
-            const float tlx = __fmaf_rn(byteToFloat(nx, i), ax, bx), thx = __fmaf_rn(byteToFloat(fx, i), ax, bx);
-            const float tly = __fmaf_rn(byteToFloat(ny, i), ay, by), thy = __fmaf_rn(byteToFloat(fy, i), ay, by);
-            const float tlz = __fmaf_rn(byteToFloat(nz, i), az, bz), thz = __fmaf_rn(byteToFloat(fz, i), az, bz);
+            const float tlx = __fmaf_rn(byteToFloatXU(nx, i), ax, bx), thx = __fmaf_rn(byteToFloat(fx, i), ax, bx);
+            const float tly = __fmaf_rn(byteToFloatXU(ny, i), ay, by), thy = __fmaf_rn(byteToFloat(fy, i), ay, by);
+            const float tlz = __fmaf_rn(byteToFloatXU(nz, i), az, bz), thz = __fmaf_rn(byteToFloat(fz, i), az, bz);
             const float tn = fmaxf(fmaxf(tlx, tly), fmaxf(tlz, tmin));
             const float tf = fminf(fminf(thx, thy), fminf(thz, tmax));
             if (tn <= tf) {
