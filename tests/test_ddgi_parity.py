@@ -149,3 +149,32 @@ def test_rejects_bad_arguments():
     textured["materials"] = m
     with pytest.raises(VkxError):
         g.scene_upload(textured)
+
+
+def test_multi_chunk_update_equals_single_chunk(oracle_lib):
+    """More probes than one chunk holds (32768): the chunked pipeline must give the same atlases as the oracle's single pass.
+    Uses few rays per probe to keep the oracle fast."""
+    from vulkanexp_b200._lib import Context
+
+    flat = get_scene("tiny")
+    res, rays = (40, 30, 32), 8  # 38400 probes -> 2 chunks
+    grid = GridInfo.make(flat["bounds_min"], flat["bounds_max"], res, rays, hysteresis=0.0)
+    o = oracle_lib.Oracle(); o.scene_upload(flat); o.bvh_build(); o.probes_init(grid)
+    g = Context(0); g.scene_upload(flat); g.bvh_build(); g.probes_init(grid)
+    ones = np.ones(grid.probe_count, dtype=np.uint32)
+    o.probes_upload(state=ones); g.probes_upload(state=ones)
+    host = oracle_lib.HostLogic()
+    light = Light.default()
+    for frame in range(2):
+        R, _ = host.next_orientation()
+        grid.hysteresis = 0.5 * frame
+        o.probes_update(grid, light, R, None); g.probes_update(grid, light, R, None)
+        io, do, so, _ = o.probes_download(); ig, dg, sg, _ = g.probes_download()
+        assert (io != ig).mean() < 5e-3 and (do != dg).mean() < 5e-3 and (so != sg).mean() < 2e-2
+        g.probes_upload(io, do, so)
+    # explicit (unsorted) list longer than a chunk
+    idx = np.random.default_rng(3).permutation(grid.probe_count).astype(np.uint32)[:36000]
+    R, _ = host.next_orientation()
+    o.probes_update(grid, light, R, idx); g.probes_update(grid, light, R, idx)
+    io, do, so, _ = o.probes_download(); ig, dg, sg, _ = g.probes_download()
+    assert (io != ig).mean() < 5e-3 and (do != dg).mean() < 5e-3 and (so != sg).mean() < 2e-2

@@ -55,11 +55,11 @@ int vkx_create(int device, vkx_ctx** out) {
 static void freeProbes(vkx_ctx* ctx) {
     void* ptrs[] = {ctx->dIrrWork, ctx->dIrrSampled, ctx->dDepWork, ctx->dDepSampled, ctx->dStateWork, ctx->dStateSampled, ctx->dIndicesList, ctx->dDirs, ctx->dRays,
                     ctx->dHits, ctx->dShadowQueue, ctx->dQueueCount, ctx->dShadowFlags, ctx->dIrrUnpacked, ctx->dDepUnpacked, ctx->dMissQueue, ctx->dFrontQueue, ctx->dIrrNext, ctx->dDepNext, ctx->dStateNext,
-                    ctx->dPerm, ctx->dOrder, ctx->dBlockedOrder, ctx->dBlendW};
+                    ctx->dPerm, ctx->dOrder, ctx->dBlockedOrder, ctx->dBlendW, ctx->dPermList, ctx->dIota};
     for (void* p : ptrs) if (p) cudaFree(p);
     ctx->dIrrWork = ctx->dIrrSampled = ctx->dDepWork = ctx->dDepSampled = ctx->dStateWork = ctx->dStateSampled = ctx->dIndicesList = nullptr;
     ctx->dIrrNext = ctx->dDepNext = ctx->dStateNext = nullptr;
-    ctx->dPerm = ctx->dOrder = ctx->dBlockedOrder = nullptr; ctx->dBlendW = nullptr; ctx->shardOrderReady = false;
+    ctx->dPerm = ctx->dOrder = ctx->dBlockedOrder = ctx->dPermList = ctx->dIota = nullptr; ctx->dBlendW = nullptr; ctx->shardOrderReady = false;
     ctx->dDirs = nullptr; ctx->dRays = nullptr; ctx->dHits = nullptr; ctx->dShadowQueue = nullptr; ctx->dQueueCount = nullptr; ctx->dShadowFlags = nullptr;
     ctx->dIrrUnpacked = ctx->dDepUnpacked = nullptr; ctx->dMissQueue = ctx->dFrontQueue = nullptr;
     ctx->probesReady = false;
@@ -182,6 +182,9 @@ int vkx_trace(vkx_ctx* ctx, const float* origins, const float* directions, size_
 }
 
 // ---------------------------------------------------------------------------------------------------- DDGI
+} // extern "C"
+__global__ void k_iota_list(uint32_t* p, uint32_t first, uint32_t n) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = first + i; }
+extern "C" {
 static int checkGrid(vkx_ctx* ctx, const vkx_grid_info* g) {
     if (!g) return vkx_fail(ctx, VKX_E_INVALID, "null grid");
     if (g->colorRes != 8 || g->depthRes != 16) return vkx_fail(ctx, VKX_E_INVALID, "colorRes/depthRes must be 8/16 (baked into the reference's shaders)");
@@ -228,6 +231,9 @@ int vkx_probes_init(vkx_ctx* ctx, const vkx_grid_info* grid) {
     CUDA_TRY(ctx, cudaMalloc(&ctx->dPerm, VKX_MAX_RAYS_PER_PROBE * 4));
     CUDA_TRY(ctx, cudaMalloc(&ctx->dOrder, stBytes));
     CUDA_TRY(ctx, cudaMalloc(&ctx->dBlockedOrder, stBytes));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->dPermList, stBytes));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->dIota, stBytes));
+    k_iota_list<<<divUp(ctx->probeCount, 256), 256, 0, ctx->stream>>>(ctx->dIota, 0, ctx->probeCount); LAUNCH_CHECK(ctx);
     CUDA_TRY(ctx, cudaMalloc(&ctx->dBlendW, size_t(VKX_MAX_RAYS_PER_PROBE) * 288 * 4));
     { // rank of every probe in 2x2x2-block order (scheduling only: which probes share a warp)
         const uint32_t rx = uint32_t(grid->resolution[0]), ry = uint32_t(grid->resolution[1]);
@@ -341,8 +347,6 @@ static int uploadOrder(vkx_ctx* ctx, const uint32_t* probeIndices, uint32_t coun
     if (count) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dOrder + listOffset, order.data(), size_t(count) * 4, cudaMemcpyHostToDevice, ctx->stream));
     return VKX_OK;
 }
-
-__global__ void k_iota_list(uint32_t* p, uint32_t first, uint32_t n) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = first + i; }
 
 int vkx_probes_update(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx_light* light, const float orientation[16], const uint32_t* probeIndices, uint32_t count, int sync) {
     BIND(ctx);

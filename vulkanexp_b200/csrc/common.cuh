@@ -71,6 +71,8 @@ struct vkx_ctx {
     uint32_t* dPerm = nullptr;          // direction sort permutation of the frame [256]
     uint32_t* dOrder = nullptr;         // [probeCount] position -> slot of the to-update list (2x2x2 probe blocks)
     uint32_t* dBlockedOrder = nullptr;  // cached order for the full-volume list
+    uint32_t* dPermList = nullptr;      // multi-chunk updates: probe indices in block order
+    uint32_t* dIota = nullptr;          // 0..probeCount-1
     float* dBlendW = nullptr;           // per-frame blend weight table [256][288]
     std::vector<uint32_t> hBlockRank;   // probe linear index -> rank in 2x2x2-block order
     std::vector<uint32_t> hMark, hOrder; // scratch of uploadOrder

@@ -264,6 +264,12 @@ __global__ void __launch_bounds__(BLEND_COLS) k_blend(BlendParams bp, DeviceProb
     }
 }
 
+// Multi-chunk updates: probe indices gathered in block order, so that a chunk is a contiguous piece of one list.
+__global__ void k_gather_list(uint32_t* __restrict__ out, const uint32_t* __restrict__ list, const uint32_t* __restrict__ order, uint32_t n) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) out[j] = list[order[j]];
+}
+
 // work -> sampled for the updated probes (tiles + state word). One warp per probe: 16 depth rows + 8 irradiance rows.
 __global__ void k_publish(DeviceProbes pr, uint32_t* __restrict__ irrSampled, uint32_t* __restrict__ depSampled, uint32_t* __restrict__ stateSampled,
                           const uint32_t* __restrict__ probeIndices, uint32_t count) {
@@ -367,11 +373,15 @@ int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* /*unused*/,
     const unsigned persistentBlocks = unsigned(ctx->smCount * blocksPerSm);
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
     k_blend_weights<<<N, BLEND_COLS, 0, st>>>(ctx->grid.depthSharpness, N, ctx->dDirs, ctx->dBlendW); LAUNCH_CHECK(ctx);
+    // One chunk: slots are the caller's list positions (ray/hit buffers are laid out [slot][ray]) and `order` only schedules them.
+    // Several chunks: the list is first gathered in block order, a chunk is then a contiguous piece of it with identity order.
+    const bool multi = count > ctx->chunkProbes;
+    if (multi) { k_gather_list<<<divUp(count, 256), 256, 0, st>>>(ctx->dPermList, ctx->dIndicesList + listOffset, ctx->dOrder + listOffset, count); LAUNCH_CHECK(ctx); }
     for (uint32_t base = 0; base < count; base += ctx->chunkProbes) {
         const uint32_t n = std::min(ctx->chunkProbes, count - base);
         const uint32_t numRays = n * N;
-        const uint32_t* idx = ctx->dIndicesList + listOffset + base;
-        RayMap rm; rm.count = n; rm.raysPerProbe = N; rm.numDirGroups = (N + 3u) / 4u; rm.order = ctx->dOrder + listOffset + base; rm.perm = ctx->dPerm;
+        const uint32_t* idx = multi ? ctx->dPermList + base : ctx->dIndicesList + listOffset;
+        RayMap rm; rm.count = n; rm.raysPerProbe = N; rm.numDirGroups = (N + 3u) / 4u; rm.order = multi ? ctx->dIota : ctx->dOrder + listOffset; rm.perm = ctx->dPerm;
         rm.numThreads = ((n + 7u) / 8u) * rm.numDirGroups * 32u;
         TraceParams tp; tp.grid = ctx->grid; tp.tmin = 0.01f; tp.tmax = tmax; tp.raysPerProbe = N; tp.numRays = numRays;
         ShadeParams sp; sp.grid = ctx->grid; sp.light = light; sp.raysPerProbe = N; sp.numRays = numRays;
