@@ -173,6 +173,10 @@ int vkx_probes_update(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx_light* 
  * rays (optional) = the RGBA32F ray buffer of the last update [count][raysPerProbe] (rgb, depth). NULL skips. */
 int vkx_probes_download(vkx_ctx* ctx, uint32_t* irradiance, uint32_t* depth, uint32_t* state, float* rays,
                         size_t raysCapacityBytes);
+/* Asynchronous read-back: queues the copies behind the last publish on a copy stream and returns; the next update's publish waits
+ * for them. Host buffers should be pinned (cudaHostAlloc / torch pin_memory). */
+int vkx_probes_download_async(vkx_ctx* ctx, uint32_t* irradiance, uint32_t* depth, uint32_t* state);
+int vkx_probes_download_wait(vkx_ctx* ctx);
 /* Checkpoint/resume of GI state. NULL skips an array. */
 int vkx_probes_upload(vkx_ctx* ctx, const uint32_t* irradiance, const uint32_t* depth, const uint32_t* state);
 /* Enables the parity side buffers (hit records, shadow flags, unpacked blend results) and forces single-chunk updates. */

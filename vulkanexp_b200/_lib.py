@@ -145,6 +145,13 @@ class Context:
         self._check(self.l.vkx_probes_download(self.h, _p(irr), _p(dep), _p(st), _p(r), C.c_size_t(r.nbytes if rays else 0)))
         return irr, dep, st, r
 
+    def probes_download_async(self, out):
+        irr, dep, st = out
+        self._check(self.l.vkx_probes_download_async(self.h, _p(irr), _p(dep), _p(st)))
+
+    def probes_download_wait(self):
+        self._check(self.l.vkx_probes_download_wait(self.h))
+
     def probes_upload(self, irr=None, dep=None, state=None):
         a = [np.ascontiguousarray(x, dtype=np.uint32) if x is not None else None for x in (irr, dep, state)]
         self._check(self.l.vkx_probes_upload(self.h, _p(a[0]), _p(a[1]), _p(a[2])))

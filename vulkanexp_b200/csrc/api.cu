@@ -7,6 +7,8 @@
 #include <cstring>
 #include <algorithm>
 #include <nccl.h>
+#include <chrono>
+#include <cstdlib>
 
 static thread_local std::string g_createError;
 
@@ -62,6 +64,7 @@ static void freeProbes(vkx_ctx* ctx) {
     ctx->dPerm = ctx->dOrder = ctx->dBlockedOrder = ctx->dPermList = ctx->dIota = nullptr; ctx->dBlendW = nullptr; ctx->shardOrderReady = false;
     ctx->dDirs = nullptr; ctx->dRays = nullptr; ctx->dHits = nullptr; ctx->dShadowQueue = nullptr; ctx->dQueueCount = nullptr; ctx->dShadowFlags = nullptr;
     ctx->dIrrUnpacked = ctx->dDepUnpacked = nullptr; ctx->dMissQueue = ctx->dFrontQueue = nullptr;
+    if (ctx->hListStage) { cudaFreeHost(ctx->hListStage); ctx->hListStage = nullptr; }
     ctx->probesReady = false;
 }
 static void freeShadow(vkx_ctx* ctx) {
@@ -84,6 +87,7 @@ void vkx_destroy(vkx_ctx* ctx) {
     for (auto& ev : ctx->kev) if (ev) cudaEventDestroy(ev);
     if (ctx->commStream) cudaStreamDestroy(ctx->commStream);
     if (ctx->commEvent) cudaEventDestroy(ctx->commEvent);
+    if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); cudaEventDestroy(ctx->evPublished); cudaEventDestroy(ctx->evCopyDone); }
     if (ctx->hStage) { cudaFreeHost(ctx->hStage); for (auto& e : ctx->stageEvent) if (e) cudaEventDestroy(e); }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -336,15 +340,25 @@ static int uploadFrameInputs(vkx_ctx* ctx, const vkx_grid_info* grid, const floa
 }
 
 // position -> slot order for a host-provided to-update list: slots sorted by the 2x2x2-block rank of their probe (O(P))
-static int uploadOrder(vkx_ctx* ctx, const uint32_t* probeIndices, uint32_t count, uint32_t listOffset) {
-    std::vector<uint32_t>& mark = ctx->hMark; std::vector<uint32_t>& order = ctx->hOrder;
-    mark.assign(ctx->probeCount, 0u); order.resize(count);
+static int uploadOrder(vkx_ctx* ctx, const uint32_t* probeIndices, uint32_t count, uint32_t listOffset, bool uploadList) {
+    // pinned staging of the current frame slot (uploadFrameInputs picked it and waited for its previous use), so both copies are
+    // truly asynchronous and the host can queue the next frame while this one runs
+    if (!ctx->hListStage) CUDA_TRY(ctx, cudaMallocHost(&ctx->hListStage, size_t(8) * ctx->probeCount * 4));
+    uint32_t* list = ctx->hListStage + size_t(ctx->curSlot) * 2 * ctx->probeCount + listOffset;
+    uint32_t* order = list + ctx->probeCount;
+    std::vector<uint32_t>& mark = ctx->hMark;
+    mark.assign(ctx->probeCount, 0u);
     bool dup = false;
     for (uint32_t s = 0; s < count; ++s) { uint32_t& m = mark[ctx->hBlockRank[probeIndices[s]]]; if (m) dup = true; m = s + 1; }
     if (dup) { for (uint32_t s = 0; s < count; ++s) order[s] = s; }
     else { uint32_t n = 0; for (uint32_t r = 0; r < ctx->probeCount; ++r) if (mark[r]) order[n++] = mark[r] - 1; }
-    // pageable source: cudaMemcpyAsync stages it before returning, and the vector is owned by the context
-    if (count) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dOrder + listOffset, order.data(), size_t(count) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (count) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dOrder + listOffset, order, size_t(count) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (uploadList && count) {
+        memcpy(list, probeIndices, size_t(count) * 4);
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dIndicesList + listOffset, list, size_t(count) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    // the slot's event is recorded by uploadFrameInputs before these copies; record it again so the slot is not reused too early
+    CUDA_TRY(ctx, cudaEventRecord(ctx->stageEvent[ctx->curSlot], ctx->stream));
     return VKX_OK;
 }
 
@@ -352,20 +366,28 @@ int vkx_probes_update(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx_light* 
     BIND(ctx);
     if (!ctx->probesReady || !ctx->bvhBuilt) return vkx_fail(ctx, VKX_E_INVALID, "vkx_probes_update: probes or BVH not ready");
     if (!light || !orientation) return vkx_fail(ctx, VKX_E_INVALID, "null light/orientation");
+    static const bool traceHost = getenv("VKX_TRACE_HOST") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     TRY(uploadFrameInputs(ctx, grid, orientation));
+    const double t1 = now();
     if (probeIndices) {
         if (count > ctx->probeCount) return vkx_fail(ctx, VKX_E_INVALID, "more indices than probes");
         for (uint32_t i = 0; i < count; ++i) if (probeIndices[i] >= ctx->probeCount) return vkx_fail(ctx, VKX_E_INVALID, "probe index %u out of range", probeIndices[i]);
-        if (count) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dIndicesList, probeIndices, size_t(count) * 4, cudaMemcpyHostToDevice, ctx->stream));
-        TRY(uploadOrder(ctx, probeIndices, count, 0));
+        TRY(uploadOrder(ctx, probeIndices, count, 0, true));
     } else {
         count = ctx->probeCount;
         k_iota_list<<<divUp(count, 256), 256, 0, ctx->stream>>>(ctx->dIndicesList, 0, count); LAUNCH_CHECK(ctx);
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dOrder, ctx->dBlockedOrder, size_t(count) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     }
     ctx->shardOrderReady = false;
+    const double t2 = now();
     TRY(ddgiUpdate(ctx, *light, nullptr, count, 0, false));
+    const double t3 = now();
+    if (traceHost) fprintf(stderr, "[vkx host] inputs %.3f ms, list %.3f ms, enqueue %.3f ms\n", t1 - t0, t2 - t1, t3 - t2);
+    if (ctx->copyPending) { CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evCopyDone, 0)); ctx->copyPending = false; } // a queued read-back still reads the sampled atlases
     TRY(ddgiPublish(ctx, count));
+    if (ctx->evPublished) CUDA_TRY(ctx, cudaEventRecord(ctx->evPublished, ctx->stream));
     ctx->shardedLast = false;
     if (sync) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return VKX_OK;
@@ -384,6 +406,31 @@ int vkx_probes_download(vkx_ctx* ctx, uint32_t* irradiance, uint32_t* depth, uin
         if (raysCapacityBytes < need) return vkx_fail(ctx, VKX_E_INVALID, "ray buffer too small");
         if (need) CUDA_TRY(ctx, cudaMemcpy(rays, ctx->dRays, need, cudaMemcpyDeviceToHost));
     }
+    return VKX_OK;
+}
+
+/* Asynchronous variant: queues the three device->host copies on a copy stream behind the last publish and returns; the next update's
+ * publish waits for them. Host buffers should be pinned. vkx_probes_download_wait blocks until the copies have landed. */
+int vkx_probes_download_async(vkx_ctx* ctx, uint32_t* irradiance, uint32_t* depth, uint32_t* state) {
+    BIND(ctx);
+    if (!ctx->probesReady) return vkx_fail(ctx, VKX_E_INVALID, "probes not initialised");
+    if (!ctx->copyStream) {
+        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->evPublished, cudaEventDisableTiming));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->evCopyDone, cudaEventDisableTiming));
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->evPublished, ctx->stream)); // everything queued so far (including the last publish)
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copyStream, ctx->evPublished, 0));
+    if (irradiance) CUDA_TRY(ctx, cudaMemcpyAsync(irradiance, ctx->dIrrSampled, size_t(ctx->irrW) * ctx->irrH * 4, cudaMemcpyDeviceToHost, ctx->copyStream));
+    if (depth) CUDA_TRY(ctx, cudaMemcpyAsync(depth, ctx->dDepSampled, size_t(ctx->depW) * ctx->depH * 4, cudaMemcpyDeviceToHost, ctx->copyStream));
+    if (state) CUDA_TRY(ctx, cudaMemcpyAsync(state, ctx->dStateSampled, size_t(ctx->probeCount) * 4, cudaMemcpyDeviceToHost, ctx->copyStream));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->evCopyDone, ctx->copyStream));
+    ctx->copyPending = true;
+    return VKX_OK;
+}
+int vkx_probes_download_wait(vkx_ctx* ctx) {
+    BIND(ctx);
+    if (ctx->evCopyDone) CUDA_TRY(ctx, cudaEventSynchronize(ctx->evCopyDone));
     return VKX_OK;
 }
 
@@ -495,13 +542,14 @@ int vkx_probes_update_sharded(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx
     const uint32_t s = slicesPerRank / K;
     ncclComm_t comm = reinterpret_cast<ncclComm_t>(ctx->comm);
     cudaStream_t st = ctx->stream, cs = ctx->commStream;
+    if (ctx->copyPending) { CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->commStream, ctx->evCopyDone, 0)); ctx->copyPending = false; } // read-back of the buffers about to be overwritten
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], st));
     uint32_t total = 0;
     for (uint32_t k = 0; k < K; ++k) {
         const uint32_t z0 = k * s * n + uint32_t(ctx->rank) * s;
         const uint32_t first = z0 * plane, count = s * plane;
         k_iota_list<<<divUp(count, 256), 256, 0, st>>>(ctx->dIndicesList + total, first, count); LAUNCH_CHECK(ctx);
-        if (!ctx->shardOrderReady) { std::vector<uint32_t> idx(count); for (uint32_t i = 0; i < count; ++i) idx[i] = first + i; TRY(uploadOrder(ctx, idx.data(), count, total)); }
+        if (!ctx->shardOrderReady) { std::vector<uint32_t> idx(count); for (uint32_t i = 0; i < count; ++i) idx[i] = first + i; TRY(uploadOrder(ctx, idx.data(), count, total, false)); }
         TRY(ddgiUpdate(ctx, *light, nullptr, count, total, false));
         total += count;
         CUDA_TRY(ctx, cudaEventRecord(ctx->commEvent, st));

@@ -77,7 +77,7 @@ struct vkx_ctx {
     std::vector<uint32_t> hBlockRank;   // probe linear index -> rank in 2x2x2-block order
     std::vector<uint32_t> hMark, hOrder; // scratch of uploadOrder
     struct FrameStage { float4 dirs[VKX_MAX_RAYS_PER_PROBE]; uint32_t perm[VKX_MAX_RAYS_PER_PROBE]; };
-    FrameStage* hStage = nullptr; cudaEvent_t stageEvent[4] = {nullptr, nullptr, nullptr, nullptr}; bool stageUsed[4] = {false, false, false, false}; uint32_t stageCursor = 0;
+    FrameStage* hStage = nullptr; uint32_t* hListStage = nullptr; /* pinned [4][2][probeCount]: to-update list and order per slot */ int curSlot = 0; cudaEvent_t stageEvent[4] = {nullptr, nullptr, nullptr, nullptr}; bool stageUsed[4] = {false, false, false, false}; uint32_t stageCursor = 0;
     uint32_t chunkProbes = 0;           // probes traced per chunk
     float4* dRays = nullptr;            // [chunkProbes][N] (rgb, depth)
     vkx_hit* dHits = nullptr;           // [chunkProbes][N]
@@ -91,6 +91,9 @@ struct vkx_ctx {
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t kev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // per-kernel timing of chunk 0
     uint32_t kevProbes = 0, kevShadowRays = 0;
+
+    // asynchronous read-back (vkx_probes_download_async)
+    cudaStream_t copyStream = nullptr; cudaEvent_t evPublished = nullptr, evCopyDone = nullptr; bool copyPending = false;
 
     // multi-GPU
     ncclComm* comm = nullptr; int rank = 0, nranks = 1;
