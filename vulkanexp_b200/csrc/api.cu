@@ -56,14 +56,14 @@ int vkx_create(int device, vkx_ctx** out) {
 
 static void freeProbes(vkx_ctx* ctx) {
     void* ptrs[] = {ctx->dIrrWork, ctx->dIrrSampled, ctx->dDepWork, ctx->dDepSampled, ctx->dStateWork, ctx->dStateSampled, ctx->dIndicesList, ctx->dDirs, ctx->dRays,
-                    ctx->dHits, ctx->dShadowQueue, ctx->dQueueCount, ctx->dShadowFlags, ctx->dIrrUnpacked, ctx->dDepUnpacked, ctx->dMissQueue, ctx->dFrontQueue, ctx->dIrrNext, ctx->dDepNext, ctx->dStateNext,
-                    ctx->dPerm, ctx->dOrder, ctx->dBlockedOrder, ctx->dBlendW, ctx->dPermList, ctx->dIota};
+                    ctx->dHits, ctx->dShadowQueue, ctx->dQueueCount, ctx->dShadowFlags, ctx->dIrrUnpacked, ctx->dDepUnpacked, ctx->dMissQueue, ctx->dFrontQueue, ctx->dFrontKeys, ctx->dFrontKeysOut, ctx->dFrontQueueSorted, ctx->dSortTemp, ctx->dIrrNext, ctx->dDepNext, ctx->dStateNext,
+                    ctx->dPerm, ctx->dOrder, ctx->dBlockedOrder, ctx->dBlendW, ctx->dPermList, ctx->dIota, ctx->dCellHist};
     for (void* p : ptrs) if (p) cudaFree(p);
     ctx->dIrrWork = ctx->dIrrSampled = ctx->dDepWork = ctx->dDepSampled = ctx->dStateWork = ctx->dStateSampled = ctx->dIndicesList = nullptr;
     ctx->dIrrNext = ctx->dDepNext = ctx->dStateNext = nullptr;
-    ctx->dPerm = ctx->dOrder = ctx->dBlockedOrder = ctx->dPermList = ctx->dIota = nullptr; ctx->dBlendW = nullptr; ctx->shardOrderReady = false;
+    ctx->dPerm = ctx->dOrder = ctx->dBlockedOrder = ctx->dPermList = ctx->dIota = ctx->dCellHist = nullptr; ctx->dBlendW = nullptr; ctx->shardOrderReady = false;
     ctx->dDirs = nullptr; ctx->dRays = nullptr; ctx->dHits = nullptr; ctx->dShadowQueue = nullptr; ctx->dQueueCount = nullptr; ctx->dShadowFlags = nullptr;
-    ctx->dIrrUnpacked = ctx->dDepUnpacked = nullptr; ctx->dMissQueue = ctx->dFrontQueue = nullptr;
+    ctx->dIrrUnpacked = ctx->dDepUnpacked = nullptr; ctx->dMissQueue = ctx->dFrontQueue = ctx->dFrontKeys = ctx->dFrontKeysOut = ctx->dFrontQueueSorted = nullptr; ctx->dSortTemp = nullptr; ctx->sortTempBytes = 0;
     if (ctx->hListStage) { cudaFreeHost(ctx->hListStage); ctx->hListStage = nullptr; }
     ctx->probesReady = false;
 }
@@ -199,9 +199,9 @@ static int checkGrid(vkx_ctx* ctx, const vkx_grid_info* g) {
 
 static int allocProbeScratch(vkx_ctx* ctx) {
     // ray-level scratch for one chunk of probes
-    void* old[] = {ctx->dRays, ctx->dHits, ctx->dShadowQueue, ctx->dShadowFlags, ctx->dIrrUnpacked, ctx->dDepUnpacked, ctx->dMissQueue, ctx->dFrontQueue};
+    void* old[] = {ctx->dRays, ctx->dHits, ctx->dShadowQueue, ctx->dShadowFlags, ctx->dIrrUnpacked, ctx->dDepUnpacked, ctx->dMissQueue, ctx->dFrontQueue, ctx->dFrontKeys, ctx->dFrontKeysOut, ctx->dFrontQueueSorted};
     for (void* p : old) if (p) cudaFree(p);
-    ctx->dMissQueue = ctx->dFrontQueue = nullptr;
+    ctx->dMissQueue = ctx->dFrontQueue = ctx->dFrontKeys = ctx->dFrontKeysOut = ctx->dFrontQueueSorted = nullptr;
     ctx->dRays = nullptr; ctx->dHits = nullptr; ctx->dShadowQueue = nullptr; ctx->dShadowFlags = nullptr; ctx->dIrrUnpacked = ctx->dDepUnpacked = nullptr;
     const size_t maxRays = size_t(ctx->chunkProbes) * VKX_MAX_RAYS_PER_PROBE;
     CUDA_TRY(ctx, cudaMalloc(&ctx->dRays, maxRays * sizeof(float4)));
@@ -209,6 +209,9 @@ static int allocProbeScratch(vkx_ctx* ctx) {
     CUDA_TRY(ctx, cudaMalloc(&ctx->dShadowQueue, maxRays * 2 * sizeof(float4)));
     CUDA_TRY(ctx, cudaMalloc(&ctx->dMissQueue, maxRays * 4));
     CUDA_TRY(ctx, cudaMalloc(&ctx->dFrontQueue, maxRays * 4));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->dFrontKeys, maxRays * 4));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->dFrontKeysOut, maxRays * 4));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->dFrontQueueSorted, maxRays * 4));
     if (ctx->debugBuffers) {
         CUDA_TRY(ctx, cudaMalloc(&ctx->dShadowFlags, maxRays));
         CUDA_TRY(ctx, cudaMalloc(&ctx->dIrrUnpacked, size_t(ctx->probeCount) * 36 * 3 * 4));
@@ -237,6 +240,7 @@ int vkx_probes_init(vkx_ctx* ctx, const vkx_grid_info* grid) {
     CUDA_TRY(ctx, cudaMalloc(&ctx->dBlockedOrder, stBytes));
     CUDA_TRY(ctx, cudaMalloc(&ctx->dPermList, stBytes));
     CUDA_TRY(ctx, cudaMalloc(&ctx->dIota, stBytes));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->dCellHist, stBytes + 4));
     k_iota_list<<<divUp(ctx->probeCount, 256), 256, 0, ctx->stream>>>(ctx->dIota, 0, ctx->probeCount); LAUNCH_CHECK(ctx);
     CUDA_TRY(ctx, cudaMalloc(&ctx->dBlendW, size_t(VKX_MAX_RAYS_PER_PROBE) * 288 * 4));
     { // rank of every probe in 2x2x2-block order (scheduling only: which probes share a warp)

@@ -84,6 +84,7 @@ struct vkx_ctx {
     float4* dShadowQueue = nullptr;     // [chunkProbes*N][2]
     uint32_t* dQueueCount = nullptr;    // 8 counters, see ddgiUpdate
     uint32_t* dMissQueue = nullptr; uint32_t* dFrontQueue = nullptr; // ray indices sorted by what they need next
+    uint32_t *dFrontKeys = nullptr, *dFrontKeysOut = nullptr, *dFrontQueueSorted = nullptr, *dCellHist = nullptr; void* dSortTemp = nullptr; size_t sortTempBytes = 0; // front queue sorted by grid cell
     uint8_t* dShadowFlags = nullptr;    // debug
     float* dIrrUnpacked = nullptr; float* dDepUnpacked = nullptr; // debug, full count
     bool debugBuffers = false;

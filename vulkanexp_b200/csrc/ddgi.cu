@@ -14,12 +14,14 @@
 #include "ptrace.cuh"
 #include "shade.cuh"
 #include "ddgi_common.cuh"
+#include <cub/device/device_radix_sort.cuh>
 
 namespace {
 
 struct TraceParams {
     vkx_grid_info grid;
     float tmin, tmax;
+    float invCell[3];
     uint32_t raysPerProbe, numRays; // numRays = chunk probes * raysPerProbe
 };
 
@@ -48,6 +50,25 @@ struct PrimarySrc {
         else frontQueue[warpAppend(counters + 4)] = ri;
     }
 };
+
+// Sort key of a front hit = grid cell of the hit point (scheduling only: rays that shade from the same 8 probes end up in the same
+// warps of k_shade_front, and their shadow rays start close together).
+__global__ void k_front_keys(TraceParams tp, const uint32_t* __restrict__ probeIndices, const float4* __restrict__ dirs, const vkx_hit* __restrict__ hits,
+                             const uint32_t* __restrict__ frontQueue, const uint32_t* __restrict__ counters, uint32_t* __restrict__ keys) {
+    const uint32_t n = counters[4];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t ri = frontQueue[i];
+        const uint32_t slot = ri / tp.raysPerProbe, ray = ri - slot * tp.raysPerProbe;
+        int ix, iy, iz; probeGridIndex(__ldg(probeIndices + slot), tp.grid, ix, iy, iz);
+        const v3 o = probeWorldPos(ix, iy, iz, tp.grid);
+        const float4 d = __ldg(dirs + ray);
+        const float t = hits[ri].t;
+        const int cx = min(max(int((o.x + d.x * t - tp.grid.extentMin[0]) * tp.invCell[0]), 0), tp.grid.resolution[0] - 1);
+        const int cy = min(max(int((o.y + d.y * t - tp.grid.extentMin[1]) * tp.invCell[1]), 0), tp.grid.resolution[1] - 1);
+        const int cz = min(max(int((o.z + d.z * t - tp.grid.extentMin[2]) * tp.invCell[2]), 0), tp.grid.resolution[2] - 1);
+        keys[i] = uint32_t(cx + tp.grid.resolution[0] * (cy + tp.grid.resolution[1] * cz));
+    }
+}
 
 // Persistent warps; see ptrace.cuh.
 __global__ void __launch_bounds__(128, 8) k_trace_primary(DeviceScene sc, TraceParams tp, RayMap rm, const uint32_t* __restrict__ probeIndices,
@@ -384,15 +405,27 @@ int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* /*unused*/,
         RayMap rm; rm.count = n; rm.raysPerProbe = N; rm.numDirGroups = (N + 3u) / 4u; rm.order = multi ? ctx->dIota : ctx->dOrder + listOffset; rm.perm = ctx->dPerm;
         rm.numThreads = ((n + 7u) / 8u) * rm.numDirGroups * 32u;
         TraceParams tp; tp.grid = ctx->grid; tp.tmin = 0.01f; tp.tmax = tmax; tp.raysPerProbe = N; tp.numRays = numRays;
+        tp.invCell[0] = 1.0f / cx; tp.invCell[1] = 1.0f / cy; tp.invCell[2] = 1.0f / cz;
         ShadeParams sp; sp.grid = ctx->grid; sp.light = light; sp.raysPerProbe = N; sp.numRays = numRays;
         const bool timed = base == 0; // per-kernel events on the first chunk
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->dQueueCount, 0, 32, st)); // [0] shadow queue length, [1] primary work counter, [2] shadow work counter, [3] misses, [4] front hits
         if (timed) { CUDA_TRY(ctx, cudaEventRecord(ctx->kev[0], st)); ctx->kevProbes = n; }
         k_trace_primary<<<persistentBlocks, 128, 0, st>>>(sc, tp, rm, idx, ctx->dDirs, ctx->dHits, ctx->dRays, ctx->dMissQueue, ctx->dFrontQueue, ctx->dQueueCount); LAUNCH_CHECK(ctx);
         if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[1], st));
+        { // front-hit queue sorted by grid cell (radix sort over just the bits a cell index needs; unused slots carry all-ones keys).
+          // A counting sort with a per-cell atomic histogram was slower: hit points cluster in few cells.
+            CUDA_TRY(ctx, cudaMemsetAsync(ctx->dFrontKeys, 0xFF, size_t(numRays) * 4, st));
+            k_front_keys<<<std::min<unsigned>(divUp(numRays, 256), unsigned(ctx->smCount) * 8u), 256, 0, st>>>(tp, idx, ctx->dDirs, ctx->dHits, ctx->dFrontQueue, ctx->dQueueCount, ctx->dFrontKeys); LAUNCH_CHECK(ctx);
+            uint32_t cells = ctx->probeCount, bits = 1; while ((1u << bits) <= cells) ++bits;
+            size_t need = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, need, ctx->dFrontKeys, ctx->dFrontKeysOut, ctx->dFrontQueue, ctx->dFrontQueueSorted, int(numRays), 0, int(bits), st);
+            if (need > ctx->sortTempBytes) { if (ctx->dSortTemp) cudaFree(ctx->dSortTemp); CUDA_TRY(ctx, cudaMalloc(&ctx->dSortTemp, need)); ctx->sortTempBytes = need; }
+            CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->dSortTemp, need, ctx->dFrontKeys, ctx->dFrontKeysOut, ctx->dFrontQueue, ctx->dFrontQueueSorted, int(numRays), 0, int(bits), st));
+            ctx->launches += 3;
+        }
         const unsigned shadeBlocks = std::min<unsigned>(divUp(numRays, 128), unsigned(ctx->smCount) * 16u);
         launchShadeMiss(shadeBlocks, st, sp, idx, ctx->dDirs, ctx->dMissQueue, ctx->dQueueCount, ctx->dRays); LAUNCH_CHECK(ctx);
-        launchShadeFront(shadeBlocks, st, sc, pr, sp, idx, ctx->dDirs, ctx->dHits, ctx->dFrontQueue, ctx->dQueueCount, ctx->dRays, ctx->dShadowQueue); LAUNCH_CHECK(ctx);
+        launchShadeFront(shadeBlocks, st, sc, pr, sp, idx, ctx->dDirs, ctx->dHits, ctx->dFrontQueueSorted, ctx->dQueueCount, ctx->dRays, ctx->dShadowQueue); LAUNCH_CHECK(ctx);
         if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[2], st));
         if (ctx->debugBuffers) CUDA_TRY(ctx, cudaMemsetAsync(ctx->dShadowFlags, 0, numRays, st));
         k_trace_shadow<<<persistentBlocks, 128, 0, st>>>(sc, light, ctx->dShadowQueue, ctx->dQueueCount, ctx->dRays, ctx->debugBuffers ? ctx->dShadowFlags : nullptr, ctx->dQueueCount + 2); LAUNCH_CHECK(ctx);
