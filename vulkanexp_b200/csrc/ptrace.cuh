@@ -10,8 +10,12 @@
 #pragma once
 #include "traverse.cuh"
 
-#define PT_CHUNK 64u
+#ifndef PT_CHUNK
+#define PT_CHUNK 32u
+#endif
+#ifndef PT_REFILL_MIN
 #define PT_REFILL_MIN 8 // fetch when at least this many lanes are idle (or all remaining lanes are idle)
+#endif
 
 // Src must provide:
 //   __device__ bool load(uint32_t item, Ray& r, float& tmin, float& tmax, uint32_t& cullMask);   false: item is padding
