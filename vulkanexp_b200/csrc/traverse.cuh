@@ -54,26 +54,29 @@ __device__ __forceinline__ uint32_t intersectNode(const uint4 w0, const uint4 w1
     if (r.oct & 2u) { qy.n0 = w4.x; qy.n1 = w4.y; qy.f0 = w2.z; qy.f1 = w2.w; } else { qy.n0 = w2.z; qy.n1 = w2.w; qy.f0 = w4.x; qy.f1 = w4.y; }
     if (r.oct & 1u) { qz.n0 = w4.z; qz.n1 = w4.w; qz.f0 = w3.x; qz.f1 = w3.y; } else { qz.n0 = w3.x; qz.n1 = w3.y; qz.f0 = w4.z; qz.f1 = w4.w; }
     uint32_t mask = 0;
+    const uint32_t oct4 = r.oct * 0x01010101u;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const uint32_t meta4 = h ? w1.w : w1.z;
         const uint32_t nx = h ? qx.n1 : qx.n0, fx = h ? qx.f1 : qx.f0;
         const uint32_t ny = h ? qy.n1 : qy.n0, fy = h ? qy.f1 : qy.f0;
         const uint32_t nz = h ? qz.n1 : qz.n0, fz = h ? qz.f1 : qz.f0;
+        // Four children at a time, byte-parallel (same values as: bits = meta >> 5, idx = meta & 31, idx = 24 + ((idx - 24) ^ oct) for inner
+        // children). Inner meta is 0b00111sss, so (meta & meta << 1) has bit 4 set exactly for inner children; empty slots (meta 0)
+        // contribute no bits whatever their (zero) box does.
+        const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+        const uint32_t innerMask4 = (isInner4 >> 4) * 0xFFu;
+        const uint32_t bitIndex4 = (meta4 ^ (oct4 & innerMask4)) & 0x1F1F1F1Fu;
+        const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const uint32_t meta = (meta4 >> (8 * i)) & 0xFFu;
-            if (meta == 0) continue;
             const float tlx = __fmaf_rn(byteToFloatXU(nx, i), ax, bx), thx = __fmaf_rn(byteToFloat(fx, i), ax, bx);
             const float tly = __fmaf_rn(byteToFloatXU(ny, i), ay, by), thy = __fmaf_rn(byteToFloat(fy, i), ay, by);
             const float tlz = __fmaf_rn(byteToFloatXU(nz, i), az, bz), thz = __fmaf_rn(byteToFloat(fz, i), az, bz);
             const float tn = fmaxf(fmaxf(tlx, tly), fmaxf(tlz, tmin));
             const float tf = fminf(fminf(thx, thy), fminf(thz, tmax));
-            if (tn <= tf) {
-                uint32_t bits = meta >> 5, idx = meta & 31u;
-                if (idx >= 24u) idx = 24u + ((idx - 24u) ^ r.oct);
-                mask |= bits << idx;
-            }
+            const uint32_t bits = (childBits4 >> (8 * i)) & 0xFFu, idx = (bitIndex4 >> (8 * i)) & 0xFFu;
+            mask |= (tn <= tf) ? (bits << idx) : 0u;
         }
     }
     return mask;
