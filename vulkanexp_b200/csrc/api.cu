@@ -50,6 +50,8 @@ int vkx_create(int device, vkx_ctx** out) {
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
     for (auto& ev : ctx->sev) cudaEventCreate(&ev);
     for (auto& ev : ctx->kev) cudaEventCreate(&ev);
+    cudaStreamCreateWithFlags(&ctx->auxStream, cudaStreamNonBlocking);
+    for (auto& ev : ctx->auxEvent) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     *out = ctx;
     return VKX_OK;
 }
@@ -85,6 +87,8 @@ void vkx_destroy(vkx_ctx* ctx) {
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->sev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->kev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->auxEvent) if (ev) cudaEventDestroy(ev);
+    if (ctx->auxStream) cudaStreamDestroy(ctx->auxStream);
     if (ctx->commStream) cudaStreamDestroy(ctx->commStream);
     if (ctx->commEvent) cudaEventDestroy(ctx->commEvent);
     if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); cudaEventDestroy(ctx->evPublished); cudaEventDestroy(ctx->evCopyDone); }

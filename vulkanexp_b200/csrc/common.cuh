@@ -93,6 +93,8 @@ struct vkx_ctx {
     cudaEvent_t kev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // per-kernel timing of chunk 0
     uint32_t kevProbes = 0, kevShadowRays = 0;
 
+    cudaStream_t auxStream = nullptr; cudaEvent_t auxEvent[2] = {nullptr, nullptr}; // second stream of the update (sky kernel)
+
     // asynchronous read-back (vkx_probes_download_async)
     cudaStream_t copyStream = nullptr; cudaEvent_t evPublished = nullptr, evCopyDone = nullptr; bool copyPending = false;
 

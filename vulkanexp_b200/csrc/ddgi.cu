@@ -412,6 +412,12 @@ int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* /*unused*/,
         if (timed) { CUDA_TRY(ctx, cudaEventRecord(ctx->kev[0], st)); ctx->kevProbes = n; }
         k_trace_primary<<<persistentBlocks, 128, 0, st>>>(sc, tp, rm, idx, ctx->dDirs, ctx->dHits, ctx->dRays, ctx->dMissQueue, ctx->dFrontQueue, ctx->dQueueCount); LAUNCH_CHECK(ctx);
         if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[1], st));
+        // The sky kernel only needs the miss queue: it runs on a second stream, concurrently with the sort and the front-hit shading.
+        const unsigned shadeBlocks = std::min<unsigned>(divUp(numRays, 128), unsigned(ctx->smCount) * 16u);
+        CUDA_TRY(ctx, cudaEventRecord(ctx->auxEvent[0], st));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->auxStream, ctx->auxEvent[0], 0));
+        launchShadeMiss(shadeBlocks, ctx->auxStream, sp, idx, ctx->dDirs, ctx->dMissQueue, ctx->dQueueCount, ctx->dRays); LAUNCH_CHECK(ctx);
+        CUDA_TRY(ctx, cudaEventRecord(ctx->auxEvent[1], ctx->auxStream));
         { // front-hit queue sorted by grid cell (radix sort over just the bits a cell index needs; unused slots carry all-ones keys).
           // A counting sort with a per-cell atomic histogram was slower: hit points cluster in few cells.
             CUDA_TRY(ctx, cudaMemsetAsync(ctx->dFrontKeys, 0xFF, size_t(numRays) * 4, st));
@@ -423,8 +429,6 @@ int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* /*unused*/,
             CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->dSortTemp, need, ctx->dFrontKeys, ctx->dFrontKeysOut, ctx->dFrontQueue, ctx->dFrontQueueSorted, int(numRays), 0, int(bits), st));
             ctx->launches += 3;
         }
-        const unsigned shadeBlocks = std::min<unsigned>(divUp(numRays, 128), unsigned(ctx->smCount) * 16u);
-        launchShadeMiss(shadeBlocks, st, sp, idx, ctx->dDirs, ctx->dMissQueue, ctx->dQueueCount, ctx->dRays); LAUNCH_CHECK(ctx);
         launchShadeFront(shadeBlocks, st, sc, pr, sp, idx, ctx->dDirs, ctx->dHits, ctx->dFrontQueueSorted, ctx->dQueueCount, ctx->dRays, ctx->dShadowQueue); LAUNCH_CHECK(ctx);
         if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[2], st));
         if (ctx->debugBuffers) CUDA_TRY(ctx, cudaMemsetAsync(ctx->dShadowFlags, 0, numRays, st));
@@ -432,6 +436,7 @@ int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* /*unused*/,
         if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[3], st));
         if (base + n >= count) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], st));
         bp.count = n;
+        CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->auxEvent[1], 0)); // sky results
         k_blend<<<divUp(n, BLEND_P), BLEND_COLS, 0, st>>>(bp, pr, idx, ctx->dRays, ctx->dBlendW, ctx->debugBuffers ? ctx->dIrrUnpacked : nullptr, ctx->debugBuffers ? ctx->dDepUnpacked : nullptr, base); LAUNCH_CHECK(ctx);
         if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[4], st));
     }
