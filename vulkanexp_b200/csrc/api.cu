@@ -29,6 +29,11 @@ static int upload(vkx_ctx* ctx, T** dst, const T* src, size_t n) {
 #define TRY(expr) do { int _rc = (expr); if (_rc != VKX_OK) return _rc; } while (0)
 #define BIND(ctx) do { if (!(ctx)) return VKX_E_INVALID; cudaError_t _e = cudaSetDevice((ctx)->device); if (_e != cudaSuccess) return vkx_fail((ctx), VKX_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(_e)); } while (0)
 
+int waitGather(vkx_ctx* ctx) { // orders the context's stream after a pending all-gather of the sampled atlases
+    if (ctx->gatherPending) { CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->gatherDone, 0)); ctx->gatherPending = false; }
+    return VKX_OK;
+}
+
 extern "C" {
 
 int vkx_abi_version(void) { return VKX_ABI_VERSION; }
@@ -91,6 +96,7 @@ void vkx_destroy(vkx_ctx* ctx) {
     if (ctx->auxStream) cudaStreamDestroy(ctx->auxStream);
     if (ctx->commStream) cudaStreamDestroy(ctx->commStream);
     if (ctx->commEvent) cudaEventDestroy(ctx->commEvent);
+    if (ctx->gatherDone) cudaEventDestroy(ctx->gatherDone);
     if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); cudaEventDestroy(ctx->evPublished); cudaEventDestroy(ctx->evCopyDone); }
     if (ctx->hStage) { cudaFreeHost(ctx->hStage); for (auto& e : ctx->stageEvent) if (e) cudaEventDestroy(e); }
     cudaStreamDestroy(ctx->stream);
@@ -100,7 +106,7 @@ void vkx_destroy(vkx_ctx* ctx) {
 const char* vkx_last_error(vkx_ctx* ctx) { return ctx ? ctx->err.c_str() : g_createError.c_str(); }
 uint64_t vkx_launch_count(vkx_ctx* ctx) { return ctx ? ctx->launches : 0; }
 void* vkx_stream(vkx_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
-int vkx_sync(vkx_ctx* ctx) { BIND(ctx); CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); return VKX_OK; }
+int vkx_sync(vkx_ctx* ctx) { BIND(ctx); TRY(waitGather(ctx)); CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); return VKX_OK; }
 
 // ---------------------------------------------------------------------------------------------------- geometry
 int vkx_scene_upload(vkx_ctx* ctx, const vkx_vertex* vertices, size_t numVertices, const uint32_t* indices, size_t numIndices,
@@ -403,6 +409,7 @@ int vkx_probes_update(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx_light* 
 
 int vkx_probes_download(vkx_ctx* ctx, uint32_t* irradiance, uint32_t* depth, uint32_t* state, float* rays, size_t raysCapacityBytes) {
     BIND(ctx);
+    TRY(waitGather(ctx));
     if (!ctx->probesReady) return vkx_fail(ctx, VKX_E_INVALID, "probes not initialised");
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     if (irradiance) CUDA_TRY(ctx, cudaMemcpy(irradiance, ctx->dIrrSampled, size_t(ctx->irrW) * ctx->irrH * 4, cudaMemcpyDeviceToHost));
@@ -421,6 +428,7 @@ int vkx_probes_download(vkx_ctx* ctx, uint32_t* irradiance, uint32_t* depth, uin
  * publish waits for them. Host buffers should be pinned. vkx_probes_download_wait blocks until the copies have landed. */
 int vkx_probes_download_async(vkx_ctx* ctx, uint32_t* irradiance, uint32_t* depth, uint32_t* state) {
     BIND(ctx);
+    TRY(waitGather(ctx));
     if (!ctx->probesReady) return vkx_fail(ctx, VKX_E_INVALID, "probes not initialised");
     if (!ctx->copyStream) {
         CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
@@ -444,6 +452,7 @@ int vkx_probes_download_wait(vkx_ctx* ctx) {
 
 int vkx_probes_upload(vkx_ctx* ctx, const uint32_t* irradiance, const uint32_t* depth, const uint32_t* state) {
     BIND(ctx);
+    TRY(waitGather(ctx));
     if (!ctx->probesReady) return vkx_fail(ctx, VKX_E_INVALID, "probes not initialised");
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     const size_t irrBytes = size_t(ctx->irrW) * ctx->irrH * 4, depBytes = size_t(ctx->depW) * ctx->depH * 4, stBytes = size_t(ctx->probeCount) * 4;
@@ -473,6 +482,7 @@ int vkx_probes_download_hits(vkx_ctx* ctx, vkx_hit* hits, uint8_t* shadow) {
 
 int vkx_probes_timings(vkx_ctx* ctx, float ms[5]) {
     BIND(ctx);
+    TRY(waitGather(ctx));
     if (!ms) return VKX_E_INVALID;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < 5; ++i) ms[i] = 0.f;
@@ -488,6 +498,7 @@ int vkx_probes_timings(vkx_ctx* ctx, float ms[5]) {
 
 int vkx_probes_kernel_timings(vkx_ctx* ctx, float ms[4], uint32_t* probes, uint32_t* shadowRays) {
     BIND(ctx);
+    TRY(waitGather(ctx));
     if (!ms) return VKX_E_INVALID;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < 4; ++i) ms[i] = 0.f;
@@ -526,6 +537,7 @@ int vkx_comm_init(vkx_ctx* ctx, int rank, int nranks, const void* id128) {
     ctx->comm = reinterpret_cast<ncclComm*>(comm); ctx->rank = rank; ctx->nranks = nranks;
     if (!ctx->commStream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->commStream, cudaStreamNonBlocking));
     if (!ctx->commEvent) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->commEvent, cudaEventDisableTiming));
+    if (!ctx->gatherDone) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->gatherDone, cudaEventDisableTiming));
     return VKX_OK;
 }
 
@@ -543,11 +555,11 @@ int vkx_probes_update_sharded(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx
     if (rz % n != 0) return vkx_fail(ctx, VKX_E_INVALID, "grid z resolution %u is not divisible by %u ranks", rz, n);
     const size_t irrBytes = size_t(ctx->irrW) * ctx->irrH * 4, depBytes = size_t(ctx->depW) * ctx->depH * 4, stBytes = size_t(ctx->probeCount) * 4;
     if (!ctx->dIrrNext) { CUDA_TRY(ctx, cudaMalloc(&ctx->dIrrNext, irrBytes)); CUDA_TRY(ctx, cudaMalloc(&ctx->dDepNext, depBytes)); CUDA_TRY(ctx, cudaMalloc(&ctx->dStateNext, stBytes)); }
-    // chunks of at least ~8192 probes per rank (smaller launches do not fill the persistent kernels), at most 4 chunks
+    // One chunk per frame: the all-gather of frame f is not waited for at the end of the update but before the first kernel of frame
+    // f+1 that reads the sampled atlases (k_shade_front), so it overlaps frame f+1's primary traversal, which never touches them.
+    // (Measured on 4 GPUs: splitting the slab into chunks to overlap inside the frame cost more in small launches than it hid.)
     const uint32_t slicesPerRank = rz / n;
-    uint32_t K = std::min(4u, std::max(1u, (slicesPerRank * plane) / 8192u));
-    while (slicesPerRank % K != 0) --K;
-    const uint32_t s = slicesPerRank / K;
+    const uint32_t K = 1, s = slicesPerRank / K;
     ncclComm_t comm = reinterpret_cast<ncclComm_t>(ctx->comm);
     cudaStream_t st = ctx->stream, cs = ctx->commStream;
     if (ctx->copyPending) { CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->commStream, ctx->evCopyDone, 0)); ctx->copyPending = false; } // read-back of the buffers about to be overwritten
@@ -572,8 +584,8 @@ int vkx_probes_update_sharded(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx
         if (r != ncclSuccess) return vkx_fail(ctx, VKX_E_NCCL, "ncclAllGather: %s", ncclGetErrorString(r));
     }
     ctx->shardOrderReady = true;
-    CUDA_TRY(ctx, cudaEventRecord(ctx->commEvent, cs));
-    CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->commEvent, 0));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->gatherDone, cs));
+    ctx->gatherPending = true; // waited for by the next reader of the sampled atlases (waitGather)
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], st));
     // publish = swap; the work buffers keep this rank's slices current (they are the only ones it reads as `previous`)
     std::swap(ctx->dIrrSampled, ctx->dIrrNext); std::swap(ctx->dDepSampled, ctx->dDepNext); std::swap(ctx->dStateSampled, ctx->dStateNext);

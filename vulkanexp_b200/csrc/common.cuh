@@ -100,7 +100,7 @@ struct vkx_ctx {
 
     // multi-GPU
     ncclComm* comm = nullptr; int rank = 0, nranks = 1;
-    cudaStream_t commStream = nullptr; cudaEvent_t commEvent = nullptr;
+    cudaStream_t commStream = nullptr; cudaEvent_t commEvent = nullptr, gatherDone = nullptr; bool gatherPending = false;
     uint32_t *dIrrNext = nullptr, *dDepNext = nullptr, *dStateNext = nullptr; // all-gather targets (sharded update)
     bool shardedLast = false, shardOrderReady = false;
 
@@ -132,6 +132,7 @@ static inline unsigned divUp(size_t a, size_t b) { return unsigned((a + b - 1) /
 
 // ---- implemented in bvh_build.cu
 int bvhBuildDevice(vkx_ctx* ctx);
+int waitGather(vkx_ctx* ctx); // api.cu
 // ---- ddgi.cu
 int ddgiClassify(vkx_ctx* ctx, const float* dirs512);
 int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* hostIndices, uint32_t count, uint32_t firstProbe, bool publishAll);

@@ -429,6 +429,7 @@ int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* /*unused*/,
             CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->dSortTemp, need, ctx->dFrontKeys, ctx->dFrontKeysOut, ctx->dFrontQueue, ctx->dFrontQueueSorted, int(numRays), 0, int(bits), st));
             ctx->launches += 3;
         }
+        { int rc = waitGather(ctx); if (rc != VKX_OK) return rc; } // sharded path: the previous frame's atlas all-gather must have landed
         launchShadeFront(shadeBlocks, st, sc, pr, sp, idx, ctx->dDirs, ctx->dHits, ctx->dFrontQueueSorted, ctx->dQueueCount, ctx->dRays, ctx->dShadowQueue); LAUNCH_CHECK(ctx);
         if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[2], st));
         if (ctx->debugBuffers) CUDA_TRY(ctx, cudaMemsetAsync(ctx->dShadowFlags, 0, numRays, st));
