@@ -245,10 +245,13 @@ def main():
     # ---- end to end through the C ABI with host buffers: every step copies the to-update list + parameters host->device and reads
     # both atlases and the state words back into pinned host memory. The read-back of step s is queued asynchronously
     # (vkx_probes_download_async) and overlaps the tracing of step s+1; all copies have landed before the clock stops.
+    # With N ranks every rank reads back the z-slab it traced, so the job as a whole reads the volume back exactly once per step.
     (ih, iw), (dh, dw) = grid.atlas_shapes()
+    ih, dh, nst = ih // n, dh // n, grid.probe_count // n
+    z0, z1 = rank * (grid.resolution[2] // n), (rank + 1) * (grid.resolution[2] // n)
     outs = []
     for _ in range(2):
-        pin = (torch.empty((ih, iw), dtype=torch.int32).pin_memory(), torch.empty((dh, dw), dtype=torch.int32).pin_memory(), torch.empty(grid.probe_count, dtype=torch.int32).pin_memory())
+        pin = (torch.empty((ih, iw), dtype=torch.int32).pin_memory(), torch.empty((dh, dw), dtype=torch.int32).pin_memory(), torch.empty(nst, dtype=torch.int32).pin_memory())
         outs.append((pin, tuple(t.numpy().view(np.uint32) for t in pin)))
     pin_irr, pin_dep, pin_st = outs[0][0]
     pin_idx = torch.arange(grid.probe_count, dtype=torch.int32).pin_memory()
@@ -261,7 +264,7 @@ def main():
             ctx.probes_update_sharded(grid, light, Rs[args.warmup + args.steps + s], sync=False)
         else:
             ctx.probes_update(grid, light, Rs[args.warmup + args.steps + s], idx_np, sync=False)
-        ctx.probes_download_async(outs[s & 1][1])
+        ctx.probes_download_slab_async(z0, z1, outs[s & 1][1])
     ctx.probes_download_wait()
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
@@ -271,7 +274,8 @@ def main():
         e2e_ms = float(t.item())
     checksum = int(outs[(args.steps - 1) & 1][1][0].astype(np.uint64).sum() % (1 << 32))  # the host really holds the last step's atlas
     h2d = (grid.probe_count * 4 if world == 1 else 0) + 64 + 32 + 64 + RAYS * 16
-    d2h = pin_irr.numel() * 4 + pin_dep.numel() * 4 + pin_st.numel() * 4
+    d2h = (pin_irr.numel() * 4 + pin_dep.numel() * 4 + pin_st.numel() * 4) * n  # whole job
+    h2d *= n
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -283,7 +287,7 @@ def main():
             "full_volume_update_ms": ms_per_step, "grays_per_sec_per_gpu": value / n / 1e9,
             "gpu_launches": int(launches), "clocks": clocks,
             "e2e": {"value": rays_per_step_total / (e2e_ms * 1e-3), "unit": "probe rays/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "what": "vkx_probes_update from host buffers + vkx_probes_download_async of both atlases and the state words into pinned host memory every step (read-back of step s overlaps step s+1)", "host_atlas_checksum": checksum},
+                    "what": "vkx_probes_update from host buffers + asynchronous read-back of both atlases and the state words into pinned host memory every step (each rank its own z-slab; read-back of step s overlaps step s+1); byte counts are whole-job", "host_atlas_checksum": checksum},
             "kernel_ms": {k: v / args.steps for k, v in kt.items()},
         }
         if not args.no_cpu_baseline:

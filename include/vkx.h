@@ -176,6 +176,8 @@ int vkx_probes_download(vkx_ctx* ctx, uint32_t* irradiance, uint32_t* depth, uin
 /* Asynchronous read-back: queues the copies behind the last publish on a copy stream and returns; the next update's publish waits
  * for them. Host buffers should be pinned (cudaHostAlloc / torch pin_memory). */
 int vkx_probes_download_async(vkx_ctx* ctx, uint32_t* irradiance, uint32_t* depth, uint32_t* state);
+/* Same for the z-slices [z0, z1) only (the contiguous rows one rank of a sharded run owns); pointers address the first copied row. */
+int vkx_probes_download_slab_async(vkx_ctx* ctx, uint32_t z0, uint32_t z1, uint32_t* irradiance, uint32_t* depth, uint32_t* state);
 int vkx_probes_download_wait(vkx_ctx* ctx);
 /* Checkpoint/resume of GI state. NULL skips an array. */
 int vkx_probes_upload(vkx_ctx* ctx, const uint32_t* irradiance, const uint32_t* depth, const uint32_t* state);

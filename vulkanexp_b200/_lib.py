@@ -149,6 +149,10 @@ class Context:
         irr, dep, st = out
         self._check(self.l.vkx_probes_download_async(self.h, _p(irr), _p(dep), _p(st)))
 
+    def probes_download_slab_async(self, z0, z1, out):
+        irr, dep, st = out
+        self._check(self.l.vkx_probes_download_slab_async(self.h, C.c_uint32(z0), C.c_uint32(z1), _p(irr), _p(dep), _p(st)))
+
     def probes_download_wait(self):
         self._check(self.l.vkx_probes_download_wait(self.h))
 

@@ -444,6 +444,27 @@ int vkx_probes_download_async(vkx_ctx* ctx, uint32_t* irradiance, uint32_t* dept
     ctx->copyPending = true;
     return VKX_OK;
 }
+/* Same for the z-slices [z0, z1) only (contiguous atlas rows [8*z0, 8*z1) / [16*z0, 16*z1) and state words): what one rank of a sharded
+ * run owns. Destination pointers address the first copied row. */
+int vkx_probes_download_slab_async(vkx_ctx* ctx, uint32_t z0, uint32_t z1, uint32_t* irradiance, uint32_t* depth, uint32_t* state) {
+    BIND(ctx);
+    TRY(waitGather(ctx));
+    if (!ctx->probesReady || z0 >= z1 || z1 > uint32_t(ctx->grid.resolution[2])) return vkx_fail(ctx, VKX_E_INVALID, "vkx_probes_download_slab_async: bad slab");
+    if (!ctx->copyStream) {
+        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->evPublished, cudaEventDisableTiming));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->evCopyDone, cudaEventDisableTiming));
+    }
+    const size_t plane = size_t(ctx->grid.resolution[0]) * size_t(ctx->grid.resolution[1]), nz = z1 - z0;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->evPublished, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copyStream, ctx->evPublished, 0));
+    if (irradiance) CUDA_TRY(ctx, cudaMemcpyAsync(irradiance, ctx->dIrrSampled + size_t(8 * z0) * ctx->irrW, size_t(8 * nz) * ctx->irrW * 4, cudaMemcpyDeviceToHost, ctx->copyStream));
+    if (depth) CUDA_TRY(ctx, cudaMemcpyAsync(depth, ctx->dDepSampled + size_t(16 * z0) * ctx->depW, size_t(16 * nz) * ctx->depW * 4, cudaMemcpyDeviceToHost, ctx->copyStream));
+    if (state) CUDA_TRY(ctx, cudaMemcpyAsync(state, ctx->dStateSampled + size_t(z0) * plane, nz * plane * 4, cudaMemcpyDeviceToHost, ctx->copyStream));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->evCopyDone, ctx->copyStream));
+    ctx->copyPending = true;
+    return VKX_OK;
+}
 int vkx_probes_download_wait(vkx_ctx* ctx) {
     BIND(ctx);
     if (ctx->evCopyDone) CUDA_TRY(ctx, cudaEventSynchronize(ctx->evCopyDone));
