@@ -113,7 +113,6 @@ __global__ void __launch_bounds__(128) k_direct_light(DeviceScene sc, vkx_light 
 // only depend on stdDev are hoisted out of the tap loops and exp is ex2.approx (tolerance of the filter outputs: 1e-3 absolute).
 __device__ __forceinline__ float gaussNorm(float stdDev) { return 1.0f / (sqrtf(2.0f * 3.14159f) * stdDev); }
 __device__ __forceinline__ float gaussInvTwoVar(float stdDev) { return 1.0f / (2.0f * stdDev * stdDev); }
-__device__ __forceinline__ float gaussian(float norm, float invTwoVar, float dist) { return norm * __expf(-(dist * dist) * invTwoVar); }
 #define MAX_DEV 7.0f
 #define I_MAX_DEV 8
 #define DEPTH_FACTOR (1.0f / 0.5f)
@@ -126,6 +125,44 @@ __device__ __forceinline__ int filterWindow(float depth, float& stdDev) {
     return int(clampS(ceilf(sqrtf(-2.0f * stdDev * stdDev * logf(0.01f * stdDev * sqrtf(2.0f * 3.14159f)))), 1.0f, float(I_MAX_DEV)));
 }
 
+// Tap loop shared by both passes. The reference's factor gaussian(stdDev, i) * gaussian(depthStdDev, |dz|) is evaluated as
+// w[|i|] * ex2(dz^2 * cd): w[] holds the spatial gaussian times both normalisations (9 values per pixel, zero beyond the window),
+// cd = -log2(e) / (2 depthStdDev^2). Taps the reference skips at the image border are given depth = +inf in shared memory
+// (ex2(-inf) = 0, an exact zero factor); the one out-of-bounds tap it does read (coordinate == size) is stored as
+// depth 0 / value 0. Taps are accumulated in the reference's order (ascending offset) with FMAs.
+__device__ __forceinline__ float ex2Approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#define LOG2E 1.4426950408889634f
+__device__ __forceinline__ void spatialWeights(float depth, float (&w)[I_MAX_DEV + 1]) {
+    float stdDev; const int window = filterWindow(depth, stdDev);
+    const float gn = gaussNorm(stdDev) * gaussNorm(DEPTH_STD);
+    const float gv = -gaussInvTwoVar(stdDev) * LOG2E;
+#pragma unroll
+    for (int k = 0; k <= I_MAX_DEV; ++k) w[k] = k <= window ? gn * ex2Approx(float(k * k) * gv) : 0.0f;
+}
+template <int STRIDE>
+__device__ __forceinline__ float4 filterTaps(const float* __restrict__ sDepth, const float4* __restrict__ sIn, int c, float depth) {
+    float w[I_MAX_DEV + 1];
+    spatialWeights(depth, w);
+    const float cd = -gaussInvTwoVar(DEPTH_STD) * LOG2E;
+    float totalFactor = 0.0f; float4 fin = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = -I_MAX_DEV; i <= I_MAX_DEV; ++i) {
+        const float dz = depth - sDepth[c + i * STRIDE];
+        const float factor = w[i < 0 ? -i : i] * ex2Approx(dz * dz * cd);
+        totalFactor += factor;
+        const float4 v = sIn[c + i * STRIDE];
+        fin.x = __fmaf_rn(factor, v.x, fin.x); fin.y = __fmaf_rn(factor, v.y, fin.y); fin.z = __fmaf_rn(factor, v.z, fin.z);
+    }
+    // the temporal stage tests fin.z == 1.0f: sum / sum must stay exactly 1 although the quotient is a multiplication by the reciprocal
+    if (totalFactor > 1e-2f) {
+        const float inv = 1.0f / totalFactor;
+        fin.x = fin.x == totalFactor ? 1.0f : fin.x * inv; fin.y = fin.y == totalFactor ? 1.0f : fin.y * inv; fin.z = fin.z == totalFactor ? 1.0f : fin.z * inv;
+    } else { fin.x = fin.y = fin.z = 0.f; }
+    return fin;
+}
+// halo depth for coordinate q of an axis of length n: inside -> the image, q == n -> 0 (read by the reference as an out-of-bounds load), else +inf (skipped by it)
+__device__ __forceinline__ float haloDepth(int q, int n) { return q == n ? 0.0f : __int_as_float(0x7F800000); }
+
 // X pass: one CTA = 256 consecutive pixels of one row; depth + input staged in shared memory with an 8-texel halo.
 __global__ void __launch_bounds__(256) k_filter_x(uint32_t W, uint32_t H, const float4* __restrict__ posDepth, const float4* __restrict__ in, float4* __restrict__ out) {
     __shared__ float sDepth[256 + 2 * I_MAX_DEV];
@@ -134,25 +171,14 @@ __global__ void __launch_bounds__(256) k_filter_x(uint32_t W, uint32_t H, const 
     for (int i = tid; i < 256 + 2 * I_MAX_DEV; i += 256) {
         const int x = x0 + i - I_MAX_DEV;
         const bool ok = x >= 0 && x < int(W);
-        sDepth[i] = ok ? posDepth[size_t(y) * W + x].w : 0.0f;
+        sDepth[i] = ok ? posDepth[size_t(y) * W + x].w : haloDepth(x, int(W));
         sIn[i] = ok ? in[size_t(y) * W + x] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
     const int x = x0 + tid;
     if (x >= int(W)) return;
     const float depth = sDepth[tid + I_MAX_DEV];
-    float stdDev; const int window = filterWindow(depth, stdDev);
-    const int minOffset = -min(window, x), maxOffset = min(window, int(W) - x);
-    float totalFactor = 0.0f; float4 fin = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float gn = gaussNorm(stdDev), gv = gaussInvTwoVar(stdDev), dn = gaussNorm(DEPTH_STD), dv = gaussInvTwoVar(DEPTH_STD);
-    for (int i = minOffset; i <= maxOffset; ++i) {
-        float factor = gaussian(gn, gv, float(i));
-        factor *= gaussian(dn, dv, fabsf(depth - sDepth[tid + I_MAX_DEV + i]));
-        totalFactor += factor;
-        const float4 v = sIn[tid + I_MAX_DEV + i];
-        fin.x += factor * v.x; fin.y += factor * v.y; fin.z += factor * v.z; fin.w += factor * v.w;
-    }
-    if (totalFactor > 1e-2f) { fin.x = fin.x / totalFactor; fin.y = fin.y / totalFactor; fin.z = fin.z / totalFactor; } else { fin.x = fin.y = fin.z = 0.f; }
+    const float4 fin = filterTaps<1>(sDepth, sIn, tid + I_MAX_DEV, depth);
     out[size_t(y) * W + x] = make_float4(fin.x, fin.y, fin.z, depth);
 }
 
@@ -168,7 +194,7 @@ __global__ void __launch_bounds__(256) k_filter_y(uint32_t W, uint32_t H, const 
     for (int r = ty; r < 64 + 2 * I_MAX_DEV; r += 256 / TW) {
         const int y = y0 + r - I_MAX_DEV;
         const bool ok = x < int(W) && y >= 0 && y < int(H);
-        sDepth[r * TW + tx] = ok ? posDepth[size_t(y) * W + x].w : 0.0f;
+        sDepth[r * TW + tx] = ok ? posDepth[size_t(y) * W + x].w : haloDepth(y, int(H));
         sIn[r * TW + tx] = ok ? in[size_t(y) * W + x] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
@@ -179,18 +205,7 @@ __global__ void __launch_bounds__(256) k_filter_y(uint32_t W, uint32_t H, const 
         const int c = (ry + I_MAX_DEV) * TW + tx;
         const float4 pd = posDepth[size_t(y) * W + x];
         const float depth = pd.w;
-        float stdDev; const int window = filterWindow(depth, stdDev);
-        const int minOffset = -min(window, y), maxOffset = min(window, int(H) - y);
-        float totalFactor = 0.0f; float4 fin = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float gn = gaussNorm(stdDev), gv = gaussInvTwoVar(stdDev), dn = gaussNorm(DEPTH_STD), dv = gaussInvTwoVar(DEPTH_STD);
-        for (int i = minOffset; i <= maxOffset; ++i) {
-            float factor = gaussian(gn, gv, float(i));
-            factor *= gaussian(dn, dv, fabsf(depth - sDepth[c + i * TW]));
-            totalFactor += factor;
-            const float4 v = sIn[c + i * TW];
-            fin.x += factor * v.x; fin.y += factor * v.y; fin.z += factor * v.z; fin.w += factor * v.w;
-        }
-        if (totalFactor > 1e-2f) { fin.x = fin.x / totalFactor; fin.y = fin.y / totalFactor; fin.z = fin.z / totalFactor; } else { fin.x = fin.y = fin.z = 0.f; }
+        float4 fin = filterTaps<TW>(sDepth, sIn, c, depth);
         // temporal accumulation, directLightFilter.glsl:110-142
         fin.x = clampS(fin.x, 0.0f, 1.0f);
         fin.y = fin.x * fin.x;
