@@ -53,7 +53,8 @@ __global__ void __launch_bounds__(128) k_gbuffer(DeviceScene sc, M4 invView, M4 
 }
 
 __device__ __forceinline__ v3 rotateAxis(v3 p, v3 axis, float angle) { // common.glsl:6-8
-    return mix3(dot3(axis, p) * axis, p, cosf(angle)) + cross3(axis, p) * sinf(angle);
+    float sn, cs; sincosf(angle, &sn, &cs);
+    return mix3(dot3(axis, p) * axis, p, cs) + cross3(axis, p) * sn;
 }
 
 // general REPEAT wrap (uv = pixel / 64 is far outside [0, 1), unlike the atlas coordinates bilinearSetup() handles)
@@ -62,8 +63,8 @@ __device__ __forceinline__ void bilinearSetupRepeat(float u, uint32_t size, int&
     const float fl = floorf(x);
     f = x - fl;
     const int isz = int(size), i = int(fl);
-    i0 = ((i % isz) + isz) % isz;
-    i1 = (i0 + 1) % isz;
+    if ((size & (size - 1u)) == 0u) { i0 = i & (isz - 1); i1 = (i0 + 1) & (isz - 1); } // power-of-two noise tile (the reference's is 64 x 64)
+    else { i0 = ((i % isz) + isz) % isz; i1 = (i0 + 1) % isz; }
 }
 
 __device__ __forceinline__ float4 sampleNoise(const float* __restrict__ tex, uint32_t nw, uint32_t nh, float u, float v) { // linear, REPEAT
@@ -140,17 +141,17 @@ __device__ __forceinline__ void spatialWeights(float depth, float (&w)[I_MAX_DEV
     for (int k = 0; k <= I_MAX_DEV; ++k) w[k] = k <= window ? gn * ex2Approx(float(k * k) * gv) : 0.0f;
 }
 template <int STRIDE>
-__device__ __forceinline__ float4 filterTaps(const float* __restrict__ sDepth, const float4* __restrict__ sIn, int c, float depth) {
+__device__ __forceinline__ float4 filterTaps(const float4* __restrict__ sIn, int c, float depth) { // sIn: (value.xyz, depth)
     float w[I_MAX_DEV + 1];
     spatialWeights(depth, w);
     const float cd = -gaussInvTwoVar(DEPTH_STD) * LOG2E;
     float totalFactor = 0.0f; float4 fin = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int i = -I_MAX_DEV; i <= I_MAX_DEV; ++i) {
-        const float dz = depth - sDepth[c + i * STRIDE];
+        const float4 v = sIn[c + i * STRIDE];
+        const float dz = depth - v.w;
         const float factor = w[i < 0 ? -i : i] * ex2Approx(dz * dz * cd);
         totalFactor += factor;
-        const float4 v = sIn[c + i * STRIDE];
         fin.x = __fmaf_rn(factor, v.x, fin.x); fin.y = __fmaf_rn(factor, v.y, fin.y); fin.z = __fmaf_rn(factor, v.z, fin.z);
     }
     // the temporal stage tests fin.z == 1.0f: sum / sum must stay exactly 1 although the quotient is a multiplication by the reciprocal
@@ -165,20 +166,19 @@ __device__ __forceinline__ float haloDepth(int q, int n) { return q == n ? 0.0f 
 
 // X pass: one CTA = 256 consecutive pixels of one row; depth + input staged in shared memory with an 8-texel halo.
 __global__ void __launch_bounds__(256) k_filter_x(uint32_t W, uint32_t H, const float4* __restrict__ posDepth, const float4* __restrict__ in, float4* __restrict__ out) {
-    __shared__ float sDepth[256 + 2 * I_MAX_DEV];
     __shared__ float4 sIn[256 + 2 * I_MAX_DEV];
     const int y = int(blockIdx.y), x0 = int(blockIdx.x) * 256, tid = int(threadIdx.x);
     for (int i = tid; i < 256 + 2 * I_MAX_DEV; i += 256) {
         const int x = x0 + i - I_MAX_DEV;
-        const bool ok = x >= 0 && x < int(W);
-        sDepth[i] = ok ? posDepth[size_t(y) * W + x].w : haloDepth(x, int(W));
-        sIn[i] = ok ? in[size_t(y) * W + x] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 v = make_float4(0.f, 0.f, 0.f, haloDepth(x, int(W)));
+        if (x >= 0 && x < int(W)) { v = in[size_t(y) * W + x]; v.w = posDepth[size_t(y) * W + x].w; }
+        sIn[i] = v;
     }
     __syncthreads();
     const int x = x0 + tid;
     if (x >= int(W)) return;
-    const float depth = sDepth[tid + I_MAX_DEV];
-    const float4 fin = filterTaps<1>(sDepth, sIn, tid + I_MAX_DEV, depth);
+    const float depth = sIn[tid + I_MAX_DEV].w;
+    const float4 fin = filterTaps<1>(sIn, tid + I_MAX_DEV, depth);
     out[size_t(y) * W + x] = make_float4(fin.x, fin.y, fin.z, depth);
 }
 
@@ -186,16 +186,15 @@ __global__ void __launch_bounds__(256) k_filter_x(uint32_t W, uint32_t H, const 
 __global__ void __launch_bounds__(256) k_filter_y(uint32_t W, uint32_t H, const float4* __restrict__ posDepth, const float4* __restrict__ in, const float4* __restrict__ prevImg,
                                                   M4 prevView, M4 prevProj, float3 prevOrigin, float4* __restrict__ out) {
     constexpr int TW = 16;
-    __shared__ float sDepth[(64 + 2 * I_MAX_DEV) * TW];
     __shared__ float4 sIn[(64 + 2 * I_MAX_DEV) * TW];
     const int x0 = int(blockIdx.x) * TW, y0 = int(blockIdx.y) * 64;
     const int tx = int(threadIdx.x) & (TW - 1), ty = int(threadIdx.x) / TW; // 16 rows of 16
     const int x = x0 + tx;
     for (int r = ty; r < 64 + 2 * I_MAX_DEV; r += 256 / TW) {
         const int y = y0 + r - I_MAX_DEV;
-        const bool ok = x < int(W) && y >= 0 && y < int(H);
-        sDepth[r * TW + tx] = ok ? posDepth[size_t(y) * W + x].w : haloDepth(y, int(H));
-        sIn[r * TW + tx] = ok ? in[size_t(y) * W + x] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 v = make_float4(0.f, 0.f, 0.f, haloDepth(y, int(H)));
+        if (x < int(W) && y >= 0 && y < int(H)) v = in[size_t(y) * W + x]; // .w of the X pass output is the depth
+        sIn[r * TW + tx] = v;
     }
     __syncthreads();
     if (x >= int(W)) return;
@@ -205,7 +204,7 @@ __global__ void __launch_bounds__(256) k_filter_y(uint32_t W, uint32_t H, const 
         const int c = (ry + I_MAX_DEV) * TW + tx;
         const float4 pd = posDepth[size_t(y) * W + x];
         const float depth = pd.w;
-        float4 fin = filterTaps<TW>(sDepth, sIn, c, depth);
+        float4 fin = filterTaps<TW>(sIn, c, depth);
         // temporal accumulation, directLightFilter.glsl:110-142
         fin.x = clampS(fin.x, 0.0f, 1.0f);
         fin.y = fin.x * fin.x;
