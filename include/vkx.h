@@ -215,9 +215,19 @@ int vkx_gbuffer_generate(vkx_ctx* ctx, const vkx_camera* cam);
 /* Or upload a host G-buffer (RGBA32F, [h][w][4]). */
 int vkx_gbuffer_upload(vkx_ctx* ctx, const float* positionDepth, const float* normalMetalness);
 int vkx_gbuffer_download(vkx_ctx* ctx, float* positionDepth, float* normalMetalness);
+/* The two G-buffer targets only the composite reads: albedoRoughness and emissive (src/shaders/GBuffer.frag:66-67).
+ * vkx_gbuffer_generate fills them too (albedo = interpolated vertex colour * baseColorFactor, untextured). */
+int vkx_gbuffer_upload_material(vkx_ctx* ctx, const float* albedoRoughness, const float* emissive);
+int vkx_gbuffer_download_material(vkx_ctx* ctx, float* albedoRoughness, float* emissive);
 /* One frame of directLight.rgen -> directLightFilterX -> directLightFilterY (src/SwapchainManagement.cpp:409-438)
  * with the history ping-pong of src/Editor.cpp:287-316. */
 int vkx_shadow_frame(vkx_ctx* ctx, const vkx_camera* cur, const vkx_camera* prev, const vkx_light* light, int sync);
+/* Final composite of the frame, src/shaders/FinalGather.frag:38-77 (drawn by src/SwapchainManagement.cpp:466-474): sky on
+ * empty pixels, else direct * (filtered shadow of the last vkx_shadow_frame) + specular * reflection + sampleProbes(sampled
+ * atlases) * diffuse + emissive. reflection: optional host RGBA32F [h][w][4] image (the reflection pass is out of scope), NULL = black.
+ * Output: linear RGBA32F, device resident; vkx_final_gather_download copies it out and returns the kernel time. */
+int vkx_final_gather(vkx_ctx* ctx, const vkx_camera* cam, const vkx_light* light, const float* reflection, int sync);
+int vkx_final_gather_download(vkx_ctx* ctx, float* rgba, float* ms);
 /* stage: 0 = raw 1-spp (directLight.rgen output), 1 = after filter X, 2 = final (after Y + temporal). RGBA32F. */
 int vkx_shadow_download(vkx_ctx* ctx, int stage, float* rgba);
 /* Parity side buffers of the last frame: jittered light directions [h][w][4] floats, mask bytes (0 not traced, 1 lit, 2 shadowed). */

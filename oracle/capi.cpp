@@ -164,6 +164,22 @@ int orc_gbuffer_download(orc_ctx* c, float* pd, float* nm) {
     if (nm) std::memcpy(nm, c->shadow.normalMetalness.data(), c->shadow.normalMetalness.size() * 4);
     return 0;
 }
+int orc_gbuffer_upload_material(orc_ctx* c, const float* ar, const float* em) {
+    std::memcpy(c->shadow.albedoRoughness.data(), ar, c->shadow.albedoRoughness.size() * 4);
+    std::memcpy(c->shadow.emissive.data(), em, c->shadow.emissive.size() * 4); return 0;
+}
+int orc_gbuffer_download_material(orc_ctx* c, float* ar, float* em) {
+    if (ar) std::memcpy(ar, c->shadow.albedoRoughness.data(), c->shadow.albedoRoughness.size() * 4);
+    if (em) std::memcpy(em, c->shadow.emissive.data(), c->shadow.emissive.size() * 4);
+    return 0;
+}
+int orc_final_gather(orc_ctx* c, const vkx_camera* cam, const vkx_light* l, const float* reflection, double* seconds) {
+    auto t0 = std::chrono::steady_clock::now();
+    oshadow::finalGather(c->scene, c->probes, c->shadow, *cam, *l, reflection);
+    if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return 0;
+}
+int orc_final_gather_download(orc_ctx* c, float* rgba) { std::memcpy(rgba, c->shadow.gathered.data(), c->shadow.gathered.size() * 4); return 0; }
 int orc_shadow_frame(orc_ctx* c, const vkx_camera* cur, const vkx_camera* prev, const vkx_light* l, const float* dirOverride, double* seconds) {
     auto t0 = std::chrono::steady_clock::now();
     oshadow::frame(c->scene, c->shadow, *cur, *prev, *l, dirOverride);

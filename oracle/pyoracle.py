@@ -157,6 +157,24 @@ class Oracle:
         self.l.orc_gbuffer_download(self.h, _p(pd), _p(nm))
         return pd, nm
 
+    def gbuffer_upload_material(self, ar, em):
+        ar = np.ascontiguousarray(ar, dtype=np.float32); em = np.ascontiguousarray(em, dtype=np.float32)
+        self.l.orc_gbuffer_upload_material(self.h, _p(ar), _p(em))
+
+    def gbuffer_download_material(self):
+        ar = np.zeros((self.sh, self.sw, 4), dtype=np.float32)
+        em = np.zeros((self.sh, self.sw, 4), dtype=np.float32)
+        self.l.orc_gbuffer_download_material(self.h, _p(ar), _p(em))
+        return ar, em
+
+    def final_gather(self, cam, light, reflection=None):
+        r = np.ascontiguousarray(reflection, dtype=np.float32) if reflection is not None else None
+        sec = C.c_double(0)
+        self.l.orc_final_gather(self.h, C.byref(cam), C.byref(light), _p(r) if r is not None else None, C.byref(sec))
+        img = np.zeros((self.sh, self.sw, 4), dtype=np.float32)
+        self.l.orc_final_gather_download(self.h, _p(img))
+        return img, sec.value
+
     def shadow_frame(self, cur, prev, light, dir_override=None):
         d = np.ascontiguousarray(dir_override, dtype=np.float32) if dir_override is not None else None
         sec = C.c_double(0)

@@ -48,6 +48,7 @@ void init(State& st, uint32_t w, uint32_t h) {
     st.w = w; st.h = h;
     size_t n = size_t(w) * h * 4;
     st.positionDepth.assign(n, 0.0f); st.normalMetalness.assign(n, 0.0f);
+    st.albedoRoughness.assign(n, 0.0f); st.emissive.assign(n, 0.0f); st.gathered.assign(n, 0.0f);
     st.raw.assign(n, 0.0f); st.filteredX.assign(n, 0.0f); st.final_.assign(n, 0.0f); st.previous.assign(n, 0.0f);
     st.dirs.assign(size_t(w) * h * 3, 0.0f); st.mask.assign(size_t(w) * h, 0);
 }
@@ -68,19 +69,29 @@ void gbufferGenerate(const oddgi::Scene& s, State& st, const vkx_camera& cam) {
         size_t pi_ = (size_t(y) * st.w + x) * 4;
         vkx_hit h;
         float* pd = &st.positionDepth[pi_]; float* nm = &st.normalMetalness[pi_];
+        float* ar = &st.albedoRoughness[pi_]; float* em = &st.emissive[pi_];
         pd[0] = pd[1] = pd[2] = pd[3] = 0.0f; nm[0] = nm[1] = nm[2] = nm[3] = 0.0f;
+        ar[0] = ar[1] = ar[2] = ar[3] = 0.0f; em[0] = em[1] = em[2] = em[3] = 0.0f;
         if (!obvh::traceClosest(s.bvh, &origin.x, &dir.x, 0.001f, 100000.0f, 0xFFu, h)) continue;
         vec3 position = dir * h.t + origin;
         const vkx_instance& inst = s.instances[h.instance];
         const vkx_offset_entry& oe = s.offsets[inst.meshEntry];
         uint32_t prim = h.primitive & 0x7FFFFFFFu;
-        vec3 n[3];
-        for (int c = 0; c < 3; ++c) { const float* nn = s.vertices[oe.vertexOffset + s.indices[oe.indexOffset + 3 * prim + c]].normal; n[c] = V3(nn[0], nn[1], nn[2]); }
+        vec3 n[3], col[3];
+        for (int c = 0; c < 3; ++c) {
+            const vkx_vertex& vx = s.vertices[oe.vertexOffset + s.indices[oe.indexOffset + 3 * prim + c]];
+            n[c] = V3(vx.normal[0], vx.normal[1], vx.normal[2]); col[c] = V3(vx.color[0], vx.color[1], vx.color[2]);
+        }
         vec3 on = normalize(n[0] * (1.0f - h.u - h.v) + n[1] * h.u + n[2] * h.v);
+        vec3 vcolor = col[0] * (1.0f - h.u - h.v) + col[1] * h.u + col[2] * h.v; // the `color` varying of GBuffer.vert
         const mat3& W = s.worldToObject[h.instance];
         vec3 normal = normalize(V3(dot(on, W[0]), dot(on, W[1]), dot(on, W[2])));
         pd[0] = position.x; pd[1] = position.y; pd[2] = position.z; pd[3] = length(position - V3(cam.origin[0], cam.origin[1], cam.origin[2]));
-        nm[0] = normal.x; nm[1] = normal.y; nm[2] = normal.z; nm[3] = s.materials[oe.materialIndex].metallicFactor;
+        const vkx_material& mat = s.materials[oe.materialIndex];
+        nm[0] = normal.x; nm[1] = normal.y; nm[2] = normal.z; nm[3] = mat.metallicFactor;
+        // GBuffer.frag:35,52-53,59,66-67 (untextured): albedo = color * baseColorFactor
+        ar[0] = vcolor.x * mat.baseColorFactor[0]; ar[1] = vcolor.y * mat.baseColorFactor[1]; ar[2] = vcolor.z * mat.baseColorFactor[2]; ar[3] = mat.roughnessFactor;
+        em[0] = mat.emissiveFactor[0]; em[1] = mat.emissiveFactor[1]; em[2] = mat.emissiveFactor[2]; em[3] = 1.0f;
     }
 }
 
@@ -211,6 +222,52 @@ void frame(const oddgi::Scene& s, State& st, const vkx_camera& cur, const vkx_ca
     }
     filterPass<0>(st, st.raw, st.filteredX, nullptr, nullptr);
     filterPass<1>(st, st.filteredX, st.final_, &prev, &st.previous);
+}
+
+// FinalGather.frag:38-77. fragPosition of FullScreenQuad.vert interpolates to the pixel centre ((x + 0.5) / W, (y + 0.5) / H).
+// inverse() is the cofactor expansion above (GLSL leaves its precision to the implementation).
+void finalGather(const oddgi::Scene& s, const oddgi::Probes& probes, State& st, const vkx_camera& cam, const vkx_light& light, const float* reflection) {
+    (void)s;
+    const int W = int(st.w), H = int(st.h);
+    mat4 iv = inverse4(mat4_from(cam.view)), ip = inverse4(mat4_from(cam.proj));
+    vec3 origin = xyz(iv * V4(0, 0, 0, 1));
+    vec3 Ldir = V3(light.direction[0], light.direction[1], light.direction[2]);
+    vec3 Lcol = V3(light.color[0], light.color[1], light.color[2]);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t y = 0; y < H; ++y) for (int x = 0; x < W; ++x) {
+        size_t pi_ = (size_t(y) * st.w + size_t(x)) * 4;
+        vec3 color = V3(0, 0, 0);
+        vec2 fragPosition = V2((float(x) + 0.5f) / float(W), (float(y) + 0.5f) / float(H));
+        const float* pd = &st.positionDepth[pi_]; const float* nm = &st.normalMetalness[pi_];
+        const float* ar = &st.albedoRoughness[pi_]; const float* em = &st.emissive[pi_];
+        vec3 position = V3(pd[0], pd[1], pd[2]);
+        float depth = pd[3];
+        if (depth <= 0.0f) {
+            vec2 d = 2.0f * fragPosition - 1.0f;
+            vec4 t = ip * V4(d.x, d.y, 0.0f, 1.0f);
+            vec4 dir4 = iv * V4(normalize(xyz(t)), 0.0f);
+            color = oddgi::sky(origin, xyz(dir4), Ldir, Lcol, 1.0f, true);
+        } else {
+            vec3 normal = normalize(V3(nm[0], nm[1], nm[2]));
+            float metalness = nm[3];
+            vec4 albedo = V4(ar[0], ar[1], ar[2], 1.0f);
+            float roughness = ar[3];
+            vec3 refl = reflection ? V3(reflection[pi_], reflection[pi_ + 1], reflection[pi_ + 2]) : V3(0, 0, 0);
+            vec3 view = normalize(origin - position);
+            float direct = st.final_[pi_]; // subpassLoad(inputDirectLight).r
+            color += direct * xyz(oddgi::pbrMetallicRoughness(normal, view, Lcol, Ldir, albedo, metalness, roughness));
+            vec3 f0 = V3(0.004f, 0.004f, 0.004f);
+            vec3 diffuseColor = xyz(albedo) * (V3(1, 1, 1) - f0);
+            diffuseColor = diffuseColor * (1.0f - metalness);
+            vec3 specularColor = mix(f0, xyz(albedo), metalness);
+            color += specularColor * refl;
+            vec3 indirectLight = oddgi::sampleProbes(probes, position, normal, view);
+            color += indirectLight * diffuseColor;
+            color += V3(em[0], em[1], em[2]);
+        }
+        float* o = &st.gathered[pi_];
+        o[0] = color.x; o[1] = color.y; o[2] = color.z; o[3] = 1.0f;
+    }
 }
 
 } // namespace oshadow

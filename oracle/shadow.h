@@ -9,6 +9,8 @@ namespace oshadow {
 struct State {
     uint32_t w = 0, h = 0;
     std::vector<float> positionDepth, normalMetalness; // RGBA32F G-buffer
+    std::vector<float> albedoRoughness, emissive;      // RGBA32F G-buffer targets only the composite reads (GBuffer.frag:66-67)
+    std::vector<float> gathered;                       // RGBA32F output of finalGather
     std::vector<float> raw, filteredX, final_, previous; // RGBA32F
     std::vector<float> dirs;   // jittered light direction per pixel (debug / parity)
     std::vector<uint8_t> mask; // 0 not traced, 1 lit, 2 shadowed
@@ -20,5 +22,9 @@ void init(State& st, uint32_t w, uint32_t h);
 void gbufferGenerate(const oddgi::Scene& s, State& st, const vkx_camera& cam);
 // dirOverride (optional, [h][w][3]): use these jittered directions instead of computing them (bit-exact mask tests).
 void frame(const oddgi::Scene& s, State& st, const vkx_camera& cur, const vkx_camera& prev, const vkx_light& light, const float* dirOverride);
+
+// FinalGather.frag:38-77: sky on empty pixels, else direct * shadow + specular * reflection + sampleProbes * diffuse + emissive.
+// reflection: optional RGBA32F [h][w][4] (the reflection pass is out of scope; nullptr = black).
+void finalGather(const oddgi::Scene& s, const oddgi::Probes& probes, State& st, const vkx_camera& cam, const vkx_light& light, const float* reflection);
 
 } // namespace oshadow

@@ -175,3 +175,36 @@ def test_oracle_update_properties(oracle_lib, scene_getter):
     o.probes_update(grid, light, R)
     irr2, dep2, _, _ = o.probes_download()
     assert np.array_equal(irr, irr2) and np.array_equal(dep, dep2)
+
+
+def test_oracle_final_gather_properties(oracle_lib, scene_getter):
+    """FinalGather.frag restatement: with all probes off and an unlit shadow image a geometry pixel is emissive only; the
+    composite is linear in the reflection input with slope mix(0.004, albedo, metalness); sky pixels ignore every input."""
+    from vulkanexp_b200.pods import GridInfo, Light, make_camera
+
+    W, H = 96, 54
+    flat = scene_getter("court")
+    o = oracle_lib.Oracle(); o.scene_upload(flat); o.bvh_build()
+    grid = GridInfo.make(flat["bounds_min"], flat["bounds_max"], (4, 3, 4), 32)
+    o.probes_init(grid)  # state 0 everywhere: sampleProbes returns 0
+    o.shadow_init(W, H)
+    cam = make_camera((-5.0, 2.5, 4.5), (0.0, 8.0, 0.0), aspect=W / H, frame_index=0)
+    o.gbuffer_generate(cam)
+    pd, nm = o.gbuffer_download()
+    ar, em = o.gbuffer_download_material()
+    geo = pd[..., 3] > 0
+    assert 0.2 < geo.mean() < 1.0, "the view must contain both geometry and sky"
+    assert np.array_equal(em[geo][:, 3], np.ones(int(geo.sum()), dtype=np.float32)) and not em[~geo].any()
+    light = Light.default()
+    base, _ = o.final_gather(cam, light)
+    assert np.array_equal(base[geo][:, :3], em[geo][:, :3]), "no light, no probes: emissive only"
+    assert base[~geo][:, :3].min() >= 0.0 and base[~geo][:, :3].max() > 0.0, "sky pixels are lit by the atmosphere"
+    refl = np.full((H, W, 4), 0.5, dtype=np.float32)
+    withr, _ = o.final_gather(cam, light, refl)
+    assert np.array_equal(withr[~geo], base[~geo])
+    spec = 0.004 * (1.0 - nm[..., 3:4]) + ar[..., :3] * nm[..., 3:4]
+    assert np.allclose((withr - base)[geo][:, :3], 0.5 * spec[geo], rtol=1e-5, atol=1e-7)
+    # direct term: a fully lit shadow image adds the PBR direct lighting, never darkens
+    o.shadow_set_history(np.ones((H, W, 4), dtype=np.float32))
+    lit, _ = o.final_gather(cam, light)
+    assert (lit[geo][:, :3] >= base[geo][:, :3]).all() and lit[geo][:, :3].max() > base[geo][:, :3].max()

@@ -5,7 +5,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from vulkanexp_b200 import scene_format, synth
 from vulkanexp_b200._lib import Context
-from vulkanexp_b200.pods import Light, make_camera
+from vulkanexp_b200.host_logic import OrientationGenerator
+from vulkanexp_b200.pods import GridInfo, Light, make_camera
 
 W, H = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (3840, 2160)
 s = synth.make_cfg3(); flat = scene_format.flatten(s)
@@ -13,12 +14,20 @@ g = Context(0); g.scene_upload(flat); g.bvh_build()
 info = g.bvh_info()
 g.shadow_set_noise(synth.blue_noise_like(64, 64)); g.shadow_init(W, H)
 light = Light.default()
+# a lit irradiance volume for the composite (FinalGather): 32 x 8 x 32 probes x 256 rays, 6 updates
+grid = GridInfo.make(flat["bounds_min"], flat["bounds_max"], (32, 8, 32), 256, hysteresis=0.7)
+g.probes_init(grid); gen = OrientationGenerator(); g.probes_classify(gen.next())
+for _ in range(6):
+    g.probes_update(grid, light, gen.next())
 cams = [make_camera((-20.0 + 1.2 * f, 2.2, -18.0 + 0.9 * f), (0.0 + 0.5 * f, 1.5, 0.0), aspect=W / H, frame_index=f) for f in range(16)]
-prev = cams[0]; ms = []; gb = []
+prev = cams[0]; ms = []; gb = []; img = np.zeros((H, W, 4), dtype=np.float32)
 for f, cam in enumerate(cams):
     t0 = time.perf_counter(); g.gbuffer_generate(cam); gb.append((time.perf_counter() - t0) * 1e3)
     g.shadow_frame(cam, prev, light)
-    ms.append(g.shadow_timings()); prev = cam
+    t = g.shadow_timings()
+    g.final_gather(cam, light)
+    t["gather"] = g.final_gather_download(out=img)[1]
+    ms.append(t); prev = cam
 pd, _ = g.gbuffer_download()
 steady = ms[4:]
 avg = {k: float(np.mean([m[k] for m in steady])) for k in steady[0]}
@@ -26,4 +35,10 @@ px = W * H
 print(json.dumps({"metric": "sun_shadow_pass_ms", "value": avg["full"], "unit": "ms", "width": W, "height": H, "triangles": int(info.numTriangles), "stages_ms": avg,
                   "gbuffer_fixture_ms": float(np.mean(gb[4:])), "geometry_pixels": float((pd[..., 3] > 0).mean()),
                   "filter_bytes_per_px": 48 + 64, "filter_gbs": px * (48 + 64) / ((avg["filter_x"] + avg["filter_y"]) * 1e-3) / 1e9,
-                  "shadow_rays_per_s": px * float((pd[..., 3] > 0).mean()) / (avg["trace"] * 1e-3)}))
+                  "shadow_rays_per_s": px * float((pd[..., 3] > 0).mean()) / (avg["trace"] * 1e-3),
+                  "final_gather_ms": avg["gather"], "final_gather_bytes_per_px": 5 * 16 + 16, "final_gather_gbs": px * 96 / (avg["gather"] * 1e-3) / 1e9,
+                  "composite_mean_rgb": [float(v) for v in img[..., :3].mean(axis=(0, 1))]}))
+if len(sys.argv) > 3:  # optional: write the last composite as a PPM (Reinhard + gamma 2.2) for a look at the picture
+    rgb = img[..., :3] / (1.0 + img[..., :3]); rgb = (np.clip(rgb, 0, 1) ** (1 / 2.2) * 255 + 0.5).astype(np.uint8)
+    with open(sys.argv[3], "wb") as f:
+        f.write(b"P6 %d %d 255\n" % (W, H)); f.write(rgb.tobytes())

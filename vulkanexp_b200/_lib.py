@@ -224,6 +224,26 @@ class Context:
         self._check(self.l.vkx_gbuffer_download(self.h, _p(pd), _p(nm)))
         return pd, nm
 
+    def gbuffer_upload_material(self, ar, em):
+        ar = np.ascontiguousarray(ar, dtype=np.float32); em = np.ascontiguousarray(em, dtype=np.float32)
+        self._check(self.l.vkx_gbuffer_upload_material(self.h, _p(ar), _p(em)))
+
+    def gbuffer_download_material(self):
+        ar = np.zeros((self.sh, self.sw, 4), dtype=np.float32)
+        em = np.zeros((self.sh, self.sw, 4), dtype=np.float32)
+        self._check(self.l.vkx_gbuffer_download_material(self.h, _p(ar), _p(em)))
+        return ar, em
+
+    def final_gather(self, cam, light, reflection=None, sync=True):
+        r = np.ascontiguousarray(reflection, dtype=np.float32) if reflection is not None else None
+        self._check(self.l.vkx_final_gather(self.h, C.byref(cam), C.byref(light), _p(r) if r is not None else None, C.c_int(int(sync))))
+
+    def final_gather_download(self, out=None):
+        img = out if out is not None else np.zeros((self.sh, self.sw, 4), dtype=np.float32)
+        ms = C.c_float(0)
+        self._check(self.l.vkx_final_gather_download(self.h, _p(img), C.byref(ms)))
+        return img, float(ms.value)
+
     def shadow_frame(self, cur, prev, light, sync=True):
         self._check(self.l.vkx_shadow_frame(self.h, C.byref(cur), C.byref(prev), C.byref(light), C.c_int(int(sync))))
 

@@ -75,9 +75,10 @@ static void freeProbes(vkx_ctx* ctx) {
     ctx->probesReady = false;
 }
 static void freeShadow(vkx_ctx* ctx) {
-    void* ptrs[] = {ctx->dPosDepth, ctx->dNormalMetal, ctx->dShRaw, ctx->dShX, ctx->dShFinal[0], ctx->dShFinal[1], ctx->dShDirs, ctx->dShMask};
+    void* ptrs[] = {ctx->dPosDepth, ctx->dNormalMetal, ctx->dShRaw, ctx->dShX, ctx->dShFinal[0], ctx->dShFinal[1], ctx->dShDirs, ctx->dShMask, ctx->dAlbedoRough, ctx->dEmissive, ctx->dReflection, ctx->dGathered};
     for (void* p : ptrs) if (p) cudaFree(p);
     ctx->dPosDepth = ctx->dNormalMetal = ctx->dShRaw = ctx->dShX = ctx->dShFinal[0] = ctx->dShFinal[1] = ctx->dShDirs = nullptr; ctx->dShMask = nullptr;
+    ctx->dAlbedoRough = ctx->dEmissive = ctx->dReflection = ctx->dGathered = nullptr;
     ctx->shW = ctx->shH = 0;
 }
 

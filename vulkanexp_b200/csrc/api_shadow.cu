@@ -20,11 +20,12 @@ int vkx_shadow_set_noise(vkx_ctx* ctx, const float* rgba, uint32_t w, uint32_t h
 int vkx_shadow_init(vkx_ctx* ctx, uint32_t width, uint32_t height) {
     BIND(ctx);
     if (!width || !height) return vkx_fail(ctx, VKX_E_INVALID, "vkx_shadow_init: empty image");
-    void* old[] = {ctx->dPosDepth, ctx->dNormalMetal, ctx->dShRaw, ctx->dShX, ctx->dShFinal[0], ctx->dShFinal[1], ctx->dShDirs, ctx->dShMask};
+    void* old[] = {ctx->dPosDepth, ctx->dNormalMetal, ctx->dShRaw, ctx->dShX, ctx->dShFinal[0], ctx->dShFinal[1], ctx->dShDirs, ctx->dShMask, ctx->dAlbedoRough, ctx->dEmissive, ctx->dReflection, ctx->dGathered};
     for (void* p : old) if (p) cudaFree(p);
     ctx->dPosDepth = ctx->dNormalMetal = ctx->dShRaw = ctx->dShX = ctx->dShFinal[0] = ctx->dShFinal[1] = ctx->dShDirs = nullptr; ctx->dShMask = nullptr;
+    ctx->dAlbedoRough = ctx->dEmissive = ctx->dReflection = ctx->dGathered = nullptr;
     const size_t px = size_t(width) * height;
-    float4** imgs[] = {&ctx->dPosDepth, &ctx->dNormalMetal, &ctx->dShRaw, &ctx->dShX, &ctx->dShFinal[0], &ctx->dShFinal[1], &ctx->dShDirs};
+    float4** imgs[] = {&ctx->dPosDepth, &ctx->dNormalMetal, &ctx->dShRaw, &ctx->dShX, &ctx->dShFinal[0], &ctx->dShFinal[1], &ctx->dShDirs, &ctx->dAlbedoRough, &ctx->dEmissive, &ctx->dGathered};
     for (float4** p : imgs) { CUDA_TRY(ctx, cudaMalloc(p, px * 16)); CUDA_TRY(ctx, cudaMemsetAsync(*p, 0, px * 16, ctx->stream)); }
     CUDA_TRY(ctx, cudaMalloc(&ctx->dShMask, px)); CUDA_TRY(ctx, cudaMemsetAsync(ctx->dShMask, 0, px, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -58,6 +59,53 @@ int vkx_gbuffer_download(vkx_ctx* ctx, float* positionDepth, float* normalMetaln
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     if (positionDepth) CUDA_TRY(ctx, cudaMemcpy(positionDepth, ctx->dPosDepth, bytes, cudaMemcpyDeviceToHost));
     if (normalMetalness) CUDA_TRY(ctx, cudaMemcpy(normalMetalness, ctx->dNormalMetal, bytes, cudaMemcpyDeviceToHost));
+    return VKX_OK;
+}
+
+int vkx_gbuffer_upload_material(vkx_ctx* ctx, const float* albedoRoughness, const float* emissive) {
+    BIND(ctx);
+    if (!ctx->shW || !albedoRoughness || !emissive) return vkx_fail(ctx, VKX_E_INVALID, "vkx_gbuffer_upload_material: bad arguments");
+    const size_t bytes = size_t(ctx->shW) * ctx->shH * 16;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpy(ctx->dAlbedoRough, albedoRoughness, bytes, cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(ctx->dEmissive, emissive, bytes, cudaMemcpyHostToDevice));
+    return VKX_OK;
+}
+
+int vkx_gbuffer_download_material(vkx_ctx* ctx, float* albedoRoughness, float* emissive) {
+    BIND(ctx);
+    if (!ctx->shW) return vkx_fail(ctx, VKX_E_INVALID, "shadow images not initialised");
+    const size_t bytes = size_t(ctx->shW) * ctx->shH * 16;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (albedoRoughness) CUDA_TRY(ctx, cudaMemcpy(albedoRoughness, ctx->dAlbedoRough, bytes, cudaMemcpyDeviceToHost));
+    if (emissive) CUDA_TRY(ctx, cudaMemcpy(emissive, ctx->dEmissive, bytes, cudaMemcpyDeviceToHost));
+    return VKX_OK;
+}
+
+int vkx_final_gather(vkx_ctx* ctx, const vkx_camera* cam, const vkx_light* light, const float* reflection, int sync) {
+    BIND(ctx);
+    if (!cam || !light) return vkx_fail(ctx, VKX_E_INVALID, "vkx_final_gather: null argument");
+    if (!ctx->shW) return vkx_fail(ctx, VKX_E_INVALID, "vkx_final_gather: call vkx_shadow_init first");
+    if (!ctx->probeCount) return vkx_fail(ctx, VKX_E_INVALID, "vkx_final_gather: call vkx_probes_init first");
+    int rc = waitGather(ctx); // a sharded update may still be gathering the atlases this pass samples
+    if (rc != VKX_OK) return rc;
+    const size_t bytes = size_t(ctx->shW) * ctx->shH * 16;
+    if (reflection) {
+        if (!ctx->dReflection) CUDA_TRY(ctx, cudaMalloc(&ctx->dReflection, bytes));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dReflection, reflection, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    rc = finalGather(ctx, *cam, *light, reflection != nullptr);
+    if (rc != VKX_OK) return rc;
+    if (sync) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return VKX_OK;
+}
+
+int vkx_final_gather_download(vkx_ctx* ctx, float* rgba, float* ms) {
+    BIND(ctx);
+    if (!ctx->shW || !ctx->gev[0]) return vkx_fail(ctx, VKX_E_INVALID, "vkx_final_gather_download: nothing gathered yet");
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (rgba) CUDA_TRY(ctx, cudaMemcpy(rgba, ctx->dGathered, size_t(ctx->shW) * ctx->shH * 16, cudaMemcpyDeviceToHost));
+    if (ms) CUDA_TRY(ctx, cudaEventElapsedTime(ms, ctx->gev[0], ctx->gev[1]));
     return VKX_OK;
 }
 

@@ -111,6 +111,9 @@ struct vkx_ctx {
     int shCur = 0; // dShFinal[shCur] = last frame's filtered result
     float4* dShDirs = nullptr; uint8_t* dShMask = nullptr; // debug
     cudaEvent_t sev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // composite (FinalGather): the two G-buffer targets only it reads, optional reflection input, output
+    float4 *dAlbedoRough = nullptr, *dEmissive = nullptr, *dReflection = nullptr, *dGathered = nullptr;
+    cudaEvent_t gev[2] = {nullptr, nullptr};
 };
 
 int vkx_fail(vkx_ctx* ctx, int code, const char* fmt, ...);
@@ -144,6 +147,8 @@ int shadowGBuffer(vkx_ctx* ctx, const vkx_camera& cam);
 int shadowFrame(vkx_ctx* ctx, const vkx_camera& cur, const vkx_camera& prev, const vkx_light& light);
 
 DeviceScene deviceScene(const vkx_ctx* ctx);
+DeviceProbes deviceProbes(const vkx_ctx* ctx);
+int finalGather(vkx_ctx* ctx, const vkx_camera& cam, const vkx_light& light, bool haveReflection); // gather.cu
 
 // ---------------------------------------------------------------------------------------------------------------
 // device helpers

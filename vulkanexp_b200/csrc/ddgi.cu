@@ -360,7 +360,7 @@ DeviceScene deviceScene(const vkx_ctx* ctx) {
     return s;
 }
 
-static DeviceProbes deviceProbes(const vkx_ctx* ctx) {
+DeviceProbes deviceProbes(const vkx_ctx* ctx) {
     DeviceProbes p;
     p.grid = ctx->grid; p.irrW = ctx->irrW; p.irrH = ctx->irrH; p.depW = ctx->depW; p.depH = ctx->depH; p.probeCount = ctx->probeCount;
     p.irrSampled = ctx->dIrrSampled; p.depSampled = ctx->dDepSampled; p.stateSampled = ctx->dStateSampled;

@@ -264,6 +264,44 @@ __device__ inline void sampleProbes2(const DeviceProbes& p, const GridConsts& gc
     resultB = finishProbes(accB);
 }
 
+// Single look-up (FinalGather.frag:68): same per-probe sequence as one half of sampleProbePair.
+__device__ inline v3 sampleProbes1(const DeviceProbes& p, const GridConsts& gc, v3 position, v3 normal, v3 toCamera) {
+    const vkx_grid_info& grid = p.grid;
+    const v3 gridCoords = mk3(__fdiv_rn(__fsub_rn(position.x, gc.extentMin.x), gc.acell.x), __fdiv_rn(__fsub_rn(position.y, gc.extentMin.y), gc.acell.y), __fdiv_rn(__fsub_rn(position.z, gc.extentMin.z), gc.acell.z));
+    if (gridCoords.x < 0.0f || gridCoords.y < 0.0f || gridCoords.z < 0.0f) return mk3(0.0f);
+    const v3 biased = position + (normal + toCamera) * grid.shadowBias;
+    const int fx = int(gridCoords.x), fy = int(gridCoords.y), fz = int(gridCoords.z);
+    v3 alpha = (position - (mk3(float(fx), float(fy), float(fz)) * gc.cell + gc.extentMin)) / gc.acell;
+    alpha = mk3(clampS(alpha.x, 0.0f, 1.0f), clampS(alpha.y, 0.0f, 1.0f), clampS(alpha.z, 0.0f, 1.0f));
+    const float2 oct = sphereToOctUVxy(normal);
+    ProbeAccum acc;
+    acc.finalColor = acc.fallbackColor = mk3(0.0f); acc.totalWeight = acc.totalFallbackWeight = 0.0f;
+    const uint32_t* D = p.depSampled; const uint32_t* C = p.irrSampled;
+#pragma unroll 1
+    for (int i = 0; i < 8; ++i) {
+        const int ox = i & 1, oy = (i >> 1) & 1, oz = (i >> 2) & 1;
+        const int cx = fx + ox, cy = fy + oy, cz = fz + oz;
+        if (cx > gc.rx - 1 || cy > gc.ry - 1 || cz > gc.rz - 1) continue;
+        const uint32_t li = uint32_t(cx + gc.rx * cy + gc.rx * gc.ry * cz);
+        if (__ldg(p.stateSampled + li) == 0u) continue;
+        const v3 probePosition = mk3(float(cx), float(cy), float(cz)) * gc.cell + gc.extentMin;
+        const v3 directionToProbe = norm3(probePosition - position);
+        const v3 trilinear = mix3(1.0f - alpha, alpha, mk3(float(ox), float(oy), float(oz)));
+        const float tri = trilinear.x * trilinear.y * trilinear.z + 0.001f;
+        const int tile = cy * gc.rx + cx;
+        const v3 b = probePosition - biased;
+        const float len = sqrtf(dot3(b, b));
+        const float2 octD = sphereToOctUVxy(-(b * (1.0f / len)));
+        const float cu0 = float(8 * tile + 1) * 0.125f, cv0 = float(8 * cz + 1) * 0.125f, du0 = float(16 * tile + 1) * 0.0625f, dv0 = float(16 * cz + 1) * 0.0625f;
+        const BilinearTaps tc = makeTaps(divScale(cu0 + gc.cscale * oct.x, gc.usx, gc.invUsx, gc.pow2x), divScale(cv0 + gc.cscale * oct.y, gc.usy, gc.invUsy, gc.pow2y), p.irrW, p.irrH);
+        const BilinearTaps td = makeTaps(divScale(du0 + gc.dscale * octD.x, gc.usx, gc.invUsx, gc.pow2x), divScale(dv0 + gc.dscale * octD.y, gc.usy, gc.invUsy, gc.pow2y), p.depW, p.depH);
+        const uint32_t d0 = __ldg(D + td.o00), d1 = __ldg(D + td.o10), d2 = __ldg(D + td.o01), d3 = __ldg(D + td.o11);
+        const uint32_t c0 = __ldg(C + tc.o00), c1 = __ldg(C + tc.o10), c2 = __ldg(C + tc.o01), c3 = __ldg(C + tc.o11);
+        accumulateProbe(acc, normal, directionToProbe, tri, len, lerpDepth(td, d0, d1, d2, d3), lerpIrradiance(tc, c0, c1, c2, c3));
+    }
+    return finishProbes(acc);
+}
+
 // ---- sky.glsl. The 64-step integral dominates missed rays; inside the loop this uses explicit FMAs, ex2.approx and
 // approximate reciprocal/rsqrt (the function is smooth: measured deviation from the oracle ~1e-6 relative, tolerance 1e-3).
 __device__ __forceinline__ float fastExp(float x) { return __expf(x); }

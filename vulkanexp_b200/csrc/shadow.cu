@@ -22,7 +22,7 @@ __device__ __forceinline__ float4 mulM4(const M4& M, float x, float y, float z, 
 
 // G-buffer fixture: primary rays set up as raygen.rgen:27-33, outputs laid out as GBuffer.frag:64-68.
 __global__ void __launch_bounds__(128) k_gbuffer(DeviceScene sc, M4 invView, M4 invProj, float3 camOrigin, uint32_t W, uint32_t H,
-                                                 float4* __restrict__ posDepth, float4* __restrict__ normalMetal) {
+                                                 float4* __restrict__ posDepth, float4* __restrict__ normalMetal, float4* __restrict__ albedoRough, float4* __restrict__ emissive) {
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= W || y >= H) return;
     const size_t pix = size_t(y) * W + x;
@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(128) k_gbuffer(DeviceScene sc, M4 invView, M4 
     HitRec h;
     if (!traverse<false>(sc.nodes, sc.tris, r, 0.001f, 100000.0f, 0xFFu, h)) {
         posDepth[pix] = make_float4(0.f, 0.f, 0.f, 0.f); normalMetal[pix] = make_float4(0.f, 0.f, 0.f, 0.f);
+        albedoRough[pix] = make_float4(0.f, 0.f, 0.f, 0.f); emissive[pix] = make_float4(0.f, 0.f, 0.f, 0.f);
         return;
     }
     const v3 origin = mk3(o4.x, o4.y, o4.z), dir = mk3(d4.x, d4.y, d4.z);
@@ -43,13 +44,20 @@ __global__ void __launch_bounds__(128) k_gbuffer(DeviceScene sc, M4 invView, M4 
     const uint32_t meshEntry = sc.instances[h.inst].meshEntry;
     const vkx_offset_entry oe = sc.offsets[meshEntry];
     const uint32_t prim = h.prim & 0x7FFFFFFFu;
-    v3 n[3];
-    for (int c = 0; c < 3; ++c) { const float* nn = sc.vertices[oe.vertexOffset + sc.indices[oe.indexOffset + 3 * prim + c]].normal; n[c] = mk3(nn[0], nn[1], nn[2]); }
+    v3 n[3], col[3];
+    for (int c = 0; c < 3; ++c) {
+        const vkx_vertex& vx = sc.vertices[oe.vertexOffset + sc.indices[oe.indexOffset + 3 * prim + c]];
+        n[c] = mk3(vx.normal[0], vx.normal[1], vx.normal[2]); col[c] = mk3(vx.color[0], vx.color[1], vx.color[2]);
+    }
     const v3 on = norm3(n[0] * (1.0f - h.u - h.v) + n[1] * h.u + n[2] * h.v);
+    const v3 vcolor = col[0] * (1.0f - h.u - h.v) + col[1] * h.u + col[2] * h.v; // the `color` varying of GBuffer.vert
     const float* Wm = sc.worldToObject + size_t(h.inst) * 9;
     const v3 normal = norm3(mk3(dot3(on, mk3(Wm[0], Wm[3], Wm[6])), dot3(on, mk3(Wm[1], Wm[4], Wm[7])), dot3(on, mk3(Wm[2], Wm[5], Wm[8]))));
     posDepth[pix] = make_float4(position.x, position.y, position.z, len3(position - mk3(camOrigin.x, camOrigin.y, camOrigin.z)));
-    normalMetal[pix] = make_float4(normal.x, normal.y, normal.z, sc.materials[oe.materialIndex].metallicFactor);
+    const vkx_material& mat = sc.materials[oe.materialIndex];
+    normalMetal[pix] = make_float4(normal.x, normal.y, normal.z, mat.metallicFactor);
+    albedoRough[pix] = make_float4(vcolor.x * mat.baseColorFactor[0], vcolor.y * mat.baseColorFactor[1], vcolor.z * mat.baseColorFactor[2], mat.roughnessFactor); // GBuffer.frag:35,66
+    emissive[pix] = make_float4(mat.emissiveFactor[0], mat.emissiveFactor[1], mat.emissiveFactor[2], 1.0f);                                                       // GBuffer.frag:59,67
 }
 
 __device__ __forceinline__ v3 rotateAxis(v3 p, v3 axis, float angle) { // common.glsl:6-8
@@ -262,7 +270,7 @@ int shadowGBuffer(vkx_ctx* ctx, const vkx_camera& cam) {
     M4 iv, ip;
     inverse4(cam.view, iv.m); inverse4(cam.proj, ip.m);
     dim3 grid(divUp(ctx->shW, 128), ctx->shH);
-    k_gbuffer<<<grid, 128, 0, ctx->stream>>>(deviceScene(ctx), iv, ip, make_float3(cam.origin[0], cam.origin[1], cam.origin[2]), ctx->shW, ctx->shH, ctx->dPosDepth, ctx->dNormalMetal);
+    k_gbuffer<<<grid, 128, 0, ctx->stream>>>(deviceScene(ctx), iv, ip, make_float3(cam.origin[0], cam.origin[1], cam.origin[2]), ctx->shW, ctx->shH, ctx->dPosDepth, ctx->dNormalMetal, ctx->dAlbedoRough, ctx->dEmissive);
     LAUNCH_CHECK(ctx);
     return VKX_OK;
 }
