@@ -179,6 +179,17 @@ int vkx_probes_download_async(vkx_ctx* ctx, uint32_t* irradiance, uint32_t* dept
 /* Same for the z-slices [z0, z1) only (the contiguous rows one rank of a sharded run owns); pointers address the first copied row. */
 int vkx_probes_download_slab_async(vkx_ctx* ctx, uint32_t z0, uint32_t z1, uint32_t* irradiance, uint32_t* depth, uint32_t* state);
 int vkx_probes_download_wait(vkx_ctx* ctx);
+/* On-device IrradianceProbes::selectProbesToUpdate (src/IrradianceProbes.cpp:396-424): the round-robin scan over the probe
+ * states runs as a stream compaction on the GPU, so a frame neither reads the P state words back nor uploads a list; only the
+ * list length returns to the host (the hysteresis ramp of update() needs it, :462-476). probesPerUpdate = the reference's
+ * ProbesPerUpdate (0 = no limit). The list is identical to vkx_host_select_probes on the same states and counters.
+ * vkx_probes_update_scheduled consumes the list of the preceding vkx_probes_schedule (one schedule per update). */
+int vkx_probes_schedule(vkx_ctx* ctx, uint32_t probesPerUpdate, uint32_t* count);
+int vkx_probes_update_scheduled(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx_light* light, const float orientation[16], int sync);
+/* The scheduler's two counters {s_LoopIndex, _lastUpdateOffset} (both statics/members of the reference): set (or NULL), get (or NULL). */
+int vkx_probes_scheduler_state(vkx_ctx* ctx, const uint32_t set[2], uint32_t get[2]);
+/* The list the last vkx_probes_schedule produced (parity / debugging). indices may be NULL to query the count only. */
+int vkx_probes_scheduled_list(vkx_ctx* ctx, uint32_t* indices, uint32_t capacity, uint32_t* count);
 /* Checkpoint/resume of GI state. NULL skips an array. */
 int vkx_probes_upload(vkx_ctx* ctx, const uint32_t* irradiance, const uint32_t* depth, const uint32_t* state);
 /* Enables the parity side buffers (hit records, shadow flags, unpacked blend results) and forces single-chunk updates. */

@@ -57,3 +57,17 @@ def test_facade_equals_c_abi(tmp_path):
     assert np.array_equal(raw[:a], irr.reshape(-1)), "irradiance atlas differs between facade and C ABI"
     assert np.array_equal(raw[a:b], dep.reshape(-1)), "depth atlas differs"
     assert np.array_equal(raw[b:], st), "probe states differ"
+
+
+def test_facade_device_scheduler_equals_host_scheduler(tmp_path):
+    """IrradianceProbes::DeviceScheduler (vkx_probes_schedule) must not change a single bit of the result."""
+    s = synth.make_open_court()
+    path = os.path.join(tmp_path, "court.scene")
+    scene_format.write_scene(path, s)
+    outs = []
+    for mode in ("host", "device"):
+        out = os.path.join(tmp_path, mode + ".bin")
+        r = subprocess.run([os.path.join(ROOT, "vulkanexp_b200", "vkx_facade_demo"), path, "7", "5", "6", "48", "16", out, "60", mode], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        outs.append(np.fromfile(out, dtype=np.uint32))
+    assert outs[0].size and np.array_equal(outs[0], outs[1])

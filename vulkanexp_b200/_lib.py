@@ -156,6 +156,30 @@ class Context:
     def probes_download_wait(self):
         self._check(self.l.vkx_probes_download_wait(self.h))
 
+    def probes_schedule(self, probes_per_update=0):
+        n = C.c_uint32(0)
+        self._check(self.l.vkx_probes_schedule(self.h, C.c_uint32(probes_per_update), C.byref(n)))
+        return int(n.value)
+
+    def probes_scheduled_list(self):
+        n = C.c_uint32(0)
+        self._check(self.l.vkx_probes_scheduled_list(self.h, None, C.c_uint32(0), C.byref(n)))
+        out = np.zeros(int(n.value), dtype=np.uint32)
+        if n.value:
+            self._check(self.l.vkx_probes_scheduled_list(self.h, _p(out), C.c_uint32(len(out)), C.byref(n)))
+        return out
+
+    def probes_update_scheduled(self, grid, light, R, sync=True):
+        R = np.ascontiguousarray(R, dtype=np.float32)
+        self.grid = grid
+        self._check(self.l.vkx_probes_update_scheduled(self.h, C.byref(grid), C.byref(light), _p(R), C.c_int(int(sync))))
+
+    def probes_scheduler_state(self, set=None):
+        get = (C.c_uint32 * 2)()
+        st = (C.c_uint32 * 2)(*set) if set is not None else None
+        self._check(self.l.vkx_probes_scheduler_state(self.h, st, get))
+        return int(get[0]), int(get[1])
+
     def probes_upload(self, irr=None, dep=None, state=None):
         a = [np.ascontiguousarray(x, dtype=np.uint32) if x is not None else None for x in (irr, dep, state)]
         self._check(self.l.vkx_probes_upload(self.h, _p(a[0]), _p(a[1]), _p(a[2])))

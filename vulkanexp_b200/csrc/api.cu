@@ -72,6 +72,11 @@ static void freeProbes(vkx_ctx* ctx) {
     ctx->dDirs = nullptr; ctx->dRays = nullptr; ctx->dHits = nullptr; ctx->dShadowQueue = nullptr; ctx->dQueueCount = nullptr; ctx->dShadowFlags = nullptr;
     ctx->dIrrUnpacked = ctx->dDepUnpacked = nullptr; ctx->dMissQueue = ctx->dFrontQueue = ctx->dFrontKeys = ctx->dFrontKeysOut = ctx->dFrontQueueSorted = nullptr; ctx->dSortTemp = nullptr; ctx->sortTempBytes = 0;
     if (ctx->hListStage) { cudaFreeHost(ctx->hListStage); ctx->hListStage = nullptr; }
+    void* sched[] = {ctx->dSchedFlags, ctx->dSchedPos, ctx->dSchedSlotOf, ctx->dSchedResult, ctx->dSchedTemp};
+    for (void* p : sched) if (p) cudaFree(p);
+    if (ctx->hSchedResult) cudaFreeHost(ctx->hSchedResult);
+    ctx->dSchedFlags = ctx->dSchedPos = ctx->dSchedSlotOf = ctx->dSchedResult = ctx->hSchedResult = nullptr; ctx->dSchedTemp = nullptr; ctx->schedTempBytes = 0;
+    ctx->schedLoopIndex = ctx->schedOffset = ctx->schedCount = 0; ctx->schedValid = false;
     ctx->probesReady = false;
 }
 static void freeShadow(vkx_ctx* ctx) {
@@ -401,6 +406,52 @@ int vkx_probes_update(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx_light* 
     const double t3 = now();
     if (traceHost) fprintf(stderr, "[vkx host] inputs %.3f ms, list %.3f ms, enqueue %.3f ms\n", t1 - t0, t2 - t1, t3 - t2);
     if (ctx->copyPending) { CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evCopyDone, 0)); ctx->copyPending = false; } // a queued read-back still reads the sampled atlases
+    TRY(ddgiPublish(ctx, count));
+    if (ctx->evPublished) CUDA_TRY(ctx, cudaEventRecord(ctx->evPublished, ctx->stream));
+    ctx->shardedLast = false;
+    if (sync) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return VKX_OK;
+}
+
+int vkx_probes_schedule(vkx_ctx* ctx, uint32_t probesPerUpdate, uint32_t* count) {
+    BIND(ctx);
+    if (!ctx->probesReady) return vkx_fail(ctx, VKX_E_INVALID, "vkx_probes_schedule: probes not ready");
+    TRY(waitGather(ctx)); // the states of a sharded update must have landed
+    TRY(scheduleProbes(ctx, probesPerUpdate, count));
+    ctx->schedValid = true; ctx->shardOrderReady = false;
+    return VKX_OK;
+}
+
+int vkx_probes_scheduler_state(vkx_ctx* ctx, const uint32_t* set, uint32_t* get) {
+    if (!ctx) return VKX_E_INVALID;
+    if (set) { if (ctx->probeCount && set[1] >= ctx->probeCount) return vkx_fail(ctx, VKX_E_INVALID, "lastUpdateOffset out of range"); ctx->schedLoopIndex = set[0]; ctx->schedOffset = set[1]; ctx->schedValid = false; }
+    if (get) { get[0] = ctx->schedLoopIndex; get[1] = ctx->schedOffset; }
+    return VKX_OK;
+}
+
+int vkx_probes_scheduled_list(vkx_ctx* ctx, uint32_t* indices, uint32_t capacity, uint32_t* count) {
+    BIND(ctx);
+    if (!ctx->schedValid) return vkx_fail(ctx, VKX_E_INVALID, "vkx_probes_scheduled_list: call vkx_probes_schedule first");
+    if (count) *count = ctx->schedCount;
+    if (indices) {
+        if (capacity < ctx->schedCount) return vkx_fail(ctx, VKX_E_INVALID, "list capacity %u < %u", capacity, ctx->schedCount);
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->schedCount) CUDA_TRY(ctx, cudaMemcpy(indices, ctx->dIndicesList, size_t(ctx->schedCount) * 4, cudaMemcpyDeviceToHost));
+    }
+    return VKX_OK;
+}
+
+int vkx_probes_update_scheduled(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx_light* light, const float orientation[16], int sync) {
+    BIND(ctx);
+    if (!ctx->probesReady || !ctx->bvhBuilt) return vkx_fail(ctx, VKX_E_INVALID, "vkx_probes_update_scheduled: probes or BVH not ready");
+    if (!light || !orientation) return vkx_fail(ctx, VKX_E_INVALID, "null light/orientation");
+    if (!ctx->schedValid) return vkx_fail(ctx, VKX_E_INVALID, "vkx_probes_update_scheduled: call vkx_probes_schedule first (one schedule per update)");
+    ctx->schedValid = false; // the list is consumed: publish changes the states the next schedule reads
+    TRY(uploadFrameInputs(ctx, grid, orientation));
+    const uint32_t count = ctx->schedCount;
+    if (count == 0) return VKX_OK;
+    TRY(ddgiUpdate(ctx, *light, nullptr, count, 0, false));
+    if (ctx->copyPending) { CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evCopyDone, 0)); ctx->copyPending = false; }
     TRY(ddgiPublish(ctx, count));
     if (ctx->evPublished) CUDA_TRY(ctx, cudaEventRecord(ctx->evPublished, ctx->stream));
     ctx->shardedLast = false;

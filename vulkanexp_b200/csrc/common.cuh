@@ -98,6 +98,10 @@ struct vkx_ctx {
     // asynchronous read-back (vkx_probes_download_async)
     cudaStream_t copyStream = nullptr; cudaEvent_t evPublished = nullptr, evCopyDone = nullptr; bool copyPending = false;
 
+    // on-device scheduler (schedule.cu); the two counters are the reference's s_LoopIndex / _lastUpdateOffset
+    uint32_t *dSchedFlags = nullptr, *dSchedPos = nullptr, *dSchedSlotOf = nullptr, *dSchedResult = nullptr, *hSchedResult = nullptr; void* dSchedTemp = nullptr; size_t schedTempBytes = 0;
+    uint32_t schedLoopIndex = 0, schedOffset = 0, schedCount = 0; bool schedValid = false;
+
     // multi-GPU
     ncclComm* comm = nullptr; int rank = 0, nranks = 1;
     cudaStream_t commStream = nullptr; cudaEvent_t commEvent = nullptr, gatherDone = nullptr; bool gatherPending = false;
@@ -148,6 +152,7 @@ int shadowFrame(vkx_ctx* ctx, const vkx_camera& cur, const vkx_camera& prev, con
 
 DeviceScene deviceScene(const vkx_ctx* ctx);
 DeviceProbes deviceProbes(const vkx_ctx* ctx);
+int scheduleProbes(vkx_ctx* ctx, uint32_t probesPerUpdate, uint32_t* countOut); // schedule.cu
 int finalGather(vkx_ctx* ctx, const vkx_camera& cam, const vkx_light& light, bool haveReflection); // gather.cu
 
 // ---------------------------------------------------------------------------------------------------------------

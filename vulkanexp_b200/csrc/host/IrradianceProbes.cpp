@@ -32,7 +32,21 @@ void IrradianceProbes::update() { // reference src/IrradianceProbes.cpp:426-594
     vkx_ctx* ctx = _device->ctx();
     check(ctx, vkx_sync(ctx)); // vkWaitForFences
     std::vector<uint32_t> toUpdate;
-    const uint32_t probeCount = selectProbesToUpdate(toUpdate);
+    uint32_t probeCount = 0;
+    if (DeviceScheduler) {
+        if (!_deviceSchedulerSeeded) { // hand the host counters over once, so the switch can be flipped mid-run
+            const uint32_t st[2] = {_loopIndex, _lastUpdateOffset};
+            check(ctx, vkx_probes_scheduler_state(ctx, st, nullptr));
+            _deviceSchedulerSeeded = true;
+        }
+        check(ctx, vkx_probes_schedule(ctx, ProbesPerUpdate, &probeCount));
+        uint32_t st[2];
+        check(ctx, vkx_probes_scheduler_state(ctx, nullptr, st));
+        _loopIndex = st[0]; _lastUpdateOffset = st[1];
+    } else {
+        _deviceSchedulerSeeded = false;
+        probeCount = selectProbesToUpdate(toUpdate);
+    }
     if (_haveTimings) { // the five timestamp differences of the previous update (:441-452)
         float ms[5];
         check(ctx, vkx_probes_timings(ctx, ms));
@@ -60,7 +74,8 @@ void IrradianceProbes::update() { // reference src/IrradianceProbes.cpp:426-594
     // updateUniforms, but raysPerProbe also sizes the dispatch); keep the device copy's hysteresis lag, refresh the rest.
     GridInfo g = _deviceGrid;
     g.raysPerProbe = GridParameters.raysPerProbe;
-    check(ctx, vkx_probes_update(ctx, &g, &light, orientation, toUpdate.data(), probeCount, 0));
+    if (DeviceScheduler) check(ctx, vkx_probes_update_scheduled(ctx, &g, &light, orientation, 0));
+    else check(ctx, vkx_probes_update(ctx, &g, &light, orientation, toUpdate.data(), probeCount, 0));
     _haveTimings = true;
 }
 

@@ -38,6 +38,9 @@ class IrradianceProbes {
 
     static const uint32_t MaxRaysPerProbe = VKX_MAX_RAYS_PER_PROBE;
     uint32_t ProbesPerUpdate = 0;
+    // Not in the reference: run selectProbesToUpdate on the device (vkx_probes_schedule) instead of reading the states back.
+    // Same lists, same counters; only the list length returns to the host.
+    bool DeviceScheduler = false;
     float TargetHysteresis = 0.98f;
     using GridInfo = vkx_grid_info;
     GridInfo GridParameters{{0, 0, 0}, 12.0f, {0, 0, 0}, 0.0f, {32, 16, 32}, 192, 8, 16, 0.3f, 0};
@@ -57,6 +60,7 @@ class IrradianceProbes {
     GridInfo _deviceGrid{};
     std::vector<uint32_t> _probesState;
     uint32_t _lastUpdateOffset = 0, _loopIndex = 0, _updatedProbes = 0, _rngState = 1, _lastCount = 0;
+    bool _deviceSchedulerSeeded = false;
     bool _haveTimings = false;
     RollingBuffer _computeTimes, _traceTimes, _updateTimes, _borderCopyTimes, _copyTimes;
 };

@@ -1,12 +1,14 @@
 // Drives the C++ facade the way Editor::run / initVulkan / mainLoop drive the reference classes:
-//   vkx_facade_demo <scene.scene> <rx> <ry> <rz> <raysPerProbe> <frames> <out.bin>
+//   vkx_facade_demo <scene.scene> <rx> <ry> <rz> <raysPerProbe> <frames> <out.bin> [probesPerUpdate [device]]
+// (`device` selects the on-device scheduler instead of the state read-back + host loop of the reference)
 // Writes irradiance, depth and state arrays (u32) to out.bin so tests can compare them with the C-ABI path.
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include "IrradianceProbes.hpp"
 
 int main(int argc, char** argv) {
-    if (argc < 8) { std::fprintf(stderr, "usage: %s scene rx ry rz rays frames out.bin\n", argv[0]); return 2; }
+    if (argc < 8) { std::fprintf(stderr, "usage: %s scene rx ry rz rays frames out.bin [probesPerUpdate [device]]\n", argv[0]); return 2; }
     try {
         vkx::Scene scene;
         if (!scene.load(argv[1])) return 1;
@@ -19,6 +21,8 @@ int main(int argc, char** argv) {
         vkx::IrradianceProbes probes;
         probes.GridParameters.resolution[0] = std::atoi(argv[2]); probes.GridParameters.resolution[1] = std::atoi(argv[3]); probes.GridParameters.resolution[2] = std::atoi(argv[4]);
         probes.GridParameters.raysPerProbe = unsigned(std::atoi(argv[5]));
+        if (argc > 8) probes.ProbesPerUpdate = unsigned(std::atoi(argv[8]));
+        if (argc > 9) probes.DeviceScheduler = std::string(argv[9]) == "device";
         probes.init(device, scene.getBounds().min, scene.getBounds().max);
         probes.createPipeline();
         probes.writeDescriptorSet(renderer, light);
