@@ -233,9 +233,24 @@ int vkx_gbuffer_download_material(vkx_ctx* ctx, float* albedoRoughness, float* e
 /* One frame of directLight.rgen -> directLightFilterX -> directLightFilterY (src/SwapchainManagement.cpp:409-438)
  * with the history ping-pong of src/Editor.cpp:287-316. */
 int vkx_shadow_frame(vkx_ctx* ctx, const vkx_camera* cur, const vkx_camera* prev, const vkx_light* light, int sync);
+/* Reflection pass: src/shaders/reflection.rgen:117-189 (one jittered reflection ray per pixel with roughness < 0.4
+ * or metalness > 0.01, shaded by the same closest-hit / miss / shadow shaders as the probe rays) -> reflectionFilterX -> reflectionFilterY
+ * with reprojected history (src/shaders/reflectionFilter.glsl, src/SwapchainManagement.cpp:401-455). Needs the G-buffer (including the
+ * albedoRoughness target), the noise slices of vkx_shadow_set_noise and an initialised irradiance volume. Static scenes: motion vectors 0. */
+int vkx_reflection_frame(vkx_ctx* ctx, const vkx_camera* cur, const vkx_camera* prev, const vkx_light* light, int sync);
+/* stage: 0 = raw 1-spp (rgb, roughness), 1 = after filter X, 2 = final (rgb, depth). RGBA32F. */
+int vkx_reflection_download(vkx_ctx* ctx, int stage, float* rgba);
+/* Parity side buffers of the last frame: jittered directions [h][w][4], closest hits (t = -1: none), mask bytes
+ * (0 no ray, 1 miss, 2 back face, 3 front face lit, 4 front face shadowed). hits / mask are only recorded while
+ * vkx_probes_debug is enabled. */
+int vkx_reflection_download_debug(vkx_ctx* ctx, float* dirs4, vkx_hit* hits, uint8_t* mask);
+int vkx_reflection_reset_history(vkx_ctx* ctx);
+/* ms[4] = full, trace + shade, filter X, filter Y of the last vkx_reflection_frame. */
+int vkx_reflection_timings(vkx_ctx* ctx, float ms[4]);
 /* Final composite of the frame, src/shaders/FinalGather.frag:38-77 (drawn by src/SwapchainManagement.cpp:466-474): sky on
  * empty pixels, else direct * (filtered shadow of the last vkx_shadow_frame) + specular * reflection + sampleProbes(sampled
- * atlases) * diffuse + emissive. reflection: optional host RGBA32F [h][w][4] image (the reflection pass is out of scope), NULL = black.
+ * atlases) * diffuse + emissive. reflection: a host RGBA32F [h][w][4] image, or NULL = the device-resident result of the last
+ * vkx_reflection_frame (black if none was run).
  * Output: linear RGBA32F, device resident; vkx_final_gather_download copies it out and returns the kernel time. */
 int vkx_final_gather(vkx_ctx* ctx, const vkx_camera* cam, const vkx_light* light, const float* reflection, int sync);
 int vkx_final_gather_download(vkx_ctx* ctx, float* rgba, float* ms);

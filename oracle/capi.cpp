@@ -173,6 +173,21 @@ int orc_gbuffer_download_material(orc_ctx* c, float* ar, float* em) {
     if (em) std::memcpy(em, c->shadow.emissive.data(), c->shadow.emissive.size() * 4);
     return 0;
 }
+int orc_reflection_frame(orc_ctx* c, const vkx_camera* cur, const vkx_camera* prev, const vkx_light* l, const float* dirOverride, double* seconds) {
+    auto t0 = std::chrono::steady_clock::now();
+    oshadow::reflectionFrame(c->scene, c->probes, c->shadow, *cur, *prev, *l, dirOverride);
+    if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return 0;
+}
+int orc_reflection_download(orc_ctx* c, int stage, float* rgba, float* dirs, vkx_hit* hits, uint8_t* mask) {
+    const std::vector<float>& src = stage == 0 ? c->shadow.reflRaw : stage == 1 ? c->shadow.reflX : c->shadow.reflFinal;
+    if (rgba) std::memcpy(rgba, src.data(), src.size() * 4);
+    if (dirs) std::memcpy(dirs, c->shadow.reflDirs.data(), c->shadow.reflDirs.size() * 4);
+    if (hits) std::memcpy(hits, c->shadow.reflHits.data(), c->shadow.reflHits.size() * sizeof(vkx_hit));
+    if (mask) std::memcpy(mask, c->shadow.reflMask.data(), c->shadow.reflMask.size());
+    return 0;
+}
+int orc_reflection_set_history(orc_ctx* c, const float* rgba) { std::memcpy(c->shadow.reflFinal.data(), rgba, c->shadow.reflFinal.size() * 4); return 0; }
 int orc_final_gather(orc_ctx* c, const vkx_camera* cam, const vkx_light* l, const float* reflection, double* seconds) {
     auto t0 = std::chrono::steady_clock::now();
     oshadow::finalGather(c->scene, c->probes, c->shadow, *cam, *l, reflection);

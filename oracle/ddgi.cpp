@@ -405,12 +405,12 @@ void classify(const Scene& s, Probes& p, const float orientation[16]) {
 
 // ---------------------------------------------------------------- traceProbes.rgen + closesthit.glsl + miss.rmiss
 static vec4 shadeRay(const Scene& s, const Probes& p, const vkx_light& light, vec3 origin, vec3 direction, float tmax,
-                     vkx_hit& hit, uint8_t& shadowFlag, obvh::Counters* ctr, obvh::Counters* sctr, uint64_t& front) {
-    const float tmin = 0.01f; // traceProbes.rgen:27
+                     vkx_hit& hit, uint8_t& shadowFlag, obvh::Counters* ctr, obvh::Counters* sctr, uint64_t& front,
+                     float tmin = 0.01f /* traceProbes.rgen:27 */, uint32_t cullMask = VKX_INSTANCE_STATIC | VKX_INSTANCE_DYNAMIC /* :43 */) {
     shadowFlag = 0;
     vec3 lightDir = V3(light.direction[0], light.direction[1], light.direction[2]);
     vec3 lightColor = V3(light.color[0], light.color[1], light.color[2]);
-    if (!obvh::traceClosest(s.bvh, &origin.x, &direction.x, tmin, tmax, VKX_INSTANCE_STATIC | VKX_INSTANCE_DYNAMIC, hit, ctr)) {
+    if (!obvh::traceClosest(s.bvh, &origin.x, &direction.x, tmin, tmax, cullMask, hit, ctr)) {
         vec3 c = sky(origin, direction, lightDir, lightColor, light.color[3], true); // miss.rmiss:19-22
         return V4(c, -1.0f);
     }
@@ -453,6 +453,14 @@ static vec4 shadeRay(const Scene& s, const Probes& p, const vkx_light& light, ve
         if (lightDir.y < 0.0f) color *= 1.0f - clampf(-lightDir.y, 0.0f, 0.1f) / 0.1f;
     }
     return V4(color, depth);
+}
+
+// One ray through closest-hit / miss shading with the caller's ray interval and cull mask (reflection.rgen:186 traces with
+// tmin 0.1, tmax 10000, mask 0xff and payload.recursionDepth = 1, i.e. the same shading as the probe rays).
+vec4 traceAndShade(const Scene& s, const Probes& p, const vkx_light& light, vec3 origin, vec3 direction, float tmin, float tmax, uint32_t cullMask,
+                   vkx_hit& hit, uint8_t& shadowFlag) {
+    uint64_t front = 0;
+    return shadeRay(s, p, light, origin, direction, tmax, hit, shadowFlag, nullptr, nullptr, front, tmin, cullMask);
 }
 
 // ---------------------------------------------------------------- probesUpdate.glsl + probesCopyBorders.comp

@@ -46,6 +46,9 @@ void classify(const Scene& s, Probes& p, const float orientation[16]);
 void update(const Scene& s, Probes& p, const vkx_grid_info& g, const vkx_light& light, const float orientation[16],
             const uint32_t* indices, uint32_t count, int threads);
 
+// closest-hit / miss shading of one ray (closesthit.glsl with recursionDepth >= 1, miss.rmiss); returns (rgb, depth) like the payload
+ovm::vec4 traceAndShade(const Scene& s, const Probes& p, const vkx_light& light, ovm::vec3 origin, ovm::vec3 direction, float tmin, float tmax, uint32_t cullMask,
+                        vkx_hit& hit, uint8_t& shadowFlag);
 ovm::vec3 sky(ovm::vec3 rayOrigin, ovm::vec3 rayDirection, ovm::vec3 sunPosition, ovm::vec3 sunColor, float sunBrightnessFactor, bool showSun);
 ovm::vec4 pbrMetallicRoughness(ovm::vec3 normal, ovm::vec3 view, ovm::vec3 lightColor, ovm::vec3 lightDirection, ovm::vec4 albedo, float metalness, float roughness);
 ovm::vec3 sampleProbes(const Probes& p, ovm::vec3 position, ovm::vec3 normal, ovm::vec3 toCamera);

@@ -175,6 +175,24 @@ class Oracle:
         self.l.orc_final_gather_download(self.h, _p(img))
         return img, sec.value
 
+    def reflection_frame(self, cur, prev, light, dir_override=None):
+        d = np.ascontiguousarray(dir_override, dtype=np.float32) if dir_override is not None else None
+        sec = C.c_double(0)
+        self.l.orc_reflection_frame(self.h, C.byref(cur), C.byref(prev), C.byref(light), _p(d), C.byref(sec))
+        return sec.value
+
+    def reflection_download(self, stage=2):
+        img = np.zeros((self.sh, self.sw, 4), dtype=np.float32)
+        dirs = np.zeros((self.sh, self.sw, 3), dtype=np.float32)
+        hits = np.zeros((self.sh, self.sw), dtype=HIT_DTYPE)
+        mask = np.zeros((self.sh, self.sw), dtype=np.uint8)
+        self.l.orc_reflection_download(self.h, C.c_int(stage), _p(img), _p(dirs), _p(hits), _p(mask))
+        return img, dirs, hits, mask
+
+    def reflection_set_history(self, img):
+        img = np.ascontiguousarray(img, dtype=np.float32)
+        self.l.orc_reflection_set_history(self.h, _p(img))
+
     def shadow_frame(self, cur, prev, light, dir_override=None):
         d = np.ascontiguousarray(dir_override, dtype=np.float32) if dir_override is not None else None
         sec = C.c_double(0)

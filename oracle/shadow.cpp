@@ -49,6 +49,8 @@ void init(State& st, uint32_t w, uint32_t h) {
     size_t n = size_t(w) * h * 4;
     st.positionDepth.assign(n, 0.0f); st.normalMetalness.assign(n, 0.0f);
     st.albedoRoughness.assign(n, 0.0f); st.emissive.assign(n, 0.0f); st.gathered.assign(n, 0.0f);
+    st.reflRaw.assign(n, 0.0f); st.reflX.assign(n, 0.0f); st.reflFinal.assign(n, 0.0f); st.reflPrevious.assign(n, 0.0f);
+    st.reflDirs.assign(size_t(w) * h * 3, 0.0f); st.reflHits.assign(size_t(w) * h, vkx_hit{}); st.reflMask.assign(size_t(w) * h, 0);
     st.raw.assign(n, 0.0f); st.filteredX.assign(n, 0.0f); st.final_.assign(n, 0.0f); st.previous.assign(n, 0.0f);
     st.dirs.assign(size_t(w) * h * 3, 0.0f); st.mask.assign(size_t(w) * h, 0);
 }
@@ -222,6 +224,113 @@ void frame(const oddgi::Scene& s, State& st, const vkx_camera& cur, const vkx_ca
     }
     filterPass<0>(st, st.raw, st.filteredX, nullptr, nullptr);
     filterPass<1>(st, st.filteredX, st.final_, &prev, &st.previous);
+}
+
+// ---------------------------------------------------------------- reflection pass
+static inline float rgaussian(float stdDev, float dist) { // reflectionFilter.glsl:37-39
+    return (1.0f / (std::sqrt(2.0f * 3.14159f) * stdDev)) * std::exp(-(dist * dist) / (2.0f * stdDev * stdDev));
+}
+
+// reflectionFilter.glsl:58-147. The shared-memory cache of the shader is a plain image load here (out of bounds = 0, A.5.4).
+template <int DIR>
+static void reflectionFilterPass(const State& st, const std::vector<float>& in, std::vector<float>& out, const vkx_camera* cur, const vkx_camera* prevCam, const std::vector<float>* prevImg) {
+    const float maxDev = 5.0f, depthFactor = 1.0f / 20.0f, baseHysteresis = 0.98f, depthStdDev = 0.1f;
+    const int W = int(st.w), H = int(st.h);
+    mat4 pview, pproj;
+    if (DIR == 1) { pview = mat4_from(prevCam->view); pproj = mat4_from(prevCam->proj); }
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t y = 0; y < H; ++y) for (int x = 0; x < W; ++x) {
+        int coords[2] = {x, int(y)};
+        int launchSize[2] = {W, H};
+        vec4 positionDepth = load(st.positionDepth, st.w, st.h, x, int(y));
+        vec3 position = xyz(positionDepth);
+        float depth = positionDepth.w;
+        vec4 center = load(in, st.w, st.h, x, int(y));
+        float roughness = center.w;
+        float* o = &out[(size_t(y) * st.w + size_t(x)) * 4];
+        float stdDev = std::max(0.0f, maxDev * roughness / std::max(1.0f, depthFactor * depth));
+        if (stdDev == 0.0f) { o[0] = center.x; o[1] = center.y; o[2] = center.z; o[3] = center.w; continue; } // :89-92
+        float sqrDev = stdDev * stdDev;
+        int window = int(clampf(std::ceil(std::sqrt(-2.0f * sqrDev * std::log(0.01f * stdDev * std::sqrt(2.0f * 3.14159f)))), 1.0f, maxDev));
+        float totalFactor = 0.0f;
+        int minOffset = -std::min(window, coords[DIR]);
+        int maxOffset = std::min(window, launchSize[DIR] - coords[DIR]);
+        vec4 fin = V4(0, 0, 0, 0);
+        for (int i = minOffset; i <= maxOffset; ++i) {
+            int ox = x + (DIR == 0 ? i : 0), oy = int(y) + (DIR == 1 ? i : 0);
+            float factor = rgaussian(stdDev, float(i));
+            factor *= rgaussian(depthStdDev, std::fabs(depth - load(st.positionDepth, st.w, st.h, ox, oy).w));
+            totalFactor += factor;
+            fin += factor * load(in, st.w, st.h, ox, oy);
+        }
+        if (totalFactor > 1e-2f) fin = fin / totalFactor; else fin = V4(0, 0, 0, 0);
+        if (DIR == 0) { o[0] = fin.x; o[1] = fin.y; o[2] = fin.z; o[3] = roughness; continue; }
+        float hysteresis = baseHysteresis;
+        vec4 previousValue = V4(0, 0, 0, 0);
+        vec3 corigin = V3(cur->origin[0], cur->origin[1], cur->origin[2]), porigin = V3(prevCam->origin[0], prevCam->origin[1], prevCam->origin[2]);
+        float cameraMovement = length(corigin - porigin);
+        hysteresis *= std::max(0.0f, 1.0f - cameraMovement);
+        if (hysteresis > 0.0f) {
+            // motion vectors are zero: static scenes (GBuffer.vert.glsl:46-48)
+            vec4 prevCoords = pproj * (pview * V4(position, 1.0f));
+            prevCoords.x /= prevCoords.w; prevCoords.y /= prevCoords.w;
+            prevCoords.x = (0.5f * prevCoords.x + 0.5f) * float(W);
+            prevCoords.y = (0.5f * prevCoords.y + 0.5f) * float(H);
+            if (prevCoords.x > float(W) || prevCoords.x < 0.0f || prevCoords.y > float(H) || prevCoords.y < 0.0f) hysteresis = 0.0f; // note: > not >= (:128)
+            else {
+                previousValue = load(*prevImg, st.w, st.h, int(prevCoords.x), int(prevCoords.y));
+                vec3 previousPosition = porigin + previousValue.w * normalize(position - porigin);
+                float factor = length(position - previousPosition);
+                hysteresis *= 1.0f - clampf(factor, 0.0f, 1.0f);
+            }
+        }
+        o[0] = mix(fin.x, previousValue.x, hysteresis); o[1] = mix(fin.y, previousValue.y, hysteresis); o[2] = mix(fin.z, previousValue.z, hysteresis); o[3] = depth;
+    }
+}
+
+void reflectionFrame(const oddgi::Scene& s, const oddgi::Probes& probes, State& st, const vkx_camera& cur, const vkx_camera& prev, const vkx_light& light, const float* dirOverride) {
+    const int W = int(st.w), H = int(st.h);
+    st.reflPrevious = st.reflFinal; // history copy (the editor copies last frame's filtered image)
+    uint32_t slice = cur.frameIndex % st.noiseSlices;
+    vec3 camOrigin = V3(cur.origin[0], cur.origin[1], cur.origin[2]);
+    // ivec2(frameIndex / 64, frameIndex / 64 / 64) + pixel  (reflection.rgen:150)
+    const int offx = int(cur.frameIndex / 64u), offy = int(cur.frameIndex / 64u / 64u);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t y = 0; y < H; ++y) for (int x = 0; x < W; ++x) { // reflection.rgen:117-189
+        size_t pix = size_t(y) * st.w + size_t(x);
+        const float* pd = &st.positionDepth[pix * 4]; const float* nm = &st.normalMetalness[pix * 4]; const float* ar = &st.albedoRoughness[pix * 4];
+        float* o = &st.reflRaw[pix * 4];
+        vec3 position = V3(pd[0], pd[1], pd[2]); float depth = pd[3];
+        vec3 normal = V3(nm[0], nm[1], nm[2]); float metalness = nm[3];
+        float roughness = ar[3];
+        st.reflMask[pix] = 0; st.reflHits[pix] = vkx_hit{}; st.reflHits[pix].t = -1.0f;
+        st.reflDirs[3 * pix] = st.reflDirs[3 * pix + 1] = st.reflDirs[3 * pix + 2] = 0.0f;
+        if (!(depth > 0.0f && (roughness < 0.4f || metalness > 0.01f))) { o[0] = o[1] = o[2] = o[3] = 0.0f; continue; }
+        vec3 toOrigin = normalize(camOrigin - position);
+        vec3 reflectDir = normalize(reflect(-toOrigin, normal));
+        vec4 noise = sampleNoise(st, slice, float(offx + x) / 64.0f, float(offy + int(y)) / 64.0f);
+        const float theta = roughness * (noise.x - 0.5f) * 2.0f * pi;
+        const float phi = (noise.y - 0.5f) * 2.0f * pi;
+        vec3 tangent;
+        if (dot(reflectDir, normal) < 0.9f) tangent = normalize(cross(reflectDir, normal));
+        else tangent = normalize(cross(reflectDir, V3(1, 0, 0)));
+        vec3 direction = rotateAxis(reflectDir, tangent, theta);
+        direction = rotateAxis(direction, reflectDir, phi);
+        if (dirOverride) direction = V3(dirOverride[3 * pix], dirOverride[3 * pix + 1], dirOverride[3 * pix + 2]);
+        st.reflDirs[3 * pix] = direction.x; st.reflDirs[3 * pix + 1] = direction.y; st.reflDirs[3 * pix + 2] = direction.z;
+        vkx_hit hit; uint8_t shadowFlag = 0;
+        vec4 c = oddgi::traceAndShade(s, probes, light, position, direction, 0.1f, 10000.0f, 0xFFu, hit, shadowFlag);
+        if (c.w < 0.0f) { st.reflMask[pix] = 1; hit = vkx_hit{}; hit.t = -1.0f; }
+        else st.reflMask[pix] = (hit.primitive & 0x80000000u) ? 2 : (shadowFlag == 2 ? 4 : 3);
+        st.reflHits[pix] = hit;
+        vec3 v = xyz(c);
+        // colorCompression = reinhard_whitepoint(v, 1.0) (:95-110)
+        const float max_value = 1.0f;
+        vec3 comp = v * (V3(1, 1, 1) + (v / (max_value * max_value))) / (V3(1, 1, 1) + v);
+        o[0] = comp.x; o[1] = comp.y; o[2] = comp.z; o[3] = roughness;
+    }
+    reflectionFilterPass<0>(st, st.reflRaw, st.reflX, nullptr, nullptr, nullptr);
+    reflectionFilterPass<1>(st, st.reflX, st.reflFinal, &cur, &prev, &st.reflPrevious);
 }
 
 // FinalGather.frag:38-77. fragPosition of FullScreenQuad.vert interpolates to the pixel centre ((x + 0.5) / W, (y + 0.5) / H).

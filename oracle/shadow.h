@@ -11,6 +11,10 @@ struct State {
     std::vector<float> positionDepth, normalMetalness; // RGBA32F G-buffer
     std::vector<float> albedoRoughness, emissive;      // RGBA32F G-buffer targets only the composite reads (GBuffer.frag:66-67)
     std::vector<float> gathered;                       // RGBA32F output of finalGather
+    std::vector<float> reflRaw, reflX, reflFinal, reflPrevious; // reflection pass images (RGBA32F)
+    std::vector<float> reflDirs;                       // jittered reflection direction per pixel (debug / parity)
+    std::vector<vkx_hit> reflHits;                     // closest hit of the reflection ray (t = -1: miss or no ray)
+    std::vector<uint8_t> reflMask;                     // 0 no ray, 1 miss, 2 back face, 3 front lit, 4 front shadowed
     std::vector<float> raw, filteredX, final_, previous; // RGBA32F
     std::vector<float> dirs;   // jittered light direction per pixel (debug / parity)
     std::vector<uint8_t> mask; // 0 not traced, 1 lit, 2 shadowed
@@ -23,8 +27,12 @@ void gbufferGenerate(const oddgi::Scene& s, State& st, const vkx_camera& cam);
 // dirOverride (optional, [h][w][3]): use these jittered directions instead of computing them (bit-exact mask tests).
 void frame(const oddgi::Scene& s, State& st, const vkx_camera& cur, const vkx_camera& prev, const vkx_light& light, const float* dirOverride);
 
+// reflection.rgen:117-186 + reflectionFilterX/Y (reflectionFilter.glsl) with the history copy of the editor (previous <- final).
+// dirOverride (optional, [h][w][3]): use these jittered directions instead of computing them (bit-exact hit tests).
+void reflectionFrame(const oddgi::Scene& s, const oddgi::Probes& probes, State& st, const vkx_camera& cur, const vkx_camera& prev, const vkx_light& light, const float* dirOverride);
+
 // FinalGather.frag:38-77: sky on empty pixels, else direct * shadow + specular * reflection + sampleProbes * diffuse + emissive.
-// reflection: optional RGBA32F [h][w][4] (the reflection pass is out of scope; nullptr = black).
+// reflection: optional RGBA32F [h][w][4] (e.g. reflFinal of reflectionFrame; nullptr = black).
 void finalGather(const oddgi::Scene& s, const oddgi::Probes& probes, State& st, const vkx_camera& cam, const vkx_light& light, const float* reflection);
 
 } // namespace oshadow

@@ -208,3 +208,53 @@ def test_oracle_final_gather_properties(oracle_lib, scene_getter):
     o.shadow_set_history(np.ones((H, W, 4), dtype=np.float32))
     lit, _ = o.final_gather(cam, light)
     assert (lit[geo][:, :3] >= base[geo][:, :3]).all() and lit[geo][:, :3].max() > base[geo][:, :3].max()
+
+
+def test_oracle_reflection_properties(oracle_lib, scene_getter):
+    """reflection.rgen / reflectionFilter.glsl restatement: only pixels with roughness < 0.4 or metalness > 0.01 trace a ray;
+    a mirror (roughness 0) reflects exactly about the normal and skips both filters; a still camera blends 98 % history."""
+    from vulkanexp_b200 import synth
+    from vulkanexp_b200.pods import GridInfo, Light, make_camera
+
+    W, H = 96, 54
+    flat = scene_getter("court")
+    o = oracle_lib.Oracle(); o.scene_upload(flat); o.bvh_build()
+    grid = GridInfo.make(flat["bounds_min"], flat["bounds_max"], (4, 3, 4), 32)
+    o.probes_init(grid)
+    o.shadow_set_noise(synth.blue_noise_like(4, 64)); o.shadow_init(W, H)
+    cam = make_camera((-5.0, 2.5, 4.5), (0.0, 3.0, 0.0), aspect=W / H, frame_index=0)
+    o.gbuffer_generate(cam)
+    pd, nm = o.gbuffer_download()
+    ar, em = o.gbuffer_download_material()
+    geo = pd[..., 3] > 0
+    light = Light.default()
+    o.reflection_frame(cam, cam, light)
+    raw, dirs, hits, mask = o.reflection_download(0)
+    want = geo & ((ar[..., 3] < 0.4) | (nm[..., 3] > 0.01))
+    assert np.array_equal(mask > 0, want) and 0 < want.mean() < 1
+    assert not raw[~want].any() and np.array_equal(hits["t"][~want], np.full(int((~want).sum()), -1.0, dtype=np.float32))
+    # mirrors everywhere
+    ar2 = ar.copy(); ar2[..., 3] = 0.0
+    o.gbuffer_upload_material(ar2, em)
+    o.reflection_frame(cam, cam, light)
+    raw, dirs, hits, mask = o.reflection_download(0)
+    n = nm[..., :3].astype(np.float64); p = pd[..., :3].astype(np.float64)
+    to_origin = np.array([-5.0, 2.5, 4.5]) - p; to_origin /= np.linalg.norm(to_origin, axis=-1, keepdims=True) + 1e-30
+    mirror = -to_origin - 2.0 * (n * -to_origin).sum(-1, keepdims=True) * n
+    mirror /= np.linalg.norm(mirror, axis=-1, keepdims=True) + 1e-30
+    assert np.abs(dirs[geo] - mirror[geo]).max() < 1e-5
+    assert np.array_equal(mask > 0, geo)
+    x_img = o.reflection_download(1)[0]; fin = o.reflection_download(2)[0]
+    assert np.array_equal(x_img, raw) and np.array_equal(fin, raw), "roughness 0: both filters pass the pixel through"
+    assert (raw[geo][:, :3] >= 0).all() and raw[geo][:, :3].max() > 0
+    # rough metal: still camera -> 0.98 history weight
+    ar3 = ar.copy(); ar3[..., 3] = 0.3
+    nm3 = nm.copy(); nm3[..., 3] = 1.0
+    o.gbuffer_upload(pd, nm3); o.gbuffer_upload_material(ar3, em)
+    hist = np.zeros((H, W, 4), dtype=np.float32); hist[..., :3] = 7.0; hist[..., 3] = pd[..., 3]
+    o.reflection_set_history(hist)
+    o.reflection_frame(cam, cam, light)
+    x_img = o.reflection_download(1)[0]; fin = o.reflection_download(2)[0]
+    inner = geo.copy(); inner[:6] = inner[-6:] = False; inner[:, :6] = inner[:, -6:] = False
+    assert np.array_equal(fin[..., 3][geo], pd[..., 3][geo]), "final alpha carries the depth"
+    assert (fin[inner][:, :3] > 0.9 * 7.0 * 0.98).mean() > 0.9, "a still camera keeps 98 % of a matching history"

@@ -25,6 +25,13 @@ for f, cam in enumerate(cams):
     t0 = time.perf_counter(); g.gbuffer_generate(cam); gb.append((time.perf_counter() - t0) * 1e3)
     g.shadow_frame(cam, prev, light)
     t = g.shadow_timings()
+    # the dungeon's materials are rough dielectrics; polish the floor (normal.y > 0.9 -> roughness 0.15) so the reflection pass has work
+    ar, em = g.gbuffer_download_material(); nmm = g.gbuffer_download()[1]
+    ar[..., 3] = np.where(nmm[..., 1] > 0.9, np.float32(0.15), ar[..., 3])
+    g.gbuffer_upload_material(ar, em)
+    g.reflection_frame(cam, prev, light)
+    rt = g.reflection_timings()
+    t.update({"reflection": rt["full"], "reflection_trace_shade": rt["trace_shade"], "reflection_filter_x": rt["filter_x"], "reflection_filter_y": rt["filter_y"]})
     g.final_gather(cam, light)
     t["gather"] = g.final_gather_download(out=img)[1]
     ms.append(t); prev = cam
@@ -36,7 +43,7 @@ print(json.dumps({"metric": "sun_shadow_pass_ms", "value": avg["full"], "unit": 
                   "gbuffer_fixture_ms": float(np.mean(gb[4:])), "geometry_pixels": float((pd[..., 3] > 0).mean()),
                   "filter_bytes_per_px": 48 + 64, "filter_gbs": px * (48 + 64) / ((avg["filter_x"] + avg["filter_y"]) * 1e-3) / 1e9,
                   "shadow_rays_per_s": px * float((pd[..., 3] > 0).mean()) / (avg["trace"] * 1e-3),
-                  "final_gather_ms": avg["gather"], "final_gather_bytes_per_px": 5 * 16 + 16, "final_gather_gbs": px * 96 / (avg["gather"] * 1e-3) / 1e9,
+                  "reflection_ms": avg["reflection"], "reflecting_pixels": float((g.reflection_download(0)[..., 3] > 0).mean()), "final_gather_ms": avg["gather"], "final_gather_bytes_per_px": 5 * 16 + 16, "final_gather_gbs": px * 96 / (avg["gather"] * 1e-3) / 1e9,
                   "composite_mean_rgb": [float(v) for v in img[..., :3].mean(axis=(0, 1))]}))
 if len(sys.argv) > 3:  # optional: write the last composite as a PPM (Reinhard + gamma 2.2) for a look at the picture
     rgb = img[..., :3] / (1.0 + img[..., :3]); rgb = (np.clip(rgb, 0, 1) ** (1 / 2.2) * 255 + 0.5).astype(np.uint8)

@@ -268,6 +268,30 @@ class Context:
         self._check(self.l.vkx_final_gather_download(self.h, _p(img), C.byref(ms)))
         return img, float(ms.value)
 
+    def reflection_frame(self, cur, prev, light, sync=True):
+        self._check(self.l.vkx_reflection_frame(self.h, C.byref(cur), C.byref(prev), C.byref(light), C.c_int(int(sync))))
+
+    def reflection_download(self, stage=2, out=None):
+        img = out if out is not None else np.zeros((self.sh, self.sw, 4), dtype=np.float32)
+        self._check(self.l.vkx_reflection_download(self.h, C.c_int(stage), _p(img)))
+        return img
+
+    def reflection_download_debug(self):
+        from .pods import HIT_DTYPE
+        dirs = np.zeros((self.sh, self.sw, 4), dtype=np.float32)
+        hits = np.zeros((self.sh, self.sw), dtype=HIT_DTYPE)
+        mask = np.zeros((self.sh, self.sw), dtype=np.uint8)
+        self._check(self.l.vkx_reflection_download_debug(self.h, _p(dirs), _p(hits), _p(mask)))
+        return dirs[..., :3].copy(), hits, mask
+
+    def reflection_reset_history(self):
+        self._check(self.l.vkx_reflection_reset_history(self.h))
+
+    def reflection_timings(self):
+        ms = (C.c_float * 4)()
+        self._check(self.l.vkx_reflection_timings(self.h, ms))
+        return {"full": ms[0], "trace_shade": ms[1], "filter_x": ms[2], "filter_y": ms[3]}
+
     def shadow_frame(self, cur, prev, light, sync=True):
         self._check(self.l.vkx_shadow_frame(self.h, C.byref(cur), C.byref(prev), C.byref(light), C.c_int(int(sync))))
 

@@ -80,10 +80,12 @@ static void freeProbes(vkx_ctx* ctx) {
     ctx->probesReady = false;
 }
 static void freeShadow(vkx_ctx* ctx) {
-    void* ptrs[] = {ctx->dPosDepth, ctx->dNormalMetal, ctx->dShRaw, ctx->dShX, ctx->dShFinal[0], ctx->dShFinal[1], ctx->dShDirs, ctx->dShMask, ctx->dAlbedoRough, ctx->dEmissive, ctx->dReflection, ctx->dGathered};
+    void* ptrs[] = {ctx->dPosDepth, ctx->dNormalMetal, ctx->dShRaw, ctx->dShX, ctx->dShFinal[0], ctx->dShFinal[1], ctx->dShDirs, ctx->dShMask, ctx->dAlbedoRough, ctx->dEmissive, ctx->dReflection, ctx->dGathered,
+                    ctx->dReflRaw, ctx->dReflX, ctx->dReflFinal[0], ctx->dReflFinal[1], ctx->dReflDirs, ctx->dReflHits, ctx->dReflMask, ctx->dReflQueue, ctx->dReflCount};
     for (void* p : ptrs) if (p) cudaFree(p);
     ctx->dPosDepth = ctx->dNormalMetal = ctx->dShRaw = ctx->dShX = ctx->dShFinal[0] = ctx->dShFinal[1] = ctx->dShDirs = nullptr; ctx->dShMask = nullptr;
     ctx->dAlbedoRough = ctx->dEmissive = ctx->dReflection = ctx->dGathered = nullptr;
+    ctx->dReflRaw = ctx->dReflX = ctx->dReflFinal[0] = ctx->dReflFinal[1] = ctx->dReflDirs = nullptr; ctx->dReflHits = nullptr; ctx->dReflMask = nullptr; ctx->dReflQueue = ctx->dReflCount = nullptr; ctx->reflValid = false;
     ctx->shW = ctx->shH = 0;
 }
 

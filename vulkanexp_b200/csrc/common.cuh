@@ -118,6 +118,10 @@ struct vkx_ctx {
     // composite (FinalGather): the two G-buffer targets only it reads, optional reflection input, output
     float4 *dAlbedoRough = nullptr, *dEmissive = nullptr, *dReflection = nullptr, *dGathered = nullptr;
     cudaEvent_t gev[2] = {nullptr, nullptr};
+    // reflection pass (reflection.cu): raw 1-spp, after filter X, final ping-pong (dReflFinal[reflCur] = last frame's result), parity side buffers
+    float4 *dReflRaw = nullptr, *dReflX = nullptr, *dReflFinal[2] = {nullptr, nullptr}, *dReflDirs = nullptr; vkx_hit* dReflHits = nullptr; uint8_t* dReflMask = nullptr; uint32_t *dReflQueue = nullptr, *dReflCount = nullptr;
+    int reflCur = 0; bool reflValid = false;
+    cudaEvent_t rev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 int vkx_fail(vkx_ctx* ctx, int code, const char* fmt, ...);
@@ -149,6 +153,7 @@ int traceHostRays(vkx_ctx* ctx, const float* origins, const float* directions, s
 // ---- shadow.cu
 int shadowGBuffer(vkx_ctx* ctx, const vkx_camera& cam);
 int shadowFrame(vkx_ctx* ctx, const vkx_camera& cur, const vkx_camera& prev, const vkx_light& light);
+int reflectionFrame(vkx_ctx* ctx, const vkx_camera& cur, const vkx_camera& prev, const vkx_light& light); // reflection.cu
 
 DeviceScene deviceScene(const vkx_ctx* ctx);
 DeviceProbes deviceProbes(const vkx_ctx* ctx);

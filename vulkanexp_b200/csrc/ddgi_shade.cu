@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "shade.cuh"
 #include "ddgi_common.cuh"
+#include "hitshade.cuh"
 
 namespace {
 
@@ -40,40 +41,10 @@ __global__ void __launch_bounds__(128, 6) k_shade_front(DeviceScene sc, DevicePr
         const float4 d4 = __ldg(dirs + ray);
         const v3 direction = mk3(d4.x, d4.y, d4.z);
         const vkx_hit h = hits[ri];
-        const float u = h.u, v = h.v;
-        const float bx = 1.0f - u - v, by = u, bz = v;
         const v3 position = pointOnRayExact(origin, direction, h.t);
-        const uint32_t meshEntry = __ldg(&sc.instances[h.instance].meshEntry);
-        const vkx_offset_entry oe = sc.offsets[meshEntry];
-        const uint32_t prim = h.primitive & 0x7FFFFFFFu;
-        v3 n3[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const uint32_t vi = oe.vertexOffset + __ldg(sc.indices + oe.indexOffset + 3 * prim + c);
-            const float* nn = sc.vertices[vi].normal;
-            n3[c] = mk3(__ldg(nn), __ldg(nn + 1), __ldg(nn + 2));
-        }
-        const vkx_material m = sc.materials[oe.materialIndex];
-        const v3 tsn = norm3(n3[0] * bx + n3[1] * by + n3[2] * bz);
-        const float* W = sc.worldToObject + size_t(h.instance) * 9; // W[row][col]
-        // vec3(tsn * worldToObject): component j = dot(tsn, column j)
-        const v3 normal = norm3(mk3(dot3(tsn, mk3(W[0], W[3], W[6])), dot3(tsn, mk3(W[1], W[4], W[7])), dot3(tsn, mk3(W[2], W[5], W[8]))));
-        const v3 albedo = mk3(m.baseColorFactor[0], m.baseColorFactor[1], m.baseColorFactor[2]);
-        const float metalness = m.metallicFactor, roughness = m.roughnessFactor;
-        v3 color = mk3(0.0f) + mk3(m.emissiveFactor[0], m.emissiveFactor[1], m.emissiveFactor[2]);
-        const v3 f0 = mk3(0.04f);
-        v3 diffuseColor = albedo * (1.0f - f0);
-        diffuseColor = diffuseColor * (1.0f - metalness);
-        const v3 specularColor = mix3(f0, albedo, metalness);
-        const v3 reflectDir = reflect3(direction, normal);
-        v3 reflection, indirectLight;
-        sampleProbes2(pr, gc, position, reflectDir, normal, -direction, reflection, indirectLight);
-        color = color + specularColor * reflection;
-        color = color + indirectLight * diffuseColor;
-        rays[ri] = make_float4(color.x, color.y, color.z, h.t); // value if the sun is occluded
-        // direct term, applied by k_trace_shadow if the shadow ray escapes
-        v3 lit = color + pbrMetallicRoughness(normal, norm3(-direction), lightColor, lightDir, albedo, metalness, roughness);
-        if (lightDir.y < 0.0f) lit = lit * (1.0f - clampS(-lightDir.y, 0.0f, 0.1f) / 0.1f);
+        v3 color, lit;
+        shadeFrontHit(sc, pr, gc, lightDir, lightColor, direction, position, h, color, lit);
+        rays[ri] = make_float4(color.x, color.y, color.z, h.t); // value if the sun is occluded; k_trace_shadow writes `lit` if the shadow ray escapes
         const uint32_t qi = warpAppend(counters);
         queue[2 * size_t(qi)] = make_float4(position.x, position.y, position.z, __uint_as_float(ri));
         queue[2 * size_t(qi) + 1] = make_float4(lit.x, lit.y, lit.z, 0.0f);
