@@ -260,7 +260,7 @@ int vkx_probes_init(vkx_ctx* ctx, const vkx_grid_info* grid) {
     CUDA_TRY(ctx, cudaMalloc(&ctx->dIota, stBytes));
     CUDA_TRY(ctx, cudaMalloc(&ctx->dCellHist, stBytes + 4));
     k_iota_list<<<divUp(ctx->probeCount, 256), 256, 0, ctx->stream>>>(ctx->dIota, 0, ctx->probeCount); LAUNCH_CHECK(ctx);
-    CUDA_TRY(ctx, cudaMalloc(&ctx->dBlendW, size_t(VKX_MAX_RAYS_PER_PROBE) * 288 * 4));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->dBlendW, size_t(VKX_MAX_RAYS_PER_PROBE + 1) * 288 * 4)); // + the row of weight sums
     { // rank of every probe in 2x2x2-block order (scheduling only: which probes share a warp)
         const uint32_t rx = uint32_t(grid->resolution[0]), ry = uint32_t(grid->resolution[1]);
         const uint32_t nbx = (rx + 1) / 2, nby = (ry + 1) / 2;

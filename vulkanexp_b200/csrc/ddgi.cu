@@ -122,9 +122,13 @@ struct BlendParams {
 // (probesUpdate.glsl:60,75,80). Same arithmetic as evaluating the weight inside the blend loop.
 #define BLEND_COLS 288
 #define BLEND_IRR_COL0 224
+#ifndef BLEND_P
 #define BLEND_P 8
+#endif
+#define BLEND_SMEM_BYTES (BLEND_P * (VKX_MAX_RAYS_PER_PROBE * 5 * 4 + 256 * 4 + 64 * 4))
 __global__ void __launch_bounds__(BLEND_COLS) k_blend_weights(float depthSharpness, uint32_t N, const float4* __restrict__ dirs, float* __restrict__ W) {
     const uint32_t i = blockIdx.x, col = threadIdx.x;
+    if (i >= N) { W[size_t(i) * BLEND_COLS + col] = 0.0f; return; } // padding rows up to a multiple of 4 rays
     const float4 dd = __ldg(dirs + i);
     float w = 0.0f;
     if (col < 196u) {
@@ -140,94 +144,111 @@ __global__ void __launch_bounds__(BLEND_COLS) k_blend_weights(float depthSharpne
     W[size_t(i) * BLEND_COLS + col] = w;
 }
 
-// One CTA blends BLEND_P probes: their ray records are staged in shared memory, thread `col` owns one texel of every probe, so each
-// weight is loaded once and applied to BLEND_P probes from registers. Accumulation over rays is sequential (i = 0..N-1) like the oracle's,
-// with fused multiply-adds (one rounding instead of the oracle's two per term: fp32 results differ by <= 1e-6 relative, which
-// flips an 11-bit packed code on ~1e-5 of the texels). Warps 0-6: depth texels,
-// warps 7-8: irradiance texels (warp-uniform roles).
-__global__ void __launch_bounds__(BLEND_COLS) k_blend(BlendParams bp, DeviceProbes pr, const uint32_t* __restrict__ probeIndices, const float4* __restrict__ rays,
-                                                      const float* __restrict__ W, float* __restrict__ irrUnpacked, float* __restrict__ depUnpacked, uint32_t slotBase) {
-    __shared__ float4 sRay[BLEND_P][VKX_MAX_RAYS_PER_PROBE]; // (r, g, b, clamped depth)
-    __shared__ uint32_t sDep[BLEND_P][256];
-    __shared__ uint32_t sIrr[BLEND_P][64];
+// Sum of a texel's weights over the rays, in ray order (the `result.w` every blend thread of that texel would accumulate): row BLEND_WSUM_ROW.
+#define BLEND_WSUM_ROW VKX_MAX_RAYS_PER_PROBE
+__global__ void __launch_bounds__(BLEND_COLS) k_blend_weight_sums(uint32_t N, float* __restrict__ W) {
+    float rw = 0.0f;
+    for (uint32_t i = 0; i < N; ++i) rw = rw + W[size_t(i) * BLEND_COLS + threadIdx.x];
+    W[size_t(BLEND_WSUM_ROW) * BLEND_COLS + threadIdx.x] = rw;
+}
+
+// One CTA blends BLEND_P probes. Their ray records are staged in shared memory as five planes (d, d^2, r, g, b); a thread owns
+// one (texel, plane) pair of every probe: 2 x 196 depth-moment threads + 3 x 36 irradiance-channel threads (warp-uniform roles,
+// BLEND_THREADS = 576). All threads run the same loop: the weight of their texel is loaded once per ray and applied to BLEND_P
+// probes from registers, and one 128-bit shared-memory load feeds four rays of a probe, so the loop is 80 % FFMA and every warp
+// carries the same load. Accumulation over rays is sequential (i = 0..N-1) like the oracle's, with fused multiply-adds (one
+// rounding instead of the oracle's two per term; w * d^2 instead of (w * d) * d: fp32 results differ by ~1e-6 relative, which
+// flips an 11-bit packed code on ~1e-5 of the texels). The normalised sums meet again in shared memory for the hysteresis mix.
+#define BLEND_THREADS 576
+#define BLEND_DEPTH_T0 0     // threads [0, 224): first depth moment, texel = tid
+#define BLEND_DEPTH_T1 224   // threads [224, 448): second depth moment
+#define BLEND_IRR_T 448      // threads [448, 576): irradiance, channel = t / 36, texel = t % 36
+__global__ void __launch_bounds__(BLEND_THREADS) k_blend(BlendParams bp, DeviceProbes pr, const uint32_t* __restrict__ probeIndices, const float4* __restrict__ rays,
+                                                         const float* __restrict__ W, float* __restrict__ irrUnpacked, float* __restrict__ depUnpacked, uint32_t slotBase) {
+    // dynamic shared memory (50 KB): 5 planes [BLEND_P][256] of ray data, re-used for the normalised sums after the ray loop; output tiles
+    extern __shared__ float4 sBlend[];
+    float* sPlane = reinterpret_cast<float*>(sBlend);                                // [5][BLEND_P][256]
+    float* sResD = sPlane;                                                           // [BLEND_P][2][196]  (aliases the planes)
+    float* sResI = sPlane + BLEND_P * 2 * 196;                                       // [BLEND_P][3][36]
+    uint32_t (*sDep)[256] = reinterpret_cast<uint32_t (*)[256]>(sPlane + 5 * BLEND_P * VKX_MAX_RAYS_PER_PROBE);
+    uint32_t (*sIrr)[64] = reinterpret_cast<uint32_t (*)[64]>(sDep + BLEND_P);
     __shared__ uint32_t sMaxChange[BLEND_P];
     __shared__ uint32_t sOutOfRange[BLEND_P];
     __shared__ uint32_t sLinear[BLEND_P];
     const uint32_t tid = threadIdx.x, N = bp.raysPerProbe;
+    const uint32_t N4 = (N + 3u) & ~3u;
     const uint32_t slot0 = blockIdx.x * BLEND_P;
     const uint32_t np = min(uint32_t(BLEND_P), bp.count - slot0);
     const float cellLen = bp.gridCellLen;
+    constexpr uint32_t PS = BLEND_P * VKX_MAX_RAYS_PER_PROBE; // plane stride
     if (tid < BLEND_P) { sMaxChange[tid] = 0u; sOutOfRange[tid] = 0u; sLinear[tid] = tid < np ? __ldg(probeIndices + slot0 + tid) : 0u; }
     __syncthreads();
     // stage ray records; count out-of-range rays per probe (probesUpdate.glsl:74) and clamp depths (:78-79) once per ray
-    for (uint32_t e = tid; e < BLEND_P * N; e += BLEND_COLS) {
-        const uint32_t p = e / N, i = e - p * N;
+    for (uint32_t e = tid; e < BLEND_P * N4; e += BLEND_THREADS) {
+        const uint32_t p = e / N4, i = e - p * N4;
         float4 rd = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p < np) {
+        if (p < np && i < N) {
             rd = rays[size_t(slot0 + p) * N + i];
             if (rd.w < 0.0f || rd.w > cellLen) atomicAdd(&sOutOfRange[p], 1u);
             float depth = minS(cellLen, rd.w);
             if (depth < 0.0f) depth = cellLen;
             rd.w = depth;
         }
-        sRay[p][i] = rd;
+        float* q = sPlane + p * VKX_MAX_RAYS_PER_PROBE + i;
+        q[0] = rd.w; q[PS] = rd.w * rd.w; q[2 * PS] = rd.x; q[3 * PS] = rd.y; q[4 * PS] = rd.z;
+    }
+    __syncthreads();
+    // role of this thread: weight column, data plane, texel
+    int plane = -1; uint32_t col = 0, texel = 0;
+    if (tid < BLEND_DEPTH_T1) { if (tid < 196u) { plane = 0; texel = tid; col = tid; } }
+    else if (tid < BLEND_IRR_T) { if (tid - BLEND_DEPTH_T1 < 196u) { plane = 1; texel = tid - BLEND_DEPTH_T1; col = texel; } }
+    else if (tid - BLEND_IRR_T < 108u) { const uint32_t t = tid - BLEND_IRR_T; plane = 2 + int(t / 36u); texel = t % 36u; col = BLEND_IRR_COL0 + texel; }
+    float acc[BLEND_P], rw = 0.0f;
+#pragma unroll
+    for (int p = 0; p < BLEND_P; ++p) acc[p] = 0.0f;
+    if (plane >= 0) {
+        const float* Wc = W + col;
+        const float* src = sPlane + size_t(plane) * PS;
+        rw = __ldg(Wc + size_t(BLEND_WSUM_ROW) * BLEND_COLS);
+#pragma unroll 1
+        for (uint32_t i = 0; i < N4; i += 4) { // rays beyond N are zero in the planes and in the (padded) weight table
+            const float w0 = __ldg(Wc + size_t(i) * BLEND_COLS), w1 = __ldg(Wc + size_t(i + 1) * BLEND_COLS);
+            const float w2 = __ldg(Wc + size_t(i + 2) * BLEND_COLS), w3 = __ldg(Wc + size_t(i + 3) * BLEND_COLS);
+#pragma unroll
+            for (int p = 0; p < BLEND_P; ++p) {
+                const float4 m = *reinterpret_cast<const float4*>(src + p * VKX_MAX_RAYS_PER_PROBE + i);
+                acc[p] = fmaf(w0, m.x, acc[p]); acc[p] = fmaf(w1, m.y, acc[p]); acc[p] = fmaf(w2, m.z, acc[p]); acc[p] = fmaf(w3, m.w, acc[p]);
+            }
+        }
+    }
+    __syncthreads(); // the planes are dead from here on: their memory now holds the normalised sums
+    if (plane >= 0) {
+#pragma unroll
+        for (int p = 0; p < BLEND_P; ++p) {
+            float r = acc[p];
+            if (rw > 1e-3f) r = r / rw;
+            if (plane < 2) sResD[(p * 2 + plane) * 196 + texel] = r; else sResI[(p * 3 + (plane - 2)) * 36 + texel] = r;
+        }
     }
     __syncthreads();
     const float hysteresis = bp.grid.hysteresis;
-    const float* Wc = W + tid;
-    if (tid < 224u) { // ---- depth texels (warps 0..6; lanes >= 196 idle)
-        if (tid < 196u) {
-            float a0[BLEND_P], a1[BLEND_P], rw = 0.0f;
-#pragma unroll
-            for (int p = 0; p < BLEND_P; ++p) { a0[p] = 0.0f; a1[p] = 0.0f; }
-#pragma unroll 4
-            for (uint32_t i = 0; i < N; ++i) {
-                const float w = __ldg(Wc + size_t(i) * BLEND_COLS);
-#pragma unroll
-                for (int p = 0; p < BLEND_P; ++p) {
-                    const float d = sRay[p][i].w;
-                    const float t = w * d;
-                    a0[p] = fmaf(w, d, a0[p]);
-                    a1[p] = fmaf(t, d, a1[p]);
-                }
-                rw = rw + w;
-            }
-            const int lx = int(tid % 14u), ly = int(tid / 14u);
-#pragma unroll
-            for (int p = 0; p < BLEND_P; ++p) {
-                if (uint32_t(p) >= np) break;
-                float r0 = a0[p], r1 = a1[p];
-                if (rw > 1e-3f) { r0 = r0 / rw; r1 = r1 / rw; }
-                int ix, iy, iz; probeGridIndex(sLinear[p], bp.grid, ix, iy, iz);
-                const int tile = iy * bp.grid.resolution[0] + ix;
-                const size_t gi = size_t(16 * iz + 1 + ly) * pr.depW + size_t(16 * tile + 1 + lx);
-                const float2 prev = unpackRG16F(pr.depWork[gi]);
-                const float o0 = mixf(r0, prev.x, hysteresis), o1 = mixf(r1, prev.y, hysteresis);
-                sDep[p][(ly + 1) * 16 + (lx + 1)] = packRG16F(o0, o1);
-                if (depUnpacked) { float* up = depUnpacked + (size_t(slotBase + slot0 + p) * 196 + tid) * 2; up[0] = o0; up[1] = o1; }
-            }
+    if (tid < 196u) { // ---- depth texels: hysteresis mix against the work atlas, pack
+        const int lx = int(tid % 14u), ly = int(tid / 14u);
+        for (uint32_t p = 0; p < np; ++p) {
+            const float r0 = sResD[(p * 2 + 0) * 196 + tid], r1 = sResD[(p * 2 + 1) * 196 + tid];
+            int ix, iy, iz; probeGridIndex(sLinear[p], bp.grid, ix, iy, iz);
+            const int tile = iy * bp.grid.resolution[0] + ix;
+            const size_t gi = size_t(16 * iz + 1 + ly) * pr.depW + size_t(16 * tile + 1 + lx);
+            const float2 prev = unpackRG16F(pr.depWork[gi]);
+            const float o0 = mixf(r0, prev.x, hysteresis), o1 = mixf(r1, prev.y, hysteresis);
+            sDep[p][(ly + 1) * 16 + (lx + 1)] = packRG16F(o0, o1);
+            if (depUnpacked) { float* up = depUnpacked + (size_t(slotBase + slot0 + p) * 196 + tid) * 2; up[0] = o0; up[1] = o1; }
         }
-    } else if (tid < BLEND_IRR_COL0 + 36u) { // ---- irradiance texels (warps 7..8)
-        const uint32_t t = tid - BLEND_IRR_COL0;
-        float a0[BLEND_P], a1[BLEND_P], a2[BLEND_P], rw = 0.0f;
-#pragma unroll
-        for (int p = 0; p < BLEND_P; ++p) { a0[p] = 0.0f; a1[p] = 0.0f; a2[p] = 0.0f; }
-#pragma unroll 2
-        for (uint32_t i = 0; i < N; ++i) {
-            const float w = __ldg(Wc + size_t(i) * BLEND_COLS);
-#pragma unroll
-            for (int p = 0; p < BLEND_P; ++p) {
-                const float4 rd = sRay[p][i];
-                a0[p] = fmaf(w, rd.x, a0[p]); a1[p] = fmaf(w, rd.y, a1[p]); a2[p] = fmaf(w, rd.z, a2[p]);
-            }
-            rw = rw + w;
-        }
+    } else if (tid >= BLEND_DEPTH_T1 && tid < BLEND_DEPTH_T1 + 36u) { // ---- irradiance texels (a different warp than the depth texels)
+        const uint32_t t = tid - BLEND_DEPTH_T1;
         const int lx = int(t % 6u), ly = int(t / 6u);
-#pragma unroll
-        for (int p = 0; p < BLEND_P; ++p) {
-            if (uint32_t(p) >= np) break;
-            float r0 = a0[p], r1 = a1[p], r2 = a2[p];
-            if (rw > 1e-3f) { r0 = r0 / rw; r1 = r1 / rw; r2 = r2 / rw; }
+        for (uint32_t p = 0; p < np; ++p) {
+            const float r0 = sResI[(p * 3 + 0) * 36 + t], r1 = sResI[(p * 3 + 1) * 36 + t], r2 = sResI[(p * 3 + 2) * 36 + t];
             int ix, iy, iz; probeGridIndex(sLinear[p], bp.grid, ix, iy, iz);
             const int tile = iy * bp.grid.resolution[0] + ix;
             const size_t gi = size_t(8 * iz + 1 + ly) * pr.irrW + size_t(8 * tile + 1 + lx);
@@ -253,7 +274,7 @@ __global__ void __launch_bounds__(BLEND_COLS) k_blend(BlendParams bp, DeviceProb
         pr.stateWork[linearIndex] = st;
     }
     // ---- borders (probesCopyBorders.comp) from the shared tiles: 60 depth + 28 irradiance texels per probe
-    for (uint32_t e = tid; e < np * 88u; e += BLEND_COLS) {
+    for (uint32_t e = tid; e < np * 88u; e += BLEND_THREADS) {
         const uint32_t p = e / 88u, b = e - p * 88u;
         int x, y, sx, sy;
         if (b < 60u) {
@@ -269,7 +290,7 @@ __global__ void __launch_bounds__(BLEND_COLS) k_blend(BlendParams bp, DeviceProb
     }
     __syncthreads();
     // ---- vectorised tile stores: per probe depth 16 rows x 64 B (64 uint4), irradiance 8 rows x 32 B (16 uint4)
-    for (uint32_t e = tid; e < np * 80u; e += BLEND_COLS) {
+    for (uint32_t e = tid; e < np * 80u; e += BLEND_THREADS) {
         const uint32_t p = e / 80u, k = e - p * 80u;
         int ix, iy, iz; probeGridIndex(sLinear[p], bp.grid, ix, iy, iz);
         const int tile = iy * bp.grid.resolution[0] + ix;
@@ -389,11 +410,14 @@ int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* /*unused*/,
     const float tmax = sqrtf(ex * ex + ey * ey + ez * ez); // traceProbes.rgen:33
     const float cx = ex / float(ctx->grid.resolution[0] - 1), cy = ey / float(ctx->grid.resolution[1] - 1), cz = ez / float(ctx->grid.resolution[2] - 1);
     BlendParams bp; bp.grid = ctx->grid; bp.raysPerProbe = N; bp.gridCellLen = sqrtf(cx * cx + cy * cy + cz * cz);
+    static bool blendAttr = false;
+    if (!blendAttr) { CUDA_TRY(ctx, cudaFuncSetAttribute(k_blend, cudaFuncAttributeMaxDynamicSharedMemorySize, BLEND_SMEM_BYTES)); blendAttr = true; }
     static int blocksPerSm = 0;
     if (!blocksPerSm) { int a = 0, b = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_trace_primary, 128, 0); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace_shadow, 128, 0); blocksPerSm = std::max(1, std::min(a, b)); }
     const unsigned persistentBlocks = unsigned(ctx->smCount * blocksPerSm);
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
-    k_blend_weights<<<N, BLEND_COLS, 0, st>>>(ctx->grid.depthSharpness, N, ctx->dDirs, ctx->dBlendW); LAUNCH_CHECK(ctx);
+    k_blend_weights<<<(N + 3u) & ~3u, BLEND_COLS, 0, st>>>(ctx->grid.depthSharpness, N, ctx->dDirs, ctx->dBlendW); LAUNCH_CHECK(ctx);
+    k_blend_weight_sums<<<1, BLEND_COLS, 0, st>>>(N, ctx->dBlendW); LAUNCH_CHECK(ctx);
     // One chunk: slots are the caller's list positions (ray/hit buffers are laid out [slot][ray]) and `order` only schedules them.
     // Several chunks: the list is first gathered in block order, a chunk is then a contiguous piece of it with identity order.
     const bool multi = count > ctx->chunkProbes;
@@ -438,7 +462,7 @@ int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* /*unused*/,
         if (base + n >= count) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], st));
         bp.count = n;
         CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->auxEvent[1], 0)); // sky results
-        k_blend<<<divUp(n, BLEND_P), BLEND_COLS, 0, st>>>(bp, pr, idx, ctx->dRays, ctx->dBlendW, ctx->debugBuffers ? ctx->dIrrUnpacked : nullptr, ctx->debugBuffers ? ctx->dDepUnpacked : nullptr, base); LAUNCH_CHECK(ctx);
+        k_blend<<<divUp(n, BLEND_P), BLEND_THREADS, BLEND_SMEM_BYTES, st>>>(bp, pr, idx, ctx->dRays, ctx->dBlendW, ctx->debugBuffers ? ctx->dIrrUnpacked : nullptr, ctx->debugBuffers ? ctx->dDepUnpacked : nullptr, base); LAUNCH_CHECK(ctx);
         if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[4], st));
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], st));
