@@ -64,12 +64,12 @@ int vkx_create(int device, vkx_ctx** out) {
 static void freeProbes(vkx_ctx* ctx) {
     void* ptrs[] = {ctx->dIrrWork, ctx->dIrrSampled, ctx->dDepWork, ctx->dDepSampled, ctx->dStateWork, ctx->dStateSampled, ctx->dIndicesList, ctx->dDirs, ctx->dRays,
                     ctx->dHits, ctx->dShadowQueue, ctx->dQueueCount, ctx->dShadowFlags, ctx->dIrrUnpacked, ctx->dDepUnpacked, ctx->dMissQueue, ctx->dFrontQueue, ctx->dFrontKeys, ctx->dFrontKeysOut, ctx->dFrontQueueSorted, ctx->dSortTemp, ctx->dIrrNext, ctx->dDepNext, ctx->dStateNext,
-                    ctx->dPerm, ctx->dOrder, ctx->dBlockedOrder, ctx->dBlendW, ctx->dPermList, ctx->dIota, ctx->dCellHist};
+                    ctx->dPerm, ctx->dOrder, ctx->dBlockedOrder, ctx->dBlendW, ctx->dPermList, ctx->dIota, ctx->dCellHist, ctx->dInvDirs, ctx->dOrigins};
     for (void* p : ptrs) if (p) cudaFree(p);
     ctx->dIrrWork = ctx->dIrrSampled = ctx->dDepWork = ctx->dDepSampled = ctx->dStateWork = ctx->dStateSampled = ctx->dIndicesList = nullptr;
     ctx->dIrrNext = ctx->dDepNext = ctx->dStateNext = nullptr;
     ctx->dPerm = ctx->dOrder = ctx->dBlockedOrder = ctx->dPermList = ctx->dIota = ctx->dCellHist = nullptr; ctx->dBlendW = nullptr; ctx->shardOrderReady = false;
-    ctx->dDirs = nullptr; ctx->dRays = nullptr; ctx->dHits = nullptr; ctx->dShadowQueue = nullptr; ctx->dQueueCount = nullptr; ctx->dShadowFlags = nullptr;
+    ctx->dDirs = nullptr; ctx->dInvDirs = nullptr; ctx->dOrigins = nullptr; ctx->dRays = nullptr; ctx->dHits = nullptr; ctx->dShadowQueue = nullptr; ctx->dQueueCount = nullptr; ctx->dShadowFlags = nullptr;
     ctx->dIrrUnpacked = ctx->dDepUnpacked = nullptr; ctx->dMissQueue = ctx->dFrontQueue = ctx->dFrontKeys = ctx->dFrontKeysOut = ctx->dFrontQueueSorted = nullptr; ctx->dSortTemp = nullptr; ctx->sortTempBytes = 0;
     if (ctx->hListStage) { cudaFreeHost(ctx->hListStage); ctx->hListStage = nullptr; }
     void* sched[] = {ctx->dSchedFlags, ctx->dSchedPos, ctx->dSchedSlotOf, ctx->dSchedResult, ctx->dSchedTemp};
@@ -217,12 +217,14 @@ static int checkGrid(vkx_ctx* ctx, const vkx_grid_info* g) {
 
 static int allocProbeScratch(vkx_ctx* ctx) {
     // ray-level scratch for one chunk of probes
-    void* old[] = {ctx->dRays, ctx->dHits, ctx->dShadowQueue, ctx->dShadowFlags, ctx->dIrrUnpacked, ctx->dDepUnpacked, ctx->dMissQueue, ctx->dFrontQueue, ctx->dFrontKeys, ctx->dFrontKeysOut, ctx->dFrontQueueSorted};
+    void* old[] = {ctx->dRays, ctx->dHits, ctx->dShadowQueue, ctx->dShadowFlags, ctx->dIrrUnpacked, ctx->dDepUnpacked, ctx->dMissQueue, ctx->dFrontQueue, ctx->dFrontKeys, ctx->dFrontKeysOut, ctx->dFrontQueueSorted, ctx->dOrigins};
     for (void* p : old) if (p) cudaFree(p);
+    ctx->dOrigins = nullptr;
     ctx->dMissQueue = ctx->dFrontQueue = ctx->dFrontKeys = ctx->dFrontKeysOut = ctx->dFrontQueueSorted = nullptr;
     ctx->dRays = nullptr; ctx->dHits = nullptr; ctx->dShadowQueue = nullptr; ctx->dShadowFlags = nullptr; ctx->dIrrUnpacked = ctx->dDepUnpacked = nullptr;
     const size_t maxRays = size_t(ctx->chunkProbes) * VKX_MAX_RAYS_PER_PROBE;
     CUDA_TRY(ctx, cudaMalloc(&ctx->dRays, maxRays * sizeof(float4)));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->dOrigins, size_t(ctx->chunkProbes) * sizeof(float4)));
     CUDA_TRY(ctx, cudaMalloc(&ctx->dHits, maxRays * sizeof(vkx_hit)));
     CUDA_TRY(ctx, cudaMalloc(&ctx->dShadowQueue, maxRays * 2 * sizeof(float4)));
     CUDA_TRY(ctx, cudaMalloc(&ctx->dMissQueue, maxRays * 4));
@@ -252,6 +254,7 @@ int vkx_probes_init(vkx_ctx* ctx, const vkx_grid_info* grid) {
     for (int i = 0; i < 6; ++i) { CUDA_TRY(ctx, cudaMalloc(bufs[i], sizes[i])); CUDA_TRY(ctx, cudaMemsetAsync(*bufs[i], 0, sizes[i], ctx->stream)); }
     CUDA_TRY(ctx, cudaMalloc(&ctx->dIndicesList, stBytes));
     CUDA_TRY(ctx, cudaMalloc(&ctx->dDirs, 512 * sizeof(float4)));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->dInvDirs, 512 * sizeof(float4)));
     CUDA_TRY(ctx, cudaMalloc(&ctx->dQueueCount, 32));
     CUDA_TRY(ctx, cudaMalloc(&ctx->dPerm, VKX_MAX_RAYS_PER_PROBE * 4));
     CUDA_TRY(ctx, cudaMalloc(&ctx->dOrder, stBytes));

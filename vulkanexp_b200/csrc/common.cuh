@@ -68,6 +68,8 @@ struct vkx_ctx {
     uint32_t *dIrrWork = nullptr, *dIrrSampled = nullptr, *dDepWork = nullptr, *dDepSampled = nullptr, *dStateWork = nullptr, *dStateSampled = nullptr;
     uint32_t* dIndicesList = nullptr;   // to-update list [probeCount]
     float4* dDirs = nullptr;            // rotated ray directions [512]
+    float4* dInvDirs = nullptr;         // per direction: reciprocal components + ray octant, the loop-invariant half of makeRay() [512]
+    float4* dOrigins = nullptr;         // per list slot of the current chunk: probe world position
     uint32_t* dPerm = nullptr;          // direction sort permutation of the frame [256]
     uint32_t* dOrder = nullptr;         // [probeCount] position -> slot of the to-update list (2x2x2 probe blocks)
     uint32_t* dBlockedOrder = nullptr;  // cached order for the full-volume list

@@ -25,20 +25,35 @@ struct TraceParams {
     uint32_t raysPerProbe, numRays; // numRays = chunk probes * raysPerProbe
 };
 
+// Loop-invariant halves of the ray set-up, tabulated once instead of once per ray: the reciprocal direction / octant of each of the
+// frame's directions (what makeRay() derives from a direction) and the world position of each probe of the chunk's list.
+__global__ void k_dir_table(uint32_t N, const float4* __restrict__ dirs, float4* __restrict__ invDirs) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float4 d = dirs[i];
+    const Ray r = makeRay(0.f, 0.f, 0.f, d.x, d.y, d.z);
+    invDirs[i] = make_float4(r.ix, r.iy, r.iz, __uint_as_float(r.oct));
+}
+__global__ void k_origin_table(vkx_grid_info grid, const uint32_t* __restrict__ probeIndices, uint32_t n, float4* __restrict__ origins) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    int ix, iy, iz; probeGridIndex(__ldg(probeIndices + s), grid, ix, iy, iz);
+    const v3 o = probeWorldPos(ix, iy, iz, grid);
+    origins[s] = make_float4(o.x, o.y, o.z, 0.0f);
+}
+
 // Rays are sorted by what they need next when their traversal ends: misses -> sky queue, front-face hits -> shading queue,
 // back-face hits are final (closesthit.glsl:137-141) and written here. The two shading kernels then run on dense queues.
 struct PrimarySrc {
-    TraceParams tp; RayMap rm; const uint32_t* probeIndices; const float4* dirs; vkx_hit* hits;
+    TraceParams tp; RayMap rm; const float4* origins; const float4* dirs; const float4* invDirs; vkx_hit* hits;
     float4* rays; uint32_t* missQueue; uint32_t* frontQueue; uint32_t* counters; // counters[3] misses, counters[4] front hits
     uint32_t ri;
     __device__ __forceinline__ bool load(uint32_t item, Ray& r, float& tmin, float& tmax, uint32_t& cullMask) {
         uint32_t slot, ray;
         if (!mapRay(rm, item, slot, ray)) return false;
         ri = slot * tp.raysPerProbe + ray;
-        int ix, iy, iz; probeGridIndex(__ldg(probeIndices + slot), tp.grid, ix, iy, iz);
-        const v3 o = probeWorldPos(ix, iy, iz, tp.grid);
-        const float4 d = __ldg(dirs + ray);
-        r = makeRay(o.x, o.y, o.z, d.x, d.y, d.z);
+        const float4 o = __ldg(origins + slot), d = __ldg(dirs + ray), id = __ldg(invDirs + ray);
+        r.ox = o.x; r.oy = o.y; r.oz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z; r.ix = id.x; r.iy = id.y; r.iz = id.z; r.oct = __float_as_uint(id.w);
         tmin = tp.tmin; tmax = tp.tmax; cullMask = VKX_INSTANCE_STATIC | VKX_INSTANCE_DYNAMIC;
         return true;
     }
@@ -53,14 +68,13 @@ struct PrimarySrc {
 
 // Sort key of a front hit = grid cell of the hit point (scheduling only: rays that shade from the same 8 probes end up in the same
 // warps of k_shade_front, and their shadow rays start close together).
-__global__ void k_front_keys(TraceParams tp, const uint32_t* __restrict__ probeIndices, const float4* __restrict__ dirs, const vkx_hit* __restrict__ hits,
+__global__ void k_front_keys(TraceParams tp, const float4* __restrict__ origins, const float4* __restrict__ dirs, const vkx_hit* __restrict__ hits,
                              const uint32_t* __restrict__ frontQueue, const uint32_t* __restrict__ counters, uint32_t* __restrict__ keys) {
     const uint32_t n = counters[4];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t ri = frontQueue[i];
         const uint32_t slot = ri / tp.raysPerProbe, ray = ri - slot * tp.raysPerProbe;
-        int ix, iy, iz; probeGridIndex(__ldg(probeIndices + slot), tp.grid, ix, iy, iz);
-        const v3 o = probeWorldPos(ix, iy, iz, tp.grid);
+        const float4 o = __ldg(origins + slot);
         const float4 d = __ldg(dirs + ray);
         const float t = hits[ri].t;
         const int cx = min(max(int((o.x + d.x * t - tp.grid.extentMin[0]) * tp.invCell[0]), 0), tp.grid.resolution[0] - 1);
@@ -71,10 +85,10 @@ __global__ void k_front_keys(TraceParams tp, const uint32_t* __restrict__ probeI
 }
 
 // Persistent warps; see ptrace.cuh.
-__global__ void __launch_bounds__(128, 8) k_trace_primary(DeviceScene sc, TraceParams tp, RayMap rm, const uint32_t* __restrict__ probeIndices,
-                                                       const float4* __restrict__ dirs, vkx_hit* __restrict__ hits, float4* __restrict__ rays,
+__global__ void __launch_bounds__(128, 8) k_trace_primary(DeviceScene sc, TraceParams tp, RayMap rm, const float4* __restrict__ origins,
+                                                       const float4* __restrict__ dirs, const float4* __restrict__ invDirs, vkx_hit* __restrict__ hits, float4* __restrict__ rays,
                                                        uint32_t* __restrict__ missQueue, uint32_t* __restrict__ frontQueue, uint32_t* __restrict__ counters) {
-    PrimarySrc src; src.tp = tp; src.rm = rm; src.probeIndices = probeIndices; src.dirs = dirs; src.hits = hits; src.ri = 0;
+    PrimarySrc src; src.tp = tp; src.rm = rm; src.origins = origins; src.dirs = dirs; src.invDirs = invDirs; src.hits = hits; src.ri = 0;
     src.rays = rays; src.missQueue = missQueue; src.frontQueue = frontQueue; src.counters = counters;
     persistentTrace<false>(sc.nodes, sc.tris, src, rm.numThreads, counters + 1);
 }
@@ -418,6 +432,7 @@ int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* /*unused*/,
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
     k_blend_weights<<<(N + 3u) & ~3u, BLEND_COLS, 0, st>>>(ctx->grid.depthSharpness, N, ctx->dDirs, ctx->dBlendW); LAUNCH_CHECK(ctx);
     k_blend_weight_sums<<<1, BLEND_COLS, 0, st>>>(N, ctx->dBlendW); LAUNCH_CHECK(ctx);
+    k_dir_table<<<divUp(N, 128), 128, 0, st>>>(N, ctx->dDirs, ctx->dInvDirs); LAUNCH_CHECK(ctx);
     // One chunk: slots are the caller's list positions (ray/hit buffers are laid out [slot][ray]) and `order` only schedules them.
     // Several chunks: the list is first gathered in block order, a chunk is then a contiguous piece of it with identity order.
     const bool multi = count > ctx->chunkProbes;
@@ -428,24 +443,26 @@ int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* /*unused*/,
         const uint32_t* idx = multi ? ctx->dPermList + base : ctx->dIndicesList + listOffset;
         RayMap rm; rm.count = n; rm.raysPerProbe = N; rm.numDirGroups = (N + 3u) / 4u; rm.order = multi ? ctx->dIota : ctx->dOrder + listOffset; rm.perm = ctx->dPerm;
         rm.numThreads = ((n + 7u) / 8u) * rm.numDirGroups * 32u;
+        rm.dgShift = 0xFFFFFFFFu; for (uint32_t b = 0; b < 31; ++b) if ((1u << b) == rm.numDirGroups) rm.dgShift = b;
         TraceParams tp; tp.grid = ctx->grid; tp.tmin = 0.01f; tp.tmax = tmax; tp.raysPerProbe = N; tp.numRays = numRays;
         tp.invCell[0] = 1.0f / cx; tp.invCell[1] = 1.0f / cy; tp.invCell[2] = 1.0f / cz;
         ShadeParams sp; sp.grid = ctx->grid; sp.light = light; sp.raysPerProbe = N; sp.numRays = numRays;
         const bool timed = base == 0; // per-kernel events on the first chunk
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->dQueueCount, 0, 32, st)); // [0] shadow queue length, [1] primary work counter, [2] shadow work counter, [3] misses, [4] front hits
+        k_origin_table<<<divUp(n, 128), 128, 0, st>>>(ctx->grid, idx, n, ctx->dOrigins); LAUNCH_CHECK(ctx);
         if (timed) { CUDA_TRY(ctx, cudaEventRecord(ctx->kev[0], st)); ctx->kevProbes = n; }
-        k_trace_primary<<<persistentBlocks, 128, 0, st>>>(sc, tp, rm, idx, ctx->dDirs, ctx->dHits, ctx->dRays, ctx->dMissQueue, ctx->dFrontQueue, ctx->dQueueCount); LAUNCH_CHECK(ctx);
+        k_trace_primary<<<persistentBlocks, 128, 0, st>>>(sc, tp, rm, ctx->dOrigins, ctx->dDirs, ctx->dInvDirs, ctx->dHits, ctx->dRays, ctx->dMissQueue, ctx->dFrontQueue, ctx->dQueueCount); LAUNCH_CHECK(ctx);
         if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[1], st));
         // The sky kernel only needs the miss queue: it runs on a second stream, concurrently with the sort and the front-hit shading.
         const unsigned shadeBlocks = std::min<unsigned>(divUp(numRays, 128), unsigned(ctx->smCount) * 16u);
         CUDA_TRY(ctx, cudaEventRecord(ctx->auxEvent[0], st));
         CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->auxStream, ctx->auxEvent[0], 0));
-        launchShadeMiss(shadeBlocks, ctx->auxStream, sp, idx, ctx->dDirs, ctx->dMissQueue, ctx->dQueueCount, ctx->dRays); LAUNCH_CHECK(ctx);
+        launchShadeMiss(shadeBlocks, ctx->auxStream, sp, ctx->dOrigins, ctx->dDirs, ctx->dMissQueue, ctx->dQueueCount, ctx->dRays); LAUNCH_CHECK(ctx);
         CUDA_TRY(ctx, cudaEventRecord(ctx->auxEvent[1], ctx->auxStream));
         { // front-hit queue sorted by grid cell (radix sort over just the bits a cell index needs; unused slots carry all-ones keys).
           // A counting sort with a per-cell atomic histogram was slower: hit points cluster in few cells.
             CUDA_TRY(ctx, cudaMemsetAsync(ctx->dFrontKeys, 0xFF, size_t(numRays) * 4, st));
-            k_front_keys<<<std::min<unsigned>(divUp(numRays, 256), unsigned(ctx->smCount) * 8u), 256, 0, st>>>(tp, idx, ctx->dDirs, ctx->dHits, ctx->dFrontQueue, ctx->dQueueCount, ctx->dFrontKeys); LAUNCH_CHECK(ctx);
+            k_front_keys<<<std::min<unsigned>(divUp(numRays, 256), unsigned(ctx->smCount) * 8u), 256, 0, st>>>(tp, ctx->dOrigins, ctx->dDirs, ctx->dHits, ctx->dFrontQueue, ctx->dQueueCount, ctx->dFrontKeys); LAUNCH_CHECK(ctx);
             uint32_t cells = ctx->probeCount, bits = 1; while ((1u << bits) <= cells) ++bits;
             size_t need = 0;
             cub::DeviceRadixSort::SortPairs(nullptr, need, ctx->dFrontKeys, ctx->dFrontKeysOut, ctx->dFrontQueue, ctx->dFrontQueueSorted, int(numRays), 0, int(bits), st);
@@ -454,7 +471,7 @@ int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* /*unused*/,
             ctx->launches += 3;
         }
         { int rc = waitGather(ctx); if (rc != VKX_OK) return rc; } // sharded path: the previous frame's atlas all-gather must have landed
-        launchShadeFront(shadeBlocks, st, sc, pr, sp, idx, ctx->dDirs, ctx->dHits, ctx->dFrontQueueSorted, ctx->dQueueCount, ctx->dRays, ctx->dShadowQueue); LAUNCH_CHECK(ctx);
+        launchShadeFront(shadeBlocks, st, sc, pr, sp, ctx->dOrigins, ctx->dDirs, ctx->dHits, ctx->dFrontQueueSorted, ctx->dQueueCount, ctx->dRays, ctx->dShadowQueue); LAUNCH_CHECK(ctx);
         if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[2], st));
         if (ctx->debugBuffers) CUDA_TRY(ctx, cudaMemsetAsync(ctx->dShadowFlags, 0, numRays, st));
         k_trace_shadow<<<persistentBlocks, 128, 0, st>>>(sc, light, ctx->dShadowQueue, ctx->dQueueCount, ctx->dRays, ctx->debugBuffers ? ctx->dShadowFlags : nullptr, ctx->dQueueCount + 2); LAUNCH_CHECK(ctx);

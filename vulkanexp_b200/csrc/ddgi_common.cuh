@@ -9,12 +9,13 @@
 // the mapping changes scheduling only.
 struct RayMap {
     uint32_t count, raysPerProbe, numDirGroups, numThreads;
+    uint32_t dgShift;      // log2(numDirGroups) if it is a power of two (256 rays -> 64 groups), else 0xFFFFFFFF
     const uint32_t* order; // [count] position -> slot
     const uint32_t* perm;  // [raysPerProbe] position -> ray index
 };
 __device__ __forceinline__ bool mapRay(const RayMap& m, uint32_t t, uint32_t& slot, uint32_t& ray) {
     const uint32_t tile = t >> 5, lane = t & 31u;
-    const uint32_t pg = tile / m.numDirGroups, dg = tile - pg * m.numDirGroups;
+    const uint32_t pg = m.dgShift != 0xFFFFFFFFu ? tile >> m.dgShift : tile / m.numDirGroups, dg = tile - pg * m.numDirGroups;
     const uint32_t j = pg * 8u + (lane & 7u), k = dg * 4u + (lane >> 3);
     if (j >= m.count || k >= m.raysPerProbe) return false;
     slot = __ldg(m.order + j); ray = __ldg(m.perm + k);
@@ -36,7 +37,7 @@ struct ShadeParams {
     uint32_t raysPerProbe, numRays;
 };
 
-void launchShadeMiss(unsigned blocks, cudaStream_t st, const ShadeParams& sp, const uint32_t* probeIndices, const float4* dirs, const uint32_t* missQueue,
+void launchShadeMiss(unsigned blocks, cudaStream_t st, const ShadeParams& sp, const float4* origins, const float4* dirs, const uint32_t* missQueue,
                      const uint32_t* counters, float4* rays);
-void launchShadeFront(unsigned blocks, cudaStream_t st, const DeviceScene& sc, const DeviceProbes& pr, const ShadeParams& sp, const uint32_t* probeIndices,
+void launchShadeFront(unsigned blocks, cudaStream_t st, const DeviceScene& sc, const DeviceProbes& pr, const ShadeParams& sp, const float4* origins,
                       const float4* dirs, const vkx_hit* hits, const uint32_t* frontQueue, uint32_t* counters, float4* rays, float4* shadowQueue);

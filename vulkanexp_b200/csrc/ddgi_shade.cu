@@ -10,14 +10,14 @@
 namespace {
 
 // miss.rmiss + sky.glsl over the dense miss queue
-__global__ void __launch_bounds__(128) k_shade_miss(ShadeParams sp, const uint32_t* __restrict__ probeIndices, const float4* __restrict__ dirs,
+__global__ void __launch_bounds__(128) k_shade_miss(ShadeParams sp, const float4* __restrict__ origins, const float4* __restrict__ dirs,
                                                     const uint32_t* __restrict__ queue, const uint32_t* __restrict__ counters, float4* __restrict__ rays) {
     const uint32_t n = counters[3];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t ri = queue[i];
         const uint32_t slot = ri / sp.raysPerProbe, ray = ri - slot * sp.raysPerProbe;
-        int ix, iy, iz; probeGridIndex(__ldg(probeIndices + slot), sp.grid, ix, iy, iz);
-        const v3 origin = probeWorldPosExact(ix, iy, iz, sp.grid);
+        const float4 o4 = __ldg(origins + slot);
+        const v3 origin = mk3(o4.x, o4.y, o4.z);
         const float4 d4 = __ldg(dirs + ray);
         const v3 c = skyColor(origin, mk3(d4.x, d4.y, d4.z), mk3(sp.light.direction[0], sp.light.direction[1], sp.light.direction[2]),
                               mk3(sp.light.color[0], sp.light.color[1], sp.light.color[2]), sp.light.color[3]);
@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(128) k_shade_miss(ShadeParams sp, const uint32
 }
 
 // closesthit.glsl:143-288 (NO_REFLECTION, untextured) over the dense front-hit queue; appends the shadow rays
-__global__ void __launch_bounds__(128, 6) k_shade_front(DeviceScene sc, DeviceProbes pr, ShadeParams sp, const uint32_t* __restrict__ probeIndices,
+__global__ void __launch_bounds__(128, 6) k_shade_front(DeviceScene sc, DeviceProbes pr, ShadeParams sp, const float4* __restrict__ origins,
                                                      const float4* __restrict__ dirs, const vkx_hit* __restrict__ hits, const uint32_t* __restrict__ frontQueue,
                                                      uint32_t* __restrict__ counters, float4* __restrict__ rays, float4* __restrict__ queue) {
     const uint32_t n = counters[4];
@@ -36,8 +36,8 @@ __global__ void __launch_bounds__(128, 6) k_shade_front(DeviceScene sc, DevicePr
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t ri = frontQueue[i];
         const uint32_t slot = ri / sp.raysPerProbe, ray = ri - slot * sp.raysPerProbe;
-        int ix, iy, iz; probeGridIndex(__ldg(probeIndices + slot), sp.grid, ix, iy, iz);
-        const v3 origin = probeWorldPosExact(ix, iy, iz, sp.grid);
+        const float4 o4 = __ldg(origins + slot);
+        const v3 origin = mk3(o4.x, o4.y, o4.z);
         const float4 d4 = __ldg(dirs + ray);
         const v3 direction = mk3(d4.x, d4.y, d4.z);
         const vkx_hit h = hits[ri];
@@ -53,11 +53,11 @@ __global__ void __launch_bounds__(128, 6) k_shade_front(DeviceScene sc, DevicePr
 
 } // namespace
 
-void launchShadeMiss(unsigned blocks, cudaStream_t st, const ShadeParams& sp, const uint32_t* probeIndices, const float4* dirs, const uint32_t* missQueue,
+void launchShadeMiss(unsigned blocks, cudaStream_t st, const ShadeParams& sp, const float4* origins, const float4* dirs, const uint32_t* missQueue,
                      const uint32_t* counters, float4* rays) {
-    k_shade_miss<<<blocks, 128, 0, st>>>(sp, probeIndices, dirs, missQueue, counters, rays);
+    k_shade_miss<<<blocks, 128, 0, st>>>(sp, origins, dirs, missQueue, counters, rays);
 }
-void launchShadeFront(unsigned blocks, cudaStream_t st, const DeviceScene& sc, const DeviceProbes& pr, const ShadeParams& sp, const uint32_t* probeIndices,
+void launchShadeFront(unsigned blocks, cudaStream_t st, const DeviceScene& sc, const DeviceProbes& pr, const ShadeParams& sp, const float4* origins,
                       const float4* dirs, const vkx_hit* hits, const uint32_t* frontQueue, uint32_t* counters, float4* rays, float4* shadowQueue) {
-    k_shade_front<<<blocks, 128, 0, st>>>(sc, pr, sp, probeIndices, dirs, hits, frontQueue, counters, rays, shadowQueue);
+    k_shade_front<<<blocks, 128, 0, st>>>(sc, pr, sp, origins, dirs, hits, frontQueue, counters, rays, shadowQueue);
 }
