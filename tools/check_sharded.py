@@ -35,6 +35,26 @@ for frame in range(4):
     same = all(np.array_equal(x, y) for x, y in zip(a[:3], b[:3]))
     ok &= same
     print("rank %d frame %d: sharded == single-GPU: %s (sharded %.3f ms, single %.3f ms)" % (rank, frame, same, ctx.probes_timings()["full"], ref.probes_timings()["full"]), flush=True)
+# own-slab read-back queued right behind a sharded update (it reads the rank's work atlases and does not wait for the all-gather):
+# must equal the same rows of the single-GPU atlases, frame after frame, with the next update already queued
+(ih, iw), (dh, dw) = grid.atlas_shapes()
+z0, z1 = rank * (res[2] // world), (rank + 1) * (res[2] // world)
+bufs = [(np.zeros((ih // world, iw), np.uint32), np.zeros((dh // world, dw), np.uint32), np.zeros(grid.probe_count // world, np.uint32)) for _ in range(2)]
+for frame in range(4, 8):
+    R = gen.next()
+    ctx.probes_update_sharded(grid, light, R, sync=False)
+    ctx.probes_download_slab_async(z0, z1, bufs[frame & 1])
+    ref.probes_update(grid, light, R, None)
+    ctx.probes_download_wait()
+    b = ref.probes_download()
+    got = bufs[frame & 1]
+    same = np.array_equal(got[0], b[0][8 * z0:8 * z1]) and np.array_equal(got[1], b[1][16 * z0:16 * z1]) and np.array_equal(got[2], b[2][z0 * res[0] * res[1]:z1 * res[0] * res[1]])
+    ok &= same
+    print("rank %d frame %d: async own-slab read-back == single-GPU rows: %s" % (rank, frame, same), flush=True)
+a, b = ctx.probes_download(), ref.probes_download()
+same = all(np.array_equal(x, y) for x, y in zip(a[:3], b[:3]))
+ok &= same
+print("rank %d: full atlases after the async frames equal: %s" % (rank, same), flush=True)
 t = torch.tensor([0 if ok else 1], device="cuda")
 dist.all_reduce(t)
 dist.destroy_process_group()

@@ -498,28 +498,35 @@ int vkx_probes_download_async(vkx_ctx* ctx, uint32_t* irradiance, uint32_t* dept
     if (depth) CUDA_TRY(ctx, cudaMemcpyAsync(depth, ctx->dDepSampled, size_t(ctx->depW) * ctx->depH * 4, cudaMemcpyDeviceToHost, ctx->copyStream));
     if (state) CUDA_TRY(ctx, cudaMemcpyAsync(state, ctx->dStateSampled, size_t(ctx->probeCount) * 4, cudaMemcpyDeviceToHost, ctx->copyStream));
     CUDA_TRY(ctx, cudaEventRecord(ctx->evCopyDone, ctx->copyStream));
-    ctx->copyPending = true;
+    ctx->copyPending = true; ctx->copyReadsWork = false;
     return VKX_OK;
 }
 /* Same for the z-slices [z0, z1) only (contiguous atlas rows [8*z0, 8*z1) / [16*z0, 16*z1) and state words): what one rank of a sharded
  * run owns. Destination pointers address the first copied row. */
 int vkx_probes_download_slab_async(vkx_ctx* ctx, uint32_t z0, uint32_t z1, uint32_t* irradiance, uint32_t* depth, uint32_t* state) {
     BIND(ctx);
-    TRY(waitGather(ctx));
     if (!ctx->probesReady || z0 >= z1 || z1 > uint32_t(ctx->grid.resolution[2])) return vkx_fail(ctx, VKX_E_INVALID, "vkx_probes_download_slab_async: bad slab");
+    // After a sharded update the rank's own slab is complete in its work atlases as soon as its blend has run: reading it from there
+    // does not have to wait for the all-gather, which stays hidden behind the next frame's traversal. Any other slab comes from the
+    // sampled atlases and needs the gather.
+    const uint32_t own = ctx->nranks > 1 ? uint32_t(ctx->grid.resolution[2]) / uint32_t(ctx->nranks) : 0u;
+    const bool fromWork = ctx->shardedLast && ctx->gatherPending && own && z0 >= uint32_t(ctx->rank) * own && z1 <= uint32_t(ctx->rank + 1) * own;
+    if (!fromWork) TRY(waitGather(ctx));
     if (!ctx->copyStream) {
         CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
         CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->evPublished, cudaEventDisableTiming));
         CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->evCopyDone, cudaEventDisableTiming));
     }
     const size_t plane = size_t(ctx->grid.resolution[0]) * size_t(ctx->grid.resolution[1]), nz = z1 - z0;
+    const uint32_t* irrSrc = fromWork ? ctx->dIrrWork : ctx->dIrrSampled; const uint32_t* depSrc = fromWork ? ctx->dDepWork : ctx->dDepSampled;
+    const uint32_t* stSrc = fromWork ? ctx->dStateWork : ctx->dStateSampled;
     CUDA_TRY(ctx, cudaEventRecord(ctx->evPublished, ctx->stream));
     CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copyStream, ctx->evPublished, 0));
-    if (irradiance) CUDA_TRY(ctx, cudaMemcpyAsync(irradiance, ctx->dIrrSampled + size_t(8 * z0) * ctx->irrW, size_t(8 * nz) * ctx->irrW * 4, cudaMemcpyDeviceToHost, ctx->copyStream));
-    if (depth) CUDA_TRY(ctx, cudaMemcpyAsync(depth, ctx->dDepSampled + size_t(16 * z0) * ctx->depW, size_t(16 * nz) * ctx->depW * 4, cudaMemcpyDeviceToHost, ctx->copyStream));
-    if (state) CUDA_TRY(ctx, cudaMemcpyAsync(state, ctx->dStateSampled + size_t(z0) * plane, nz * plane * 4, cudaMemcpyDeviceToHost, ctx->copyStream));
+    if (irradiance) CUDA_TRY(ctx, cudaMemcpyAsync(irradiance, irrSrc + size_t(8 * z0) * ctx->irrW, size_t(8 * nz) * ctx->irrW * 4, cudaMemcpyDeviceToHost, ctx->copyStream));
+    if (depth) CUDA_TRY(ctx, cudaMemcpyAsync(depth, depSrc + size_t(16 * z0) * ctx->depW, size_t(16 * nz) * ctx->depW * 4, cudaMemcpyDeviceToHost, ctx->copyStream));
+    if (state) CUDA_TRY(ctx, cudaMemcpyAsync(state, stSrc + size_t(z0) * plane, nz * plane * 4, cudaMemcpyDeviceToHost, ctx->copyStream));
     CUDA_TRY(ctx, cudaEventRecord(ctx->evCopyDone, ctx->copyStream));
-    ctx->copyPending = true;
+    ctx->copyPending = true; ctx->copyReadsWork = fromWork;
     return VKX_OK;
 }
 int vkx_probes_download_wait(vkx_ctx* ctx) {
@@ -640,7 +647,7 @@ int vkx_probes_update_sharded(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx
     const uint32_t K = 1, s = slicesPerRank / K;
     ncclComm_t comm = reinterpret_cast<ncclComm_t>(ctx->comm);
     cudaStream_t st = ctx->stream, cs = ctx->commStream;
-    if (ctx->copyPending) { CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->commStream, ctx->evCopyDone, 0)); ctx->copyPending = false; } // read-back of the buffers about to be overwritten
+    if (ctx->copyPending && !ctx->copyReadsWork) { CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->commStream, ctx->evCopyDone, 0)); ctx->copyPending = false; } // read-back of the buffers about to be overwritten
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], st));
     uint32_t total = 0;
     for (uint32_t k = 0; k < K; ++k) {

@@ -98,7 +98,7 @@ struct vkx_ctx {
     cudaStream_t auxStream = nullptr; cudaEvent_t auxEvent[2] = {nullptr, nullptr}; // second stream of the update (sky kernel)
 
     // asynchronous read-back (vkx_probes_download_async)
-    cudaStream_t copyStream = nullptr; cudaEvent_t evPublished = nullptr, evCopyDone = nullptr; bool copyPending = false;
+    cudaStream_t copyStream = nullptr; cudaEvent_t evPublished = nullptr, evCopyDone = nullptr; bool copyPending = false, copyReadsWork = false; // copyReadsWork: the queued read-back reads the work atlases (own slab of a sharded update)
 
     // on-device scheduler (schedule.cu); the two counters are the reference's s_LoopIndex / _lastUpdateOffset
     uint32_t *dSchedFlags = nullptr, *dSchedPos = nullptr, *dSchedSlotOf = nullptr, *dSchedResult = nullptr, *hSchedResult = nullptr; void* dSchedTemp = nullptr; size_t schedTempBytes = 0;

@@ -479,6 +479,7 @@ int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* /*unused*/,
         if (base + n >= count) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], st));
         bp.count = n;
         CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->auxEvent[1], 0)); // sky results
+        if (ctx->copyPending && ctx->copyReadsWork) { CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->evCopyDone, 0)); ctx->copyPending = false; ctx->copyReadsWork = false; } // a queued read-back still reads the work atlases
         k_blend<<<divUp(n, BLEND_P), BLEND_THREADS, BLEND_SMEM_BYTES, st>>>(bp, pr, idx, ctx->dRays, ctx->dBlendW, ctx->debugBuffers ? ctx->dIrrUnpacked : nullptr, ctx->debugBuffers ? ctx->dDepUnpacked : nullptr, base); LAUNCH_CHECK(ctx);
         if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[4], st));
     }
