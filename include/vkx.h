@@ -143,6 +143,11 @@ int vkx_scene_upload(vkx_ctx* ctx, const vkx_vertex* vertices, size_t numVertice
                      size_t numMeshes, const vkx_material* materials, size_t numMaterials,
                      const vkx_instance* instances, size_t numInstances);
 
+/* Dynamic instances: Renderer::updateAccelerationStructureInstances + updateTLAS (src/Renderer.cpp:671-742, called from
+ * onHierarchicalChanges). New transforms / masks / ids for the instance list of vkx_scene_upload (same count, same meshes). The
+ * reference refits its TLAS in place; here all instanced geometry lives in one world-space BVH, so the structure is marked stale
+ * and the next vkx_bvh_build rebuilds it (the same deterministic build: the result equals a fresh upload with these transforms). */
+int vkx_instances_update(vkx_ctx* ctx, const vkx_instance* instances, size_t numInstances);
 /* Deterministic binned-SAH build of the 8-wide compressed BVH on the device (replaces the driver's BLAS/TLAS
  * build, src/Renderer.cpp:272-449,525-642). Topology is bit-identical to oracle/bvh.cpp. */
 int vkx_bvh_build(vkx_ctx* ctx);

@@ -69,3 +69,48 @@ def test_cull_mask_and_empty_scene(oracle_lib):
     g2 = Context(0); g2.scene_upload(empty); g2.bvh_build()
     assert g2.bvh_info().numNodes == 1
     assert (g2.trace(org[:100], d[:100], 0.01, 100.0)["t"] < 0).all()
+
+
+def test_instances_update_equals_fresh_upload(oracle_lib):
+    """Dynamic instances (Renderer::updateAccelerationStructureInstances + updateTLAS): new transforms + rebuild must give exactly the
+    structure a fresh upload with those transforms gives - on the GPU and in the oracle - and the next probe update must agree."""
+    import copy
+    from conftest import get_scene
+    from vulkanexp_b200._lib import Context, VkxError
+    from vulkanexp_b200.pods import GridInfo, Light
+
+    flat = get_scene("cfg1")
+    moved = dict(flat)
+    inst = flat["instances"].copy()
+    assert len(inst) > 3
+    rng = np.random.default_rng(3)
+    for k in range(1, len(inst)):  # translate + rotate about y every instance but the room
+        ang = float(rng.uniform(0, 2 * np.pi)); c, s = np.float32(np.cos(ang)), np.float32(np.sin(ang))
+        M = inst[k]["transform"].reshape(3, 4).copy()  # row-major 3x4 (VkTransformMatrixKHR)
+        R = np.eye(3, dtype=np.float32); R[0, 0] = c; R[0, 2] = s; R[2, 0] = -s; R[2, 2] = c
+        M = (R @ M).astype(np.float32)
+        M[0, 3] += np.float32(rng.uniform(-0.8, 0.8)); M[1, 3] += np.float32(rng.uniform(0.0, 0.5)); M[2, 3] += np.float32(rng.uniform(-0.8, 0.8))
+        inst[k]["transform"] = M.reshape(-1)
+    moved["instances"] = inst
+    a = Context(0); a.scene_upload(flat); a.bvh_build()
+    before = a.bvh_download()[0].tobytes()
+    a.instances_update(inst)
+    with pytest.raises(VkxError):
+        a.trace(np.zeros((1, 3), np.float32), np.array([[0, 0, 1]], np.float32), 0.0, 10.0)  # stale structure: must be rebuilt first
+    a.bvh_build()
+    b = Context(0); b.scene_upload(moved); b.bvh_build()
+    o = oracle_lib.Oracle(); o.scene_upload(moved); o.bvh_build()
+    na, ta = a.bvh_download(); nb, tb = b.bvh_download(); no, to = o.bvh_download()
+    assert na.tobytes() != before, "the move must change the structure"
+    assert na.tobytes() == nb.tobytes() == no.tobytes() and ta.tobytes() == tb.tobytes() == to.tobytes()
+    grid = GridInfo.make(flat["bounds_min"], flat["bounds_max"], (6, 6, 6), 32)
+    R, _ = oracle_lib.HostLogic().next_orientation()
+    outs = []
+    for g in (a, b):
+        g.probes_init(grid); g.probes_upload(state=np.ones(grid.probe_count, dtype=np.uint32)); g.probes_update(grid, Light.default(), R)
+        outs.append(g.probes_download())
+    assert all(np.array_equal(x, y) for x, y in zip(outs[0][:3], outs[1][:3]))
+    bad = inst.copy(); bad[1]["meshEntry"] = bad[0]["meshEntry"]
+    if bad[1]["meshEntry"] != inst[1]["meshEntry"]:
+        with pytest.raises(VkxError):
+            a.instances_update(bad)

@@ -84,6 +84,10 @@ class Context:
             self.l.vkx_scene_upload(self.h, _p(v), C.c_size_t(len(v)), _p(i), C.c_size_t(len(i)), _p(o), _p(c), C.c_size_t(len(o)), _p(m), C.c_size_t(len(m)), _p(inst), C.c_size_t(len(inst)))
         )
 
+    def instances_update(self, instances):
+        inst = np.ascontiguousarray(instances)
+        self._check(self.l.vkx_instances_update(self.h, _p(inst), C.c_size_t(len(inst))))
+
     def bvh_build(self):
         self._check(self.l.vkx_bvh_build(self.h))
 

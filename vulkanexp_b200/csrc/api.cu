@@ -179,6 +179,32 @@ int vkx_scene_upload(vkx_ctx* ctx, const vkx_vertex* vertices, size_t numVertice
     return VKX_OK;
 }
 
+int vkx_instances_update(vkx_ctx* ctx, const vkx_instance* instances, size_t numInstances) {
+    BIND(ctx);
+    if (!instances || numInstances != ctx->numInstances) return vkx_fail(ctx, VKX_E_INVALID, "vkx_instances_update: expected %zu instances (same list as vkx_scene_upload)", ctx->numInstances);
+    std::vector<vkx_instance> cur(numInstances);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpy(cur.data(), ctx->dInstances, numInstances * sizeof(vkx_instance), cudaMemcpyDeviceToHost));
+    std::vector<float> w2o(numInstances * 9);
+    for (size_t k = 0; k < numInstances; ++k) {
+        if (instances[k].meshEntry != cur[k].meshEntry) return vkx_fail(ctx, VKX_E_INVALID, "vkx_instances_update: instance %zu changed its mesh (only transforms, masks and ids may change)", k);
+        for (int q = 0; q < 12; ++q) if (!std::isfinite(instances[k].transform[q])) return vkx_fail(ctx, VKX_E_INVALID, "instance %zu has a non-finite transform", k);
+        const float* M = instances[k].transform; // inverse of the 3x3 part, same arithmetic as vkx_scene_upload
+        float a = M[0], b = M[1], c = M[2], d = M[4], e = M[5], f = M[6], g = M[8], h = M[9], i = M[10];
+        float A = e * i - f * h, B = -(d * i - f * g), C = d * h - e * g;
+        float det = a * A + b * B + c * C;
+        float id = 1.0f / det;
+        float* W = &w2o[k * 9];
+        W[0] = A * id; W[1] = -(b * i - c * h) * id; W[2] = (b * f - c * e) * id;
+        W[3] = B * id; W[4] = (a * i - c * g) * id;  W[5] = -(a * f - c * d) * id;
+        W[6] = C * id; W[7] = -(a * h - b * g) * id; W[8] = (a * e - b * d) * id;
+    }
+    CUDA_TRY(ctx, cudaMemcpy(ctx->dInstances, instances, numInstances * sizeof(vkx_instance), cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(ctx->dWorldToObject, w2o.data(), w2o.size() * 4, cudaMemcpyHostToDevice));
+    ctx->bvhBuilt = false; // the flattened world-space BVH is stale: vkx_bvh_build rebuilds it (deterministic, same spec as the first build)
+    return VKX_OK;
+}
+
 int vkx_bvh_build(vkx_ctx* ctx) { BIND(ctx); return bvhBuildDevice(ctx); }
 
 int vkx_bvh_info_get(vkx_ctx* ctx, vkx_bvh_info* out) {

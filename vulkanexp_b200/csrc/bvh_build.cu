@@ -102,26 +102,38 @@ __global__ void k_init_bins(BinArrays bins, uint32_t numActive) {
     k[3] = k[4] = k[5] = 0u;          // max keys
 }
 
+// Atomics are pre-reduced inside the warp: primitives are stored node by node, so near the root all 32 lanes of a warp target the
+// same bin / child entry and one lane issues the atomics for the group (min / max / count are order-independent: same result).
 __global__ void k_bin(const uint32_t* __restrict__ prim, const int* __restrict__ nodeOf, uint32_t T, ActiveArrays act, BinArrays bins,
                       const float* __restrict__ lo, const float* __restrict__ hi, const float* __restrict__ cent) {
-    uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos >= T) return;
-    int a = nodeOf[pos];
-    if (a < 0) return;
-    uint32_t g = prim[pos];
-    const float* cb = act.cbox + size_t(a) * 6;
-    uint32_t kl[3], kh[3];
-    for (int ax = 0; ax < 3; ++ax) { kl[ax] = okey(lo[3 * size_t(g) + ax]); kh[ax] = okey(hi[3 * size_t(g) + ax]); }
+    const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    const int a = pos < T ? nodeOf[pos] : -1;
+    const bool valid = a >= 0;
+    uint32_t g = 0, kl[3] = {0, 0, 0}, kh[3] = {0, 0, 0};
+    const float* cb = act.cbox + size_t(valid ? a : 0) * 6;
+    if (valid) {
+        g = prim[pos];
+        for (int ax = 0; ax < 3; ++ax) { kl[ax] = okey(lo[3 * size_t(g) + ax]); kh[ax] = okey(hi[3 * size_t(g) + ax]); }
+    }
     for (int ax = 0; ax < 3; ++ax) {
-        float ext = cb[3 + ax] - cb[ax];
-        if (!(ext > 0.0f)) continue;
-        float k = float(NBINS) / ext;
-        int b = binOf(cent[3 * size_t(g) + ax], cb[ax], k);
-        size_t bi = (size_t(a) * 3 + ax) * NBINS + b;
-        atomicAdd(&bins.cnt[bi], 1u);
-        uint32_t* keys = bins.keys + bi * 6;
-        atomicMin(&keys[0], kl[0]); atomicMin(&keys[1], kl[1]); atomicMin(&keys[2], kl[2]);
-        atomicMax(&keys[3], kh[0]); atomicMax(&keys[4], kh[1]); atomicMax(&keys[5], kh[2]);
+        uint32_t bi = 0xFFFFFFFFu;
+        if (valid) {
+            const float ext = cb[3 + ax] - cb[ax];
+            if (ext > 0.0f) {
+                const float k = float(NBINS) / ext;
+                bi = uint32_t((size_t(a) * 3 + ax) * NBINS + binOf(cent[3 * size_t(g) + ax], cb[ax], k));
+            }
+        }
+        const unsigned grp = __match_any_sync(0xFFFFFFFFu, bi);
+        const uint32_t m0 = __reduce_min_sync(grp, kl[0]), m1 = __reduce_min_sync(grp, kl[1]), m2 = __reduce_min_sync(grp, kl[2]);
+        const uint32_t x0 = __reduce_max_sync(grp, kh[0]), x1 = __reduce_max_sync(grp, kh[1]), x2 = __reduce_max_sync(grp, kh[2]);
+        if (bi != 0xFFFFFFFFu && lane == uint32_t(__ffs(int(grp))) - 1u) {
+            atomicAdd(&bins.cnt[bi], uint32_t(__popc(grp)));
+            uint32_t* keys = bins.keys + size_t(bi) * 6;
+            atomicMin(&keys[0], m0); atomicMin(&keys[1], m1); atomicMin(&keys[2], m2);
+            atomicMax(&keys[3], x0); atomicMax(&keys[4], x1); atomicMax(&keys[5], x2);
+        }
     }
 }
 
@@ -191,25 +203,37 @@ __global__ void k_scatter(const uint32_t* __restrict__ prim, uint32_t* __restric
                           ActiveArrays act, SplitArrays sp, const uint32_t* __restrict__ flag, const uint32_t* __restrict__ flagScan,
                           const uint32_t* __restrict__ innerScan, uint32_t* __restrict__ childKeys,
                           const float* __restrict__ lo, const float* __restrict__ hi, const float* __restrict__ cent) {
-    uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos >= T) return;
-    int a = nodeOf[pos];
-    uint32_t g = prim[pos];
-    if (a < 0) { prim2[pos] = g; nodeOf2[pos] = -1; return; }
-    const uint32_t first = act.first[a], nL = sp.nL[a];
-    const uint32_t rankL = flagScan[pos] - flagScan[first];
-    const uint32_t side = flag[pos] ? 0u : 1u;
-    const uint32_t newpos = side == 0 ? first + rankL : first + nL + ((pos - first) - rankL);
-    prim2[newpos] = g;
-    const uint32_t child = 2 * uint32_t(a) + side;
-    nodeOf2[newpos] = sp.innerFlag[child] ? int(innerScan[child]) : -1;
-    uint32_t* k = childKeys + size_t(child) * 12;
-    for (int ax = 0; ax < 3; ++ax) {
-        atomicMin(&k[ax], okey(lo[3 * size_t(g) + ax]));
-        atomicMax(&k[3 + ax], okey(hi[3 * size_t(g) + ax]));
-        uint32_t ck = okey(cent[3 * size_t(g) + ax]);
-        atomicMin(&k[6 + ax], ck);
-        atomicMax(&k[9 + ax], ck);
+    const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    const int a = pos < T ? nodeOf[pos] : -1;
+    uint32_t child = 0xFFFFFFFFu, key[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) key[i] = (i % 6) < 3 ? 0xFFFFFFFFu : 0u; // neutral elements of min (0..2, 6..8) and max (3..5, 9..11)
+    if (pos < T) {
+        const uint32_t g = prim[pos];
+        if (a < 0) { prim2[pos] = g; nodeOf2[pos] = -1; }
+        else {
+            const uint32_t first = act.first[a], nL = sp.nL[a];
+            const uint32_t rankL = flagScan[pos] - flagScan[first];
+            const uint32_t side = flag[pos] ? 0u : 1u;
+            const uint32_t newpos = side == 0 ? first + rankL : first + nL + ((pos - first) - rankL);
+            prim2[newpos] = g;
+            child = 2 * uint32_t(a) + side;
+            nodeOf2[newpos] = sp.innerFlag[child] ? int(innerScan[child]) : -1;
+            for (int ax = 0; ax < 3; ++ax) {
+                key[ax] = okey(lo[3 * size_t(g) + ax]); key[3 + ax] = okey(hi[3 * size_t(g) + ax]);
+                key[6 + ax] = key[9 + ax] = okey(cent[3 * size_t(g) + ax]);
+            }
+        }
+    }
+    // warp-level pre-reduction per child (see k_bin)
+    const unsigned grp = __match_any_sync(0xFFFFFFFFu, child);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) key[i] = (i % 6) < 3 ? __reduce_min_sync(grp, key[i]) : __reduce_max_sync(grp, key[i]);
+    if (child != 0xFFFFFFFFu && lane == uint32_t(__ffs(int(grp))) - 1u) {
+        uint32_t* k = childKeys + size_t(child) * 12;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) { if ((i % 6) < 3) atomicMin(&k[i], key[i]); else atomicMax(&k[i], key[i]); }
     }
 }
 
@@ -366,10 +390,26 @@ struct Scan {
     ~Scan() { if (temp) cudaFree(temp); }
 };
 
+// Build scratch: a bump allocator over a few large device blocks (about 40 arrays are needed; one cudaMalloc / cudaFree pair per
+// array cost more than all build kernels together: 265 k triangles built in 106-190 ms with per-array allocations, kernels 17 ms).
 struct Pool { // frees everything on scope exit
-    std::vector<void*> ptrs;
-    template <typename Tp> cudaError_t alloc(Tp** p, size_t count) { void* q = nullptr; cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(Tp)); if (e == cudaSuccess) { ptrs.push_back(q); *p = (Tp*)q; } return e; }
-    ~Pool() { for (void* p : ptrs) cudaFree(p); }
+    struct Block { char* base; size_t size, used; };
+    std::vector<Block> blocks;
+    size_t nextSize = size_t(64) << 20;
+    template <typename Tp> cudaError_t alloc(Tp** p, size_t count) {
+        const size_t bytes = (std::max<size_t>(count, 1) * sizeof(Tp) + 255) & ~size_t(255);
+        if (blocks.empty() || blocks.back().used + bytes > blocks.back().size) {
+            Block b; b.size = std::max(bytes, nextSize); b.used = 0; b.base = nullptr;
+            cudaError_t e = cudaMalloc(&b.base, b.size);
+            if (e != cudaSuccess) return e;
+            blocks.push_back(b); nextSize = std::max<size_t>(b.size / 2, size_t(64) << 20);
+        }
+        Block& b = blocks.back();
+        *p = reinterpret_cast<Tp*>(b.base + b.used); b.used += bytes;
+        return cudaSuccess;
+    }
+    void reserve(size_t bytes) { nextSize = std::max(nextSize, bytes); }
+    ~Pool() { for (Block& b : blocks) cudaFree(b.base); }
 };
 
 } // namespace
@@ -394,9 +434,10 @@ int bvhBuildDevice(vkx_ctx* ctx) {
         cudaEventDestroy(e0); cudaEventDestroy(e1);
         return VKX_OK;
     }
-    if (T >= (1u << 29)) return vkx_fail(ctx, VKX_E_UNSUPPORTED, "too many triangles (%u)", T);
+    if (T >= (1u << 28)) return vkx_fail(ctx, VKX_E_UNSUPPORTED, "too many triangles (%u)", T); // bin indices (12 per primitive slot) are 32-bit
 
     Pool pool; Scan scan;
+    pool.reserve(size_t(T) * 800 + (size_t(8) << 20)); // the arrays below: ~560 bytes per triangle for the binary phase + ~190 for the wide phase
     const unsigned B = 256;
     FlatTri* flat; float *lo, *hi, *cent; uint32_t* rootKeys;
     CUDA_TRY(ctx, pool.alloc(&flat, T)); CUDA_TRY(ctx, pool.alloc(&lo, 3 * size_t(T))); CUDA_TRY(ctx, pool.alloc(&hi, 3 * size_t(T))); CUDA_TRY(ctx, pool.alloc(&cent, 3 * size_t(T)));

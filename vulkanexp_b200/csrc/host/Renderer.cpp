@@ -57,6 +57,15 @@ void Renderer::createAccelerationStructures() {
     check(ctx, vkx_bvh_build(ctx));
 }
 
+void Renderer::updateAccelerationStructureInstances() {
+    const size_t before = _instances.size();
+    createTLAS(); // same order (sortRenderers is stable), transforms re-read from the scene graph
+    if (_instances.size() != before) throw Error(VKX_E_INVALID, "updateAccelerationStructureInstances: the set of renderers changed; call createAccelerationStructures");
+    check(_device->ctx(), vkx_instances_update(_device->ctx(), _instances.data(), _instances.size()));
+}
+
+void Renderer::updateTLAS() { check(_device->ctx(), vkx_bvh_build(_device->ctx())); }
+
 vkx_bvh_info Renderer::getTLAS() const {
     vkx_bvh_info info{};
     check(_device->ctx(), vkx_bvh_info_get(_device->ctx(), &info));

@@ -35,6 +35,11 @@ class Renderer {
     void createAccelerationStructures();  // reference src/Renderer.cpp:272-449 (+ createTLAS)
     void createTLAS();                    // instance list, reference src/Renderer.cpp:525-642
     void destroyTLAS() { _instances.clear(); }
+    // reference src/Renderer.cpp:671-742: new instance transforms after Scene::update(), then the structure update (here: the
+    // deterministic rebuild of the world-space BVH; the reference refits its TLAS)
+    void updateAccelerationStructureInstances();
+    void updateTLAS();
+    void onHierarchicalChanges() { updateAccelerationStructureInstances(); updateTLAS(); }
     vkx_bvh_info getTLAS() const;         // the reference returns the TLAS handle; here: the wide-BVH description
 
     std::vector<vkx_vertex> Vertices;     // public arenas, as in the reference
