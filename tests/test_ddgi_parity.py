@@ -129,6 +129,34 @@ def test_partial_update_leaves_other_probes_untouched(oracle_lib):
     _compare_update(o, g, 0)
 
 
+def test_repeated_and_alternating_lists(oracle_lib):
+    """An unchanged to-update list is kept on the device between updates; alternating lists, a full update and a scheduled update
+    in between must each invalidate it."""
+    o, g, flat, grid = _setup(oracle_lib, "court", (6, 4, 6), 32)
+    host = oracle_lib.HostLogic()
+    light = Light.default()
+    st = np.ones(grid.probe_count, dtype=np.uint32)
+    o.probes_upload(state=st); g.probes_upload(state=st)
+    A = np.array([5, 17, 100, 3, 44, 45, 46], dtype=np.uint32)
+    B = np.array([9, 17, 2, 101, 60, 61, 62], dtype=np.uint32)  # same length as A, different probes
+    plan = [A, A, B, B, A, None, A, "sched", A, A[:4], A]
+    for frame, lst in enumerate(plan):
+        R, _ = host.next_orientation()
+        grid.hysteresis = 0.3
+        if isinstance(lst, str):
+            n = g.probes_schedule(7)
+            lst = g.probes_scheduled_list()
+            assert n == len(lst) == 7
+            g.probes_update_scheduled(grid, light, R)
+        else:
+            g.probes_update(grid, light, R, lst)
+        o.probes_update(grid, light, R, lst)
+        _compare_update(o, g, frame)
+        io, do, sto, _ = o.probes_download(); ig, dg, stg, _ = g.probes_download()
+        assert np.array_equal(sto, stg)
+        o.probes_upload(ig, dg, stg)  # resync packed atlases so that 1-code flips do not accumulate
+
+
 def test_rejects_bad_arguments():
     from vulkanexp_b200._lib import Context, VkxError
 

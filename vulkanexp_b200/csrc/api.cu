@@ -72,6 +72,7 @@ static void freeProbes(vkx_ctx* ctx) {
     ctx->dDirs = nullptr; ctx->dInvDirs = nullptr; ctx->dOrigins = nullptr; ctx->dRays = nullptr; ctx->dHits = nullptr; ctx->dShadowQueue = nullptr; ctx->dQueueCount = nullptr; ctx->dShadowFlags = nullptr;
     ctx->dIrrUnpacked = ctx->dDepUnpacked = nullptr; ctx->dMissQueue = ctx->dFrontQueue = ctx->dFrontKeys = ctx->dFrontKeysOut = ctx->dFrontQueueSorted = nullptr; ctx->dSortTemp = nullptr; ctx->sortTempBytes = 0;
     if (ctx->hListStage) { cudaFreeHost(ctx->hListStage); ctx->hListStage = nullptr; }
+    ctx->hLastList.clear();
     void* sched[] = {ctx->dSchedFlags, ctx->dSchedPos, ctx->dSchedSlotOf, ctx->dSchedResult, ctx->dSchedTemp};
     for (void* p : sched) if (p) cudaFree(p);
     if (ctx->hSchedResult) cudaFreeHost(ctx->hSchedResult);
@@ -424,9 +425,15 @@ int vkx_probes_update(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx_light* 
     const double t1 = now();
     if (probeIndices) {
         if (count > ctx->probeCount) return vkx_fail(ctx, VKX_E_INVALID, "more indices than probes");
-        for (uint32_t i = 0; i < count; ++i) if (probeIndices[i] >= ctx->probeCount) return vkx_fail(ctx, VKX_E_INVALID, "probe index %u out of range", probeIndices[i]);
-        TRY(uploadOrder(ctx, probeIndices, count, 0, true));
+        // an unchanged to-update list (every frame of a full-volume schedule) is already on the device together with its slot order
+        if (ctx->hLastList.size() != count || (count && memcmp(ctx->hLastList.data(), probeIndices, size_t(count) * 4) != 0)) {
+            for (uint32_t i = 0; i < count; ++i) if (probeIndices[i] >= ctx->probeCount) return vkx_fail(ctx, VKX_E_INVALID, "probe index %u out of range", probeIndices[i]);
+            ctx->hLastList.clear();
+            TRY(uploadOrder(ctx, probeIndices, count, 0, true));
+            ctx->hLastList.assign(probeIndices, probeIndices + count);
+        }
     } else {
+        ctx->hLastList.clear();
         count = ctx->probeCount;
         k_iota_list<<<divUp(count, 256), 256, 0, ctx->stream>>>(ctx->dIndicesList, 0, count); LAUNCH_CHECK(ctx);
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dOrder, ctx->dBlockedOrder, size_t(count) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -448,6 +455,7 @@ int vkx_probes_schedule(vkx_ctx* ctx, uint32_t probesPerUpdate, uint32_t* count)
     BIND(ctx);
     if (!ctx->probesReady) return vkx_fail(ctx, VKX_E_INVALID, "vkx_probes_schedule: probes not ready");
     TRY(waitGather(ctx)); // the states of a sharded update must have landed
+    ctx->hLastList.clear();
     TRY(scheduleProbes(ctx, probesPerUpdate, count));
     ctx->schedValid = true; ctx->shardOrderReady = false;
     return VKX_OK;
@@ -662,6 +670,7 @@ int vkx_probes_update_sharded(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx
     if (!light || !orientation) return vkx_fail(ctx, VKX_E_INVALID, "null light/orientation");
     if (ctx->nranks == 1 || !ctx->comm) return vkx_probes_update(ctx, grid, light, orientation, nullptr, 0, sync);
     TRY(uploadFrameInputs(ctx, grid, orientation));
+    ctx->hLastList.clear();
     const uint32_t n = uint32_t(ctx->nranks), rz = uint32_t(ctx->grid.resolution[2]), plane = uint32_t(ctx->grid.resolution[0] * ctx->grid.resolution[1]);
     if (rz % n != 0) return vkx_fail(ctx, VKX_E_INVALID, "grid z resolution %u is not divisible by %u ranks", rz, n);
     const size_t irrBytes = size_t(ctx->irrW) * ctx->irrH * 4, depBytes = size_t(ctx->depW) * ctx->depH * 4, stBytes = size_t(ctx->probeCount) * 4;

@@ -76,6 +76,7 @@ struct vkx_ctx {
     uint32_t* dPermList = nullptr;      // multi-chunk updates: probe indices in block order
     uint32_t* dIota = nullptr;          // 0..probeCount-1
     float* dBlendW = nullptr;           // per-frame blend weight table [256][288]
+    std::vector<uint32_t> hLastList;    // the host list currently resident in dIndicesList / dOrder (empty: none), so an unchanged list is not uploaded again
     std::vector<uint32_t> hBlockRank;   // probe linear index -> rank in 2x2x2-block order
     std::vector<uint32_t> hMark, hOrder; // scratch of uploadOrder
     struct FrameStage { float4 dirs[VKX_MAX_RAYS_PER_PROBE]; uint32_t perm[VKX_MAX_RAYS_PER_PROBE]; };
