@@ -217,6 +217,13 @@ int vkx_probes_device_ptrs(vkx_ctx* ctx, void** irradiance, void** depth, void**
 /* ncclUniqueId is 128 bytes; create it on rank 0 with vkx_comm_unique_id and broadcast it out of band. */
 int vkx_comm_unique_id(void* id128);
 int vkx_comm_init(vkx_ctx* ctx, int rank, int nranks, const void* id128);
+/* Optional: blend fused with the atlas exchange over NVLink peer memory instead of the NCCL all-gather. After vkx_comm_init and
+ * vkx_probes_init every rank exports a CUDA IPC handle of its atlas slab (two atlas sets + arrival flags), the host passes all
+ * handles around (like the NCCL id) and every rank imports them. From then on vkx_probes_update_sharded lets k_blend store its
+ * finished tiles straight into every rank's next atlas set, raises an arrival flag in peer memory, and the next reader of the
+ * sampled atlases waits for all flags on the device - no collective, no host synchronisation. Results are identical. */
+int vkx_comm_p2p_export(vkx_ctx* ctx, void* handle64);
+int vkx_comm_p2p_import(vkx_ctx* ctx, const void* handles /* nranks x 64 bytes, rank order */, int count);
 /* Full-volume update of this rank's z-slab followed by the all-gather of the atlas/state slabs. */
 int vkx_probes_update_sharded(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx_light* light,
                               const float orientation[16], int sync);

@@ -23,6 +23,10 @@ ctx.probes_upload(state=ones)
 uid = [Context.comm_unique_id() if rank == 0 else None]
 dist.broadcast_object_list(uid, src=0)
 ctx.comm_init(rank, world, uid[0])
+P2P = os.environ.get("VKX_P2P", "0") == "1"
+if P2P:  # blend fused with the atlas exchange over NVLink peer memory instead of the NCCL all-gather
+    ctx.comm_p2p_enable(dist)
+    print("rank %d: peer-memory exchange enabled" % rank, flush=True)
 ref = Context(local); ref.scene_upload(flat); ref.bvh_build(); ref.probes_init(grid); ref.probes_upload(state=ones)
 gen = OrientationGenerator()
 ok = True

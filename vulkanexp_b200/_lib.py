@@ -229,6 +229,23 @@ class Context:
         buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
         self._check(self.l.vkx_comm_init(self.h, C.c_int(rank), C.c_int(nranks), buf))
 
+    def comm_p2p_export(self):
+        buf = (C.c_ubyte * 64)()
+        self._check(self.l.vkx_comm_p2p_export(self.h, buf))
+        return bytes(buf)
+
+    def comm_p2p_import(self, handles):
+        blob = b"".join(handles)
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self._check(self.l.vkx_comm_p2p_import(self.h, buf, C.c_int(len(handles))))
+
+    def comm_p2p_enable(self, dist):
+        """Exchange the IPC handles through torch.distributed and map every peer's atlas slab."""
+        mine = self.comm_p2p_export()
+        handles = [None] * dist.get_world_size()
+        dist.all_gather_object(handles, mine)
+        self.comm_p2p_import(handles)
+
     # ---- shadows
     def shadow_set_noise(self, noise):
         n = np.ascontiguousarray(noise, dtype=np.float32)

@@ -29,8 +29,9 @@ static int upload(vkx_ctx* ctx, T** dst, const T* src, size_t n) {
 #define TRY(expr) do { int _rc = (expr); if (_rc != VKX_OK) return _rc; } while (0)
 #define BIND(ctx) do { if (!(ctx)) return VKX_E_INVALID; cudaError_t _e = cudaSetDevice((ctx)->device); if (_e != cudaSuccess) return vkx_fail((ctx), VKX_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(_e)); } while (0)
 
-int waitGather(vkx_ctx* ctx) { // orders the context's stream after a pending all-gather of the sampled atlases
+int waitGather(vkx_ctx* ctx) { // orders the context's stream after a pending exchange (all-gather or peer stores) of the sampled atlases
     if (ctx->gatherPending) { CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->gatherDone, 0)); ctx->gatherPending = false; }
+    if (ctx->p2pPending) { ctx->p2pPending = false; int rc = launchP2pWait(ctx); if (rc != VKX_OK) return rc; }
     return VKX_OK;
 }
 
@@ -61,7 +62,17 @@ int vkx_create(int device, vkx_ctx** out) {
     return VKX_OK;
 }
 
+static void releaseP2p(vkx_ctx* ctx) { // the six atlas pointers live inside the slab while peer exchange is enabled
+    if (!ctx->p2pSlab) return;
+    cudaDeviceSynchronize();
+    for (int r = 0; r < VKX_MAX_RANKS; ++r) { if (ctx->peerSlab[r] && ctx->peerSlab[r] != ctx->p2pSlab) cudaIpcCloseMemHandle(ctx->peerSlab[r]); ctx->peerSlab[r] = nullptr; }
+    cudaFree(ctx->p2pSlab); ctx->p2pSlab = nullptr;
+    ctx->dIrrSampled = ctx->dDepSampled = ctx->dStateSampled = ctx->dIrrNext = ctx->dDepNext = ctx->dStateNext = nullptr;
+    ctx->p2p = ctx->p2pPending = ctx->blendToPeers = false; ctx->p2pFrame = 0; ctx->p2pSampledSet = 0;
+}
+
 static void freeProbes(vkx_ctx* ctx) {
+    releaseP2p(ctx);
     void* ptrs[] = {ctx->dIrrWork, ctx->dIrrSampled, ctx->dDepWork, ctx->dDepSampled, ctx->dStateWork, ctx->dStateSampled, ctx->dIndicesList, ctx->dDirs, ctx->dRays,
                     ctx->dHits, ctx->dShadowQueue, ctx->dQueueCount, ctx->dShadowFlags, ctx->dIrrUnpacked, ctx->dDepUnpacked, ctx->dMissQueue, ctx->dFrontQueue, ctx->dFrontKeys, ctx->dFrontKeysOut, ctx->dFrontQueueSorted, ctx->dSortTemp, ctx->dIrrNext, ctx->dDepNext, ctx->dStateNext,
                     ctx->dPerm, ctx->dOrder, ctx->dBlockedOrder, ctx->dBlendW, ctx->dPermList, ctx->dIota, ctx->dCellHist, ctx->dInvDirs, ctx->dOrigins};
@@ -115,7 +126,15 @@ void vkx_destroy(vkx_ctx* ctx) {
 const char* vkx_last_error(vkx_ctx* ctx) { return ctx ? ctx->err.c_str() : g_createError.c_str(); }
 uint64_t vkx_launch_count(vkx_ctx* ctx) { return ctx ? ctx->launches : 0; }
 void* vkx_stream(vkx_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
-int vkx_sync(vkx_ctx* ctx) { BIND(ctx); TRY(waitGather(ctx)); CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); return VKX_OK; }
+int vkx_sync(vkx_ctx* ctx) {
+    BIND(ctx); TRY(waitGather(ctx)); CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->p2pSlab) { // the device-side wait gives up after ~10 s instead of hanging the GPU; report it here
+        uint32_t err = 0;
+        CUDA_TRY(ctx, cudaMemcpy(&err, ctx->p2pSlab + ctx->p2pFlagsOff + 256, 4, cudaMemcpyDeviceToHost));
+        if (err) return vkx_fail(ctx, VKX_E_NCCL, "peer exchange: rank %u never signalled its tiles", err - 1u);
+    }
+    return VKX_OK;
+}
 
 // ---------------------------------------------------------------------------------------------------- geometry
 int vkx_scene_upload(vkx_ctx* ctx, const vkx_vertex* vertices, size_t numVertices, const uint32_t* indices, size_t numIndices,
@@ -544,7 +563,7 @@ int vkx_probes_download_slab_async(vkx_ctx* ctx, uint32_t z0, uint32_t z1, uint3
     // does not have to wait for the all-gather, which stays hidden behind the next frame's traversal. Any other slab comes from the
     // sampled atlases and needs the gather.
     const uint32_t own = ctx->nranks > 1 ? uint32_t(ctx->grid.resolution[2]) / uint32_t(ctx->nranks) : 0u;
-    const bool fromWork = ctx->shardedLast && ctx->gatherPending && own && z0 >= uint32_t(ctx->rank) * own && z1 <= uint32_t(ctx->rank + 1) * own;
+    const bool fromWork = ctx->shardedLast && (ctx->gatherPending || ctx->p2pPending) && own && z0 >= uint32_t(ctx->rank) * own && z1 <= uint32_t(ctx->rank + 1) * own;
     if (!fromWork) TRY(waitGather(ctx));
     if (!ctx->copyStream) {
         CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
@@ -660,6 +679,53 @@ int vkx_comm_init(vkx_ctx* ctx, int rank, int nranks, const void* id128) {
     return VKX_OK;
 }
 
+int vkx_comm_p2p_export(vkx_ctx* ctx, void* handle64) {
+    BIND(ctx);
+    if (!handle64) return VKX_E_INVALID;
+    if (!ctx->probesReady) return vkx_fail(ctx, VKX_E_INVALID, "vkx_comm_p2p_export: call vkx_probes_init first");
+    if (ctx->nranks < 2 || ctx->nranks > VKX_MAX_RANKS) return vkx_fail(ctx, VKX_E_INVALID, "vkx_comm_p2p_export: needs vkx_comm_init with 2..%d ranks", VKX_MAX_RANKS);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    TRY(waitGather(ctx));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!ctx->p2pSlab) {
+        auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
+        const size_t irrBytes = size_t(ctx->irrW) * ctx->irrH * 4, depBytes = size_t(ctx->depW) * ctx->depH * 4, stBytes = size_t(ctx->probeCount) * 4;
+        ctx->p2pDepOff = al(irrBytes); ctx->p2pStOff = ctx->p2pDepOff + al(depBytes); ctx->p2pSetBytes = ctx->p2pStOff + al(stBytes);
+        ctx->p2pFlagsOff = 2 * ctx->p2pSetBytes;
+        char* slab = nullptr;
+        CUDA_TRY(ctx, cudaMalloc(&slab, ctx->p2pFlagsOff + 512));
+        CUDA_TRY(ctx, cudaMemset(slab, 0, ctx->p2pFlagsOff + 512));
+        CUDA_TRY(ctx, cudaMemcpy(slab, ctx->dIrrSampled, irrBytes, cudaMemcpyDeviceToDevice));
+        CUDA_TRY(ctx, cudaMemcpy(slab + ctx->p2pDepOff, ctx->dDepSampled, depBytes, cudaMemcpyDeviceToDevice));
+        CUDA_TRY(ctx, cudaMemcpy(slab + ctx->p2pStOff, ctx->dStateSampled, stBytes, cudaMemcpyDeviceToDevice));
+        void* old[] = {ctx->dIrrSampled, ctx->dDepSampled, ctx->dStateSampled, ctx->dIrrNext, ctx->dDepNext, ctx->dStateNext};
+        for (void* p : old) if (p) cudaFree(p);
+        ctx->p2pSlab = slab; ctx->p2pSampledSet = 0; ctx->p2pFrame = 0;
+        ctx->dIrrSampled = reinterpret_cast<uint32_t*>(slab); ctx->dDepSampled = reinterpret_cast<uint32_t*>(slab + ctx->p2pDepOff); ctx->dStateSampled = reinterpret_cast<uint32_t*>(slab + ctx->p2pStOff);
+        char* s1 = slab + ctx->p2pSetBytes;
+        ctx->dIrrNext = reinterpret_cast<uint32_t*>(s1); ctx->dDepNext = reinterpret_cast<uint32_t*>(s1 + ctx->p2pDepOff); ctx->dStateNext = reinterpret_cast<uint32_t*>(s1 + ctx->p2pStOff);
+    }
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(ctx, cudaIpcGetMemHandle(&h, ctx->p2pSlab));
+    memcpy(handle64, &h, 64);
+    return VKX_OK;
+}
+
+int vkx_comm_p2p_import(vkx_ctx* ctx, const void* handles, int count) {
+    BIND(ctx);
+    if (!handles || count != ctx->nranks || !ctx->p2pSlab) return vkx_fail(ctx, VKX_E_INVALID, "vkx_comm_p2p_import: export first, then pass one 64-byte handle per rank");
+    for (int r = 0; r < count; ++r) {
+        if (r == ctx->rank) { ctx->peerSlab[r] = ctx->p2pSlab; continue; }
+        cudaIpcMemHandle_t h; memcpy(&h, static_cast<const char*>(handles) + size_t(r) * 64, 64);
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return vkx_fail(ctx, VKX_E_CUDA, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+        ctx->peerSlab[r] = static_cast<char*>(p);
+    }
+    ctx->p2p = true;
+    return VKX_OK;
+}
+
 // Full-volume update, sharded: the z range is cut into K chunks of s*nranks slices; inside chunk k rank r traces and blends
 // the s slices [k*s*n + r*s, k*s*n + (r+1)*s). A chunk's atlas rows are contiguous in memory, so one ncclAllGather per
 // atlas per chunk (on a second stream, overlapped with the next chunk's tracing) assembles the *next* sampled atlases on
@@ -674,7 +740,8 @@ int vkx_probes_update_sharded(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx
     const uint32_t n = uint32_t(ctx->nranks), rz = uint32_t(ctx->grid.resolution[2]), plane = uint32_t(ctx->grid.resolution[0] * ctx->grid.resolution[1]);
     if (rz % n != 0) return vkx_fail(ctx, VKX_E_INVALID, "grid z resolution %u is not divisible by %u ranks", rz, n);
     const size_t irrBytes = size_t(ctx->irrW) * ctx->irrH * 4, depBytes = size_t(ctx->depW) * ctx->depH * 4, stBytes = size_t(ctx->probeCount) * 4;
-    if (!ctx->dIrrNext) { CUDA_TRY(ctx, cudaMalloc(&ctx->dIrrNext, irrBytes)); CUDA_TRY(ctx, cudaMalloc(&ctx->dDepNext, depBytes)); CUDA_TRY(ctx, cudaMalloc(&ctx->dStateNext, stBytes)); }
+    if (!ctx->dIrrNext) { // (with peer exchange enabled the next set lives in the shared slab)
+        CUDA_TRY(ctx, cudaMalloc(&ctx->dIrrNext, irrBytes)); CUDA_TRY(ctx, cudaMalloc(&ctx->dDepNext, depBytes)); CUDA_TRY(ctx, cudaMalloc(&ctx->dStateNext, stBytes)); }
     // One chunk per frame: the all-gather of frame f is not waited for at the end of the update but before the first kernel of frame
     // f+1 that reads the sampled atlases (k_shade_front), so it overlaps frame f+1's primary traversal, which never touches them.
     // (Measured on 4 GPUs: splitting the slab into chunks to overlap inside the frame cost more in small launches than it hid.)
@@ -682,7 +749,16 @@ int vkx_probes_update_sharded(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx
     const uint32_t K = 1, s = slicesPerRank / K;
     ncclComm_t comm = reinterpret_cast<ncclComm_t>(ctx->comm);
     cudaStream_t st = ctx->stream, cs = ctx->commStream;
-    if (ctx->copyPending && !ctx->copyReadsWork) { CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->commStream, ctx->evCopyDone, 0)); ctx->copyPending = false; } // read-back of the buffers about to be overwritten
+    const bool p2p = ctx->p2p;
+    if (p2p) { // k_blend stores its tiles straight into every rank's next atlas set (NVLink peer memory): no separate exchange step
+        const int nextSet = ctx->p2pSampledSet ^ 1;
+        PeerTargets pt{}; pt.n = int(n);
+        for (uint32_t r = 0; r < n; ++r) {
+            char* base = ctx->peerSlab[r] + size_t(nextSet) * ctx->p2pSetBytes;
+            pt.irr[r] = reinterpret_cast<uint32_t*>(base); pt.dep[r] = reinterpret_cast<uint32_t*>(base + ctx->p2pDepOff); pt.state[r] = reinterpret_cast<uint32_t*>(base + ctx->p2pStOff);
+        }
+        ctx->blendPeers = pt; ctx->blendToPeers = true;
+    } else if (ctx->copyPending && !ctx->copyReadsWork) { CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->commStream, ctx->evCopyDone, 0)); ctx->copyPending = false; } // read-back of the buffers about to be overwritten
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], st));
     uint32_t total = 0;
     for (uint32_t k = 0; k < K; ++k) {
@@ -690,8 +766,9 @@ int vkx_probes_update_sharded(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx
         const uint32_t first = z0 * plane, count = s * plane;
         k_iota_list<<<divUp(count, 256), 256, 0, st>>>(ctx->dIndicesList + total, first, count); LAUNCH_CHECK(ctx);
         if (!ctx->shardOrderReady) { std::vector<uint32_t> idx(count); for (uint32_t i = 0; i < count; ++i) idx[i] = first + i; TRY(uploadOrder(ctx, idx.data(), count, total, false)); }
-        TRY(ddgiUpdate(ctx, *light, nullptr, count, total, false));
+        { int rc = ddgiUpdate(ctx, *light, nullptr, count, total, false); if (rc != VKX_OK) { ctx->blendToPeers = false; return rc; } }
         total += count;
+        if (p2p) continue;
         CUDA_TRY(ctx, cudaEventRecord(ctx->commEvent, st));
         CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ctx->commEvent, 0));
         const size_t irrChunk = size_t(8 * s) * ctx->irrW, depChunk = size_t(16 * s) * ctx->depW, stChunk = size_t(s) * plane; // elements per rank
@@ -704,8 +781,16 @@ int vkx_probes_update_sharded(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx
         if (r != ncclSuccess) return vkx_fail(ctx, VKX_E_NCCL, "ncclAllGather: %s", ncclGetErrorString(r));
     }
     ctx->shardOrderReady = true;
-    CUDA_TRY(ctx, cudaEventRecord(ctx->gatherDone, cs));
-    ctx->gatherPending = true; // waited for by the next reader of the sampled atlases (waitGather)
+    if (p2p) {
+        ctx->blendToPeers = false;
+        // peers may overwrite the set a queued read-back still reads as soon as they see this rank's flag: raise it after the copy
+        if (ctx->copyPending && !ctx->copyReadsWork) { CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->evCopyDone, 0)); ctx->copyPending = false; }
+        TRY(launchP2pSignal(ctx));
+        ctx->p2pFrame++; ctx->p2pSampledSet ^= 1; ctx->p2pPending = true; // waited for by the next reader of the sampled atlases (waitGather)
+    } else {
+        CUDA_TRY(ctx, cudaEventRecord(ctx->gatherDone, cs));
+        ctx->gatherPending = true; // waited for by the next reader of the sampled atlases (waitGather)
+    }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], st));
     // publish = swap; the work buffers keep this rank's slices current (they are the only ones it reads as `previous`)
     std::swap(ctx->dIrrSampled, ctx->dIrrNext); std::swap(ctx->dDepSampled, ctx->dDepNext); std::swap(ctx->dStateSampled, ctx->dStateNext);

@@ -43,6 +43,11 @@ struct DeviceProbes {
     uint32_t* stateWork;
 };
 
+// Fused blend + atlas exchange over NVLink peer memory: where k_blend stores its finished tiles (every rank's *next* atlas set)
+#define VKX_MAX_RANKS 16
+struct PeerTargets { uint32_t* irr[VKX_MAX_RANKS]; uint32_t* dep[VKX_MAX_RANKS]; uint32_t* state[VKX_MAX_RANKS]; int n; };
+struct PeerFlags { uint32_t* flags[VKX_MAX_RANKS]; };
+
 struct vkx_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -109,6 +114,13 @@ struct vkx_ctx {
     ncclComm* comm = nullptr; int rank = 0, nranks = 1;
     cudaStream_t commStream = nullptr; cudaEvent_t commEvent = nullptr, gatherDone = nullptr; bool gatherPending = false;
     uint32_t *dIrrNext = nullptr, *dDepNext = nullptr, *dStateNext = nullptr; // all-gather targets (sharded update)
+    // peer-memory exchange (vkx_comm_p2p_export / _import): one slab per rank = atlas set 0 | atlas set 1 | arrival flags | error word,
+    // mapped into every peer through CUDA IPC; sampled / next point into the slab
+    bool p2p = false, p2pPending = false, blendToPeers = false;
+    char* p2pSlab = nullptr; char* peerSlab[VKX_MAX_RANKS] = {};
+    size_t p2pSetBytes = 0, p2pDepOff = 0, p2pStOff = 0, p2pFlagsOff = 0;
+    uint32_t p2pFrame = 0; int p2pSampledSet = 0;
+    PeerTargets blendPeers = {};
     bool shardedLast = false, shardOrderReady = false;
 
     // shadows
@@ -147,6 +159,8 @@ static inline unsigned divUp(size_t a, size_t b) { return unsigned((a + b - 1) /
 // ---- implemented in bvh_build.cu
 int bvhBuildDevice(vkx_ctx* ctx);
 int waitGather(vkx_ctx* ctx); // api.cu
+int launchP2pWait(vkx_ctx* ctx);   // ddgi.cu: stream-ordered wait for every rank's tiles of the last sharded update
+int launchP2pSignal(vkx_ctx* ctx); // ddgi.cu
 // ---- ddgi.cu
 int ddgiClassify(vkx_ctx* ctx, const float* dirs512);
 int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* hostIndices, uint32_t count, uint32_t firstProbe, bool publishAll);

@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(BLEND_COLS) k_blend_weight_sums(uint32_t N, fl
 #define BLEND_DEPTH_T1 224   // threads [224, 448): second depth moment
 #define BLEND_IRR_T 448      // threads [448, 576): irradiance, channel = t / 36, texel = t % 36
 __global__ void __launch_bounds__(BLEND_THREADS) k_blend(BlendParams bp, DeviceProbes pr, const uint32_t* __restrict__ probeIndices, const float4* __restrict__ rays,
-                                                         const float* __restrict__ W, float* __restrict__ irrUnpacked, float* __restrict__ depUnpacked, uint32_t slotBase) {
+                                                         const float* __restrict__ W, float* __restrict__ irrUnpacked, float* __restrict__ depUnpacked, uint32_t slotBase, PeerTargets pt) {
     // dynamic shared memory (50 KB): 5 planes [BLEND_P][256] of ray data, re-used for the normalised sums after the ray loop; output tiles
     extern __shared__ float4 sBlend[];
     float* sPlane = reinterpret_cast<float*>(sBlend);                                // [5][BLEND_P][256]
@@ -286,6 +286,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(BlendParams bp, DeviceP
             else if (maxChange > 0.25f) st = 1;
         }
         pr.stateWork[linearIndex] = st;
+        for (int r = 0; r < pt.n; ++r) pt.state[r][linearIndex] = st; // sharded + peer memory: straight into every rank's next state array
     }
     // ---- borders (probesCopyBorders.comp) from the shared tiles: 60 depth + 28 irradiance texels per probe
     for (uint32_t e = tid; e < np * 88u; e += BLEND_THREADS) {
@@ -311,12 +312,35 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(BlendParams bp, DeviceP
         if (k < 64u) {
             const int row = int(k >> 2), q = int(k & 3u);
             const uint4 v = *reinterpret_cast<const uint4*>(&sDep[p][row * 16 + q * 4]);
-            *reinterpret_cast<uint4*>(pr.depWork + size_t(16 * iz + row) * pr.depW + size_t(16 * tile + q * 4)) = v;
+            const size_t off = size_t(16 * iz + row) * pr.depW + size_t(16 * tile + q * 4);
+            *reinterpret_cast<uint4*>(pr.depWork + off) = v;
+            for (int r = 0; r < pt.n; ++r) *reinterpret_cast<uint4*>(pt.dep[r] + off) = v; // NVLink peer stores (or the local next set)
         } else {
             const int kk = int(k) - 64; const int row = kk >> 1, q = kk & 1;
             const uint4 v = *reinterpret_cast<const uint4*>(&sIrr[p][row * 8 + q * 4]);
-            *reinterpret_cast<uint4*>(pr.irrWork + size_t(8 * iz + row) * pr.irrW + size_t(8 * tile + q * 4)) = v;
+            const size_t off = size_t(8 * iz + row) * pr.irrW + size_t(8 * tile + q * 4);
+            *reinterpret_cast<uint4*>(pr.irrWork + off) = v;
+            for (int r = 0; r < pt.n; ++r) *reinterpret_cast<uint4*>(pt.irr[r] + off) = v;
         }
+    }
+    if (pt.n) __threadfence_system(); // peer stores are ordered before the arrival flag the next kernel on this stream raises
+}
+
+// Arrival flags of the peer-memory exchange. After its last blend of frame g a rank writes g + 1 into slot [rank] of every rank's flag
+// array; before the first kernel that reads the sampled atlases a rank waits until all slots of its own array have reached the frame
+// it is about to shade. No host round trip and no collective: the wait is a one-warp kernel polling local memory.
+__global__ void k_p2p_signal(PeerFlags pf, int n, int self, uint32_t value) {
+    const int r = int(threadIdx.x);
+    if (r < n) { __threadfence_system(); *reinterpret_cast<volatile uint32_t*>(pf.flags[r] + self) = value; }
+}
+__global__ void k_p2p_wait(const uint32_t* flags, int n, uint32_t need, uint32_t* err) {
+    const int r = int(threadIdx.x);
+    if (r >= n) return;
+    const volatile uint32_t* f = flags + r;
+    const long long t0 = clock64();
+    while (*f < need) {
+        if (clock64() - t0 > (20LL << 30)) { *err = 1u + uint32_t(r); break; } // ~10 s at 2 GHz: a peer died; do not hang the GPU
+        __nanosleep(500);
     }
 }
 
@@ -480,11 +504,23 @@ int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* /*unused*/,
         bp.count = n;
         CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->auxEvent[1], 0)); // sky results
         if (ctx->copyPending && ctx->copyReadsWork) { CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->evCopyDone, 0)); ctx->copyPending = false; ctx->copyReadsWork = false; } // a queued read-back still reads the work atlases
-        k_blend<<<divUp(n, BLEND_P), BLEND_THREADS, BLEND_SMEM_BYTES, st>>>(bp, pr, idx, ctx->dRays, ctx->dBlendW, ctx->debugBuffers ? ctx->dIrrUnpacked : nullptr, ctx->debugBuffers ? ctx->dDepUnpacked : nullptr, base); LAUNCH_CHECK(ctx);
+        k_blend<<<divUp(n, BLEND_P), BLEND_THREADS, BLEND_SMEM_BYTES, st>>>(bp, pr, idx, ctx->dRays, ctx->dBlendW, ctx->debugBuffers ? ctx->dIrrUnpacked : nullptr, ctx->debugBuffers ? ctx->dDepUnpacked : nullptr, base, ctx->blendToPeers ? ctx->blendPeers : PeerTargets{}); LAUNCH_CHECK(ctx);
         if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[4], st));
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], st));
     ctx->lastCount = count; ctx->lastRays = count * N;
+    return VKX_OK;
+}
+
+int launchP2pSignal(vkx_ctx* ctx) {
+    PeerFlags pf{};
+    for (int r = 0; r < ctx->nranks; ++r) pf.flags[r] = reinterpret_cast<uint32_t*>(ctx->peerSlab[r] + ctx->p2pFlagsOff);
+    k_p2p_signal<<<1, 32, 0, ctx->stream>>>(pf, ctx->nranks, ctx->rank, ctx->p2pFrame + 1u); LAUNCH_CHECK(ctx);
+    return VKX_OK;
+}
+int launchP2pWait(vkx_ctx* ctx) {
+    uint32_t* flags = reinterpret_cast<uint32_t*>(ctx->p2pSlab + ctx->p2pFlagsOff);
+    k_p2p_wait<<<1, 32, 0, ctx->stream>>>(flags, ctx->nranks, ctx->p2pFrame, flags + 64); LAUNCH_CHECK(ctx);
     return VKX_OK;
 }
 
