@@ -188,6 +188,11 @@ def main():
         uid = [Context.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(rank, world, uid[0])
+        exchange = os.environ.get("VKX_EXCHANGE", "nccl")
+        if exchange == "p2p":  # VKX_EXCHANGE=p2p: blend fused with the atlas exchange over NVLink peer memory (measured slower than the deferred all-gather at 8 GPUs)
+            exchange = "p2p" if ctx.comm_p2p_enable(dist) else "nccl"
+    else:
+        exchange = "none"
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     Rs = orientations(args.warmup + args.steps + args.steps)
@@ -283,7 +288,7 @@ def main():
             "metric": "ddgi_probe_rays_per_sec", "value": value, "unit": "probe rays/s", "n_gpus": n, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(n), "probes_per_gpu": probes_per_rank, "rays_per_probe": RAYS, "l2": "256 MiB buffer written between timed steps (flush, untimed)",
-                       "parallelism": "probe z-slices x%d, NCCL all-gather of atlas slices" % n if n > 1 else "single GPU"},
+                       "parallelism": ("probe z-slabs x%d, %s" % (n, "blend fused with the atlas exchange over NVLink peer memory (P2P stores + device-side flags)" if exchange == "p2p" else "NCCL all-gather of atlas slabs")) if n > 1 else "single GPU"},
             "full_volume_update_ms": ms_per_step, "grays_per_sec_per_gpu": value / n / 1e9,
             "gpu_launches": int(launches), "clocks": clocks,
             "e2e": {"value": rays_per_step_total / (e2e_ms * 1e-3), "unit": "probe rays/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

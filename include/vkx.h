@@ -223,7 +223,7 @@ int vkx_comm_init(vkx_ctx* ctx, int rank, int nranks, const void* id128);
  * finished tiles straight into every rank's next atlas set, raises an arrival flag in peer memory, and the next reader of the
  * sampled atlases waits for all flags on the device - no collective, no host synchronisation. Results are identical. */
 int vkx_comm_p2p_export(vkx_ctx* ctx, void* handle64);
-int vkx_comm_p2p_import(vkx_ctx* ctx, const void* handles /* nranks x 64 bytes, rank order */, int count);
+int vkx_comm_p2p_import(vkx_ctx* ctx, const void* handles /* nranks x 64 bytes, rank order; NULL, 0 = back to NCCL */, int count);
 /* Full-volume update of this rank's z-slab followed by the all-gather of the atlas/state slabs. */
 int vkx_probes_update_sharded(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx_light* light,
                               const float orientation[16], int sync);

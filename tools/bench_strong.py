@@ -29,6 +29,11 @@ if world > 1:
     uid = [Context.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     ctx.comm_init(rank, world, uid[0])
+    exchange = os.environ.get("VKX_EXCHANGE", "nccl")
+    if exchange == "p2p":
+        exchange = "p2p" if ctx.comm_p2p_enable(dist) else "nccl"  # VKX_EXCHANGE=p2p: k_blend stores into every rank's next atlas set over NVLink (default: deferred NCCL all-gather)
+else:
+    exchange = "none"
 gen = OrientationGenerator(); gen.next()
 Rs = [gen.next() for _ in range(args.warmup + args.steps)]
 stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
@@ -67,7 +72,7 @@ irr, dep, st, _ = ctx.probes_download()
 if rank == 0:
     info = ctx.bvh_info()
     print(json.dumps({"metric": "ddgi_full_volume_update_ms", "value": ms, "unit": "ms", "n_gpus": world, "scaling": "strong", "steps": args.steps, "warmup": args.warmup,
-                      "probe_rays_per_sec": grid.probe_count * 256 / (ms * 1e-3), "workload": "nature-like scene, %d triangles, %dx%dx%d probes x 256 rays" % (info.numTriangles, *args.res),
+                      "probe_rays_per_sec": grid.probe_count * 256 / (ms * 1e-3), "exchange": exchange, "workload": "nature-like scene, %d triangles, %dx%dx%d probes x 256 rays" % (info.numTriangles, *args.res),
                       "atlas_checksum": int(irr.astype(np.uint64).sum() % (1 << 32)), "depth_checksum": int(dep.astype(np.uint64).sum() % (1 << 32))}), flush=True)
 if world > 1:
     dist.destroy_process_group()

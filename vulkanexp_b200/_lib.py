@@ -241,10 +241,24 @@ class Context:
 
     def comm_p2p_enable(self, dist):
         """Exchange the IPC handles through torch.distributed and map every peer's atlas slab."""
-        mine = self.comm_p2p_export()
+        try:
+            mine = self.comm_p2p_export()
+        except VkxError:
+            mine = None
         handles = [None] * dist.get_world_size()
         dist.all_gather_object(handles, mine)
-        self.comm_p2p_import(handles)
+        ok = all(h is not None for h in handles)
+        if ok:
+            try:
+                self.comm_p2p_import(handles)
+            except VkxError:
+                ok = False
+        flags = [None] * dist.get_world_size()
+        dist.all_gather_object(flags, ok)
+        if not all(flags):  # every rank or none: a rank without peer access sends everybody back to the all-gather
+            self._check(self.l.vkx_comm_p2p_import(self.h, None, C.c_int(0)))
+            return False
+        return True
 
     # ---- shadows
     def shadow_set_noise(self, noise):

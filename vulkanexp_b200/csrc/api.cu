@@ -713,6 +713,7 @@ int vkx_comm_p2p_export(vkx_ctx* ctx, void* handle64) {
 
 int vkx_comm_p2p_import(vkx_ctx* ctx, const void* handles, int count) {
     BIND(ctx);
+    if (!handles && count == 0) { TRY(waitGather(ctx)); ctx->p2p = false; return VKX_OK; } // back to the NCCL all-gather (every rank must do the same)
     if (!handles || count != ctx->nranks || !ctx->p2pSlab) return vkx_fail(ctx, VKX_E_INVALID, "vkx_comm_p2p_import: export first, then pass one 64-byte handle per rank");
     for (int r = 0; r < count; ++r) {
         if (r == ctx->rank) { ctx->peerSlab[r] = ctx->p2pSlab; continue; }

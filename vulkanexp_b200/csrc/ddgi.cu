@@ -323,7 +323,8 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(BlendParams bp, DeviceP
             for (int r = 0; r < pt.n; ++r) *reinterpret_cast<uint4*>(pt.irr[r] + off) = v;
         }
     }
-    if (pt.n) __threadfence_system(); // peer stores are ordered before the arrival flag the next kernel on this stream raises
+    // (no fence here: the arrival flag is raised by the next kernel on this stream, i.e. after this grid and all its stores have completed;
+    // a per-CTA __threadfence_system() made every CTA wait for its NVLink write acknowledgements: blend 0.25 -> 0.32 ms on 2 GPUs)
 }
 
 // Arrival flags of the peer-memory exchange. After its last blend of frame g a rank writes g + 1 into slot [rank] of every rank's flag
