@@ -35,7 +35,7 @@ extern "C" {
 #define VKX_E_INVALID (-1)  /* bad argument / call order */
 #define VKX_E_CUDA (-2)     /* a CUDA runtime call failed; vkx_last_error has the string */
 #define VKX_E_NOMEM (-3)
-#define VKX_E_UNSUPPORTED (-4) /* e.g. textured materials */
+#define VKX_E_UNSUPPORTED (-4) /* e.g. a texture larger than 16384 texels on a side */
 #define VKX_E_NCCL (-5)
 
 #define VKX_MAX_RAYS_PER_PROBE 256 /* IrradianceProbes::MaxRaysPerProbe, src/IrradianceProbes.hpp:42 */
@@ -71,6 +71,18 @@ typedef struct vkx_offset_entry {
     uint32_t vertexOffset;  /* in vertices */
     uint32_t indexOffset;   /* in indices */
 } vkx_offset_entry;
+
+/* One texture of Scene's texture list: the decoded image (what stb_image hands to Image::upload, src/vulkan/Image.cpp:62-111), its
+ * VkFormat (albedo / emissive textures are R8G8B8A8_SRGB, normal / metallic-roughness maps R8G8B8A8_UNORM: src/Scene.cpp:43,671,677)
+ * and the glTF sampler description stored in the .scene file (src/Resources.cpp:88-93; 0 = the reference's default, 9729 / 10497). */
+typedef struct vkx_texture {
+    const uint8_t* pixels; /* width * height RGBA8 texels, row-major, tightly packed */
+    uint32_t width, height;
+    uint32_t srgb;         /* 1: VK_FORMAT_R8G8B8A8_SRGB, 0: VK_FORMAT_R8G8B8A8_UNORM */
+    uint32_t magFilter;    /* glTF: 9728 NEAREST, 9729 LINEAR */
+    uint32_t minFilter;    /* glTF: 9728, 9729, 9984..9987; mapped like glTFToVkFilter / glTFToVkSamplerMipmapMode (src/Resources.cpp:8-32) */
+    uint32_t wrapS, wrapT; /* glTF: 10497 REPEAT, 33071 CLAMP_TO_EDGE, 33648 MIRRORED_REPEAT (src/Resources.cpp:34-43) */
+} vkx_texture;
 
 /* One TLAS instance (VkAccelerationStructureInstanceKHR as filled by Renderer::createTLAS, src/Renderer.cpp:532-551). */
 typedef struct vkx_instance {
@@ -137,11 +149,26 @@ int vkx_abi_version(void);
 /* Uploads the mesh arenas, the offset table (src/Renderer.cpp:97-126), the material SSBO and the instance list
  * (one per MeshRendererComponent, already sorted as Renderer::sortRenderers does, src/Renderer.cpp:512-523).
  * meshIndexCounts[m] = number of indices of mesh entry m (the reference keeps it in VkAccelerationStructure
- * BuildRangeInfo.primitiveCount, src/Renderer.cpp:294-300). Textured materials are rejected (VKX_E_UNSUPPORTED). */
+ * BuildRangeInfo.primitiveCount, src/Renderer.cpp:294-300). Texture indices of the materials refer to the list given to
+ * vkx_scene_textures (call it first; without it every material must be untextured). */
 int vkx_scene_upload(vkx_ctx* ctx, const vkx_vertex* vertices, size_t numVertices, const uint32_t* indices,
                      size_t numIndices, const vkx_offset_entry* offsets, const uint32_t* meshIndexCounts,
                      size_t numMeshes, const vkx_material* materials, size_t numMaterials,
                      const vkx_instance* instances, size_t numInstances);
+
+/* uploadTextures (src/Resources.cpp:46-95): copies the images to the device and generates their mip chains (Image::generateMipmaps,
+ * src/vulkan/Image.cpp:195-275: floor(log2(max(w, h))) + 1 levels, each a LINEAR vkCmdBlitImage of the previous one). The images may
+ * be freed after the call. Sampling follows "sampler spec v1" (DESIGN.md section 9f): the Vulkan texel-filtering equations with exact
+ * fp32 weights, isotropic level of detail (the reference enables anisotropic filtering, whose footprint is implementation-defined).
+ * Consumers: closest-hit shading of probe and reflection rays (textureGrad with the ray differentials of texDerivative,
+ * src/shaders/closesthit.glsl:50-107,161-192) and the alpha cut-out of anyhit.rahit in the sun-shadow and reflection pipelines.
+ * numTextures = 0 removes the list. Must precede the vkx_scene_upload whose materials use the textures. */
+int vkx_scene_textures(vkx_ctx* ctx, const vkx_texture* textures, size_t numTextures);
+/* Parity primitives for the texture path: the generated mip chain (level-major RGBA8, numLevels = floor(log2(max(w, h))) + 1) and
+ * n texture look-ups with explicit gradients (uv: 2 floats, grads: dudx, dvdx, dudy, dvdy per look-up; grads NULL = texture() of a
+ * ray-tracing stage = base level) -> out: 4 floats per look-up. */
+int vkx_texture_download(vkx_ctx* ctx, uint32_t texture, void* texels, size_t texelsBytes, uint32_t* numLevels);
+int vkx_texture_sample(vkx_ctx* ctx, uint32_t texture, const float* uv, const float* grads, size_t n, float* out);
 
 /* Dynamic instances: Renderer::updateAccelerationStructureInstances + updateTLAS (src/Renderer.cpp:671-742, called from
  * onHierarchicalChanges). New transforms / masks / ids for the instance list of vkx_scene_upload (same count, same meshes). The
@@ -159,6 +186,12 @@ int vkx_bvh_download(vkx_ctx* ctx, void* nodes, size_t nodesBytes, void* triangl
  * BVH. anyHit != 0: terminate-on-first-hit query (shadow rays), out[i].t = 1 if occluded else -1. */
 int vkx_trace(vkx_ctx* ctx, const float* origins, const float* directions, size_t n, float tmin, float tmax,
               uint32_t cullMask, int anyHit, vkx_hit* out);
+
+/* The same through a pipeline whose hit group has anyhit.rahit (the direct-light and reflection pipelines,
+ * src/RenderPasses/DirectLightPipeline.cpp:43-51): candidates on materials with an albedo texture whose alpha at the hit is below
+ * 0.01 are ignored (src/shaders/anyhit.rahit:24-48). */
+int vkx_trace_alpha(vkx_ctx* ctx, const float* origins, const float* directions, size_t n, float tmin, float tmax,
+                    uint32_t cullMask, int anyHit, vkx_hit* out);
 
 /* ---- DDGI: IrradianceProbes ----------------------------------------------------------------------------------- */
 /* IrradianceProbes::init (src/IrradianceProbes.cpp:12-104): allocates both atlases (work + sampled), the state

@@ -340,7 +340,7 @@ inline bool intersectTri(const Tri48& tr, const RayCtx& r, float& t, float& u, f
 
 template <bool ANY>
 bool traverse(const Bvh& bvh, const float o[3], const float d[3], float tmin, float tmax, uint32_t cullMask,
-              vkx_hit* hit, Counters* ctr) {
+              vkx_hit* hit, Counters* ctr, const AnyHitFilter* filter) {
     RayCtx r; setupRay(r, o, d);
     float tbest = tmax; bool found = false;
     uint32_t bestInst = 0xFFFFFFFFu, bestPrim = 0xFFFFFFFFu; float bu = 0, bv = 0; bool bback = false;
@@ -374,6 +374,7 @@ bool traverse(const Bvh& bvh, const float o[3], const float d[3], float tmin, fl
             uint32_t inst = tr.inst & 0x00FFFFFFu, prim = tr.prim & 0x7FFFFFFFu;
             bool closer = t < tbest || (found && t == tbest && (inst < bestInst || (inst == bestInst && prim < bestPrim)));
             if (!closer) continue;
+            if (filter && filter->ignore(filter->user, inst, prim, u, v)) continue;
             if (ANY) return true;
             found = true; tbest = t; bestInst = inst; bestPrim = prim; bu = u; bv = v;
             bback = (det > 0.0f) == ((tr.prim & 0x80000000u) != 0); // front <=> det > 0 (unflipped)
@@ -393,11 +394,11 @@ bool traverse(const Bvh& bvh, const float o[3], const float d[3], float tmin, fl
 
 } // namespace
 
-bool traceClosest(const Bvh& bvh, const float o[3], const float d[3], float tmin, float tmax, uint32_t cullMask, vkx_hit& hit, Counters* ctr) {
-    return traverse<false>(bvh, o, d, tmin, tmax, cullMask, &hit, ctr);
+bool traceClosest(const Bvh& bvh, const float o[3], const float d[3], float tmin, float tmax, uint32_t cullMask, vkx_hit& hit, Counters* ctr, const AnyHitFilter* filter) {
+    return traverse<false>(bvh, o, d, tmin, tmax, cullMask, &hit, ctr, filter);
 }
-bool traceAny(const Bvh& bvh, const float o[3], const float d[3], float tmin, float tmax, uint32_t cullMask, Counters* ctr) {
-    return traverse<true>(bvh, o, d, tmin, tmax, cullMask, nullptr, ctr);
+bool traceAny(const Bvh& bvh, const float o[3], const float d[3], float tmin, float tmax, uint32_t cullMask, Counters* ctr, const AnyHitFilter* filter) {
+    return traverse<true>(bvh, o, d, tmin, tmax, cullMask, nullptr, ctr, filter);
 }
 
 } // namespace obvh

@@ -44,6 +44,11 @@ struct Bvh {
 
 struct Counters { uint64_t nodes = 0, tris = 0, rays = 0; };
 
+// anyhit.rahit as a candidate filter: ignore(user, instance, primitive, u, v) == true drops the candidate (ignoreIntersectionEXT).
+// It is asked only for candidates that would otherwise be accepted, so the result is the closest / any non-ignored hit whatever
+// the order of the triangle tests (Vulkan leaves the order of any-hit invocations unspecified too).
+struct AnyHitFilter { bool (*ignore)(const void* user, uint32_t instance, uint32_t primitive, float u, float v); const void* user; };
+
 // Flatten instances into world-space triangles (spec section 3.1) in (instance, primitive) order.
 void flatten(const vkx_vertex* vertices, const uint32_t* indices, const vkx_offset_entry* offsets,
              const uint32_t* meshIndexCounts, const vkx_instance* instances, size_t numInstances,
@@ -53,9 +58,9 @@ void build(const std::vector<Tri48>& flat, const std::vector<float>& lo, const s
 
 // Closest hit. Returns true on hit. hit.t < 0 on miss.
 bool traceClosest(const Bvh& bvh, const float o[3], const float d[3], float tmin, float tmax, uint32_t cullMask,
-                  vkx_hit& hit, Counters* ctr = nullptr);
+                  vkx_hit& hit, Counters* ctr = nullptr, const AnyHitFilter* filter = nullptr);
 // Terminate-on-first-hit occlusion query.
 bool traceAny(const Bvh& bvh, const float o[3], const float d[3], float tmin, float tmax, uint32_t cullMask,
-              Counters* ctr = nullptr);
+              Counters* ctr = nullptr, const AnyHitFilter* filter = nullptr);
 
 } // namespace obvh

@@ -36,6 +36,37 @@ int orc_scene_upload(orc_ctx* c, const vkx_vertex* v, size_t nv, const uint32_t*
     s.meshIndexCounts.assign(counts, counts + nm); s.materials.assign(mat, mat + nmat); s.instances.assign(inst, inst + ninst);
     return 0;
 }
+// Scene texture list (mip chains generated here, sampler spec v1); numTextures = 0 clears it.
+int orc_scene_textures(orc_ctx* c, const vkx_texture* tex, size_t n) {
+    c->scene.textures.clear();
+    for (size_t i = 0; i < n; ++i) c->scene.textures.push_back(otex::makeTexture(tex[i]));
+    return 0;
+}
+int orc_texture_download(orc_ctx* c, uint32_t index, void* texels, size_t bytes, uint32_t* levels) {
+    if (index >= c->scene.textures.size()) return -1;
+    const otex::Texture& t = c->scene.textures[index];
+    if (levels) *levels = t.levels;
+    size_t total = 0; for (auto& l : t.mip) total += l.size() * 4;
+    if (texels) { if (bytes < total) return -1; char* o = static_cast<char*>(texels); for (auto& l : t.mip) { std::memcpy(o, l.data(), l.size() * 4); o += l.size() * 4; } }
+    return 0;
+}
+int orc_texture_sample(orc_ctx* c, uint32_t index, const float* uv, const float* grads, size_t n, float* out) {
+    if (index >= c->scene.textures.size()) return -1;
+    const otex::Texture& t = c->scene.textures[index];
+    for (size_t i = 0; i < n; ++i) {
+        otex::RGBA r = grads ? otex::sampleGrad(t, uv[2 * i], uv[2 * i + 1], grads[4 * i], grads[4 * i + 1], grads[4 * i + 2], grads[4 * i + 3]) : otex::sampleBase(t, uv[2 * i], uv[2 * i + 1]);
+        out[4 * i] = r.r; out[4 * i + 1] = r.g; out[4 * i + 2] = r.b; out[4 * i + 3] = r.a;
+    }
+    return 0;
+}
+// texDerivative for one hit (test hook): v = 3 vertices, o2w = row-major 3x4 instance transform
+int orc_tex_derivative(const float position[3], const float rayOrigin[3], const float transform[12], const vkx_vertex* v, const float raydx[3], const float raydy[3], float out[4]) {
+    ovm::mat3 m; for (int c = 0; c < 3; ++c) m[c] = ovm::V3(transform[c], transform[4 + c], transform[8 + c]);
+    ovm::vec4 g = oddgi::texDerivative(ovm::V3(position[0], position[1], position[2]), ovm::V3(rayOrigin[0], rayOrigin[1], rayOrigin[2]), m, v[0], v[1], v[2],
+                                       ovm::V3(raydx[0], raydx[1], raydx[2]), ovm::V3(raydy[0], raydy[1], raydy[2]));
+    out[0] = g.x; out[1] = g.y; out[2] = g.z; out[3] = g.w;
+    return 0;
+}
 int orc_bvh_build(orc_ctx* c) { oddgi::sceneFinalize(c->scene); return 0; }
 int orc_bvh_info(orc_ctx* c, vkx_bvh_info* out) {
     const obvh::Bvh& b = c->scene.bvh;
@@ -53,15 +84,19 @@ int orc_bvh_download(orc_ctx* c, void* nodes, size_t nb, void* tris, size_t tb) 
 }
 int orc_trace(orc_ctx* c, const float* o, const float* d, size_t n, float tmin, float tmax, uint32_t mask, int any, vkx_hit* out, uint64_t* counters) {
     obvh::Counters total;
+    // any: bit 0 terminate on first hit, bit 1 run anyhit.rahit on the candidates (alpha cut-outs)
+    const obvh::AnyHitFilter filter = oddgi::anyHitFilter(c->scene);
+    const obvh::AnyHitFilter* flt = ((any & 2) && !c->scene.textures.empty()) ? &filter : nullptr;
+    any &= 1;
 #pragma omp parallel
     {
         obvh::Counters ctr;
 #pragma omp for schedule(dynamic, 256)
         for (int64_t i = 0; i < int64_t(n); ++i) {
             if (any) {
-                bool h = obvh::traceAny(c->scene.bvh, o + 3 * i, d + 3 * i, tmin, tmax, mask, &ctr);
+                bool h = obvh::traceAny(c->scene.bvh, o + 3 * i, d + 3 * i, tmin, tmax, mask, &ctr, flt);
                 out[i].t = h ? 1.0f : -1.0f; out[i].instance = 0xFFFFFFFFu; out[i].primitive = 0xFFFFFFFFu; out[i].u = out[i].v = 0.0f;
-            } else obvh::traceClosest(c->scene.bvh, o + 3 * i, d + 3 * i, tmin, tmax, mask, out[i], &ctr);
+            } else obvh::traceClosest(c->scene.bvh, o + 3 * i, d + 3 * i, tmin, tmax, mask, out[i], &ctr, flt);
         }
 #pragma omp critical
         { total.nodes += ctr.nodes; total.tris += ctr.tris; total.rays += ctr.rays; }

@@ -8,7 +8,8 @@
 // path. What *is* pinned: the border tables (tests/golden/border_tables.json, extracted from
 // probesCopyBorders.comp), the POD layouts, and glm::sphericalRand/genBasis (tests/golden/glm_pin.json, produced by
 // compiling the reference's vendored GLM). Undefined behaviour in the shaders is resolved as SURVEY A.5 decrees.
-// Untextured materials only (texture filtering is implementation-defined in the reference).
+// Textures: closesthit.glsl:161-192 through "sampler spec v1" (texture.h; SURVEY A.8: filtering is implementation-defined in the
+// reference, the decrees are listed there).
 #include "ddgi.h"
 #include "packing.h"
 #include <cmath>
@@ -403,14 +404,83 @@ void classify(const Scene& s, Probes& p, const float orientation[16]) {
     }
 }
 
+// ---------------------------------------------------------------- textures: anyhit.rahit, texDerivative
+vec3 rotateAxis(vec3 p, vec3 axis, float angle) { // common.glsl:6-8
+    return mix(dot(axis, p) * axis, p, std::cos(angle)) + cross(axis, p) * std::sin(angle);
+}
+
+static inline mat3 objectToWorld3(const vkx_instance& inst) { // mat3(gl_ObjectToWorldEXT): column c = (T[0][c], T[1][c], T[2][c])
+    const float* T = inst.transform;
+    mat3 m;
+    for (int c = 0; c < 3; ++c) m[c] = V3(T[c], T[4 + c], T[8 + c]);
+    return m;
+}
+
+bool anyHitIgnores(const Scene& s, uint32_t instance, uint32_t primitive, float u, float v) { // anyhit.rahit:24-48
+    const vkx_offset_entry& oe = s.offsets[s.instances[instance].meshEntry];
+    const vkx_material& m = s.materials[oe.materialIndex];
+    if (m.albedoTexture == VKX_INVALID_TEXTURE) return false; // :29
+    const vkx_vertex* vx[3];
+    for (int c = 0; c < 3; ++c) vx[c] = &s.vertices[oe.vertexOffset + s.indices[oe.indexOffset + 3 * primitive + c]];
+    vec3 bary = V3(1.0f - u - v, u, v); // :40
+    vec2 texCoord = V2(vx[0]->texCoord[0], vx[0]->texCoord[1]) * bary.x + V2(vx[1]->texCoord[0], vx[1]->texCoord[1]) * bary.y + V2(vx[2]->texCoord[0], vx[2]->texCoord[1]) * bary.z; // :41
+    otex::RGBA texColor = otex::sampleBase(s.textures[m.albedoTexture], texCoord.x, texCoord.y); // :43
+    return texColor.a < 1e-2f; // :45-46
+}
+static bool anyHitThunk(const void* user, uint32_t instance, uint32_t primitive, float u, float v) { return anyHitIgnores(*static_cast<const Scene*>(user), instance, primitive, u, v); }
+obvh::AnyHitFilter anyHitFilter(const Scene& s) { return obvh::AnyHitFilter{anyHitThunk, &s}; }
+
+vec4 texDerivative(vec3 worldPosition, vec3 rayOrigin, const mat3& o2w, const vkx_vertex& v0, const vkx_vertex& v1, const vkx_vertex& v2, vec3 raydx, vec3 raydy) { // closesthit.glsl:50-107
+    auto P = [](const vkx_vertex& v) { return V3(v.pos[0], v.pos[1], v.pos[2]); };
+    auto UV = [](const vkx_vertex& v) { return V2(v.texCoord[0], v.texCoord[1]); };
+    vec3 dpdu, dpdv;
+    vec3 p01 = o2w * (P(v1) - P(v0));
+    vec3 p02 = o2w * (P(v2) - P(v0));
+    vec3 normal = normalize(cross(p01, p02));
+    vec2 tex01 = UV(v1) - UV(v0);
+    vec2 tex02 = UV(v2) - UV(v0);
+    float det = tex01.x * tex02.y - tex01.y * tex02.x;
+    if (std::fabs(det) < 1e-10f) {
+        dpdu = normalize(std::fabs(normal.x) > std::fabs(normal.y) ? V3(-normal.z, 0, normal.x) : V3(0, -normal.z, normal.y));
+        dpdv = cross(normal, dpdu);
+    } else {
+        float inv_det = 1.0f / det;
+        dpdu = (tex02.y * p01 - tex01.y * p02) * inv_det;
+        dpdv = (-tex02.x * p01 + tex01.x * p02) * inv_det;
+    }
+    float tx = dot(worldPosition - rayOrigin, normal) / dot(raydx, normal);
+    float ty = dot(worldPosition - rayOrigin, normal) / dot(raydy, normal);
+    vec3 dpdx = (rayOrigin + raydx * tx) - worldPosition;
+    vec3 dpdy = (rayOrigin + raydy * ty) - worldPosition;
+    float dudx = 0, dvdx = 0, dudy = 0, dvdy = 0;
+    {
+        int dim0 = 0, dim1 = 1;
+        vec3 a = abs(normal);
+        if (a.x > a.y && a.x > a.z) { dim0 = 1; dim1 = 2; }
+        else if (a.y > a.z) { dim0 = 0; dim1 = 2; }
+        float a00 = dpdu[dim0], a01 = dpdv[dim0], a10 = dpdu[dim1], a11 = dpdv[dim1];
+        float det2 = a00 * a11 - a01 * a10;
+        if (std::fabs(det2) > 1e-10f) {
+            float inv_det = 1.0f / det2;
+            dudx = (a11 * dpdx[dim0] - a01 * dpdx[dim1]) * inv_det;
+            dvdx = (-a10 * dpdx[dim0] - a00 * dpdx[dim1]) * inv_det; // sic (:98)
+            dudy = (a11 * dpdy[dim0] - a01 * dpdy[dim1]) * inv_det;
+            dvdy = (-a10 * dpdy[dim0] - a00 * dpdy[dim1]) * inv_det; // sic (:101)
+        }
+    }
+    return V4(dudx, dvdx, dudy, dvdy);
+}
+
 // ---------------------------------------------------------------- traceProbes.rgen + closesthit.glsl + miss.rmiss
 static vec4 shadeRay(const Scene& s, const Probes& p, const vkx_light& light, vec3 origin, vec3 direction, float tmax,
                      vkx_hit& hit, uint8_t& shadowFlag, obvh::Counters* ctr, obvh::Counters* sctr, uint64_t& front,
-                     float tmin = 0.01f /* traceProbes.rgen:27 */, uint32_t cullMask = VKX_INSTANCE_STATIC | VKX_INSTANCE_DYNAMIC /* :43 */) {
+                     float tmin, uint32_t cullMask, vec3 raydx, vec3 raydy, bool anyHit) {
     shadowFlag = 0;
     vec3 lightDir = V3(light.direction[0], light.direction[1], light.direction[2]);
     vec3 lightColor = V3(light.color[0], light.color[1], light.color[2]);
-    if (!obvh::traceClosest(s.bvh, &origin.x, &direction.x, tmin, tmax, cullMask, hit, ctr)) {
+    const obvh::AnyHitFilter filter = anyHitFilter(s);
+    const obvh::AnyHitFilter* flt = (anyHit && !s.textures.empty()) ? &filter : nullptr;
+    if (!obvh::traceClosest(s.bvh, &origin.x, &direction.x, tmin, tmax, cullMask, hit, ctr, flt)) {
         vec3 c = sky(origin, direction, lightDir, lightColor, light.color[3], true); // miss.rmiss:19-22
         return V4(c, -1.0f);
     }
@@ -434,6 +504,33 @@ static vec4 shadeRay(const Scene& s, const Probes& p, const vkx_light& light, ve
     vec4 albedo = V4(m.baseColorFactor[0], m.baseColorFactor[1], m.baseColorFactor[2], 1.0f);
     float metalness = m.metallicFactor, roughness = m.roughnessFactor;
     vec3 emissiveLight = V3(m.emissiveFactor[0], m.emissiveFactor[1], m.emissiveFactor[2]);
+    const bool textured = m.albedoTexture != VKX_INVALID_TEXTURE || m.normalTexture != VKX_INVALID_TEXTURE ||
+                          m.metallicRoughnessTexture != VKX_INVALID_TEXTURE || m.emissiveTexture != VKX_INVALID_TEXTURE;
+    if (textured) { // :157,161-192 (without a texture none of this reaches the result)
+        auto UV = [&](int c) { return V2(vx[c]->texCoord[0], vx[c]->texCoord[1]); };
+        vec2 texCoord = UV(0) * bary.x + UV(1) * bary.y + UV(2) * bary.z; // :157
+        vec4 grad = texDerivative(position, origin, objectToWorld3(inst), *vx[0], *vx[1], *vx[2], raydx, raydy); // :161
+        auto tex = [&](uint32_t index) {
+            otex::RGBA c = otex::sampleGrad(s.textures[index], texCoord.x, texCoord.y, grad.x, grad.y, grad.z, grad.w); // textureGrad(.., grad.xy, grad.zw)
+            return V4(c.r, c.g, c.b, c.a);
+        };
+        if (m.albedoTexture != VKX_INVALID_TEXTURE) albedo = albedo * tex(m.albedoTexture); // :163-166
+        if (m.normalTexture != VKX_INVALID_TEXTURE) { // :169-177
+            auto T = [&](int c) { return V4(vx[c]->tangent[0], vx[c]->tangent[1], vx[c]->tangent[2], vx[c]->tangent[3]); };
+            vec4 tangentData = T(0) * bary.x + T(1) * bary.y + T(2) * bary.z;
+            vec3 td = xyz(tangentData);
+            vec3 tangent = normalize(V3(dot(td, W[0]), dot(td, W[1]), dot(td, W[2])));
+            float tangentHandedness = tangentData.w;
+            vec3 bitangent = cross(normal, tangent) * tangentHandedness;
+            vec3 mappedNormal = normalize(2.0f * xyz(tex(m.normalTexture)) - 1.0f);
+            normal = normalize(tangent * mappedNormal.x + bitangent * mappedNormal.y + normal * mappedNormal.z); // mat3(tangent, bitangent, normal) * mappedNormal
+        }
+        if (m.metallicRoughnessTexture != VKX_INVALID_TEXTURE) { // :181-185
+            vec4 mr = tex(m.metallicRoughnessTexture);
+            metalness *= mr.z; roughness *= mr.y;
+        }
+        if (m.emissiveTexture != VKX_INVALID_TEXTURE) emissiveLight *= xyz(tex(m.emissiveTexture)); // :188-190
+    }
     vec3 color = V3(0.0f) + emissiveLight; // :194
     vec3 f0 = V3(0.04f);
     vec3 diffuseColor = xyz(albedo) * (1.0f - f0);
@@ -445,7 +542,7 @@ static vec4 shadeRay(const Scene& s, const Probes& p, const vkx_light& light, ve
     vec3 indirectLight = sampleProbes(p, position, normal, -direction); // :248
     color += indirectLight * diffuseColor;
     // shadow ray :252-281 (tmin 0.1, tmax 10000, cull mask 0xFF, un-normalised light direction)
-    bool isShadowed = obvh::traceAny(s.bvh, &position.x, &lightDir.x, 0.1f, 10000.0f, 0xFFu, sctr);
+    bool isShadowed = obvh::traceAny(s.bvh, &position.x, &lightDir.x, 0.1f, 10000.0f, 0xFFu, sctr, flt);
     shadowFlag = isShadowed ? 2 : 1;
     if (!isShadowed) {
         vec4 pbr = pbrMetallicRoughness(normal, normalize(-direction), lightColor, lightDir, albedo, metalness, roughness);
@@ -458,9 +555,9 @@ static vec4 shadeRay(const Scene& s, const Probes& p, const vkx_light& light, ve
 // One ray through closest-hit / miss shading with the caller's ray interval and cull mask (reflection.rgen:186 traces with
 // tmin 0.1, tmax 10000, mask 0xff and payload.recursionDepth = 1, i.e. the same shading as the probe rays).
 vec4 traceAndShade(const Scene& s, const Probes& p, const vkx_light& light, vec3 origin, vec3 direction, float tmin, float tmax, uint32_t cullMask,
-                   vkx_hit& hit, uint8_t& shadowFlag) {
+                   vkx_hit& hit, uint8_t& shadowFlag, vec3 raydx, vec3 raydy, bool anyHit) {
     uint64_t front = 0;
-    return shadeRay(s, p, light, origin, direction, tmax, hit, shadowFlag, nullptr, nullptr, front, tmin, cullMask);
+    return shadeRay(s, p, light, origin, direction, tmax, hit, shadowFlag, nullptr, nullptr, front, tmin, cullMask, raydx, raydy, anyHit);
 }
 
 // ---------------------------------------------------------------- probesUpdate.glsl + probesCopyBorders.comp
@@ -505,7 +602,14 @@ void update(const Scene& s, Probes& p, const vkx_grid_info& g, const vkx_light& 
             for (uint32_t r = 0; r < N; ++r) {
                 vec3 direction = V3(p.dirs[3 * r], p.dirs[3 * r + 1], p.dirs[3 * r + 2]);
                 size_t ri = size_t(slot) * N + r;
-                vec4 c = shadeRay(s, p, light, origin, direction, tmax, p.hits[ri], p.shadow[ri], &ctr, &sctr, front);
+                // payload.raydx / raydy, traceProbes.rgen:40-41 (NaN when the direction is parallel to the axis; only textured hits read them)
+                vec3 raydx = V3(0.0f), raydy = V3(0.0f);
+                if (!s.textures.empty()) {
+                    raydx = rotateAxis(direction, normalize(cross(direction, V3(1, 0, 0))), 0.001f);
+                    raydy = rotateAxis(direction, normalize(cross(direction, V3(0, 1, 0))), 0.001f);
+                }
+                vec4 c = shadeRay(s, p, light, origin, direction, tmax, p.hits[ri], p.shadow[ri], &ctr, &sctr, front, 0.01f /* traceProbes.rgen:27 */,
+                                  VKX_INSTANCE_STATIC | VKX_INSTANCE_DYNAMIC /* :43 */, raydx, raydy, false);
                 p.rays[4 * ri + 0] = c.x; p.rays[4 * ri + 1] = c.y; p.rays[4 * ri + 2] = c.z; p.rays[4 * ri + 3] = c.w;
             }
         }

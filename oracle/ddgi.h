@@ -5,6 +5,7 @@
 #include <vector>
 #include "../include/vkx.h"
 #include "bvh.h"
+#include "texture.h"
 #include "vmath.h"
 
 namespace oddgi {
@@ -17,8 +18,18 @@ struct Scene {
     std::vector<vkx_material> materials;
     std::vector<vkx_instance> instances;
     std::vector<ovm::mat3> worldToObject; // per instance, inverse of the 3x3 part (math convention W[row][col] = c[col][row])
+    std::vector<otex::Texture> textures;  // Scene's texture list with generated mip chains (sampler spec v1, texture.h)
     obvh::Bvh bvh;
 };
+
+// anyhit.rahit:24-48 for one candidate: true = ignoreIntersectionEXT (albedo alpha < 1e-2 at the hit's texture coordinate)
+bool anyHitIgnores(const Scene& s, uint32_t instance, uint32_t primitive, float u, float v);
+// The filter object for obvh::traceClosest / traceAny in pipelines whose hit group has the any-hit shader (direct light, reflection)
+obvh::AnyHitFilter anyHitFilter(const Scene& s);
+ovm::vec3 rotateAxis(ovm::vec3 p, ovm::vec3 axis, float angle); // common.glsl:6-8
+// texDerivative, closesthit.glsl:50-107 -> (dudx, dvdx, dudy, dvdy)
+ovm::vec4 texDerivative(ovm::vec3 worldPosition, ovm::vec3 rayOrigin, const ovm::mat3& objectToWorld, const vkx_vertex& v0, const vkx_vertex& v1, const vkx_vertex& v2,
+                        ovm::vec3 raydx, ovm::vec3 raydy);
 
 struct Probes {
     vkx_grid_info grid{};
@@ -46,9 +57,11 @@ void classify(const Scene& s, Probes& p, const float orientation[16]);
 void update(const Scene& s, Probes& p, const vkx_grid_info& g, const vkx_light& light, const float orientation[16],
             const uint32_t* indices, uint32_t count, int threads);
 
-// closest-hit / miss shading of one ray (closesthit.glsl with recursionDepth >= 1, miss.rmiss); returns (rgb, depth) like the payload
+// closest-hit / miss shading of one ray (closesthit.glsl with recursionDepth >= 1, miss.rmiss); returns (rgb, depth) like the payload.
+// raydx / raydy: payload ray differentials set by the ray-generation shader; anyHit: the pipeline's hit group has anyhit.rahit
+// (reflection pipeline: yes, src/RenderPasses/ReflectionPipeline.cpp:51; probe pipeline: no, src/IrradianceProbes.cpp:244-254).
 ovm::vec4 traceAndShade(const Scene& s, const Probes& p, const vkx_light& light, ovm::vec3 origin, ovm::vec3 direction, float tmin, float tmax, uint32_t cullMask,
-                        vkx_hit& hit, uint8_t& shadowFlag);
+                        vkx_hit& hit, uint8_t& shadowFlag, ovm::vec3 raydx, ovm::vec3 raydy, bool anyHit);
 ovm::vec3 sky(ovm::vec3 rayOrigin, ovm::vec3 rayDirection, ovm::vec3 sunPosition, ovm::vec3 sunColor, float sunBrightnessFactor, bool showSun);
 ovm::vec4 pbrMetallicRoughness(ovm::vec3 normal, ovm::vec3 view, ovm::vec3 lightColor, ovm::vec3 lightDirection, ovm::vec4 albedo, float metalness, float roughness);
 ovm::vec3 sampleProbes(const Probes& p, ovm::vec3 position, ovm::vec3 normal, ovm::vec3 toCamera);

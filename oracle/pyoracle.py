@@ -6,7 +6,7 @@ import subprocess
 
 import numpy as np
 
-from vulkanexp_b200.pods import BvhInfo, Camera, GridInfo, HIT_DTYPE, Light, NODE_DTYPE, TRI_DTYPE
+from vulkanexp_b200.pods import BvhInfo, Camera, GridInfo, HIT_DTYPE, Light, NODE_DTYPE, TRI_DTYPE, VERTEX_DTYPE, mip_chain_texels, texture_array
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
@@ -54,7 +54,33 @@ class Oracle:
     def __del__(self):
         self.close()
 
+    def scene_textures(self, textures):
+        arr, keep = texture_array(textures)
+        self.l.orc_scene_textures(self.h, arr, C.c_size_t(len(textures)))
+        self._tex_dims = [(k.shape[1], k.shape[0]) for k in keep]
+
+    def texture_download(self, index):
+        w, h = self._tex_dims[index]
+        buf = np.zeros(mip_chain_texels(w, h) * 4, dtype=np.uint8)
+        levels = C.c_uint32(0)
+        assert self.l.orc_texture_download(self.h, C.c_uint32(index), _p(buf), C.c_size_t(buf.nbytes), C.byref(levels)) == 0
+        out, off = [], 0
+        for l in range(levels.value):
+            lw, lh = max(1, w >> l), max(1, h >> l)
+            out.append(buf[off : off + lw * lh * 4].reshape(lh, lw, 4))
+            off += lw * lh * 4
+        return out
+
+    def texture_sample(self, index, uv, grads=None):
+        uv = np.ascontiguousarray(uv, dtype=np.float32)
+        g = np.ascontiguousarray(grads, dtype=np.float32) if grads is not None else None
+        out = np.zeros((len(uv), 4), dtype=np.float32)
+        assert self.l.orc_texture_sample(self.h, C.c_uint32(index), _p(uv), _p(g), C.c_size_t(len(uv)), _p(out)) == 0
+        return out
+
     def scene_upload(self, flat):
+        if "textures" in flat:
+            self.scene_textures(flat["textures"])
         v, i, o, c, m, inst = (np.ascontiguousarray(flat[k]) for k in ("vertices", "indices", "offsets", "mesh_index_counts", "materials", "instances"))
         self._keep = (v, i, o, c, m, inst)
         self.l.orc_scene_upload(self.h, _p(v), C.c_size_t(len(v)), _p(i), C.c_size_t(len(i)), _p(o), _p(c), C.c_size_t(len(o)), _p(m), C.c_size_t(len(m)), _p(inst), C.c_size_t(len(inst)))
@@ -74,12 +100,12 @@ class Oracle:
         self.l.orc_bvh_download(self.h, _p(nodes), C.c_size_t(nodes.nbytes), _p(tris), C.c_size_t(tris.nbytes))
         return nodes, tris
 
-    def trace(self, origins, dirs, tmin, tmax, mask=0xFF, any_hit=False):
+    def trace(self, origins, dirs, tmin, tmax, mask=0xFF, any_hit=False, alpha_test=False):
         o = np.ascontiguousarray(origins, dtype=np.float32)
         d = np.ascontiguousarray(dirs, dtype=np.float32)
         out = np.zeros(len(o), dtype=HIT_DTYPE)
         ctr = np.zeros(3, dtype=np.uint64)
-        self.l.orc_trace(self.h, _p(o), _p(d), C.c_size_t(len(o)), C.c_float(tmin), C.c_float(tmax), C.c_uint32(mask), C.c_int(int(any_hit)), _p(out), _p(ctr))
+        self.l.orc_trace(self.h, _p(o), _p(d), C.c_size_t(len(o)), C.c_float(tmin), C.c_float(tmax), C.c_uint32(mask), C.c_int(int(any_hit) | (2 if alpha_test else 0)), _p(out), _p(ctr))
         self.trace_counters = ctr
         return out
 

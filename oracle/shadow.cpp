@@ -74,7 +74,9 @@ void gbufferGenerate(const oddgi::Scene& s, State& st, const vkx_camera& cam) {
         float* ar = &st.albedoRoughness[pi_]; float* em = &st.emissive[pi_];
         pd[0] = pd[1] = pd[2] = pd[3] = 0.0f; nm[0] = nm[1] = nm[2] = nm[3] = 0.0f;
         ar[0] = ar[1] = ar[2] = ar[3] = 0.0f; em[0] = em[1] = em[2] = em[3] = 0.0f;
-        if (!obvh::traceClosest(s.bvh, &origin.x, &dir.x, 0.001f, 100000.0f, 0xFFu, h)) continue;
+        // Fixture, not a transliteration of the raster pass: cut-outs follow anyhit.rahit (alpha < 0.01; GBuffer.frag:38 discards below 0.05)
+        const obvh::AnyHitFilter filter = oddgi::anyHitFilter(s);
+        if (!obvh::traceClosest(s.bvh, &origin.x, &dir.x, 0.001f, 100000.0f, 0xFFu, h, nullptr, s.textures.empty() ? nullptr : &filter)) continue;
         vec3 position = dir * h.t + origin;
         const vkx_instance& inst = s.instances[h.instance];
         const vkx_offset_entry& oe = s.offsets[inst.meshEntry];
@@ -213,7 +215,9 @@ void frame(const oddgi::Scene& s, State& st, const vkx_camera& cur, const vkx_ca
         if (dirOverride) direction = V3(dirOverride[3 * pix], dirOverride[3 * pix + 1], dirOverride[3 * pix + 2]);
         st.dirs[3 * pix] = direction.x; st.dirs[3 * pix + 1] = direction.y; st.dirs[3 * pix + 2] = direction.z;
         if (dot(direction, normal) > 0.0f) {
-            bool isShadowed = obvh::traceAny(s.bvh, &position.x, &direction.x, 0.01f, 10000.0f, 0xFFu);
+            // the direct-light pipeline's hit group is anyhit.rahit alone (src/RenderPasses/DirectLightPipeline.cpp:43-51)
+            const obvh::AnyHitFilter filter = oddgi::anyHitFilter(s);
+            bool isShadowed = obvh::traceAny(s.bvh, &position.x, &direction.x, 0.01f, 10000.0f, 0xFFu, nullptr, s.textures.empty() ? nullptr : &filter);
             st.mask[pix] = isShadowed ? 2 : 1;
             if (!isShadowed) {
                 outColor = 1.0f;
@@ -319,7 +323,10 @@ void reflectionFrame(const oddgi::Scene& s, const oddgi::Probes& probes, State& 
         if (dirOverride) direction = V3(dirOverride[3 * pix], dirOverride[3 * pix + 1], dirOverride[3 * pix + 2]);
         st.reflDirs[3 * pix] = direction.x; st.reflDirs[3 * pix + 1] = direction.y; st.reflDirs[3 * pix + 2] = direction.z;
         vkx_hit hit; uint8_t shadowFlag = 0;
-        vec4 c = oddgi::traceAndShade(s, probes, light, position, direction, 0.1f, 10000.0f, 0xFFu, hit, shadowFlag);
+        // payload.raydx / raydy, reflection.rgen:169-170; the reflection pipeline's hit group has the any-hit shader
+        vec3 raydx = V3(0.0f), raydy = V3(0.0f);
+        if (!s.textures.empty()) { raydx = oddgi::rotateAxis(direction, normal, 0.001f); raydy = oddgi::rotateAxis(direction, cross(normal, direction), 0.001f); }
+        vec4 c = oddgi::traceAndShade(s, probes, light, position, direction, 0.1f, 10000.0f, 0xFFu, hit, shadowFlag, raydx, raydy, true);
         if (c.w < 0.0f) { st.reflMask[pix] = 1; hit = vkx_hit{}; hit.t = -1.0f; }
         else st.reflMask[pix] = (hit.primitive & 0x80000000u) ? 2 : (shadowFlag == 2 ? 4 : 3);
         st.reflHits[pix] = hit;

@@ -37,6 +37,8 @@ def get_scene(name):
             s = synth.make_cfg2()
         elif name == "cfg3":
             s = synth.make_cfg3()
+        elif name == "tcourt":  # every texture slot in use + a cut-out canopy (sampler spec v1)
+            s = synth.make_textured_court()
         elif name == "tiny":
             s = synth.make_open_court(columns=2, col_segments=6, col_stacks=1)
         else:

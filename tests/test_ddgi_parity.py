@@ -53,7 +53,7 @@ def _compare_update(o, g, frame):
     return irr_flip, dep_flip, st_diff
 
 
-@pytest.mark.parametrize("scene,res,rays", [("court", (8, 8, 8), 64), ("cfg1", (8, 8, 8), 64), ("court", (6, 5, 7), 256), ("tiny", (4, 3, 5), 17)])
+@pytest.mark.parametrize("scene,res,rays", [("court", (8, 8, 8), 64), ("cfg1", (8, 8, 8), 64), ("court", (6, 5, 7), 256), ("tiny", (4, 3, 5), 17), ("tcourt", (8, 8, 8), 64)])
 def test_classify_and_multi_frame_update(oracle_lib, scene, res, rays):
     o, g, flat, grid = _setup(oracle_lib, scene, res, rays)
     host = oracle_lib.HostLogic()

@@ -48,7 +48,8 @@ def _gbuffer(o, g, cam, rng):
     return pd, nm, ar
 
 
-@pytest.mark.parametrize("scene,res,eye,target", [("court", (8, 6, 8), (-5.0, 2.5, 4.5), (0.0, 3.0, 0.0)), ("cfg1", (8, 8, 8), (-3.0, 2.0, 3.5), (0.5, 1.5, 0.0))])
+@pytest.mark.parametrize("scene,res,eye,target", [("court", (8, 6, 8), (-5.0, 2.5, 4.5), (0.0, 3.0, 0.0)), ("cfg1", (8, 8, 8), (-3.0, 2.0, 3.5), (0.5, 1.5, 0.0)),
+                                                    ("tcourt", (8, 6, 8), (-5.0, 2.5, 4.5), (0.0, 3.0, 0.0))])
 def test_reflection_frames_match_oracle(oracle_lib, scene, res, eye, target):
     o, g, light = _prepare(oracle_lib, scene, res)
     rng = np.random.default_rng(11)

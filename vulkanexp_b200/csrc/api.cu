@@ -106,7 +106,9 @@ void vkx_destroy(vkx_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->comm) ncclCommDestroy(reinterpret_cast<ncclComm_t>(ctx->comm));
-    freeProbes(ctx); freeShadow(ctx);
+    freeProbes(ctx); freeShadow(ctx); freeTextures(ctx);
+    if (ctx->dSrgbLut) cudaFree(ctx->dSrgbLut);
+    if (ctx->dSrgbThreshold) cudaFree(ctx->dSrgbThreshold);
     void* ptrs[] = {ctx->dVertices, ctx->dIndices, ctx->dOffsets, ctx->dMeshCounts, ctx->dMaterials, ctx->dInstances, ctx->dWorldToObject, ctx->dInstTriBase, ctx->dNodes, ctx->dTris, ctx->dNoise};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -144,10 +146,14 @@ int vkx_scene_upload(vkx_ctx* ctx, const vkx_vertex* vertices, size_t numVertice
     if ((numVertices && !vertices) || (numIndices && !indices) || (numMeshes && (!offsets || !meshIndexCounts)) || (numMaterials && !materials) || (numInstances && !instances))
         return vkx_fail(ctx, VKX_E_INVALID, "vkx_scene_upload: null array");
     if (numInstances >= (1u << 24)) return vkx_fail(ctx, VKX_E_UNSUPPORTED, "more than 2^24 instances");
-    for (size_t m = 0; m < numMaterials; ++m)
-        if (materials[m].albedoTexture != VKX_INVALID_TEXTURE || materials[m].normalTexture != VKX_INVALID_TEXTURE ||
-            materials[m].metallicRoughnessTexture != VKX_INVALID_TEXTURE || materials[m].emissiveTexture != VKX_INVALID_TEXTURE)
-            return vkx_fail(ctx, VKX_E_UNSUPPORTED, "material %zu is textured; texture sampling is implementation-defined in the reference and not supported (SURVEY A.8)", m);
+    uint32_t texturesUsed = 0;
+    for (size_t m = 0; m < numMaterials; ++m) { // texture indices refer to the list of vkx_scene_textures
+        const uint32_t t[4] = {materials[m].albedoTexture, materials[m].normalTexture, materials[m].metallicRoughnessTexture, materials[m].emissiveTexture};
+        for (uint32_t i : t)
+            if (i != VKX_INVALID_TEXTURE && i >= ctx->hTextures.size())
+                return vkx_fail(ctx, VKX_E_INVALID, "material %zu uses texture %u but vkx_scene_textures provided %zu textures", m, i, ctx->hTextures.size());
+        for (uint32_t i : t) if (i != VKX_INVALID_TEXTURE) texturesUsed = std::max(texturesUsed, i + 1u);
+    }
     for (size_t m = 0; m < numMeshes; ++m) {
         if (meshIndexCounts[m] % 3 != 0) return vkx_fail(ctx, VKX_E_INVALID, "mesh %zu: index count %u is not a multiple of 3", m, meshIndexCounts[m]);
         if (size_t(offsets[m].indexOffset) + meshIndexCounts[m] > numIndices) return vkx_fail(ctx, VKX_E_INVALID, "mesh %zu: index range out of bounds", m);
@@ -194,7 +200,7 @@ int vkx_scene_upload(vkx_ctx* ctx, const vkx_vertex* vertices, size_t numVertice
     TRY(upload(ctx, &ctx->dInstTriBase, ctx->hInstTriBase.data(), ctx->hInstTriBase.size()));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->numVertices = numVertices; ctx->numIndices = numIndices; ctx->numMeshes = numMeshes; ctx->numMaterials = numMaterials;
-    ctx->numInstances = numInstances; ctx->numFlatTris = total;
+    ctx->numInstances = numInstances; ctx->numFlatTris = total; ctx->texturesUsed = texturesUsed;
     ctx->bvhBuilt = false;
     return VKX_OK;
 }
@@ -246,7 +252,14 @@ int vkx_trace(vkx_ctx* ctx, const float* origins, const float* directions, size_
     BIND(ctx);
     if (!ctx->bvhBuilt) return vkx_fail(ctx, VKX_E_INVALID, "BVH not built");
     if (n && (!origins || !directions || !out)) return vkx_fail(ctx, VKX_E_INVALID, "vkx_trace: null array");
-    return traceHostRays(ctx, origins, directions, n, tmin, tmax, cullMask, anyHit, out);
+    return traceHostRays(ctx, origins, directions, n, tmin, tmax, cullMask, anyHit, out, false);
+}
+
+int vkx_trace_alpha(vkx_ctx* ctx, const float* origins, const float* directions, size_t n, float tmin, float tmax, uint32_t cullMask, int anyHit, vkx_hit* out) {
+    BIND(ctx);
+    if (!ctx->bvhBuilt) return vkx_fail(ctx, VKX_E_INVALID, "BVH not built");
+    if (n && (!origins || !directions || !out)) return vkx_fail(ctx, VKX_E_INVALID, "vkx_trace_alpha: null array");
+    return traceHostRays(ctx, origins, directions, n, tmin, tmax, cullMask, anyHit, out, true);
 }
 
 // ---------------------------------------------------------------------------------------------------- DDGI

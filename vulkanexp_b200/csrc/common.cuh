@@ -21,6 +21,10 @@ static_assert(sizeof(vkx_hit) == 20, "vkx_hit");
 
 struct ncclComm;
 
+// One texture of the scene's list: all mip levels live in one texel arena (RGBA8 words), levelOffset in texels.
+struct DeviceTexture { uint32_t width, height, levels, flags; uint32_t levelOffset[16]; };
+#define VKX_MAX_TEXTURE_SIZE 16384u // 15 mip levels
+
 struct DeviceScene {
     const vkx_vertex* vertices;
     const uint32_t* indices;
@@ -30,6 +34,10 @@ struct DeviceScene {
     const float* worldToObject; // 9 floats per instance, W[row][col] row-major = inverse of the 3x3 part
     const uint4* nodes;         // 5 x uint4 per node
     const float4* tris;         // 3 x float4 per triangle
+    const uint32_t* texels;     // texel arena of every texture's mip chain (texture.cu)
+    const DeviceTexture* textures;
+    const float* srgbLut;       // 256 entries: sRGB code -> linear
+    uint32_t numTextures;
 };
 
 struct DeviceProbes {
@@ -60,6 +68,9 @@ struct vkx_ctx {
     vkx_material* dMaterials = nullptr; vkx_instance* dInstances = nullptr; float* dWorldToObject = nullptr; uint32_t* dInstTriBase = nullptr;
     size_t numVertices = 0, numIndices = 0, numMeshes = 0, numMaterials = 0, numInstances = 0, numFlatTris = 0;
     std::vector<uint32_t> hInstTriBase;
+    // textures (texture.cu): arena + descriptors + sRGB tables; hTextures mirrors the descriptors for validation / read-back
+    uint32_t* dTexels = nullptr; DeviceTexture* dTextures = nullptr; float* dSrgbLut = nullptr; float* dSrgbThreshold = nullptr;
+    std::vector<DeviceTexture> hTextures; size_t numTexels = 0; uint32_t texturesUsed = 0; // texturesUsed: highest texture index of the uploaded materials + 1
 
     // bvh
     uint4* dNodes = nullptr; float4* dTris = nullptr;
@@ -165,8 +176,9 @@ int launchP2pSignal(vkx_ctx* ctx); // ddgi.cu
 int ddgiClassify(vkx_ctx* ctx, const float* dirs512);
 int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* hostIndices, uint32_t count, uint32_t firstProbe, bool publishAll);
 int ddgiPublish(vkx_ctx* ctx, uint32_t count);
-// ---- trace_api.cu
-int traceHostRays(vkx_ctx* ctx, const float* origins, const float* directions, size_t n, float tmin, float tmax, uint32_t cullMask, int anyHit, vkx_hit* out);
+// ---- trace_api.cu (alphaTest: run anyhit.rahit's cut-out test on the candidates)
+int traceHostRays(vkx_ctx* ctx, const float* origins, const float* directions, size_t n, float tmin, float tmax, uint32_t cullMask, int anyHit, vkx_hit* out, bool alphaTest);
+void freeTextures(vkx_ctx* ctx); // texture.cu
 // ---- shadow.cu
 int shadowGBuffer(vkx_ctx* ctx, const vkx_camera& cam);
 int shadowFrame(vkx_ctx* ctx, const vkx_camera& cur, const vkx_camera& prev, const vkx_light& light);

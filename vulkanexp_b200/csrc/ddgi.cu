@@ -84,13 +84,21 @@ __global__ void k_front_keys(TraceParams tp, const float4* __restrict__ origins,
     }
 }
 
-// Persistent warps; see ptrace.cuh.
+#ifndef PT_DEFER_PRIMARY_DEFAULT
+#define PT_DEFER_PRIMARY_DEFAULT 0
+#endif
+#ifndef PT_DEFER_SHADOW_DEFAULT
+#define PT_DEFER_SHADOW_DEFAULT 0
+#endif
+// Persistent warps; see ptrace.cuh. DEFER = 0: triangles tested right after their node; DEFER > 0: parked until DEFER lanes hold some.
+template <int DEFER>
 __global__ void __launch_bounds__(128, 8) k_trace_primary(DeviceScene sc, TraceParams tp, RayMap rm, const float4* __restrict__ origins,
                                                        const float4* __restrict__ dirs, const float4* __restrict__ invDirs, vkx_hit* __restrict__ hits, float4* __restrict__ rays,
                                                        uint32_t* __restrict__ missQueue, uint32_t* __restrict__ frontQueue, uint32_t* __restrict__ counters) {
     PrimarySrc src; src.tp = tp; src.rm = rm; src.origins = origins; src.dirs = dirs; src.invDirs = invDirs; src.hits = hits; src.ri = 0;
     src.rays = rays; src.missQueue = missQueue; src.frontQueue = frontQueue; src.counters = counters;
-    persistentTrace<false>(sc.nodes, sc.tris, src, rm.numThreads, counters + 1);
+    if (DEFER == 0) persistentTrace<false>(sc.nodes, sc.tris, src, rm.numThreads, counters + 1);
+    else persistentTraceDeferred<false, DEFER>(sc.nodes, sc.tris, src, rm.numThreads, counters + 1);
 }
 
 struct ShadowSrc {
@@ -110,10 +118,12 @@ struct ShadowSrc {
     }
 };
 
+template <int DEFER>
 __global__ void __launch_bounds__(128, 8) k_trace_shadow(DeviceScene sc, vkx_light light, const float4* __restrict__ queue, const uint32_t* __restrict__ queueCount,
                                                       float4* __restrict__ rays, uint8_t* __restrict__ shadowFlags, uint32_t* __restrict__ counter) {
     ShadowSrc src; src.light = light; src.queue = queue; src.rays = rays; src.shadowFlags = shadowFlags; src.count = *queueCount; src.ri = 0; src.lx = src.ly = src.lz = 0.f;
-    persistentTrace<true>(sc.nodes, sc.tris, src, src.count, counter);
+    if (DEFER == 0) persistentTrace<true>(sc.nodes, sc.tris, src, src.count, counter);
+    else persistentTraceDeferred<true, DEFER>(sc.nodes, sc.tris, src, src.count, counter);
 }
 
 // ------------------------------------------------------------------------------------------------ blend
@@ -417,6 +427,7 @@ DeviceScene deviceScene(const vkx_ctx* ctx) {
     DeviceScene s;
     s.vertices = ctx->dVertices; s.indices = ctx->dIndices; s.offsets = ctx->dOffsets; s.materials = ctx->dMaterials; s.instances = ctx->dInstances;
     s.worldToObject = ctx->dWorldToObject; s.nodes = ctx->dNodes; s.tris = ctx->dTris;
+    s.texels = ctx->dTexels; s.textures = ctx->dTextures; s.srgbLut = ctx->dSrgbLut; s.numTextures = uint32_t(ctx->hTextures.size());
     return s;
 }
 
@@ -451,8 +462,15 @@ int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* /*unused*/,
     BlendParams bp; bp.grid = ctx->grid; bp.raysPerProbe = N; bp.gridCellLen = sqrtf(cx * cx + cy * cy + cz * cz);
     static bool blendAttr = false;
     if (!blendAttr) { CUDA_TRY(ctx, cudaFuncSetAttribute(k_blend, cudaFuncAttributeMaxDynamicSharedMemorySize, BLEND_SMEM_BYTES)); blendAttr = true; }
+    // Leaf deferral of the two persistent traversals (ptrace.cuh): 0 = off, else the number of waiting lanes that triggers a triangle phase.
+    // Tuning knobs (results are identical for every value): VKX_PT_DEFER / VKX_PT_DEFER_SHADOW in {0, 8, 12, 16}.
+    static int deferPrimary = -1, deferShadow = -1;
+    if (deferPrimary < 0) {
+        auto pick = [](const char* name, int dflt) { const char* e = getenv(name); int v = e ? atoi(e) : dflt; return v <= 0 ? 0 : v <= 8 ? 8 : v <= 12 ? 12 : 16; };
+        deferPrimary = pick("VKX_PT_DEFER", PT_DEFER_PRIMARY_DEFAULT); deferShadow = pick("VKX_PT_DEFER_SHADOW", PT_DEFER_SHADOW_DEFAULT);
+    }
     static int blocksPerSm = 0;
-    if (!blocksPerSm) { int a = 0, b = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_trace_primary, 128, 0); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace_shadow, 128, 0); blocksPerSm = std::max(1, std::min(a, b)); }
+    if (!blocksPerSm) { int a = 0, b = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_trace_primary<0>, 128, 0); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace_shadow<0>, 128, 0); blocksPerSm = std::max(1, std::min(a, b)); }
     const unsigned persistentBlocks = unsigned(ctx->smCount * blocksPerSm);
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
     k_blend_weights<<<(N + 3u) & ~3u, BLEND_COLS, 0, st>>>(ctx->grid.depthSharpness, N, ctx->dDirs, ctx->dBlendW); LAUNCH_CHECK(ctx);
@@ -476,7 +494,10 @@ int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* /*unused*/,
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->dQueueCount, 0, 32, st)); // [0] shadow queue length, [1] primary work counter, [2] shadow work counter, [3] misses, [4] front hits
         k_origin_table<<<divUp(n, 128), 128, 0, st>>>(ctx->grid, idx, n, ctx->dOrigins); LAUNCH_CHECK(ctx);
         if (timed) { CUDA_TRY(ctx, cudaEventRecord(ctx->kev[0], st)); ctx->kevProbes = n; }
-        k_trace_primary<<<persistentBlocks, 128, 0, st>>>(sc, tp, rm, ctx->dOrigins, ctx->dDirs, ctx->dInvDirs, ctx->dHits, ctx->dRays, ctx->dMissQueue, ctx->dFrontQueue, ctx->dQueueCount); LAUNCH_CHECK(ctx);
+#define VKX_LAUNCH_PRIMARY(D) k_trace_primary<D><<<persistentBlocks, 128, 0, st>>>(sc, tp, rm, ctx->dOrigins, ctx->dDirs, ctx->dInvDirs, ctx->dHits, ctx->dRays, ctx->dMissQueue, ctx->dFrontQueue, ctx->dQueueCount)
+        switch (deferPrimary) { case 8: VKX_LAUNCH_PRIMARY(8); break; case 12: VKX_LAUNCH_PRIMARY(12); break; case 16: VKX_LAUNCH_PRIMARY(16); break; default: VKX_LAUNCH_PRIMARY(0); }
+#undef VKX_LAUNCH_PRIMARY
+        LAUNCH_CHECK(ctx);
         if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[1], st));
         // The sky kernel only needs the miss queue: it runs on a second stream, concurrently with the sort and the front-hit shading.
         const unsigned shadeBlocks = std::min<unsigned>(divUp(numRays, 128), unsigned(ctx->smCount) * 16u);
@@ -499,7 +520,10 @@ int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* /*unused*/,
         launchShadeFront(shadeBlocks, st, sc, pr, sp, ctx->dOrigins, ctx->dDirs, ctx->dHits, ctx->dFrontQueueSorted, ctx->dQueueCount, ctx->dRays, ctx->dShadowQueue); LAUNCH_CHECK(ctx);
         if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[2], st));
         if (ctx->debugBuffers) CUDA_TRY(ctx, cudaMemsetAsync(ctx->dShadowFlags, 0, numRays, st));
-        k_trace_shadow<<<persistentBlocks, 128, 0, st>>>(sc, light, ctx->dShadowQueue, ctx->dQueueCount, ctx->dRays, ctx->debugBuffers ? ctx->dShadowFlags : nullptr, ctx->dQueueCount + 2); LAUNCH_CHECK(ctx);
+#define VKX_LAUNCH_SHADOW(D) k_trace_shadow<D><<<persistentBlocks, 128, 0, st>>>(sc, light, ctx->dShadowQueue, ctx->dQueueCount, ctx->dRays, ctx->debugBuffers ? ctx->dShadowFlags : nullptr, ctx->dQueueCount + 2)
+        switch (deferShadow) { case 8: VKX_LAUNCH_SHADOW(8); break; case 12: VKX_LAUNCH_SHADOW(12); break; case 16: VKX_LAUNCH_SHADOW(16); break; default: VKX_LAUNCH_SHADOW(0); }
+#undef VKX_LAUNCH_SHADOW
+        LAUNCH_CHECK(ctx);
         if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[3], st));
         if (base + n >= count) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], st));
         bp.count = n;

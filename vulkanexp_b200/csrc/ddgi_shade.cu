@@ -25,7 +25,9 @@ __global__ void __launch_bounds__(128) k_shade_miss(ShadeParams sp, const float4
     }
 }
 
-// closesthit.glsl:143-288 (NO_REFLECTION, untextured) over the dense front-hit queue; appends the shadow rays
+// closesthit.glsl:143-288 (NO_REFLECTION) over the dense front-hit queue; appends the shadow rays. TEXTURED: the scene has a texture
+// list (the host picks the variant, so untextured scenes run the kernel without any texture code).
+template <bool TEXTURED>
 __global__ void __launch_bounds__(128, 6) k_shade_front(DeviceScene sc, DeviceProbes pr, ShadeParams sp, const float4* __restrict__ origins,
                                                      const float4* __restrict__ dirs, const vkx_hit* __restrict__ hits, const uint32_t* __restrict__ frontQueue,
                                                      uint32_t* __restrict__ counters, float4* __restrict__ rays, float4* __restrict__ queue) {
@@ -43,7 +45,11 @@ __global__ void __launch_bounds__(128, 6) k_shade_front(DeviceScene sc, DevicePr
         const vkx_hit h = hits[ri];
         const v3 position = pointOnRayExact(origin, direction, h.t);
         v3 color, lit;
-        shadeFrontHit(sc, pr, gc, lightDir, lightColor, direction, position, h, color, lit);
+        if (TEXTURED) { // payload.raydx / raydy, traceProbes.rgen:40-41
+            const v3 raydx = rotateAxisH(direction, norm3(cross3(direction, mk3(1.0f, 0.0f, 0.0f))), 0.001f);
+            const v3 raydy = rotateAxisH(direction, norm3(cross3(direction, mk3(0.0f, 1.0f, 0.0f))), 0.001f);
+            shadeFrontHit<true>(sc, pr, gc, lightDir, lightColor, direction, position, h, color, lit, origin, raydx, raydy);
+        } else shadeFrontHit<false>(sc, pr, gc, lightDir, lightColor, direction, position, h, color, lit);
         rays[ri] = make_float4(color.x, color.y, color.z, h.t); // value if the sun is occluded; k_trace_shadow writes `lit` if the shadow ray escapes
         const uint32_t qi = warpAppend(counters);
         queue[2 * size_t(qi)] = make_float4(position.x, position.y, position.z, __uint_as_float(ri));
@@ -59,5 +65,6 @@ void launchShadeMiss(unsigned blocks, cudaStream_t st, const ShadeParams& sp, co
 }
 void launchShadeFront(unsigned blocks, cudaStream_t st, const DeviceScene& sc, const DeviceProbes& pr, const ShadeParams& sp, const float4* origins,
                       const float4* dirs, const vkx_hit* hits, const uint32_t* frontQueue, uint32_t* counters, float4* rays, float4* shadowQueue) {
-    k_shade_front<<<blocks, 128, 0, st>>>(sc, pr, sp, origins, dirs, hits, frontQueue, counters, rays, shadowQueue);
+    if (sc.numTextures) k_shade_front<true><<<blocks, 128, 0, st>>>(sc, pr, sp, origins, dirs, hits, frontQueue, counters, rays, shadowQueue);
+    else k_shade_front<false><<<blocks, 128, 0, st>>>(sc, pr, sp, origins, dirs, hits, frontQueue, counters, rays, shadowQueue);
 }

@@ -75,8 +75,11 @@ __global__ void __launch_bounds__(128) k_reflect_gen(float3 camOrigin, const flo
 
 // reflection.rgen:186-187 with closesthit.glsl / miss.rmiss / shadow.rmiss: closest hit, shading from the irradiance volume, sun
 // shadow ray, colour compression. One thread per queued pixel.
+// TEX: the scene has a texture list. The reflection pipeline's hit group has anyhit.rahit (src/RenderPasses/ReflectionPipeline.cpp:51),
+// so both traversals run the alpha cut-out test, and the closest hit shades with textures (ray differentials reflection.rgen:169-170).
+template <bool TEX>
 __global__ void __launch_bounds__(128) k_reflect_shade(DeviceScene sc, DeviceProbes pr, vkx_light light, const uint32_t* __restrict__ queue, const uint32_t* __restrict__ queueCount,
-                                                       const float4* __restrict__ posDepth, const float4* __restrict__ dirs, float4* __restrict__ out,
+                                                       const float4* __restrict__ posDepth, const float4* __restrict__ normalMetal, const float4* __restrict__ dirs, float4* __restrict__ out,
                                                        vkx_hit* __restrict__ dbgHits, uint8_t* __restrict__ dbgMask) {
     const uint32_t n = *queueCount;
     const v3 lightDir = mk3(light.direction[0], light.direction[1], light.direction[2]);
@@ -89,7 +92,7 @@ __global__ void __launch_bounds__(128) k_reflect_shade(DeviceScene sc, DevicePro
         const Ray r = makeRay(position.x, position.y, position.z, direction.x, direction.y, direction.z);
         HitRec h;
         v3 color;
-        if (!traverse<false>(sc.nodes, sc.tris, r, 0.1f, 10000.0f, 0xFFu, h)) { // miss.rmiss
+        if (!traverse<false, TEX>(sc.nodes, sc.tris, r, 0.1f, 10000.0f, 0xFFu, h, &sc)) { // miss.rmiss
             color = skyColor(position, direction, lightDir, lightColor, light.color[3]);
             if (dbgMask) dbgMask[pix] = 1;
         } else {
@@ -99,10 +102,15 @@ __global__ void __launch_bounds__(128) k_reflect_shade(DeviceScene sc, DevicePro
             else {
                 const v3 hitPos = pointOnRayExact(position, direction, h.t);
                 v3 base, lit;
-                shadeFrontHit(sc, pr, gc, lightDir, lightColor, direction, hitPos, vh, base, lit);
+                if (TEX) {
+                    const float4 nm = __ldg(normalMetal + pix);
+                    const v3 normal = mk3(nm.x, nm.y, nm.z);
+                    const v3 raydx = rotateAxisH(direction, normal, 0.001f), raydy = rotateAxisH(direction, cross3(normal, direction), 0.001f);
+                    shadeFrontHit<true>(sc, pr, gc, lightDir, lightColor, direction, hitPos, vh, base, lit, position, raydx, raydy);
+                } else shadeFrontHit<false>(sc, pr, gc, lightDir, lightColor, direction, hitPos, vh, base, lit);
                 const Ray sr = makeRay(hitPos.x, hitPos.y, hitPos.z, lightDir.x, lightDir.y, lightDir.z);
                 HitRec sh;
-                const bool shadowed = traverse<true>(sc.nodes, sc.tris, sr, 0.1f, 10000.0f, 0xFFu, sh);
+                const bool shadowed = traverse<true, TEX>(sc.nodes, sc.tris, sr, 0.1f, 10000.0f, 0xFFu, sh, &sc);
                 color = shadowed ? base : lit;
                 if (dbgMask) dbgMask[pix] = shadowed ? 4 : 3;
             }
@@ -195,8 +203,9 @@ int reflectionFrame(vkx_ctx* ctx, const vkx_camera& cur, const vkx_camera& prev,
     k_reflect_gen<<<grid, 128, 0, st>>>(co, slice, ctx->noiseW, ctx->noiseH, int(cur.frameIndex / 64u), int(cur.frameIndex / 64u / 64u), W, H, ctx->dPosDepth, ctx->dNormalMetal,
                                         ctx->dAlbedoRough, ctx->dReflRaw, ctx->dReflDirs, ctx->dReflQueue, ctx->dReflCount, dbgHits, dbgMask);
     LAUNCH_CHECK(ctx);
-    k_reflect_shade<<<std::min<unsigned>(divUp(size_t(W) * H, 128), unsigned(ctx->smCount) * 16u), 128, 0, st>>>(deviceScene(ctx), deviceProbes(ctx), light, ctx->dReflQueue, ctx->dReflCount,
-                                                                                                             ctx->dPosDepth, ctx->dReflDirs, ctx->dReflRaw, dbgHits, dbgMask);
+    const unsigned shadeBlocks = std::min<unsigned>(divUp(size_t(W) * H, 128), unsigned(ctx->smCount) * 16u);
+    if (!ctx->hTextures.empty()) k_reflect_shade<true><<<shadeBlocks, 128, 0, st>>>(deviceScene(ctx), deviceProbes(ctx), light, ctx->dReflQueue, ctx->dReflCount, ctx->dPosDepth, ctx->dNormalMetal, ctx->dReflDirs, ctx->dReflRaw, dbgHits, dbgMask);
+    else k_reflect_shade<false><<<shadeBlocks, 128, 0, st>>>(deviceScene(ctx), deviceProbes(ctx), light, ctx->dReflQueue, ctx->dReflCount, ctx->dPosDepth, ctx->dNormalMetal, ctx->dReflDirs, ctx->dReflRaw, dbgHits, dbgMask);
     LAUNCH_CHECK(ctx);
     CUDA_TRY(ctx, cudaEventRecord(ctx->rev[1], st));
     k_refl_filter<0><<<grid, 128, 0, st>>>(int(W), int(H), ctx->dPosDepth, ctx->dReflRaw, nullptr, pv, pp, co, po, ctx->dReflX); LAUNCH_CHECK(ctx);

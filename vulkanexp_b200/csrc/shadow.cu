@@ -21,6 +21,8 @@ __device__ __forceinline__ float4 mulM4(const M4& M, float x, float y, float z, 
 }
 
 // G-buffer fixture: primary rays set up as raygen.rgen:27-33, outputs laid out as GBuffer.frag:64-68.
+// ALPHA: the scene has a texture list; cut-outs follow anyhit.rahit (the raster pass discards below 0.05, GBuffer.frag:38: this is a fixture).
+template <bool ALPHA>
 __global__ void __launch_bounds__(128) k_gbuffer(DeviceScene sc, M4 invView, M4 invProj, float3 camOrigin, uint32_t W, uint32_t H,
                                                  float4* __restrict__ posDepth, float4* __restrict__ normalMetal, float4* __restrict__ albedoRough, float4* __restrict__ emissive) {
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
@@ -34,7 +36,7 @@ __global__ void __launch_bounds__(128) k_gbuffer(DeviceScene sc, M4 invView, M4 
     const float4 d4 = mulM4(invView, tn.x, tn.y, tn.z, 0.f);
     const Ray r = makeRay(o4.x, o4.y, o4.z, d4.x, d4.y, d4.z);
     HitRec h;
-    if (!traverse<false>(sc.nodes, sc.tris, r, 0.001f, 100000.0f, 0xFFu, h)) {
+    if (!traverse<false, ALPHA>(sc.nodes, sc.tris, r, 0.001f, 100000.0f, 0xFFu, h, &sc)) {
         posDepth[pix] = make_float4(0.f, 0.f, 0.f, 0.f); normalMetal[pix] = make_float4(0.f, 0.f, 0.f, 0.f);
         albedoRough[pix] = make_float4(0.f, 0.f, 0.f, 0.f); emissive[pix] = make_float4(0.f, 0.f, 0.f, 0.f);
         return;
@@ -89,7 +91,9 @@ __device__ __forceinline__ float4 sampleNoise(const float* __restrict__ tex, uin
     return r;
 }
 
-// directLight.rgen:42-99
+// directLight.rgen:42-99. ALPHA: the scene has a texture list; the pipeline's only hit group is anyhit.rahit
+// (src/RenderPasses/DirectLightPipeline.cpp:43-51), i.e. the shadow ray passes through texels with alpha < 0.01.
+template <bool ALPHA>
 __global__ void __launch_bounds__(128) k_direct_light(DeviceScene sc, vkx_light light, const float* __restrict__ noiseSlice, uint32_t nw, uint32_t nh, uint32_t W, uint32_t H,
                                                       const float4* __restrict__ posDepth, const float4* __restrict__ normalMetal, const float4* __restrict__ previous,
                                                       float4* __restrict__ out, float4* __restrict__ dbgDirs, uint8_t* __restrict__ dbgMask) {
@@ -109,7 +113,7 @@ __global__ void __launch_bounds__(128) k_direct_light(DeviceScene sc, vkx_light 
     if (dot3(direction, normal) > 0.0f) {
         const Ray r = makeRay(pd.x, pd.y, pd.z, direction.x, direction.y, direction.z);
         HitRec h;
-        const bool shadowed = traverse<true>(sc.nodes, sc.tris, r, 0.01f, 10000.0f, 0xFFu, h);
+        const bool shadowed = traverse<true, ALPHA>(sc.nodes, sc.tris, r, 0.01f, 10000.0f, 0xFFu, h, &sc);
         if (dbgMask) dbgMask[pix] = shadowed ? 2 : 1;
         float outColor = 0.0f;
         if (!shadowed) { outColor = 1.0f; if (direction.y < 0.0f) outColor *= 1.0f - clampS(-direction.y, 0.0f, 0.1f) / 0.1f; }
@@ -270,7 +274,8 @@ int shadowGBuffer(vkx_ctx* ctx, const vkx_camera& cam) {
     M4 iv, ip;
     inverse4(cam.view, iv.m); inverse4(cam.proj, ip.m);
     dim3 grid(divUp(ctx->shW, 128), ctx->shH);
-    k_gbuffer<<<grid, 128, 0, ctx->stream>>>(deviceScene(ctx), iv, ip, make_float3(cam.origin[0], cam.origin[1], cam.origin[2]), ctx->shW, ctx->shH, ctx->dPosDepth, ctx->dNormalMetal, ctx->dAlbedoRough, ctx->dEmissive);
+    if (!ctx->hTextures.empty()) k_gbuffer<true><<<grid, 128, 0, ctx->stream>>>(deviceScene(ctx), iv, ip, make_float3(cam.origin[0], cam.origin[1], cam.origin[2]), ctx->shW, ctx->shH, ctx->dPosDepth, ctx->dNormalMetal, ctx->dAlbedoRough, ctx->dEmissive);
+    else k_gbuffer<false><<<grid, 128, 0, ctx->stream>>>(deviceScene(ctx), iv, ip, make_float3(cam.origin[0], cam.origin[1], cam.origin[2]), ctx->shW, ctx->shH, ctx->dPosDepth, ctx->dNormalMetal, ctx->dAlbedoRough, ctx->dEmissive);
     LAUNCH_CHECK(ctx);
     return VKX_OK;
 }
@@ -283,7 +288,8 @@ int shadowFrame(vkx_ctx* ctx, const vkx_camera& cur, const vkx_camera& prev, con
     float4* next = ctx->dShFinal[ctx->shCur ^ 1];
     M4 pv, pp; memcpy(pv.m, prev.view, 64); memcpy(pp.m, prev.proj, 64);
     CUDA_TRY(ctx, cudaEventRecord(ctx->sev[0], st));
-    k_direct_light<<<dim3(divUp(W, 128), H), 128, 0, st>>>(deviceScene(ctx), light, slice, ctx->noiseW, ctx->noiseH, W, H, ctx->dPosDepth, ctx->dNormalMetal, previous, ctx->dShRaw, ctx->dShDirs, ctx->dShMask);
+    if (!ctx->hTextures.empty()) k_direct_light<true><<<dim3(divUp(W, 128), H), 128, 0, st>>>(deviceScene(ctx), light, slice, ctx->noiseW, ctx->noiseH, W, H, ctx->dPosDepth, ctx->dNormalMetal, previous, ctx->dShRaw, ctx->dShDirs, ctx->dShMask);
+    else k_direct_light<false><<<dim3(divUp(W, 128), H), 128, 0, st>>>(deviceScene(ctx), light, slice, ctx->noiseW, ctx->noiseH, W, H, ctx->dPosDepth, ctx->dNormalMetal, previous, ctx->dShRaw, ctx->dShDirs, ctx->dShMask);
     LAUNCH_CHECK(ctx);
     CUDA_TRY(ctx, cudaEventRecord(ctx->sev[1], st));
     k_filter_x<<<dim3(divUp(W, 256), H), 256, 0, st>>>(W, H, ctx->dPosDepth, ctx->dShRaw, ctx->dShX); LAUNCH_CHECK(ctx);

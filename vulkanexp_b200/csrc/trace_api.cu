@@ -3,14 +3,14 @@
 #include "traverse.cuh"
 
 namespace {
-template <bool ANY>
+template <bool ANY, bool ALPHA>
 __global__ void __launch_bounds__(128) k_trace_host(DeviceScene sc, const float* __restrict__ o, const float* __restrict__ d, uint32_t n, float tmin, float tmax,
                                                     uint32_t cullMask, vkx_hit* __restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const Ray r = makeRay(o[3 * i], o[3 * i + 1], o[3 * i + 2], d[3 * i], d[3 * i + 1], d[3 * i + 2]);
     HitRec h;
-    const bool hit = traverse<ANY>(sc.nodes, sc.tris, r, tmin, tmax, cullMask, h);
+    const bool hit = traverse<ANY, ALPHA>(sc.nodes, sc.tris, r, tmin, tmax, cullMask, h, &sc);
     vkx_hit res;
     if (ANY) { res.t = hit ? 1.0f : -1.0f; res.instance = 0xFFFFFFFFu; res.primitive = 0xFFFFFFFFu; res.u = 0.f; res.v = 0.f; }
     else { res.t = h.t; res.instance = h.inst; res.primitive = h.prim; res.u = h.u; res.v = h.v; }
@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(128) k_trace_host(DeviceScene sc, const float*
 }
 } // namespace
 
-int traceHostRays(vkx_ctx* ctx, const float* origins, const float* directions, size_t n, float tmin, float tmax, uint32_t cullMask, int anyHit, vkx_hit* out) {
+int traceHostRays(vkx_ctx* ctx, const float* origins, const float* directions, size_t n, float tmin, float tmax, uint32_t cullMask, int anyHit, vkx_hit* out, bool alphaTest) {
     if (n == 0) return VKX_OK;
     if (n > 0x7FFFFFFFu) return vkx_fail(ctx, VKX_E_INVALID, "too many rays");
     cudaStream_t st = ctx->stream;
@@ -33,8 +33,9 @@ int traceHostRays(vkx_ctx* ctx, const float* origins, const float* directions, s
         if ((e = cudaMemcpyAsync(dO, origins, n * 12, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
         if ((e = cudaMemcpyAsync(dD, directions, n * 12, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
         const DeviceScene sc = deviceScene(ctx);
-        if (anyHit) k_trace_host<true><<<divUp(n, 128), 128, 0, st>>>(sc, dO, dD, uint32_t(n), tmin, tmax, cullMask, dH);
-        else k_trace_host<false><<<divUp(n, 128), 128, 0, st>>>(sc, dO, dD, uint32_t(n), tmin, tmax, cullMask, dH);
+        const bool alpha = alphaTest && sc.numTextures != 0u;
+        if (anyHit) { if (alpha) k_trace_host<true, true><<<divUp(n, 128), 128, 0, st>>>(sc, dO, dD, uint32_t(n), tmin, tmax, cullMask, dH); else k_trace_host<true, false><<<divUp(n, 128), 128, 0, st>>>(sc, dO, dD, uint32_t(n), tmin, tmax, cullMask, dH); }
+        else { if (alpha) k_trace_host<false, true><<<divUp(n, 128), 128, 0, st>>>(sc, dO, dD, uint32_t(n), tmin, tmax, cullMask, dH); else k_trace_host<false, false><<<divUp(n, 128), 128, 0, st>>>(sc, dO, dD, uint32_t(n), tmin, tmax, cullMask, dH); }
         ctx->launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) break;
         if ((e = cudaMemcpyAsync(out, dH, n * sizeof(vkx_hit), cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;

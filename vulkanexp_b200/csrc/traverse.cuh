@@ -4,6 +4,7 @@
 // one oracle/bvh.cpp executes; only the scheduling of rays onto lanes differs.
 #pragma once
 #include "common.cuh"
+#include "texture.cuh"
 
 #define VKX_STACK 48
 
@@ -117,9 +118,12 @@ __device__ __forceinline__ void loadNode(const uint4* __restrict__ nodes, uint32
 }
 
 // One full traversal. ANY: terminate on first accepted hit, returns true if occluded.
-template <bool ANY>
+// ALPHA: the pipeline's hit group has anyhit.rahit (direct light, reflection; not the probe pipelines): a candidate that would be
+// accepted is first shown to the cut-out test and dropped if its albedo alpha is below 0.01 (needs alphaScene). The test runs only
+// on would-be-accepted candidates, so the result is the closest / any non-ignored hit whatever the order of the triangle tests.
+template <bool ANY, bool ALPHA = false>
 __device__ __forceinline__ bool traverse(const uint4* __restrict__ nodes, const float4* __restrict__ tris, const Ray& r, float tmin, float tmax,
-                                         uint32_t cullMask, HitRec& hit) {
+                                         uint32_t cullMask, HitRec& hit, const DeviceScene* alphaScene = nullptr) {
     float tbest = tmax;
     hit.found = false; hit.inst = 0xFFFFFFFFu; hit.prim = 0xFFFFFFFFu; hit.u = 0.f; hit.v = 0.f; hit.t = -1.0f;
     uint2 stack[VKX_STACK];
@@ -153,6 +157,7 @@ __device__ __forceinline__ bool traverse(const uint4* __restrict__ nodes, const 
             const uint32_t inst = instW & 0x00FFFFFFu, prim = primW & 0x7FFFFFFFu;
             const bool closer = t < tbest || (hit.found && t == tbest && (inst < hit.inst || (inst == hit.inst && prim < (hit.prim & 0x7FFFFFFFu))));
             if (!closer) continue;
+            if (ALPHA) { if (anyHitIgnores(*alphaScene, inst, prim, u, v)) continue; }
             if (ANY) return true;
             const bool back = (det > 0.0f) == ((primW & 0x80000000u) != 0u);
             hit.found = true; tbest = t; hit.t = t; hit.inst = inst; hit.prim = prim | (back ? 0x80000000u : 0u); hit.u = u; hit.v = v;

@@ -105,6 +105,48 @@ class Camera(C.Structure):
     _fields_ = [("view", C.c_float * 16), ("proj", C.c_float * 16), ("origin", C.c_float * 3), ("frameIndex", C.c_uint32)]
 
 
+class Texture(C.Structure):
+    """vkx_texture (include/vkx.h): one decoded RGBA8 image + VkFormat class + glTF sampler description."""
+
+    _fields_ = [
+        ("pixels", C.c_void_p),
+        ("width", C.c_uint32),
+        ("height", C.c_uint32),
+        ("srgb", C.c_uint32),
+        ("magFilter", C.c_uint32),
+        ("minFilter", C.c_uint32),
+        ("wrapS", C.c_uint32),
+        ("wrapT", C.c_uint32),
+    ]
+
+
+def texture_array(textures):
+    """list of dicts {pixels: uint8 [h, w, 4], srgb, magFilter, minFilter, wrapS, wrapT} -> (ctypes array, keep-alive list)."""
+    arr = (Texture * max(1, len(textures)))()
+    keep = []
+    for i, t in enumerate(textures):
+        px = np.ascontiguousarray(t["pixels"], dtype=np.uint8)
+        assert px.ndim == 3 and px.shape[2] == 4, "texture pixels must be [height, width, 4] uint8"
+        keep.append(px)
+        arr[i].pixels = px.ctypes.data
+        arr[i].height, arr[i].width = px.shape[0], px.shape[1]
+        arr[i].srgb = int(t.get("srgb", 1))
+        arr[i].magFilter = int(t.get("magFilter", 0))
+        arr[i].minFilter = int(t.get("minFilter", 0))
+        arr[i].wrapS = int(t.get("wrapS", 0))
+        arr[i].wrapT = int(t.get("wrapT", 0))
+    return arr, keep
+
+
+def mip_level_count(width, height):
+    """floor(log2(max(w, h))) + 1 (reference src/vulkan/Image.cpp:29-31)."""
+    return int(max(width, height)).bit_length()
+
+
+def mip_chain_texels(width, height):
+    return sum(max(1, width >> l) * max(1, height >> l) for l in range(mip_level_count(width, height)))
+
+
 class BvhInfo(C.Structure):
     _fields_ = [
         ("numNodes", C.c_uint32),

@@ -8,6 +8,7 @@ propagation), :1077-1103 (bounds), src/Renderer.cpp:97-126 (offset table) and :5
 from __future__ import annotations
 
 import json
+import os
 import struct
 from dataclasses import dataclass, field
 
@@ -43,7 +44,50 @@ class SceneFile:
     materials: list = field(default_factory=list)  # glTF-style dicts
     entities: list = field(default_factory=list)
     meshes: list = field(default_factory=list)
-    textures: list = field(default_factory=list)
+    textures: list = field(default_factory=list)  # {"source": path, "format": VkFormat, "sampler": glTF sampler} (src/Scene.cpp:776-784)
+    images: list = field(default_factory=list)  # decoded RGBA8 images [h, w, 4], parallel to textures (the reference decodes `source` with stb_image)
+
+
+VK_FORMAT_R8G8B8A8_UNORM = 37
+VK_FORMAT_R8G8B8A8_SRGB = 43
+
+
+def write_pam(path, pixels):
+    """Netpbm P7 (RGB_ALPHA, 8 bit): the image container of the synthetic scenes (no PNG encoder is assumed)."""
+    px = np.ascontiguousarray(pixels, dtype=np.uint8)
+    h, w, c = px.shape
+    assert c == 4
+    with open(path, "wb") as f:
+        f.write(("P7\nWIDTH %d\nHEIGHT %d\nDEPTH 4\nMAXVAL 255\nTUPLTYPE RGB_ALPHA\nENDHDR\n" % (w, h)).encode("ascii"))
+        f.write(px.tobytes())
+
+
+def read_pam(path):
+    data = open(path, "rb").read()
+    end = data.index(b"ENDHDR\n") + 7
+    hdr = dict(line.split(None, 1) for line in data[:end].decode("ascii").splitlines()[1:-1] if line and not line.startswith("#"))
+    w, h, d = int(hdr["WIDTH"]), int(hdr["HEIGHT"]), int(hdr["DEPTH"])
+    if d != 4 or int(hdr["MAXVAL"]) != 255:
+        raise ValueError("%s: only 8-bit RGB_ALPHA PAM images are supported" % path)
+    return np.frombuffer(data, dtype=np.uint8, count=w * h * 4, offset=end).reshape(h, w, 4).copy()
+
+
+def texture_list(scene):
+    """The scene's textures as the list vkx_scene_textures takes (pods.texture_array): image + VkFormat class + glTF sampler."""
+    out = []
+    for t, img in zip(scene.textures, scene.images):
+        smp = t.get("sampler", {}) or {}
+        out.append(
+            {
+                "pixels": img,
+                "srgb": 1 if int(t.get("format", VK_FORMAT_R8G8B8A8_SRGB)) == VK_FORMAT_R8G8B8A8_SRGB else 0,
+                "magFilter": int(smp.get("magFilter", 0)),
+                "minFilter": int(smp.get("minFilter", 0)),
+                "wrapS": int(smp.get("wrapS", 0)),
+                "wrapT": int(smp.get("wrapT", 0)),
+            }
+        )
+    return out
 
 
 def _fmt(v):
@@ -76,6 +120,8 @@ def material_json(name, base_color=(1.0, 1.0, 1.0), metallic=0.0, roughness=1.0,
 
 
 def write_scene(path, scene: SceneFile):
+    for t, img in zip(scene.textures, scene.images):  # texture sources are relative to the scene file (src/Scene.cpp:780,899)
+        write_pam(os.path.join(os.path.dirname(os.path.abspath(path)), t["source"]), img)
     root = {
         "materials": scene.materials,
         "entities": [],
@@ -141,6 +187,8 @@ def read_scene(path) -> SceneFile:
         v = np.frombuffer(buffers[m["vertexArray"] - 1], dtype=VERTEX_DTYPE).copy()
         i = np.frombuffer(buffers[m["indexArray"] - 1], dtype="<u4").copy()
         s.meshes.append(Mesh(m["name"], int(m.get("material", 0)), v, i))
+    for t in s.textures:
+        s.images.append(read_pam(os.path.join(os.path.dirname(os.path.abspath(path)), t["source"])))
     return s
 
 
@@ -260,4 +308,5 @@ def flatten(scene: SceneFile) -> dict:
         "instances": instances,
         "bounds_min": np.asarray(bmin, dtype=np.float32),
         "bounds_max": np.asarray(bmax, dtype=np.float32),
+        **({"textures": texture_list(scene)} if scene.textures else {}),
     }

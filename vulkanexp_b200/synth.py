@@ -306,6 +306,109 @@ def make_open_court(seed=SEED_BASE + 9, columns=6, col_segments=16, col_stacks=4
     return s
 
 
+def planar_uvs(mesh, scale=0.35):
+    """Texture coordinates + tangents for a synthetic mesh: box projection along the dominant normal axis (in place)."""
+    v = mesh.vertices
+    p, n = v["pos"].astype(np.float64), v["normal"].astype(np.float64)
+    axis = np.argmax(np.abs(n), axis=1)
+    ua = np.where(axis == 0, 2, 0)  # u runs along z for x-facing faces, along x otherwise
+    va = np.where(axis == 1, 2, 1)  # v runs along z for y-facing faces, along y otherwise
+    rows = np.arange(len(v))
+    v["texCoord"] = np.stack([p[rows, ua] * scale, p[rows, va] * scale], axis=1).astype(np.float32)
+    t = np.zeros((len(v), 3))
+    t[rows, ua] = 1.0
+    t -= n * np.sum(t * n, axis=1, keepdims=True)  # Gram-Schmidt against the normal
+    t /= np.maximum(np.linalg.norm(t, axis=1, keepdims=True), 1e-20)
+    v["tangent"] = np.concatenate([t, np.where(axis[:, None] == 1, -1.0, 1.0)], axis=1).astype(np.float32)
+    return mesh
+
+
+def procedural_textures(seed=SEED_BASE + 77):
+    """Five small RGBA8 images + their .scene texture entries: albedo (sRGB, 64x32), normal map (UNORM, 32x32), metallic-roughness
+    (UNORM, 16x16, NEAREST mip), emissive (sRGB, 20x12: odd mip sizes, clamp / mirror) and a cut-out grate (sRGB, alpha 0 / 255)."""
+    from .scene_format import VK_FORMAT_R8G8B8A8_SRGB, VK_FORMAT_R8G8B8A8_UNORM
+
+    rng = np.random.default_rng(seed)
+
+    def smooth(h, w, octaves=3):
+        out = np.zeros((h, w))
+        for o in range(octaves):
+            f = 2 ** (o + 1)
+            y, x = np.mgrid[0:h, 0:w]
+            out += np.sin(2 * np.pi * (f * x / w + rng.uniform())) * np.sin(2 * np.pi * (f * y / h + rng.uniform())) / f
+        return out
+
+    images, entries = [], []
+
+    def add(name, img, fmt, sampler):
+        images.append(np.clip(np.rint(img), 0, 255).astype(np.uint8))
+        entries.append({"source": name, "format": fmt, "sampler": sampler})
+
+    h, w = 32, 64  # 0: albedo, tiles with REPEAT (glTF defaults)
+    a = np.zeros((h, w, 4))
+    brick = ((np.mgrid[0:h, 0:w][0] // 8 + np.mgrid[0:h, 0:w][1] // 16) % 2).astype(np.float64)
+    a[..., 0] = 150 + 70 * brick + 25 * smooth(h, w)
+    a[..., 1] = 110 + 60 * brick + 25 * smooth(h, w)
+    a[..., 2] = 90 + 40 * brick + 25 * smooth(h, w)
+    a[..., 3] = 255
+    add("tex_albedo.pam", a, VK_FORMAT_R8G8B8A8_SRGB, {})
+    h, w = 32, 32  # 1: tangent-space normal map
+    hx, hy = smooth(h, w), smooth(h, w)
+    nz = np.sqrt(np.maximum(1.0 - 0.25 * (hx**2 + hy**2), 0.05))
+    nm = np.stack([0.5 * hx, 0.5 * hy, nz], axis=-1)
+    nm /= np.linalg.norm(nm, axis=-1, keepdims=True)
+    n = np.zeros((h, w, 4))
+    n[..., :3] = (nm * 0.5 + 0.5) * 255
+    n[..., 3] = 255
+    add("tex_normal.pam", n, VK_FORMAT_R8G8B8A8_UNORM, {"magFilter": 9729, "minFilter": 9987, "wrapS": 10497, "wrapT": 10497})
+    h, w = 16, 16  # 2: metallic (b) / roughness (g), NEAREST_MIPMAP_NEAREST minification
+    m = np.zeros((h, w, 4))
+    m[..., 1] = 120 + 100 * (smooth(h, w) > 0)
+    m[..., 2] = 255 * (rng.uniform(size=(h, w)) > 0.5)
+    m[..., 3] = 255
+    add("tex_metalrough.pam", m, VK_FORMAT_R8G8B8A8_UNORM, {"magFilter": 9728, "minFilter": 9984, "wrapS": 33648, "wrapT": 10497})
+    h, w = 12, 20  # 3: emissive, non-power-of-two, clamp / mirror
+    e = np.zeros((h, w, 4))
+    e[..., 0] = 255 * (smooth(h, w) > 0.3)
+    e[..., 1] = 180 * (smooth(h, w) > 0.3)
+    e[..., 2] = 60
+    e[..., 3] = 255
+    add("tex_emissive.pam", e, VK_FORMAT_R8G8B8A8_SRGB, {"magFilter": 9729, "minFilter": 9986, "wrapS": 33071, "wrapT": 33648})
+    h, w = 32, 32  # 4: cut-out grate: opaque bars, holes with alpha 0
+    g = np.zeros((h, w, 4))
+    yy, xx = np.mgrid[0:h, 0:w]
+    bars = ((xx % 8) < 3) | ((yy % 8) < 3)
+    g[..., 0], g[..., 1], g[..., 2] = 60 + 30 * bars, 60 + 30 * bars, 70 + 30 * bars
+    g[..., 3] = 255 * bars
+    add("tex_grate.pam", g, VK_FORMAT_R8G8B8A8_SRGB, {"magFilter": 9729, "minFilter": 9729, "wrapS": 10497, "wrapT": 10497})
+    return images, entries
+
+
+def make_textured_court(seed=SEED_BASE + 9):
+    """make_open_court with every texture slot of closesthit.glsl in use: albedo + normal map on the stone, metallic-roughness and
+    emissive maps on the balls, and a canopy that is a cut-out grate (alpha 0 holes: the any-hit test of the shadow / reflection rays)."""
+    s = make_open_court(seed)
+    s.images, s.textures = procedural_textures()
+    stone, blue = s.materials[0], s.materials[1]
+    stone["pbrMetallicRoughness"]["baseColorTexture"] = {"index": 0}
+    stone["normalTexture"] = {"index": 1}
+    blue["pbrMetallicRoughness"]["metallicRoughnessTexture"] = {"index": 2}
+    blue["pbrMetallicRoughness"]["metallicFactor"] = 1.0
+    blue["emissiveTexture"] = {"index": 3}
+    blue["emissiveFactor"] = [0.6, 0.5, 0.4]
+    grate = material_json("grate", (0.9, 0.9, 0.9), 0.0, 0.8)
+    grate["pbrMetallicRoughness"]["baseColorTexture"] = {"index": 4}
+    s.materials.append(grate)
+    for m in s.meshes:
+        planar_uvs(m)
+    canopy = next(i for i, m in enumerate(s.meshes) if m.name == "Canopy")
+    s.meshes[canopy].material = len(s.materials) - 1
+    for e in s.entities:
+        if e.mesh_renderer is not None and e.mesh_renderer[0] == canopy:
+            e.mesh_renderer = (canopy, len(s.materials) - 1)
+    return s
+
+
 def make_cfg2(target_tris=262_144):
     """"sponza-scale" atrium: two storeys of fluted columns and arches around an open courtyard, banners, ~262 k triangles."""
     rng = np.random.default_rng(SEED_BASE + 2)
