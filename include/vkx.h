@@ -164,6 +164,10 @@ int vkx_scene_upload(vkx_ctx* ctx, const vkx_vertex* vertices, size_t numVertice
  * src/shaders/closesthit.glsl:50-107,161-192) and the alpha cut-out of anyhit.rahit in the sun-shadow and reflection pipelines.
  * numTextures = 0 removes the list. Must precede the vkx_scene_upload whose materials use the textures. */
 int vkx_scene_textures(vkx_ctx* ctx, const vkx_texture* textures, size_t numTextures);
+/* Host-side image decoder (no context, no GPU): what STBImage does in uploadTextures (src/Resources.cpp:56-60), for the formats the
+ * library reads itself: PNG (8 bits per channel, non-interlaced), Netpbm P6 and P7. Always expands to RGBA8. rgba may be NULL to
+ * query the size. Returns VKX_E_UNSUPPORTED for files it cannot decode. */
+int vkx_image_decode(const char* path, uint8_t* rgba, size_t rgbaBytes, uint32_t* width, uint32_t* height);
 /* Parity primitives for the texture path: the generated mip chain (level-major RGBA8, numLevels = floor(log2(max(w, h))) + 1) and
  * n texture look-ups with explicit gradients (uv: 2 floats, grads: dudx, dvdx, dudy, dvdy per look-up; grads NULL = texture() of a
  * ray-tracing stage = base level) -> out: 4 floats per look-up. */

@@ -13,11 +13,16 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_facade_equals_c_abi(tmp_path):
+@pytest.mark.parametrize("textured", [False, True])
+def test_facade_equals_c_abi(tmp_path, textured):
     from vulkanexp_b200._lib import Context
     from vulkanexp_b200.host_logic import OrientationGenerator, ProbeScheduler
 
-    s = synth.make_open_court()
+    s = synth.make_textured_court() if textured else synth.make_open_court()
+    if textured:  # two of the images go through the facade's PNG decoder, the others through its Netpbm reader
+        pytest.importorskip("PIL")
+        s.textures[0]["source"] = "tex_albedo.png"
+        s.textures[4]["source"] = "tex_grate.png"
     path = os.path.join(tmp_path, "court.scene")
     scene_format.write_scene(path, s)
     res, rays, frames = (7, 5, 6), 48, 14

@@ -273,3 +273,33 @@ def test_scene_file_round_trip_keeps_textures(tmp_path):
     assert fa["materials"].tobytes() == fb["materials"].tobytes()
     assert [t["srgb"] for t in fb["textures"]] == [1, 0, 0, 1, 1]
     assert [t["minFilter"] for t in fb["textures"]] == [0, 9987, 9984, 9986, 9729]
+
+
+def test_image_decoder_of_the_library(tmp_path):
+    """vkx_image_decode (host only): PNG in every 8-bit colour type PIL writes, P6 and P7, against Pillow's own RGBA conversion."""
+    Image = pytest.importorskip("PIL.Image")
+    from vulkanexp_b200._lib import VkxError, image_decode
+
+    rng = np.random.default_rng(5)
+    rgba = rng.integers(0, 256, (37, 53, 4), dtype=np.uint8)
+    for mode in ("RGBA", "RGB", "L", "LA", "P"):
+        im = Image.fromarray(rgba, "RGBA").convert(mode) if mode != "P" else Image.fromarray(rgba[..., :3].copy(), "RGB").quantize(64)
+        path = str(tmp_path / ("img_%s.png" % mode))
+        im.save(path)
+        want = np.asarray(Image.open(path).convert("RGBA"), dtype=np.uint8)
+        got = image_decode(path)
+        assert got.shape == want.shape and np.array_equal(got, want), mode
+    big = rng.integers(0, 256, (300, 500, 4), dtype=np.uint8)  # several IDAT chunks, every filter type
+    path = str(tmp_path / "big.png")
+    Image.fromarray(big, "RGBA").save(path, optimize=True)
+    assert np.array_equal(image_decode(path), big)
+    scene_format.write_pam(str(tmp_path / "a.pam"), rgba)
+    assert np.array_equal(image_decode(str(tmp_path / "a.pam")), rgba)
+    with open(tmp_path / "b.ppm", "wb") as f:
+        f.write(b"P6\n# comment\n53 37\n255\n" + rgba[..., :3].tobytes())
+    got = image_decode(str(tmp_path / "b.ppm"))
+    assert np.array_equal(got[..., :3], rgba[..., :3]) and (got[..., 3] == 255).all()
+    with open(tmp_path / "c.jpg", "wb") as f:
+        f.write(b"\xff\xd8\xff\xe0" + bytes(64))
+    with pytest.raises(VkxError):
+        image_decode(str(tmp_path / "c.jpg"))

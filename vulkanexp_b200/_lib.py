@@ -48,6 +48,20 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
+def image_decode(path):
+    """vkx_image_decode: PNG / P6 / P7 file -> uint8 [h, w, 4] (host only, no GPU needed)."""
+    l = load()
+    w, h = C.c_uint32(0), C.c_uint32(0)
+    rc = l.vkx_image_decode(os.fsencode(path), None, C.c_size_t(0), C.byref(w), C.byref(h))
+    if rc != 0:
+        raise VkxError(rc, "vkx_image_decode(%s) failed" % path)
+    out = np.zeros((h.value, w.value, 4), dtype=np.uint8)
+    rc = l.vkx_image_decode(os.fsencode(path), _p(out), C.c_size_t(out.nbytes), C.byref(w), C.byref(h))
+    if rc != 0:
+        raise VkxError(rc, "vkx_image_decode(%s) failed" % path)
+    return out
+
+
 class Context:
     """One per GPU (vkx_ctx). Method names follow the C ABI; see include/vkx.h for the reference call each replaces."""
 

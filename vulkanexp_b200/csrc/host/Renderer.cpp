@@ -52,6 +52,17 @@ void Renderer::createAccelerationStructures() {
     std::vector<vkx_material> mats;
     for (const auto& m : _scene->getMaterials()) mats.push_back(m.properties);
     vkx_ctx* ctx = _device->ctx();
+    { // uploadTextures (reference src/Resources.cpp:46-95): images + sampler descriptions; mip chains are generated on the device
+        std::vector<vkx_texture> tex;
+        for (const auto& t : _scene->getTextures()) {
+            vkx_texture d{};
+            d.pixels = t.image.pixels.data(); d.width = t.image.width; d.height = t.image.height;
+            d.srgb = t.format == 43u ? 1u : 0u; // VK_FORMAT_R8G8B8A8_SRGB, else R8G8B8A8_UNORM (src/Scene.cpp:43,671,677)
+            d.magFilter = t.magFilter; d.minFilter = t.minFilter; d.wrapS = t.wrapS; d.wrapT = t.wrapT;
+            tex.push_back(d);
+        }
+        check(ctx, vkx_scene_textures(ctx, tex.data(), tex.size()));
+    }
     check(ctx, vkx_scene_upload(ctx, Vertices.data(), Vertices.size(), Indices.data(), Indices.size(), OffsetTable.data(), MeshIndexCounts.data(), OffsetTable.size(),
                                 mats.data(), mats.size(), _instances.data(), _instances.size()));
     check(ctx, vkx_bvh_build(ctx));

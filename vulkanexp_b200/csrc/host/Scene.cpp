@@ -27,7 +27,7 @@ void Mesh::computeBounds() {
 }
 
 bool Scene::loadScene(const std::string& path) {
-    _meshes.clear(); _nodes.clear(); _materials.clear(); _root = -1;
+    _meshes.clear(); _nodes.clear(); _materials.clear(); _textures.clear(); _root = -1;
     std::ifstream file(path, std::ios::binary | std::ios::ate);
     if (!file) { std::fprintf(stderr, "Scene::loadScene error: Could not open file '%s'.\n", path.c_str()); return false; }
     std::streamsize size = file.tellg();
@@ -89,6 +89,26 @@ bool Scene::loadScene(const std::string& path) {
             mesh.computeBounds();
             _meshes.push_back(std::move(mesh));
         }
+        if (root.contains("textures")) { // src/Scene.cpp:895-904; sources are relative to the scene file
+            const size_t slash = path.find_last_of("/\\");
+            const std::string dir = slash == std::string::npos ? std::string() : path.substr(0, slash + 1);
+            for (const Json& t : root["textures"].items()) {
+                TextureDesc d;
+                d.source = t["source"].asString();
+                d.format = uint32_t(t.get("format", 43));
+                if (t.contains("sampler")) {
+                    const Json& smp = t["sampler"];
+                    d.magFilter = uint32_t(smp.get("magFilter", 0)); d.minFilter = uint32_t(smp.get("minFilter", 0));
+                    d.wrapS = uint32_t(smp.get("wrapS", 0)); d.wrapT = uint32_t(smp.get("wrapT", 0));
+                }
+                std::string err;
+                if (!d.image.load(dir + d.source, &err)) { // the reference substitutes a blank image for textures it cannot read (src/Scene.cpp:699)
+                    std::fprintf(stderr, "Scene::loadScene: texture '%s': %s (replaced by a blank image).\n", d.source.c_str(), err.c_str());
+                    d.image = Image::blank();
+                }
+                _textures.push_back(std::move(d));
+            }
+        }
     } catch (const std::exception& e) { std::fprintf(stderr, "Scene::loadScene: malformed scene '%s': %s\n", path.c_str(), e.what()); return false; }
     for (size_t i = 0; i < _nodes.size(); ++i) if (_nodes[i].parent < 0) { _root = int(i); break; } // src/Scene.cpp:924-928
     _dirty = true;
@@ -130,7 +150,18 @@ bool Scene::save(const std::string& path) const {
         chunk += 2; meshes.push(j);
     }
     root["meshes"] = meshes;
-    root["textures"] = Json::array();
+    Json texs = Json::array(); // src/Scene.cpp:776-784 (the image files themselves are not rewritten)
+    for (const auto& t : _textures) {
+        Json j = Json::object(); j["source"] = t.source; j["format"] = Json(int(t.format));
+        Json smp = Json::object();
+        if (t.magFilter) smp["magFilter"] = Json(int(t.magFilter));
+        if (t.minFilter) smp["minFilter"] = Json(int(t.minFilter));
+        if (t.wrapS) smp["wrapS"] = Json(int(t.wrapS));
+        if (t.wrapT) smp["wrapT"] = Json(int(t.wrapT));
+        j["sampler"] = smp;
+        texs.push(j);
+    }
+    root["textures"] = texs;
     const std::string js = root.toString();
     uint32_t total = uint32_t(sizeof(Header) + sizeof(ChunkHeader) + js.size());
     for (const auto& m : _meshes) total += uint32_t(2 * sizeof(ChunkHeader) + m.vertices.size() * sizeof(vkx_vertex) + m.indices.size() * 4);

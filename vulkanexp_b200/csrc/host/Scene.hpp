@@ -1,11 +1,12 @@
 // Host-side scene: the reference's Scene class reduced to what the hot path consumes (reference src/Scene.hpp:87-118):
 // the binary .scene container (loadScene / save), the node hierarchy with cached global transforms (update), bounds.
-// glTF/OBJ importers, skinning and animation are out of scope (component 5).
+// and the texture list (decoded by Image.cpp). glTF/OBJ importers, skinning and animation are out of scope (component 5).
 #pragma once
 #include <cstdint>
 #include <string>
 #include <vector>
 #include "../../../include/vkx.h"
+#include "Image.hpp"
 #include "Math.hpp"
 
 namespace vkx {
@@ -33,6 +34,15 @@ struct NodeComponent { // reference src/Scene.hpp:15-27
 
 struct MaterialDesc { std::string name; vkx_material properties; };
 
+// One entry of the reference's global Textures list (reference src/Resources.hpp, filled by Scene::loadScene src/Scene.cpp:895-904):
+// image source relative to the scene file, VkFormat (43 = R8G8B8A8_SRGB, 37 = R8G8B8A8_UNORM) and the glTF sampler description.
+struct TextureDesc {
+    std::string source;
+    uint32_t format = 43;
+    uint32_t magFilter = 0, minFilter = 0, wrapS = 0, wrapT = 0; // 0 = absent (the reference's defaults 9729 / 10497 apply)
+    Image image;                                                  // decoded at load time (the reference decodes in uploadTextures)
+};
+
 class Scene {
   public:
     bool load(const std::string& path) { return loadScene(path); }
@@ -47,6 +57,8 @@ class Scene {
     const std::vector<NodeComponent>& getNodes() const { return _nodes; }
     std::vector<MaterialDesc>& getMaterials() { return _materials; }
     const std::vector<MaterialDesc>& getMaterials() const { return _materials; }
+    std::vector<TextureDesc>& getTextures() { return _textures; }
+    const std::vector<TextureDesc>& getTextures() const { return _textures; }
     int getRoot() const { return _root; }
     void markDirty() { _dirty = true; }
 
@@ -54,6 +66,7 @@ class Scene {
     std::vector<Mesh> _meshes;
     std::vector<NodeComponent> _nodes;
     std::vector<MaterialDesc> _materials;
+    std::vector<TextureDesc> _textures;
     int _root = -1;
     bool _dirty = false;
     Bounds _bounds;

@@ -72,6 +72,24 @@ def read_pam(path):
     return np.frombuffer(data, dtype=np.uint8, count=w * h * 4, offset=end).reshape(h, w, 4).copy()
 
 
+def write_image(path, pixels):
+    """.png through Pillow when the source name asks for it (tests of the PNG decoder), Netpbm P7 otherwise."""
+    if path.lower().endswith(".png"):
+        from PIL import Image
+
+        Image.fromarray(np.ascontiguousarray(pixels, dtype=np.uint8), "RGBA").save(path)
+    else:
+        write_pam(path, pixels)
+
+
+def read_image(path):
+    if path.lower().endswith(".png"):
+        from PIL import Image
+
+        return np.asarray(Image.open(path).convert("RGBA"), dtype=np.uint8).copy()
+    return read_pam(path)
+
+
 def texture_list(scene):
     """The scene's textures as the list vkx_scene_textures takes (pods.texture_array): image + VkFormat class + glTF sampler."""
     out = []
@@ -121,7 +139,7 @@ def material_json(name, base_color=(1.0, 1.0, 1.0), metallic=0.0, roughness=1.0,
 
 def write_scene(path, scene: SceneFile):
     for t, img in zip(scene.textures, scene.images):  # texture sources are relative to the scene file (src/Scene.cpp:780,899)
-        write_pam(os.path.join(os.path.dirname(os.path.abspath(path)), t["source"]), img)
+        write_image(os.path.join(os.path.dirname(os.path.abspath(path)), t["source"]), img)
     root = {
         "materials": scene.materials,
         "entities": [],
@@ -188,7 +206,7 @@ def read_scene(path) -> SceneFile:
         i = np.frombuffer(buffers[m["indexArray"] - 1], dtype="<u4").copy()
         s.meshes.append(Mesh(m["name"], int(m.get("material", 0)), v, i))
     for t in s.textures:
-        s.images.append(read_pam(os.path.join(os.path.dirname(os.path.abspath(path)), t["source"])))
+        s.images.append(read_image(os.path.join(os.path.dirname(os.path.abspath(path)), t["source"])))
     return s
 
 
