@@ -162,7 +162,8 @@ int vkx_scene_upload(vkx_ctx* ctx, const vkx_vertex* vertices, size_t numVertice
  * fp32 weights, isotropic level of detail (the reference enables anisotropic filtering, whose footprint is implementation-defined).
  * Consumers: closest-hit shading of probe and reflection rays (textureGrad with the ray differentials of texDerivative,
  * src/shaders/closesthit.glsl:50-107,161-192) and the alpha cut-out of anyhit.rahit in the sun-shadow and reflection pipelines.
- * numTextures = 0 removes the list. Must precede the vkx_scene_upload whose materials use the textures. */
+ * numTextures = 0 removes the list. Must precede the vkx_scene_upload whose materials use the textures; replacing the list by one
+ * shorter than the uploaded materials need discards the uploaded scene (tracing fails until the next vkx_scene_upload + vkx_bvh_build). */
 int vkx_scene_textures(vkx_ctx* ctx, const vkx_texture* textures, size_t numTextures);
 /* Host-side image decoder (no context, no GPU): what STBImage does in uploadTextures (src/Resources.cpp:56-60), for the formats the
  * library reads itself: PNG (8 bits per channel, non-interlaced), Netpbm P6 and P7. Always expands to RGBA8. rgba may be NULL to

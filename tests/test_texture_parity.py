@@ -79,13 +79,16 @@ def test_texture_errors():
     flat = get_scene("tcourt")
     with pytest.raises(VkxError):  # materials use textures that were not provided
         g.scene_upload({k: v for k, v in flat.items() if k != "textures"})
-    g.scene_upload(flat)
-    with pytest.raises(VkxError):  # cannot drop textures the uploaded materials use
-        g.scene_textures([])
+    g.scene_upload(flat); g.bvh_build()
+    ray = (np.array([[0.0, 3.0, 0.0]], dtype=np.float32), np.array([[0.0, -1.0, 0.0]], dtype=np.float32))
+    assert g.trace(*ray, 0.01, 100.0)["t"][0] > 0
     with pytest.raises(VkxError):
         g.texture_sample(99, np.zeros((1, 2), dtype=np.float32))
-    g.scene_upload(get_scene("court"))  # an untextured scene releases the constraint
-    g.scene_textures([])
+    g.scene_textures([])  # dropping textures the uploaded materials use discards that scene
+    with pytest.raises(VkxError):
+        g.trace(*ray, 0.01, 100.0)
+    g.scene_upload(get_scene("court")); g.bvh_build()
+    assert g.trace(*ray, 0.01, 100.0)["t"][0] > 0
 
 
 def test_shadow_pass_through_cut_out_canopy(oracle_lib):

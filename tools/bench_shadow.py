@@ -9,7 +9,8 @@ from vulkanexp_b200.host_logic import OrientationGenerator
 from vulkanexp_b200.pods import GridInfo, Light, make_camera
 
 W, H = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (3840, 2160)
-s = synth.make_cfg3(); flat = scene_format.flatten(s)
+ALPHA = os.environ.get("VKX_CFG3_ALPHA", "0") == "1"  # cfg3 with the cut-out (alpha-textured) grates: shadow rays run the any-hit test
+s = synth.make_cfg3(alpha_grates=ALPHA); flat = scene_format.flatten(s)
 g = Context(0); g.scene_upload(flat); g.bvh_build()
 info = g.bvh_info()
 g.shadow_set_noise(synth.blue_noise_like(64, 64)); g.shadow_init(W, H)
@@ -39,7 +40,7 @@ pd, _ = g.gbuffer_download()
 steady = ms[4:]
 avg = {k: float(np.mean([m[k] for m in steady])) for k in steady[0]}
 px = W * H
-print(json.dumps({"metric": "sun_shadow_pass_ms", "value": avg["full"], "unit": "ms", "width": W, "height": H, "triangles": int(info.numTriangles), "stages_ms": avg,
+print(json.dumps({"metric": "sun_shadow_pass_ms", "alpha_grates": ALPHA, "value": avg["full"], "unit": "ms", "width": W, "height": H, "triangles": int(info.numTriangles), "stages_ms": avg,
                   "gbuffer_fixture_ms": float(np.mean(gb[4:])), "geometry_pixels": float((pd[..., 3] > 0).mean()),
                   "filter_bytes_per_px": 48 + 64, "filter_gbs": px * (48 + 64) / ((avg["filter_x"] + avg["filter_y"]) * 1e-3) / 1e9,
                   "shadow_rays_per_s": px * float((pd[..., 3] > 0).mean()) / (avg["trace"] * 1e-3),

@@ -15,7 +15,12 @@ g.probes_init(grid)
 g.probes_upload(state=np.ones(grid.probe_count, dtype=np.uint32))
 gen = OrientationGenerator(); gen.next()
 light = Light.default()
+hist = []
 for f in range(steps):
     grid.hysteresis = min(0.98, 0.25 * f)
     g.probes_update(grid, light, gen.next(), None)
-    print(f, g.probes_timings(), g.probes_kernel_timings())
+    t, k = g.probes_timings(), g.probes_kernel_timings()
+    print(f, t, k)
+    hist.append({**k, "full": t["full"]})
+if len(hist) > 2:  # last line: medians over the steps after the first two (tools/pick_defer.py reads it)
+    print("median", {name: float(np.median([h[name] for h in hist[2:]])) for name in hist[0]})

@@ -73,7 +73,6 @@ extern "C" int vkx_scene_textures(vkx_ctx* ctx, const vkx_texture* textures, siz
     if (!ctx) return VKX_E_INVALID;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     if (numTextures && !textures) return vkx_fail(ctx, VKX_E_INVALID, "vkx_scene_textures: null array");
-    if (numTextures < ctx->texturesUsed) return vkx_fail(ctx, VKX_E_INVALID, "vkx_scene_textures: the uploaded materials use %u textures, %zu given", ctx->texturesUsed, numTextures);
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     std::vector<DeviceTexture> desc(numTextures);
     size_t total = 0;
@@ -93,6 +92,9 @@ extern "C" int vkx_scene_textures(vkx_ctx* ctx, const vkx_texture* textures, siz
         }
     }
     if (total >= (1ull << 32)) return vkx_fail(ctx, VKX_E_UNSUPPORTED, "texture arena exceeds 2^32 texels");
+    if (numTextures < ctx->texturesUsed) { // the uploaded materials point past the new list: that scene is gone until the next vkx_scene_upload
+        ctx->numInstances = 0; ctx->numFlatTris = 0; ctx->texturesUsed = 0; ctx->bvhBuilt = false;
+    }
     freeTextures(ctx);
     if (!ctx->dSrgbLut) { // T4: exact transfer function per code, evaluated in double precision
         float lut[256], thr[256];

@@ -461,8 +461,10 @@ def count_triangles(s: SceneFile):
     return sum(len(s.meshes[e.mesh_renderer[0]].indices) // 3 for e in s.entities if e.mesh_renderer is not None)
 
 
-def make_cfg3(cells=10):
-    """"dungeon-like": corridor maze with pillars and bar grates (geometry, no alpha textures); ~0.5 M triangles."""
+def make_cfg3(cells=10, alpha_grates=False):
+    """"dungeon-like": corridor maze with pillars and bar grates (geometry); ~0.5 M triangles. alpha_grates=True adds the cut-out grates
+    of SURVEY 8(d) cfg3: quads across corridor cells whose albedo texture has alpha 0 holes (61 % opaque), so the sun-shadow rays
+    run the any-hit cut-out test."""
     rng = np.random.default_rng(SEED_BASE + 3)
     mats = [
         material_json("rock", (0.45, 0.43, 0.4), 0.0, 0.95),
@@ -492,6 +494,24 @@ def make_cfg3(cells=10):
             if rng.random() < 0.3:
                 for b in range(12):
                     _add(s, "B%d_%d_%d" % (i, j, b), M["Bar"], trs((-half + cs * i + 0.45 * b + 0.3, 0, -half + cs * j + 0.2)))
+    if alpha_grates:
+        images, entries = procedural_textures()
+        s.images, s.textures = [images[4]], [entries[4]]
+        grate = material_json("grate", (0.9, 0.9, 0.9), 0.0, 0.8)
+        grate["pbrMetallicRoughness"]["baseColorTexture"] = {"index": 0}
+        s.materials.append(grate)
+        # horizontal grates 4.5 m above the floor (they shadow the corridor below) and vertical ones across corridors
+        s.meshes.append(planar_uvs(grid_patch("GrateH", len(s.materials) - 1, (-cs / 2, 4.5, -cs / 2), (0, 0, cs), (cs, 0, 0), 2, 2), scale=1.0))
+        s.meshes.append(planar_uvs(grid_patch("GrateV", len(s.materials) - 1, (-cs / 2, 0, 0), (cs, 0, 0), (0, 5.0, 0), 2, 2), scale=1.0))
+        gh, gv = len(s.meshes) - 2, len(s.meshes) - 1
+        rng2 = np.random.default_rng(SEED_BASE + 33)
+        for i in range(cells):
+            for j in range(cells):
+                r = rng2.random()
+                if r < 0.35:
+                    _add(s, "GH%d_%d" % (i, j), gh, trs((-half + cs * i + cs / 2, 0, -half + cs * j + cs / 2)))
+                elif r < 0.5:
+                    _add(s, "GV%d_%d" % (i, j), gv, trs((-half + cs * i + cs / 2, 0, -half + cs * j + cs / 2), ry=float(rng2.integers(0, 2)) * np.pi / 2))
     return s
 
 
