@@ -129,7 +129,8 @@ def test_shadow_pass_through_cut_out_canopy(oracle_lib):
 
 
 def test_textured_update_differs_from_untextured_only_in_radiance(oracle_lib):
-    """Probe pipeline: no any-hit shader, so hit records equal the untextured scene's; radiance changes; parity as usual."""
+    """Probe pipeline: no any-hit shader, so the rays hit what they hit in the untextured scene (same hit distances; instance ids differ
+    because the instance list is sorted by material); radiance changes; parity as usual."""
     o, g, flat = make_pair(oracle_lib, "tcourt")
     gp = Context(0)
     gp.scene_upload(get_scene("court")); gp.bvh_build()
@@ -148,7 +149,9 @@ def test_textured_update_differs_from_untextured_only_in_radiance(oracle_lib):
     hg, sg = g.probes_download_hits()
     hp, sp = gp.probes_download_hits()
     ho, so = o.probes_download_hits()
-    assert hg.tobytes() == hp.tobytes() == ho.tobytes() and np.array_equal(sg, sp) and np.array_equal(sg, so)
+    assert hg.tobytes() == ho.tobytes() and np.array_equal(sg, so)
+    assert np.array_equal(hg["t"], hp["t"]), "hit distances must not depend on the textures"
+    assert np.array_equal(sg, sp), "the nested shadow rays of the probe pipeline do not see the cut-outs either"
     ro = o.probes_download(rays=True)[3]
     rg = g.probes_download(rays=True)[3]
     rp = gp.probes_download(rays=True)[3]

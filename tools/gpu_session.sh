@@ -11,12 +11,16 @@ log "start $(nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,no
 timeout 120 python __graft_entry__.py smoke > $out/smoke.log 2>&1; log "smoke rc=$? $(tail -1 $out/smoke.log | cut -c1-200)"
 timeout 400 python -m pytest tests/test_texture_parity.py -q -m gpu --maxfail=20 -p no:cacheprovider > $out/pytest_texture.log 2>&1; log "texture tests rc=$? $(tail -1 $out/pytest_texture.log)"
 timeout 700 python -m pytest tests -q -m gpu -n 4 --maxfail=20 --durations=12 -p no:cacheprovider --deselect tests/test_texture_parity.py > $out/pytest_all.log 2>&1; log "gpu suite rc=$? $(tail -1 $out/pytest_all.log)"
-for d in 8 16; do
+for d in ${PARITY_DEFER:-1}; do
   VKX_PT_DEFER=$d VKX_PT_DEFER_SHADOW=$d timeout 300 python -m pytest tests/test_ddgi_parity.py tests/test_bvh_parity.py -q -m gpu -n 4 -p no:cacheprovider > $out/pytest_defer_$d.log 2>&1; log "defer $d parity rc=$? $(tail -1 $out/pytest_defer_$d.log)"
 done
-for d in 0 8 12 16; do
+for d in ${SWEEP_DEFER:-0 1 12}; do
   VKX_PT_DEFER=$d VKX_PT_DEFER_SHADOW=$d timeout 120 python tools/profile_step.py 8 2> $out/sweep_defer_$d.err | tail -1 > $out/sweep_defer_$d.txt; log "sweep defer=$d: $(cat $out/sweep_defer_$d.txt | cut -c1-300)"
 done
+if [ -f vulkanexp_b200/libvkexp_b200_lazy.so ]; then # A/B of a compile-time variant: triangle words loaded lazily (old) vs all at once (new default)
+  VKX_LIB_PATH=$PWD/vulkanexp_b200/libvkexp_b200_lazy.so VKX_PT_DEFER=0 VKX_PT_DEFER_SHADOW=12 timeout 120 python tools/profile_step.py 8 2> $out/sweep_lazy.err | tail -1 > $out/sweep_lazy.txt; log "sweep lazy-load build, defer 0/12: $(cat $out/sweep_lazy.txt | cut -c1-300)"
+  VKX_PT_DEFER=0 VKX_PT_DEFER_SHADOW=12 timeout 120 python tools/profile_step.py 8 2> $out/sweep_eager.err | tail -1 > $out/sweep_eager.txt; log "sweep eager-load build, defer 0/12: $(cat $out/sweep_eager.txt | cut -c1-300)"
+fi
 best=$(python tools/pick_defer.py $out)
 log "best: $best"
 timeout 300 python bench.py > $out/bench_default.json 2> $out/bench_default.err; log "bench default rc=$? $(cut -c1-160 $out/bench_default.json)"
@@ -24,9 +28,9 @@ env $best timeout 300 python bench.py --no-cpu-baseline > $out/bench_best.json 2
 timeout 200 python tools/bench_shadow.py > $out/shadow_plain.json 2> $out/shadow_plain.err; log "shadow plain rc=$? $(cut -c1-400 $out/shadow_plain.json)"
 VKX_CFG3_ALPHA=1 timeout 200 python tools/bench_shadow.py > $out/shadow_alpha.json 2> $out/shadow_alpha.err; log "shadow alpha rc=$? $(cut -c1-400 $out/shadow_alpha.json)"
 # ncu: launch list of the bench command and full captures of the two traversal kernels, with the best variant
-env $best timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/launches_r01b.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/bench_under_ncu.log 2>&1; log "ncu launch list rc=$?"
+env $best timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/launches_${TAG:-r01c}.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/bench_under_ncu.log 2>&1; log "ncu launch list rc=$?"
 for k in k_trace_primary k_trace_shadow; do
-  env $best timeout 300 ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 1 -f -o $out/prof_r01b_$k python tools/profile_step.py 4 > $out/prof_$k.log 2>&1; log "ncu full $k rc=$?"
+  env $best timeout 300 ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 1 -f -o $out/prof_${TAG:-r01c}_$k python tools/profile_step.py 4 > $out/prof_$k.log 2>&1; log "ncu full $k rc=$?"
 done
-VKX_CFG3_ALPHA=1 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_direct_light -s 6 -c 1 -f -o $out/prof_r01b_k_direct_light_alpha python tools/bench_shadow.py > $out/prof_k_direct_light_alpha.log 2>&1; log "ncu full k_direct_light alpha rc=$?"
+VKX_CFG3_ALPHA=1 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_direct_light -s 6 -c 1 -f -o $out/prof_${TAG:-r01c}_k_direct_light_alpha python tools/bench_shadow.py > $out/prof_k_direct_light_alpha.log 2>&1; log "ncu full k_direct_light alpha rc=$?"
 log done

@@ -4,7 +4,7 @@ import ast, os, re, sys
 
 out = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out"
 best = {"trace_primary": (1e9, 0), "trace_shadow": (1e9, 0)}
-for d in (0, 8, 12, 16):
+for d in (0, 1, 8, 12, 16):
     p = os.path.join(out, "sweep_defer_%d.txt" % d)
     if not os.path.exists(p):
         continue

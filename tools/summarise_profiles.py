@@ -12,8 +12,12 @@ KEEP = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
 traffic = {}
+_tp = os.path.join(ROOT, "profiles", "traffic.json")
+if os.path.exists(_tp):  # kernels captured in earlier sessions keep their entries; this run's captures replace theirs
+    traffic = {k: v for k, v in json.load(open(_tp)).items() if not k.startswith("_")}
 for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "prof_%s_k_*.ncu-rep" % tag))):
     kernel = re.search(r"prof_%s_(k_\w+)\.ncu-rep" % tag, rep).group(1)
+    traffic_key = kernel[:-len("_alpha")] + "<alpha>" if kernel.endswith("_alpha") else kernel
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     if len(rows) < 3:
@@ -28,12 +32,12 @@ for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "prof_%s_k_*.ncu-re
     def num(name):
         i = hdr.index(name); v = float(vals[i].replace(",", "")); u = units[i].lower()
         return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
-    traffic[kernel] = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
-    print(kernel, vals[hdr.index("gpu__time_duration.sum")], units[hdr.index("gpu__time_duration.sum")], "dram bytes", traffic[kernel])
+    traffic[traffic_key] = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
+    print(kernel, vals[hdr.index("gpu__time_duration.sum")], units[hdr.index("gpu__time_duration.sum")], "dram bytes", traffic[traffic_key])
 if "k_shade_front" in traffic and "k_shade_miss" in traffic:
     traffic["k_shade"] = traffic["k_shade_front"] + traffic["k_shade_miss"]
 traffic["_source"] = ("dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full --clock-control none, tools/collect_profiles.sh "
-                      "(DDGI kernels: cfg2, 16384 probes x 256 rays; screen-space kernels: cfg3 at 3840x2160), summaries in profiles/%s_ncu_full_*.csv" % tag)
+                      "(DDGI kernels: cfg2, 16384 probes x 256 rays; screen-space kernels: cfg3 at 3840x2160), summaries in profiles/r01*_ncu_full_*.csv (latest capture: %s)" % tag)
 json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
 src = os.path.join(ROOT, "gpurun_out", "launches_%s.csv" % tag)
 if os.path.exists(src):

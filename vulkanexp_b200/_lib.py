@@ -11,7 +11,8 @@ import numpy as np
 from .pods import BvhInfo, Camera, GridInfo, HIT_DTYPE, Light, NODE_DTYPE, TRI_DTYPE, mip_chain_texels, texture_array
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvkexp_b200.so")
+# VKX_LIB_PATH: an alternative build of the same library (A/B timing of compile-time variants, tools/gpu_session.sh)
+LIB_PATH = os.environ.get("VKX_LIB_PATH") or os.path.join(_HERE, "libvkexp_b200.so")
 _LIB = None
 
 

@@ -24,10 +24,9 @@
 template <bool ANY>
 __device__ __forceinline__ bool testTriangle(const float4* __restrict__ tris, uint32_t triIndex, const Ray& r, float tmin, float& tbest, uint32_t cullMask, HitRec& hit) {
     const float4* tp = tris + size_t(triIndex) * 3;
-    const float4 q2 = __ldg(tp + 2);
+    const float4 q2 = __ldg(tp + 2), q0 = __ldg(tp + 0), q1 = __ldg(tp + 1); // all three words at once: one memory round trip per triangle
     const uint32_t instW = __float_as_uint(q2.y), primW = __float_as_uint(q2.z);
     if (!((instW >> 24) & cullMask)) return false;
-    const float4 q0 = __ldg(tp + 0), q1 = __ldg(tp + 1);
     float t, u, v, det;
     if (!intersectTri(q0, q1, q2, r, t, u, v, det)) return false;
     if (!(t > tmin)) return false;
@@ -89,9 +88,32 @@ __device__ __forceinline__ void persistentTraceDeferred(const uint4* __restrict_
             }
         }
         const bool parked = active && pBits != 0u;
+        bool advance = false, done = false; // advance: this lane has no untested triangles left and must pick its next node
+        if (DEFER == 1) {
+            // Interleaved mode: every iteration a lane does one unit of work, either one node step or ONE of its parked triangles. The
+            // two paths still serialise inside the warp, but the triangle path now collects the lanes of ~2.5 baseline iterations
+            // (profiles/r01b: 2.5 triangle-loop trips per node step at 3.7 of 32 lanes) into one trip.
+            if (parked) {
+                const uint32_t b = uint32_t(__ffs(int(pBits))) - 1u;
+                pBits &= pBits - 1u;
+                if (testTriangle<ANY>(tris, pBase + b, r, tmin, tbest, cullMask, hit)) { done = true; pBits = 0u; }
+                advance = pBits == 0u;
+            } else if (active) {
+                const uint32_t bit = 31u - uint32_t(__clz(int(g.y)));
+                g.y &= ~(1u << bit);
+                if (g.y & 0xFF000000u) { if (sp < VKX_STACK) stack[sp++] = g; }
+                const uint32_t slot = (bit - 24u) ^ r.oct;
+                const uint32_t rel = uint32_t(__popc(g.y & 0xFFu & ((1u << slot) - 1u)));
+                uint4 w0, w1, w2, w3, w4;
+                loadNode(nodes, g.x + rel, w0, w1, w2, w3, w4);
+                const uint32_t m = intersectNode(w0, w1, w2, w3, w4, r, tmin, tbest);
+                g.x = w1.x; g.y = (m & 0xFF000000u) | (w0.w >> 24);
+                pBase = w1.y; pBits = m & 0x00FFFFFFu;
+                advance = pBits == 0u;
+            }
+        } else {
         const int nParked = __popc(__ballot_sync(0xFFFFFFFFu, parked));
         const int nStep = __popc(__ballot_sync(0xFFFFFFFFu, active && pBits == 0u));
-        bool advance = false, done = false; // advance: this lane has no untested triangles left and must pick its next node
         if (nParked >= DEFER || (nParked > 0 && nParked >= nStep)) { // triangle phase
             if (parked) {
                 do {
@@ -113,6 +135,7 @@ __device__ __forceinline__ void persistentTraceDeferred(const uint4* __restrict_
             g.x = w1.x; g.y = (m & 0xFF000000u) | (w0.w >> 24);
             pBase = w1.y; pBits = m & 0x00FFFFFFu;
             advance = pBits == 0u;
+        }
         }
         if (advance) {
             if (!done && !(g.y & 0xFF000000u)) {
@@ -182,10 +205,16 @@ __device__ __forceinline__ void persistentTrace(const uint4* __restrict__ nodes,
                 const uint32_t b = uint32_t(__ffs(int(triBits))) - 1u;
                 triBits &= triBits - 1u;
                 const float4* tp = tris + size_t(triBase + b) * 3;
+#ifdef PT_LAZY_TRI_LOADS
                 const float4 q2 = __ldg(tp + 2);
                 const uint32_t instW = __float_as_uint(q2.y), primW = __float_as_uint(q2.z);
                 if (!((instW >> 24) & cullMask)) continue;
                 const float4 q0 = __ldg(tp + 0), q1 = __ldg(tp + 1);
+#else
+                const float4 q2 = __ldg(tp + 2), q0 = __ldg(tp + 0), q1 = __ldg(tp + 1); // one memory round trip per triangle instead of two
+                const uint32_t instW = __float_as_uint(q2.y), primW = __float_as_uint(q2.z);
+                if (!((instW >> 24) & cullMask)) continue;
+#endif
                 float t, u, v, det;
                 if (!intersectTri(q0, q1, q2, r, t, u, v, det)) continue;
                 if (!(t > tmin)) continue;
