@@ -146,6 +146,8 @@ def test_textured_update_differs_from_untextured_only_in_radiance(oracle_lib):
         for c in (o, g, gp):
             c.probes_update(grid, light, R, None)
         grid.hysteresis = 0.6
+        io, do, sto, _ = o.probes_download()  # the next frame reads these atlases: continue from the oracle's (a 1-ulp difference can
+        g.probes_upload(io, do, sto)          # flip a packed code, which is 2^-6 relative; same protocol as test_ddgi_parity)
     hg, sg = g.probes_download_hits()
     hp, sp = gp.probes_download_hits()
     ho, so = o.probes_download_hits()

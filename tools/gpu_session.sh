@@ -29,8 +29,14 @@ timeout 200 python tools/bench_shadow.py > $out/shadow_plain.json 2> $out/shadow
 VKX_CFG3_ALPHA=1 timeout 200 python tools/bench_shadow.py > $out/shadow_alpha.json 2> $out/shadow_alpha.err; log "shadow alpha rc=$? $(cut -c1-400 $out/shadow_alpha.json)"
 # ncu: launch list of the bench command and full captures of the two traversal kernels, with the best variant
 env $best timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/launches_${TAG:-r01c}.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/bench_under_ncu.log 2>&1; log "ncu launch list rc=$?"
-for k in k_trace_primary k_trace_shadow; do
+for k in ${PROFILE_DDGI:-k_trace_primary k_trace_shadow}; do
   env $best timeout 300 ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 1 -f -o $out/prof_${TAG:-r01c}_$k python tools/profile_step.py 4 > $out/prof_$k.log 2>&1; log "ncu full $k rc=$?"
 done
-VKX_CFG3_ALPHA=1 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_direct_light -s 6 -c 1 -f -o $out/prof_${TAG:-r01c}_k_direct_light_alpha python tools/bench_shadow.py > $out/prof_k_direct_light_alpha.log 2>&1; log "ncu full k_direct_light alpha rc=$?"
+for k in ${PROFILE_SCREEN:-}; do
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:$k -s 6 -c 1 -f -o $out/prof_${TAG:-r01c}_$k python tools/bench_shadow.py > $out/prof_$k.log 2>&1; log "ncu full $k rc=$?"
+done
+# the textured kernel variants: cfg3 with cut-out grates (k_direct_light<true>, k_reflect_shade<true>)
+for k in ${PROFILE_ALPHA:-k_direct_light}; do
+  VKX_CFG3_ALPHA=1 timeout 300 ncu --set full --clock-control none --import-source on -k regex:$k -s 6 -c 1 -f -o $out/prof_${TAG:-r01c}_${k}_alpha python tools/bench_shadow.py > $out/prof_${k}_alpha.log 2>&1; log "ncu full $k alpha rc=$?"
+done
 log done

@@ -463,11 +463,10 @@ int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* /*unused*/,
     static bool blendAttr = false;
     if (!blendAttr) { CUDA_TRY(ctx, cudaFuncSetAttribute(k_blend, cudaFuncAttributeMaxDynamicSharedMemorySize, BLEND_SMEM_BYTES)); blendAttr = true; }
     // Leaf deferral of the two persistent traversals (ptrace.cuh): 0 = off, else the number of waiting lanes that triggers a triangle phase.
-    // 1 = interleaved mode (one node step or one parked triangle per lane and iteration).
-    // Tuning knobs (results are identical for every value): VKX_PT_DEFER / VKX_PT_DEFER_SHADOW in {0, 1, 8, 12, 16}.
+    // Tuning knobs (results are identical for every value): VKX_PT_DEFER / VKX_PT_DEFER_SHADOW in {0, 8, 12, 16}.
     static int deferPrimary = -1, deferShadow = -1;
     if (deferPrimary < 0) {
-        auto pick = [](const char* name, int dflt) { const char* e = getenv(name); int v = e ? atoi(e) : dflt; return v <= 0 ? 0 : v == 1 ? 1 : v <= 8 ? 8 : v <= 12 ? 12 : 16; };
+        auto pick = [](const char* name, int dflt) { const char* e = getenv(name); int v = e ? atoi(e) : dflt; return v <= 0 ? 0 : v <= 8 ? 8 : v <= 12 ? 12 : 16; };
         deferPrimary = pick("VKX_PT_DEFER", PT_DEFER_PRIMARY_DEFAULT); deferShadow = pick("VKX_PT_DEFER_SHADOW", PT_DEFER_SHADOW_DEFAULT);
     }
     static int blocksPerSm = 0;
@@ -496,7 +495,7 @@ int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* /*unused*/,
         k_origin_table<<<divUp(n, 128), 128, 0, st>>>(ctx->grid, idx, n, ctx->dOrigins); LAUNCH_CHECK(ctx);
         if (timed) { CUDA_TRY(ctx, cudaEventRecord(ctx->kev[0], st)); ctx->kevProbes = n; }
 #define VKX_LAUNCH_PRIMARY(D) k_trace_primary<D><<<persistentBlocks, 128, 0, st>>>(sc, tp, rm, ctx->dOrigins, ctx->dDirs, ctx->dInvDirs, ctx->dHits, ctx->dRays, ctx->dMissQueue, ctx->dFrontQueue, ctx->dQueueCount)
-        switch (deferPrimary) { case 1: VKX_LAUNCH_PRIMARY(1); break; case 8: VKX_LAUNCH_PRIMARY(8); break; case 12: VKX_LAUNCH_PRIMARY(12); break; case 16: VKX_LAUNCH_PRIMARY(16); break; default: VKX_LAUNCH_PRIMARY(0); }
+        switch (deferPrimary) { case 8: VKX_LAUNCH_PRIMARY(8); break; case 12: VKX_LAUNCH_PRIMARY(12); break; case 16: VKX_LAUNCH_PRIMARY(16); break; default: VKX_LAUNCH_PRIMARY(0); }
 #undef VKX_LAUNCH_PRIMARY
         LAUNCH_CHECK(ctx);
         if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[1], st));
@@ -522,7 +521,7 @@ int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* /*unused*/,
         if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[2], st));
         if (ctx->debugBuffers) CUDA_TRY(ctx, cudaMemsetAsync(ctx->dShadowFlags, 0, numRays, st));
 #define VKX_LAUNCH_SHADOW(D) k_trace_shadow<D><<<persistentBlocks, 128, 0, st>>>(sc, light, ctx->dShadowQueue, ctx->dQueueCount, ctx->dRays, ctx->debugBuffers ? ctx->dShadowFlags : nullptr, ctx->dQueueCount + 2)
-        switch (deferShadow) { case 1: VKX_LAUNCH_SHADOW(1); break; case 8: VKX_LAUNCH_SHADOW(8); break; case 12: VKX_LAUNCH_SHADOW(12); break; case 16: VKX_LAUNCH_SHADOW(16); break; default: VKX_LAUNCH_SHADOW(0); }
+        switch (deferShadow) { case 8: VKX_LAUNCH_SHADOW(8); break; case 12: VKX_LAUNCH_SHADOW(12); break; case 16: VKX_LAUNCH_SHADOW(16); break; default: VKX_LAUNCH_SHADOW(0); }
 #undef VKX_LAUNCH_SHADOW
         LAUNCH_CHECK(ctx);
         if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[3], st));

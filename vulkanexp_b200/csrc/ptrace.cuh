@@ -47,6 +47,10 @@ __device__ __forceinline__ bool testTriangle(const float4* __restrict__ tris, ui
 // hit of a ray does not depend on the order of its triangle tests (equal t is resolved by (instance, primitive)), and the node a
 // lane visits next is decided only after its parked triangles have been tested, so every ray executes exactly the per-ray
 // operation sequence of traverse<>: results are bit-identical, only the interleaving of rays inside a warp changes.
+// Measured on B200, cfg2 (profiles/r01c_defer_sweep.txt): any-hit rays gain (k_trace_shadow 0.400 -> 0.374 ms at DEFER = 12, the
+// default); closest-hit rays lose (k_trace_primary 0.949 -> 0.978 ms at 16, 1.04 ms at 8): a parked lane does not step, and with
+// 5-6 of 28 lanes receiving triangles per node step the node phase thins out faster than the triangle phase fills. A variant
+// without the threshold (every iteration one node step or one parked triangle per lane) was slower still (1.22 ms) and is gone.
 template <bool ANY, int DEFER, class Src>
 __device__ __forceinline__ void persistentTraceDeferred(const uint4* __restrict__ nodes, const float4* __restrict__ tris, Src& src, uint32_t total, uint32_t* __restrict__ counter) {
     const unsigned lane = threadIdx.x & 31u;
@@ -89,29 +93,6 @@ __device__ __forceinline__ void persistentTraceDeferred(const uint4* __restrict_
         }
         const bool parked = active && pBits != 0u;
         bool advance = false, done = false; // advance: this lane has no untested triangles left and must pick its next node
-        if (DEFER == 1) {
-            // Interleaved mode: every iteration a lane does one unit of work, either one node step or ONE of its parked triangles. The
-            // two paths still serialise inside the warp, but the triangle path now collects the lanes of ~2.5 baseline iterations
-            // (profiles/r01b: 2.5 triangle-loop trips per node step at 3.7 of 32 lanes) into one trip.
-            if (parked) {
-                const uint32_t b = uint32_t(__ffs(int(pBits))) - 1u;
-                pBits &= pBits - 1u;
-                if (testTriangle<ANY>(tris, pBase + b, r, tmin, tbest, cullMask, hit)) { done = true; pBits = 0u; }
-                advance = pBits == 0u;
-            } else if (active) {
-                const uint32_t bit = 31u - uint32_t(__clz(int(g.y)));
-                g.y &= ~(1u << bit);
-                if (g.y & 0xFF000000u) { if (sp < VKX_STACK) stack[sp++] = g; }
-                const uint32_t slot = (bit - 24u) ^ r.oct;
-                const uint32_t rel = uint32_t(__popc(g.y & 0xFFu & ((1u << slot) - 1u)));
-                uint4 w0, w1, w2, w3, w4;
-                loadNode(nodes, g.x + rel, w0, w1, w2, w3, w4);
-                const uint32_t m = intersectNode(w0, w1, w2, w3, w4, r, tmin, tbest);
-                g.x = w1.x; g.y = (m & 0xFF000000u) | (w0.w >> 24);
-                pBase = w1.y; pBits = m & 0x00FFFFFFu;
-                advance = pBits == 0u;
-            }
-        } else {
         const int nParked = __popc(__ballot_sync(0xFFFFFFFFu, parked));
         const int nStep = __popc(__ballot_sync(0xFFFFFFFFu, active && pBits == 0u));
         if (nParked >= DEFER || (nParked > 0 && nParked >= nStep)) { // triangle phase
@@ -135,7 +116,6 @@ __device__ __forceinline__ void persistentTraceDeferred(const uint4* __restrict_
             g.x = w1.x; g.y = (m & 0xFF000000u) | (w0.w >> 24);
             pBase = w1.y; pBits = m & 0x00FFFFFFu;
             advance = pBits == 0u;
-        }
         }
         if (advance) {
             if (!done && !(g.y & 0xFF000000u)) {
@@ -205,16 +185,10 @@ __device__ __forceinline__ void persistentTrace(const uint4* __restrict__ nodes,
                 const uint32_t b = uint32_t(__ffs(int(triBits))) - 1u;
                 triBits &= triBits - 1u;
                 const float4* tp = tris + size_t(triBase + b) * 3;
-#ifdef PT_LAZY_TRI_LOADS
-                const float4 q2 = __ldg(tp + 2);
+                const float4 q2 = __ldg(tp + 2); // (loading all three words before the mask test measured the same: 0.951 vs 0.944 ms)
                 const uint32_t instW = __float_as_uint(q2.y), primW = __float_as_uint(q2.z);
                 if (!((instW >> 24) & cullMask)) continue;
                 const float4 q0 = __ldg(tp + 0), q1 = __ldg(tp + 1);
-#else
-                const float4 q2 = __ldg(tp + 2), q0 = __ldg(tp + 0), q1 = __ldg(tp + 1); // one memory round trip per triangle instead of two
-                const uint32_t instW = __float_as_uint(q2.y), primW = __float_as_uint(q2.z);
-                if (!((instW >> 24) & cullMask)) continue;
-#endif
                 float t, u, v, det;
                 if (!intersectTri(q0, q1, q2, r, t, u, v, det)) continue;
                 if (!(t > tmin)) continue;
