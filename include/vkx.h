@@ -180,6 +180,21 @@ int vkx_texture_sample(vkx_ctx* ctx, uint32_t texture, const float* uv, const fl
  * reference refits its TLAS in place; here all instanced geometry lives in one world-space BVH, so the structure is marked stale
  * and the next vkx_bvh_build rebuilds it (the same deterministic build: the result equals a fresh upload with these transforms). */
 int vkx_instances_update(vkx_ctx* ctx, const vkx_instance* instances, size_t numInstances);
+/* Skinned meshes: vertexSkinning.comp (src/shaders/vertexSkinning.comp:37-60) as dispatched per SkinnedMeshRendererComponent by
+ * Renderer::updateSkinnedVertexBuffer (src/Renderer.cpp:201-240), then Renderer::updateSkinnedBLAS (src/Renderer.cpp:644-669).
+ * The caller lays the arenas out like Renderer::allocateSkinnedMeshes / updateSkinnedMeshOffsetTable (src/Renderer.cpp:133-164): a
+ * bind-pose copy of the mesh's vertices appended to the vertex arena (the destination range), an offset-table entry {material,
+ * that vertex offset, the mesh's index offset} and an instance with mask VKX_INSTANCE_SKINNED pointing at it.
+ *   jointTransforms  numJoints column-major mat4 (the reference's jointPoses: inverse(parent global) * joint global * inverse bind)
+ *   skinJoints       4 joint indices per vertex (uint16, as the shader reads them), skinWeights: 4 floats per vertex
+ *   src/dstOffset    first vertex of the mesh and of the skinned copy (push constants srcOffset / dstOffset), size: vertices
+ *   motionVectors    optional host array, 4 floats per vertex: new position - previous skinned position, w = 1
+ * Writes the skinned positions into the destination range and, as the shader does, the skinned normals / tangents into the
+ * *source* range. The BVH becomes stale: call vkx_bvh_build next (the reference rebuilds the skinned BLASes in place). */
+int vkx_skin_vertices(vkx_ctx* ctx, const float* jointTransforms, size_t numJoints, const uint16_t* skinJoints,
+                      const float* skinWeights, uint32_t srcOffset, uint32_t dstOffset, uint32_t size, float* motionVectors);
+/* Reads vertices of the device arena back (parity checks of vkx_skin_vertices). */
+int vkx_vertices_download(vkx_ctx* ctx, size_t firstVertex, size_t count, vkx_vertex* out);
 /* Deterministic binned-SAH build of the 8-wide compressed BVH on the device (replaces the driver's BLAS/TLAS
  * build, src/Renderer.cpp:272-449,525-642). Topology is bit-identical to oracle/bvh.cpp. */
 int vkx_bvh_build(vkx_ctx* ctx);

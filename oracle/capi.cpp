@@ -67,6 +67,16 @@ int orc_tex_derivative(const float position[3], const float rayOrigin[3], const 
     out[0] = g.x; out[1] = g.y; out[2] = g.z; out[3] = g.w;
     return 0;
 }
+int orc_skin_vertices(orc_ctx* c, const float* jointTransforms, size_t numJoints, const uint16_t* skinJoints, const float* skinWeights, uint32_t srcOffset, uint32_t dstOffset, uint32_t size, float* motionVectors) {
+    (void)numJoints;
+    oddgi::skinVertices(c->scene, jointTransforms, skinJoints, skinWeights, srcOffset, dstOffset, size, motionVectors);
+    return 0;
+}
+int orc_vertices_download(orc_ctx* c, size_t first, size_t count, vkx_vertex* out) {
+    if (first + count > c->scene.vertices.size()) return -1;
+    std::memcpy(out, c->scene.vertices.data() + first, count * sizeof(vkx_vertex));
+    return 0;
+}
 int orc_bvh_build(orc_ctx* c) { oddgi::sceneFinalize(c->scene); return 0; }
 int orc_bvh_info(orc_ctx* c, vkx_bvh_info* out) {
     const obvh::Bvh& b = c->scene.bvh;

@@ -404,6 +404,30 @@ void classify(const Scene& s, Probes& p, const float orientation[16]) {
     }
 }
 
+// ---------------------------------------------------------------- vertexSkinning.comp
+void skinVertices(Scene& s, const float* jointTransforms, const uint16_t* skinJoints, const float* skinWeights, uint32_t srcOffset, uint32_t dstOffset, uint32_t size, float* motionVectors) {
+    for (uint32_t i = 0; i < size; ++i) { // one invocation per vertex (:39-40)
+        const float* w = skinWeights + 4 * size_t(i);
+        mat4 J[4];
+        for (int k = 0; k < 4; ++k) J[k] = mat4_from(jointTransforms + 16 * size_t(skinJoints[4 * size_t(i) + k]));
+        mat4 skinMatrix; // :42-45, component-wise, left to right
+        for (int c = 0; c < 4; ++c) skinMatrix[c] = ((J[0][c] * w[0] + J[1][c] * w[1]) + J[2][c] * w[2]) + J[3][c] * w[3];
+        vkx_vertex& src = s.vertices[srcOffset + i];
+        vkx_vertex& dst = s.vertices[dstOffset + i];
+        vec4 np = skinMatrix * V4(src.pos[0], src.pos[1], src.pos[2], 1.0f);                     // :47
+        vec3 motionVector = xyz(np) - V3(dst.pos[0], dst.pos[1], dst.pos[2]);                    // :48
+        mat3 m3; for (int c = 0; c < 3; ++c) m3[c] = xyz(skinMatrix[c]);
+        // :52-53 read the normal / tangent of the *destination* vertex (the bind-pose copy) ...
+        vec3 normal = m3 * V3(dst.normal[0], dst.normal[1], dst.normal[2]);
+        vec3 tangent = m3 * V3(dst.tangent[0], dst.tangent[1], dst.tangent[2]);
+        dst.pos[0] = np.x; dst.pos[1] = np.y; dst.pos[2] = np.z;                                 // :49
+        // ... and :54-57 store them at the *source* vertex (sic)
+        src.normal[0] = normal.x; src.normal[1] = normal.y; src.normal[2] = normal.z;
+        src.tangent[0] = tangent.x; src.tangent[1] = tangent.y; src.tangent[2] = tangent.z;
+        if (motionVectors) { motionVectors[4 * size_t(i)] = motionVector.x; motionVectors[4 * size_t(i) + 1] = motionVector.y; motionVectors[4 * size_t(i) + 2] = motionVector.z; motionVectors[4 * size_t(i) + 3] = 1.0f; } // :59
+    }
+}
+
 // ---------------------------------------------------------------- textures: anyhit.rahit, texDerivative
 vec3 rotateAxis(vec3 p, vec3 axis, float angle) { // common.glsl:6-8
     return mix(dot(axis, p) * axis, p, std::cos(angle)) + cross(axis, p) * std::sin(angle);

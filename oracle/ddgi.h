@@ -50,6 +50,9 @@ struct Probes {
 };
 
 void sceneFinalize(Scene& s); // worldToObject + BVH
+// vertexSkinning.comp:37-60 over `size` vertices (push constants srcOffset / dstOffset); motionVectors: optional, 4 floats per vertex.
+// The BVH must be rebuilt afterwards (sceneFinalize), as Renderer::updateSkinnedBLAS does for the skinned BLASes.
+void skinVertices(Scene& s, const float* jointTransforms, const uint16_t* skinJoints, const float* skinWeights, uint32_t srcOffset, uint32_t dstOffset, uint32_t size, float* motionVectors);
 void probesInit(Probes& p, const vkx_grid_info& g);
 // mat3(orientation) * sphericalFibonacci(i, n) for i in [0, count)  (traceProbes.rgen:36, probesInit.rgen:41)
 void rayDirections(const float orientation[16], uint32_t count, float n, std::vector<float>& out);

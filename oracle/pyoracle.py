@@ -85,6 +85,21 @@ class Oracle:
         self._keep = (v, i, o, c, m, inst)
         self.l.orc_scene_upload(self.h, _p(v), C.c_size_t(len(v)), _p(i), C.c_size_t(len(i)), _p(o), _p(c), C.c_size_t(len(o)), _p(m), C.c_size_t(len(m)), _p(inst), C.c_size_t(len(inst)))
 
+    def skin_vertices(self, joint_transforms, skin_joints, skin_weights, src_offset, dst_offset, motion=False):
+        """vertexSkinning.comp: joint_transforms [J, 16] column-major, skin_joints uint16 [n, 4], skin_weights float32 [n, 4]."""
+        jt = np.ascontiguousarray(joint_transforms, dtype=np.float32).reshape(-1, 16)
+        sj = np.ascontiguousarray(skin_joints, dtype=np.uint16).reshape(-1, 4)
+        sw = np.ascontiguousarray(skin_weights, dtype=np.float32).reshape(-1, 4)
+        assert len(sj) == len(sw)
+        mv = np.zeros((len(sj), 4), dtype=np.float32) if motion else None
+        assert 0 == (self.l.orc_skin_vertices(self.h, _p(jt), C.c_size_t(len(jt)), _p(sj), _p(sw), C.c_uint32(src_offset), C.c_uint32(dst_offset), C.c_uint32(len(sj)), _p(mv)))
+        return mv
+
+    def vertices_download(self, first, count):
+        out = np.zeros(count, dtype=VERTEX_DTYPE)
+        assert 0 == (self.l.orc_vertices_download(self.h, C.c_size_t(first), C.c_size_t(count), _p(out)))
+        return out
+
     def bvh_build(self):
         self.l.orc_bvh_build(self.h)
 

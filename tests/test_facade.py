@@ -13,8 +13,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("textured", [False, True])
-def test_facade_equals_c_abi(tmp_path, textured):
+@pytest.mark.parametrize("textured,skinned", [(False, False), (True, False), (False, True)])
+def test_facade_equals_c_abi(tmp_path, textured, skinned):
     from vulkanexp_b200._lib import Context
     from vulkanexp_b200.host_logic import OrientationGenerator, ProbeScheduler
 
@@ -27,11 +27,27 @@ def test_facade_equals_c_abi(tmp_path, textured):
     scene_format.write_scene(path, s)
     res, rays, frames = (7, 5, 6), 48, 14
     out = os.path.join(tmp_path, "facade.bin")
-    r = subprocess.run([os.path.join(ROOT, "vulkanexp_b200", "vkx_facade_demo"), path, str(res[0]), str(res[1]), str(res[2]), str(rays), str(frames), out], capture_output=True, text=True)
+    skin_mesh = 2  # the ball mesh, as a skinned renderer on the root node (facade: Renderer::updateSkinnedVertexBuffer + updateSkinnedBLAS per frame)
+    extra = ["0", "host", str(skin_mesh)] if skinned else []
+    r = subprocess.run([os.path.join(ROOT, "vulkanexp_b200", "vkx_facade_demo"), path, str(res[0]), str(res[1]), str(res[2]), str(rays), str(frames), out] + extra, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert "facade ok" in r.stdout
     # the same sequence through the C ABI, flattening done by the Python harness
     flat = scene_format.flatten(scene_format.read_scene(path))
+    if skinned:
+        flat, src, dst, size = scene_format.add_skinned_instance(flat, skin_mesh)
+        sj = ((np.arange(size)[:, None] + np.arange(4)[None, :]) % 3).astype(np.uint16)
+        sw = np.tile(np.array([[0.4, 0.3, 0.2, 0.1]], dtype=np.float32), (size, 1))
+
+        def pose(frame):
+            js = np.zeros((3, 4, 4), dtype=np.float32)  # [joint][col][row]
+            for j in range(3):
+                sc = np.float32(1.0) + np.float32(j) / np.float32(8.0)
+                js[j, 0, 0] = js[j, 1, 1] = js[j, 2, 2] = sc
+                js[j, 3, 3] = 1.0
+                js[j, 3, 0] = np.float32(frame) * np.float32(j + 1) / np.float32(32.0)
+                js[j, 3, 1] = np.float32(frame) / np.float32(64.0)
+            return js.reshape(3, 16)
     g = Context(0); g.scene_upload(flat); g.bvh_build()
     grid = GridInfo.make(flat["bounds_min"], flat["bounds_max"], res, rays)
     g.probes_init(grid)
@@ -41,6 +57,8 @@ def test_facade_equals_c_abi(tmp_path, textured):
     target, updated, device_h = np.float32(0.98), 0, np.float32(0.0)
     h = np.float32(0.0)
     for f in range(frames):
+        if skinned:
+            g.skin_vertices(pose(f), sj, sw, src, dst); g.bvh_build()
         st = g.probes_download()[2]
         idx = sched.select(st)
         R = gen.next()

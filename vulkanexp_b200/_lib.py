@@ -8,7 +8,7 @@ import os
 
 import numpy as np
 
-from .pods import BvhInfo, Camera, GridInfo, HIT_DTYPE, Light, NODE_DTYPE, TRI_DTYPE, mip_chain_texels, texture_array
+from .pods import BvhInfo, Camera, GridInfo, HIT_DTYPE, Light, NODE_DTYPE, TRI_DTYPE, VERTEX_DTYPE, mip_chain_texels, texture_array
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # VKX_LIB_PATH: an alternative build of the same library (A/B timing of compile-time variants, tools/gpu_session.sh)
@@ -130,6 +130,21 @@ class Context:
     def instances_update(self, instances):
         inst = np.ascontiguousarray(instances)
         self._check(self.l.vkx_instances_update(self.h, _p(inst), C.c_size_t(len(inst))))
+
+    def skin_vertices(self, joint_transforms, skin_joints, skin_weights, src_offset, dst_offset, motion=False):
+        """vertexSkinning.comp: joint_transforms [J, 16] column-major, skin_joints uint16 [n, 4], skin_weights float32 [n, 4]."""
+        jt = np.ascontiguousarray(joint_transforms, dtype=np.float32).reshape(-1, 16)
+        sj = np.ascontiguousarray(skin_joints, dtype=np.uint16).reshape(-1, 4)
+        sw = np.ascontiguousarray(skin_weights, dtype=np.float32).reshape(-1, 4)
+        assert len(sj) == len(sw)
+        mv = np.zeros((len(sj), 4), dtype=np.float32) if motion else None
+        self._check(self.l.vkx_skin_vertices(self.h, _p(jt), C.c_size_t(len(jt)), _p(sj), _p(sw), C.c_uint32(src_offset), C.c_uint32(dst_offset), C.c_uint32(len(sj)), _p(mv)))
+        return mv
+
+    def vertices_download(self, first, count):
+        out = np.zeros(count, dtype=VERTEX_DTYPE)
+        self._check(self.l.vkx_vertices_download(self.h, C.c_size_t(first), C.c_size_t(count), _p(out)))
+        return out
 
     def bvh_build(self):
         self._check(self.l.vkx_bvh_build(self.h))

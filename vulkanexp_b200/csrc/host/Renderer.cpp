@@ -25,6 +25,40 @@ void Renderer::allocateMeshes() {
         Indices.insert(Indices.end(), m.indices.begin(), m.indices.end());
         vo += uint32_t(m.vertices.size()); io += uint32_t(m.indices.size());
     }
+    allocateSkinnedMeshes();
+}
+
+void Renderer::allocateSkinnedMeshes() { // updateSkinnedMeshOffsetTable (reference src/Renderer.cpp:144-164) + the bind-pose copy (:812-831)
+    for (SkinnedMeshRenderer& r : _scene->getSkinnedRenderers()) {
+        const Mesh& mesh = _scene->getMeshes().at(r.meshIndex);
+        if (!mesh.isValid()) throw Error(VKX_E_INVALID, "allocateSkinnedMeshes: skinned renderer uses an invalid mesh");
+        if (r.joints.size() != 4 * mesh.vertices.size() || r.weights.size() != 4 * mesh.vertices.size()) throw Error(VKX_E_INVALID, "allocateSkinnedMeshes: 4 joints and 4 weights per vertex expected");
+        r.indexIntoOffsetTable = uint32_t(OffsetTable.size());
+        r.vertexOffset = uint32_t(Vertices.size());
+        OffsetTable.push_back(OffsetEntry{r.materialIndex, r.vertexOffset, OffsetTable.at(mesh.indexIntoOffsetTable).indexOffset});
+        MeshIndexCounts.push_back(uint32_t(mesh.indices.size()));
+        Vertices.insert(Vertices.end(), mesh.vertices.begin(), mesh.vertices.end());
+    }
+}
+
+bool Renderer::updateSkinnedVertexBuffer(const std::vector<std::vector<mat4>>& jointPoses) {
+    const auto& skinned = _scene->getSkinnedRenderers();
+    if (skinned.empty()) return false;
+    if (jointPoses.size() != skinned.size()) throw Error(VKX_E_INVALID, "updateSkinnedVertexBuffer: one pose array per skinned renderer expected");
+    vkx_ctx* ctx = _device->ctx();
+    for (size_t i = 0; i < skinned.size(); ++i) {
+        const SkinnedMeshRenderer& r = skinned[i];
+        const Mesh& mesh = _scene->getMeshes().at(r.meshIndex);
+        check(ctx, vkx_skin_vertices(ctx, &jointPoses[i].at(0).m[0][0], jointPoses[i].size(), r.joints.data(), r.weights.data(), OffsetTable.at(mesh.indexIntoOffsetTable).vertexOffset,
+                                     r.vertexOffset, uint32_t(mesh.vertices.size()), nullptr));
+    }
+    return true;
+}
+
+bool Renderer::updateSkinnedBLAS() {
+    if (_scene->getSkinnedRenderers().empty()) return false; // reference src/Renderer.cpp:647-648
+    check(_device->ctx(), vkx_bvh_build(_device->ctx()));
+    return true;
 }
 
 void Renderer::createTLAS() {
@@ -43,6 +77,14 @@ void Renderer::createTLAS() {
         for (int row = 0; row < 3; ++row) for (int col = 0; col < 4; ++col) inst.transform[4 * row + col] = g.m[col][row];
         inst.meshEntry = mesh.indexIntoOffsetTable;
         inst.mask = VKX_INSTANCE_STATIC;
+        _instances.push_back(inst);
+    }
+    for (const SkinnedMeshRenderer& r : _scene->getSkinnedRenderers()) { // skinned instances follow the static ones (reference src/Renderer.cpp:553-575)
+        vkx_instance inst{};
+        const mat4& g = nodes.at(size_t(r.node)).globalTransform;
+        for (int row = 0; row < 3; ++row) for (int col = 0; col < 4; ++col) inst.transform[4 * row + col] = g.m[col][row];
+        inst.meshEntry = r.indexIntoOffsetTable;
+        inst.mask = VKX_INSTANCE_SKINNED;
         _instances.push_back(inst);
     }
 }

@@ -40,6 +40,13 @@ class Renderer {
     void updateAccelerationStructureInstances();
     void updateTLAS();
     void onHierarchicalChanges() { updateAccelerationStructureInstances(); updateTLAS(); }
+    // Skinned meshes (reference src/Renderer.cpp:133-164, 201-240, 644-669): allocateMeshes appends a bind-pose copy of the vertices of
+    // every Scene::getSkinnedRenderers() entry + its offset-table entry; createTLAS adds its instance (mask SKINNED);
+    // updateSkinnedVertexBuffer runs the skinning kernel with one pose array per skinned renderer (jointPoses[r][j], the reference
+    // computes them from the animated scene graph); updateSkinnedBLAS rebuilds the structure.
+    void allocateSkinnedMeshes();
+    bool updateSkinnedVertexBuffer(const std::vector<std::vector<mat4>>& jointPoses);
+    bool updateSkinnedBLAS();
     vkx_bvh_info getTLAS() const;         // the reference returns the TLAS handle; here: the wide-BVH description
 
     std::vector<vkx_vertex> Vertices;     // public arenas, as in the reference

@@ -43,6 +43,18 @@ struct TextureDesc {
     Image image;                                                  // decoded at load time (the reference decodes in uploadTextures)
 };
 
+// SkinnedMeshRendererComponent + the mesh's SkinVertexData (reference src/Scene.hpp:39-45, src/vulkan/Mesh.hpp:18-21), reduced to what
+// vertexSkinning.comp consumes. The animation system that produces joint poses is out of scope: poses are handed to
+// Renderer::updateSkinnedVertexBuffer.
+struct SkinnedMeshRenderer {
+    int node = 0;                     // entity whose global transform places the instance
+    uint32_t meshIndex = 0, materialIndex = 0;
+    std::vector<uint16_t> joints;     // 4 per vertex
+    std::vector<float> weights;       // 4 per vertex
+    uint32_t indexIntoOffsetTable = 0; // set by Renderer::allocateSkinnedMeshes
+    uint32_t vertexOffset = 0;         // first vertex of the skinned copy in Renderer::Vertices
+};
+
 class Scene {
   public:
     bool load(const std::string& path) { return loadScene(path); }
@@ -59,6 +71,8 @@ class Scene {
     const std::vector<MaterialDesc>& getMaterials() const { return _materials; }
     std::vector<TextureDesc>& getTextures() { return _textures; }
     const std::vector<TextureDesc>& getTextures() const { return _textures; }
+    std::vector<SkinnedMeshRenderer>& getSkinnedRenderers() { return _skinned; }
+    const std::vector<SkinnedMeshRenderer>& getSkinnedRenderers() const { return _skinned; }
     int getRoot() const { return _root; }
     void markDirty() { _dirty = true; }
 
@@ -67,6 +81,7 @@ class Scene {
     std::vector<NodeComponent> _nodes;
     std::vector<MaterialDesc> _materials;
     std::vector<TextureDesc> _textures;
+    std::vector<SkinnedMeshRenderer> _skinned;
     int _root = -1;
     bool _dirty = false;
     Bounds _bounds;

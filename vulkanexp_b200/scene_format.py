@@ -72,6 +72,30 @@ def read_pam(path):
     return np.frombuffer(data, dtype=np.uint8, count=w * h * 4, offset=end).reshape(h, w, 4).copy()
 
 
+def add_skinned_instance(flat, mesh_entry, transform_rows=None, material=None):
+    """A SkinnedMeshRendererComponent at the arena level (Renderer::allocateSkinnedMeshes / updateSkinnedMeshOffsetTable, reference
+    src/Renderer.cpp:133-164): a bind-pose copy of the mesh's vertices appended to the vertex arena, an offset-table entry {material,
+    that vertex offset, the mesh's index offset} and an instance with mask INSTANCE_SKINNED. Returns (flat', srcOffset, dstOffset, size)."""
+    from .pods import INSTANCE_SKINNED
+
+    out = dict(flat)
+    src = int(flat["offsets"][mesh_entry]["vertexOffset"])
+    size = int(flat["mesh_vertex_counts"][mesh_entry])
+    dst = len(flat["vertices"])
+    out["vertices"] = np.concatenate([flat["vertices"], flat["vertices"][src : src + size]])
+    entry = np.zeros(1, dtype=OFFSET_DTYPE)
+    entry[0] = (int(flat["offsets"][mesh_entry]["materialIndex"]) if material is None else material, dst, int(flat["offsets"][mesh_entry]["indexOffset"]))
+    out["offsets"] = np.concatenate([flat["offsets"], entry])
+    out["mesh_index_counts"] = np.concatenate([flat["mesh_index_counts"], flat["mesh_index_counts"][mesh_entry : mesh_entry + 1]])
+    out["mesh_vertex_counts"] = np.concatenate([flat["mesh_vertex_counts"], np.array([size], dtype=np.uint32)])
+    inst = np.zeros(1, dtype=INSTANCE_DTYPE)
+    inst[0]["transform"] = np.asarray(transform_rows if transform_rows is not None else [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], dtype=np.float32)
+    inst[0]["meshEntry"] = len(flat["offsets"])
+    inst[0]["mask"] = INSTANCE_SKINNED
+    out["instances"] = np.concatenate([flat["instances"], inst])
+    return out, src, dst, size
+
+
 def write_image(path, pixels):
     """.png through Pillow when the source name asks for it (tests of the PNG decoder), Netpbm P7 otherwise."""
     if path.lower().endswith(".png"):
@@ -322,6 +346,7 @@ def flatten(scene: SceneFile) -> dict:
         "indices": indices,
         "offsets": offsets,
         "mesh_index_counts": counts,
+        "mesh_vertex_counts": np.array([len(m.vertices) for m in scene.meshes], dtype=np.uint32),
         "materials": materials_array(scene.materials),
         "instances": instances,
         "bounds_min": np.asarray(bmin, dtype=np.float32),
