@@ -21,12 +21,16 @@ if [ -f vulkanexp_b200/libvkexp_b200_lazy.so ]; then # A/B of a compile-time var
   VKX_LIB_PATH=$PWD/vulkanexp_b200/libvkexp_b200_lazy.so VKX_PT_DEFER=0 VKX_PT_DEFER_SHADOW=12 timeout 120 python tools/profile_step.py 8 2> $out/sweep_lazy.err | tail -1 > $out/sweep_lazy.txt; log "sweep lazy-load build, defer 0/12: $(cat $out/sweep_lazy.txt | cut -c1-300)"
   VKX_PT_DEFER=0 VKX_PT_DEFER_SHADOW=12 timeout 120 python tools/profile_step.py 8 2> $out/sweep_eager.err | tail -1 > $out/sweep_eager.txt; log "sweep eager-load build, defer 0/12: $(cat $out/sweep_eager.txt | cut -c1-300)"
 fi
+for b in ${SWEEP_SHADE_BLOCKS:-}; do
+  VKX_SHADE_BLOCKS_PER_SM=$b timeout 120 python tools/profile_step.py 8 2> $out/sweep_shade_$b.err | tail -1 > $out/sweep_shade_$b.txt; log "sweep shade blocks/SM=$b: $(cat $out/sweep_shade_$b.txt | cut -c1-300)"
+done
 best=$(python tools/pick_defer.py $out)
 log "best: $best"
 timeout 300 python bench.py > $out/bench_default.json 2> $out/bench_default.err; log "bench default rc=$? $(cut -c1-160 $out/bench_default.json)"
 env $best timeout 300 python bench.py --no-cpu-baseline > $out/bench_best.json 2> $out/bench_best.err; log "bench best rc=$? $(cut -c1-160 $out/bench_best.json)"
 timeout 200 python tools/bench_shadow.py > $out/shadow_plain.json 2> $out/shadow_plain.err; log "shadow plain rc=$? $(cut -c1-400 $out/shadow_plain.json)"
 VKX_CFG3_ALPHA=1 timeout 200 python tools/bench_shadow.py > $out/shadow_alpha.json 2> $out/shadow_alpha.err; log "shadow alpha rc=$? $(cut -c1-400 $out/shadow_alpha.json)"
+if [ "${SKIP_NCU:-0}" = "1" ]; then log "done (ncu skipped)"; exit 0; fi
 # ncu: launch list of the bench command and full captures of the two traversal kernels, with the best variant
 env $best timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/launches_${TAG:-r01c}.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/bench_under_ncu.log 2>&1; log "ncu launch list rc=$?"
 for k in ${PROFILE_DDGI:-k_trace_primary k_trace_shadow}; do

@@ -2,6 +2,7 @@
 // (reference src/shaders/miss.rmiss, sky.glsl, closesthit.glsl NO_REFLECTION, irradiance.glsl::sampleProbes,
 // pbrMetallicRoughness.glsl). Separate translation unit so that its floating-point flags can differ from the traversal and
 // blend kernels; everything that feeds a later traversal (probe origin, hit position) uses explicit _rn intrinsics.
+#include <cstdlib>
 #include "common.cuh"
 #include "shade.cuh"
 #include "ddgi_common.cuh"
@@ -65,6 +66,20 @@ void launchShadeMiss(unsigned blocks, cudaStream_t st, const ShadeParams& sp, co
 }
 void launchShadeFront(unsigned blocks, cudaStream_t st, const DeviceScene& sc, const DeviceProbes& pr, const ShadeParams& sp, const float4* origins,
                       const float4* dirs, const vkx_hit* hits, const uint32_t* frontQueue, uint32_t* counters, float4* rays, float4* shadowQueue) {
+    // The kernel is a grid-stride loop over equal items: the grid is a whole number of waves, 3 x resident blocks per SM (16 blocks per
+    // SM at 6 resident were 2.67 waves, the last one two-thirds full; a single wave of long blocks would queue behind the sky kernel that
+    // runs concurrently on the second stream). VKX_SHADE_BLOCKS_PER_SM overrides (tuning).
+    static int perSm[2] = {0, 0}, smCount = 0;
+    const int v = sc.numTextures ? 1 : 0;
+    if (!perSm[v]) {
+        int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&smCount, cudaDevAttrMultiProcessorCount, dev);
+        int occ = 0;
+        if (v) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade_front<true>, 128, 0); else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade_front<false>, 128, 0);
+        const char* e = getenv("VKX_SHADE_BLOCKS_PER_SM");
+        perSm[v] = e && atoi(e) > 0 ? atoi(e) : 3 * (occ > 0 ? occ : 6);
+    }
+    const unsigned all = unsigned((sp.numRays + 127u) / 128u);
+    blocks = all < unsigned(smCount * perSm[v]) ? all : unsigned(smCount * perSm[v]);
     if (sc.numTextures) k_shade_front<true><<<blocks, 128, 0, st>>>(sc, pr, sp, origins, dirs, hits, frontQueue, counters, rays, shadowQueue);
     else k_shade_front<false><<<blocks, 128, 0, st>>>(sc, pr, sp, origins, dirs, hits, frontQueue, counters, rays, shadowQueue);
 }
