@@ -18,4 +18,20 @@ for d in (0, 1, 8, 12, 16):
     for name in best:
         if name in k and float(k[name]) < best[name][0] * 0.99:  # a later threshold must win by more than 1 %
             best[name] = (float(k[name]), d)
-print("VKX_PT_DEFER=%d VKX_PT_DEFER_SHADOW=%d" % (best["trace_primary"][1], best["trace_shadow"][1]))
+extra = ""
+shade = (1e9, None)  # gpurun_out/sweep_shade_<blocks per SM>.txt: grid size of k_shade_front
+import glob
+for p in glob.glob(os.path.join(out, "sweep_shade_*.txt")):
+    m = re.findall(r"\{[^{}]*\}", open(p).read())
+    if not m:
+        continue
+    try:
+        k = ast.literal_eval(m[-1])
+    except Exception:
+        continue
+    b = int(re.search(r"sweep_shade_(\d+)\.txt", p).group(1))
+    if "shade" in k and float(k["shade"]) < shade[0]:
+        shade = (float(k["shade"]), b)
+if shade[1] is not None:
+    extra = " VKX_SHADE_BLOCKS_PER_SM=%d" % shade[1]
+print("VKX_PT_DEFER=%d VKX_PT_DEFER_SHADOW=%d%s" % (best["trace_primary"][1], best["trace_shadow"][1], extra))

@@ -66,9 +66,10 @@ void launchShadeMiss(unsigned blocks, cudaStream_t st, const ShadeParams& sp, co
 }
 void launchShadeFront(unsigned blocks, cudaStream_t st, const DeviceScene& sc, const DeviceProbes& pr, const ShadeParams& sp, const float4* origins,
                       const float4* dirs, const vkx_hit* hits, const uint32_t* frontQueue, uint32_t* counters, float4* rays, float4* shadowQueue) {
-    // The kernel is a grid-stride loop over equal items: the grid is a whole number of waves, 3 x resident blocks per SM (16 blocks per
-    // SM at 6 resident were 2.67 waves, the last one two-thirds full; a single wave of long blocks would queue behind the sky kernel that
-    // runs concurrently on the second stream). VKX_SHADE_BLOCKS_PER_SM overrides (tuning).
+    // Grid-stride loop over the sorted queue. Items are not equal (a hit near the volume's border or next to disabled probes skips
+    // probes), and the sky kernel shares the SMs, so many short blocks beat few long ones: measured on B200, cfg2, sort + shading
+    // (profiles/r01d_shade_grid_sweep.txt): 6 blocks per SM (one wave) 0.907 ms, 12: 0.872, 16: 0.854, 24: 0.849, 36: 0.841.
+    // VKX_SHADE_BLOCKS_PER_SM overrides (tuning).
     static int perSm[2] = {0, 0}, smCount = 0;
     const int v = sc.numTextures ? 1 : 0;
     if (!perSm[v]) {
@@ -76,7 +77,7 @@ void launchShadeFront(unsigned blocks, cudaStream_t st, const DeviceScene& sc, c
         int occ = 0;
         if (v) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade_front<true>, 128, 0); else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade_front<false>, 128, 0);
         const char* e = getenv("VKX_SHADE_BLOCKS_PER_SM");
-        perSm[v] = e && atoi(e) > 0 ? atoi(e) : 3 * (occ > 0 ? occ : 6);
+        perSm[v] = e && atoi(e) > 0 ? atoi(e) : 6 * (occ > 0 ? occ : 6);
     }
     const unsigned all = unsigned((sp.numRays + 127u) / 128u);
     blocks = all < unsigned(smCount * perSm[v]) ? all : unsigned(smCount * perSm[v]);
