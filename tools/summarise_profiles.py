@@ -47,12 +47,14 @@ if os.path.exists(src):
 # SASS listings of the hot kernels (built objects, no GPU needed)
 objs = {"k_trace_primary": "ddgi.o", "k_trace_shadow": "ddgi.o", "k_blend": "ddgi.o", "k_shade_front": "ddgi_shade.o", "k_shade_miss": "ddgi_shade.o",
         "k_filter_x": "shadow.o", "k_filter_y": "shadow.o", "k_direct_light": "shadow.o", "k_final_gather": "gather.o", "k_reflect_shade": "reflection.o"}
+# template instantiation that ships as the default (name suffix after the kernel name in the mangled symbol)
+inst = {"k_trace_primary": "ILi0E", "k_trace_shadow": "ILi12E", "k_shade_front": "ILb0E", "k_direct_light": "ILb0E", "k_reflect_shade": "ILb0E"}
 for kernel, obj in objs.items():
     txt = subprocess.run(["cuobjdump", "-sass", os.path.join(ROOT, "vulkanexp_b200", "csrc", "build", obj)], capture_output=True, text=True).stdout
     blocks = re.split(r"\n\s*Function : ", txt)
     for b in blocks[1:]:
         name = b.split("\n", 1)[0]
-        if re.search(r"\d+%s(E|I)" % kernel, name):
+        if re.search(r"\d+%s%s" % (kernel, inst.get(kernel, "(E|I)")), name):
             body = [re.sub(r"\s*/\* 0x[0-9a-f]+ \*/\s*$", "", l).rstrip() for l in b.split("\n") if re.match(r"\s+/\*[0-9a-f]{4,}\*/", l)]
             with open(os.path.join(ROOT, "profiles", "%s_sass_%s.txt" % (tag, kernel)), "w") as f:
                 f.write("// cuobjdump -sass %s, function %s (%d instructions)\n" % (obj, name, len(body)) + "\n".join(body) + "\n")

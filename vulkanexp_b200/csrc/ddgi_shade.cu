@@ -52,7 +52,10 @@ __global__ void __launch_bounds__(128, 6) k_shade_front(DeviceScene sc, DevicePr
             shadeFrontHit<true>(sc, pr, gc, lightDir, lightColor, direction, position, h, color, lit, origin, raydx, raydy);
         } else shadeFrontHit<false>(sc, pr, gc, lightDir, lightColor, direction, position, h, color, lit);
         rays[ri] = make_float4(color.x, color.y, color.z, h.t); // value if the sun is occluded; k_trace_shadow writes `lit` if the shadow ray escapes
-        const uint32_t qi = warpAppend(counters);
+        // Every front hit spawns exactly one shadow ray, so its slot is the item's own index: no atomic append, and the shadow queue
+        // keeps the cell-sorted order of the front queue exactly (coherent origins for k_trace_shadow).
+        const uint32_t qi = i;
+        if (i == 0u) counters[0] = n;
         queue[2 * size_t(qi)] = make_float4(position.x, position.y, position.z, __uint_as_float(ri));
         queue[2 * size_t(qi) + 1] = make_float4(lit.x, lit.y, lit.z, 0.0f);
     }
@@ -66,10 +69,12 @@ void launchShadeMiss(unsigned blocks, cudaStream_t st, const ShadeParams& sp, co
 }
 void launchShadeFront(unsigned blocks, cudaStream_t st, const DeviceScene& sc, const DeviceProbes& pr, const ShadeParams& sp, const float4* origins,
                       const float4* dirs, const vkx_hit* hits, const uint32_t* frontQueue, uint32_t* counters, float4* rays, float4* shadowQueue) {
-    // Grid-stride loop over the sorted queue. Items are not equal (a hit near the volume's border or next to disabled probes skips
-    // probes), and the sky kernel shares the SMs, so many short blocks beat few long ones: measured on B200, cfg2, sort + shading
-    // (profiles/r01d_shade_grid_sweep.txt): 6 blocks per SM (one wave) 0.907 ms, 12: 0.872, 16: 0.854, 24: 0.849, 36: 0.841.
-    // VKX_SHADE_BLOCKS_PER_SM overrides (tuning).
+    // One queue item per thread (the loop only matters if the grid is capped). Items are not equal (a hit near the volume's border or
+    // next to disabled probes skips probes) and the sky kernel shares the SMs, so the hardware block scheduler balances short blocks
+    // better than a grid-stride loop over few long ones; the shadow queue is also appended closer to the sorted order, which makes the
+    // shadow rays more coherent. Measured on B200, cfg2 (profiles/r01d_shade_grid_sweep.txt), sort + shading / k_trace_shadow:
+    // 6 blocks per SM (one wave) 0.907 ms, 16 (the old grid) 0.854 / 0.375 ms, 36: 0.841, 64: 0.832 / 0.360, 128: 0.825 / 0.357,
+    // uncapped: 0.823 / 0.351 ms. VKX_SHADE_BLOCKS_PER_SM caps the grid (tuning).
     static int perSm[2] = {0, 0}, smCount = 0;
     const int v = sc.numTextures ? 1 : 0;
     if (!perSm[v]) {
@@ -77,10 +82,12 @@ void launchShadeFront(unsigned blocks, cudaStream_t st, const DeviceScene& sc, c
         int occ = 0;
         if (v) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade_front<true>, 128, 0); else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade_front<false>, 128, 0);
         const char* e = getenv("VKX_SHADE_BLOCKS_PER_SM");
-        perSm[v] = e && atoi(e) > 0 ? atoi(e) : 6 * (occ > 0 ? occ : 6);
+        (void)occ;
+        perSm[v] = e && atoi(e) > 0 ? atoi(e) : (1 << 20); // default: no cap
     }
     const unsigned all = unsigned((sp.numRays + 127u) / 128u);
-    blocks = all < unsigned(smCount * perSm[v]) ? all : unsigned(smCount * perSm[v]);
+    const unsigned long long cap = (unsigned long long)(smCount) * (unsigned long long)(perSm[v]);
+    blocks = (unsigned long long)(all) < cap ? all : unsigned(cap);
     if (sc.numTextures) k_shade_front<true><<<blocks, 128, 0, st>>>(sc, pr, sp, origins, dirs, hits, frontQueue, counters, rays, shadowQueue);
     else k_shade_front<false><<<blocks, 128, 0, st>>>(sc, pr, sp, origins, dirs, hits, frontQueue, counters, rays, shadowQueue);
 }
