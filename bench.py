@@ -114,6 +114,27 @@ def cpu_baseline(flat, grid, light, sample_probes, threads=0):
     }, c, rays
 
 
+_RESULT_OUT = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout. Libraries may write to file descriptor 1 (NCCL prints its version line there when
+    NCCL_DEBUG is set in the environment), so fd 1 is pointed at stderr for the rest of the run and the result line goes to a
+    duplicate of the original stdout."""
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+    return _RESULT_OUT
+
+
+def _emit(line):
+    out = _claim_stdout()
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -147,10 +168,11 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "probe rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "full_volume_update_ms_extrapolated": 1e3 * total / args.steps * grid.probe_count / sample,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -326,7 +348,7 @@ def main():
                                 "nodes_per_primary_ray": nodes_p, "tris_per_primary_ray": tris_p, "nodes_per_shadow_ray": nodes_s, "tris_per_shadow_ray": tris_s,
                                 "front_hit_fraction": front,
                                 "note": "every kernel of this path is instruction-issue bound at this scene size (DRAM < 6 % of peak in ncu); the HBM fraction is reported as required, issue-slot utilisation is in profiles/"}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
