@@ -331,6 +331,20 @@ int vkx_shadow_timings(vkx_ctx* ctx, float ms[4]);
 /* The per-frame random orientation push constant: glm::sphericalRand(1) + genBasis -> mat4(transpose(mat3(X, Y, Z)))
  * (src/IrradianceProbes.cpp:347-355, 455-460). *rngState is the MSVC rand() state; the reference never seeds it: start at 1. */
 void vkx_host_next_orientation(uint32_t* rngState, float orientation[16]);
+/* Host-side scene code without a context or GPU: Scene::loadScene + Scene::update (src/Scene.cpp:818-961), Renderer::allocateMeshes
+ * (arenas + offset table, src/Renderer.cpp:57-131) and Renderer::createTLAS's instance list (src/Renderer.cpp:512-575), i.e. exactly
+ * the arrays vkx_scene_textures / vkx_scene_upload take. counts = {vertices, indices, meshes, materials, instances, textures};
+ * vkx_host_scene_copy fills caller arrays of those sizes (any pointer may be NULL) and the scene bounds (IrradianceProbes::init's
+ * extent, src/VulkanLifecycle.cpp:132-133); vkx_host_scene_texture returns texture i with pixels pointing into the scene object
+ * (valid until vkx_host_scene_free); vkx_host_scene_save is Scene::save (src/Scene.cpp:710-816). */
+typedef struct vkx_host_scene vkx_host_scene;
+int vkx_host_scene_load(const char* path, vkx_host_scene** out);
+void vkx_host_scene_free(vkx_host_scene* scene);
+int vkx_host_scene_counts(const vkx_host_scene* scene, size_t counts[6]);
+int vkx_host_scene_copy(const vkx_host_scene* scene, vkx_vertex* vertices, uint32_t* indices, vkx_offset_entry* offsets,
+                        uint32_t* meshIndexCounts, vkx_material* materials, vkx_instance* instances, float boundsMinMax[6]);
+int vkx_host_scene_texture(const vkx_host_scene* scene, size_t index, vkx_texture* desc);
+int vkx_host_scene_save(const vkx_host_scene* scene, const char* path);
 /* selectProbesToUpdate (src/IrradianceProbes.cpp:396-424). loopIndex / lastUpdateOffset are the function's statics. */
 uint32_t vkx_host_select_probes(uint32_t* loopIndex, uint32_t* lastUpdateOffset, const uint32_t* state, uint32_t probeCount,
                                 uint32_t probesPerUpdate, uint32_t* out);

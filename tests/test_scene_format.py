@@ -3,6 +3,7 @@ import os
 import struct
 
 import numpy as np
+import pytest
 
 from vulkanexp_b200 import scene_format, synth
 
@@ -47,3 +48,46 @@ def test_generators_are_deterministic_and_sized():
     assert scene_format.flatten(a)["vertices"].tobytes() == scene_format.flatten(b)["vertices"].tobytes()
     assert 4000 < synth.count_triangles(a) < 6000
     assert abs(synth.count_triangles(synth.make_cfg2()) - 262_144) < 0.03 * 262_144
+
+
+@pytest.mark.parametrize("maker", ["court", "tcourt", "cfg1"])
+def test_facade_loader_equals_python_harness(tmp_path, maker):
+    """The product's own .scene loader + flattening (csrc/host: Scene::loadScene, Scene::update, Renderer::allocateMeshes / createTLAS,
+    the image decoders), reached through vkx_host_scene_* without a GPU, must produce the arrays the Python harness produces."""
+    from vulkanexp_b200._lib import host_scene_load, host_scene_resave
+
+    s = {"court": synth.make_open_court, "tcourt": synth.make_textured_court, "cfg1": synth.make_cfg1}[maker]()
+    if maker == "tcourt":
+        pytest.importorskip("PIL")
+        s.textures[1]["source"] = "tex_normal.png"  # one image through the PNG decoder
+    path = str(tmp_path / "a.scene")
+    scene_format.write_scene(path, s)
+    want = scene_format.flatten(scene_format.read_scene(path))
+    got = host_scene_load(path)
+    for key in ("vertices", "indices", "offsets", "mesh_index_counts", "materials", "instances"):
+        assert got[key].tobytes() == want[key].tobytes(), key
+    assert np.array_equal(got["bounds_min"], want["bounds_min"]) and np.array_equal(got["bounds_max"], want["bounds_max"])
+    assert ("textures" in got) == ("textures" in want)
+    for a, b in zip(got.get("textures", []), want.get("textures", [])):
+        assert np.array_equal(a["pixels"], b["pixels"])
+        assert all(int(a[k]) == int(b[k]) for k in ("srgb", "magFilter", "minFilter", "wrapS", "wrapT"))
+    # Scene::save -> the Python reader: same scene again (texture files are referenced, not rewritten)
+    out = str(tmp_path / "b.scene")
+    host_scene_resave(path, out)
+    again = scene_format.flatten(scene_format.read_scene(out))
+    for key in ("vertices", "indices", "offsets", "mesh_index_counts", "materials", "instances"):
+        assert again[key].tobytes() == want[key].tobytes(), "after Scene::save: " + key
+    assert [t["minFilter"] for t in again.get("textures", [])] == [t["minFilter"] for t in want.get("textures", [])]
+
+
+def test_facade_loader_reports_missing_files(tmp_path):
+    from vulkanexp_b200._lib import VkxError, host_scene_load
+
+    with pytest.raises(VkxError):
+        host_scene_load(str(tmp_path / "nope.scene"))
+    s = synth.make_textured_court()
+    path = str(tmp_path / "a.scene")
+    scene_format.write_scene(path, s)
+    os.remove(str(tmp_path / "tex_grate.pam"))  # an unreadable texture becomes the blank image (reference src/Scene.cpp:699), with a warning
+    got = host_scene_load(path)
+    assert got["textures"][4]["pixels"].shape == (1, 1, 4) and (got["textures"][4]["pixels"] == 255).all()

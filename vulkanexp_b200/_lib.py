@@ -41,6 +41,13 @@ def load():
         lib.vkx_stream.argtypes = [C.c_void_p]
         lib.vkx_destroy.restype = None
         lib.vkx_destroy.argtypes = [C.c_void_p]
+        lib.vkx_host_scene_free.restype = None
+        lib.vkx_host_scene_free.argtypes = [C.c_void_p]
+        lib.vkx_host_scene_counts.argtypes = [C.c_void_p, C.c_void_p]
+        lib.vkx_host_scene_copy.argtypes = [C.c_void_p] * 8
+        lib.vkx_host_scene_texture.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        lib.vkx_host_scene_save.argtypes = [C.c_void_p, C.c_char_p]
+        lib.vkx_host_scene_load.argtypes = [C.c_char_p, C.c_void_p]
         _LIB = lib
     return _LIB
 
@@ -61,6 +68,55 @@ def image_decode(path):
     if rc != 0:
         raise VkxError(rc, "vkx_image_decode(%s) failed" % path)
     return out
+
+
+def host_scene_load(path):
+    """The product's own .scene loader + flattening (vkx_host_scene_*; host only): returns the dict Context.scene_upload takes."""
+    from .pods import INSTANCE_DTYPE, MATERIAL_DTYPE, OFFSET_DTYPE, Texture
+
+    l = load()
+    h = C.c_void_p()
+    rc = l.vkx_host_scene_load(os.fsencode(path), C.byref(h))
+    if rc != 0:
+        raise VkxError(rc, "vkx_host_scene_load(%s) failed" % path)
+    try:
+        counts = (C.c_size_t * 6)()
+        l.vkx_host_scene_counts(h, counts)
+        nv, ni, nm, nmat, ninst, ntex = (int(c) for c in counts)
+        flat = {
+            "vertices": np.zeros(nv, dtype=VERTEX_DTYPE), "indices": np.zeros(ni, dtype=np.uint32), "offsets": np.zeros(nm, dtype=OFFSET_DTYPE),
+            "mesh_index_counts": np.zeros(nm, dtype=np.uint32), "materials": np.zeros(nmat, dtype=MATERIAL_DTYPE), "instances": np.zeros(ninst, dtype=INSTANCE_DTYPE),
+        }
+        bounds = np.zeros(6, dtype=np.float32)
+        rc = l.vkx_host_scene_copy(h, _p(flat["vertices"]), _p(flat["indices"]), _p(flat["offsets"]), _p(flat["mesh_index_counts"]), _p(flat["materials"]), _p(flat["instances"]), _p(bounds))
+        if rc != 0:
+            raise VkxError(rc, "vkx_host_scene_copy failed")
+        flat["bounds_min"], flat["bounds_max"] = bounds[:3].copy(), bounds[3:].copy()
+        if ntex:
+            flat["textures"] = []
+            for i in range(ntex):
+                d = Texture()
+                l.vkx_host_scene_texture(h, C.c_size_t(i), C.byref(d))
+                px = np.ctypeslib.as_array(C.cast(d.pixels, C.POINTER(C.c_uint8)), shape=(d.height, d.width, 4)).copy()
+                flat["textures"].append({"pixels": px, "srgb": d.srgb, "magFilter": d.magFilter, "minFilter": d.minFilter, "wrapS": d.wrapS, "wrapT": d.wrapT})
+        return flat
+    finally:
+        l.vkx_host_scene_free(h)
+
+
+def host_scene_resave(path_in, path_out):
+    """Scene::loadScene followed by Scene::save through the facade (host only)."""
+    l = load()
+    h = C.c_void_p()
+    rc = l.vkx_host_scene_load(os.fsencode(path_in), C.byref(h))
+    if rc != 0:
+        raise VkxError(rc, "vkx_host_scene_load(%s) failed" % path_in)
+    try:
+        rc = l.vkx_host_scene_save(h, os.fsencode(path_out))
+        if rc != 0:
+            raise VkxError(rc, "vkx_host_scene_save(%s) failed" % path_out)
+    finally:
+        l.vkx_host_scene_free(h)
 
 
 class Context:
