@@ -8,7 +8,8 @@ from vulkanexp_b200.host_logic import OrientationGenerator
 from vulkanexp_b200.pods import GridInfo, Light
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 4
-flat = scene_format.flatten(synth.make_cfg2())
+TEXTURED = os.environ.get("VKX_CFG2_TEXTURED", "0") == "1"  # the same atrium with the procedural texture set on every material
+flat = scene_format.flatten(synth.make_cfg2(textured=TEXTURED))
 g = Context(0); g.scene_upload(flat); g.bvh_build()
 grid = GridInfo.make(flat["bounds_min"], flat["bounds_max"], (32, 16, 32), 256)
 g.probes_init(grid)
@@ -23,4 +24,4 @@ for f in range(steps):
     print(f, t, k)
     hist.append({**k, "full": t["full"]})
 if len(hist) > 2:  # last line: medians over the steps after the first two (tools/pick_defer.py reads it)
-    print("median", {name: float(np.median([h[name] for h in hist[2:]])) for name in hist[0]})
+    print("median", "textured" if TEXTURED else "untextured", {name: float(np.median([h[name] for h in hist[2:]])) for name in hist[0]})

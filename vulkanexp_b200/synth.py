@@ -409,8 +409,11 @@ def make_textured_court(seed=SEED_BASE + 9):
     return s
 
 
-def make_cfg2(target_tris=262_144):
-    """"sponza-scale" atrium: two storeys of fluted columns and arches around an open courtyard, banners, ~262 k triangles."""
+def make_cfg2(target_tris=262_144, textured=False):
+    """"sponza-scale" atrium: two storeys of fluted columns and arches around an open courtyard, banners, ~262 k triangles.
+    textured=True (hard part 5: "procedurally textured for cfg 2-4 with the defined sampler"): box-projected texture
+    coordinates and the procedural texture set on every material (albedo + normal map on floor / walls / columns, metallic-roughness
+    and emissive maps on the bronze, albedo on the banners); same geometry, so hit records are those of the untextured scene."""
     rng = np.random.default_rng(SEED_BASE + 2)
     mats = [
         material_json("floor", (0.62, 0.6, 0.55), 0.0, 0.8),
@@ -454,6 +457,21 @@ def make_cfg2(target_tris=262_144):
     for k in range(4):
         _add(s, "Urn%d" % k, M["Urn"], trs((-12.0 + 8.0 * k, 0.6, float(rng.uniform(-1.5, 1.5)))))
     # top up to the target with a finely tessellated lion-head stand-in (spheres) at the ends
+    if textured:
+        s.images, s.textures = procedural_textures()
+        s.images, s.textures = s.images[:4], s.textures[:4]  # no cut-outs here: the probe pipeline has no any-hit shader anyway
+        for name in ("floor", "wall", "column"):
+            m = next(m for m in s.materials if m["name"] == name)
+            m["pbrMetallicRoughness"]["baseColorTexture"] = {"index": 0}
+            m["normalTexture"] = {"index": 1}
+        for name in ("banner_red", "banner_green"):
+            next(m for m in s.materials if m["name"] == name)["pbrMetallicRoughness"]["baseColorTexture"] = {"index": 0}
+        bronze = next(m for m in s.materials if m["name"] == "bronze")
+        bronze["pbrMetallicRoughness"]["metallicRoughnessTexture"] = {"index": 2}
+        bronze["emissiveTexture"] = {"index": 3}
+        bronze["emissiveFactor"] = [0.3, 0.25, 0.2]
+        for m in s.meshes:
+            planar_uvs(m)
     return s
 
 
