@@ -36,7 +36,7 @@ struct DeviceScene {
     const float4* tris;         // 3 x float4 per triangle
     const uint32_t* texels;     // texel arena of every texture's mip chain (texture.cu)
     const DeviceTexture* textures;
-    const float* srgbLut;       // 256 entries: sRGB code -> linear
+    const float* srgbLut;       // 512 entries: sRGB code -> linear, then code / 255 (texture.cuh::texDecode)
     uint32_t numTextures;
 };
 

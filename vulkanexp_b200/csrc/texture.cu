@@ -97,8 +97,8 @@ extern "C" int vkx_scene_textures(vkx_ctx* ctx, const vkx_texture* textures, siz
     }
     freeTextures(ctx);
     if (!ctx->dSrgbLut) { // T4: exact transfer function per code, evaluated in double precision
-        float lut[256], thr[256];
-        for (int i = 0; i < 256; ++i) { lut[i] = float(srgbDecode(double(i) / 255.0)); thr[i] = i == 0 ? 0.0f : float(srgbDecode((double(i) - 0.5) / 255.0)); }
+        float lut[512], thr[256]; // lut: sRGB -> linear, then code / 255 (texDecode)
+        for (int i = 0; i < 256; ++i) { lut[i] = float(srgbDecode(double(i) / 255.0)); lut[256 + i] = float(i) / 255.0f; thr[i] = i == 0 ? 0.0f : float(srgbDecode((double(i) - 0.5) / 255.0)); }
         CUDA_TRY(ctx, cudaMalloc(&ctx->dSrgbLut, sizeof(lut))); CUDA_TRY(ctx, cudaMalloc(&ctx->dSrgbThreshold, sizeof(thr)));
         CUDA_TRY(ctx, cudaMemcpy(ctx->dSrgbLut, lut, sizeof(lut), cudaMemcpyHostToDevice)); CUDA_TRY(ctx, cudaMemcpy(ctx->dSrgbThreshold, thr, sizeof(thr), cudaMemcpyHostToDevice));
     }
