@@ -34,7 +34,8 @@ struct DeviceScene {
     const float* worldToObject; // 9 floats per instance, W[row][col] row-major = inverse of the 3x3 part
     const uint4* nodes;         // 5 x uint4 per node
     const float4* tris;         // 3 x float4 per triangle
-    const uint32_t* texels;     // texel arena of every texture's mip chain (texture.cu)
+    const uint32_t* texels;     // texel arena of every texture's mip chain, RGBA8 words (texture.cu)
+    const float4* texelsDecoded; // the same texels decoded to linear fp32 (one 128-bit load per tap instead of a word + 4 table look-ups)
     const DeviceTexture* textures;
     const float* srgbLut;       // 512 entries: sRGB code -> linear, then code / 255 (texture.cuh::texDecode)
     uint32_t numTextures;
@@ -69,7 +70,7 @@ struct vkx_ctx {
     size_t numVertices = 0, numIndices = 0, numMeshes = 0, numMaterials = 0, numInstances = 0, numFlatTris = 0;
     std::vector<uint32_t> hInstTriBase;
     // textures (texture.cu): arena + descriptors + sRGB tables; hTextures mirrors the descriptors for validation / read-back
-    uint32_t* dTexels = nullptr; DeviceTexture* dTextures = nullptr; float* dSrgbLut = nullptr; float* dSrgbThreshold = nullptr;
+    uint32_t* dTexels = nullptr; float4* dTexelsDecoded = nullptr; DeviceTexture* dTextures = nullptr; float* dSrgbLut = nullptr; float* dSrgbThreshold = nullptr;
     std::vector<DeviceTexture> hTextures; size_t numTexels = 0; uint32_t texturesUsed = 0; // texturesUsed: highest texture index of the uploaded materials + 1
 
     // bvh

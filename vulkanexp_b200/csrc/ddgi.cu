@@ -427,7 +427,7 @@ DeviceScene deviceScene(const vkx_ctx* ctx) {
     DeviceScene s;
     s.vertices = ctx->dVertices; s.indices = ctx->dIndices; s.offsets = ctx->dOffsets; s.materials = ctx->dMaterials; s.instances = ctx->dInstances;
     s.worldToObject = ctx->dWorldToObject; s.nodes = ctx->dNodes; s.tris = ctx->dTris;
-    s.texels = ctx->dTexels; s.textures = ctx->dTextures; s.srgbLut = ctx->dSrgbLut; s.numTextures = uint32_t(ctx->hTextures.size());
+    s.texels = ctx->dTexels; s.texelsDecoded = ctx->dTexelsDecoded; s.textures = ctx->dTextures; s.srgbLut = ctx->dSrgbLut; s.numTextures = uint32_t(ctx->hTextures.size());
     return s;
 }
 

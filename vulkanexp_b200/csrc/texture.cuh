@@ -39,7 +39,7 @@ __device__ __forceinline__ float4 texDecode(const float* __restrict__ lut, uint3
 __device__ __forceinline__ float4 texFetch(const DeviceScene& sc, const DeviceTexture& t, uint32_t level, int x, int y) {
     const int w = int(max(1u, t.width >> level)), h = int(max(1u, t.height >> level));
     const int xx = texWrap(x, w, (t.flags >> VKX_TEX_WRAP_S_SHIFT) & 3u), yy = texWrap(y, h, (t.flags >> VKX_TEX_WRAP_T_SHIFT) & 3u);
-    return texDecode(sc.srgbLut, t.flags, __ldg(sc.texels + size_t(t.levelOffset[level]) + size_t(yy) * size_t(w) + size_t(xx)));
+    return __ldg(sc.texelsDecoded + size_t(t.levelOffset[level]) + size_t(yy) * size_t(w) + size_t(xx)); // = texDecode(lut, flags, texels[...]), decoded at upload
 }
 
 __device__ __forceinline__ float4 texSampleLevel(const DeviceScene& sc, const DeviceTexture& t, uint32_t level, float s, float tt, bool linear) {
