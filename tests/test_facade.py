@@ -13,6 +13,14 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _demo():
+    """Path of the facade demo executable (a build artefact, not tracked): built on demand if build() has not run in this tree."""
+    path = os.path.join(ROOT, "vulkanexp_b200", "vkx_facade_demo")
+    if not os.path.exists(path):
+        subprocess.check_call(["make", "-s", "-j8", "-C", os.path.join(ROOT, "vulkanexp_b200", "csrc")])
+    return path
+
+
 @pytest.mark.parametrize("textured,skinned", [(False, False), (True, False), (False, True)])
 def test_facade_equals_c_abi(tmp_path, textured, skinned):
     from vulkanexp_b200._lib import Context
@@ -29,7 +37,7 @@ def test_facade_equals_c_abi(tmp_path, textured, skinned):
     out = os.path.join(tmp_path, "facade.bin")
     skin_mesh = 2  # the ball mesh, as a skinned renderer on the root node (facade: Renderer::updateSkinnedVertexBuffer + updateSkinnedBLAS per frame)
     extra = ["0", "host", str(skin_mesh)] if skinned else []
-    r = subprocess.run([os.path.join(ROOT, "vulkanexp_b200", "vkx_facade_demo"), path, str(res[0]), str(res[1]), str(res[2]), str(rays), str(frames), out] + extra, capture_output=True, text=True)
+    r = subprocess.run([_demo(), path, str(res[0]), str(res[1]), str(res[2]), str(rays), str(frames), out] + extra, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert "facade ok" in r.stdout
     # the same sequence through the C ABI, flattening done by the Python harness
@@ -90,7 +98,7 @@ def test_facade_device_scheduler_equals_host_scheduler(tmp_path):
     outs = []
     for mode in ("host", "device"):
         out = os.path.join(tmp_path, mode + ".bin")
-        r = subprocess.run([os.path.join(ROOT, "vulkanexp_b200", "vkx_facade_demo"), path, "7", "5", "6", "48", "16", out, "60", mode], capture_output=True, text=True)
+        r = subprocess.run([_demo(), path, "7", "5", "6", "48", "16", out, "60", mode], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
         outs.append(np.fromfile(out, dtype=np.uint32))
     assert outs[0].size and np.array_equal(outs[0], outs[1])
