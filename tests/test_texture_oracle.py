@@ -303,3 +303,22 @@ def test_image_decoder_of_the_library(tmp_path):
         f.write(b"\xff\xd8\xff\xe0" + bytes(64))
     with pytest.raises(VkxError):
         image_decode(str(tmp_path / "c.jpg"))
+
+
+def test_image_decoder_matches_the_reference_stb_image():
+    """tests/golden/stb_pin.json holds the SHA-256 of stbi_load(path, .., 4) — the call of src/STBImage.hpp:25, from the reference's
+    vendored ext/stb_image.h — for the files under tests/golden/img (tools/gen_golden.py): the library's decoders must return the
+    same bytes."""
+    import hashlib
+    import json
+    import os
+
+    from vulkanexp_b200._lib import image_decode
+
+    gold_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    gold = json.load(open(os.path.join(gold_dir, "stb_pin.json")))
+    assert len(gold) >= 8
+    for name, want in gold.items():
+        px = image_decode(os.path.join(gold_dir, "img", name))
+        assert px.shape == (want["height"], want["width"], 4), name
+        assert hashlib.sha256(px.tobytes()).hexdigest() == want["sha256"], name

@@ -1,6 +1,7 @@
 #include "Image.hpp"
 #include "../../../include/vkx.h"
 #include <zlib.h>
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -32,20 +33,29 @@ bool decodePng(const std::vector<uint8_t>& f, Image& img, std::string* error) {
         else if (!std::memcmp(type, "IEND", 4)) break;
         off += 12 + size_t(len);
     }
-    if (w == 0 || h == 0 || depth != 8 || interlace != 0) return fail(error, "unsupported PNG (needs 8 bits per channel, non-interlaced)");
+    if (w == 0 || h == 0 || interlace != 0) return fail(error, "unsupported PNG (interlaced or empty)");
     int channels;
     switch (colour) { case 0: channels = 1; break; case 2: channels = 3; break; case 3: channels = 1; break; case 4: channels = 2; break; case 6: channels = 4; break; default: return fail(error, "unsupported PNG colour type"); }
-    const size_t stride = size_t(w) * channels;
+    const bool depthOk = depth == 8 || depth == 16 || ((colour == 0 || colour == 3) && (depth == 1 || depth == 2 || depth == 4));
+    if (!depthOk || (colour == 3 && depth == 16)) return fail(error, "unsupported PNG bit depth");
+    const size_t stride = (size_t(w) * size_t(channels) * size_t(depth) + 7) / 8; // bytes per scanline
+    const size_t bpp = std::max<size_t>(1, size_t(channels) * size_t(depth) / 8); // filter distance
     std::vector<uint8_t> raw((stride + 1) * h);
     uLongf rawLen = uLongf(raw.size());
     if (uncompress(raw.data(), &rawLen, idat.data(), uLong(idat.size())) != Z_OK || rawLen != raw.size()) return fail(error, "PNG inflate failed");
     std::vector<uint8_t> cur(stride), prev(stride, 0);
+    std::vector<uint16_t> samples(size_t(w) * channels);
     img.width = w; img.height = h; img.pixels.assign(size_t(w) * h * 4, 255);
+    // tRNS for grey / RGB images: one colour that becomes transparent (compared at the file's bit depth)
+    const bool keyed = (colour == 0 && trns.size() >= 2) || (colour == 2 && trns.size() >= 6);
+    uint16_t key[3] = {0, 0, 0};
+    if (keyed) for (int k = 0; k < (colour == 0 ? 1 : 3); ++k) key[k] = uint16_t((trns[2 * k] << 8) | trns[2 * k + 1]);
+    const int scale = depth == 1 ? 255 : depth == 2 ? 85 : depth == 4 ? 17 : 1; // grey samples below 8 bits are stretched to 0..255
     for (uint32_t y = 0; y < h; ++y) {
         const uint8_t* line = &raw[(stride + 1) * y];
         const int filter = line[0];
         for (size_t i = 0; i < stride; ++i) {
-            const int a = i >= size_t(channels) ? cur[i - channels] : 0, b = prev[i], c = i >= size_t(channels) ? prev[i - channels] : 0;
+            const int a = i >= bpp ? cur[i - bpp] : 0, b = prev[i], c = i >= bpp ? prev[i - bpp] : 0;
             int pred = 0;
             switch (filter) {
                 case 0: pred = 0; break;
@@ -57,15 +67,21 @@ bool decodePng(const std::vector<uint8_t>& f, Image& img, std::string* error) {
             }
             cur[i] = uint8_t(line[1 + i] + pred);
         }
+        for (size_t k = 0; k < samples.size(); ++k) { // samples at the file's depth
+            if (depth == 8) samples[k] = cur[k];
+            else if (depth == 16) samples[k] = uint16_t((cur[2 * k] << 8) | cur[2 * k + 1]);
+            else { const size_t bit = k * size_t(depth); samples[k] = uint16_t((cur[bit / 8] >> (8 - depth - int(bit % 8))) & ((1 << depth) - 1)); }
+        }
+        auto to8 = [&](uint16_t v) { return uint8_t(depth == 16 ? (v >> 8) : v); }; // 16-bit samples keep their high byte (as stbi_load's 8-bit interface does)
         for (uint32_t x = 0; x < w; ++x) {
             uint8_t* o = &img.pixels[(size_t(y) * w + x) * 4];
-            const uint8_t* s = &cur[size_t(x) * channels];
+            const uint16_t* sp = &samples[size_t(x) * channels];
             switch (colour) {
-                case 0: o[0] = o[1] = o[2] = s[0]; break;
-                case 2: o[0] = s[0]; o[1] = s[1]; o[2] = s[2]; break;
-                case 3: { const size_t k = s[0]; if (3 * k + 2 >= palette.size()) return fail(error, "PNG palette index out of range"); o[0] = palette[3 * k]; o[1] = palette[3 * k + 1]; o[2] = palette[3 * k + 2]; if (k < trns.size()) o[3] = trns[k]; break; }
-                case 4: o[0] = o[1] = o[2] = s[0]; o[3] = s[1]; break;
-                case 6: o[0] = s[0]; o[1] = s[1]; o[2] = s[2]; o[3] = s[3]; break;
+                case 0: o[0] = o[1] = o[2] = uint8_t(to8(sp[0]) * (depth < 8 ? scale : 1)); if (keyed && sp[0] == key[0]) o[3] = 0; break;
+                case 2: o[0] = to8(sp[0]); o[1] = to8(sp[1]); o[2] = to8(sp[2]); if (keyed && sp[0] == key[0] && sp[1] == key[1] && sp[2] == key[2]) o[3] = 0; break;
+                case 3: { const size_t k = sp[0]; if (3 * k + 2 >= palette.size()) return fail(error, "PNG palette index out of range"); o[0] = palette[3 * k]; o[1] = palette[3 * k + 1]; o[2] = palette[3 * k + 2]; if (k < trns.size()) o[3] = trns[k]; break; }
+                case 4: o[0] = o[1] = o[2] = to8(sp[0]); o[3] = to8(sp[1]); break;
+                case 6: o[0] = to8(sp[0]); o[1] = to8(sp[1]); o[2] = to8(sp[2]); o[3] = to8(sp[3]); break;
             }
         }
         prev.swap(cur);
