@@ -178,6 +178,53 @@ void orc_sample_probes(orc_ctx* c, const float pos[3], const float n[3], const f
     ovm::vec3 r = oddgi::sampleProbes(c->probes, ovm::V3(pos[0], pos[1], pos[2]), ovm::V3(n[0], n[1], n[2]), ovm::V3(toCam[0], toCam[1], toCam[2]));
     out[0] = r.x; out[1] = r.y; out[2] = r.z;
 }
+
+// ---- function-level batch entry points: the restated shader functions one by one, for the pin against oracle/_ref
+// (the reference's own GLSL text compiled as C++, tests/test_glsl_ref_pin.py).
+void orc_fetch_atlas(const void* user, int kind, float u, float v, float out4[4]) { // textureLod(colorTex | depthTex, uv, 0)
+    const orc_ctx* c = static_cast<const orc_ctx*>(user);
+    if (kind == 0) { ovm::vec3 r = oddgi::sampleIrradiance(c->probes, ovm::V2(u, v)); out4[0] = r.x; out4[1] = r.y; out4[2] = r.z; out4[3] = 1.0f; }
+    else { ovm::vec2 r = oddgi::sampleDepth(c->probes, ovm::V2(u, v)); out4[0] = r.x; out4[1] = r.y; out4[2] = 0.0f; out4[3] = 1.0f; }
+}
+void orc_fn_sky(const float* o, const float* d, const float* sun, const float* sunColor, float brightness, int showSun, size_t n, float* out) {
+    for (size_t i = 0; i < n; ++i) {
+        ovm::vec3 c = oddgi::sky(ovm::V3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), ovm::V3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), ovm::V3(sun[0], sun[1], sun[2]), ovm::V3(sunColor[0], sunColor[1], sunColor[2]), brightness, showSun != 0);
+        out[3 * i] = c.x; out[3 * i + 1] = c.y; out[3 * i + 2] = c.z;
+    }
+}
+void orc_fn_sample_probes(orc_ctx* c, const float* pos, const float* nrm, const float* toCam, size_t n, float* out) {
+    for (size_t i = 0; i < n; ++i) {
+        ovm::vec3 r = oddgi::sampleProbes(c->probes, ovm::V3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]), ovm::V3(nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]), ovm::V3(toCam[3 * i], toCam[3 * i + 1], toCam[3 * i + 2]));
+        out[3 * i] = r.x; out[3 * i + 1] = r.y; out[3 * i + 2] = r.z;
+    }
+}
+void orc_fn_pbr(const float* nrm, const float* view, const float* lightColor, const float* lightDir, const float* albedo, const float* metalRough, size_t n, float* out) {
+    for (size_t i = 0; i < n; ++i) {
+        ovm::vec4 c = oddgi::pbrMetallicRoughness(ovm::V3(nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]), ovm::V3(view[3 * i], view[3 * i + 1], view[3 * i + 2]), ovm::V3(lightColor[0], lightColor[1], lightColor[2]),
+                                                  ovm::V3(lightDir[0], lightDir[1], lightDir[2]), ovm::V4(albedo[4 * i], albedo[4 * i + 1], albedo[4 * i + 2], albedo[4 * i + 3]), metalRough[2 * i], metalRough[2 * i + 1]);
+        out[4 * i] = c.x; out[4 * i + 1] = c.y; out[4 * i + 2] = c.z; out[4 * i + 3] = c.w;
+    }
+}
+void orc_fn_spherical_fibonacci(const float* i_, float nn, size_t n, float* out) {
+    for (size_t i = 0; i < n; ++i) { ovm::vec3 v = oddgi::sphericalFibonacci(i_[i], nn); out[3 * i] = v.x; out[3 * i + 1] = v.y; out[3 * i + 2] = v.z; }
+}
+void orc_fn_oct_decode(const float* o, size_t n, float* out) {
+    for (size_t i = 0; i < n; ++i) { ovm::vec3 v = oddgi::octDecode(ovm::V2(o[2 * i], o[2 * i + 1])); out[3 * i] = v.x; out[3 * i + 1] = v.y; out[3 * i + 2] = v.z; }
+}
+void orc_fn_oct_encode(const float* d, size_t n, float* out) {
+    for (size_t i = 0; i < n; ++i) { ovm::vec2 v = oddgi::octEncode(ovm::V3(d[3 * i], d[3 * i + 1], d[3 * i + 2])); out[2 * i] = v.x; out[2 * i + 1] = v.y; }
+}
+void orc_fn_sphere_to_oct_uv(const float* d, size_t n, float* out) {
+    for (size_t i = 0; i < n; ++i) { ovm::vec2 v = oddgi::spherePointToOctohedralUV(ovm::V3(d[3 * i], d[3 * i + 1], d[3 * i + 2])); out[2 * i] = v.x; out[2 * i + 1] = v.y; }
+}
+void orc_fn_rotate_axis(const float* p, const float* axis, const float* angle, size_t n, float* out) {
+    for (size_t i = 0; i < n; ++i) { ovm::vec3 v = oddgi::rotateAxis(ovm::V3(p[3 * i], p[3 * i + 1], p[3 * i + 2]), ovm::V3(axis[3 * i], axis[3 * i + 1], axis[3 * i + 2]), angle[i]); out[3 * i] = v.x; out[3 * i + 1] = v.y; out[3 * i + 2] = v.z; }
+}
+void orc_fn_gaussian(const float* stdDev, const float* dist, size_t n, float* out) { for (size_t i = 0; i < n; ++i) out[i] = oshadow::gaussian(stdDev[i], dist[i]); }
+void orc_fn_gaussian_refl(const float* stdDev, const float* dist, size_t n, float* out) { for (size_t i = 0; i < n; ++i) out[i] = oshadow::rgaussian(stdDev[i], dist[i]); }
+void orc_fn_probe_helpers(const vkx_grid_info* g, const uint32_t* index, size_t n, int* outI, float* outF) {
+    for (size_t i = 0; i < n; ++i) oddgi::probeHelpers(*g, index[i], outI + 8 * i, outF + 6 * i);
+}
 void orc_border_source(int T, int x, int y, int out[2]);
 
 // host logic (IrradianceProbes.cpp)

@@ -47,6 +47,13 @@ static inline ivec2 probeIndexToDepthUVOffset(ivec3 i, const vkx_grid_info& g) {
     return ivec2{int(g.depthRes) * (i.y * g.resolution[0] + i.x), int(g.depthRes) * i.z};
 }
 
+void probeHelpers(const vkx_grid_info& g, uint32_t index, int outI[8], float outF[6]) { // irradiance.glsl:7-38, every helper on one index (pin hook)
+    const ivec3 gi = probeLinearIndexToGridIndex(index, g);
+    const ivec2 cu = probeIndexToColorUVOffset(gi, g), du = probeIndexToDepthUVOffset(gi, g);
+    outI[0] = gi.x; outI[1] = gi.y; outI[2] = gi.z; outI[3] = int(probeLinearIndex(gi, g)); outI[4] = cu.x; outI[5] = cu.y; outI[6] = du.x; outI[7] = du.y;
+    const vec3 w = probeIndexToWorldPosition(gi, g), cs = probeGridCellSize(g);
+    outF[0] = w.x; outF[1] = w.y; outF[2] = w.z; outF[3] = cs.x; outF[4] = cs.y; outF[5] = cs.z;
+}
 vec3 sphericalFibonacci(float i, float n) { // irradiance.glsl:52-64
     const float PHI = std::sqrt(5.0f) * 0.5f + 0.5f;
     float ab = i * (PHI - 1.0f);
@@ -58,6 +65,12 @@ vec3 sphericalFibonacci(float i, float n) { // irradiance.glsl:52-64
 
 static inline float signNotZero(float k) { return (k >= 0.0f) ? 1.0f : -1.0f; } // :88-90
 
+vec2 octEncode(vec3 v) { // :97-103 (not called on the hot path; restated so that row a12 is pinned as a whole)
+    float l1norm = std::fabs(v.x) + std::fabs(v.y) + std::fabs(v.z);
+    vec2 result = V2(v.x, v.y) * (1.0f / l1norm);
+    if (v.z < 0.0f) result = V2((1.0f - std::fabs(result.y)) * signNotZero(result.x), (1.0f - std::fabs(result.x)) * signNotZero(result.y));
+    return result;
+}
 vec3 octDecode(vec2 o) { // :107-112
     vec3 v = V3(o.x, o.y, 1.0f - std::fabs(o.x) - std::fabs(o.y));
     if (v.z < 0.0f) {
@@ -90,7 +103,7 @@ static inline void bilinearSetup(float u, float size, int& i0, int& i1, float& f
     i0 = ((i % isz) + isz) % isz;
     i1 = (i0 + 1) % isz;
 }
-static vec3 sampleIrradiance(const Probes& p, vec2 uv) {
+vec3 sampleIrradiance(const Probes& p, vec2 uv) {
     int x0, x1, y0, y1; float fx, fy;
     bilinearSetup(uv.x, float(p.irrW), x0, x1, fx);
     bilinearSetup(uv.y, float(p.irrH), y0, y1, fy);
@@ -107,7 +120,7 @@ static vec3 sampleIrradiance(const Probes& p, vec2 uv) {
     }
     return r;
 }
-static vec2 sampleDepth(const Probes& p, vec2 uv) {
+vec2 sampleDepth(const Probes& p, vec2 uv) {
     int x0, x1, y0, y1; float fx, fy;
     bilinearSetup(uv.x, float(p.depW), x0, x1, fx);
     bilinearSetup(uv.y, float(p.depH), y0, y1, fy);

@@ -68,7 +68,11 @@ ovm::vec4 traceAndShade(const Scene& s, const Probes& p, const vkx_light& light,
 ovm::vec3 sky(ovm::vec3 rayOrigin, ovm::vec3 rayDirection, ovm::vec3 sunPosition, ovm::vec3 sunColor, float sunBrightnessFactor, bool showSun);
 ovm::vec4 pbrMetallicRoughness(ovm::vec3 normal, ovm::vec3 view, ovm::vec3 lightColor, ovm::vec3 lightDirection, ovm::vec4 albedo, float metalness, float roughness);
 ovm::vec3 sampleProbes(const Probes& p, ovm::vec3 position, ovm::vec3 normal, ovm::vec3 toCamera);
+ovm::vec3 sampleIrradiance(const Probes& p, ovm::vec2 uv); // textureLod(colorTex, uv, 0): decreed exact-fp32 bilinear, REPEAT
+ovm::vec2 sampleDepth(const Probes& p, ovm::vec2 uv);
 ovm::vec3 sphericalFibonacci(float i, float n);
+ovm::vec2 octEncode(ovm::vec3 v);
+void probeHelpers(const vkx_grid_info& g, uint32_t index, int outI[8], float outF[6]);
 ovm::vec3 octDecode(ovm::vec2 o);
 ovm::vec2 spherePointToOctohedralUV(ovm::vec3 direction);
 

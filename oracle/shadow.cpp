@@ -124,7 +124,7 @@ static vec4 sampleNoise(const State& st, uint32_t slice, float u, float v) {
     return r;
 }
 
-static inline float gaussian(float stdDev, float dist) { // directLightFilter.glsl:29-31
+float gaussian(float stdDev, float dist) { // directLightFilter.glsl:29-31
     return (1.0f / (std::sqrt(2.0f * 3.14159f) * stdDev)) * std::exp(-(dist * dist) / (2.0f * stdDev * stdDev));
 }
 
@@ -231,7 +231,7 @@ void frame(const oddgi::Scene& s, State& st, const vkx_camera& cur, const vkx_ca
 }
 
 // ---------------------------------------------------------------- reflection pass
-static inline float rgaussian(float stdDev, float dist) { // reflectionFilter.glsl:37-39
+float rgaussian(float stdDev, float dist) { // reflectionFilter.glsl:37-39
     return (1.0f / (std::sqrt(2.0f * 3.14159f) * stdDev)) * std::exp(-(dist * dist) / (2.0f * stdDev * stdDev));
 }
 

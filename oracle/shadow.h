@@ -35,4 +35,7 @@ void reflectionFrame(const oddgi::Scene& s, const oddgi::Probes& probes, State& 
 // reflection: optional RGBA32F [h][w][4] (e.g. reflFinal of reflectionFrame; nullptr = black).
 void finalGather(const oddgi::Scene& s, const oddgi::Probes& probes, State& st, const vkx_camera& cam, const vkx_light& light, const float* reflection);
 
+float gaussian(float stdDev, float dist);  // directLightFilter.glsl:29-31
+float rgaussian(float stdDev, float dist); // reflectionFilter.glsl:37-39
+
 } // namespace oshadow
