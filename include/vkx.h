@@ -166,8 +166,9 @@ int vkx_scene_upload(vkx_ctx* ctx, const vkx_vertex* vertices, size_t numVertice
  * shorter than the uploaded materials need discards the uploaded scene (tracing fails until the next vkx_scene_upload + vkx_bvh_build). */
 int vkx_scene_textures(vkx_ctx* ctx, const vkx_texture* textures, size_t numTextures);
 /* Host-side image decoder (no context, no GPU): what STBImage does in uploadTextures (src/Resources.cpp:56-60), for the formats the
- * library reads itself: PNG (8 bits per channel, non-interlaced), Netpbm P6 and P7. Always expands to RGBA8. rgba may be NULL to
- * query the size. Returns VKX_E_UNSUPPORTED for files it cannot decode. */
+ * library reads itself: PNG (every colour type and bit depth incl. palettes and tRNS keys, non-interlaced, at most 16384 x 16384),
+ * Netpbm P6 and P7. Always expands to RGBA8. rgba may be NULL to query the size. Returns VKX_E_UNSUPPORTED for files it cannot
+ * decode (never throws across the boundary; VKX_E_NOMEM if the host allocation fails). */
 int vkx_image_decode(const char* path, uint8_t* rgba, size_t rgbaBytes, uint32_t* width, uint32_t* height);
 /* Parity primitives for the texture path: the generated mip chain (level-major RGBA8, numLevels = floor(log2(max(w, h))) + 1) and
  * n texture look-ups with explicit gradients (uv: 2 floats, grads: dudx, dvdx, dudy, dvdy per look-up; grads NULL = texture() of a

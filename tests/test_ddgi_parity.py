@@ -206,3 +206,113 @@ def test_multi_chunk_update_equals_single_chunk(oracle_lib):
     o.probes_update(grid, light, R, idx); g.probes_update(grid, light, R, idx)
     io, do, so, _ = o.probes_download(); ig, dg, sg, _ = g.probes_download()
     assert (io != ig).mean() < 5e-3 and (do != dg).mean() < 5e-3 and (so != sg).mean() < 2e-2
+
+
+def test_queued_async_updates_with_changing_lists(oracle_lib):
+    """Frames queued without host synchronisation (sync=0), each with a different to-update list: every frame must trace its own
+    list and slot order (the pinned staging of the list rotates through four slots together with the frame inputs; ADVICE r1:
+    the slot index was never set, so queued frames shared one staging area)."""
+    o, g, flat, grid = _setup(oracle_lib, "court", (8, 6, 8), 32)
+    host = oracle_lib.HostLogic()
+    light = Light.default()
+    st = np.ones(grid.probe_count, dtype=np.uint32)
+    rng = np.random.default_rng(11)
+    lists = [rng.permutation(grid.probe_count).astype(np.uint32)[: int(n)] for n in (300, 17, 384, 200, 5, 333, 384, 64)]
+    Rs = [host.next_orientation()[0] for _ in lists]
+    grid.hysteresis = 0.4
+    # reference run: one synchronised update per frame
+    g.probes_upload(np.zeros_like(g.probes_download()[0]), np.zeros_like(g.probes_download()[1]), st)
+    for R, lst in zip(Rs, lists):
+        g.probes_update(grid, light, R, lst, sync=True)
+    want = g.probes_download()
+    # queued run: the same frames back to back without waiting
+    g.probes_upload(np.zeros_like(want[0]), np.zeros_like(want[1]), st)
+    for R, lst in zip(Rs, lists):
+        g.probes_update(grid, light, R, lst, sync=False)
+    got = g.probes_download()
+    assert np.array_equal(want[0], got[0]) and np.array_equal(want[1], got[1]) and np.array_equal(want[2], got[2])
+    # and the last frame agrees with the oracle run over the same sequence
+    o.probes_upload(np.zeros_like(want[0]), np.zeros_like(want[1]), st)
+    for R, lst in zip(Rs, lists):
+        o.probes_update(grid, light, R, lst)
+    io, do, sto, _ = o.probes_download()
+    assert (io != got[0]).mean() < 5e-3 and (do != got[1]).mean() < 5e-3
+
+
+def test_cfg2_full_volume_update_parity(oracle_lib):
+    """The benchmarked workload itself (BASELINE.json configs[1]): 32x16x32 probes x 256 rays on the 265k-triangle atrium, two
+    full-volume updates. Hit records and shadow visibility bit-exact, ray depths bit-exact, fp32 texels within 1e-3; the packed
+    code-flip rate is printed and bounded."""
+    o, g, flat, grid = _setup(oracle_lib, "cfg2", (32, 16, 32), 256)
+    host = oracle_lib.HostLogic()
+    R, _ = host.next_orientation()
+    o.probes_classify(R); g.probes_classify(R)
+    _, _, sto, _ = o.probes_download(); _, _, stg, _ = g.probes_download()
+    assert np.array_equal(sto, stg), "probe classification differs on cfg2"
+    ones = np.ones(grid.probe_count, dtype=np.uint32)  # the benchmark updates every probe
+    o.probes_upload(state=ones); g.probes_upload(state=ones)
+    light = Light.default()
+    worst = (0.0, 0.0, 0.0)
+    for frame in range(2):
+        R, _ = host.next_orientation()
+        grid.hysteresis = 0.0 if frame == 0 else 0.7
+        o.probes_update(grid, light, R, None); g.probes_update(grid, light, R, None)
+        f = _compare_update(o, g, frame)
+        worst = tuple(max(a, b) for a, b in zip(worst, f))
+        io, do, sto, _ = o.probes_download()
+        g.probes_upload(io, do, sto)
+    print("cfg2 packed-code flip rates (irradiance, depth, state):", worst)
+    assert worst[0] < 1e-3 and worst[1] < 1e-3 and worst[2] < 2e-3
+
+
+def test_32_frame_free_run_reports_drift(oracle_lib):
+    """32 free-running frames (no resynchronisation): the recursion reads its own quantised atlases, so a flipped code persists and
+    diffuses. Reports irradiance drift and state mismatches per checkpoint; bounds them at the end."""
+    o, g, flat, grid = _setup(oracle_lib, "court", (8, 6, 8), 64)
+    host = oracle_lib.HostLogic()
+    R, _ = host.next_orientation()
+    o.probes_classify(R); g.probes_classify(R)
+    light = Light.default()
+    grid.hysteresis = 0.9
+    report = []
+    for frame in range(32):
+        R, _ = host.next_orientation()
+        o.probes_update(grid, light, R, None); g.probes_update(grid, light, R, None)
+        if frame in (0, 1, 3, 7, 15, 31):
+            io, do, sto, _ = o.probes_download(); ig, dg, stg, _ = g.probes_download()
+            a, b = _unpack_r11g11b10(io.astype(np.int64)), _unpack_r11g11b10(ig.astype(np.int64))
+            e = rel_err(a, b, floor=1e-2)
+            report.append((frame + 1, float((io != ig).mean()), float(e.max()), float((e > 2.0 ** -5).mean()), float((do != dg).mean()), float((sto != stg).mean())))
+    print("free run: (frames, irr words differing, max rel err, frac > 1 code, depth words differing, state mismatch)")
+    for r in report:
+        print("  ", r)
+    last = report[-1]
+    assert last[3] < 5e-4, "more than 0.05 %% of the irradiance texels drifted by more than one R11G11B10 code: %r" % (last,)
+    assert last[5] < 5e-3, "probe states diverged: %r" % (last,)
+
+
+def test_cfg4_slab_update_parity(oracle_lib):
+    """BASELINE.json configs[3]: the nature-like scene (2.24 M instanced triangles), 64x32x64 probes x 256 rays. One z-slab of the
+    volume (what one rank of a sharded run traces: 2 of 64 slices = 4096 probes, 1 M rays) against the oracle, two frames."""
+    from vulkanexp_b200 import scene_format, synth
+    from vulkanexp_b200._lib import Context
+
+    flat = scene_format.flatten(synth.make_cfg4())
+    grid = GridInfo.make(flat["bounds_min"], flat["bounds_max"], (64, 32, 64), 256, hysteresis=0.0)
+    o = oracle_lib.Oracle(); o.scene_upload(flat); o.bvh_build(); o.probes_init(grid)
+    g = Context(0); g.scene_upload(flat); g.bvh_build(); g.probes_debug(True); g.probes_init(grid)
+    assert o.bvh_download()[0].tobytes() == g.bvh_download()[0].tobytes(), "cfg4 BVH differs"
+    ones = np.ones(grid.probe_count, dtype=np.uint32)
+    o.probes_upload(state=ones); g.probes_upload(state=ones)
+    plane = 64 * 32
+    idx = np.arange(30 * plane, 32 * plane, dtype=np.uint32)
+    host = oracle_lib.HostLogic()
+    light = Light.default()
+    for frame in range(2):
+        R, _ = host.next_orientation()
+        grid.hysteresis = 0.0 if frame == 0 else 0.8
+        o.probes_update(grid, light, R, idx); g.probes_update(grid, light, R, idx)
+        irr_flip, dep_flip, st_diff = _compare_update(o, g, frame)
+        assert irr_flip < 1e-3 and dep_flip < 1e-3 and st_diff < 2e-3
+        io, do, sto, _ = o.probes_download()
+        g.probes_upload(io, do, sto)

@@ -91,3 +91,48 @@ def test_facade_loader_reports_missing_files(tmp_path):
     os.remove(str(tmp_path / "tex_grate.pam"))  # an unreadable texture becomes the blank image (reference src/Scene.cpp:699), with a warning
     got = host_scene_load(path)
     assert got["textures"][4]["pixels"].shape == (1, 1, 4) and (got["textures"][4]["pixels"] == 255).all()
+
+
+def _write_raw_scene(path, entities, json_len_lie=None):
+    import json
+
+    doc = json.dumps({"materials": [], "entities": entities, "meshes": [], "textures": []}).encode()
+    jlen = len(doc) if json_len_lie is None else json_len_lie
+    total = 12 + 8 + len(doc)
+    open(path, "wb").write(struct.pack("<III", 0x4E454353, 0, total) + struct.pack("<II", jlen, 0x4E4F534A) + doc)
+
+
+def test_loader_rejects_truncated_and_cyclic_files(tmp_path):
+    """Corrupt input must fail with an error code, not read past the buffer or recurse without end."""
+    from vulkanexp_b200._lib import VkxError, host_scene_load
+
+    ident = [1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0]
+    ok = [{"name": "root", "transform": ident, "parent": -1, "children": [1]}, {"name": "a", "transform": ident, "parent": -1, "children": []}]
+    p = os.path.join(tmp_path, "ok.scene"); _write_raw_scene(p, ok); host_scene_load(p)
+    p = os.path.join(tmp_path, "lie.scene"); _write_raw_scene(p, ok, json_len_lie=1 << 20)  # JSON chunk claims 1 MiB
+    with pytest.raises(VkxError):
+        host_scene_load(p)
+    for name, ents in (("self", [{"name": "root", "transform": ident, "parent": -1, "children": [1]}, {"name": "a", "transform": ident, "parent": -1, "children": [1]}]),
+                       ("cycle", [{"name": "root", "transform": ident, "parent": -1, "children": [1]}, {"name": "a", "transform": ident, "parent": -1, "children": [2]}, {"name": "b", "transform": ident, "parent": -1, "children": [1]}]),
+                       ("range", [{"name": "root", "transform": ident, "parent": -1, "children": [7]}])):
+        p = os.path.join(tmp_path, name + ".scene"); _write_raw_scene(p, ents)
+        with pytest.raises(VkxError):
+            host_scene_load(p)
+
+
+def test_png_decoder_refuses_huge_headers(tmp_path):
+    import zlib
+
+    from vulkanexp_b200._lib import VkxError, image_decode
+
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xFFFFFFFF)
+
+    p = os.path.join(tmp_path, "huge.png")
+    open(p, "wb").write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", 0xFFFFFFF0, 0xFFFFFFF0, 8, 6, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(b"\0" * 16)) + chunk(b"IEND", b""))
+    with pytest.raises(VkxError):
+        image_decode(p)
+    p = os.path.join(tmp_path, "thin.png")  # plausible size, but 8 bytes of IDAT cannot hold 4096 x 4096 RGBA
+    open(p, "wb").write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", 4096, 4096, 8, 6, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(b"\0" * 8)) + chunk(b"IEND", b""))
+    with pytest.raises(VkxError):
+        image_decode(p)

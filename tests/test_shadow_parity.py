@@ -103,3 +103,47 @@ def test_sky_pixels_and_odd_sizes(oracle_lib):
     assert (raw[pd[..., 3] <= 0] == -1.0).all()
     for stage in (0, 1, 2):
         assert np.abs(o.shadow_download(stage)[0] - g.shadow_download(stage)).max() < 1e-3
+
+
+def test_cfg3_1080p_with_reference_blue_noise(oracle_lib):
+    """BASELINE.json configs[2] at 1920x1080 on the dungeon-like scene (cut-out grates: the any-hit test runs), jittered with the
+    REFERENCE's 64 blue-noise slices (data/BlueNoise/64_64/LDR_RGBA_*.png via tests/golden/blue_noise_ldr_rgba_64.npz). Three
+    frames of a moving camera: mask bit-exact on identical jitter directions, X filter < 1e-3, temporal stage: bounded flips."""
+    from vulkanexp_b200 import scene_format
+    from vulkanexp_b200._lib import Context
+
+    w, h = 1920, 1080
+    flat = scene_format.flatten(synth.make_cfg3(alpha_grates=True))
+    o = oracle_lib.Oracle(); o.scene_upload(flat); o.bvh_build()
+    g = Context(0); g.scene_upload(flat); g.bvh_build()
+    assert o.bvh_download()[0].tobytes() == g.bvh_download()[0].tobytes()
+    noise = synth.reference_blue_noise(64)
+    assert noise.shape == (64, 64, 64, 4)
+    for c in (o, g):
+        c.shadow_set_noise(noise); c.shadow_init(w, h)
+    light = Light.default()
+    cams = [make_camera((-20.0 + 1.2 * f, 2.2, -18.0 + 0.9 * f), (0.0 + 0.5 * f, 1.5, 0.0), aspect=w / h, frame_index=62 + f) for f in range(3)]  # slices 62, 63, 0: wraps % 64
+    prev = cams[0]
+    for f, cam in enumerate(cams):
+        g.gbuffer_generate(cam)
+        pd, nm = g.gbuffer_download()
+        o.gbuffer_upload(pd, nm)
+        g.shadow_frame(cam, prev, light)
+        dirs, mask_g = g.shadow_download_debug()
+        o.shadow_frame(cam, prev, light, dir_override=dirs)
+        raw_o, _, mask_o = o.shadow_download(0)
+        assert np.array_equal(mask_o, mask_g), "frame %d: shadow mask differs" % f
+        assert (mask_g == 2).mean() > 0.02 and (mask_g == 1).mean() > 0.02
+        e = np.abs(o.shadow_download(1)[0].astype(np.float64) - g.shadow_download(1).astype(np.float64))
+        assert e.max() < 1e-3, "frame %d filter X: %g" % (f, e.max())
+        b = g.shadow_download(2)
+        e = np.abs(o.shadow_download(2)[0].astype(np.float64) - b.astype(np.float64)).max(axis=-1)
+        bad = float((e > 1e-3).mean())
+        print("cfg3 1080p frame %d: shadowed %.3f, temporal-stage pixels off by > 1e-3: %.2e" % (f, float((mask_g == 2).mean()), bad))
+        assert bad < 1e-3
+        o.shadow_set_history(b)
+        prev = cam
+    # free jitter (each side computes its own directions from the noise): the directions agree to rounding
+    o.shadow_frame(cams[2], cams[1], light)
+    _, dirs_o, mask_free = o.shadow_download(0)
+    assert np.abs(dirs_o - dirs).max() < 2e-6 and (mask_free != mask_g).mean() < 1e-3

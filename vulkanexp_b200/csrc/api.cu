@@ -399,6 +399,7 @@ static int uploadFrameInputs(vkx_ctx* ctx, const vkx_grid_info* grid, const floa
     if (!ctx->hStage) { CUDA_TRY(ctx, cudaMallocHost(&ctx->hStage, 4 * sizeof(vkx_ctx::FrameStage))); for (auto& e : ctx->stageEvent) CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); }
     const int slot = int(ctx->stageCursor++ & 3u);
     if (ctx->stageUsed[slot]) CUDA_TRY(ctx, cudaEventSynchronize(ctx->stageEvent[slot]));
+    ctx->curSlot = slot; // uploadOrder stages the to-update list / slot order of this frame in the same slot
     vkx_ctx::FrameStage& fs = ctx->hStage[slot];
     float4* d4 = fs.dirs;
     for (uint32_t i = 0; i < N; ++i) d4[i] = make_float4(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2], 1.0f);

@@ -63,6 +63,7 @@ struct vkx_ctx {
     std::string err;
     uint64_t launches = 0;
     int smCount = 148;
+    bool blendAttrSet = false; int traceBlocksPerSm = 0; // per-device kernel attributes / occupancy (set on first use)
 
     // scene
     vkx_vertex* dVertices = nullptr; uint32_t* dIndices = nullptr; vkx_offset_entry* dOffsets = nullptr; uint32_t* dMeshCounts = nullptr;

@@ -460,8 +460,8 @@ int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* /*unused*/,
     const float tmax = sqrtf(ex * ex + ey * ey + ez * ez); // traceProbes.rgen:33
     const float cx = ex / float(ctx->grid.resolution[0] - 1), cy = ey / float(ctx->grid.resolution[1] - 1), cz = ez / float(ctx->grid.resolution[2] - 1);
     BlendParams bp; bp.grid = ctx->grid; bp.raysPerProbe = N; bp.gridCellLen = sqrtf(cx * cx + cy * cy + cz * cz);
-    static bool blendAttr = false;
-    if (!blendAttr) { CUDA_TRY(ctx, cudaFuncSetAttribute(k_blend, cudaFuncAttributeMaxDynamicSharedMemorySize, BLEND_SMEM_BYTES)); blendAttr = true; }
+    // function attributes and occupancy are per device: cached in the context, not in process-wide statics
+    if (!ctx->blendAttrSet) { CUDA_TRY(ctx, cudaFuncSetAttribute(k_blend, cudaFuncAttributeMaxDynamicSharedMemorySize, BLEND_SMEM_BYTES)); ctx->blendAttrSet = true; }
     // Leaf deferral of the two persistent traversals (ptrace.cuh): 0 = off, else the number of waiting lanes that triggers a triangle phase.
     // Tuning knobs (results are identical for every value): VKX_PT_DEFER / VKX_PT_DEFER_SHADOW in {0, 8, 12, 16}.
     static int deferPrimary = -1, deferShadow = -1;
@@ -469,9 +469,8 @@ int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* /*unused*/,
         auto pick = [](const char* name, int dflt) { const char* e = getenv(name); int v = e ? atoi(e) : dflt; return v <= 0 ? 0 : v <= 8 ? 8 : v <= 12 ? 12 : 16; };
         deferPrimary = pick("VKX_PT_DEFER", PT_DEFER_PRIMARY_DEFAULT); deferShadow = pick("VKX_PT_DEFER_SHADOW", PT_DEFER_SHADOW_DEFAULT);
     }
-    static int blocksPerSm = 0;
-    if (!blocksPerSm) { int a = 0, b = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_trace_primary<0>, 128, 0); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace_shadow<0>, 128, 0); blocksPerSm = std::max(1, std::min(a, b)); }
-    const unsigned persistentBlocks = unsigned(ctx->smCount * blocksPerSm);
+    if (!ctx->traceBlocksPerSm) { int a = 0, b = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_trace_primary<0>, 128, 0); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace_shadow<0>, 128, 0); ctx->traceBlocksPerSm = std::max(1, std::min(a, b)); }
+    const unsigned persistentBlocks = unsigned(ctx->smCount * ctx->traceBlocksPerSm);
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
     k_blend_weights<<<(N + 3u) & ~3u, BLEND_COLS, 0, st>>>(ctx->grid.depthSharpness, N, ctx->dDirs, ctx->dBlendW); LAUNCH_CHECK(ctx);
     k_blend_weight_sums<<<1, BLEND_COLS, 0, st>>>(N, ctx->dBlendW); LAUNCH_CHECK(ctx);

@@ -75,19 +75,13 @@ void launchShadeFront(unsigned blocks, cudaStream_t st, const DeviceScene& sc, c
     // shadow rays more coherent. Measured on B200, cfg2 (profiles/r01d_shade_grid_sweep.txt), sort + shading / k_trace_shadow:
     // 6 blocks per SM (one wave) 0.907 ms, 16 (the old grid) 0.854 / 0.375 ms, 36: 0.841, 64: 0.832 / 0.360, 128: 0.825 / 0.357,
     // uncapped: 0.823 / 0.351 ms. VKX_SHADE_BLOCKS_PER_SM caps the grid (tuning).
-    static int perSm[2] = {0, 0}, smCount = 0;
-    const int v = sc.numTextures ? 1 : 0;
-    if (!perSm[v]) {
-        int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&smCount, cudaDevAttrMultiProcessorCount, dev);
-        int occ = 0;
-        if (v) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade_front<true>, 128, 0); else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade_front<false>, 128, 0);
-        const char* e = getenv("VKX_SHADE_BLOCKS_PER_SM");
-        (void)occ;
-        perSm[v] = e && atoi(e) > 0 ? atoi(e) : (1 << 20); // default: no cap
+    static const int capPerSm = [] { const char* e = getenv("VKX_SHADE_BLOCKS_PER_SM"); return e && atoi(e) > 0 ? atoi(e) : 0; }(); // an environment setting, not device state
+    blocks = unsigned((sp.numRays + 127u) / 128u);
+    if (capPerSm) { // the SM count belongs to the current device (one context per device; several contexts may live in one process)
+        int dev = 0, smCount = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&smCount, cudaDevAttrMultiProcessorCount, dev);
+        const unsigned long long cap = (unsigned long long)(smCount) * (unsigned long long)(capPerSm);
+        if ((unsigned long long)(blocks) > cap) blocks = unsigned(cap);
     }
-    const unsigned all = unsigned((sp.numRays + 127u) / 128u);
-    const unsigned long long cap = (unsigned long long)(smCount) * (unsigned long long)(perSm[v]);
-    blocks = (unsigned long long)(all) < cap ? all : unsigned(cap);
     if (sc.numTextures) k_shade_front<true><<<blocks, 128, 0, st>>>(sc, pr, sp, origins, dirs, hits, frontQueue, counters, rays, shadowQueue);
     else k_shade_front<false><<<blocks, 128, 0, st>>>(sc, pr, sp, origins, dirs, hits, frontQueue, counters, rays, shadowQueue);
 }

@@ -6,6 +6,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <new>
+#include <stdexcept>
 #include <sstream>
 
 namespace vkx {
@@ -34,12 +36,14 @@ bool decodePng(const std::vector<uint8_t>& f, Image& img, std::string* error) {
         off += 12 + size_t(len);
     }
     if (w == 0 || h == 0 || interlace != 0) return fail(error, "unsupported PNG (interlaced or empty)");
+    if (w > 16384u || h > 16384u) return fail(error, "PNG larger than 16384 x 16384 (VKX_MAX_TEXTURE_SIZE)"); // IHDR values are attacker-controlled: no multi-GB allocations
     int channels;
     switch (colour) { case 0: channels = 1; break; case 2: channels = 3; break; case 3: channels = 1; break; case 4: channels = 2; break; case 6: channels = 4; break; default: return fail(error, "unsupported PNG colour type"); }
     const bool depthOk = depth == 8 || depth == 16 || ((colour == 0 || colour == 3) && (depth == 1 || depth == 2 || depth == 4));
     if (!depthOk || (colour == 3 && depth == 16)) return fail(error, "unsupported PNG bit depth");
     const size_t stride = (size_t(w) * size_t(channels) * size_t(depth) + 7) / 8; // bytes per scanline
     const size_t bpp = std::max<size_t>(1, size_t(channels) * size_t(depth) / 8); // filter distance
+    if (idat.size() < 2 || (stride + 1) * size_t(h) > idat.size() * 1040 + 64) return fail(error, "PNG IDAT too small for the image size"); // deflate expands at most ~1032x
     std::vector<uint8_t> raw((stride + 1) * h);
     uLongf rawLen = uLongf(raw.size());
     if (uncompress(raw.data(), &rawLen, idat.data(), uLong(idat.size())) != Z_OK || rawLen != raw.size()) return fail(error, "PNG inflate failed");
@@ -150,12 +154,15 @@ Image Image::blank() { Image i; i.width = i.height = 1; i.pixels = {255, 255, 25
 // C ABI: the image decoder on its own, for callers that bind the library without the C++ facade (include/vkx.h).
 extern "C" int vkx_image_decode(const char* path, uint8_t* rgba, size_t rgbaBytes, uint32_t* width, uint32_t* height) {
     if (!path || !width || !height) return VKX_E_INVALID;
-    vkx::Image img;
-    std::string err;
-    if (!img.load(path, &err)) { std::fprintf(stderr, "vkx_image_decode: %s\n", err.c_str()); return VKX_E_UNSUPPORTED; }
-    *width = img.width; *height = img.height;
-    if (!rgba) return VKX_OK;
-    if (rgbaBytes < img.pixels.size()) return VKX_E_INVALID;
-    std::memcpy(rgba, img.pixels.data(), img.pixels.size());
-    return VKX_OK;
+    try { // no exception may cross the C boundary
+        vkx::Image img;
+        std::string err;
+        if (!img.load(path, &err)) { std::fprintf(stderr, "vkx_image_decode: %s\n", err.c_str()); return VKX_E_UNSUPPORTED; }
+        *width = img.width; *height = img.height;
+        if (!rgba) return VKX_OK;
+        if (rgbaBytes < img.pixels.size()) return VKX_E_INVALID;
+        std::memcpy(rgba, img.pixels.data(), img.pixels.size());
+        return VKX_OK;
+    } catch (const std::bad_alloc&) { return VKX_E_NOMEM;
+    } catch (const std::exception& e) { std::fprintf(stderr, "vkx_image_decode: %s\n", e.what()); return VKX_E_UNSUPPORTED; }
 }

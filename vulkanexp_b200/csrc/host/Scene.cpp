@@ -2,6 +2,7 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <stdexcept>
 #include <functional>
 #include "Json.hpp"
 
@@ -39,6 +40,7 @@ bool Scene::loadScene(const std::string& path) {
     ChunkHeader jc; std::memcpy(&jc, buf.data() + sizeof(Header), sizeof(jc));
     if (jc.type != kChunkJson) return false;
     size_t off = sizeof(Header) + sizeof(ChunkHeader);
+    if (size_t(jc.length) > buf.size() - off) { std::fprintf(stderr, "Scene::loadScene: '%s' is truncated (JSON chunk of %u bytes, %zu left).\n", path.c_str(), jc.length, buf.size() - off); return false; }
     Json root;
     try { root = Json::parse(buf.data() + off, jc.length); } catch (const std::exception& e) { std::fprintf(stderr, "Scene::loadScene: %s\n", e.what()); return false; }
     off += jc.length;
@@ -59,7 +61,18 @@ bool Scene::loadScene(const std::string& path) {
             if (n.contains("meshRenderer")) { node.hasMeshRenderer = true; node.meshIndex = uint32_t(n["meshRenderer"]["meshIndex"].asInt()); node.materialIndex = uint32_t(n["meshRenderer"]["materialIndex"].asInt()); }
             _nodes.push_back(std::move(node));
         }
-        for (size_t i = 0; i < _nodes.size(); ++i) for (int c : _nodes[i].children) _nodes.at(size_t(c)).parent = int(i);
+        // The hierarchy must be a forest: child indices in range, one parent each, no node its own ancestor (a file where a node lists
+        // itself or an ancestor would send Scene::update / computeBounds into unbounded recursion).
+        for (size_t i = 0; i < _nodes.size(); ++i)
+            for (int c : _nodes[i].children) {
+                if (c < 0 || size_t(c) >= _nodes.size() || size_t(c) == i) throw std::runtime_error("entity " + std::to_string(i) + ": child index " + std::to_string(c) + " is out of range or the node itself");
+                if (_nodes[size_t(c)].parent != -1) throw std::runtime_error("entity " + std::to_string(c) + " has two parents");
+                _nodes[size_t(c)].parent = int(i);
+            }
+        for (size_t i = 0; i < _nodes.size(); ++i) { // every parent chain ends at a root within |nodes| steps
+            size_t steps = 0;
+            for (int p = _nodes[i].parent; p != -1; p = _nodes[size_t(p)].parent) if (++steps > _nodes.size()) throw std::runtime_error("entity hierarchy contains a cycle");
+        }
         if (root.contains("materials"))
             for (const Json& m : root["materials"].items()) { // parseMaterial, src/vulkan/Material.cpp:7-28
                 MaterialDesc d; d.name = m.contains("name") ? m["name"].asString() : "NoName";

@@ -581,3 +581,14 @@ def blue_noise_like(slices=64, size=64, seed=SEED_BASE + 64):
     RGBA32F, the value domain Image.cpp:62-69 produces. The pass only needs decorrelated [0,1] values."""
     rng = np.random.default_rng(seed)
     return (rng.integers(0, 256, size=(slices, size, size, 4), dtype=np.uint8).astype(np.float32) / np.float32(255.0)).astype(np.float32)
+
+
+def reference_blue_noise(slices=64):
+    """The reference's own blue-noise slices (data/BlueNoise/64_64/LDR_RGBA_{0..63}.png, bound by src/VulkanLifecycle.cpp:113-119),
+    from the committed fixture tests/golden/blue_noise_ldr_rgba_64.npz (tools/gen_blue_noise_fixture.py decodes the PNGs with the
+    product's decoder). RGBA32F = byte / 255, the value domain src/vulkan/Image.cpp:62-69 produces."""
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "blue_noise_ldr_rgba_64.npz")
+    rgba8 = np.load(path)["rgba8"][:slices]
+    return (rgba8.astype(np.float32) / np.float32(255.0)).astype(np.float32)
