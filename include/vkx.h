@@ -281,6 +281,21 @@ int vkx_comm_p2p_import(vkx_ctx* ctx, const void* handles /* nranks x 64 bytes, 
 /* Full-volume update of this rank's z-slab followed by the all-gather of the atlas/state slabs. */
 int vkx_probes_update_sharded(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx_light* light,
                               const float orientation[16], int sync);
+/* Partial update of a to-update list on several GPUs (the reference's ProbesPerUpdate / refresh-period scheduling,
+ * src/IrradianceProbes.cpp:396-424, sharded): every rank passes the SAME list; rank r traces and blends the list positions
+ * vkx_shard_range gives it, the updated probes' tiles (2 x 16x16 depth + 8x8 irradiance texels + state word, 1296 bytes per probe)
+ * are packed, all-gathered and written into every rank's work and sampled atlases. Results equal vkx_probes_update with the same
+ * list on one GPU. With one rank (or without vkx_comm_init) it is vkx_probes_update. */
+int vkx_probes_update_sharded_list(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx_light* light, const float orientation[16],
+                                   const uint32_t* probeIndices, uint32_t count, int sync);
+/* Orders the context's stream after a pending atlas exchange (the deferred all-gather of vkx_probes_update_sharded); returns at
+ * once. An event recorded on vkx_stream() afterwards completes when the exchange has landed (bench.py times with it). */
+int vkx_stream_wait_exchange(vkx_ctx* ctx);
+/* The sharding arithmetic itself (host only, no context): z-slices [*z0, *z1) of rank `rank` in a full-volume sharded update, and
+ * the positions [*first, *first + *n) of a `count`-long to-update list that rank `rank` processes in vkx_probes_update_sharded_list.
+ * Return VKX_E_INVALID for rz not divisible by nranks / bad rank. */
+int vkx_shard_slab(uint32_t rz, int nranks, int rank, uint32_t* z0, uint32_t* z1);
+int vkx_shard_range(uint32_t count, int nranks, int rank, uint32_t* first, uint32_t* n);
 
 /* ---- sun shadows: DirectLight pass ---------------------------------------------------------------------------- */
 /* Blue-noise slices (RGBA32F = byte/255, src/vulkan/Image.cpp:62-69): [slices][h][w][4]. */

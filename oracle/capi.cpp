@@ -21,6 +21,12 @@ extern "C" {
 
 orc_ctx* orc_create() { return new (std::nothrow) orc_ctx(); }
 void orc_destroy(orc_ctx* c) { delete c; }
+// torch.distributed.run exports OMP_NUM_THREADS=1 to every rank; the CPU arms call this with the cores they may use.
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#endif
+}
 int orc_max_threads() {
 #ifdef _OPENMP
     return omp_get_max_threads();

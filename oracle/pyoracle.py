@@ -39,6 +39,13 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
+def use_all_cores():
+    """All cores this process may run on (torchrun sets OMP_NUM_THREADS=1 in the environment of every rank): returns the count."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().orc_set_threads(C.c_int(n))
+    return lib().orc_max_threads()
+
+
 class Oracle:
     def __init__(self):
         self.l = lib()

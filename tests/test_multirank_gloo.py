@@ -1,6 +1,10 @@
-"""CPU-only, world_size 2 over gloo: the host-side logic of the sharded update (slice plan, gather layout, rendezvous of
-the 128-byte communicator id) with the oracle standing in for the per-rank device work. Checks that the gathered atlases
-equal a single-rank update bit for bit, which is the property the NCCL path relies on."""
+"""CPU-only, world_size 2 over gloo: the host-side logic of the two sharded updates, driven by the sharding arithmetic the
+library itself uses (vkx_shard_slab / vkx_shard_range, exported host-only through the C ABI: csrc/api.cu), with the oracle
+standing in for the per-rank device work.
+  * full-volume update: z-slab per rank, all-gather of contiguous atlas rows and state words;
+  * list update (ProbesPerUpdate scheduling): list positions per rank, all-gather of packed 1296-byte tile records, scatter into
+    the atlases in list order (the layout k_pack_tiles / k_unpack_tiles use).
+Both must reproduce a single-rank update bit for bit, which is the property the NCCL path relies on."""
 import os
 import socket
 import sys
@@ -12,24 +16,46 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+RES, RAYS = (4, 3, 8), 24
 
 
-def test_chunk_plan_partitions_the_volume():
-    from vulkanexp_b200.sharding import chunk_plan, rank_slices
+def test_slab_arithmetic_partitions_the_volume():
+    from vulkanexp_b200._lib import VkxError, shard_slab
 
     for rz in (2, 8, 32, 64, 128, 12):
         for n in (1, 2, 4, 8):
             if rz % n:
-                with pytest.raises(ValueError):
-                    chunk_plan(rz, n)
+                with pytest.raises(VkxError):
+                    shard_slab(rz, n, 0)
                 continue
-            s, K = chunk_plan(rz, n, 2048)
-            assert s * n * K == rz
-            owned = sorted(z for r in range(n) for (a, b) in rank_slices(rz, n, r, 2048) for z in range(a, b))
-            assert owned == list(range(rz))
-            for k in range(K):  # within a chunk, ranks own consecutive equal blocks -> plain all-gather layout
-                blocks = [rank_slices(rz, n, r, 2048)[k] for r in range(n)]
-                assert all(blocks[r][1] == blocks[r + 1][0] for r in range(n - 1)) and len({b - a for a, b in blocks}) == 1
+            slabs = [shard_slab(rz, n, r) for r in range(n)]
+            assert slabs[0][0] == 0 and slabs[-1][1] == rz
+            assert all(slabs[r][1] == slabs[r + 1][0] for r in range(n - 1))  # consecutive: plain all-gather layout
+            assert len({b - a for a, b in slabs}) == 1                          # equal: ncclAllGather takes one count
+    with pytest.raises(VkxError):
+        shard_slab(8, 2, 2)
+
+
+def test_list_range_arithmetic_covers_every_position_once():
+    from vulkanexp_b200._lib import shard_range
+
+    for count in (0, 1, 5, 7, 8, 100, 16384, 131071):
+        for n in (1, 2, 3, 4, 8):
+            per = (count + n - 1) // n
+            seen = []
+            for r in range(n):
+                f, c = shard_range(count, n, r)
+                assert c <= per and (c == per or f + c == count)  # only the tail is short
+                assert f == min(count, r * per)                    # rank r's records start at r * per in the gathered buffer
+                seen.extend(range(f, f + c))
+            assert seen == list(range(count))
+
+
+def _tiles(irr, dep, st, grid, probe):
+    rx, ry, _ = grid.resolution
+    ix, iy, iz = probe % rx, (probe % (rx * ry)) // rx, probe // (rx * ry)
+    t = iy * rx + ix
+    return irr[8 * iz:8 * iz + 8, 8 * t:8 * t + 8], dep[16 * iz:16 * iz + 16, 16 * t:16 * t + 16]
 
 
 def _worker(rank, world, port, out_dir):
@@ -39,9 +65,8 @@ def _worker(rank, world, port, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from oracle import pyoracle
     from vulkanexp_b200 import scene_format, synth
-    from vulkanexp_b200.host_logic import OrientationGenerator
+    from vulkanexp_b200._lib import shard_range, shard_slab
     from vulkanexp_b200.pods import GridInfo, Light
-    from vulkanexp_b200.sharding import chunk_plan, rank_slices
 
     # rendezvous of an opaque 128-byte id, as bench.py does for ncclUniqueId
     uid = [os.urandom(128) if rank == 0 else None]
@@ -51,43 +76,55 @@ def _worker(rank, world, port, out_dir):
     assert len(set(ids)) == 1 and len(ids[0]) == 128
 
     flat = scene_format.flatten(synth.make_open_court(columns=2, col_segments=6, col_stacks=1))
-    grid = GridInfo.make(flat["bounds_min"], flat["bounds_max"], (4, 3, 8), 24, hysteresis=0.0)
+    grid = GridInfo.make(flat["bounds_min"], flat["bounds_max"], RES, RAYS, hysteresis=0.0)
     light = Light.default()
     o = pyoracle.Oracle(); o.scene_upload(flat); o.bvh_build(); o.probes_init(grid)
     o.probes_upload(state=np.ones(grid.probe_count, dtype=np.uint32))
-    gen = OrientationGenerator()
+    host = pyoracle.HostLogic()
     rx, ry, rz = grid.resolution
     plane = rx * ry
-    s, K = chunk_plan(rz, world, 4096)  # small plane value -> 2 chunks in this tiny test
-    for frame in range(3):
-        R = gen.next()
-        grid.hysteresis = 0.4 * frame
-        # every rank holds the previous frame's full sampled atlases; trace + blend own slices only
-        idx = np.array([p for (z0, z1) in rank_slices(rz, world, rank, 4096) for p in range(z0 * plane, z1 * plane)], dtype=np.uint32)
-        o.probes_update(grid, light, R, idx, 1)
-        irr, dep, st, _ = o.probes_download()
-        nirr, ndep, nst = np.zeros_like(irr), np.zeros_like(dep), np.zeros_like(st)
-        for k in range(K):  # per chunk: all-gather of contiguous row blocks
-            z0 = k * s * world
-            for arr, out, rows in ((irr, nirr, 8), (dep, ndep, 16)):
-                mine = torch.from_numpy(arr[rows * (z0 + rank * s) : rows * (z0 + (rank + 1) * s)].astype(np.int64))
-                parts = [torch.zeros_like(mine) for _ in range(world)]
-                dist.all_gather(parts, mine)
-                out[rows * z0 : rows * (z0 + s * world)] = torch.cat(parts).numpy().astype(np.uint32)
-            mine = torch.from_numpy(st[(z0 + rank * s) * plane : (z0 + (rank + 1) * s) * plane].astype(np.int64))
-            parts = [torch.zeros_like(mine) for _ in range(world)]
-            dist.all_gather(parts, mine)
-            nst[z0 * plane : (z0 + s * world) * plane] = torch.cat(parts).numpy().astype(np.uint32)
-        o.probes_upload(nirr, ndep, nst)  # publish = swap to the gathered atlases
+
+    def gather(t):
+        parts = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        return torch.cat(parts)
+
+    for frame in range(4):
+        R, _ = host.next_orientation()
+        grid.hysteresis = 0.3 * frame
+        if frame % 2 == 0:  # ---- full-volume update: own z-slab, all-gather of contiguous rows
+            z0, z1 = shard_slab(rz, world, rank)
+            o.probes_update(grid, light, R, np.arange(z0 * plane, z1 * plane, dtype=np.uint32), 1)
+            irr, dep, st, _ = o.probes_download()
+            nirr = gather(torch.from_numpy(irr[8 * z0:8 * z1].astype(np.int64))).numpy().astype(np.uint32)
+            ndep = gather(torch.from_numpy(dep[16 * z0:16 * z1].astype(np.int64))).numpy().astype(np.uint32)
+            nst = gather(torch.from_numpy(st[z0 * plane:z1 * plane].astype(np.int64))).numpy().astype(np.uint32)
+            o.probes_upload(nirr, ndep, nst)  # publish = swap to the gathered atlases
+        else:  # ---- list update: own list positions, all-gather of packed tile records, scatter in list order
+            lst = np.random.default_rng(100 + frame).permutation(grid.probe_count).astype(np.uint32)[: 37 + frame]
+            count = len(lst)
+            per = (count + world - 1) // world
+            first, mine = shard_range(count, world, rank)
+            o.probes_update(grid, light, R, lst[first:first + mine], 1)
+            irr, dep, st, _ = o.probes_download()
+            rec = np.zeros((per, 81 * 4), dtype=np.int64)  # 64 uint4 depth + 16 uint4 irradiance + (state, index, 0, 0)
+            for j, p in enumerate(lst[first:first + mine]):
+                ti, td = _tiles(irr, dep, st, grid, int(p))
+                rec[j, :256] = td.reshape(-1); rec[j, 256:320] = ti.reshape(-1); rec[j, 320] = st[p]; rec[j, 321] = p
+            allrec = gather(torch.from_numpy(rec)).numpy()
+            for s, p in enumerate(lst):  # list position s = rank s // per, item s % per = record s
+                ti, td = _tiles(irr, dep, st, grid, int(p))
+                td[...] = allrec[s, :256].reshape(16, 16); ti[...] = allrec[s, 256:320].reshape(8, 8); st[p] = allrec[s, 320]
+                assert allrec[s, 321] == p
+            o.probes_upload(irr, dep, st)
     irr, dep, st, _ = o.probes_download()
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), irr=irr, dep=dep, st=st)
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_sharded_update_equals_single_rank(tmp_path, oracle_lib):
+def test_sharded_updates_equal_single_rank(tmp_path, oracle_lib):
     from vulkanexp_b200 import scene_format, synth
-    from vulkanexp_b200.host_logic import OrientationGenerator
     from vulkanexp_b200.pods import GridInfo, Light
 
     with socket.socket() as sk:
@@ -95,13 +132,15 @@ def test_sharded_update_equals_single_rank(tmp_path, oracle_lib):
         port = sk.getsockname()[1]
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     flat = scene_format.flatten(synth.make_open_court(columns=2, col_segments=6, col_stacks=1))
-    grid = GridInfo.make(flat["bounds_min"], flat["bounds_max"], (4, 3, 8), 24, hysteresis=0.0)
+    grid = GridInfo.make(flat["bounds_min"], flat["bounds_max"], RES, RAYS, hysteresis=0.0)
     o = oracle_lib.Oracle(); o.scene_upload(flat); o.bvh_build(); o.probes_init(grid)
     o.probes_upload(state=np.ones(grid.probe_count, dtype=np.uint32))
-    gen = OrientationGenerator()
-    for frame in range(3):
-        grid.hysteresis = 0.4 * frame
-        o.probes_update(grid, Light.default(), gen.next(), None, 1)
+    host = oracle_lib.HostLogic()
+    for frame in range(4):
+        R, _ = host.next_orientation()
+        grid.hysteresis = 0.3 * frame
+        lst = None if frame % 2 == 0 else np.random.default_rng(100 + frame).permutation(grid.probe_count).astype(np.uint32)[: 37 + frame]
+        o.probes_update(grid, Light.default(), R, lst, 1)
     irr, dep, st, _ = o.probes_download()
     for r in range(2):
         z = np.load(os.path.join(tmp_path, "rank%d.npz" % r))

@@ -14,8 +14,9 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 flat = scene_format.flatten(synth.make_open_court())
-res = (8, 6, 8 * world)
-grid = GridInfo.make(flat["bounds_min"], flat["bounds_max"], res, 64)
+res = tuple(int(x) for x in os.environ.get("VKX_CHECK_RES", "8,6,%d" % (8 * world)).split(","))
+RAYS = int(os.environ.get("VKX_CHECK_RAYS", "64"))
+grid = GridInfo.make(flat["bounds_min"], flat["bounds_max"], res, RAYS)
 light = Light.default()
 ctx = Context(local); ctx.scene_upload(flat); ctx.bvh_build(); ctx.probes_init(grid)
 ones = np.ones(grid.probe_count, dtype=np.uint32)
@@ -59,6 +60,21 @@ a, b = ctx.probes_download(), ref.probes_download()
 same = all(np.array_equal(x, y) for x, y in zip(a[:3], b[:3]))
 ok &= same
 print("rank %d: full atlases after the async frames equal: %s" % (rank, same), flush=True)
+# list updates (ProbesPerUpdate scheduling) on all ranks: every rank passes the same list, traces its share, the tiles are exchanged
+# as packed records; must equal the single-GPU list update; alternate with full-volume sharded frames (pending deferred gather)
+if not P2P:
+    rng = np.random.default_rng(5)
+    for frame in range(8, 14):
+        R = gen.next()
+        if frame % 3 == 2:
+            ctx.probes_update_sharded(grid, light, R, sync=False); ref.probes_update(grid, light, R, None)
+        else:
+            lst = rng.permutation(grid.probe_count).astype(np.uint32)[: int(rng.integers(1, grid.probe_count))]
+            ctx.probes_update_sharded_list(grid, light, R, lst, sync=False); ref.probes_update(grid, light, R, lst)
+        a, b = ctx.probes_download(), ref.probes_download()
+        same = all(np.array_equal(x, y) for x, y in zip(a[:3], b[:3]))
+        ok &= same
+        print("rank %d frame %d: sharded %s update == single-GPU: %s" % (rank, frame, "full" if frame % 3 == 2 else "list", same), flush=True)
 t = torch.tensor([0 if ok else 1], device="cuda")
 dist.all_reduce(t)
 dist.destroy_process_group()

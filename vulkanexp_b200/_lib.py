@@ -70,6 +70,24 @@ def image_decode(path):
     return out
 
 
+def shard_slab(rz, nranks, rank):
+    """z-slices [z0, z1) of `rank` in a full-volume sharded update (vkx_shard_slab: the arithmetic vkx_probes_update_sharded uses)."""
+    z0, z1 = C.c_uint32(0), C.c_uint32(0)
+    rc = load().vkx_shard_slab(C.c_uint32(rz), C.c_int(nranks), C.c_int(rank), C.byref(z0), C.byref(z1))
+    if rc != 0:
+        raise VkxError(rc, "vkx_shard_slab(%d, %d, %d)" % (rz, nranks, rank))
+    return z0.value, z1.value
+
+
+def shard_range(count, nranks, rank):
+    """List positions [first, first + n) of `rank` in vkx_probes_update_sharded_list."""
+    f, n = C.c_uint32(0), C.c_uint32(0)
+    rc = load().vkx_shard_range(C.c_uint32(count), C.c_int(nranks), C.c_int(rank), C.byref(f), C.byref(n))
+    if rc != 0:
+        raise VkxError(rc, "vkx_shard_range(%d, %d, %d)" % (count, nranks, rank))
+    return f.value, n.value
+
+
 def host_scene_load(path):
     """The product's own .scene loader + flattening (vkx_host_scene_*; host only): returns the dict Context.scene_upload takes."""
     from .pods import INSTANCE_DTYPE, MATERIAL_DTYPE, OFFSET_DTYPE, Texture
@@ -251,6 +269,18 @@ class Context:
         R = np.ascontiguousarray(R, dtype=np.float32)
         self.grid = grid
         self._check(self.l.vkx_probes_update_sharded(self.h, C.byref(grid), C.byref(light), _p(R), C.c_int(int(sync))))
+
+    def probes_update_sharded_list(self, grid, light, R, indices, sync=True):
+        """Partial update of a to-update list on several GPUs: every rank passes the same list (vkx_probes_update_sharded_list)."""
+        R = np.ascontiguousarray(R, dtype=np.float32)
+        indices = np.ascontiguousarray(indices, dtype=np.uint32)
+        self.grid = grid
+        self.count = len(indices)
+        self._check(self.l.vkx_probes_update_sharded_list(self.h, C.byref(grid), C.byref(light), _p(R), _p(indices), C.c_uint32(len(indices)), C.c_int(int(sync))))
+
+    def stream_wait_exchange(self):
+        """Orders the context's stream after a pending atlas exchange; an event recorded afterwards covers the all-gather."""
+        self._check(self.l.vkx_stream_wait_exchange(self.h))
 
     def probes_download(self, rays=False, out=None):
         (ih, iw), (dh, dw) = self.grid.atlas_shapes()

@@ -760,8 +760,9 @@ int vkx_probes_update_sharded(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx
     // One chunk per frame: the all-gather of frame f is not waited for at the end of the update but before the first kernel of frame
     // f+1 that reads the sampled atlases (k_shade_front), so it overlaps frame f+1's primary traversal, which never touches them.
     // (Measured on 4 GPUs: splitting the slab into chunks to overlap inside the frame cost more in small launches than it hid.)
-    const uint32_t slicesPerRank = rz / n;
-    const uint32_t K = 1, s = slicesPerRank / K;
+    uint32_t slab0 = 0, slab1 = 0;
+    if (vkx_shard_slab(rz, ctx->nranks, ctx->rank, &slab0, &slab1) != VKX_OK) return vkx_fail(ctx, VKX_E_INVALID, "vkx_shard_slab");
+    const uint32_t K = 1, s = slab1 - slab0; // slices per rank
     ncclComm_t comm = reinterpret_cast<ncclComm_t>(ctx->comm);
     cudaStream_t st = ctx->stream, cs = ctx->commStream;
     const bool p2p = ctx->p2p;
@@ -777,7 +778,7 @@ int vkx_probes_update_sharded(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], st));
     uint32_t total = 0;
     for (uint32_t k = 0; k < K; ++k) {
-        const uint32_t z0 = k * s * n + uint32_t(ctx->rank) * s;
+        const uint32_t z0 = k * s * n + slab0; // K = 1: the rank's slab
         const uint32_t first = z0 * plane, count = s * plane;
         k_iota_list<<<divUp(count, 256), 256, 0, st>>>(ctx->dIndicesList + total, first, count); LAUNCH_CHECK(ctx);
         if (!ctx->shardOrderReady) { std::vector<uint32_t> idx(count); for (uint32_t i = 0; i < count; ++i) idx[i] = first + i; TRY(uploadOrder(ctx, idx.data(), count, total, false)); }
@@ -810,6 +811,71 @@ int vkx_probes_update_sharded(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx
     // publish = swap; the work buffers keep this rank's slices current (they are the only ones it reads as `previous`)
     std::swap(ctx->dIrrSampled, ctx->dIrrNext); std::swap(ctx->dDepSampled, ctx->dDepNext); std::swap(ctx->dStateSampled, ctx->dStateNext);
     ctx->lastCount = total; ctx->lastRays = total * ctx->grid.raysPerProbe; ctx->shardedLast = true;
+    if (sync) CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return VKX_OK;
+}
+
+
+int vkx_shard_slab(uint32_t rz, int nranks, int rank, uint32_t* z0, uint32_t* z1) {
+    if (nranks < 1 || rank < 0 || rank >= nranks || !z0 || !z1 || rz % uint32_t(nranks) != 0u) return VKX_E_INVALID;
+    const uint32_t s = rz / uint32_t(nranks);
+    *z0 = uint32_t(rank) * s; *z1 = uint32_t(rank + 1) * s;
+    return VKX_OK;
+}
+int vkx_shard_range(uint32_t count, int nranks, int rank, uint32_t* first, uint32_t* n) {
+    if (nranks < 1 || rank < 0 || rank >= nranks || !first || !n) return VKX_E_INVALID;
+    const uint32_t per = (count + uint32_t(nranks) - 1u) / uint32_t(nranks); // every rank's share is `per` list positions, the tail ranks get what is left
+    const uint32_t f = std::min(count, uint32_t(rank) * per);
+    *first = f; *n = std::min(per, count - f);
+    return VKX_OK;
+}
+int vkx_stream_wait_exchange(vkx_ctx* ctx) { BIND(ctx); return waitGather(ctx); }
+
+int vkx_probes_update_sharded_list(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx_light* light, const float orientation[16], const uint32_t* probeIndices, uint32_t count, int sync) {
+    BIND(ctx);
+    if (ctx->nranks == 1 || !ctx->comm) return vkx_probes_update(ctx, grid, light, orientation, probeIndices, count, sync);
+    if (!ctx->probesReady || !ctx->bvhBuilt) return vkx_fail(ctx, VKX_E_INVALID, "vkx_probes_update_sharded_list: probes or BVH not ready");
+    if (!light || !orientation || (!probeIndices && count)) return vkx_fail(ctx, VKX_E_INVALID, "null light/orientation/list");
+    if (ctx->p2p) return vkx_fail(ctx, VKX_E_INVALID, "vkx_probes_update_sharded_list uses the NCCL exchange; disable the peer-memory exchange first (vkx_comm_p2p_import(NULL, 0))");
+    if (count > ctx->probeCount) return vkx_fail(ctx, VKX_E_INVALID, "more indices than probes");
+    for (uint32_t i = 0; i < count; ++i) if (probeIndices[i] >= ctx->probeCount) return vkx_fail(ctx, VKX_E_INVALID, "probe index %u out of range", probeIndices[i]);
+    TRY(waitGather(ctx)); // a pending full-volume exchange writes the sampled set this update patches
+    TRY(uploadFrameInputs(ctx, grid, orientation));
+    ctx->hLastList.clear(); ctx->shardOrderReady = false;
+    cudaStream_t st = ctx->stream, cs = ctx->commStream;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], st));
+    if (count == 0) { CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], st)); ctx->lastCount = 0; ctx->lastRays = 0; ctx->shardedLast = true; return VKX_OK; }
+    const uint32_t n = uint32_t(ctx->nranks), per = (count + n - 1u) / n;
+    uint32_t first = 0, mine = 0;
+    vkx_shard_range(count, ctx->nranks, ctx->rank, &first, &mine);
+    const size_t need = size_t(per) * n;
+    if (!ctx->dShardList) CUDA_TRY(ctx, cudaMalloc(&ctx->dShardList, size_t(ctx->probeCount) * 4));
+    if (need > ctx->packCapacity) {
+        CUDA_TRY(ctx, cudaStreamSynchronize(st)); CUDA_TRY(ctx, cudaStreamSynchronize(cs));
+        if (ctx->dPackSend) cudaFree(ctx->dPackSend); if (ctx->dPackRecv) cudaFree(ctx->dPackRecv);
+        ctx->dPackSend = ctx->dPackRecv = nullptr; ctx->packCapacity = 0;
+        CUDA_TRY(ctx, cudaMalloc(&ctx->dPackSend, size_t(per) * 81 * sizeof(uint4)));
+        CUDA_TRY(ctx, cudaMalloc(&ctx->dPackRecv, need * 81 * sizeof(uint4)));
+        ctx->packCapacity = need;
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dShardList, probeIndices, size_t(count) * 4, cudaMemcpyHostToDevice, st)); // pageable source: returns after staging
+    if (mine) {
+        TRY(uploadOrder(ctx, probeIndices + first, mine, first, true));
+        TRY(ddgiUpdate(ctx, *light, nullptr, mine, first, false));
+    }
+    TRY(ddgiPackTiles(ctx, ctx->dIndicesList + first, mine, ctx->dPackSend, st));
+    if (ctx->copyPending) { CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->evCopyDone, 0)); ctx->copyPending = false; ctx->copyReadsWork = false; } // a queued read-back still reads the atlases about to be patched
+    CUDA_TRY(ctx, cudaEventRecord(ctx->commEvent, st));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ctx->commEvent, 0));
+    ncclResult_t r = ncclAllGather(ctx->dPackSend, ctx->dPackRecv, size_t(per) * 81 * 4, ncclUint32, reinterpret_cast<ncclComm_t>(ctx->comm), cs);
+    if (r != ncclSuccess) return vkx_fail(ctx, VKX_E_NCCL, "ncclAllGather: %s", ncclGetErrorString(r));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->gatherDone, cs));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->gatherDone, 0));
+    // rank r's records sit at [r * per, r * per + its share): exactly list order, because every full share is `per` long
+    TRY(ddgiUnpackTiles(ctx, ctx->dShardList, count, per, ctx->dPackRecv, st));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], st));
+    if (ctx->evPublished) CUDA_TRY(ctx, cudaEventRecord(ctx->evPublished, st));
+    ctx->lastCount = mine; ctx->lastRays = mine * ctx->grid.raysPerProbe; ctx->shardedLast = true;
     if (sync) CUDA_TRY(ctx, cudaStreamSynchronize(st));
     return VKX_OK;
 }

@@ -127,6 +127,7 @@ struct vkx_ctx {
     ncclComm* comm = nullptr; int rank = 0, nranks = 1;
     cudaStream_t commStream = nullptr; cudaEvent_t commEvent = nullptr, gatherDone = nullptr; bool gatherPending = false;
     uint32_t *dIrrNext = nullptr, *dDepNext = nullptr, *dStateNext = nullptr; // all-gather targets (sharded update)
+    uint32_t* dShardList = nullptr; uint4 *dPackSend = nullptr, *dPackRecv = nullptr; size_t packCapacity = 0; // sharded list update: whole list, packed tiles (81 uint4 per probe)
     // peer-memory exchange (vkx_comm_p2p_export / _import): one slab per rank = atlas set 0 | atlas set 1 | arrival flags | error word,
     // mapped into every peer through CUDA IPC; sampled / next point into the slab
     bool p2p = false, p2pPending = false, blendToPeers = false;
@@ -178,6 +179,8 @@ int launchP2pSignal(vkx_ctx* ctx); // ddgi.cu
 int ddgiClassify(vkx_ctx* ctx, const float* dirs512);
 int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* hostIndices, uint32_t count, uint32_t firstProbe, bool publishAll);
 int ddgiPublish(vkx_ctx* ctx, uint32_t count);
+int ddgiPackTiles(vkx_ctx* ctx, const uint32_t* probeIndices, uint32_t count, uint4* packed, cudaStream_t st);                      // work atlases -> packed records
+int ddgiUnpackTiles(vkx_ctx* ctx, const uint32_t* probeIndices, uint32_t count, uint32_t perRank, const uint4* packed, cudaStream_t st); // records of every rank -> work + sampled atlases
 // ---- trace_api.cu (alphaTest: run anyhit.rahit's cut-out test on the candidates)
 int traceHostRays(vkx_ctx* ctx, const float* origins, const float* directions, size_t n, float tmin, float tmax, uint32_t cullMask, int anyHit, vkx_hit* out, bool alphaTest);
 void freeTextures(vkx_ctx* ctx); // texture.cu

@@ -383,6 +383,43 @@ __global__ void k_publish(DeviceProbes pr, uint32_t* __restrict__ irrSampled, ui
     if (lane == 0) stateSampled[linearIndex] = pr.stateWork[linearIndex];
 }
 
+// Sharded list update: the tiles of an updated probe as one 1296-byte record (64 uint4 depth rows, 16 uint4 irradiance rows, state),
+// so that ranks can exchange the probes they updated with one all-gather. One warp per probe, like k_publish.
+#define VKX_TILE_RECORD 81u // uint4 per probe
+__global__ void k_pack_tiles(DeviceProbes pr, const uint32_t* __restrict__ probeIndices, uint32_t count, uint4* __restrict__ packed) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (warp >= count) return;
+    const uint32_t linearIndex = __ldg(probeIndices + warp);
+    int ix, iy, iz; probeGridIndex(linearIndex, pr.grid, ix, iy, iz);
+    const int tile = iy * pr.grid.resolution[0] + ix;
+    uint4* rec = packed + size_t(warp) * VKX_TILE_RECORD;
+    for (int k = int(lane); k < 64; k += 32) rec[k] = *reinterpret_cast<const uint4*>(pr.depWork + size_t(16 * iz + (k >> 2)) * pr.depW + size_t(16 * tile + (k & 3) * 4));
+    if (lane < 16) rec[64 + lane] = *reinterpret_cast<const uint4*>(pr.irrWork + size_t(8 * iz + int(lane >> 1)) * pr.irrW + size_t(8 * tile + int(lane & 1) * 4));
+    if (lane == 16) rec[80] = make_uint4(pr.stateWork[linearIndex], linearIndex, 0u, 0u);
+}
+// List position s was processed by rank s / perRank as its item s % perRank; its record goes to the work and the sampled set.
+__global__ void k_unpack_tiles(DeviceProbes pr, uint32_t* __restrict__ irrSampled, uint32_t* __restrict__ depSampled, uint32_t* __restrict__ stateSampled,
+                               const uint32_t* __restrict__ probeIndices, uint32_t count, uint32_t perRank, const uint4* __restrict__ packed) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (warp >= count) return;
+    const uint32_t linearIndex = __ldg(probeIndices + warp);
+    int ix, iy, iz; probeGridIndex(linearIndex, pr.grid, ix, iy, iz);
+    const int tile = iy * pr.grid.resolution[0] + ix;
+    const uint4* rec = packed + size_t(warp) * VKX_TILE_RECORD; // records are stored rank after rank with perRank slots each = list order
+    (void)perRank;
+    for (int k = int(lane); k < 64; k += 32) {
+        const size_t off = size_t(16 * iz + (k >> 2)) * pr.depW + size_t(16 * tile + (k & 3) * 4);
+        const uint4 v = rec[k];
+        *reinterpret_cast<uint4*>(pr.depWork + off) = v; *reinterpret_cast<uint4*>(depSampled + off) = v;
+    }
+    if (lane < 16) {
+        const size_t off = size_t(8 * iz + int(lane >> 1)) * pr.irrW + size_t(8 * tile + int(lane & 1) * 4);
+        const uint4 v = rec[64 + lane];
+        *reinterpret_cast<uint4*>(pr.irrWork + off) = v; *reinterpret_cast<uint4*>(irrSampled + off) = v;
+    }
+    if (lane == 16) { const uint32_t st = rec[80].x; pr.stateWork[linearIndex] = st; stateSampled[linearIndex] = st; }
+}
+
 // ------------------------------------------------------------------------------------------------ classification
 // probesInit.rgen:31-64 + backfaceTest.rchit + probeInitMiss.rmiss. One CTA of 128 threads per probe, 4 rays each.
 __global__ void __launch_bounds__(128) k_classify(DeviceScene sc, vkx_grid_info grid, const float4* __restrict__ dirs512, uint32_t* __restrict__ stateWork,
@@ -553,5 +590,14 @@ int ddgiPublish(vkx_ctx* ctx, uint32_t count) {
     const DeviceProbes pr = deviceProbes(ctx);
     if (count) { k_publish<<<divUp(size_t(count) * 32, 256), 256, 0, st>>>(pr, ctx->dIrrSampled, ctx->dDepSampled, ctx->dStateSampled, ctx->dIndicesList, count); LAUNCH_CHECK(ctx); }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], st));
+    return VKX_OK;
+}
+
+int ddgiPackTiles(vkx_ctx* ctx, const uint32_t* probeIndices, uint32_t count, uint4* packed, cudaStream_t st) {
+    if (count) { k_pack_tiles<<<divUp(size_t(count) * 32, 256), 256, 0, st>>>(deviceProbes(ctx), probeIndices, count, packed); LAUNCH_CHECK(ctx); }
+    return VKX_OK;
+}
+int ddgiUnpackTiles(vkx_ctx* ctx, const uint32_t* probeIndices, uint32_t count, uint32_t perRank, const uint4* packed, cudaStream_t st) {
+    if (count) { k_unpack_tiles<<<divUp(size_t(count) * 32, 256), 256, 0, st>>>(deviceProbes(ctx), ctx->dIrrSampled, ctx->dDepSampled, ctx->dStateSampled, probeIndices, count, perRank, packed); LAUNCH_CHECK(ctx); }
     return VKX_OK;
 }
