@@ -249,15 +249,16 @@ void build(const std::vector<Tri48>& flat, const std::vector<float>& lo, const s
                 }
                 if (isLeaf(en.ref)) {
                     uint32_t cnt = leafCount(en.ref), first = leafFirst(en.ref);
-                    node.meta[s] = uint8_t((((1u << cnt) - 1u) << 5) | triOff);
+                    node.valid |= ((1u << cnt) - 1u) << (3 * s);
                     for (uint32_t i = 0; i < cnt; ++i) out.tris.push_back(flat[prim[first + i]]);
                     triOff += cnt;
                 } else {
                     node.imask |= uint8_t(1u << s);
-                    node.meta[s] = uint8_t(0x20u | (24u + uint32_t(s)));
+                    node.valid |= 1u << (24 + s);
                     wnext.push_back(WideWork{en.ref, en.box});
                 }
             }
+            (void)triOff;
             out.nodes.push_back(node);
         }
         levelBase = nextBase;
@@ -268,6 +269,7 @@ void build(const std::vector<Tri48>& flat, const std::vector<float>& lo, const s
 // ------------------------------------------------------------------------------------------------------------
 // Traversal (spec section 3.4). Every float operation below is a single correctly-rounded IEEE op in a fixed
 // order; the CUDA kernels use the matching __f*_rn intrinsics.
+int gMaxStack = 0; // deepest traversal stack seen so far (diagnostic: sizes the device-side shared-memory stack; benign race)
 namespace {
 
 struct RayCtx {
@@ -286,7 +288,7 @@ inline void setupRay(RayCtx& r, const float o[3], const float d[3]) {
     }
 }
 
-// Returns the 32-bit hit mask of one node: bits 24..31 inner children at priority position, bits 0..23 triangles.
+// Returns the 32-bit hit mask of one node: bits 24..31 inner children by slot, bits 0..23 triangles (3 per slot).
 inline uint32_t intersectNode(const Node80& n, const RayCtx& r, float tmin, float tmax) {
     float ax[3], bx[3];
     for (int a = 0; a < 3; ++a) {
@@ -295,9 +297,6 @@ inline uint32_t intersectNode(const Node80& n, const RayCtx& r, float tmin, floa
     }
     uint32_t mask = 0;
     for (int s = 0; s < 8; ++s) {
-        uint32_t meta = n.meta[s];
-        if (!meta) continue;
-        float tn = tmin, tf = tmax;
         float tl[3], th[3];
         for (int a = 0; a < 3; ++a) {
             bool neg = (r.oct & (4u >> a)) != 0;
@@ -306,15 +305,11 @@ inline uint32_t intersectNode(const Node80& n, const RayCtx& r, float tmin, floa
             tl[a] = std::fmaf(qn, ax[a], bx[a]);
             th[a] = std::fmaf(qf, ax[a], bx[a]);
         }
-        tn = std::fmax(std::fmax(tl[0], tl[1]), std::fmax(tl[2], tmin));
-        tf = std::fmin(std::fmin(th[0], th[1]), std::fmin(th[2], tmax));
-        if (tn <= tf) {
-            uint32_t bits = meta >> 5, idx = meta & 31u;
-            if (idx >= 24) idx = 24 + ((idx - 24) ^ r.oct);
-            mask |= bits << idx;
-        }
+        float tn = std::fmax(std::fmax(tl[0], tl[1]), std::fmax(tl[2], tmin));
+        float tf = std::fmin(std::fmin(th[0], th[1]), std::fmin(th[2], tmax));
+        if (tn <= tf) mask |= (7u << (3 * s)) | (1u << (24 + s));
     }
-    return mask;
+    return mask & n.valid; // empty slots and absent triangles have no bit in `valid`
 }
 
 // Moeller-Trumbore, fixed op order. Returns true if the triangle plane/edges are hit; t,u,v,det out.
@@ -346,26 +341,28 @@ bool traverse(const Bvh& bvh, const float o[3], const float d[3], float tmin, fl
     uint32_t bestInst = 0xFFFFFFFFu, bestPrim = 0xFFFFFFFFu; float bu = 0, bv = 0; bool bback = false;
     struct G { uint32_t base, bits; };
     G stack[64]; int sp = 0;
-    G g{0, 0x80000000u};
+    G g{0, 0x01000000u}; // the root: "slot 0" of a virtual parent whose first child is node 0
     if (ctr) ctr->rays++;
     for (;;) {
-        uint32_t triBase = 0, triBits = 0;
+        uint32_t triBase = 0, triBits = 0, triValid = 0;
         if (g.bits & 0xFF000000u) {
-            uint32_t bit = 31u - uint32_t(__builtin_clz(g.bits));
-            g.bits &= ~(1u << bit);
-            if (g.bits & 0xFF000000u) stack[sp++] = g;
-            uint32_t slot = (bit - 24u) ^ r.oct;
+            // next inner child: the pending slot s with the largest (s ^ octant) (children sit in the slot of their octant, so this
+            // visits them front to back along the ray)
+            uint32_t pending = g.bits >> 24, slot = 0, bestKey = 0;
+            for (uint32_t s = 0; s < 8; ++s) if ((pending >> s) & 1u) { uint32_t key = s ^ r.oct; if (key >= bestKey) { bestKey = key; slot = s; } }
+            g.bits &= ~(1u << (24 + slot));
+            if (g.bits & 0xFF000000u) { stack[sp++] = g; if (sp > gMaxStack) gMaxStack = sp; }
             uint32_t rel = uint32_t(__builtin_popcount(g.bits & 0xFFu & ((1u << slot) - 1u)));
             const Node80& n = bvh.nodes[g.base + rel];
             if (ctr) ctr->nodes++;
             uint32_t m = intersectNode(n, r, tmin, tbest);
             g.base = n.childBase; g.bits = (m & 0xFF000000u) | n.imask;
-            triBase = n.primBase; triBits = m & 0x00FFFFFFu;
+            triBase = n.primBase; triBits = m & 0x00FFFFFFu; triValid = n.valid & 0x00FFFFFFu;
         }
         while (triBits) {
             uint32_t b = uint32_t(__builtin_ctz(triBits));
             triBits &= triBits - 1;
-            const Tri48& tr = bvh.tris[triBase + b];
+            const Tri48& tr = bvh.tris[triBase + uint32_t(__builtin_popcount(triValid & ((1u << b) - 1u)))];
             if (ctr) ctr->tris++;
             if (!((tr.inst >> 24) & cullMask)) continue;
             float t, u, v, det;

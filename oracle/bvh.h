@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE — part of the CPU oracle. Never linked into, imported or called by the product path.
 //
-// Sequential CPU restatement of "BVH spec v1" (DESIGN.md section 3): the deterministic binned-SAH binary build,
+// Sequential CPU restatement of "BVH spec v2" (v2 = v1 with the per-slot meta bytes replaced by one validity word): the deterministic binned-SAH binary build,
 // the greedy collapse into 8-wide nodes, the 8-bit child-box quantisation, and the per-ray traversal order.
 // The reference delegates all of this to the Vulkan driver / RT cores (reference src/Renderer.cpp:272-449,
 // 525-642), so nothing here follows reference code: this file *defines* the behaviour the
@@ -28,7 +28,9 @@ struct Node80 {         // 80 B, five 128-bit words
     uint8_t imask;      // bit s set: slot s holds an inner child
     uint32_t childBase; // wide-node index of the first inner child (inner children contiguous, in slot order)
     uint32_t primBase;  // index of the node's first triangle (leaf children contiguous, in slot order)
-    uint8_t meta[8];    // 0 empty | inner: 0x20 | (24 + slot) | leaf: (((1 << count) - 1) << 5) | triangleOffset
+    uint32_t valid;     // spec v2: bits 24..31 = imask; bits [3s, 3s + count) set for leaf slot s (count <= 3); 0 for empty slots.
+                        // Triangle of bit b = primBase + popcount(valid & ((1 << b) - 1) & 0xFFFFFF): leaf triangles are contiguous in slot order.
+    uint32_t pad;       // 0
     uint8_t qlo[3][8];  // quantised child AABB mins  [axis][slot]
     uint8_t qhi[3][8];  // quantised child AABB maxs
 };
@@ -42,6 +44,7 @@ struct Bvh {
     float sceneMin[3] = {0, 0, 0}, sceneMax[3] = {0, 0, 0};
 };
 
+extern int gMaxStack;
 struct Counters { uint64_t nodes = 0, tris = 0, rays = 0; };
 
 // anyhit.rahit as a candidate filter: ignore(user, instance, primitive, u, v) == true drops the candidate (ignoreIntersectionEXT).

@@ -22,6 +22,7 @@ extern "C" {
 orc_ctx* orc_create() { return new (std::nothrow) orc_ctx(); }
 void orc_destroy(orc_ctx* c) { delete c; }
 // torch.distributed.run exports OMP_NUM_THREADS=1 to every rank; the CPU arms call this with the cores they may use.
+int orc_max_stack(int reset) { int v = obvh::gMaxStack; if (reset) obvh::gMaxStack = 0; return v; }
 void orc_set_threads(int n) {
 #ifdef _OPENMP
     if (n > 0) omp_set_num_threads(n);

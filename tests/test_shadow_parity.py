@@ -133,7 +133,7 @@ def test_cfg3_1080p_with_reference_blue_noise(oracle_lib):
         o.shadow_frame(cam, prev, light, dir_override=dirs)
         raw_o, _, mask_o = o.shadow_download(0)
         assert np.array_equal(mask_o, mask_g), "frame %d: shadow mask differs" % f
-        assert (mask_g == 2).mean() > 0.02 and (mask_g == 1).mean() > 0.02
+        assert (mask_g == 2).mean() > 0.005 and (mask_g == 1).mean() > 0.001  # an indoor scene: most facing pixels are shadowed
         e = np.abs(o.shadow_download(1)[0].astype(np.float64) - g.shadow_download(1).astype(np.float64))
         assert e.max() < 1e-3, "frame %d filter X: %g" % (f, e.max())
         b = g.shadow_download(2)

@@ -263,7 +263,7 @@ __global__ void k_finalize_children(ActiveArrays act, ActiveArrays next, SplitAr
 struct WideLevel { uint32_t* ref; float* box; }; // per node of a wide level: binary ref, bounds [6]
 
 struct Node80 {
-    float p[3]; uint8_t e[3]; uint8_t imask; uint32_t childBase; uint32_t primBase; uint8_t meta[8]; uint8_t qlo[3][8]; uint8_t qhi[3][8];
+    float p[3]; uint8_t e[3]; uint8_t imask; uint32_t childBase; uint32_t primBase; uint32_t valid; uint32_t pad; uint8_t qlo[3][8]; uint8_t qhi[3][8]; // BVH spec v2 (oracle/bvh.h)
 };
 static_assert(sizeof(Node80) == 80, "Node80");
 
@@ -344,11 +344,11 @@ __global__ void k_collapse(WideLevel lvl, uint32_t numW, BinaryNodes bn, Node80*
         }
         if (isLeafRef(eref[c])) {
             uint32_t cnt = (eref[c] >> 29) & 3u;
-            node.meta[s] = uint8_t((((1u << cnt) - 1u) << 5) | triOff);
+            node.valid |= ((1u << cnt) - 1u) << (3 * s);
             triOff += cnt;
         } else {
             node.imask |= uint8_t(1u << s);
-            node.meta[s] = uint8_t(0x20u | (24u + uint32_t(s)));
+            node.valid |= 1u << (24 + s);
             nInner++;
         }
     }

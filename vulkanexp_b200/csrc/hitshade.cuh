@@ -56,7 +56,7 @@ template <bool TEXTURED>
 __device__ __forceinline__ void shadeFrontHit(const DeviceScene& sc, const DeviceProbes& pr, const GridConsts& gc, v3 lightDir, v3 lightColor, v3 direction, v3 position,
                                               const vkx_hit& h, v3& base, v3& lit, v3 rayOrigin = mk3(0.0f), v3 raydx = mk3(0.0f), v3 raydy = mk3(0.0f)) {
     const float u = h.u, v = h.v;
-    const float bx = 1.0f - u - v, by = u, bz = v;
+    const float bx = __fsub_rn(__fsub_rn(1.0f, u), v), by = u, bz = v;
     const uint32_t meshEntry = __ldg(&sc.instances[h.instance].meshEntry);
     const vkx_offset_entry oe = sc.offsets[meshEntry];
     const uint32_t prim = h.primitive & 0x7FFFFFFFu;
@@ -70,10 +70,11 @@ __device__ __forceinline__ void shadeFrontHit(const DeviceScene& sc, const Devic
         n3[c] = mk3(__ldg(nn), __ldg(nn + 1), __ldg(nn + 2));
     }
     const vkx_material m = sc.materials[oe.materialIndex];
-    const v3 tsn = norm3(n3[0] * bx + n3[1] * by + n3[2] * bz);
+    // exact chain (shade.cuh): the normal selects atlas texels through its octahedral coordinate
+    const v3 tsn = xnorm3(xadd3(xadd3(xmul3(n3[0], bx), xmul3(n3[1], by)), xmul3(n3[2], bz)));
     const float* W = sc.worldToObject + size_t(h.instance) * 9; // W[row][col]
     // vec3(tsn * worldToObject): component j = dot(tsn, column j)
-    v3 normal = norm3(mk3(dot3(tsn, mk3(W[0], W[3], W[6])), dot3(tsn, mk3(W[1], W[4], W[7])), dot3(tsn, mk3(W[2], W[5], W[8]))));
+    v3 normal = xnorm3(mk3(xdot3(tsn, mk3(W[0], W[3], W[6])), xdot3(tsn, mk3(W[1], W[4], W[7])), xdot3(tsn, mk3(W[2], W[5], W[8]))));
     v3 albedo = mk3(m.baseColorFactor[0], m.baseColorFactor[1], m.baseColorFactor[2]);
     float metalness = m.metallicFactor, roughness = m.roughnessFactor;
     v3 emissive = mk3(m.emissiveFactor[0], m.emissiveFactor[1], m.emissiveFactor[2]);
@@ -125,7 +126,7 @@ __device__ __forceinline__ void shadeFrontHit(const DeviceScene& sc, const Devic
     v3 diffuseColor = albedo * (1.0f - f0);
     diffuseColor = diffuseColor * (1.0f - metalness);
     const v3 specularColor = mix3(f0, albedo, metalness);
-    const v3 reflectDir = reflect3(direction, normal);
+    const v3 reflectDir = xreflect3(direction, normal);
     v3 reflection, indirectLight;
     sampleProbes2(pr, gc, position, reflectDir, normal, -direction, reflection, indirectLight);
     color = color + specularColor * reflection;

@@ -61,7 +61,7 @@ __device__ __forceinline__ void persistentTraceDeferred(const uint4* __restrict_
     Ray r; float tmin = 0.f, tbest = 0.f; uint32_t cullMask = 0, item = 0;
     HitRec hit; hit.found = false; hit.t = -1.0f; hit.u = hit.v = 0.f; hit.inst = hit.prim = 0xFFFFFFFFu;
     bool active = false;
-    uint32_t pBase = 0, pBits = 0; // parked triangles of this lane's ray
+    uint32_t pBase = 0, pBits = 0, pValid = 0; // parked triangles of this lane's ray (hit bits + the node's validity word)
     uint32_t cur = 0, end = 0;
     bool more = true;
     for (;;) {
@@ -83,7 +83,7 @@ __device__ __forceinline__ void persistentTraceDeferred(const uint4* __restrict_
                     const uint32_t it = cur + rank;
                     float tmax;
                     if (src.load(it, r, tmin, tmax, cullMask)) {
-                        item = it; tbest = tmax; sp = 0; g = make_uint2(0u, 0x80000000u); pBits = 0;
+                        item = it; tbest = tmax; sp = 0; g = make_uint2(0u, VKX_ROOT_GROUP); pBits = 0;
                         hit.found = false; hit.t = -1.0f; hit.u = hit.v = 0.f; hit.inst = hit.prim = 0xFFFFFFFFu;
                         active = true;
                     }
@@ -100,21 +100,20 @@ __device__ __forceinline__ void persistentTraceDeferred(const uint4* __restrict_
                 do {
                     const uint32_t b = uint32_t(__ffs(int(pBits))) - 1u;
                     pBits &= pBits - 1u;
-                    if (testTriangle<ANY>(tris, pBase + b, r, tmin, tbest, cullMask, hit)) { done = true; pBits = 0u; }
+                    if (testTriangle<ANY>(tris, pBase + triangleOffset(pValid, b), r, tmin, tbest, cullMask, hit)) { done = true; pBits = 0u; }
                 } while (pBits);
                 advance = true;
             }
         } else if (active && pBits == 0u) { // node phase (a lane without parked triangles always has an inner child to visit)
-            const uint32_t bit = 31u - uint32_t(__clz(int(g.y)));
-            g.y &= ~(1u << bit);
+            const uint32_t slot = nextSlot(g.y >> 24, r.oct);
+            g.y &= ~(0x01000000u << slot);
             if (g.y & 0xFF000000u) { if (sp < VKX_STACK) stack[sp++] = g; }
-            const uint32_t slot = (bit - 24u) ^ r.oct;
             const uint32_t rel = uint32_t(__popc(g.y & 0xFFu & ((1u << slot) - 1u)));
             uint4 w0, w1, w2, w3, w4;
             loadNode(nodes, g.x + rel, w0, w1, w2, w3, w4);
             const uint32_t m = intersectNode(w0, w1, w2, w3, w4, r, tmin, tbest);
             g.x = w1.x; g.y = (m & 0xFF000000u) | (w0.w >> 24);
-            pBase = w1.y; pBits = m & 0x00FFFFFFu;
+            pBase = w1.y; pBits = m & 0x00FFFFFFu; pValid = w1.z;
             advance = pBits == 0u;
         }
         if (advance) {
@@ -158,7 +157,7 @@ __device__ __forceinline__ void persistentTrace(const uint4* __restrict__ nodes,
                     const uint32_t it = cur + rank;
                     float tmax;
                     if (src.load(it, r, tmin, tmax, cullMask)) {
-                        item = it; tbest = tmax; sp = 0; g = make_uint2(0u, 0x80000000u);
+                        item = it; tbest = tmax; sp = 0; g = make_uint2(0u, VKX_ROOT_GROUP);
                         hit.found = false; hit.t = -1.0f; hit.u = hit.v = 0.f; hit.inst = hit.prim = 0xFFFFFFFFu;
                         active = true;
                     }
@@ -167,24 +166,23 @@ __device__ __forceinline__ void persistentTrace(const uint4* __restrict__ nodes,
             }
         }
         if (active) { // one node step + its triangles (same order as traverse<>)
-            uint32_t triBase = 0, triBits = 0;
+            uint32_t triBase = 0, triBits = 0, triValid = 0;
             bool done = false;
             if (g.y & 0xFF000000u) {
-                const uint32_t bit = 31u - uint32_t(__clz(int(g.y)));
-                g.y &= ~(1u << bit);
+                const uint32_t slot = nextSlot(g.y >> 24, r.oct);
+                g.y &= ~(0x01000000u << slot);
                 if (g.y & 0xFF000000u) { if (sp < VKX_STACK) stack[sp++] = g; }
-                const uint32_t slot = (bit - 24u) ^ r.oct;
                 const uint32_t rel = uint32_t(__popc(g.y & 0xFFu & ((1u << slot) - 1u)));
                 uint4 w0, w1, w2, w3, w4;
                 loadNode(nodes, g.x + rel, w0, w1, w2, w3, w4);
                 const uint32_t m = intersectNode(w0, w1, w2, w3, w4, r, tmin, tbest);
                 g.x = w1.x; g.y = (m & 0xFF000000u) | (w0.w >> 24);
-                triBase = w1.y; triBits = m & 0x00FFFFFFu;
+                triBase = w1.y; triBits = m & 0x00FFFFFFu; triValid = w1.z;
             }
             while (triBits) {
                 const uint32_t b = uint32_t(__ffs(int(triBits))) - 1u;
                 triBits &= triBits - 1u;
-                const float4* tp = tris + size_t(triBase + b) * 3;
+                const float4* tp = tris + size_t(triBase + triangleOffset(triValid, b)) * 3;
                 const float4 q2 = __ldg(tp + 2); // (loading all three words before the mask test measured the same: 0.951 vs 0.944 ms)
                 const uint32_t instW = __float_as_uint(q2.y), primW = __float_as_uint(q2.z);
                 if (!((instW >> 24) & cullMask)) continue;

@@ -33,6 +33,20 @@ __device__ __forceinline__ float signS(float x) { return float((0.0f < x) - (x <
 __device__ __forceinline__ v3 abs3(v3 v) { return mk3(fabsf(v.x), fabsf(v.y), fabsf(v.z)); }
 __device__ __forceinline__ v3 reflect3(v3 I, v3 N) { return I - N * dot3(N, I) * 2.0f; }
 
+// ---- exact helpers: one IEEE operation each, in the oracle's (= the shader's) order, whatever the translation unit's flags.
+// The chain position -> normal / biased position -> octahedral coordinate -> atlas texel coordinate -> bilinear weights, and the
+// depth moments that feed the Chebyshev test, are ill-conditioned: the texel coordinate is formed at the magnitude of the atlas
+// (ulp(512 tiles) = 1e-3 depth texels), and variance = |mean^2 - mean2| cancels on flat walls, then enters the weight cubed and
+// crushed (x9). Measured on cfg2 / cfg4 (profiles/r02_parity_flags.txt): with FMA contraction on this chain single rays differ from
+// the oracle by 0.4 % ... 16 %; with it exact the largest difference is 3e-5. Everything smooth (colour filtering, weights, BRDF)
+// keeps fused / approximate arithmetic.
+__device__ __forceinline__ v3 xadd3(v3 a, v3 b) { return mk3(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z)); }
+__device__ __forceinline__ v3 xsub3(v3 a, v3 b) { return mk3(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z)); }
+__device__ __forceinline__ v3 xmul3(v3 a, float s) { return mk3(__fmul_rn(a.x, s), __fmul_rn(a.y, s), __fmul_rn(a.z, s)); }
+__device__ __forceinline__ float xdot3(v3 a, v3 b) { return __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z)); }
+__device__ __forceinline__ v3 xnorm3(v3 v) { return xmul3(v, __fdiv_rn(1.0f, __fsqrt_rn(xdot3(v, v)))); } // v * inversesqrt(dot(v, v))
+__device__ __forceinline__ v3 xreflect3(v3 I, v3 N) { return xsub3(I, xmul3(xmul3(N, xdot3(N, I)), 2.0f)); } // I - N * dot(N, I) * 2
+
 #define VKX_PI 3.1415926538f
 
 // ---- grid helpers (irradiance.glsl:7-38)
@@ -86,9 +100,9 @@ __device__ __forceinline__ float2 sphereToOctUV(v3 direction) { // irradiance.gl
 // REPEAT addressing without integer division or branches: atlas/noise coordinates produced on this path lie in [-size, 2*size)
 // (uv in [-1, 2)), where one conditional add/subtract equals the oracle's ((i % size) + size) % size.
 __device__ __forceinline__ void bilinearSetup(float u, uint32_t size, int& i0, int& i1, float& f) {
-    float x = u * float(size) - 0.5f;
+    float x = __fsub_rn(__fmul_rn(u, float(size)), 0.5f); // u * size - 0.5 with both roundings (exact chain, see above)
     float fl = floorf(x);
-    f = x - fl;
+    f = __fsub_rn(x, fl);
     const int isz = int(size);
     int i = int(fl);
     i += (i < 0) ? isz : 0;
@@ -139,21 +153,25 @@ __device__ __forceinline__ GridConsts makeGridConsts(const vkx_grid_info& grid) 
     return c;
 }
 // x / scale, exactly: a division by a power of two equals the multiplication by its (exact) reciprocal.
-__device__ __forceinline__ float divScale(float x, float scale, float inv, bool pow2) { return pow2 ? x * inv : x / scale; }
+__device__ __forceinline__ float divScale(float x, float scale, float inv, bool pow2) { return pow2 ? __fmul_rn(x, inv) : __fdiv_rn(x, scale); }
+// (tileOrigin + 1) / res + localScale * oct, all over uvScaling (irradiance.glsl:171-175): the sum is formed at atlas magnitude, exact chain
+__device__ __forceinline__ float atlasU(float base, float localScale, float oct, float scale, float inv, bool pow2) {
+    return divScale(__fadd_rn(base, __fmul_rn(localScale, oct)), scale, inv, pow2);
+}
 
-// spherePointToOctohedralUV without the (unused) z division: octahedron.z < 0 <=> direction.z < 0 because the divisor
-// dot(direction, sign(direction)) = |x|+|y|+|z| is positive. x and y are the same IEEE quotients as in the shader.
+// spherePointToOctohedralUV (irradiance.glsl:119-138), exact chain, without the z division: octahedron.z < 0 <=> direction.z < 0
+// because the divisor dot(direction, sign(direction)) = |x| + |y| + |z| is positive (a quotient that underflows to -0 would need
+// |z| < 2^-149). x and y are the shader's IEEE quotients.
 __device__ __forceinline__ float2 sphereToOctUVxy(v3 direction) {
     const v3 octant = mk3(signS(direction.x), signS(direction.y), signS(direction.z));
-    const float sum = dot3(direction, octant);
-    float ox = direction.x / sum, oy = direction.y / sum;
-    const float oz = direction.z / sum;
-    if (oz < 0.0f) {
+    const float sum = xdot3(direction, octant);
+    float ox = __fdiv_rn(direction.x, sum), oy = __fdiv_rn(direction.y, sum);
+    if (direction.z < 0.0f) {
         const float ax = fabsf(ox), ay = fabsf(oy);
-        ox = octant.x * (1.0f - ay);
-        oy = octant.y * (1.0f - ax);
+        ox = __fmul_rn(octant.x, __fsub_rn(1.0f, ay));
+        oy = __fmul_rn(octant.y, __fsub_rn(1.0f, ax));
     }
-    return make_float2(ox * 0.5f + 0.5f, oy * 0.5f + 0.5f);
+    return make_float2(__fadd_rn(__fmul_rn(ox, 0.5f), 0.5f), __fadd_rn(__fmul_rn(oy, 0.5f), 0.5f));
 }
 
 // Two sampleProbes calls of one closest hit (closesthit.glsl:241 with the reflected direction, :248 with the normal) share the
@@ -168,10 +186,14 @@ __device__ __forceinline__ BilinearTaps makeTaps(float u, float v, uint32_t w, u
     t.o00 = y0 * int(w) + x0; t.o10 = y0 * int(w) + x1; t.o01 = y1 * int(w) + x0; t.o11 = y1 * int(w) + x1;
     return t;
 }
-__device__ __forceinline__ float2 lerpDepth(const BilinearTaps& t, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+__device__ __forceinline__ float lerp2X(float t00, float t10, float t01, float t11, float gx, float fx, float gy, float fy) { // sampleDepth's arithmetic, op for op
+    const float top = __fadd_rn(__fmul_rn(t00, gx), __fmul_rn(t10, fx)), bot = __fadd_rn(__fmul_rn(t01, gx), __fmul_rn(t11, fx));
+    return __fadd_rn(__fmul_rn(top, gy), __fmul_rn(bot, fy));
+}
+__device__ __forceinline__ float2 lerpDepth(const BilinearTaps& t, uint32_t a, uint32_t b, uint32_t c, uint32_t d) { // exact: the moments feed the variance
     const float2 t00 = unpackRG16F(a), t10 = unpackRG16F(b), t01 = unpackRG16F(c), t11 = unpackRG16F(d);
-    const float gx = 1.0f - t.fx, gy = 1.0f - t.fy;
-    return make_float2((t00.x * gx + t10.x * t.fx) * gy + (t01.x * gx + t11.x * t.fx) * t.fy, (t00.y * gx + t10.y * t.fx) * gy + (t01.y * gx + t11.y * t.fx) * t.fy);
+    const float gx = __fsub_rn(1.0f, t.fx), gy = __fsub_rn(1.0f, t.fy);
+    return make_float2(lerp2X(t00.x, t10.x, t01.x, t11.x, gx, t.fx, gy, t.fy), lerp2X(t00.y, t10.y, t01.y, t11.y, gx, t.fx, gy, t.fy));
 }
 __device__ __forceinline__ v3 lerpIrradiance(const BilinearTaps& t, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     const float3 t00 = unpackR11G11B10(a), t10 = unpackR11G11B10(b), t01 = unpackR11G11B10(c), t11 = unpackR11G11B10(d);
@@ -185,7 +207,7 @@ __device__ __forceinline__ void accumulateProbe(ProbeAccum& acc, v3 normal, v3 d
     weight *= backfaceweight * backfaceweight + 0.2f;
     float fallbackWeight = weight;
     const float mean = depth.x;
-    const float variance = fabsf(depth.x * depth.x - depth.y);
+    const float variance = fabsf(__fsub_rn(__fmul_rn(depth.x, depth.x), depth.y)); // two roundings like the shader: a contracted FMA changes this cancellation-prone difference by orders of magnitude on flat walls (mean^2 ~ mean2), and the Chebyshev ratio with it
     const float dd = maxS(biasedDistToProbe - mean, 0.0001f);
     float chebyshevWeight = variance / (variance + dd * dd);
     chebyshevWeight = maxS(chebyshevWeight * chebyshevWeight * chebyshevWeight, 0.0f); // pow(x, 3.0): within 2 ulp of powf
@@ -206,14 +228,14 @@ __device__ __forceinline__ void accumulateProbe(ProbeAccum& acc, v3 normal, v3 d
 // the loads overlap instead of forming four dependent round trips to L2.
 __device__ __forceinline__ void sampleProbePair(const DeviceProbes& p, const GridConsts& gc, ProbeAccum& accA, ProbeAccum& accB, v3 normalA, v3 normalB, float2 octA, float2 octB,
                                                 v3 biasedA, v3 biasedB, v3 probePosition, v3 directionToProbe, float tri, int tile, int cz) {
-    const v3 bA = probePosition - biasedA, bB = probePosition - biasedB;
-    const float lenA = sqrtf(dot3(bA, bA)), lenB = sqrtf(dot3(bB, bB));
-    const float2 octDA = sphereToOctUVxy(-(bA * (1.0f / lenA))), octDB = sphereToOctUVxy(-(bB * (1.0f / lenB)));
-    const float cu0 = float(8 * tile + 1) * 0.125f, cv0 = float(8 * cz + 1) * 0.125f, du0 = float(16 * tile + 1) * 0.0625f, dv0 = float(16 * cz + 1) * 0.0625f;
-    const BilinearTaps tcA = makeTaps(divScale(cu0 + gc.cscale * octA.x, gc.usx, gc.invUsx, gc.pow2x), divScale(cv0 + gc.cscale * octA.y, gc.usy, gc.invUsy, gc.pow2y), p.irrW, p.irrH);
-    const BilinearTaps tcB = makeTaps(divScale(cu0 + gc.cscale * octB.x, gc.usx, gc.invUsx, gc.pow2x), divScale(cv0 + gc.cscale * octB.y, gc.usy, gc.invUsy, gc.pow2y), p.irrW, p.irrH);
-    const BilinearTaps tdA = makeTaps(divScale(du0 + gc.dscale * octDA.x, gc.usx, gc.invUsx, gc.pow2x), divScale(dv0 + gc.dscale * octDA.y, gc.usy, gc.invUsy, gc.pow2y), p.depW, p.depH);
-    const BilinearTaps tdB = makeTaps(divScale(du0 + gc.dscale * octDB.x, gc.usx, gc.invUsx, gc.pow2x), divScale(dv0 + gc.dscale * octDB.y, gc.usy, gc.invUsy, gc.pow2y), p.depW, p.depH);
+    const v3 bA = xsub3(probePosition, biasedA), bB = xsub3(probePosition, biasedB);
+    const float lenA = __fsqrt_rn(xdot3(bA, bA)), lenB = __fsqrt_rn(xdot3(bB, bB)); // biasedDistToProbe
+    const float2 octDA = sphereToOctUVxy(-xmul3(bA, __fdiv_rn(1.0f, lenA))), octDB = sphereToOctUVxy(-xmul3(bB, __fdiv_rn(1.0f, lenB))); // -normalize(biasedDirectionToProbe)
+    const float cu0 = float(8 * tile + 1) * 0.125f, cv0 = float(8 * cz + 1) * 0.125f, du0 = float(16 * tile + 1) * 0.0625f, dv0 = float(16 * cz + 1) * 0.0625f; // exact
+    const BilinearTaps tcA = makeTaps(atlasU(cu0, gc.cscale, octA.x, gc.usx, gc.invUsx, gc.pow2x), atlasU(cv0, gc.cscale, octA.y, gc.usy, gc.invUsy, gc.pow2y), p.irrW, p.irrH);
+    const BilinearTaps tcB = makeTaps(atlasU(cu0, gc.cscale, octB.x, gc.usx, gc.invUsx, gc.pow2x), atlasU(cv0, gc.cscale, octB.y, gc.usy, gc.invUsy, gc.pow2y), p.irrW, p.irrH);
+    const BilinearTaps tdA = makeTaps(atlasU(du0, gc.dscale, octDA.x, gc.usx, gc.invUsx, gc.pow2x), atlasU(dv0, gc.dscale, octDA.y, gc.usy, gc.invUsy, gc.pow2y), p.depW, p.depH);
+    const BilinearTaps tdB = makeTaps(atlasU(du0, gc.dscale, octDB.x, gc.usx, gc.invUsx, gc.pow2x), atlasU(dv0, gc.dscale, octDB.y, gc.usy, gc.invUsy, gc.pow2y), p.depW, p.depH);
     const uint32_t* D = p.depSampled; const uint32_t* C = p.irrSampled;
     const uint32_t dA0 = __ldg(D + tdA.o00), dA1 = __ldg(D + tdA.o10), dA2 = __ldg(D + tdA.o01), dA3 = __ldg(D + tdA.o11);
     const uint32_t dB0 = __ldg(D + tdB.o00), dB1 = __ldg(D + tdB.o10), dB2 = __ldg(D + tdB.o01), dB3 = __ldg(D + tdB.o11);
@@ -237,8 +259,8 @@ __device__ inline void sampleProbes2(const DeviceProbes& p, const GridConsts& gc
     const v3 gridCoords = mk3(__fdiv_rn(__fsub_rn(position.x, gc.extentMin.x), gc.acell.x), __fdiv_rn(__fsub_rn(position.y, gc.extentMin.y), gc.acell.y), __fdiv_rn(__fsub_rn(position.z, gc.extentMin.z), gc.acell.z));
     resultA = mk3(0.0f); resultB = mk3(0.0f);
     if (gridCoords.x < 0.0f || gridCoords.y < 0.0f || gridCoords.z < 0.0f) return;
-    const v3 biasedA = position + (normalA + toCamera) * grid.shadowBias;
-    const v3 biasedB = position + (normalB + toCamera) * grid.shadowBias;
+    const v3 biasedA = xadd3(position, xmul3(xadd3(normalA, toCamera), grid.shadowBias));
+    const v3 biasedB = xadd3(position, xmul3(xadd3(normalB, toCamera), grid.shadowBias));
     const int fx = int(gridCoords.x), fy = int(gridCoords.y), fz = int(gridCoords.z);
     v3 alpha = (position - (mk3(float(fx), float(fy), float(fz)) * gc.cell + gc.extentMin)) / gc.acell;
     alpha = mk3(clampS(alpha.x, 0.0f, 1.0f), clampS(alpha.y, 0.0f, 1.0f), clampS(alpha.z, 0.0f, 1.0f));
@@ -253,7 +275,7 @@ __device__ inline void sampleProbes2(const DeviceProbes& p, const GridConsts& gc
         if (cx > gc.rx - 1 || cy > gc.ry - 1 || cz > gc.rz - 1) continue;
         const uint32_t li = uint32_t(cx + gc.rx * cy + gc.rx * gc.ry * cz);
         if (__ldg(p.stateSampled + li) == 0u) continue;
-        const v3 probePosition = mk3(float(cx), float(cy), float(cz)) * gc.cell + gc.extentMin;
+        const v3 probePosition = mk3(__fadd_rn(__fmul_rn(float(cx), gc.cell.x), gc.extentMin.x), __fadd_rn(__fmul_rn(float(cy), gc.cell.y), gc.extentMin.y), __fadd_rn(__fmul_rn(float(cz), gc.cell.z), gc.extentMin.z));
         const v3 directionToProbe = norm3(probePosition - position);
         const v3 trilinear = mix3(1.0f - alpha, alpha, mk3(float(ox), float(oy), float(oz)));
         const float tri = trilinear.x * trilinear.y * trilinear.z + 0.001f;
@@ -269,7 +291,7 @@ __device__ inline v3 sampleProbes1(const DeviceProbes& p, const GridConsts& gc, 
     const vkx_grid_info& grid = p.grid;
     const v3 gridCoords = mk3(__fdiv_rn(__fsub_rn(position.x, gc.extentMin.x), gc.acell.x), __fdiv_rn(__fsub_rn(position.y, gc.extentMin.y), gc.acell.y), __fdiv_rn(__fsub_rn(position.z, gc.extentMin.z), gc.acell.z));
     if (gridCoords.x < 0.0f || gridCoords.y < 0.0f || gridCoords.z < 0.0f) return mk3(0.0f);
-    const v3 biased = position + (normal + toCamera) * grid.shadowBias;
+    const v3 biased = xadd3(position, xmul3(xadd3(normal, toCamera), grid.shadowBias));
     const int fx = int(gridCoords.x), fy = int(gridCoords.y), fz = int(gridCoords.z);
     v3 alpha = (position - (mk3(float(fx), float(fy), float(fz)) * gc.cell + gc.extentMin)) / gc.acell;
     alpha = mk3(clampS(alpha.x, 0.0f, 1.0f), clampS(alpha.y, 0.0f, 1.0f), clampS(alpha.z, 0.0f, 1.0f));
@@ -284,17 +306,17 @@ __device__ inline v3 sampleProbes1(const DeviceProbes& p, const GridConsts& gc, 
         if (cx > gc.rx - 1 || cy > gc.ry - 1 || cz > gc.rz - 1) continue;
         const uint32_t li = uint32_t(cx + gc.rx * cy + gc.rx * gc.ry * cz);
         if (__ldg(p.stateSampled + li) == 0u) continue;
-        const v3 probePosition = mk3(float(cx), float(cy), float(cz)) * gc.cell + gc.extentMin;
+        const v3 probePosition = mk3(__fadd_rn(__fmul_rn(float(cx), gc.cell.x), gc.extentMin.x), __fadd_rn(__fmul_rn(float(cy), gc.cell.y), gc.extentMin.y), __fadd_rn(__fmul_rn(float(cz), gc.cell.z), gc.extentMin.z));
         const v3 directionToProbe = norm3(probePosition - position);
         const v3 trilinear = mix3(1.0f - alpha, alpha, mk3(float(ox), float(oy), float(oz)));
         const float tri = trilinear.x * trilinear.y * trilinear.z + 0.001f;
         const int tile = cy * gc.rx + cx;
-        const v3 b = probePosition - biased;
-        const float len = sqrtf(dot3(b, b));
-        const float2 octD = sphereToOctUVxy(-(b * (1.0f / len)));
+        const v3 b = xsub3(probePosition, biased);
+        const float len = __fsqrt_rn(xdot3(b, b));
+        const float2 octD = sphereToOctUVxy(-xmul3(b, __fdiv_rn(1.0f, len)));
         const float cu0 = float(8 * tile + 1) * 0.125f, cv0 = float(8 * cz + 1) * 0.125f, du0 = float(16 * tile + 1) * 0.0625f, dv0 = float(16 * cz + 1) * 0.0625f;
-        const BilinearTaps tc = makeTaps(divScale(cu0 + gc.cscale * oct.x, gc.usx, gc.invUsx, gc.pow2x), divScale(cv0 + gc.cscale * oct.y, gc.usy, gc.invUsy, gc.pow2y), p.irrW, p.irrH);
-        const BilinearTaps td = makeTaps(divScale(du0 + gc.dscale * octD.x, gc.usx, gc.invUsx, gc.pow2x), divScale(dv0 + gc.dscale * octD.y, gc.usy, gc.invUsy, gc.pow2y), p.depW, p.depH);
+        const BilinearTaps tc = makeTaps(atlasU(cu0, gc.cscale, oct.x, gc.usx, gc.invUsx, gc.pow2x), atlasU(cv0, gc.cscale, oct.y, gc.usy, gc.invUsy, gc.pow2y), p.irrW, p.irrH);
+        const BilinearTaps td = makeTaps(atlasU(du0, gc.dscale, octD.x, gc.usx, gc.invUsx, gc.pow2x), atlasU(dv0, gc.dscale, octD.y, gc.usy, gc.invUsy, gc.pow2y), p.depW, p.depH);
         const uint32_t d0 = __ldg(D + td.o00), d1 = __ldg(D + td.o10), d2 = __ldg(D + td.o01), d3 = __ldg(D + td.o11);
         const uint32_t c0 = __ldg(C + tc.o00), c1 = __ldg(C + tc.o10), c2 = __ldg(C + tc.o01), c3 = __ldg(C + tc.o11);
         accumulateProbe(acc, normal, directionToProbe, tri, len, lerpDepth(td, d0, d1, d2, d3), lerpIrradiance(tc, c0, c1, c2, c3));

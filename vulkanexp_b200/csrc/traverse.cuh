@@ -1,4 +1,4 @@
-// Per-ray traversal of the 8-wide compressed BVH ("BVH spec v1"). Replaces the RT-core
+// Per-ray traversal of the 8-wide compressed BVH ("BVH spec v2"). Replaces the RT-core
 // traversal behind traceRayEXT in the reference's shaders (reference src/shaders/traceProbes.rgen:43,
 // closesthit.glsl:270-281, directLight.rgen:79-90, probesInit.rgen:45). The float operation sequence per ray is the
 // one oracle/bvh.cpp executes; only the scheduling of rays onto lanes differs.
@@ -7,45 +7,65 @@
 #include "texture.cuh"
 
 #define VKX_STACK 48
+#define VKX_ROOT_GROUP 0x01000000u // the root as "slot 0" of a virtual parent whose first child is node 0
+// index (within the node's triangle range) of the triangle behind bit b of a hit mask: leaf triangles are contiguous in slot order
+__device__ __forceinline__ uint32_t triangleOffset(uint32_t valid, uint32_t b) { return uint32_t(__popc(valid & 0x00FFFFFFu & ((1u << b) - 1u))); }
 
 struct Ray {
     float ox, oy, oz;
     float dx, dy, dz;
     float ix, iy, iz; // 1 / zero-fixed direction
-    uint32_t oct;     // bit 2: dx < 0, bit 1: dy < 0, bit 0: dz < 0
+    uint32_t oct;     // bit 2: dx < 0, bit 1: dy < 0, bit 0: dz < 0; bytes 1..3: the slot-preference masks of nextSlot() for this octant
 };
 
 __device__ __forceinline__ float fixZero(float d) { return fabsf(d) < 1e-20f ? copysignf(1e-20f, d) : d; }
+
+// Octant word: the 3 sign bits plus, per bit k of the octant, the slots whose (slot ^ octant) has bit k set (see nextSlot).
+__device__ __forceinline__ uint32_t octantWord(uint32_t oct) { return oct | ((0xF0u >> (oct & 4u)) << 8) | ((0xCCu >> (oct & 2u)) << 16) | ((0xAAu >> (oct & 1u)) << 24); }
 
 __device__ __forceinline__ Ray makeRay(float ox, float oy, float oz, float dx, float dy, float dz) {
     Ray r;
     r.ox = ox; r.oy = oy; r.oz = oz; r.dx = dx; r.dy = dy; r.dz = dz;
     float fx = fixZero(dx), fy = fixZero(dy), fz = fixZero(dz);
     r.ix = __fdiv_rn(1.0f, fx); r.iy = __fdiv_rn(1.0f, fy); r.iz = __fdiv_rn(1.0f, fz);
-    r.oct = (fx < 0.0f ? 4u : 0u) | (fy < 0.0f ? 2u : 0u) | (fz < 0.0f ? 1u : 0u);
+    r.oct = octantWord((fx < 0.0f ? 4u : 0u) | (fy < 0.0f ? 2u : 0u) | (fz < 0.0f ? 1u : 0u));
     return r;
 }
 
-// float(byte i of w), exactly, without the conversion (XU) pipe: PRMT builds 0x4B0000qq = 2^23 + q, one FADD removes 2^23.
-// (profiles/r01c: I2F.U8 saturated the XU pipe at 94 % in the node test.)
-__device__ __forceinline__ float byteToFloat(uint32_t w, int i) { return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u + uint32_t(i))), 8388608.0f); }
+// The pending inner child to visit next: the slot s with the largest (s ^ octant). Children sit in the slot of their octant
+// relative to the node centre, so this order is front to back along the ray (spec section 3.5; oracle/bvh.cpp::traverse runs the
+// same rule as a loop). Three binary choices, most significant key bit first; `pending` is the 8-bit set of hit inner slots.
+__device__ __forceinline__ uint32_t nextSlot(uint32_t pending, uint32_t octw) {
+    uint32_t m = pending, t;
+    t = m & (octw >> 8);  m = t ? t : m; // (the bytes above the selected one are harmless: m has only 8 bits)
+    t = m & (octw >> 16); m = t ? t : m;
+    t = m & (octw >> 24); m = t ? t : m;
+    return uint32_t(__ffs(int(m))) - 1u;
+}
 
-// Same value through the conversion pipe (I2F.U8). The node test needs 48 byte->float conversions; splitting them between the XU pipe
-// (this) and the ALU/FMA pipes (byteToFloat) balances the pipes: profiles/r01c (all I2F): XU 94 % busy; r01f (all PRMT+FADD): 2.2x more
-// instructions in the child loop at the same run time.
-__device__ __forceinline__ float byteToFloatXU(uint32_t w, int i) { return __uint2float_rn((w >> (8 * i)) & 0xFFu); }
+// Two quantised plane bytes -> two floats q * 2^-24: PRMT places each byte in the low half of a binary16 (a subnormal, value
+// q * 2^-24, exact) and the two conversions run on the FMA pipe (HADD2.F32). With the axis scale multiplied by 2^24 (exact) the
+// plane distance fma(q * 2^-24, a * 2^24, b) is bit-identical to the spec's fma(float(q), a, b). Replaces 24 I2F.U8 (quarter-rate
+// conversion pipe, 94 % busy in profiles/r01c) + 24 PRMT/FADD pairs by 24 PRMT + 48 HADD2.F32.
+__device__ __forceinline__ void bytePairToFloats(uint32_t w, uint32_t sel, float& f0, float& f1) {
+    const uint32_t pr = __byte_perm(w, 0u, sel);
+    const __half2 h = *reinterpret_cast<const __half2*>(&pr);
+    f0 = __low2float(h); f1 = __high2float(h);
+}
 
 // 8 quantised child boxes of one axis: near plane bytes (n0: slots 0-3, n1: slots 4-7) and far plane bytes.
 struct AxisQ { uint32_t n0, n1, f0, f1; };
 
-// Returns the hit mask of one node: bits 24..31 inner children at priority position, bits 0..23 triangles.
+// Returns the hit mask of one node (BVH spec v2): bits 24..31 inner children by slot, bits 0..23 triangles (3 bits per leaf slot),
+// already restricted to what the node holds (w1.z = the node's validity word).
 __device__ __forceinline__ uint32_t intersectNode(const uint4 w0, const uint4 w1, const uint4 w2, const uint4 w3, const uint4 w4,
                                                    const Ray& r, float tmin, float tmax) {
     const float px = __uint_as_float(w0.x), py = __uint_as_float(w0.y), pz = __uint_as_float(w0.z);
     const uint32_t ew = w0.w;
-    const float ax = __fmul_rn(__uint_as_float((ew & 0xFFu) << 23), r.ix);
-    const float ay = __fmul_rn(__uint_as_float(((ew >> 8) & 0xFFu) << 23), r.iy);
-    const float az = __fmul_rn(__uint_as_float(((ew >> 16) & 0xFFu) << 23), r.iz);
+    const float S = 16777216.0f; // 2^24, exact: a is rounded first like the spec's, then scaled
+    const float ax = __fmul_rn(__fmul_rn(__uint_as_float((ew & 0xFFu) << 23), r.ix), S);
+    const float ay = __fmul_rn(__fmul_rn(__uint_as_float(((ew >> 8) & 0xFFu) << 23), r.iy), S);
+    const float az = __fmul_rn(__fmul_rn(__uint_as_float(((ew >> 16) & 0xFFu) << 23), r.iz), S);
     const float bx = __fmul_rn(__fsub_rn(px, r.ox), r.ix);
     const float by = __fmul_rn(__fsub_rn(py, r.oy), r.iy);
     const float bz = __fmul_rn(__fsub_rn(pz, r.oz), r.iz);
@@ -54,33 +74,34 @@ __device__ __forceinline__ uint32_t intersectNode(const uint4 w0, const uint4 w1
     if (r.oct & 4u) { qx.n0 = w3.z; qx.n1 = w3.w; qx.f0 = w2.x; qx.f1 = w2.y; } else { qx.n0 = w2.x; qx.n1 = w2.y; qx.f0 = w3.z; qx.f1 = w3.w; }
     if (r.oct & 2u) { qy.n0 = w4.x; qy.n1 = w4.y; qy.f0 = w2.z; qy.f1 = w2.w; } else { qy.n0 = w2.z; qy.n1 = w2.w; qy.f0 = w4.x; qy.f1 = w4.y; }
     if (r.oct & 1u) { qz.n0 = w4.z; qz.n1 = w4.w; qz.f0 = w3.x; qz.f1 = w3.y; } else { qz.n0 = w3.x; qz.n1 = w3.y; qz.f0 = w4.z; qz.f1 = w4.w; }
-    uint32_t mask = 0;
-    const uint32_t oct4 = r.oct * 0x01010101u;
+    uint32_t acc = 0;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        const uint32_t meta4 = h ? w1.w : w1.z;
         const uint32_t nx = h ? qx.n1 : qx.n0, fx = h ? qx.f1 : qx.f0;
         const uint32_t ny = h ? qy.n1 : qy.n0, fy = h ? qy.f1 : qy.f0;
         const uint32_t nz = h ? qz.n1 : qz.n0, fz = h ? qz.f1 : qz.f0;
-        // Four children at a time, byte-parallel (same values as: bits = meta >> 5, idx = meta & 31, idx = 24 + ((idx - 24) ^ oct) for inner
-        // children). Inner meta is 0b00111sss, so (meta & meta << 1) has bit 4 set exactly for inner children; empty slots (meta 0)
-        // contribute no bits whatever their (zero) box does.
-        const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-        const uint32_t innerMask4 = (isInner4 >> 4) * 0xFFu;
-        const uint32_t bitIndex4 = (meta4 ^ (oct4 & innerMask4)) & 0x1F1F1F1Fu;
-        const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float tlx = __fmaf_rn(byteToFloatXU(nx, i), ax, bx), thx = __fmaf_rn(byteToFloat(fx, i), ax, bx);
-            const float tly = __fmaf_rn(byteToFloatXU(ny, i), ay, by), thy = __fmaf_rn(byteToFloat(fy, i), ay, by);
-            const float tlz = __fmaf_rn(byteToFloatXU(nz, i), az, bz), thz = __fmaf_rn(byteToFloat(fz, i), az, bz);
-            const float tn = fmaxf(fmaxf(tlx, tly), fmaxf(tlz, tmin));
-            const float tf = fminf(fminf(thx, thy), fminf(thz, tmax));
-            const uint32_t bits = (childBits4 >> (8 * i)) & 0xFFu, idx = (bitIndex4 >> (8 * i)) & 0xFFu;
-            mask |= (tn <= tf) ? (bits << idx) : 0u;
+        for (int j = 0; j < 2; ++j) {
+            const uint32_t sel = j ? 0x4342u : 0x4140u; // bytes (2j, 2j+1) into the low bytes of the two halves
+            float nxa, nxb, fxa, fxb, nya, nyb, fya, fyb, nza, nzb, fza, fzb;
+            bytePairToFloats(nx, sel, nxa, nxb); bytePairToFloats(fx, sel, fxa, fxb);
+            bytePairToFloats(ny, sel, nya, nyb); bytePairToFloats(fy, sel, fya, fyb);
+            bytePairToFloats(nz, sel, nza, nzb); bytePairToFloats(fz, sel, fza, fzb);
+            {
+                const int s = 4 * h + 2 * j;
+                const float tn = fmaxf(fmaxf(__fmaf_rn(nxa, ax, bx), __fmaf_rn(nya, ay, by)), fmaxf(__fmaf_rn(nza, az, bz), tmin));
+                const float tf = fminf(fminf(__fmaf_rn(fxa, ax, bx), __fmaf_rn(fya, ay, by)), fminf(__fmaf_rn(fza, az, bz), tmax));
+                if (tn <= tf) acc |= (7u << (3 * s)) | (1u << (24 + s));
+            }
+            {
+                const int s = 4 * h + 2 * j + 1;
+                const float tn = fmaxf(fmaxf(__fmaf_rn(nxb, ax, bx), __fmaf_rn(nyb, ay, by)), fmaxf(__fmaf_rn(nzb, az, bz), tmin));
+                const float tf = fminf(fminf(__fmaf_rn(fxb, ax, bx), __fmaf_rn(fyb, ay, by)), fminf(__fmaf_rn(fzb, az, bz), tmax));
+                if (tn <= tf) acc |= (7u << (3 * s)) | (1u << (24 + s));
+            }
         }
     }
-    return mask;
+    return acc & w1.z;
 }
 
 // Moeller-Trumbore with the fixed operation order of oracle/bvh.cpp::intersectTri.
@@ -128,25 +149,24 @@ __device__ __forceinline__ bool traverse(const uint4* __restrict__ nodes, const 
     hit.found = false; hit.inst = 0xFFFFFFFFu; hit.prim = 0xFFFFFFFFu; hit.u = 0.f; hit.v = 0.f; hit.t = -1.0f;
     uint2 stack[VKX_STACK];
     int sp = 0;
-    uint2 g = make_uint2(0u, 0x80000000u);
+    uint2 g = make_uint2(0u, VKX_ROOT_GROUP);
     for (;;) {
-        uint32_t triBase = 0, triBits = 0;
+        uint32_t triBase = 0, triBits = 0, triValid = 0;
         if (g.y & 0xFF000000u) {
-            const uint32_t bit = 31u - uint32_t(__clz(int(g.y)));
-            g.y &= ~(1u << bit);
+            const uint32_t slot = nextSlot(g.y >> 24, r.oct);
+            g.y &= ~(0x01000000u << slot);
             if (g.y & 0xFF000000u) { if (sp < VKX_STACK) stack[sp++] = g; }
-            const uint32_t slot = (bit - 24u) ^ r.oct;
             const uint32_t rel = uint32_t(__popc(g.y & 0xFFu & ((1u << slot) - 1u)));
             uint4 w0, w1, w2, w3, w4;
             loadNode(nodes, g.x + rel, w0, w1, w2, w3, w4);
             const uint32_t m = intersectNode(w0, w1, w2, w3, w4, r, tmin, tbest);
             g.x = w1.x; g.y = (m & 0xFF000000u) | (w0.w >> 24);
-            triBase = w1.y; triBits = m & 0x00FFFFFFu;
+            triBase = w1.y; triBits = m & 0x00FFFFFFu; triValid = w1.z;
         }
         while (triBits) {
             const uint32_t b = uint32_t(__ffs(int(triBits))) - 1u;
             triBits &= triBits - 1u;
-            const float4* tp = tris + size_t(triBase + b) * 3;
+            const float4* tp = tris + size_t(triBase + triangleOffset(triValid, b)) * 3;
             const float4 q2 = __ldg(tp + 2);
             const uint32_t instW = __float_as_uint(q2.y), primW = __float_as_uint(q2.z);
             if (!((instW >> 24) & cullMask)) continue;

@@ -34,7 +34,8 @@ NODE_DTYPE = np.dtype(
         ("imask", "u1"),
         ("childBase", "<u4"),
         ("primBase", "<u4"),
-        ("meta", "u1", 8),
+        ("valid", "<u4"),  # BVH spec v2: bits 24..31 imask, bits [3s, 3s + count) leaf slot s
+        ("pad", "<u4"),
         ("qlo", "u1", (3, 8)),
         ("qhi", "u1", (3, 8)),
     ]
