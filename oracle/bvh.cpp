@@ -29,6 +29,34 @@ static inline float halfArea(const float* lo, const float* hi) {
     return (ex * ey + ey * ez) + ez * ex;
 }
 
+// One instanced triangle in world space (spec section 3.1): vertices through the instance's 3x4 transform without FMA, edges from
+// the transformed vertices, bounds by the total order on floats.
+static void flattenTriangle(const vkx_vertex* vertices, const uint32_t* indices, const vkx_offset_entry& oe, const vkx_instance& in, uint32_t k, uint32_t j, uint32_t flip,
+                            Tri48& t, float lo[3], float hi[3]) {
+    const float* M = in.transform;
+    float w[3][3];
+    for (int c = 0; c < 3; ++c) {
+        uint32_t vi = oe.vertexOffset + indices[oe.indexOffset + 3 * j + c];
+        const float* p = vertices[vi].pos;
+        for (int r = 0; r < 3; ++r)
+            w[c][r] = ((M[4 * r + 0] * p[0] + M[4 * r + 1] * p[1]) + M[4 * r + 2] * p[2]) + M[4 * r + 3];
+    }
+    for (int a = 0; a < 3; ++a) {
+        t.v0[a] = w[0][a];
+        t.e1[a] = w[1][a] - w[0][a];
+        t.e2[a] = w[2][a] - w[0][a];
+        lo[a] = omin(omin(w[0][a], w[1][a]), w[2][a]);
+        hi[a] = omax(omax(w[0][a], w[1][a]), w[2][a]);
+    }
+    t.inst = k | ((in.mask & 0xFFu) << 24);
+    t.prim = j | flip;
+    t.pad = 0;
+}
+static inline uint32_t windingFlip(const float* M) {
+    float det = M[0] * (M[5] * M[10] - M[6] * M[9]) - M[1] * (M[4] * M[10] - M[6] * M[8]) + M[2] * (M[4] * M[9] - M[5] * M[8]);
+    return det < 0.0f ? 0x80000000u : 0u;
+}
+
 void flatten(const vkx_vertex* vertices, const uint32_t* indices, const vkx_offset_entry* offsets,
              const uint32_t* meshIndexCounts, const vkx_instance* instances, size_t numInstances,
              std::vector<Tri48>& out, std::vector<float>& lo, std::vector<float>& hi) {
@@ -37,28 +65,12 @@ void flatten(const vkx_vertex* vertices, const uint32_t* indices, const vkx_offs
         const vkx_instance& in = instances[k];
         const vkx_offset_entry& oe = offsets[in.meshEntry];
         const float* M = in.transform;
-        float det = M[0] * (M[5] * M[10] - M[6] * M[9]) - M[1] * (M[4] * M[10] - M[6] * M[8]) + M[2] * (M[4] * M[9] - M[5] * M[8]);
-        uint32_t flip = det < 0.0f ? 0x80000000u : 0u;
+        uint32_t flip = windingFlip(M);
         uint32_t ntri = meshIndexCounts[in.meshEntry] / 3;
         for (uint32_t j = 0; j < ntri; ++j) {
-            float w[3][3];
-            for (int c = 0; c < 3; ++c) {
-                uint32_t vi = oe.vertexOffset + indices[oe.indexOffset + 3 * j + c];
-                const float* p = vertices[vi].pos;
-                for (int r = 0; r < 3; ++r)
-                    w[c][r] = ((M[4 * r + 0] * p[0] + M[4 * r + 1] * p[1]) + M[4 * r + 2] * p[2]) + M[4 * r + 3];
-            }
-            Tri48 t;
-            for (int a = 0; a < 3; ++a) {
-                t.v0[a] = w[0][a];
-                t.e1[a] = w[1][a] - w[0][a];
-                t.e2[a] = w[2][a] - w[0][a];
-                lo.push_back(omin(omin(w[0][a], w[1][a]), w[2][a]));
-                hi.push_back(omax(omax(w[0][a], w[1][a]), w[2][a]));
-            }
-            t.inst = uint32_t(k) | ((in.mask & 0xFFu) << 24);
-            t.prim = j | flip;
-            t.pad = 0;
+            Tri48 t; float l[3], h[3];
+            flattenTriangle(vertices, indices, oe, in, uint32_t(k), j, flip, t, l, h);
+            for (int a = 0; a < 3; ++a) { lo.push_back(l[a]); hi.push_back(h[a]); }
             out.push_back(t);
         }
     }
@@ -78,6 +90,39 @@ struct BNode { uint32_t ref[2]; Box box[2]; };
 struct Active { uint32_t first, count, id; Box box, cbox; };
 
 } // namespace
+
+// Quantisation origin / exponents of a wide node from its box, and the 8-bit child planes of the occupied slots (spec section 3.4):
+// shared by the build and the refit, which must produce the same bytes for the same boxes.
+static void quantiseNode(Node80& node, const Box& nodeBox, const Box* slotBox, const bool* present) {
+    float cell[3], inv[3];
+    for (int a = 0; a < 3; ++a) {
+        node.p[a] = nodeBox.lo[a];
+        float ext = nodeBox.hi[a] - nodeBox.lo[a];
+        uint32_t bits = f2u(ext / 255.0f);
+        uint32_t e = (bits >> 23) & 0xFFu;
+        if (bits & 0x7FFFFFu) e += 1;
+        e = std::min(std::max(e, 1u), 253u);
+        if (ext * u2f((254u - e) << 23) > 255.0f) e = std::min(e + 1, 253u);
+        node.e[a] = uint8_t(e);
+        cell[a] = u2f(e << 23);
+        inv[a] = u2f((254u - e) << 23);
+    }
+    for (int s = 0; s < 8; ++s) {
+        for (int a = 0; a < 3; ++a) { node.qlo[a][s] = 0; node.qhi[a][s] = 0; }
+        if (!present[s]) continue;
+        const Box& b = slotBox[s];
+        for (int a = 0; a < 3; ++a) {
+            float ql = std::floor((b.lo[a] - node.p[a]) * inv[a]);
+            ql = std::min(std::max(ql, 0.0f), 255.0f);
+            if (ql > 0.0f && node.p[a] + ql * cell[a] > b.lo[a]) ql -= 1.0f;
+            float qh = std::ceil((b.hi[a] - node.p[a]) * inv[a]);
+            qh = std::min(std::max(qh, 0.0f), 255.0f);
+            if (qh < 255.0f && node.p[a] + qh * cell[a] < b.hi[a]) qh += 1.0f;
+            node.qlo[a][s] = uint8_t(ql);
+            node.qhi[a][s] = uint8_t(qh);
+        }
+    }
+}
 
 void build(const std::vector<Tri48>& flat, const std::vector<float>& lo, const std::vector<float>& hi, Bvh& out) {
     const uint32_t T = uint32_t(flat.size());
@@ -217,53 +262,70 @@ void build(const std::vector<Tri48>& flat, const std::vector<float>& lo, const s
             for (int c = 0; c < n; ++c) entAt[slotOf[c]] = c;
 
             Node80 node; std::memset(&node, 0, sizeof(node));
-            float cell[3], inv[3];
-            for (int a = 0; a < 3; ++a) {
-                node.p[a] = w.box.lo[a];
-                float ext = w.box.hi[a] - w.box.lo[a];
-                uint32_t bits = f2u(ext / 255.0f);
-                uint32_t e = (bits >> 23) & 0xFFu;
-                if (bits & 0x7FFFFFu) e += 1;
-                e = std::min(std::max(e, 1u), 253u);
-                if (ext * u2f((254u - e) << 23) > 255.0f) e = std::min(e + 1, 253u);
-                node.e[a] = uint8_t(e);
-                cell[a] = u2f(e << 23);
-                inv[a] = u2f((254u - e) << 23);
-            }
+            Box slotBox[8]; bool present[8];
+            for (int s = 0; s < 8; ++s) { present[s] = entAt[s] >= 0; if (present[s]) slotBox[s] = ent[entAt[s]].box; }
+            quantiseNode(node, w.box, slotBox, present);
             node.childBase = nextBase + uint32_t(wnext.size());
             node.primBase = uint32_t(out.tris.size());
-            uint32_t triOff = 0;
             for (int s = 0; s < 8; ++s) {
                 int c = entAt[s];
                 if (c < 0) continue;
                 const Entry& en = ent[c];
-                for (int a = 0; a < 3; ++a) {
-                    float ql = std::floor((en.box.lo[a] - node.p[a]) * inv[a]);
-                    ql = std::min(std::max(ql, 0.0f), 255.0f);
-                    if (ql > 0.0f && node.p[a] + ql * cell[a] > en.box.lo[a]) ql -= 1.0f;
-                    float qh = std::ceil((en.box.hi[a] - node.p[a]) * inv[a]);
-                    qh = std::min(std::max(qh, 0.0f), 255.0f);
-                    if (qh < 255.0f && node.p[a] + qh * cell[a] < en.box.hi[a]) qh += 1.0f;
-                    node.qlo[a][s] = uint8_t(ql);
-                    node.qhi[a][s] = uint8_t(qh);
-                }
                 if (isLeaf(en.ref)) {
                     uint32_t cnt = leafCount(en.ref), first = leafFirst(en.ref);
                     node.valid |= ((1u << cnt) - 1u) << (3 * s);
                     for (uint32_t i = 0; i < cnt; ++i) out.tris.push_back(flat[prim[first + i]]);
-                    triOff += cnt;
                 } else {
                     node.imask |= uint8_t(1u << s);
                     node.valid |= 1u << (24 + s);
                     wnext.push_back(WideWork{en.ref, en.box});
                 }
             }
-            (void)triOff;
             out.nodes.push_back(node);
         }
         levelBase = nextBase;
         wcur.swap(wnext);
     }
+}
+
+// Topology-preserving refit (the reference refits its TLAS in place after instance transforms change, src/Renderer.cpp:681-742): the
+// tree, the slot assignment and the triangle order stay; the world-space triangles are recomputed from the current vertices and
+// instance transforms, and every node's origin, exponents and child planes are re-quantised from the new bounds, children before
+// parents (nodes are stored level by level, so descending index order is bottom-up). With unchanged transforms this reproduces the
+// built structure byte for byte; with moved instances the result differs from a rebuild (the split decisions are the old ones) but
+// is still a valid, conservative hierarchy over the same triangles.
+void refit(const vkx_vertex* vertices, const uint32_t* indices, const vkx_offset_entry* offsets, const vkx_instance* instances, Bvh& bvh) {
+    const size_t T = bvh.tris.size(), N = bvh.nodes.size();
+    std::vector<Box> triBox(T), nodeBox(N);
+    for (size_t i = 0; i < T; ++i) {
+        Tri48& t = bvh.tris[i];
+        const uint32_t k = t.inst & 0x00FFFFFFu, j = t.prim & 0x7FFFFFFFu;
+        const vkx_instance& in = instances[k];
+        flattenTriangle(vertices, indices, offsets[in.meshEntry], in, k, j, windingFlip(in.transform), t, triBox[i].lo, triBox[i].hi);
+    }
+    for (size_t n = N; n-- > 0;) {
+        Node80& node = bvh.nodes[n];
+        Box slotBox[8]; bool present[8]; Box nb; nb.reset();
+        for (int s = 0; s < 8; ++s) {
+            present[s] = false;
+            if (node.imask & (1u << s)) {
+                slotBox[s] = nodeBox[node.childBase + uint32_t(__builtin_popcount(node.imask & ((1u << s) - 1u)))];
+                present[s] = true;
+            } else {
+                const uint32_t cnt = uint32_t(__builtin_popcount((node.valid >> (3 * s)) & 7u));
+                if (cnt) {
+                    const uint32_t first = node.primBase + uint32_t(__builtin_popcount(node.valid & 0x00FFFFFFu & ((1u << (3 * s)) - 1u)));
+                    slotBox[s].reset();
+                    for (uint32_t i = 0; i < cnt; ++i) slotBox[s].grow(triBox[first + i]);
+                    present[s] = true;
+                }
+            }
+            if (present[s]) nb.grow(slotBox[s]);
+        }
+        nodeBox[n] = nb;
+        quantiseNode(node, nb, slotBox, present);
+    }
+    if (N) for (int a = 0; a < 3; ++a) { bvh.sceneMin[a] = nodeBox[0].lo[a]; bvh.sceneMax[a] = nodeBox[0].hi[a]; }
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -59,6 +59,9 @@ void flatten(const vkx_vertex* vertices, const uint32_t* indices, const vkx_offs
 
 void build(const std::vector<Tri48>& flat, const std::vector<float>& lo, const std::vector<float>& hi, Bvh& out);
 
+// Topology-preserving refit after the vertices / instance transforms changed (same instance list, same meshes): see bvh.cpp.
+void refit(const vkx_vertex* vertices, const uint32_t* indices, const vkx_offset_entry* offsets, const vkx_instance* instances, Bvh& bvh);
+
 // Closest hit. Returns true on hit. hit.t < 0 on miss.
 bool traceClosest(const Bvh& bvh, const float o[3], const float d[3], float tmin, float tmax, uint32_t cullMask,
                   vkx_hit& hit, Counters* ctr = nullptr, const AnyHitFilter* filter = nullptr);

@@ -85,6 +85,13 @@ int orc_vertices_download(orc_ctx* c, size_t first, size_t count, vkx_vertex* ou
     return 0;
 }
 int orc_bvh_build(orc_ctx* c) { oddgi::sceneFinalize(c->scene); return 0; }
+// New instance transforms / masks for the uploaded instance list (same meshes), then either orc_bvh_build (rebuild) or orc_bvh_refit.
+int orc_instances_update(orc_ctx* c, const vkx_instance* inst, size_t n) {
+    if (n != c->scene.instances.size()) return -1;
+    c->scene.instances.assign(inst, inst + n);
+    return 0;
+}
+int orc_bvh_refit(orc_ctx* c) { oddgi::sceneRefit(c->scene); return 0; }
 int orc_bvh_info(orc_ctx* c, vkx_bvh_info* out) {
     const obvh::Bvh& b = c->scene.bvh;
     std::memset(out, 0, sizeof(*out));

@@ -363,6 +363,11 @@ void sceneFinalize(Scene& s) {
     obvh::build(flat, lo, hi, s.bvh);
 }
 
+void sceneRefit(Scene& s) { // Renderer::updateAccelerationStructureInstances + updateTLAS (src/Renderer.cpp:671-742) on the wide BVH
+    for (size_t k = 0; k < s.instances.size(); ++k) s.worldToObject[k] = inverse3(s.instances[k].transform);
+    obvh::refit(s.vertices.data(), s.indices.data(), s.offsets.data(), s.instances.data(), s.bvh);
+}
+
 void probesInit(Probes& p, const vkx_grid_info& g) { // IrradianceProbes::init, src/IrradianceProbes.cpp:12-104
     p.grid = g;
     p.probeCount = uint32_t(g.resolution[0]) * uint32_t(g.resolution[1]) * uint32_t(g.resolution[2]);

@@ -50,6 +50,7 @@ struct Probes {
 };
 
 void sceneFinalize(Scene& s); // worldToObject + BVH
+void sceneRefit(Scene& s);    // worldToObject + topology-preserving BVH refit after instance transforms / vertices changed
 // vertexSkinning.comp:37-60 over `size` vertices (push constants srcOffset / dstOffset); motionVectors: optional, 4 floats per vertex.
 // The BVH must be rebuilt afterwards (sceneFinalize), as Renderer::updateSkinnedBLAS does for the skinned BLASes.
 void skinVertices(Scene& s, const float* jointTransforms, const uint16_t* skinJoints, const float* skinWeights, uint32_t srcOffset, uint32_t dstOffset, uint32_t size, float* motionVectors);

@@ -110,6 +110,13 @@ class Oracle:
     def bvh_build(self):
         self.l.orc_bvh_build(self.h)
 
+    def instances_update(self, instances):
+        inst = np.ascontiguousarray(instances)
+        assert self.l.orc_instances_update(self.h, _p(inst), C.c_size_t(len(inst))) == 0
+
+    def bvh_refit(self):
+        self.l.orc_bvh_refit(self.h)
+
     def bvh_info(self):
         info = BvhInfo()
         self.l.orc_bvh_info(self.h, C.byref(info))

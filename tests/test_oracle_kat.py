@@ -258,3 +258,49 @@ def test_oracle_reflection_properties(oracle_lib, scene_getter):
     inner = geo.copy(); inner[:6] = inner[-6:] = False; inner[:, :6] = inner[:, -6:] = False
     assert np.array_equal(fin[..., 3][geo], pd[..., 3][geo]), "final alpha carries the depth"
     assert (fin[inner][:, :3] > 0.9 * 7.0 * 0.98).mean() > 0.9, "a still camera keeps 98 % of a matching history"
+
+
+def _moved_instances(flat, seed=3):
+    inst = flat["instances"].copy()
+    rng = np.random.default_rng(seed)
+    for k in range(1, len(inst)):  # translate + rotate about y every instance but the room
+        ang = float(rng.uniform(0, 2 * np.pi)); c, s = np.float32(np.cos(ang)), np.float32(np.sin(ang))
+        M = inst[k]["transform"].reshape(3, 4).copy()
+        R = np.eye(3, dtype=np.float32); R[0, 0] = c; R[0, 2] = s; R[2, 0] = -s; R[2, 2] = c
+        M = (R @ M).astype(np.float32)
+        M[0, 3] += np.float32(rng.uniform(-0.8, 0.8)); M[1, 3] += np.float32(rng.uniform(0.0, 0.5)); M[2, 3] += np.float32(rng.uniform(-0.8, 0.8))
+        inst[k]["transform"] = M.reshape(-1)
+    return inst
+
+
+def test_refit_restatement_properties():
+    """Topology-preserving refit (Renderer::updateTLAS, reference src/Renderer.cpp:681-742, on the wide BVH): with unchanged transforms
+    it reproduces the built structure byte for byte; after moving instances it keeps topology (child / triangle layout words) and
+    still finds every hit a rebuilt structure finds (same triangles, conservative boxes)."""
+    from conftest import get_scene
+    from oracle import pyoracle
+
+    flat = get_scene("cfg1")
+    o = pyoracle.Oracle(); o.scene_upload(flat); o.bvh_build()
+    n0, t0 = o.bvh_download()
+    o.bvh_refit()
+    n1, t1 = o.bvh_download()
+    assert n0.tobytes() == n1.tobytes() and t0.tobytes() == t1.tobytes(), "refit with unchanged transforms must be the identity"
+    inst = _moved_instances(flat)
+    o.instances_update(inst); o.bvh_refit()
+    n2, t2 = o.bvh_download()
+    assert n2.tobytes() != n0.tobytes()
+    for f in ("imask", "childBase", "primBase", "valid"):
+        assert np.array_equal(n2[f], n0[f]), f
+    assert np.array_equal(t2["inst"] & 0xFFFFFF, t0["inst"] & 0xFFFFFF) and np.array_equal(t2["prim"] & 0x7FFFFFFF, t0["prim"] & 0x7FFFFFFF)
+    moved = dict(flat); moved["instances"] = inst
+    r = pyoracle.Oracle(); r.scene_upload(moved); r.bvh_build()
+    rng = np.random.default_rng(9)
+    lo, hi = np.array(flat["bounds_min"]), np.array(flat["bounds_max"])
+    org = rng.uniform(lo, hi, size=(20000, 3)).astype(np.float32)
+    d = rng.normal(size=(20000, 3)); d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    ha = o.trace(org, d, 0.001, 1000.0)[0] if isinstance(o.trace(org[:1], d[:1], 0.001, 1000.0), tuple) else o.trace(org, d, 0.001, 1000.0)
+    hb = r.trace(org, d, 0.001, 1000.0)[0] if isinstance(r.trace(org[:1], d[:1], 0.001, 1000.0), tuple) else r.trace(org, d, 0.001, 1000.0)
+    same = (ha["t"] == hb["t"]) & (ha["instance"] == hb["instance"]) & (ha["primitive"] == hb["primitive"])
+    assert same.mean() > 0.9999, "refit and rebuilt structures must find the same hits (up to grazing ties): %g" % same.mean()
+    assert (ha["t"] > 0).mean() > 0.5

@@ -2,6 +2,7 @@
 // kernels in bvh_build.cu / ddgi.cu / shadow.cu. There is deliberately no CPU fallback: without a usable CUDA device
 // vkx_create fails and nothing else can be called.
 #include "common.cuh"
+#include "blend_tc.cuh"
 #include <cmath>
 #include <cstdarg>
 #include <cstring>
@@ -74,13 +75,13 @@ static void releaseP2p(vkx_ctx* ctx) { // the six atlas pointers live inside the
 static void freeProbes(vkx_ctx* ctx) {
     releaseP2p(ctx);
     void* ptrs[] = {ctx->dIrrWork, ctx->dIrrSampled, ctx->dDepWork, ctx->dDepSampled, ctx->dStateWork, ctx->dStateSampled, ctx->dIndicesList, ctx->dDirs, ctx->dRays,
-                    ctx->dHits, ctx->dShadowQueue, ctx->dQueueCount, ctx->dShadowFlags, ctx->dIrrUnpacked, ctx->dDepUnpacked, ctx->dMissQueue, ctx->dFrontQueue, ctx->dFrontKeys, ctx->dFrontKeysOut, ctx->dFrontQueueSorted, ctx->dSortTemp, ctx->dIrrNext, ctx->dDepNext, ctx->dStateNext,
-                    ctx->dPerm, ctx->dOrder, ctx->dBlockedOrder, ctx->dBlendW, ctx->dPermList, ctx->dIota, ctx->dCellHist, ctx->dInvDirs, ctx->dOrigins};
+                    ctx->dHits, ctx->dShadowQueue, ctx->dShadowVis, ctx->dQueueCount, ctx->dShadowFlags, ctx->dIrrUnpacked, ctx->dDepUnpacked, ctx->dMissQueue, ctx->dFrontQueue, ctx->dFrontKeys, ctx->dFrontKeysOut, ctx->dFrontQueueSorted, ctx->dSortTemp, ctx->dIrrNext, ctx->dDepNext, ctx->dStateNext,
+                    ctx->dPerm, ctx->dOrder, ctx->dBlockedOrder, ctx->dBlendW, ctx->dBlendImage, ctx->dPermList, ctx->dIota, ctx->dCellHist, ctx->dInvDirs, ctx->dOrigins};
     for (void* p : ptrs) if (p) cudaFree(p);
     ctx->dIrrWork = ctx->dIrrSampled = ctx->dDepWork = ctx->dDepSampled = ctx->dStateWork = ctx->dStateSampled = ctx->dIndicesList = nullptr;
     ctx->dIrrNext = ctx->dDepNext = ctx->dStateNext = nullptr;
-    ctx->dPerm = ctx->dOrder = ctx->dBlockedOrder = ctx->dPermList = ctx->dIota = ctx->dCellHist = nullptr; ctx->dBlendW = nullptr; ctx->shardOrderReady = false;
-    ctx->dDirs = nullptr; ctx->dInvDirs = nullptr; ctx->dOrigins = nullptr; ctx->dRays = nullptr; ctx->dHits = nullptr; ctx->dShadowQueue = nullptr; ctx->dQueueCount = nullptr; ctx->dShadowFlags = nullptr;
+    ctx->dPerm = ctx->dOrder = ctx->dBlockedOrder = ctx->dPermList = ctx->dIota = ctx->dCellHist = nullptr; ctx->dBlendW = nullptr; ctx->dBlendImage = nullptr; ctx->shardOrderReady = false;
+    ctx->dDirs = nullptr; ctx->dInvDirs = nullptr; ctx->dOrigins = nullptr; ctx->dRays = nullptr; ctx->dHits = nullptr; ctx->dShadowQueue = nullptr; ctx->dShadowVis = nullptr; ctx->dQueueCount = nullptr; ctx->dShadowFlags = nullptr;
     ctx->dIrrUnpacked = ctx->dDepUnpacked = nullptr; ctx->dMissQueue = ctx->dFrontQueue = ctx->dFrontKeys = ctx->dFrontKeysOut = ctx->dFrontQueueSorted = nullptr; ctx->dSortTemp = nullptr; ctx->sortTempBytes = 0;
     if (ctx->hListStage) { cudaFreeHost(ctx->hListStage); ctx->hListStage = nullptr; }
     ctx->hLastList.clear();
@@ -276,16 +277,17 @@ static int checkGrid(vkx_ctx* ctx, const vkx_grid_info* g) {
 
 static int allocProbeScratch(vkx_ctx* ctx) {
     // ray-level scratch for one chunk of probes
-    void* old[] = {ctx->dRays, ctx->dHits, ctx->dShadowQueue, ctx->dShadowFlags, ctx->dIrrUnpacked, ctx->dDepUnpacked, ctx->dMissQueue, ctx->dFrontQueue, ctx->dFrontKeys, ctx->dFrontKeysOut, ctx->dFrontQueueSorted, ctx->dOrigins};
+    void* old[] = {ctx->dRays, ctx->dHits, ctx->dShadowQueue, ctx->dShadowVis, ctx->dShadowFlags, ctx->dIrrUnpacked, ctx->dDepUnpacked, ctx->dMissQueue, ctx->dFrontQueue, ctx->dFrontKeys, ctx->dFrontKeysOut, ctx->dFrontQueueSorted, ctx->dOrigins};
     for (void* p : old) if (p) cudaFree(p);
     ctx->dOrigins = nullptr;
     ctx->dMissQueue = ctx->dFrontQueue = ctx->dFrontKeys = ctx->dFrontKeysOut = ctx->dFrontQueueSorted = nullptr;
-    ctx->dRays = nullptr; ctx->dHits = nullptr; ctx->dShadowQueue = nullptr; ctx->dShadowFlags = nullptr; ctx->dIrrUnpacked = ctx->dDepUnpacked = nullptr;
+    ctx->dRays = nullptr; ctx->dHits = nullptr; ctx->dShadowQueue = nullptr; ctx->dShadowVis = nullptr; ctx->dShadowFlags = nullptr; ctx->dIrrUnpacked = ctx->dDepUnpacked = nullptr;
     const size_t maxRays = size_t(ctx->chunkProbes) * VKX_MAX_RAYS_PER_PROBE;
     CUDA_TRY(ctx, cudaMalloc(&ctx->dRays, maxRays * sizeof(float4)));
     CUDA_TRY(ctx, cudaMalloc(&ctx->dOrigins, size_t(ctx->chunkProbes) * sizeof(float4)));
     CUDA_TRY(ctx, cudaMalloc(&ctx->dHits, maxRays * sizeof(vkx_hit)));
     CUDA_TRY(ctx, cudaMalloc(&ctx->dShadowQueue, maxRays * 2 * sizeof(float4)));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->dShadowVis, maxRays));
     CUDA_TRY(ctx, cudaMalloc(&ctx->dMissQueue, maxRays * 4));
     CUDA_TRY(ctx, cudaMalloc(&ctx->dFrontQueue, maxRays * 4));
     CUDA_TRY(ctx, cudaMalloc(&ctx->dFrontKeys, maxRays * 4));
@@ -323,6 +325,7 @@ int vkx_probes_init(vkx_ctx* ctx, const vkx_grid_info* grid) {
     CUDA_TRY(ctx, cudaMalloc(&ctx->dCellHist, stBytes + 4));
     k_iota_list<<<divUp(ctx->probeCount, 256), 256, 0, ctx->stream>>>(ctx->dIota, 0, ctx->probeCount); LAUNCH_CHECK(ctx);
     CUDA_TRY(ctx, cudaMalloc(&ctx->dBlendW, size_t(VKX_MAX_RAYS_PER_PROBE + 1) * 288 * 4)); // + the row of weight sums
+    CUDA_TRY(ctx, cudaMalloc(&ctx->dBlendImage, BTC_IMAGE_BYTES)); CUDA_TRY(ctx, cudaMemsetAsync(ctx->dBlendImage, 0, BTC_IMAGE_BYTES, ctx->stream));
     { // rank of every probe in 2x2x2-block order (scheduling only: which probes share a warp)
         const uint32_t rx = uint32_t(grid->resolution[0]), ry = uint32_t(grid->resolution[1]);
         const uint32_t nbx = (rx + 1) / 2, nby = (ry + 1) / 2;
@@ -447,8 +450,23 @@ static int uploadOrder(vkx_ctx* ctx, const uint32_t* probeIndices, uint32_t coun
     return VKX_OK;
 }
 
+// A sharded full-volume update blends only this rank's z-slab, so its work atlases (the `previous` texels of the next blend) are
+// stale everywhere else; the gathered *sampled* set is complete. Any update that may blend probes outside the slab (a host list,
+// the unsharded full volume, a sharded list) first brings the work set up to date.
+static int syncWorkAtlases(vkx_ctx* ctx) {
+    if (!ctx->workStale) return VKX_OK;
+    { int rc = waitGather(ctx); if (rc != VKX_OK) return rc; }
+    const size_t irrBytes = size_t(ctx->irrW) * ctx->irrH * 4, depBytes = size_t(ctx->depW) * ctx->depH * 4, stBytes = size_t(ctx->probeCount) * 4;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dIrrWork, ctx->dIrrSampled, irrBytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dDepWork, ctx->dDepSampled, depBytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dStateWork, ctx->dStateSampled, stBytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->workStale = false;
+    return VKX_OK;
+}
+
 int vkx_probes_update(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx_light* light, const float orientation[16], const uint32_t* probeIndices, uint32_t count, int sync) {
     BIND(ctx);
+    TRY(syncWorkAtlases(ctx));
     if (!ctx->probesReady || !ctx->bvhBuilt) return vkx_fail(ctx, VKX_E_INVALID, "vkx_probes_update: probes or BVH not ready");
     if (!light || !orientation) return vkx_fail(ctx, VKX_E_INVALID, "null light/orientation");
     static const bool traceHost = getenv("VKX_TRACE_HOST") != nullptr;
@@ -519,6 +537,7 @@ int vkx_probes_update_scheduled(vkx_ctx* ctx, const vkx_grid_info* grid, const v
     if (!light || !orientation) return vkx_fail(ctx, VKX_E_INVALID, "null light/orientation");
     if (!ctx->schedValid) return vkx_fail(ctx, VKX_E_INVALID, "vkx_probes_update_scheduled: call vkx_probes_schedule first (one schedule per update)");
     ctx->schedValid = false; // the list is consumed: publish changes the states the next schedule reads
+    TRY(syncWorkAtlases(ctx));
     TRY(uploadFrameInputs(ctx, grid, orientation));
     const uint32_t count = ctx->schedCount;
     if (count == 0) return VKX_OK;
@@ -605,6 +624,7 @@ int vkx_probes_download_wait(vkx_ctx* ctx) {
 int vkx_probes_upload(vkx_ctx* ctx, const uint32_t* irradiance, const uint32_t* depth, const uint32_t* state) {
     BIND(ctx);
     TRY(waitGather(ctx));
+    TRY(syncWorkAtlases(ctx)); // a partial upload (e.g. states only) must not leave the other arrays of the work set stale
     if (!ctx->probesReady) return vkx_fail(ctx, VKX_E_INVALID, "probes not initialised");
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     const size_t irrBytes = size_t(ctx->irrW) * ctx->irrH * 4, depBytes = size_t(ctx->depW) * ctx->depH * 4, stBytes = size_t(ctx->probeCount) * 4;
@@ -810,6 +830,7 @@ int vkx_probes_update_sharded(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], st));
     // publish = swap; the work buffers keep this rank's slices current (they are the only ones it reads as `previous`)
     std::swap(ctx->dIrrSampled, ctx->dIrrNext); std::swap(ctx->dDepSampled, ctx->dDepNext); std::swap(ctx->dStateSampled, ctx->dStateNext);
+    ctx->workStale = true;
     ctx->lastCount = total; ctx->lastRays = total * ctx->grid.raysPerProbe; ctx->shardedLast = true;
     if (sync) CUDA_TRY(ctx, cudaStreamSynchronize(st));
     return VKX_OK;
@@ -840,6 +861,7 @@ int vkx_probes_update_sharded_list(vkx_ctx* ctx, const vkx_grid_info* grid, cons
     if (count > ctx->probeCount) return vkx_fail(ctx, VKX_E_INVALID, "more indices than probes");
     for (uint32_t i = 0; i < count; ++i) if (probeIndices[i] >= ctx->probeCount) return vkx_fail(ctx, VKX_E_INVALID, "probe index %u out of range", probeIndices[i]);
     TRY(waitGather(ctx)); // a pending full-volume exchange writes the sampled set this update patches
+    TRY(syncWorkAtlases(ctx));
     TRY(uploadFrameInputs(ctx, grid, orientation));
     ctx->hLastList.clear(); ctx->shardOrderReady = false;
     cudaStream_t st = ctx->stream, cs = ctx->commStream;

@@ -63,7 +63,7 @@ struct vkx_ctx {
     std::string err;
     uint64_t launches = 0;
     int smCount = 148;
-    bool blendAttrSet = false; int traceBlocksPerSm = 0; // per-device kernel attributes / occupancy (set on first use)
+    bool blendAttrSet = false; int traceBlocksPerSm = 0; int poolBlocksPerSm[2] = {0, 0}; // per-device kernel attributes / occupancy (set on first use)
 
     // scene
     vkx_vertex* dVertices = nullptr; uint32_t* dIndices = nullptr; vkx_offset_entry* dOffsets = nullptr; uint32_t* dMeshCounts = nullptr;
@@ -94,6 +94,7 @@ struct vkx_ctx {
     uint32_t* dPermList = nullptr;      // multi-chunk updates: probe indices in block order
     uint32_t* dIota = nullptr;          // 0..probeCount-1
     float* dBlendW = nullptr;           // per-frame blend weight table [256][288]
+    float* dBlendImage = nullptr; bool blendTcAttrSet = false; // the same weights as the tensor-core blend's A-operand image (blend_tc.cu)
     std::vector<uint32_t> hLastList;    // the host list currently resident in dIndicesList / dOrder (empty: none), so an unchanged list is not uploaded again
     std::vector<uint32_t> hBlockRank;   // probe linear index -> rank in 2x2x2-block order
     std::vector<uint32_t> hMark, hOrder; // scratch of uploadOrder
@@ -107,6 +108,7 @@ struct vkx_ctx {
     uint32_t* dMissQueue = nullptr; uint32_t* dFrontQueue = nullptr; // ray indices sorted by what they need next
     uint32_t *dFrontKeys = nullptr, *dFrontKeysOut = nullptr, *dFrontQueueSorted = nullptr, *dCellHist = nullptr; void* dSortTemp = nullptr; size_t sortTempBytes = 0; // front queue sorted by grid cell
     uint8_t* dShadowFlags = nullptr;    // debug
+    uint8_t* dShadowVis = nullptr;      // per shadow-queue item: 1 lit, 2 occluded (ray-pool traversal + k_apply_shadow)
     float* dIrrUnpacked = nullptr; float* dDepUnpacked = nullptr; // debug, full count
     bool debugBuffers = false;
     uint32_t lastCount = 0, lastRays = 0;
@@ -136,6 +138,7 @@ struct vkx_ctx {
     uint32_t p2pFrame = 0; int p2pSampledSet = 0;
     PeerTargets blendPeers = {};
     bool shardedLast = false, shardOrderReady = false;
+    bool workStale = false; // after a sharded full-volume update the work atlases are current only inside this rank's slab (see syncWorkAtlases)
 
     // shadows
     float* dNoise = nullptr; uint32_t noiseW = 0, noiseH = 0, noiseSlices = 0;

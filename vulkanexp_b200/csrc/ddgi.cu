@@ -14,6 +14,7 @@
 #include "ptrace.cuh"
 #include "shade.cuh"
 #include "ddgi_common.cuh"
+#include "blend_tc.cuh"
 #include <cub/device/device_radix_sort.cuh>
 
 namespace {
@@ -57,30 +58,56 @@ struct PrimarySrc {
         tmin = tp.tmin; tmax = tp.tmax; cullMask = VKX_INSTANCE_STATIC | VKX_INSTANCE_DYNAMIC;
         return true;
     }
+    // The hit record only (plus the final value of a back-face hit, closesthit.glsl:137-141). Which queue the ray goes to next is
+    // decided by k_classify_hits: appending here cost a global atomic round trip per finishing ray with the whole warp waiting on
+    // it (16 % of the kernel's stall samples, profiles/r02f_src_k_trace_primary.txt).
     __device__ __forceinline__ void store(uint32_t, const HitRec& h, bool) {
         vkx_hit out; out.t = h.t; out.instance = h.inst; out.primitive = h.prim; out.u = h.u; out.v = h.v;
         hits[ri] = out;
-        if (!h.found) missQueue[warpAppend(counters + 3)] = ri;
-        else if (h.prim & 0x80000000u) rays[ri] = make_float4(0.f, 0.f, 0.f, h.t * 0.80f);
-        else frontQueue[warpAppend(counters + 4)] = ri;
+        if (h.found && (h.prim & 0x80000000u)) rays[ri] = make_float4(0.f, 0.f, 0.f, h.t * 0.80f);
     }
 };
 
-// Sort key of a front hit = grid cell of the hit point (scheduling only: rays that shade from the same 8 probes end up in the same
-// warps of k_shade_front, and their shadow rays start close together).
-__global__ void k_front_keys(TraceParams tp, const float4* __restrict__ origins, const float4* __restrict__ dirs, const vkx_hit* __restrict__ hits,
-                             const uint32_t* __restrict__ frontQueue, const uint32_t* __restrict__ counters, uint32_t* __restrict__ keys) {
-    const uint32_t n = counters[4];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t ri = frontQueue[i];
-        const uint32_t slot = ri / tp.raysPerProbe, ray = ri - slot * tp.raysPerProbe;
-        const float4 o = __ldg(origins + slot);
-        const float4 d = __ldg(dirs + ray);
-        const float t = hits[ri].t;
-        const int cx = min(max(int((o.x + d.x * t - tp.grid.extentMin[0]) * tp.invCell[0]), 0), tp.grid.resolution[0] - 1);
-        const int cy = min(max(int((o.y + d.y * t - tp.grid.extentMin[1]) * tp.invCell[1]), 0), tp.grid.resolution[1] - 1);
-        const int cz = min(max(int((o.z + d.z * t - tp.grid.extentMin[2]) * tp.invCell[2]), 0), tp.grid.resolution[2] - 1);
-        keys[i] = uint32_t(cx + tp.grid.resolution[0] * (cy + tp.grid.resolution[1] * cz));
+// Rays are sorted by what they need next: misses -> sky queue, front-face hits -> shading queue with the sort key of the hit
+// (= grid cell of the hit point; scheduling only: rays that shade from the same 8 probes end up in the same warps of
+// k_shade_front, and their shadow rays start close together). Back-face hits are final. A dense pass over the hit records
+// (84 MB at cfg2), warp-aggregated appends.
+__global__ void __launch_bounds__(256) k_classify_hits(TraceParams tp, const float4* __restrict__ origins, const float4* __restrict__ dirs, const vkx_hit* __restrict__ hits,
+                                                       uint32_t* __restrict__ missQueue, uint32_t* __restrict__ frontQueue, uint32_t* __restrict__ keys, uint32_t* __restrict__ counters) {
+    // Appends are aggregated per block: one atomic per queue per 256 rays (per-warp atomics on the two counters serialised in L2:
+    // the pass took 0.14 ms instead of 0.02).
+    __shared__ uint32_t sCount[2][8], sBase[2];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (uint32_t base = blockIdx.x * 256u; base < tp.numRays; base += gridDim.x * 256u) { // block-uniform trip count
+        const uint32_t ri = base + threadIdx.x;
+        bool miss = false, front = false; float t = 0.0f;
+        if (ri < tp.numRays) {
+            t = hits[ri].t; const uint32_t prim = hits[ri].primitive;
+            miss = prim == 0xFFFFFFFFu; front = !miss && !(prim & 0x80000000u);
+        }
+        const uint32_t mm = __ballot_sync(0xFFFFFFFFu, miss), fm = __ballot_sync(0xFFFFFFFFu, front);
+        if (lane == 0) { sCount[0][warp] = uint32_t(__popc(mm)); sCount[1][warp] = uint32_t(__popc(fm)); }
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            uint32_t total = 0;
+            for (int w = 0; w < 8; ++w) { const uint32_t c = sCount[threadIdx.x][w]; sCount[threadIdx.x][w] = total; total += c; }
+            sBase[threadIdx.x] = total ? atomicAdd(counters + 3 + threadIdx.x, total) : 0u;
+        }
+        __syncthreads();
+        const uint32_t lt = (1u << lane) - 1u;
+        if (miss) missQueue[sBase[0] + sCount[0][warp] + uint32_t(__popc(mm & lt))] = ri;
+        if (front) {
+            const uint32_t slot = ri / tp.raysPerProbe, ray = ri - slot * tp.raysPerProbe;
+            const float4 o = __ldg(origins + slot);
+            const float4 d = __ldg(dirs + ray);
+            const int cx = min(max(int((o.x + d.x * t - tp.grid.extentMin[0]) * tp.invCell[0]), 0), tp.grid.resolution[0] - 1);
+            const int cy = min(max(int((o.y + d.y * t - tp.grid.extentMin[1]) * tp.invCell[1]), 0), tp.grid.resolution[1] - 1);
+            const int cz = min(max(int((o.z + d.z * t - tp.grid.extentMin[2]) * tp.invCell[2]), 0), tp.grid.resolution[2] - 1);
+            const uint32_t i = sBase[1] + sCount[1][warp] + uint32_t(__popc(fm & lt));
+            frontQueue[i] = ri;
+            keys[i] = uint32_t(cx + tp.grid.resolution[0] * (cy + tp.grid.resolution[1] * cz));
+        }
+        __syncthreads(); // sCount / sBase are rewritten by the next iteration
     }
 }
 
@@ -91,61 +118,119 @@ __global__ void k_front_keys(TraceParams tp, const float4* __restrict__ origins,
 #define PT_DEFER_SHADOW_DEFAULT 12 // measured on B200, cfg2 (gpurun_out r01b sweep): 0.400 ms immediate, 0.378 / 0.374 / 0.382 ms with 8 / 12 / 16
 #endif
 // Persistent warps; see ptrace.cuh. DEFER = 0: triangles tested right after their node; DEFER > 0: parked until DEFER lanes hold some.
+#ifndef PT_MIN_BLOCKS
+#define PT_MIN_BLOCKS 8 // resident CTAs per SM the traversal kernels are compiled for (64 registers)
+#endif
 template <int DEFER>
-__global__ void __launch_bounds__(128, 8) k_trace_primary(DeviceScene sc, TraceParams tp, RayMap rm, const float4* __restrict__ origins,
+__global__ void __launch_bounds__(128, PT_MIN_BLOCKS) k_trace_primary(DeviceScene sc, TraceParams tp, RayMap rm, const float4* __restrict__ origins,
                                                        const float4* __restrict__ dirs, const float4* __restrict__ invDirs, vkx_hit* __restrict__ hits, float4* __restrict__ rays,
                                                        uint32_t* __restrict__ missQueue, uint32_t* __restrict__ frontQueue, uint32_t* __restrict__ counters) {
     PrimarySrc src; src.tp = tp; src.rm = rm; src.origins = origins; src.dirs = dirs; src.invDirs = invDirs; src.hits = hits; src.ri = 0;
     src.rays = rays; src.missQueue = missQueue; src.frontQueue = frontQueue; src.counters = counters;
     if (DEFER == 0) persistentTrace<false>(sc.nodes, sc.tris, src, rm.numThreads, counters + 1);
-    else persistentTraceDeferred<false, DEFER>(sc.nodes, sc.tris, src, rm.numThreads, counters + 1);
+    else if (DEFER < 0) persistentTracePF<false>(sc.nodes, sc.tris, src, rm.numThreads, counters + 1);
+    else persistentTraceDeferred<false, (DEFER > 0 ? DEFER : 1)>(sc.nodes, sc.tris, src, rm.numThreads, counters + 1);
 }
 
 struct ShadowSrc {
     vkx_light light; const float4* queue; float4* rays; uint8_t* shadowFlags; uint32_t count;
-    uint32_t ri; float lx, ly, lz;
+    uint32_t ri; float lx, ly, lz, lt;
     __device__ __forceinline__ bool load(uint32_t item, Ray& r, float& tmin, float& tmax, uint32_t& cullMask) {
         if (item >= count) return false;
         const float4 q0 = queue[2 * size_t(item)], q1 = queue[2 * size_t(item) + 1];
-        ri = __float_as_uint(q0.w); lx = q1.x; ly = q1.y; lz = q1.z;
+        ri = __float_as_uint(q0.w); lx = q1.x; ly = q1.y; lz = q1.z; lt = q1.w;
         r = makeRay(q0.x, q0.y, q0.z, light.direction[0], light.direction[1], light.direction[2]);
         tmin = 0.1f; tmax = 10000.0f; cullMask = 0xFFu; // closesthit.glsl:270-281
         return true;
     }
     __device__ __forceinline__ void store(uint32_t, const HitRec& h, bool) {
-        if (!h.found) { float4 rec = rays[ri]; rec.x = lx; rec.y = ly; rec.z = lz; rays[ri] = rec; }
+        if (!h.found) rays[ri] = make_float4(lx, ly, lz, lt); // the queue entry carries the ray's depth: no read-modify-write (the load was 8 % of this kernel's stall samples)
         if (shadowFlags) shadowFlags[ri] = h.found ? 2 : 1;
     }
 };
 
 template <int DEFER>
-__global__ void __launch_bounds__(128, 8) k_trace_shadow(DeviceScene sc, vkx_light light, const float4* __restrict__ queue, const uint32_t* __restrict__ queueCount,
+__global__ void __launch_bounds__(128, PT_MIN_BLOCKS) k_trace_shadow(DeviceScene sc, vkx_light light, const float4* __restrict__ queue, const uint32_t* __restrict__ queueCount,
                                                       float4* __restrict__ rays, uint8_t* __restrict__ shadowFlags, uint32_t* __restrict__ counter) {
-    ShadowSrc src; src.light = light; src.queue = queue; src.rays = rays; src.shadowFlags = shadowFlags; src.count = *queueCount; src.ri = 0; src.lx = src.ly = src.lz = 0.f;
+    ShadowSrc src; src.light = light; src.queue = queue; src.rays = rays; src.shadowFlags = shadowFlags; src.count = *queueCount; src.ri = 0; src.lx = src.ly = src.lz = src.lt = 0.f;
     if (DEFER == 0) persistentTrace<true>(sc.nodes, sc.tris, src, src.count, counter);
-    else persistentTraceDeferred<true, DEFER>(sc.nodes, sc.tris, src, src.count, counter);
+    else if (DEFER < 0) persistentTracePF<true>(sc.nodes, sc.tris, src, src.count, counter);
+    else persistentTraceDeferred<true, (DEFER > 0 ? DEFER : 1)>(sc.nodes, sc.tris, src, src.count, counter);
+}
+
+// ---- ray-pool variants (ptrace.cuh::poolTrace): K rays per lane in shared memory, node passes and triangle passes at full width
+struct PrimaryPoolSrc {
+    TraceParams tp; RayMap rm; const float4* origins; const float4* dirs; const float4* invDirs; vkx_hit* hits; float4* rays;
+    __device__ __forceinline__ uint32_t rayOf(uint32_t ri) const { return (tp.raysPerProbe & (tp.raysPerProbe - 1u)) == 0u ? ri & (tp.raysPerProbe - 1u) : ri % tp.raysPerProbe; }
+    __device__ __forceinline__ bool begin(uint32_t item, uint32_t& tag, float& ox, float& oy, float& oz, float& tmax) {
+        uint32_t slot, ray;
+        if (!mapRay(rm, item, slot, ray)) return false;
+        tag = slot * tp.raysPerProbe + ray;
+        const float4 o = __ldg(origins + slot);
+        ox = o.x; oy = o.y; oz = o.z; tmax = tp.tmax;
+        return true;
+    }
+    __device__ __forceinline__ void nodeRay(uint32_t tag, float& ix, float& iy, float& iz, uint32_t& octw) const { const float4 id = __ldg(invDirs + rayOf(tag)); ix = id.x; iy = id.y; iz = id.z; octw = __float_as_uint(id.w); }
+    __device__ __forceinline__ void triRay(uint32_t tag, float& dx, float& dy, float& dz) const { const float4 d = __ldg(dirs + rayOf(tag)); dx = d.x; dy = d.y; dz = d.z; }
+    __device__ __forceinline__ float tmin() const { return tp.tmin; }
+    __device__ __forceinline__ uint32_t cullMask() const { return VKX_INSTANCE_STATIC | VKX_INSTANCE_DYNAMIC; }
+    __device__ __forceinline__ void finish(uint32_t ri, bool found, float t, float u, float v, uint32_t inst, uint32_t prim) {
+        vkx_hit out; out.t = t; out.instance = inst; out.primitive = prim; out.u = u; out.v = v;
+        hits[ri] = out;
+        if (found && (prim & 0x80000000u)) rays[ri] = make_float4(0.f, 0.f, 0.f, t * 0.80f); // closesthit.glsl:137-141
+    }
+};
+// Shadow rays share one direction: reciprocal / octant are per-kernel constants; the visibility goes to a byte per queue item and
+// k_apply_shadow writes the lit colour of the unoccluded ones (no per-ray colour in the pool, no loads on the finishing path).
+struct ShadowPoolSrc {
+    const float4* queue; uint8_t* visibility; uint32_t count; float dx, dy, dz, ix, iy, iz; uint32_t octw;
+    __device__ __forceinline__ bool begin(uint32_t item, uint32_t& tag, float& ox, float& oy, float& oz, float& tmax) {
+        if (item >= count) return false;
+        const float4 q0 = queue[2 * size_t(item)];
+        tag = item; ox = q0.x; oy = q0.y; oz = q0.z; tmax = 10000.0f; // closesthit.glsl:270-281
+        return true;
+    }
+    __device__ __forceinline__ void nodeRay(uint32_t, float& x, float& y, float& z, uint32_t& o) const { x = ix; y = iy; z = iz; o = octw; }
+    __device__ __forceinline__ void triRay(uint32_t, float& x, float& y, float& z) const { x = dx; y = dy; z = dz; }
+    __device__ __forceinline__ float tmin() const { return 0.1f; }
+    __device__ __forceinline__ uint32_t cullMask() const { return 0xFFu; }
+    __device__ __forceinline__ void finish(uint32_t item, bool found, float, float, float, uint32_t, uint32_t) { visibility[item] = found ? 2 : 1; }
+};
+
+#ifndef POOL_K
+#define POOL_K 2
+#endif
+#ifndef POOL_TRI_THRESH
+#define POOL_TRI_THRESH 20
+#endif
+template <int STK>
+__global__ void __launch_bounds__(128) k_trace_primary_pool(DeviceScene sc, TraceParams tp, RayMap rm, const float4* __restrict__ origins, const float4* __restrict__ dirs,
+                                                           const float4* __restrict__ invDirs, vkx_hit* __restrict__ hits, float4* __restrict__ rays, uint32_t* __restrict__ counters) {
+    extern __shared__ uint32_t sPool[];
+    PrimaryPoolSrc src; src.tp = tp; src.rm = rm; src.origins = origins; src.dirs = dirs; src.invDirs = invDirs; src.hits = hits; src.rays = rays;
+    poolTrace<false, POOL_K, STK, POOL_TRI_THRESH>(sc.nodes, sc.tris, src, rm.numThreads, counters + 1, sPool + (threadIdx.x >> 5) * PoolLayout<POOL_K, STK>::wordsPerWarp);
+}
+template <int STK>
+__global__ void __launch_bounds__(128) k_trace_shadow_pool(DeviceScene sc, vkx_light light, const float4* __restrict__ queue, const uint32_t* __restrict__ queueCount,
+                                                          uint8_t* __restrict__ visibility, uint32_t* __restrict__ counter) {
+    extern __shared__ uint32_t sPool[];
+    const Ray lr = makeRay(0.f, 0.f, 0.f, light.direction[0], light.direction[1], light.direction[2]);
+    ShadowPoolSrc src; src.queue = queue; src.visibility = visibility; src.count = *queueCount;
+    src.dx = lr.dx; src.dy = lr.dy; src.dz = lr.dz; src.ix = lr.ix; src.iy = lr.iy; src.iz = lr.iz; src.octw = lr.oct;
+    poolTrace<true, POOL_K, STK, POOL_TRI_THRESH>(sc.nodes, sc.tris, src, src.count, counter, sPool + (threadIdx.x >> 5) * PoolLayout<POOL_K, STK>::wordsPerWarp);
+}
+// Shadow rays that escaped: the ray record becomes the lit colour the shading kernel left in the queue (closesthit.glsl:282-286)
+__global__ void k_apply_shadow(const float4* __restrict__ queue, const uint32_t* __restrict__ queueCount, const uint8_t* __restrict__ visibility, float4* __restrict__ rays, uint8_t* __restrict__ shadowFlags) {
+    const uint32_t n = *queueCount;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t vis = visibility[i];
+        const uint32_t ri = __float_as_uint(queue[2 * size_t(i)].w);
+        if (vis == 1u) rays[ri] = queue[2 * size_t(i) + 1];
+        if (shadowFlags) shadowFlags[ri] = uint8_t(vis);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ blend
-__device__ __forceinline__ void borderSource(int T, int x, int y, int& sx, int& sy) { // probesCopyBorders.comp:21-220 as a formula
-    const int L = T - 1;
-    const bool bx = (x == 0 || x == L), by = (y == 0 || y == L);
-    if (bx && by) { sx = x == 0 ? L - 1 : 1; sy = y == 0 ? L - 1 : 1; }
-    else if (bx) { sx = x == 0 ? 1 : L - 1; sy = L - y; }
-    else { sx = L - x; sy = y == 0 ? 1 : L - 1; }
-}
-
-struct BlendParams {
-    vkx_grid_info grid;
-    uint32_t raysPerProbe, count;
-    float gridCellLen;   // length(probeGridCellSize)
-};
-
-// Per-frame weight table shared by every probe (the texel directions are fixed and all probes use the same rotated ray
-// directions): W[ray][col], col 0..195 depth texels pow(max(0, dot), sharpness), col 224..259 irradiance texels max(0, dot)
-// (probesUpdate.glsl:60,75,80). Same arithmetic as evaluating the weight inside the blend loop.
-#define BLEND_COLS 288
-#define BLEND_IRR_COL0 224
 #ifndef BLEND_P
 #define BLEND_P 8
 #endif
@@ -169,7 +254,6 @@ __global__ void __launch_bounds__(BLEND_COLS) k_blend_weights(float depthSharpne
 }
 
 // Sum of a texel's weights over the rays, in ray order (the `result.w` every blend thread of that texel would accumulate): row BLEND_WSUM_ROW.
-#define BLEND_WSUM_ROW VKX_MAX_RAYS_PER_PROBE
 __global__ void __launch_bounds__(BLEND_COLS) k_blend_weight_sums(uint32_t N, float* __restrict__ W) {
     float rw = 0.0f;
     for (uint32_t i = 0; i < N; ++i) rw = rw + W[size_t(i) * BLEND_COLS + threadIdx.x];
@@ -304,12 +388,12 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(BlendParams bp, DeviceP
         int x, y, sx, sy;
         if (b < 60u) {
             if (b < 16u) { x = int(b); y = 0; } else if (b < 32u) { x = int(b) - 16; y = 15; } else if (b < 46u) { x = 0; y = int(b) - 32 + 1; } else { x = 15; y = int(b) - 46 + 1; }
-            borderSource(16, x, y, sx, sy);
+            blendBorderSource(16, x, y, sx, sy);
             sDep[p][y * 16 + x] = sDep[p][sy * 16 + sx];
         } else {
             const int c = int(b) - 60;
             if (c < 8) { x = c; y = 0; } else if (c < 16) { x = c - 8; y = 7; } else if (c < 22) { x = 0; y = c - 16 + 1; } else { x = 7; y = c - 22 + 1; }
-            borderSource(8, x, y, sx, sy);
+            blendBorderSource(8, x, y, sx, sy);
             sIrr[p][y * 8 + x] = sIrr[p][sy * 8 + sx];
         }
     }
@@ -502,8 +586,9 @@ int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* /*unused*/,
     // Leaf deferral of the two persistent traversals (ptrace.cuh): 0 = off, else the number of waiting lanes that triggers a triangle phase.
     // Tuning knobs (results are identical for every value): VKX_PT_DEFER / VKX_PT_DEFER_SHADOW in {0, 8, 12, 16}.
     static int deferPrimary = -1, deferShadow = -1;
+    static const bool poolMode = [] { const char* e = getenv("VKX_PT_POOL"); return e ? atoi(e) != 0 : false; }();
     if (deferPrimary < 0) {
-        auto pick = [](const char* name, int dflt) { const char* e = getenv(name); int v = e ? atoi(e) : dflt; return v <= 0 ? 0 : v <= 8 ? 8 : v <= 12 ? 12 : 16; };
+        auto pick = [](const char* name, int dflt) { const char* e = getenv(name); int v = e ? atoi(e) : dflt; return v < 0 ? -1 : v == 0 ? 0 : v <= 8 ? 8 : v <= 12 ? 12 : 16; }; // -1: prefetching variant
         deferPrimary = pick("VKX_PT_DEFER", PT_DEFER_PRIMARY_DEFAULT); deferShadow = pick("VKX_PT_DEFER_SHADOW", PT_DEFER_SHADOW_DEFAULT);
     }
     if (!ctx->traceBlocksPerSm) { int a = 0, b = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_trace_primary<0>, 128, 0); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace_shadow<0>, 128, 0); ctx->traceBlocksPerSm = std::max(1, std::min(a, b)); }
@@ -511,6 +596,10 @@ int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* /*unused*/,
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
     k_blend_weights<<<(N + 3u) & ~3u, BLEND_COLS, 0, st>>>(ctx->grid.depthSharpness, N, ctx->dDirs, ctx->dBlendW); LAUNCH_CHECK(ctx);
     k_blend_weight_sums<<<1, BLEND_COLS, 0, st>>>(N, ctx->dBlendW); LAUNCH_CHECK(ctx);
+    // blend on the tensor cores (blend_tc.cu) unless tiles go straight to peer memory (fused exchange) or VKX_BLEND=simt asks for the CUDA-core kernel
+    static const bool blendSimt = [] { const char* e = getenv("VKX_BLEND"); return e && !strcmp(e, "simt"); }();
+    const bool blendTc = !blendSimt && !ctx->blendToPeers;
+    if (blendTc) { int rc = blendTcWeights(ctx, st); if (rc != VKX_OK) return rc; }
     k_dir_table<<<divUp(N, 128), 128, 0, st>>>(N, ctx->dDirs, ctx->dInvDirs); LAUNCH_CHECK(ctx);
     // One chunk: slots are the caller's list positions (ray/hit buffers are laid out [slot][ray]) and `order` only schedules them.
     // Several chunks: the list is first gathered in block order, a chunk is then a contiguous piece of it with identity order.
@@ -530,21 +619,41 @@ int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* /*unused*/,
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->dQueueCount, 0, 32, st)); // [0] shadow queue length, [1] primary work counter, [2] shadow work counter, [3] misses, [4] front hits
         k_origin_table<<<divUp(n, 128), 128, 0, st>>>(ctx->grid, idx, n, ctx->dOrigins); LAUNCH_CHECK(ctx);
         if (timed) { CUDA_TRY(ctx, cudaEventRecord(ctx->kev[0], st)); ctx->kevProbes = n; }
+        // ray-pool traversal (VKX_PT_POOL, default on): needs a shared-memory stack of depth - 1 group entries per ray
+        const int poolStk = ctx->bvh.depth <= 9u ? 8 : ctx->bvh.depth <= 13u ? 12 : 0;
+        const bool pool = poolMode && poolStk;
+        const size_t poolBytes = size_t(4) * (poolStk == 8 ? PoolLayout<POOL_K, 8>::wordsPerWarp : PoolLayout<POOL_K, 12>::wordsPerWarp) * 4;
+        unsigned poolBlocks = 0;
+        if (pool) {
+            int& cached = poolStk == 8 ? ctx->poolBlocksPerSm[0] : ctx->poolBlocksPerSm[1];
+            if (!cached) {
+                int a = 0, b = 0;
+                if (poolStk == 8) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_trace_primary_pool<8>, 128, poolBytes); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace_shadow_pool<8>, 128, poolBytes); }
+                else { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_trace_primary_pool<12>, 128, poolBytes); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace_shadow_pool<12>, 128, poolBytes); }
+                cached = std::max(1, std::min(a, b));
+            }
+            poolBlocks = unsigned(ctx->smCount * cached);
+        }
+        if (pool) {
+            if (poolStk == 8) k_trace_primary_pool<8><<<poolBlocks, 128, poolBytes, st>>>(sc, tp, rm, ctx->dOrigins, ctx->dDirs, ctx->dInvDirs, ctx->dHits, ctx->dRays, ctx->dQueueCount);
+            else k_trace_primary_pool<12><<<poolBlocks, 128, poolBytes, st>>>(sc, tp, rm, ctx->dOrigins, ctx->dDirs, ctx->dInvDirs, ctx->dHits, ctx->dRays, ctx->dQueueCount);
+        } else
 #define VKX_LAUNCH_PRIMARY(D) k_trace_primary<D><<<persistentBlocks, 128, 0, st>>>(sc, tp, rm, ctx->dOrigins, ctx->dDirs, ctx->dInvDirs, ctx->dHits, ctx->dRays, ctx->dMissQueue, ctx->dFrontQueue, ctx->dQueueCount)
-        switch (deferPrimary) { case 8: VKX_LAUNCH_PRIMARY(8); break; case 12: VKX_LAUNCH_PRIMARY(12); break; case 16: VKX_LAUNCH_PRIMARY(16); break; default: VKX_LAUNCH_PRIMARY(0); }
+        switch (deferPrimary) { case -1: VKX_LAUNCH_PRIMARY(-1); break; case 8: VKX_LAUNCH_PRIMARY(8); break; case 12: VKX_LAUNCH_PRIMARY(12); break; case 16: VKX_LAUNCH_PRIMARY(16); break; default: VKX_LAUNCH_PRIMARY(0); }
 #undef VKX_LAUNCH_PRIMARY
         LAUNCH_CHECK(ctx);
         if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[1], st));
+        // front-hit keys default to all-ones (unused slots sort to the end); then one dense pass fills both queues
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->dFrontKeys, 0xFF, size_t(numRays) * 4, st));
+        k_classify_hits<<<std::min<unsigned>(divUp(numRays, 256), unsigned(ctx->smCount) * 16u), 256, 0, st>>>(tp, ctx->dOrigins, ctx->dDirs, ctx->dHits, ctx->dMissQueue, ctx->dFrontQueue, ctx->dFrontKeys, ctx->dQueueCount); LAUNCH_CHECK(ctx);
         // The sky kernel only needs the miss queue: it runs on a second stream, concurrently with the sort and the front-hit shading.
         const unsigned shadeBlocks = std::min<unsigned>(divUp(numRays, 128), unsigned(ctx->smCount) * 16u);
         CUDA_TRY(ctx, cudaEventRecord(ctx->auxEvent[0], st));
         CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->auxStream, ctx->auxEvent[0], 0));
         launchShadeMiss(shadeBlocks, ctx->auxStream, sp, ctx->dOrigins, ctx->dDirs, ctx->dMissQueue, ctx->dQueueCount, ctx->dRays); LAUNCH_CHECK(ctx);
         CUDA_TRY(ctx, cudaEventRecord(ctx->auxEvent[1], ctx->auxStream));
-        { // front-hit queue sorted by grid cell (radix sort over just the bits a cell index needs; unused slots carry all-ones keys).
+        { // front-hit queue sorted by grid cell (radix sort over just the bits a cell index needs).
           // A counting sort with a per-cell atomic histogram was slower: hit points cluster in few cells.
-            CUDA_TRY(ctx, cudaMemsetAsync(ctx->dFrontKeys, 0xFF, size_t(numRays) * 4, st));
-            k_front_keys<<<std::min<unsigned>(divUp(numRays, 256), unsigned(ctx->smCount) * 8u), 256, 0, st>>>(tp, ctx->dOrigins, ctx->dDirs, ctx->dHits, ctx->dFrontQueue, ctx->dQueueCount, ctx->dFrontKeys); LAUNCH_CHECK(ctx);
             uint32_t cells = ctx->probeCount, bits = 1; while ((1u << bits) <= cells) ++bits;
             size_t need = 0;
             cub::DeviceRadixSort::SortPairs(nullptr, need, ctx->dFrontKeys, ctx->dFrontKeysOut, ctx->dFrontQueue, ctx->dFrontQueueSorted, int(numRays), 0, int(bits), st);
@@ -556,8 +665,14 @@ int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* /*unused*/,
         launchShadeFront(shadeBlocks, st, sc, pr, sp, ctx->dOrigins, ctx->dDirs, ctx->dHits, ctx->dFrontQueueSorted, ctx->dQueueCount, ctx->dRays, ctx->dShadowQueue); LAUNCH_CHECK(ctx);
         if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[2], st));
         if (ctx->debugBuffers) CUDA_TRY(ctx, cudaMemsetAsync(ctx->dShadowFlags, 0, numRays, st));
+        if (pool) {
+            if (poolStk == 8) k_trace_shadow_pool<8><<<poolBlocks, 128, poolBytes, st>>>(sc, light, ctx->dShadowQueue, ctx->dQueueCount, ctx->dShadowVis, ctx->dQueueCount + 2);
+            else k_trace_shadow_pool<12><<<poolBlocks, 128, poolBytes, st>>>(sc, light, ctx->dShadowQueue, ctx->dQueueCount, ctx->dShadowVis, ctx->dQueueCount + 2);
+            LAUNCH_CHECK(ctx);
+            k_apply_shadow<<<std::min<unsigned>(divUp(numRays, 256), unsigned(ctx->smCount) * 16u), 256, 0, st>>>(ctx->dShadowQueue, ctx->dQueueCount, ctx->dShadowVis, ctx->dRays, ctx->debugBuffers ? ctx->dShadowFlags : nullptr);
+        } else
 #define VKX_LAUNCH_SHADOW(D) k_trace_shadow<D><<<persistentBlocks, 128, 0, st>>>(sc, light, ctx->dShadowQueue, ctx->dQueueCount, ctx->dRays, ctx->debugBuffers ? ctx->dShadowFlags : nullptr, ctx->dQueueCount + 2)
-        switch (deferShadow) { case 8: VKX_LAUNCH_SHADOW(8); break; case 12: VKX_LAUNCH_SHADOW(12); break; case 16: VKX_LAUNCH_SHADOW(16); break; default: VKX_LAUNCH_SHADOW(0); }
+        switch (deferShadow) { case -1: VKX_LAUNCH_SHADOW(-1); break; case 8: VKX_LAUNCH_SHADOW(8); break; case 12: VKX_LAUNCH_SHADOW(12); break; case 16: VKX_LAUNCH_SHADOW(16); break; default: VKX_LAUNCH_SHADOW(0); }
 #undef VKX_LAUNCH_SHADOW
         LAUNCH_CHECK(ctx);
         if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[3], st));
@@ -565,7 +680,8 @@ int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* /*unused*/,
         bp.count = n;
         CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->auxEvent[1], 0)); // sky results
         if (ctx->copyPending && ctx->copyReadsWork) { CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->evCopyDone, 0)); ctx->copyPending = false; ctx->copyReadsWork = false; } // a queued read-back still reads the work atlases
-        k_blend<<<divUp(n, BLEND_P), BLEND_THREADS, BLEND_SMEM_BYTES, st>>>(bp, pr, idx, ctx->dRays, ctx->dBlendW, ctx->debugBuffers ? ctx->dIrrUnpacked : nullptr, ctx->debugBuffers ? ctx->dDepUnpacked : nullptr, base, ctx->blendToPeers ? ctx->blendPeers : PeerTargets{}); LAUNCH_CHECK(ctx);
+        if (blendTc) { int rc = blendTcLaunch(ctx, bp, pr, idx, n, base, st); if (rc != VKX_OK) return rc; }
+        else k_blend<<<divUp(n, BLEND_P), BLEND_THREADS, BLEND_SMEM_BYTES, st>>>(bp, pr, idx, ctx->dRays, ctx->dBlendW, ctx->debugBuffers ? ctx->dIrrUnpacked : nullptr, ctx->debugBuffers ? ctx->dDepUnpacked : nullptr, base, ctx->blendToPeers ? ctx->blendPeers : PeerTargets{}); LAUNCH_CHECK(ctx);
         if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[4], st));
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], st));

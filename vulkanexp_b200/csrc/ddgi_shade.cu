@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(128, 6) k_shade_front(DeviceScene sc, DevicePr
         const uint32_t qi = i;
         if (i == 0u) counters[0] = n;
         queue[2 * size_t(qi)] = make_float4(position.x, position.y, position.z, __uint_as_float(ri));
-        queue[2 * size_t(qi) + 1] = make_float4(lit.x, lit.y, lit.z, 0.0f);
+        queue[2 * size_t(qi) + 1] = make_float4(lit.x, lit.y, lit.z, h.t); // the complete ray record if the shadow ray escapes
     }
 }
 
