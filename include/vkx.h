@@ -179,7 +179,8 @@ int vkx_texture_sample(vkx_ctx* ctx, uint32_t texture, const float* uv, const fl
 /* Dynamic instances: Renderer::updateAccelerationStructureInstances + updateTLAS (src/Renderer.cpp:671-742, called from
  * onHierarchicalChanges). New transforms / masks / ids for the instance list of vkx_scene_upload (same count, same meshes). The
  * reference refits its TLAS in place; here all instanced geometry lives in one world-space BVH, so the structure is marked stale
- * and the next vkx_bvh_build rebuilds it (the same deterministic build: the result equals a fresh upload with these transforms). */
+ * and the next vkx_bvh_build rebuilds it (the same deterministic build: the result equals a fresh upload with these transforms) or
+ * vkx_bvh_refit re-fits it in place like the reference's TLAS update. */
 int vkx_instances_update(vkx_ctx* ctx, const vkx_instance* instances, size_t numInstances);
 /* Skinned meshes: vertexSkinning.comp (src/shaders/vertexSkinning.comp:37-60) as dispatched per SkinnedMeshRendererComponent by
  * Renderer::updateSkinnedVertexBuffer (src/Renderer.cpp:201-240), then Renderer::updateSkinnedBLAS (src/Renderer.cpp:644-669).
@@ -199,6 +200,14 @@ int vkx_vertices_download(vkx_ctx* ctx, size_t firstVertex, size_t count, vkx_ve
 /* Deterministic binned-SAH build of the 8-wide compressed BVH on the device (replaces the driver's BLAS/TLAS
  * build, src/Renderer.cpp:272-449,525-642). Topology is bit-identical to oracle/bvh.cpp. */
 int vkx_bvh_build(vkx_ctx* ctx);
+/* Topology-preserving refit: Renderer::updateTLAS (src/Renderer.cpp:735-742, vkCmdBuildAccelerationStructuresKHR in UPDATE mode
+ * after updateAccelerationStructureInstances, :671-733) and the in-place skinned BLAS update (:644-669). After vkx_instances_update
+ * or vkx_skin_vertices: the tree, the slot assignment and the triangle order of the last vkx_bvh_build stay; the world-space
+ * triangles are recomputed and every node is re-quantised from the new bounds, leaves first (one launch per level). With unchanged
+ * inputs the result is the built structure byte for byte; otherwise it is a conservative hierarchy over the same triangles (hits
+ * equal a rebuild's up to grazing ties) whose quality decays with the motion, as the reference's refitted TLAS does: rebuild with
+ * vkx_bvh_build when that matters. Bytes are identical to oracle/bvh.cpp::refit. */
+int vkx_bvh_refit(vkx_ctx* ctx);
 int vkx_bvh_info_get(vkx_ctx* ctx, vkx_bvh_info* out);
 /* Copies the device BVH back: nodes (80 B each) and triangles (48 B each). Either pointer may be NULL. */
 int vkx_bvh_download(vkx_ctx* ctx, void* nodes, size_t nodesBytes, void* triangles, size_t trianglesBytes);

@@ -299,8 +299,8 @@ def test_refit_restatement_properties():
     lo, hi = np.array(flat["bounds_min"]), np.array(flat["bounds_max"])
     org = rng.uniform(lo, hi, size=(20000, 3)).astype(np.float32)
     d = rng.normal(size=(20000, 3)); d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
-    ha = o.trace(org, d, 0.001, 1000.0)[0] if isinstance(o.trace(org[:1], d[:1], 0.001, 1000.0), tuple) else o.trace(org, d, 0.001, 1000.0)
-    hb = r.trace(org, d, 0.001, 1000.0)[0] if isinstance(r.trace(org[:1], d[:1], 0.001, 1000.0), tuple) else r.trace(org, d, 0.001, 1000.0)
+    ha = o.trace(org, d, 0.001, 1000.0)
+    hb = r.trace(org, d, 0.001, 1000.0)
     same = (ha["t"] == hb["t"]) & (ha["instance"] == hb["instance"]) & (ha["primitive"] == hb["primitive"])
     assert same.mean() > 0.9999, "refit and rebuilt structures must find the same hits (up to grazing ties): %g" % same.mean()
     assert (ha["t"] > 0).mean() > 0.5

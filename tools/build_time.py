@@ -9,3 +9,7 @@ for name, mk in (("cfg2", synth.make_cfg2), ("cfg4", synth.make_cfg4)):
         t0 = time.perf_counter(); g.bvh_build(); dt = (time.perf_counter() - t0) * 1e3
         info = g.bvh_info()
         print(name, "build", i, "wall %.1f ms, event %.1f ms, %d tris, %d nodes, depth %d" % (dt, info.buildMs, info.numTriangles, info.numNodes, info.depth), flush=True)
+    for i in range(3):  # topology-preserving refit (vkx_bvh_refit) of the same structure
+        g.instances_update(flat["instances"])
+        t0 = time.perf_counter(); g.bvh_refit(); dt = (time.perf_counter() - t0) * 1e3
+        print(name, "refit", i, "wall %.2f ms, event %.2f ms" % (dt, g.bvh_info().buildMs), flush=True)

@@ -223,6 +223,9 @@ class Context:
     def bvh_build(self):
         self._check(self.l.vkx_bvh_build(self.h))
 
+    def bvh_refit(self):
+        self._check(self.l.vkx_bvh_refit(self.h))
+
     def bvh_info(self):
         info = BvhInfo()
         self._check(self.l.vkx_bvh_info_get(self.h, C.byref(info)))

@@ -110,7 +110,7 @@ void vkx_destroy(vkx_ctx* ctx) {
     freeProbes(ctx); freeShadow(ctx); freeTextures(ctx);
     if (ctx->dSrgbLut) cudaFree(ctx->dSrgbLut);
     if (ctx->dSrgbThreshold) cudaFree(ctx->dSrgbThreshold);
-    void* ptrs[] = {ctx->dVertices, ctx->dIndices, ctx->dOffsets, ctx->dMeshCounts, ctx->dMaterials, ctx->dInstances, ctx->dWorldToObject, ctx->dInstTriBase, ctx->dNodes, ctx->dTris, ctx->dNoise};
+    void* ptrs[] = {ctx->dVertices, ctx->dIndices, ctx->dOffsets, ctx->dMeshCounts, ctx->dMaterials, ctx->dInstances, ctx->dWorldToObject, ctx->dInstTriBase, ctx->dNodes, ctx->dTris, ctx->dNoise, ctx->dRefitScratch};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->sev) if (ev) cudaEventDestroy(ev);
@@ -202,7 +202,7 @@ int vkx_scene_upload(vkx_ctx* ctx, const vkx_vertex* vertices, size_t numVertice
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->numVertices = numVertices; ctx->numIndices = numIndices; ctx->numMeshes = numMeshes; ctx->numMaterials = numMaterials;
     ctx->numInstances = numInstances; ctx->numFlatTris = total; ctx->texturesUsed = texturesUsed;
-    ctx->bvhBuilt = false;
+    ctx->bvhBuilt = false; ctx->bvhTopology = false;
     return VKX_OK;
 }
 
@@ -228,11 +228,17 @@ int vkx_instances_update(vkx_ctx* ctx, const vkx_instance* instances, size_t num
     }
     CUDA_TRY(ctx, cudaMemcpy(ctx->dInstances, instances, numInstances * sizeof(vkx_instance), cudaMemcpyHostToDevice));
     CUDA_TRY(ctx, cudaMemcpy(ctx->dWorldToObject, w2o.data(), w2o.size() * 4, cudaMemcpyHostToDevice));
-    ctx->bvhBuilt = false; // the flattened world-space BVH is stale: vkx_bvh_build rebuilds it (deterministic, same spec as the first build)
+    ctx->bvhBuilt = false; // the flattened world-space BVH is stale: vkx_bvh_build rebuilds it (deterministic, same spec as the first build), vkx_bvh_refit re-fits it
     return VKX_OK;
 }
 
 int vkx_bvh_build(vkx_ctx* ctx) { BIND(ctx); return bvhBuildDevice(ctx); }
+
+int vkx_bvh_refit(vkx_ctx* ctx) {
+    BIND(ctx);
+    if (!ctx->bvhTopology) return vkx_fail(ctx, VKX_E_INVALID, "vkx_bvh_refit: no built BVH for the uploaded scene (call vkx_bvh_build first)");
+    return bvhRefitDevice(ctx);
+}
 
 int vkx_bvh_info_get(vkx_ctx* ctx, vkx_bvh_info* out) {
     if (!ctx || !out) return VKX_E_INVALID;

@@ -24,9 +24,14 @@ __device__ __forceinline__ void blendBorderSource(int T, int x, int y, int& sx, 
 }
 
 // ---- tensor-core blend geometry (blend_tc.cu)
-#define BTC_P 64u            // probes per CTA: N = 128 (depth planes) / 192 (colour planes)
+#define BTC_P 64u            // probes per tile: N = 128 (depth planes) / 192 (colour planes)
 #define BTC_KC 16u           // rays per chunk (two K = 8 TF32 MMAs)
-#define BTC_THREADS 256u
+#define BTC_STAGES 2u        // shared-memory stages (chunks in flight between the producer warps and the MMA warp)
+#define BTC_EPI_WARPS 8u     // warps 0..3: accumulator rows of weight tile 0, warps 4..7: weight tile 1 (a warp reads the TMEM lane quarter warp % 4)
+#define BTC_PROD_WARPS 8u    // warps 8..15: ray records -> TF32 hi / lo operand tiles
+#define BTC_MMA_WARP 16u     // one lane issues tcgen05.mma
+#define BTC_TMA_WARP 17u     // one lane issues the bulk copies of the weight image
+#define BTC_THREADS (32u * (BTC_EPI_WARPS + BTC_PROD_WARPS + 2u))
 #define BTC_MAX_CHUNKS (VKX_MAX_RAYS_PER_PROBE / 16)
 #define BTC_LBO 128u         // bytes between the 16-byte K cores of an operand tile (core matrix = 8 rows x 16 bytes)
 #define BTC_SBO 528u         // bytes between 8-row groups: 4 K cores + 16 bytes, so that 8 probes x 4 rays of a warp hit 32 different banks
@@ -35,7 +40,7 @@ __device__ __forceinline__ void blendBorderSource(int T, int x, int y, int& sx, 
 #define BTC_BD_TILE_BYTES (16u * BTC_SBO)                // 128 rows: (probe, d | d^2)
 #define BTC_BC_TILE_BYTES (24u * BTC_SBO)                // 192 rows: (probe, r | g | b)
 #define BTC_STAGE_BYTES (BTC_A_CHUNK_BYTES + 2u * BTC_BD_TILE_BYTES + 2u * BTC_BC_TILE_BYTES)
-#define BTC_SMEM_BYTES (2u * BTC_STAGE_BYTES)
+#define BTC_SMEM_BYTES (BTC_STAGES * BTC_STAGE_BYTES)
 #define BTC_IMAGE_BYTES (size_t(BTC_MAX_CHUNKS) * BTC_A_CHUNK_BYTES)
 
 int blendTcWeights(vkx_ctx* ctx, cudaStream_t st);  // per frame, after k_blend_weights: the A-operand image

@@ -419,7 +419,7 @@ int bvhBuildDevice(vkx_ctx* ctx) {
     const uint32_t T = uint32_t(ctx->numFlatTris);
     if (ctx->dNodes) { cudaFree(ctx->dNodes); ctx->dNodes = nullptr; }
     if (ctx->dTris) { cudaFree(ctx->dTris); ctx->dTris = nullptr; }
-    ctx->bvhBuilt = false;
+    ctx->bvhBuilt = false; ctx->bvhTopology = false;
     memset(&ctx->bvh, 0, sizeof(ctx->bvh));
     cudaEvent_t e0, e1; CUDA_TRY(ctx, cudaEventCreate(&e0)); CUDA_TRY(ctx, cudaEventCreate(&e1));
     CUDA_TRY(ctx, cudaEventRecord(e0, st));
@@ -430,7 +430,7 @@ int bvhBuildDevice(vkx_ctx* ctx) {
         CUDA_TRY(ctx, cudaMalloc(&ctx->dTris, 48));
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dNodes, &n, 80, cudaMemcpyHostToDevice, st));
         CUDA_TRY(ctx, cudaStreamSynchronize(st));
-        ctx->bvh.numNodes = 1; ctx->bvh.depth = 1; ctx->bvhBuilt = true;
+        ctx->bvh.numNodes = 1; ctx->bvh.depth = 1; ctx->bvhBuilt = true; ctx->bvhTopology = true; ctx->hLevelBase = {0u, 1u};
         cudaEventDestroy(e0); cudaEventDestroy(e1);
         return VKX_OK;
     }
@@ -519,8 +519,10 @@ int bvhBuildDevice(vkx_ctx* ctx) {
     CUDA_TRY(ctx, cudaMemcpyAsync(wl[0].ref, &rootRef, 4, cudaMemcpyHostToDevice, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(wl[0].box, rootBox, 24, cudaMemcpyHostToDevice, st));
     uint32_t numW = 1, levelBase = 0, triBase = 0, depth = 0; cur = 0;
+    ctx->hLevelBase.clear();
     while (numW > 0) {
         depth++;
+        ctx->hLevelBase.push_back(levelBase);
         if (size_t(levelBase) + numW > maxWide) return vkx_fail(ctx, VKX_E_INVALID, "wide node overflow");
         k_collapse<<<divUp(numW, 64), 64, 0, st>>>(wl[cur], numW, bn, nodesTmp + levelBase, ws); LAUNCH_CHECK(ctx);
         // numInner / numTris have one extra slot so the exclusive scan's last element is the total
@@ -541,7 +543,136 @@ int bvhBuildDevice(vkx_ctx* ctx) {
     CUDA_TRY(ctx, cudaEventRecord(e1, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    ctx->hLevelBase.push_back(levelBase);
     ctx->bvh.numNodes = levelBase; ctx->bvh.numTriangles = T; ctx->bvh.depth = depth; ctx->bvh.buildMs = ms;
+    ctx->bvhBuilt = true; ctx->bvhTopology = true;
+    return VKX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ refit
+// Topology-preserving refit = Renderer::updateAccelerationStructureInstances + updateTLAS (reference src/Renderer.cpp:671-742: new
+// instance transforms, then vkCmdBuildAccelerationStructuresKHR in UPDATE mode) on the single-level wide BVH: tree, slot assignment
+// and triangle order stay; the world-space triangles are recomputed from the current vertex arena and instance transforms (so it
+// also serves skinned meshes, src/Renderer.cpp:644-669), and origin / exponents / child planes of every node are re-quantised from
+// the new bounds, one launch per level from the leaves up. Defined by oracle/bvh.cpp::refit; nodes and triangles are byte-identical
+// to it (tests/test_bvh_parity.py).
+namespace {
+
+__global__ void k_refit_tris(const vkx_vertex* __restrict__ vertices, const uint32_t* __restrict__ indices, const vkx_offset_entry* __restrict__ offsets,
+                             const vkx_instance* __restrict__ instances, uint32_t T, FlatTri* __restrict__ tris, float* __restrict__ triBox) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= T) return;
+    const uint32_t k = tris[g].inst & 0x00FFFFFFu, j = tris[g].prim & 0x7FFFFFFFu;
+    const vkx_instance in = instances[k];
+    const vkx_offset_entry oe = offsets[in.meshEntry];
+    const float* M = in.transform;
+    const float det = M[0] * (M[5] * M[10] - M[6] * M[9]) - M[1] * (M[4] * M[10] - M[6] * M[8]) + M[2] * (M[4] * M[9] - M[5] * M[8]);
+    const uint32_t flip = det < 0.0f ? 0x80000000u : 0u;
+    float w[3][3];
+    for (int c = 0; c < 3; ++c) {
+        const uint32_t vi = oe.vertexOffset + indices[oe.indexOffset + 3 * j + c];
+        const float* p = vertices[vi].pos;
+        const float x = p[0], y = p[1], z = p[2];
+        for (int r = 0; r < 3; ++r) w[c][r] = ((M[4 * r + 0] * x + M[4 * r + 1] * y) + M[4 * r + 2] * z) + M[4 * r + 3];
+    }
+    FlatTri t;
+    for (int ax = 0; ax < 3; ++ax) {
+        t.v0[ax] = w[0][ax];
+        t.e1[ax] = w[1][ax] - w[0][ax];
+        t.e2[ax] = w[2][ax] - w[0][ax];
+        triBox[6 * size_t(g) + ax] = kmin(kmin(w[0][ax], w[1][ax]), w[2][ax]);
+        triBox[6 * size_t(g) + 3 + ax] = kmax(kmax(w[0][ax], w[1][ax]), w[2][ax]);
+    }
+    t.inst = k | ((in.mask & 0xFFu) << 24);
+    t.prim = j | flip;
+    t.pad = 0;
+    tris[g] = t;
+}
+
+__global__ void k_refit_level(uint32_t base, uint32_t count, Node80* __restrict__ nodes, const float* __restrict__ triBox, float* __restrict__ nodeBox) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    const uint32_t n = base + j;
+    Node80 node = nodes[n];
+    float sb[8][6]; bool present[8];
+    float nb[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    for (int s = 0; s < 8; ++s) {
+        present[s] = false;
+        if (node.imask & (1u << s)) {
+            const uint32_t c = node.childBase + uint32_t(__popc(node.imask & ((1u << s) - 1u)));
+            for (int q = 0; q < 6; ++q) sb[s][q] = nodeBox[6 * size_t(c) + q];
+            present[s] = true;
+        } else {
+            const uint32_t cnt = uint32_t(__popc((node.valid >> (3 * s)) & 7u));
+            if (cnt) {
+                const uint32_t first = node.primBase + uint32_t(__popc(node.valid & 0x00FFFFFFu & ((1u << (3 * s)) - 1u)));
+                for (int a = 0; a < 3; ++a) { sb[s][a] = INFINITY; sb[s][3 + a] = -INFINITY; }
+                for (uint32_t i = 0; i < cnt; ++i)
+                    for (int a = 0; a < 3; ++a) { sb[s][a] = kmin(sb[s][a], triBox[6 * size_t(first + i) + a]); sb[s][3 + a] = kmax(sb[s][3 + a], triBox[6 * size_t(first + i) + 3 + a]); }
+                present[s] = true;
+            }
+        }
+        if (present[s]) for (int a = 0; a < 3; ++a) { nb[a] = kmin(nb[a], sb[s][a]); nb[3 + a] = kmax(nb[3 + a], sb[s][3 + a]); }
+    }
+    for (int q = 0; q < 6; ++q) nodeBox[6 * size_t(n) + q] = nb[q];
+    float cell[3], inv[3];
+    for (int a = 0; a < 3; ++a) { // spec section 3.4, the arithmetic of k_collapse
+        node.p[a] = nb[a];
+        const float ext = nb[3 + a] - nb[a];
+        const uint32_t bits = __float_as_uint(ext / 255.0f);
+        uint32_t e = (bits >> 23) & 0xFFu;
+        if (bits & 0x7FFFFFu) e += 1;
+        e = min(max(e, 1u), 253u);
+        if (ext * __uint_as_float((254u - e) << 23) > 255.0f) e = min(e + 1, 253u);
+        node.e[a] = uint8_t(e);
+        cell[a] = __uint_as_float(e << 23);
+        inv[a] = __uint_as_float((254u - e) << 23);
+    }
+    for (int s = 0; s < 8; ++s) {
+        for (int a = 0; a < 3; ++a) { node.qlo[a][s] = 0; node.qhi[a][s] = 0; }
+        if (!present[s]) continue;
+        for (int a = 0; a < 3; ++a) {
+            float ql = floorf((sb[s][a] - node.p[a]) * inv[a]);
+            ql = fminf(fmaxf(ql, 0.0f), 255.0f);
+            if (ql > 0.0f && node.p[a] + ql * cell[a] > sb[s][a]) ql -= 1.0f;
+            float qh = ceilf((sb[s][3 + a] - node.p[a]) * inv[a]);
+            qh = fminf(fmaxf(qh, 0.0f), 255.0f);
+            if (qh < 255.0f && node.p[a] + qh * cell[a] < sb[s][3 + a]) qh += 1.0f;
+            node.qlo[a][s] = uint8_t(ql);
+            node.qhi[a][s] = uint8_t(qh);
+        }
+    }
+    nodes[n] = node;
+}
+
+} // namespace
+
+int bvhRefitDevice(vkx_ctx* ctx) {
+    cudaStream_t st = ctx->stream;
+    const uint32_t T = uint32_t(ctx->bvh.numTriangles), N = ctx->bvh.numNodes;
+    if (T == 0) { ctx->bvhBuilt = true; return VKX_OK; }
+    cudaEvent_t e0, e1; CUDA_TRY(ctx, cudaEventCreate(&e0)); CUDA_TRY(ctx, cudaEventCreate(&e1));
+    CUDA_TRY(ctx, cudaEventRecord(e0, st));
+    const size_t need = (size_t(T) + N) * 6 * sizeof(float);
+    if (need > ctx->refitScratchBytes) { // kept between refits: a per-frame operation
+        if (ctx->dRefitScratch) cudaFree(ctx->dRefitScratch);
+        ctx->dRefitScratch = nullptr; ctx->refitScratchBytes = 0;
+        CUDA_TRY(ctx, cudaMalloc(&ctx->dRefitScratch, need)); ctx->refitScratchBytes = need;
+    }
+    float* triBox = ctx->dRefitScratch; float* nodeBox = triBox + size_t(T) * 6;
+    Node80* nodes = reinterpret_cast<Node80*>(ctx->dNodes);
+    k_refit_tris<<<divUp(T, 256), 256, 0, st>>>(ctx->dVertices, ctx->dIndices, ctx->dOffsets, ctx->dInstances, T, reinterpret_cast<FlatTri*>(ctx->dTris), triBox); LAUNCH_CHECK(ctx);
+    for (size_t l = ctx->hLevelBase.size() - 1; l-- > 0;) {
+        const uint32_t base = ctx->hLevelBase[l], count = ctx->hLevelBase[l + 1] - base;
+        k_refit_level<<<divUp(count, 64), 64, 0, st>>>(base, count, nodes, triBox, nodeBox); LAUNCH_CHECK(ctx);
+    }
+    float root[6];
+    CUDA_TRY(ctx, cudaMemcpyAsync(root, nodeBox, sizeof(root), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaEventRecord(e1, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    for (int a = 0; a < 3; ++a) { ctx->bvh.sceneMin[a] = root[a]; ctx->bvh.sceneMax[a] = root[3 + a]; }
+    ctx->bvh.buildMs = ms;
     ctx->bvhBuilt = true;
     return VKX_OK;
 }

@@ -78,6 +78,9 @@ struct vkx_ctx {
     uint4* dNodes = nullptr; float4* dTris = nullptr;
     vkx_bvh_info bvh{};
     bool bvhBuilt = false;
+    bool bvhTopology = false;           // a built tree exists for the uploaded scene (vkx_bvh_refit can re-fit it after transforms / vertices changed)
+    std::vector<uint32_t> hLevelBase;   // first node of every level of the wide tree + the node count (nodes are stored level by level)
+    float* dRefitScratch = nullptr; size_t refitScratchBytes = 0; // triangle + node boxes of the refit
 
     // probes
     bool probesReady = false;
@@ -175,6 +178,7 @@ static inline unsigned divUp(size_t a, size_t b) { return unsigned((a + b - 1) /
 
 // ---- implemented in bvh_build.cu
 int bvhBuildDevice(vkx_ctx* ctx);
+int bvhRefitDevice(vkx_ctx* ctx);
 int waitGather(vkx_ctx* ctx); // api.cu
 int launchP2pWait(vkx_ctx* ctx);   // ddgi.cu: stream-ordered wait for every rank's tiles of the last sharded update
 int launchP2pSignal(vkx_ctx* ctx); // ddgi.cu

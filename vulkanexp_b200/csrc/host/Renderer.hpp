@@ -38,6 +38,7 @@ class Renderer {
     // reference src/Renderer.cpp:671-742: new instance transforms after Scene::update(), then the structure update (here: the
     // deterministic rebuild of the world-space BVH; the reference refits its TLAS)
     void updateAccelerationStructureInstances();
+    bool RebuildOnUpdate = false; // updateTLAS: false = topology-preserving refit like the reference, true = full rebuild
     void updateTLAS();
     void onHierarchicalChanges() { updateAccelerationStructureInstances(); updateTLAS(); }
     // Skinned meshes (reference src/Renderer.cpp:133-164, 201-240, 644-669): allocateMeshes appends a bind-pose copy of the vertices of
