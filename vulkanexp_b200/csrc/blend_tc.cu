@@ -26,6 +26,10 @@
 #include "shade.cuh"
 #include "ddgi_common.cuh"
 #include "blend_tc.cuh"
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
 
 namespace {
 
@@ -71,11 +75,17 @@ __device__ __forceinline__ void mbarArrive(uint64_t* bar) { asm volatile("mbarri
 __device__ __forceinline__ void namedBarrier(uint32_t id, uint32_t threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 __device__ __forceinline__ void tmemLoadWait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major, unswizzled UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): start address, leading byte offset (between the
-// two 16-byte K cores of one MMA), stride byte offset (between 8-row groups), all in 16-byte units; version 1 (Blackwell).
+// K-major UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): start address, leading byte offset (between the two 16-byte
+// K cores of one MMA; unswizzled layout only), stride byte offset (between 8-row groups), all in 16-byte units; version 1
+// (Blackwell); layout type in bits 61..63 (0 = no swizzle, 4 = SWIZZLE_64B). One K = 8 step advances the start address by 32 bytes.
 __device__ __forceinline__ uint64_t ummaDesc(uint32_t smemByteAddr) {
-    return uint64_t((smemByteAddr >> 4) & 0x3FFFu) | (uint64_t(BTC_LBO >> 4) << 16) | (uint64_t(BTC_SBO >> 4) << 32) | (uint64_t(1) << 46);
+    return uint64_t((smemByteAddr >> 4) & 0x3FFFu) | (uint64_t(BTC_LBO >> 4) << 16) | (uint64_t(BTC_SBO >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(BTC_LAYOUT == 1 ? 4 : 0) << 61);
 }
+#if BTC_LAYOUT == 1
+#define BTC_KSTEP_BYTES 32u
+#else
+#define BTC_KSTEP_BYTES (2u * BTC_LBO)
+#endif
 // Instruction descriptor (cute::UMMA::InstrDescriptor): F32 accumulate, TF32 x TF32, both operands K-major, M = 128, N = n
 __host__ __device__ constexpr uint32_t ummaIdesc(uint32_t n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24); }
 
@@ -86,8 +96,12 @@ __device__ __forceinline__ void splitTf32(float x, float& hi, float& lo) {
     hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
     lo = __fsub_rn(x, hi);
 }
-// byte offset of element (row, k) inside one operand tile of a chunk: [row group][k core][row in group][k in core]
+// byte offset of element (row, k) inside one operand tile of a chunk (see BTC_LAYOUT in blend_tc.cuh)
+#if BTC_LAYOUT == 1
+__device__ __forceinline__ uint32_t tileOffset(uint32_t row, uint32_t k) { return (row >> 3) * BTC_SBO + (row & 7u) * 64u + (((k >> 2) ^ ((row >> 1) & 3u)) << 4) + (k & 3u) * 4u; }
+#else
 __device__ __forceinline__ uint32_t tileOffset(uint32_t row, uint32_t k) { return (row >> 3) * BTC_SBO + (k >> 2) * BTC_LBO + (row & 7u) * 16u + (k & 3u) * 4u; }
+#endif
 
 } // namespace
 
@@ -111,6 +125,9 @@ __global__ void k_blend_weight_image(uint32_t N, const float* __restrict__ W, fl
 }
 
 
+// VKX_BLEND_PROFILE=1 (diagnostics): per-CTA cycle counts of where each role waits, 16 slots per CTA (see blendTcLaunch)
+#define BTC_TIMED(slot, stmt) do { if (prof) { const long long t0_ = clock64(); stmt; pacc[slot] += (unsigned long long)(clock64() - t0_); } else { stmt; } } while (0)
+
 // Word offsets (relative to the probe's tile origin) of an interior texel and of the border texels that copy from it: the inverse of
 // blendBorderSource (probesCopyBorders.comp). (ix, iy) in [1, T-2]^2; up to three borders (interior corners feed a row, a column and
 // the opposite corner texel).
@@ -129,23 +146,32 @@ __device__ __forceinline__ void texelTargets(int T, int ix, int iy, uint32_t pit
     border[2] = cornerB;
 }
 
+// n / d for the per-texel weight sum d (the same for every probe of the frame) with r = RN(1 / d) computed once per thread:
+// q0 = RN(n r), e = n - d q0 exactly (FMA), q = RN(q0 + e r) is the correctly rounded quotient (Markstein's correction step; d is a
+// positive normal number > 1e-3 here), i.e. what the `/` of probesUpdate.glsl:85 gives, at three instructions instead of a division.
+__device__ __forceinline__ float divShared(float n, float d, float r) { const float q0 = __fmul_rn(n, r); return __fmaf_rn(__fmaf_rn(-d, q0, n), r, q0); }
+__device__ __forceinline__ uint32_t packRG16Fx2(float r, float g) { const __half2 h = __floats2half2_rn(r, g); return *reinterpret_cast<const uint32_t*>(&h); } // one F2FP instead of two F2F + shift/or
+
 struct TileMeta { uint32_t linear[BTC_P]; uint32_t originD[BTC_P]; uint32_t originI[BTC_P]; uint32_t outOfRange[BTC_P]; uint32_t maxChange[BTC_P]; };
 
 __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, DeviceProbes pr, const uint32_t* __restrict__ probeIndices, const float4* __restrict__ rays,
                                                              const float* __restrict__ W, const float* __restrict__ image, float* __restrict__ irrUnpacked,
-                                                             float* __restrict__ depUnpacked, uint32_t slotBase) {
+                                                             float* __restrict__ depUnpacked, uint32_t slotBase, unsigned long long* __restrict__ prof, uint32_t diag) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    // stage s: [A chunk image (hi t0, hi t1, lo t0, lo t1)][B depth hi][B depth lo][B colour hi][B colour lo]
-    __shared__ __align__(8) uint64_t barFull[BTC_STAGES], barEmpty[BTC_STAGES], barAccFull, barAccEmpty, barMetaFree[2];
+    // weight ring: ASTAGES x [A chunk image (hi t0, hi t1, lo t0, lo t1)]; ray-data ring: BSTAGES x [B depth hi][B depth lo][B colour hi][B colour lo]
+    unsigned char* const smemB = smem + BTC_ASTAGES * BTC_A_CHUNK_BYTES;
+    __shared__ __align__(8) uint64_t barFullA[BTC_ASTAGES], barEmptyA[BTC_ASTAGES], barFullB[BTC_BSTAGES], barEmptyB[BTC_BSTAGES], barAccFull, barAccEmpty, barMetaFree[2];
     __shared__ uint32_t sTmem;
     __shared__ TileMeta sMeta[2];
     __shared__ float sRw[232]; // per-texel weight sums (depth 0..195, irradiance 196..231)
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u, N = bp.raysPerProbe;
+    unsigned long long pacc[13] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; // diagnostics (VKX_BLEND_PROFILE): cycle counters kept in registers, flushed once at the end
     const uint32_t chunks = (N + BTC_KC - 1u) / BTC_KC;
     const uint32_t numTiles = (bp.count + BTC_P - 1u) / BTC_P;
     const float cellLen = bp.gridCellLen;
     if (tid == 0) {
-        for (uint32_t s = 0; s < BTC_STAGES; ++s) { mbarInit(&barFull[s], BTC_PROD_WARPS + 1u); mbarInit(&barEmpty[s], 1); }
+        for (uint32_t s = 0; s < BTC_ASTAGES; ++s) { mbarInit(&barFullA[s], 1); mbarInit(&barEmptyA[s], 1); }
+        for (uint32_t s = 0; s < BTC_BSTAGES; ++s) { mbarInit(&barFullB[s], BTC_PROD_WARPS); mbarInit(&barEmptyB[s], 1); }
         mbarInit(&barAccFull, 1); mbarInit(&barAccEmpty, BTC_EPI_WARPS); mbarInit(&barMetaFree[0], BTC_EPI_WARPS); mbarInit(&barMetaFree[1], BTC_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -163,28 +189,32 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
             uint32_t g = 0; // chunks issued by this CTA so far (stage = g % STAGES, use = g / STAGES)
             for (uint32_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x)
                 for (uint32_t c = 0; c < chunks; ++c, ++g) {
-                    const uint32_t s = g % BTC_STAGES, use = g / BTC_STAGES;
-                    if (use) mbarWait(&barEmpty[s], (use - 1u) & 1u);
-                    mbarExpectTx(&barFull[s], BTC_A_CHUNK_BYTES);
-                    bulkCopyG2S(smem + s * BTC_STAGE_BYTES, reinterpret_cast<const char*>(image) + size_t(c) * BTC_A_CHUNK_BYTES, BTC_A_CHUNK_BYTES, &barFull[s]);
+                    const uint32_t s = g % BTC_ASTAGES, use = g / BTC_ASTAGES;
+                    if (use) BTC_TIMED(0, mbarWait(&barEmptyA[s], (use - 1u) & 1u));
+                    if (diag & 2u) { mbarArrive(&barFullA[s]); continue; } // diagnostics: no weight copies
+                    mbarExpectTx(&barFullA[s], BTC_A_CHUNK_BYTES);
+                    bulkCopyG2S(smem + s * BTC_A_CHUNK_BYTES, reinterpret_cast<const char*>(image) + size_t(c) * BTC_A_CHUNK_BYTES, BTC_A_CHUNK_BYTES, &barFullA[s]);
                 }
         }
     } else if (warp == BTC_MMA_WARP) {
         // ------------------------------------------------------------------------------------------ MMA issue
         if (lane == 0) {
+            const long long tStart = clock64();
             uint32_t g = 0, it = 0;
             constexpr uint32_t idD = ummaIdesc(2 * BTC_P), idC = ummaIdesc(3 * BTC_P);
             for (uint32_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x, ++it) {
-                if (it) { mbarWait(&barAccEmpty, (it - 1u) & 1u); tcFenceAfter(); } // the epilogue has read the previous tile's accumulators
+                if (it) { BTC_TIMED(1, mbarWait(&barAccEmpty, (it - 1u) & 1u)); tcFenceAfter(); } // the epilogue has read the previous tile's accumulators
                 for (uint32_t c = 0; c < chunks; ++c, ++g) {
-                    const uint32_t s = g % BTC_STAGES, use = g / BTC_STAGES;
-                    mbarWait(&barFull[s], use & 1u);
+                    const uint32_t sa = g % BTC_ASTAGES, useA = g / BTC_ASTAGES, sb = g % BTC_BSTAGES, useB = g / BTC_BSTAGES;
+                    BTC_TIMED(2, mbarWait(&barFullA[sa], useA & 1u));
+                    BTC_TIMED(3, mbarWait(&barFullB[sb], useB & 1u));
                     tcFenceAfter();
-                    const uint32_t aHi0 = smemAddr(smem + s * BTC_STAGE_BYTES), aHi1 = aHi0 + BTC_A_TILE_BYTES, aLo0 = aHi0 + 2 * BTC_A_TILE_BYTES, aLo1 = aHi0 + 3 * BTC_A_TILE_BYTES;
-                    const uint32_t dHi = aHi0 + BTC_A_CHUNK_BYTES, dLo = dHi + BTC_BD_TILE_BYTES, cHi = dHi + 2 * BTC_BD_TILE_BYTES, cLo = cHi + BTC_BC_TILE_BYTES;
+                    const long long tIssue = prof ? clock64() : 0;
+                    const uint32_t aHi0 = smemAddr(smem + sa * BTC_A_CHUNK_BYTES), aHi1 = aHi0 + BTC_A_TILE_BYTES, aLo0 = aHi0 + 2 * BTC_A_TILE_BYTES, aLo1 = aHi0 + 3 * BTC_A_TILE_BYTES;
+                    const uint32_t dHi = smemAddr(smemB + sb * BTC_B_STAGE_BYTES), dLo = dHi + BTC_BD_TILE_BYTES, cHi = dHi + 2 * BTC_BD_TILE_BYTES, cLo = cHi + BTC_BC_TILE_BYTES;
 #pragma unroll
                     for (uint32_t ks = 0; ks < BTC_KC / 8u; ++ks) {
-                        const uint32_t ko = ks * 2u * BTC_LBO; // two K cores per MMA
+                        const uint32_t ko = ks * BTC_KSTEP_BYTES; // two K cores per MMA
                         const uint32_t acc = (c | ks) ? 1u : 0u;
                         // depth tile 0 -> columns [0, 2P), depth tile 1 -> [2P, 4P), tile 1 x colour -> [4P, 7P)
                         umma(tmem + 0u, ummaDesc(aHi0 + ko), ummaDesc(dHi + ko), idD, acc);
@@ -197,10 +227,15 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
                         umma(tmem + 4u * BTC_P, ummaDesc(aHi1 + ko), ummaDesc(cLo + ko), idC, 1u);
                         umma(tmem + 4u * BTC_P, ummaDesc(aLo1 + ko), ummaDesc(cHi + ko), idC, 1u);
                     }
-                    ummaCommit(&barEmpty[s]);                      // stage free when these MMAs have read it
+                    const long long tCommit = prof ? clock64() : 0;
+                    if (prof) pacc[11] += (unsigned long long)(tCommit - tIssue);
+                    ummaCommit(&barEmptyA[sa]);                    // stages free when these MMAs have read them
+                    ummaCommit(&barEmptyB[sb]);
                     if (c + 1u == chunks) ummaCommit(&barAccFull); // accumulators of the tile complete
+                    if (prof) pacc[12] += (unsigned long long)(clock64() - tCommit);
                 }
             }
+            if (prof) pacc[4] = (unsigned long long)(clock64() - tStart);
         }
     } else if (warp >= BTC_EPI_WARPS) {
         // ------------------------------------------------------------------------------------------ producers: ray records -> operand tiles
@@ -215,18 +250,7 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
             const uint32_t slot0 = tile * BTC_P;
             const uint32_t np = min(uint32_t(BTC_P), bp.count - slot0);
             TileMeta& meta = sMeta[it & 1u];
-            if (it >= 2u) mbarWait(&barMetaFree[it & 1u], ((it >> 1) - 1u) & 1u); // the epilogue two tiles back is done with this meta block
-            if (pt < BTC_P) {
-                uint32_t lin = 0, oD = 0, oI = 0;
-                if (pt < np) {
-                    lin = __ldg(probeIndices + slot0 + pt);
-                    int ix, iy, iz; probeGridIndex(lin, bp.grid, ix, iy, iz);
-                    const int tl = iy * bp.grid.resolution[0] + ix;
-                    oD = uint32_t(size_t(16 * iz) * pr.depW + size_t(16 * tl));
-                    oI = uint32_t(size_t(8 * iz) * pr.irrW + size_t(8 * tl));
-                }
-                meta.linear[pt] = lin; meta.originD[pt] = oD; meta.originI[pt] = oI;
-            }
+            if (it >= 2u) { if (pt == 0) BTC_TIMED(5, mbarWait(&barMetaFree[it & 1u], ((it >> 1) - 1u) & 1u)); else mbarWait(&barMetaFree[it & 1u], ((it >> 1) - 1u) & 1u); } // the epilogue two tiles back is done with this meta block
             const float4* myRays = rays + size_t(slot0 + myP) * N;
             auto fetch = [&](uint32_t c, float4 (&rd)[EPT]) {
 #pragma unroll
@@ -235,17 +259,21 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
                     rd[i] = (myP < np && ray < N) ? __ldcs(myRays + ray) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             };
-            float4 cur[EPT], nxt[EPT];
+            // the ray records of chunks c + 1 and c + 2 are in flight while chunk c is converted
+            float4 cur[EPT], nxt[EPT], nx2[EPT];
             fetch(0, cur);
+            if (1u < chunks) fetch(1u, nxt);
             uint32_t outOfRange = 0;
             for (uint32_t c = 0; c < chunks; ++c, ++g) {
-                const uint32_t s = g % BTC_STAGES, use = g / BTC_STAGES;
-                if (c + 1u < chunks) fetch(c + 1u, nxt);
-                if (use) mbarWait(&barEmpty[s], (use - 1u) & 1u); // the MMAs that read this stage have completed
-                unsigned char* bD = smem + s * BTC_STAGE_BYTES + BTC_A_CHUNK_BYTES; // depth planes hi, then lo
+                const uint32_t s = g % BTC_BSTAGES, use = g / BTC_BSTAGES;
+                if (c + 2u < chunks) fetch(c + 2u, nx2);
+                if (use) { if (pt == 0) BTC_TIMED(6, mbarWait(&barEmptyB[s], (use - 1u) & 1u)); else mbarWait(&barEmptyB[s], (use - 1u) & 1u); } // the MMAs that read this stage have completed
+                const long long tConv = (prof && pt == 0) ? clock64() : 0;
+                unsigned char* bD = smemB + s * BTC_B_STAGE_BYTES;                   // depth planes hi, then lo
                 unsigned char* bC = bD + 2 * BTC_BD_TILE_BYTES;                      // colour planes hi, then lo
 #pragma unroll
                 for (uint32_t i = 0; i < EPT; ++i) {
+                    if (diag & 1u) { if (cur[i].x == 123.456f) outOfRange++; continue; } // diagnostics: no conversion / stores
                     const uint32_t k = 4u * i + myKq, ray = c * BTC_KC + k;
                     float4 rd = cur[i];
                     if (myP < np && ray < N) {
@@ -255,9 +283,9 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
                         rd.w = depth;
                     }
                     float hi, lo;
-                    const uint32_t od = tileOffset(2u * myP, k), oc = tileOffset(3u * myP, k);
+                    const uint32_t od = tileOffset(2u * myP, k), od1 = tileOffset(2u * myP + 1u, k), oc = tileOffset(3u * myP, k);
                     splitTf32(rd.w, hi, lo);           *reinterpret_cast<float*>(bD + od) = hi;        *reinterpret_cast<float*>(bD + BTC_BD_TILE_BYTES + od) = lo;
-                    splitTf32(rd.w * rd.w, hi, lo);    *reinterpret_cast<float*>(bD + od + 16u) = hi;  *reinterpret_cast<float*>(bD + BTC_BD_TILE_BYTES + od + 16u) = lo;
+                    splitTf32(rd.w * rd.w, hi, lo);    *reinterpret_cast<float*>(bD + od1) = hi;       *reinterpret_cast<float*>(bD + BTC_BD_TILE_BYTES + od1) = lo;
                     // colour rows 3p, 3p+1, 3p+2 may cross an 8-row group: address each
                     splitTf32(rd.x, hi, lo);           *reinterpret_cast<float*>(bC + oc) = hi;        *reinterpret_cast<float*>(bC + BTC_BC_TILE_BYTES + oc) = lo;
                     const uint32_t oc1 = tileOffset(3u * myP + 1u, k), oc2 = tileOffset(3u * myP + 2u, k);
@@ -265,11 +293,12 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
                     splitTf32(rd.z, hi, lo);           *reinterpret_cast<float*>(bC + oc2) = hi;       *reinterpret_cast<float*>(bC + BTC_BC_TILE_BYTES + oc2) = lo;
                 }
 #pragma unroll
-                for (uint32_t i = 0; i < EPT; ++i) cur[i] = nxt[i];
+                for (uint32_t i = 0; i < EPT; ++i) { cur[i] = nxt[i]; nxt[i] = nx2[i]; }
                 if (c + 1u == chunks && outOfRange) atomicAdd(&meta.outOfRange[myP], outOfRange); // visible to the epilogue through the arrive below
                 fenceProxyAsync(); // generic-proxy stores -> visible to the tensor core
                 __syncwarp();
-                if (lane == 0) mbarArrive(&barFull[s]);
+                if (lane == 0) mbarArrive(&barFullB[s]);
+                if (prof && pt == 0) pacc[7] += (unsigned long long)(clock64() - tConv);
             }
         }
     } else {
@@ -285,33 +314,57 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
         else if (isIrr) texelTargets(8, int(te % 6u) + 1, int(te / 6u) + 1, pr.irrW, interior, border, nb);
         const float rw = isDepth ? sRw[te] : (isIrr ? sRw[196u + te] : 0.0f);
         const bool norm = rw > 1e-3f;
+        const float rwInv = norm ? __frcp_rn(rw) : 0.0f;
         const float hysteresis = bp.grid.hysteresis;
         // warp-uniform: does this warp hold any useful row? (tile 1: warps 4, 5 depth; warp 6 depth rows 64..67 + irradiance 68..95; warp 7 irradiance 96..103)
+        const bool depthWarp = !tile1 || (warp & 3u) < 3u; // depth rows: tile 0 all warps, tile 1 warps 4..6 (rows 0..95, of which 0..67 are texels)
+        const bool irrWarp = tile1 && (warp & 3u) >= 2u;   // irradiance rows 68..103 live in warps 6 and 7
+        const uint32_t* prevAtlas = isDepth ? pr.depWork : pr.irrWork;
         uint32_t it = 0;
         for (uint32_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x, ++it) {
             const uint32_t slot0 = tile * BTC_P;
             const uint32_t np = min(uint32_t(BTC_P), bp.count - slot0);
             TileMeta& meta = sMeta[it & 1u];
-            mbarWait(&barAccFull, it & 1u);
+            // While the tensor core accumulates this tile the epilogue warps are idle: they work out where the tile's probes live and pull
+            // the previous texels (the work atlases were last touched a frame ago: DRAM) into L2, then hold the first group in registers.
+            if (tid < BTC_P) {
+                uint32_t lin = 0, oD = 0, oI = 0;
+                if (tid < np) {
+                    lin = __ldg(probeIndices + slot0 + tid);
+                    int ix, iy, iz; probeGridIndex(lin, bp.grid, ix, iy, iz);
+                    const int tl = iy * bp.grid.resolution[0] + ix;
+                    oD = uint32_t(size_t(16 * iz) * pr.depW + size_t(16 * tl));
+                    oI = uint32_t(size_t(8 * iz) * pr.irrW + size_t(8 * tl));
+                }
+                meta.linear[tid] = lin; meta.originD[tid] = oD; meta.originI[tid] = oI;
+            }
+            namedBarrier(2, BTC_EPI_WARPS * 32u);
+            const uint32_t* origin = isDepth ? meta.originD : meta.originI;
+            if (isDepth || isIrr) for (uint32_t p = 8u; p < np; ++p) asm volatile("prefetch.global.L2 [%0];" ::"l"(prevAtlas + origin[p] + interior));
+            uint32_t prevWord[8], nextWord[8];
+#pragma unroll
+            for (uint32_t q = 0; q < 8; ++q) prevWord[q] = ((isDepth || isIrr) && q < np) ? prevAtlas[origin[q] + interior] : 0u;
+            if (tid == 0) BTC_TIMED(8, mbarWait(&barAccFull, it & 1u)); else mbarWait(&barAccFull, it & 1u);
+            __syncwarp(); // reconverge before the warp-aligned tcgen05.ld below
             tcFenceAfter();
-            for (uint32_t p0 = 0; p0 < np; p0 += 8u) { // eight probes per pass
+            const long long tEpi = (prof && tid == 0) ? clock64() : 0;
+            for (uint32_t p0 = 0; p0 < ((diag & 4u) ? 0u : np); p0 += 8u) { // eight probes per pass (diag bit 2: skipped)
                 const uint32_t npj = min(8u, np - p0);
-                if (!tile1 || (warp & 3u) < 3u) { // depth rows: tile 0 all warps, tile 1 warps 4..6 (rows 0..95, of which 0..67 are texels)
+#pragma unroll
+                for (uint32_t q = 0; q < 8; ++q) nextWord[q] = ((isDepth || isIrr) && p0 + 8u + q < np) ? prevAtlas[origin[p0 + 8u + q] + interior] : 0u; // the next pass's previous texels
+                if (depthWarp) {
                     uint32_t v[16];
                     tmemLoad16(tmem + laneBase + (tile1 ? 2u * BTC_P : 0u) + 2u * p0, v);
-                    uint32_t prevWord[8];
-#pragma unroll
-                    for (uint32_t q = 0; q < 8; ++q) prevWord[q] = (isDepth && q < npj) ? pr.depWork[meta.originD[p0 + q] + interior] : 0u;
                     tmemLoadWait();
                     if (isDepth) {
 #pragma unroll
                         for (uint32_t q = 0; q < 8; ++q) {
                             if (q >= npj) break;
                             float r0 = __uint_as_float(v[2 * q]), r1 = __uint_as_float(v[2 * q + 1]);
-                            if (norm) { r0 = r0 / rw; r1 = r1 / rw; }                        // probesUpdate.glsl:85-86
+                            if (norm) { r0 = divShared(r0, rw, rwInv); r1 = divShared(r1, rw, rwInv); } // probesUpdate.glsl:85-86
                             const float2 prev = unpackRG16F(prevWord[q]);
                             const float o0 = mixf(r0, prev.x, hysteresis), o1 = mixf(r1, prev.y, hysteresis); // :103
-                            const uint32_t word = packRG16F(o0, o1);
+                            const uint32_t word = packRG16Fx2(o0, o1);
                             uint32_t* tileBase = pr.depWork + meta.originD[p0 + q];
                             tileBase[interior] = word;
 #pragma unroll
@@ -320,14 +373,11 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
                         }
                     }
                 }
-                if (tile1 && (warp & 3u) >= 2u) { // irradiance rows 68..103 live in warps 6 and 7
+                if (irrWarp) {
                     uint32_t v[24];
                     uint32_t a[16], b8[8];
                     tmemLoad16(tmem + laneBase + 4u * BTC_P + 3u * p0, a);
                     tmemLoad8(tmem + laneBase + 4u * BTC_P + 3u * p0 + 16u, b8);
-                    uint32_t prevWord[8];
-#pragma unroll
-                    for (uint32_t q = 0; q < 8; ++q) prevWord[q] = (isIrr && q < npj) ? pr.irrWork[meta.originI[p0 + q] + interior] : 0u;
                     tmemLoadWait();
 #pragma unroll
                     for (uint32_t q = 0; q < 16; ++q) v[q] = a[q];
@@ -339,7 +389,7 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
                         float maxChange = 0.0f;
                         if (isIrr) {
                             float r0 = __uint_as_float(v[3 * q]), r1 = __uint_as_float(v[3 * q + 1]), r2 = __uint_as_float(v[3 * q + 2]);
-                            if (norm) { r0 = r0 / rw; r1 = r1 / rw; r2 = r2 / rw; }
+                            if (norm) { r0 = divShared(r0, rw, rwInv); r1 = divShared(r1, rw, rwInv); r2 = divShared(r2, rw, rwInv); }
                             const float3 prev = unpackR11G11B10(prevWord[q]);
                             maxChange = maxS(maxS(fabsf(r0 - prev.x), fabsf(r1 - prev.y)), fabsf(r2 - prev.z));
                             const float o0 = mixf(r0, prev.x, hysteresis), o1 = mixf(r1, prev.y, hysteresis), o2 = mixf(r2, prev.z, hysteresis);
@@ -355,12 +405,17 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
                         if (lane == 0 && wmax) atomicMax(&meta.maxChange[p0 + q], wmax);
                     }
                 }
+#pragma unroll
+                for (uint32_t q = 0; q < 8; ++q) prevWord[q] = nextWord[q];
             }
             // tensor memory is free for the next tile
             tcFenceBefore();
             __syncwarp();
             if (lane == 0) mbarArrive(&barAccEmpty);
-            namedBarrier(1, BTC_EPI_WARPS * 32u); // every texel of the tile is mixed: maxChange is complete
+            if (prof && tid == 0) pacc[9] += (unsigned long long)(clock64() - tEpi);
+            const long long tBar = (prof && tid == 0) ? clock64() : 0;
+            namedBarrier(1, BTC_EPI_WARPS * 32u); // (aligned barrier: every lane of the warp must execute the same instruction - no divergent timing wrapper here)
+            if (prof && tid == 0) pacc[10] += (unsigned long long)(clock64() - tBar); // every texel of the tile is mixed: maxChange is complete
             if (tid < np) { // state machine, probesUpdate.glsl:110-119 (decree A.5.3: full max over the 36 texels)
                 const uint32_t linearIndex = meta.linear[tid];
                 uint32_t stt = pr.stateWork[linearIndex];
@@ -378,6 +433,12 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
             if (lane == 0) mbarArrive(&barMetaFree[it & 1u]); // release semantics: the zeroes above are visible to the producers that wait
         }
     }
+    if (prof) { // slot owners: TMA lane (0), MMA lane (1-4, 11, 12), first producer thread (5-7), first epilogue thread (8-10)
+        const bool owner[13] = {warp == BTC_TMA_WARP && lane == 0, warp == BTC_MMA_WARP && lane == 0, warp == BTC_MMA_WARP && lane == 0, warp == BTC_MMA_WARP && lane == 0, warp == BTC_MMA_WARP && lane == 0,
+                                tid == BTC_EPI_WARPS * 32u, tid == BTC_EPI_WARPS * 32u, tid == BTC_EPI_WARPS * 32u, tid == 0, tid == 0, tid == 0, warp == BTC_MMA_WARP && lane == 0, warp == BTC_MMA_WARP && lane == 0};
+#pragma unroll
+        for (int k = 0; k < 13; ++k) if (owner[k]) prof[blockIdx.x * 16 + k] = pacc[k];
+    }
     tcFenceBefore();
     __syncthreads();
     if (warp == BTC_MMA_WARP) tmemFree(tmem, 512);
@@ -391,7 +452,18 @@ int blendTcWeights(vkx_ctx* ctx, cudaStream_t st) {
 int blendTcLaunch(vkx_ctx* ctx, const BlendParams& bp, const DeviceProbes& pr, const uint32_t* idx, uint32_t n, uint32_t slotBase, cudaStream_t st) {
     if (n == 0) return VKX_OK;
     if (!ctx->blendTcAttrSet) { CUDA_TRY(ctx, cudaFuncSetAttribute(k_blend_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, BTC_SMEM_BYTES)); ctx->blendTcAttrSet = true; }
-    k_blend_tc<<<std::min<unsigned>(divUp(n, BTC_P), unsigned(ctx->smCount)), BTC_THREADS, BTC_SMEM_BYTES, st>>>(bp, pr, idx, ctx->dRays, ctx->dBlendW, ctx->dBlendImage, ctx->debugBuffers ? ctx->dIrrUnpacked : nullptr,
-                                                                      ctx->debugBuffers ? ctx->dDepUnpacked : nullptr, slotBase); LAUNCH_CHECK(ctx);
+    const unsigned grid = std::min<unsigned>(divUp(n, BTC_P), unsigned(ctx->smCount));
+    static const bool profile = getenv("VKX_BLEND_PROFILE") != nullptr;
+    unsigned long long* prof = nullptr;
+    static const uint32_t diag = [] { const char* e = getenv("VKX_BLEND_DIAG"); return e ? uint32_t(atoi(e)) : 0u; }(); // diagnostics only: results are wrong with any bit set
+    if (profile) { CUDA_TRY(ctx, cudaMallocManaged(&prof, size_t(grid) * 16 * sizeof(unsigned long long))); memset(prof, 0, size_t(grid) * 16 * sizeof(unsigned long long)); }
+    k_blend_tc<<<grid, BTC_THREADS, BTC_SMEM_BYTES, st>>>(bp, pr, idx, ctx->dRays, ctx->dBlendW, ctx->dBlendImage, ctx->debugBuffers ? ctx->dIrrUnpacked : nullptr,
+                                                                      ctx->debugBuffers ? ctx->dDepUnpacked : nullptr, slotBase, prof, diag); LAUNCH_CHECK(ctx);
+    if (prof) { // diagnostics: mean / max cycles per CTA of every instrumented wait (slots: see BTC_TIMED uses)
+        cudaStreamSynchronize(st);
+        static const char* names[16] = {"tma: wait emptyA", "mma: wait accEmpty", "mma: wait fullA", "mma: wait fullB", "mma: total", "prod: wait metaFree", "prod: wait emptyB", "prod: convert+arrive", "epi: wait accFull", "epi: drain+mix", "epi: named barrier", "mma: issue 18 MMAs", "mma: commits", "", "", ""};
+        for (int k = 0; k < 13; ++k) { double sum = 0, mx = 0; for (unsigned b = 0; b < grid; ++b) { const double v = double(prof[b * 16 + k]); sum += v; mx = v > mx ? v : mx; } fprintf(stderr, "[blend_tc profile] %-22s mean %10.0f max %10.0f cycles per CTA (%u CTAs, %u probes)\n", names[k], sum / grid, mx, grid, n); }
+        cudaFree(prof);
+    }
     return VKX_OK;
 }

@@ -26,21 +26,36 @@ __device__ __forceinline__ void blendBorderSource(int T, int x, int y, int& sx, 
 // ---- tensor-core blend geometry (blend_tc.cu)
 #define BTC_P 64u            // probes per tile: N = 128 (depth planes) / 192 (colour planes)
 #define BTC_KC 16u           // rays per chunk (two K = 8 TF32 MMAs)
-#define BTC_STAGES 2u        // shared-memory stages (chunks in flight between the producer warps and the MMA warp)
+#define BTC_ASTAGES 4u       // weight chunks in flight (TMA warp -> MMA warp): the bulk copies need ~4 chunk periods of L2 latency
+#define BTC_BSTAGES 2u       // ray-data chunks in flight (producer warps -> MMA warp)
 #define BTC_EPI_WARPS 8u     // warps 0..3: accumulator rows of weight tile 0, warps 4..7: weight tile 1 (a warp reads the TMEM lane quarter warp % 4)
 #define BTC_PROD_WARPS 8u    // warps 8..15: ray records -> TF32 hi / lo operand tiles
 #define BTC_MMA_WARP 16u     // one lane issues tcgen05.mma
 #define BTC_TMA_WARP 17u     // one lane issues the bulk copies of the weight image
 #define BTC_THREADS (32u * (BTC_EPI_WARPS + BTC_PROD_WARPS + 2u))
 #define BTC_MAX_CHUNKS (VKX_MAX_RAYS_PER_PROBE / 16)
+// Operand tiles are K-major with 16 rays (64 bytes) per row. BTC_LAYOUT 1 (default): the canonical SWIZZLE_64B layout - 8-row groups of
+// 512 bytes, the four 16-byte K cores of a row XOR-ed with (row / 2) % 4. BTC_LAYOUT 0: unswizzled "interleaved" core matrices
+// (8 rows x 16 bytes contiguous, K cores BTC_LBO apart, row groups BTC_SBO apart) - kept for the measurement in DESIGN.md: its
+// tcgen05.mma ran at a quarter of the tensor-core floor (operand fetch), the swizzled layout runs at the floor.
+#ifndef BTC_LAYOUT
+#define BTC_LAYOUT 1
+#endif
+#if BTC_LAYOUT == 1
+#define BTC_SBO 512u
+#define BTC_LBO 16u          // ignored by the hardware for swizzled K-major operands
+#else
 #define BTC_LBO 128u         // bytes between the 16-byte K cores of an operand tile (core matrix = 8 rows x 16 bytes)
+#ifndef BTC_SBO
 #define BTC_SBO 528u         // bytes between 8-row groups: 4 K cores + 16 bytes, so that 8 probes x 4 rays of a warp hit 32 different banks
+#endif
+#endif
 #define BTC_A_TILE_BYTES (16u * BTC_SBO)                 // 128 weight rows
 #define BTC_A_CHUNK_BYTES (4u * BTC_A_TILE_BYTES)        // hi tile 0, hi tile 1, lo tile 0, lo tile 1
 #define BTC_BD_TILE_BYTES (16u * BTC_SBO)                // 128 rows: (probe, d | d^2)
 #define BTC_BC_TILE_BYTES (24u * BTC_SBO)                // 192 rows: (probe, r | g | b)
-#define BTC_STAGE_BYTES (BTC_A_CHUNK_BYTES + 2u * BTC_BD_TILE_BYTES + 2u * BTC_BC_TILE_BYTES)
-#define BTC_SMEM_BYTES (BTC_STAGES * BTC_STAGE_BYTES)
+#define BTC_B_STAGE_BYTES (2u * BTC_BD_TILE_BYTES + 2u * BTC_BC_TILE_BYTES)
+#define BTC_SMEM_BYTES (BTC_ASTAGES * BTC_A_CHUNK_BYTES + BTC_BSTAGES * BTC_B_STAGE_BYTES)
 #define BTC_IMAGE_BYTES (size_t(BTC_MAX_CHUNKS) * BTC_A_CHUNK_BYTES)
 
 int blendTcWeights(vkx_ctx* ctx, cudaStream_t st);  // per frame, after k_blend_weights: the A-operand image

@@ -256,7 +256,15 @@ __global__ void __launch_bounds__(BLEND_COLS) k_blend_weights(float depthSharpne
 // Sum of a texel's weights over the rays, in ray order (the `result.w` every blend thread of that texel would accumulate): row BLEND_WSUM_ROW.
 __global__ void __launch_bounds__(BLEND_COLS) k_blend_weight_sums(uint32_t N, float* __restrict__ W) {
     float rw = 0.0f;
-    for (uint32_t i = 0; i < N; ++i) rw = rw + W[size_t(i) * BLEND_COLS + threadIdx.x];
+    uint32_t i = 0;
+    for (; i + 16u <= N; i += 16u) { // sixteen loads in flight, then the additions in ray order (one block: the loop is latency-bound)
+        float w[16];
+#pragma unroll
+        for (uint32_t k = 0; k < 16u; ++k) w[k] = W[size_t(i + k) * BLEND_COLS + threadIdx.x];
+#pragma unroll
+        for (uint32_t k = 0; k < 16u; ++k) rw = rw + w[k];
+    }
+    for (; i < N; ++i) rw = rw + W[size_t(i) * BLEND_COLS + threadIdx.x];
     W[size_t(BLEND_WSUM_ROW) * BLEND_COLS + threadIdx.x] = rw;
 }
 

@@ -28,8 +28,11 @@ __global__ void __launch_bounds__(128) k_shade_miss(ShadeParams sp, const float4
 
 // closesthit.glsl:143-288 (NO_REFLECTION) over the dense front-hit queue; appends the shadow rays. TEXTURED: the scene has a texture
 // list (the host picks the variant, so untextured scenes run the kernel without any texture code).
+#ifndef SHADE_MIN_BLOCKS
+#define SHADE_MIN_BLOCKS 6 // resident 128-thread CTAs per SM k_shade_front is compiled for (80 registers)
+#endif
 template <bool TEXTURED>
-__global__ void __launch_bounds__(128, 6) k_shade_front(DeviceScene sc, DeviceProbes pr, ShadeParams sp, const float4* __restrict__ origins,
+__global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade_front(DeviceScene sc, DeviceProbes pr, ShadeParams sp, const float4* __restrict__ origins,
                                                      const float4* __restrict__ dirs, const vkx_hit* __restrict__ hits, const uint32_t* __restrict__ frontQueue,
                                                      uint32_t* __restrict__ counters, float4* __restrict__ rays, float4* __restrict__ queue) {
     const uint32_t n = counters[4];

@@ -139,6 +139,7 @@ struct GridConsts {
     bool pow2x, pow2y;
     float cscale, dscale;
     int rx, ry, rz;
+    float irrWf, irrHf, depWf, depHf; // atlas sizes as floats (8 / 16 texels per probe tile)
 };
 __device__ __forceinline__ bool isPow2f(float x) { return (__float_as_uint(x) & 0x007FFFFFu) == 0u && x > 0.0f; }
 __device__ __forceinline__ GridConsts makeGridConsts(const vkx_grid_info& grid) {
@@ -150,6 +151,7 @@ __device__ __forceinline__ GridConsts makeGridConsts(const vkx_grid_info& grid) 
     c.invUsx = 1.0f / c.usx; c.invUsy = 1.0f / c.usy;
     c.cscale = float(grid.colorRes - 2) / float(grid.colorRes); c.dscale = float(grid.depthRes - 2) / float(grid.depthRes);
     c.rx = grid.resolution[0]; c.ry = grid.resolution[1]; c.rz = grid.resolution[2];
+    c.irrWf = float(8 * c.rx * c.ry); c.irrHf = float(8 * c.rz); c.depWf = float(16 * c.rx * c.ry); c.depHf = float(16 * c.rz);
     return c;
 }
 // x / scale, exactly: a division by a power of two equals the multiplication by its (exact) reciprocal.
@@ -186,16 +188,31 @@ __device__ __forceinline__ BilinearTaps makeTaps(float u, float v, uint32_t w, u
     t.o00 = y0 * int(w) + x0; t.o10 = y0 * int(w) + x1; t.o01 = y1 * int(w) + x0; t.o11 = y1 * int(w) + x1;
     return t;
 }
+// Atlas look-ups of sampleProbes never wrap: the octahedral coordinate lies in [0, 1], so the unnormalised texel coordinate
+// tile * res + 1 + (res - 2) * oct - 0.5 stays inside [tile * res + 0.5, tile * res + res - 1.5] (rounding cannot carry it to the
+// next integer), i.e. x0 >= 0 and x0 + 1 <= size - 1: the REPEAT arithmetic of bilinearSetup is the identity there. The four texels
+// are base, base + 1, base + w, base + w + 1; fx / fy are bilinearSetup's (same two roundings).
+struct AtlasTaps { int base; float fx, fy; };
+__device__ __forceinline__ AtlasTaps makeAtlasTaps(float u, float v, float wf, float hf, int w) {
+    AtlasTaps t;
+    const float x = __fsub_rn(__fmul_rn(u, wf), 0.5f), y = __fsub_rn(__fmul_rn(v, hf), 0.5f);
+    const float flx = floorf(x), fly = floorf(y);
+    t.fx = __fsub_rn(x, flx); t.fy = __fsub_rn(y, fly);
+    t.base = int(fly) * w + int(flx);
+    return t;
+}
 __device__ __forceinline__ float lerp2X(float t00, float t10, float t01, float t11, float gx, float fx, float gy, float fy) { // sampleDepth's arithmetic, op for op
     const float top = __fadd_rn(__fmul_rn(t00, gx), __fmul_rn(t10, fx)), bot = __fadd_rn(__fmul_rn(t01, gx), __fmul_rn(t11, fx));
     return __fadd_rn(__fmul_rn(top, gy), __fmul_rn(bot, fy));
 }
-__device__ __forceinline__ float2 lerpDepth(const BilinearTaps& t, uint32_t a, uint32_t b, uint32_t c, uint32_t d) { // exact: the moments feed the variance
+template <class Taps>
+__device__ __forceinline__ float2 lerpDepth(const Taps& t, uint32_t a, uint32_t b, uint32_t c, uint32_t d) { // exact: the moments feed the variance
     const float2 t00 = unpackRG16F(a), t10 = unpackRG16F(b), t01 = unpackRG16F(c), t11 = unpackRG16F(d);
     const float gx = __fsub_rn(1.0f, t.fx), gy = __fsub_rn(1.0f, t.fy);
     return make_float2(lerp2X(t00.x, t10.x, t01.x, t11.x, gx, t.fx, gy, t.fy), lerp2X(t00.y, t10.y, t01.y, t11.y, gx, t.fx, gy, t.fy));
 }
-__device__ __forceinline__ v3 lerpIrradiance(const BilinearTaps& t, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+template <class Taps>
+__device__ __forceinline__ v3 lerpIrradiance(const Taps& t, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     const float3 t00 = unpackR11G11B10(a), t10 = unpackR11G11B10(b), t01 = unpackR11G11B10(c), t11 = unpackR11G11B10(d);
     const float gx = 1.0f - t.fx, gy = 1.0f - t.fy;
     return mk3((t00.x * gx + t10.x * t.fx) * gy + (t01.x * gx + t11.x * t.fx) * t.fy, (t00.y * gx + t10.y * t.fx) * gy + (t01.y * gx + t11.y * t.fx) * t.fy,
@@ -226,21 +243,26 @@ __device__ __forceinline__ void accumulateProbe(ProbeAccum& acc, v3 normal, v3 d
 
 // One probe, both sampleProbes calls: all 16 atlas texels (2 x (4 depth + 4 irradiance)) are requested before any is used, so
 // the loads overlap instead of forming four dependent round trips to L2.
-__device__ __forceinline__ void sampleProbePair(const DeviceProbes& p, const GridConsts& gc, ProbeAccum& accA, ProbeAccum& accB, v3 normalA, v3 normalB, float2 octA, float2 octB,
+__device__ __forceinline__ void sampleProbePair(const DeviceProbes& p, const GridConsts& gc, ProbeAccum& accA, ProbeAccum& accB, v3 normalA, v3 normalB, float2 locA, float2 locB,
                                                 v3 biasedA, v3 biasedB, v3 probePosition, v3 directionToProbe, float tri, int tile, int cz) {
+    // locA / locB: (colorRes - 2) / colorRes * spherePointToOctohedralUV(normal) of the two calls (the same for all eight probes)
     const v3 bA = xsub3(probePosition, biasedA), bB = xsub3(probePosition, biasedB);
     const float lenA = __fsqrt_rn(xdot3(bA, bA)), lenB = __fsqrt_rn(xdot3(bB, bB)); // biasedDistToProbe
     const float2 octDA = sphereToOctUVxy(-xmul3(bA, __fdiv_rn(1.0f, lenA))), octDB = sphereToOctUVxy(-xmul3(bB, __fdiv_rn(1.0f, lenB))); // -normalize(biasedDirectionToProbe)
-    const float cu0 = float(8 * tile + 1) * 0.125f, cv0 = float(8 * cz + 1) * 0.125f, du0 = float(16 * tile + 1) * 0.0625f, dv0 = float(16 * cz + 1) * 0.0625f; // exact
-    const BilinearTaps tcA = makeTaps(atlasU(cu0, gc.cscale, octA.x, gc.usx, gc.invUsx, gc.pow2x), atlasU(cv0, gc.cscale, octA.y, gc.usy, gc.invUsy, gc.pow2y), p.irrW, p.irrH);
-    const BilinearTaps tcB = makeTaps(atlasU(cu0, gc.cscale, octB.x, gc.usx, gc.invUsx, gc.pow2x), atlasU(cv0, gc.cscale, octB.y, gc.usy, gc.invUsy, gc.pow2y), p.irrW, p.irrH);
-    const BilinearTaps tdA = makeTaps(atlasU(du0, gc.dscale, octDA.x, gc.usx, gc.invUsx, gc.pow2x), atlasU(dv0, gc.dscale, octDA.y, gc.usy, gc.invUsy, gc.pow2y), p.depW, p.depH);
-    const BilinearTaps tdB = makeTaps(atlasU(du0, gc.dscale, octDB.x, gc.usx, gc.invUsx, gc.pow2x), atlasU(dv0, gc.dscale, octDB.y, gc.usy, gc.invUsy, gc.pow2y), p.depW, p.depH);
-    const uint32_t* D = p.depSampled; const uint32_t* C = p.irrSampled;
-    const uint32_t dA0 = __ldg(D + tdA.o00), dA1 = __ldg(D + tdA.o10), dA2 = __ldg(D + tdA.o01), dA3 = __ldg(D + tdA.o11);
-    const uint32_t dB0 = __ldg(D + tdB.o00), dB1 = __ldg(D + tdB.o10), dB2 = __ldg(D + tdB.o01), dB3 = __ldg(D + tdB.o11);
-    const uint32_t cA0 = __ldg(C + tcA.o00), cA1 = __ldg(C + tcA.o10), cA2 = __ldg(C + tcA.o01), cA3 = __ldg(C + tcA.o11);
-    const uint32_t cB0 = __ldg(C + tcB.o00), cB1 = __ldg(C + tcB.o10), cB2 = __ldg(C + tcB.o01), cB3 = __ldg(C + tcB.o11);
+    // (tileOrigin + 1) / res = tile + 1 / res: exact in fp32 (tile counts are far below 2^20)
+    const float tileF = float(tile), czF = float(cz);
+    const float cu0 = __fadd_rn(tileF, 0.125f), cv0 = __fadd_rn(czF, 0.125f), du0 = __fadd_rn(tileF, 0.0625f), dv0 = __fadd_rn(czF, 0.0625f);
+    const int irrW = int(p.irrW), depW = int(p.depW);
+    const AtlasTaps tcA = makeAtlasTaps(divScale(__fadd_rn(cu0, locA.x), gc.usx, gc.invUsx, gc.pow2x), divScale(__fadd_rn(cv0, locA.y), gc.usy, gc.invUsy, gc.pow2y), gc.irrWf, gc.irrHf, irrW);
+    const AtlasTaps tcB = makeAtlasTaps(divScale(__fadd_rn(cu0, locB.x), gc.usx, gc.invUsx, gc.pow2x), divScale(__fadd_rn(cv0, locB.y), gc.usy, gc.invUsy, gc.pow2y), gc.irrWf, gc.irrHf, irrW);
+    const AtlasTaps tdA = makeAtlasTaps(atlasU(du0, gc.dscale, octDA.x, gc.usx, gc.invUsx, gc.pow2x), atlasU(dv0, gc.dscale, octDA.y, gc.usy, gc.invUsy, gc.pow2y), gc.depWf, gc.depHf, depW);
+    const AtlasTaps tdB = makeAtlasTaps(atlasU(du0, gc.dscale, octDB.x, gc.usx, gc.invUsx, gc.pow2x), atlasU(dv0, gc.dscale, octDB.y, gc.usy, gc.invUsy, gc.pow2y), gc.depWf, gc.depHf, depW);
+    const uint32_t* DA = p.depSampled + tdA.base; const uint32_t* DB = p.depSampled + tdB.base;
+    const uint32_t* CA = p.irrSampled + tcA.base; const uint32_t* CB = p.irrSampled + tcB.base;
+    const uint32_t dA0 = __ldg(DA), dA1 = __ldg(DA + 1), dA2 = __ldg(DA + depW), dA3 = __ldg(DA + depW + 1);
+    const uint32_t dB0 = __ldg(DB), dB1 = __ldg(DB + 1), dB2 = __ldg(DB + depW), dB3 = __ldg(DB + depW + 1);
+    const uint32_t cA0 = __ldg(CA), cA1 = __ldg(CA + 1), cA2 = __ldg(CA + irrW), cA3 = __ldg(CA + irrW + 1);
+    const uint32_t cB0 = __ldg(CB), cB1 = __ldg(CB + 1), cB2 = __ldg(CB + irrW), cB3 = __ldg(CB + irrW + 1);
     accumulateProbe(accA, normalA, directionToProbe, tri, lenA, lerpDepth(tdA, dA0, dA1, dA2, dA3), lerpIrradiance(tcA, cA0, cA1, cA2, cA3));
     accumulateProbe(accB, normalB, directionToProbe, tri, lenB, lerpDepth(tdB, dB0, dB1, dB2, dB3), lerpIrradiance(tcB, cB0, cB1, cB2, cB3));
 }
@@ -265,6 +287,7 @@ __device__ inline void sampleProbes2(const DeviceProbes& p, const GridConsts& gc
     v3 alpha = (position - (mk3(float(fx), float(fy), float(fz)) * gc.cell + gc.extentMin)) / gc.acell;
     alpha = mk3(clampS(alpha.x, 0.0f, 1.0f), clampS(alpha.y, 0.0f, 1.0f), clampS(alpha.z, 0.0f, 1.0f));
     const float2 octA = sphereToOctUVxy(normalA), octB = sphereToOctUVxy(normalB);
+    const float2 locA = make_float2(__fmul_rn(gc.cscale, octA.x), __fmul_rn(gc.cscale, octA.y)), locB = make_float2(__fmul_rn(gc.cscale, octB.x), __fmul_rn(gc.cscale, octB.y));
     ProbeAccum accA, accB;
     accA.finalColor = accA.fallbackColor = mk3(0.0f); accA.totalWeight = accA.totalFallbackWeight = 0.0f;
     accB = accA;
@@ -280,7 +303,7 @@ __device__ inline void sampleProbes2(const DeviceProbes& p, const GridConsts& gc
         const v3 trilinear = mix3(1.0f - alpha, alpha, mk3(float(ox), float(oy), float(oz)));
         const float tri = trilinear.x * trilinear.y * trilinear.z + 0.001f;
         const int tile = cy * gc.rx + cx;
-        sampleProbePair(p, gc, accA, accB, normalA, normalB, octA, octB, biasedA, biasedB, probePosition, directionToProbe, tri, tile, cz);
+        sampleProbePair(p, gc, accA, accB, normalA, normalB, locA, locB, biasedA, biasedB, probePosition, directionToProbe, tri, tile, cz);
     }
     resultA = finishProbes(accA);
     resultB = finishProbes(accB);
