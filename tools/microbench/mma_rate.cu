@@ -23,10 +23,12 @@ __device__ __forceinline__ uint64_t desc(uint32_t addr, uint32_t lbo, uint32_t s
 __host__ __device__ constexpr uint32_t idescOf(int kind, uint32_t n) { return (1u << 4) | ((kind == 0 ? 2u : 1u) << 7) | ((kind == 0 ? 2u : 1u) << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24); }
 
 template <int KIND>
-__global__ void __launch_bounds__(128, 1) k_rate(uint32_t n, uint32_t lbo, uint32_t sbo, uint32_t layout, uint32_t kstep, uint32_t iters, uint32_t accs, uint32_t batch, unsigned long long* out) {
+__global__ void __launch_bounds__(288, 1) k_rate(uint32_t n, uint32_t lbo, uint32_t sbo, uint32_t layout, uint32_t kstep, uint32_t iters, uint32_t accs, uint32_t batch, uint32_t background, unsigned long long* out) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t sTmem;
+    __shared__ volatile uint32_t sStop;
+    if (threadIdx.x == 0) sStop = 0u;
     for (uint32_t i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
     if (threadIdx.x == 0) { mbarInit(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     if (threadIdx.x < 32) { asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smemAddr(&sTmem)), "r"(512) : "memory"); asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
@@ -48,24 +50,37 @@ __global__ void __launch_bounds__(128, 1) k_rate(uint32_t n, uint32_t lbo, uint3
         }
         const long long t1 = clock64();
         out[blockIdx.x] = (unsigned long long)(t1 - t0);
+        sStop = 1u;
+    } else if (background && threadIdx.x >= 32) { // background shared-memory stores while the MMAs run (the producer warps of the blend)
+        uint32_t* dst = reinterpret_cast<uint32_t*>(smem + 140 * 1024) + (threadIdx.x - 32);
+        uint32_t v = threadIdx.x;
+        while (!sStop) {
+#pragma unroll
+            for (int k = 0; k < 40; ++k) dst[(k & 7) * 512] = v + k;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
     }
     tcFenceBefore(); __syncthreads();
     if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
 template <int KIND>
-static void run(const char* what, uint32_t n, uint32_t lbo, uint32_t sbo, uint32_t layout, uint32_t kstep, uint32_t accs, uint32_t batch, int blocks) {
+static void run(const char* what, uint32_t n, uint32_t lbo, uint32_t sbo, uint32_t layout, uint32_t kstep, uint32_t accs, uint32_t batch, int blocks, uint32_t background = 0) {
     unsigned long long* out; cudaMallocManaged(&out, 8 * blocks);
     const uint32_t iters = 4608;
     cudaFuncSetAttribute(k_rate<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    for (int rep = 0; rep < 2; ++rep) { k_rate<KIND><<<blocks, 128, 160 * 1024>>>(n, lbo, sbo, layout, kstep, iters, accs, batch, out); cudaError_t e = cudaDeviceSynchronize(); if (e != cudaSuccess) { printf("%s: %s\n", what, cudaGetErrorString(e)); return; } }
+    for (int rep = 0; rep < 2; ++rep) { k_rate<KIND><<<blocks, background ? 288 : 128, 160 * 1024>>>(n, lbo, sbo, layout, kstep, iters, accs, batch, background, out); cudaError_t e = cudaDeviceSynchronize(); if (e != cudaSuccess) { printf("%s: %s\n", what, cudaGetErrorString(e)); return; } }
     double mean = 0; for (int b = 0; b < blocks; ++b) mean += double(out[b]); mean /= blocks;
-    printf("%-64s N=%3u accs=%u batch=%3u blocks=%3d : %7.1f cycles per MMA\n", what, n, accs, batch, blocks, mean / iters);
+    printf("%-64s N=%3u accs=%u batch=%3u blocks=%3d bg=%u : %7.1f cycles per MMA\n", what, n, accs, batch, blocks, background, mean / iters);
     cudaFree(out);
 }
 int main() {
-    for (int blocks : {1, 148}) {
-        for (uint32_t batch : {18u, 144u}) {
+    for (uint32_t bg : {0u, 1u}) { // the blend's mix with and without 8 warps of background shared-memory stores
+        run<0>("tf32 M128 K8, SWIZZLE_64B SBO 512 (blend mix)", 128, 16, 512, 4, 32, 3, 18, 148, bg);
+        run<0>("tf32 M128 K8, SWIZZLE_64B SBO 512 (blend mix)", 192, 16, 512, 4, 32, 2, 18, 148, bg);
+    }
+    for (int blocks : {148}) {
+        for (uint32_t batch : {18u}) {
             run<0>("tf32 M128 K8, interleaved LBO 128 SBO 528", 128, 128, 528, 0, 256, 3, batch, blocks);
             run<0>("tf32 M128 K8, interleaved LBO 128 SBO 512", 128, 128, 512, 0, 256, 3, batch, blocks);
             run<0>("tf32 M128 K8, SWIZZLE_64B SBO 512", 128, 16, 512, 4, 32, 3, batch, blocks);

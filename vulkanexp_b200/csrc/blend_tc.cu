@@ -160,12 +160,13 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
     extern __shared__ __align__(1024) unsigned char smem[];
     // weight ring: ASTAGES x [A chunk image (hi t0, hi t1, lo t0, lo t1)]; ray-data ring: BSTAGES x [B depth hi][B depth lo][B colour hi][B colour lo]
     unsigned char* const smemB = smem + BTC_ASTAGES * BTC_A_CHUNK_BYTES;
+    uint32_t* const smemPrev = reinterpret_cast<uint32_t*>(smemB + BTC_BSTAGES * BTC_B_STAGE_BYTES); // [local probe][A | B][epilogue thread]
     __shared__ __align__(8) uint64_t barFullA[BTC_ASTAGES], barEmptyA[BTC_ASTAGES], barFullB[BTC_BSTAGES], barEmptyB[BTC_BSTAGES], barAccFull, barAccEmpty, barMetaFree[2];
     __shared__ uint32_t sTmem;
     __shared__ TileMeta sMeta[2];
     __shared__ float sRw[232]; // per-texel weight sums (depth 0..195, irradiance 196..231)
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u, N = bp.raysPerProbe;
-    unsigned long long pacc[13] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; // diagnostics (VKX_BLEND_PROFILE): cycle counters kept in registers, flushed once at the end
+    unsigned long long pacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; // diagnostics (VKX_BLEND_PROFILE): cycle counters kept in registers, flushed once at the end
     const uint32_t chunks = (N + BTC_KC - 1u) / BTC_KC;
     const uint32_t numTiles = (bp.count + BTC_P - 1u) / BTC_P;
     const float cellLen = bp.gridCellLen;
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
                     if (prof) pacc[11] += (unsigned long long)(tCommit - tIssue);
                     ummaCommit(&barEmptyA[sa]);                    // stages free when these MMAs have read them
                     ummaCommit(&barEmptyB[sb]);
-                    if (c + 1u == chunks) ummaCommit(&barAccFull); // accumulators of the tile complete
+                    if (c + 1u == chunks) { ummaCommit(&barAccFull); if (prof && it == 0) pacc[15] = (unsigned long long)(clock64() - tStart); } // accumulators of the tile complete
                     if (prof) pacc[12] += (unsigned long long)(clock64() - tCommit);
                 }
             }
@@ -302,31 +303,37 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
             }
         }
     } else {
-        // ------------------------------------------------------------------------------------------ epilogue: one accumulator row (texel) per thread
-        const bool tile1 = warp >= 4u;
-        const uint32_t row = (warp & 3u) * 32u + lane;            // accumulator row = TMEM lane
-        const uint32_t laneBase = ((warp & 3u) * 32u) << 16;
-        // what this row holds: a depth texel (both moments in adjacent columns), an irradiance texel (three columns), or nothing
-        const bool isDepth = !tile1 || row < 68u, isIrr = tile1 && row >= 68u && row < 104u;
-        const uint32_t te = !tile1 ? row : (row < 68u ? 128u + row : row - 68u); // depth texel 0..195 / irradiance texel 0..35
-        uint32_t interior = 0, border[3] = {0, 0, 0}; int nb = 0;
-        if (isDepth) texelTargets(16, int(te % 14u) + 1, int(te / 14u) + 1, pr.depW, interior, border, nb);
-        else if (isIrr) texelTargets(8, int(te % 6u) + 1, int(te / 6u) + 1, pr.irrW, interior, border, nb);
-        const float rw = isDepth ? sRw[te] : (isIrr ? sRw[196u + te] : 0.0f);
-        const bool norm = rw > 1e-3f;
-        const float rwInv = norm ? __frcp_rn(rw) : 0.0f;
+        // ------------------------------------------------------------------------------------------ epilogue
+        // A warp reads the TMEM lane quarter warp % 4, so rows 32 q .. 32 q + 31 of BOTH weight tiles belong to the two warps q and
+        // q + 4; they split the tile's probes (warp q: probes 0..31, warp q + 4: probes 32..63), which balances the irradiance rows
+        // (three channels, 11-bit packing, the max-change reduction) that all live in quarters 2 and 3 of tile 1. A thread owns up
+        // to two texels: row r of tile 0 = depth texel r, and row r of tile 1 = depth texel 128 + r (r < 68) or irradiance texel
+        // r - 68 (68 <= r < 104).
+        const uint32_t quarter = warp & 3u, half = warp >> 2;
+        const uint32_t row = quarter * 32u + lane;                // accumulator row = TMEM lane
+        const uint32_t laneBase = (quarter * 32u) << 16;
+        const bool bDepth = row < 68u, bIrr = row >= 68u && row < 104u;
+        const uint32_t teA = row, teB = bDepth ? 128u + row : row - 68u;
+        uint32_t interiorA = 0, borderA[3] = {0, 0, 0}, interiorB = 0, borderB[3] = {0, 0, 0}; int nbA = 0, nbB = 0;
+        texelTargets(16, int(teA % 14u) + 1, int(teA / 14u) + 1, pr.depW, interiorA, borderA, nbA);
+        if (bDepth) texelTargets(16, int(teB % 14u) + 1, int(teB / 14u) + 1, pr.depW, interiorB, borderB, nbB);
+        else if (bIrr) texelTargets(8, int(teB % 6u) + 1, int(teB / 6u) + 1, pr.irrW, interiorB, borderB, nbB);
+        const float rwA = sRw[teA], rwB = bDepth ? sRw[teB] : (bIrr ? sRw[196u + teB] : 0.0f);
+        const bool normA = rwA > 1e-3f, normB = rwB > 1e-3f;
+        const float rwInvA = normA ? __frcp_rn(rwA) : 0.0f, rwInvB = normB ? __frcp_rn(rwB) : 0.0f;
         const float hysteresis = bp.grid.hysteresis;
-        // warp-uniform: does this warp hold any useful row? (tile 1: warps 4, 5 depth; warp 6 depth rows 64..67 + irradiance 68..95; warp 7 irradiance 96..103)
-        const bool depthWarp = !tile1 || (warp & 3u) < 3u; // depth rows: tile 0 all warps, tile 1 warps 4..6 (rows 0..95, of which 0..67 are texels)
-        const bool irrWarp = tile1 && (warp & 3u) >= 2u;   // irradiance rows 68..103 live in warps 6 and 7
-        const uint32_t* prevAtlas = isDepth ? pr.depWork : pr.irrWork;
+        const bool warpHasBDepth = quarter * 32u < 68u;          // warp-uniform: quarters 0, 1, 2 hold depth rows of tile 1
+        const bool warpHasIrr = quarter >= 2u;                    // warp-uniform: irradiance rows 68..103 live in quarters 2 and 3
+        const uint32_t* prevAtlasB = bDepth ? pr.depWork : pr.irrWork;
+        const uint32_t pBegin = half * (BTC_P / 2u);
         uint32_t it = 0;
         for (uint32_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x, ++it) {
             const uint32_t slot0 = tile * BTC_P;
             const uint32_t np = min(uint32_t(BTC_P), bp.count - slot0);
+            const uint32_t pEnd = min(np, pBegin + BTC_P / 2u);
             TileMeta& meta = sMeta[it & 1u];
             // While the tensor core accumulates this tile the epilogue warps are idle: they work out where the tile's probes live and pull
-            // the previous texels (the work atlases were last touched a frame ago: DRAM) into L2, then hold the first group in registers.
+            // the previous texels (the work atlases were last touched a frame ago: DRAM) into L2.
             if (tid < BTC_P) {
                 uint32_t lin = 0, oD = 0, oI = 0;
                 if (tid < np) {
@@ -339,41 +346,72 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
                 meta.linear[tid] = lin; meta.originD[tid] = oD; meta.originI[tid] = oI;
             }
             namedBarrier(2, BTC_EPI_WARPS * 32u);
-            const uint32_t* origin = isDepth ? meta.originD : meta.originI;
-            if (isDepth || isIrr) for (uint32_t p = 8u; p < np; ++p) asm volatile("prefetch.global.L2 [%0];" ::"l"(prevAtlas + origin[p] + interior));
-            uint32_t prevWord[8], nextWord[8];
+            const uint32_t* originB = bDepth ? meta.originD : meta.originI;
+            // Previous texels of this thread's probes -> its private column of the staging area (the same thread reads them back: no
+            // barrier). Real loads, eight in flight, issued a whole main loop before they are needed: the drain below touches global
+            // memory only with stores, and those go to sectors these loads have just brought into L2. (prefetch.global.L2 hints were
+            // dropped under load: drains of 17 k cycles with them honoured, 125 k without.)
+            for (uint32_t p0 = pBegin; p0 < pEnd; p0 += 8u) {
+                uint32_t a[8], b[8];
 #pragma unroll
-            for (uint32_t q = 0; q < 8; ++q) prevWord[q] = ((isDepth || isIrr) && q < np) ? prevAtlas[origin[q] + interior] : 0u;
+                for (uint32_t q = 0; q < 8; ++q) {
+                    const bool in = p0 + q < pEnd;
+                    a[q] = in ? pr.depWork[meta.originD[p0 + q] + interiorA] : 0u;
+                    b[q] = (in && (bDepth || bIrr)) ? prevAtlasB[originB[p0 + q] + interiorB] : 0u;
+                }
+#pragma unroll
+                for (uint32_t q = 0; q < 8; ++q) { smemPrev[((p0 - pBegin + q) * 2u + 0u) * (BTC_EPI_WARPS * 32u) + tid] = a[q]; smemPrev[((p0 - pBegin + q) * 2u + 1u) * (BTC_EPI_WARPS * 32u) + tid] = b[q]; }
+            }
             if (tid == 0) BTC_TIMED(8, mbarWait(&barAccFull, it & 1u)); else mbarWait(&barAccFull, it & 1u);
             __syncwarp(); // reconverge before the warp-aligned tcgen05.ld below
             tcFenceAfter();
             const long long tEpi = (prof && tid == 0) ? clock64() : 0;
-            for (uint32_t p0 = 0; p0 < ((diag & 4u) ? 0u : np); p0 += 8u) { // eight probes per pass (diag bit 2: skipped)
-                const uint32_t npj = min(8u, np - p0);
+            for (uint32_t p0 = pBegin; p0 < ((diag & 4u) ? 0u : pEnd); p0 += 8u) { // eight probes per pass (diag bit 2: skipped)
+                const uint32_t npj = min(8u, pEnd - p0);
+                uint32_t prevA[8], prevB[8];
 #pragma unroll
-                for (uint32_t q = 0; q < 8; ++q) nextWord[q] = ((isDepth || isIrr) && p0 + 8u + q < np) ? prevAtlas[origin[p0 + 8u + q] + interior] : 0u; // the next pass's previous texels
-                if (depthWarp) {
+                for (uint32_t q = 0; q < 8; ++q) { prevA[q] = smemPrev[((p0 - pBegin + q) * 2u + 0u) * (BTC_EPI_WARPS * 32u) + tid]; prevB[q] = smemPrev[((p0 - pBegin + q) * 2u + 1u) * (BTC_EPI_WARPS * 32u) + tid]; }
+                { // tile 0: depth texel teA of probes p0 .. p0 + 7 (columns 2 p, 2 p + 1)
                     uint32_t v[16];
-                    tmemLoad16(tmem + laneBase + (tile1 ? 2u * BTC_P : 0u) + 2u * p0, v);
+                    tmemLoad16(tmem + laneBase + 2u * p0, v);
                     tmemLoadWait();
-                    if (isDepth) {
+#pragma unroll
+                    for (uint32_t q = 0; q < 8; ++q) {
+                        if (q >= npj) break;
+                        float r0 = __uint_as_float(v[2 * q]), r1 = __uint_as_float(v[2 * q + 1]);
+                        if (normA) { r0 = divShared(r0, rwA, rwInvA); r1 = divShared(r1, rwA, rwInvA); } // probesUpdate.glsl:85-86
+                        const float2 prev = unpackRG16F(prevA[q]);
+                        const float o0 = mixf(r0, prev.x, hysteresis), o1 = mixf(r1, prev.y, hysteresis); // :103
+                        const uint32_t word = packRG16Fx2(o0, o1);
+                        uint32_t* tileBase = pr.depWork + meta.originD[p0 + q];
+                        tileBase[interiorA] = word;
+#pragma unroll
+                        for (int b = 0; b < 3; ++b) if (b < nbA) tileBase[borderA[b]] = word;   // probesCopyBorders.comp
+                        if (depUnpacked) { float* up = depUnpacked + (size_t(slotBase + slot0 + p0 + q) * 196 + teA) * 2; up[0] = o0; up[1] = o1; }
+                    }
+                }
+                if (warpHasBDepth) { // tile 1, depth rows (columns 2 P + 2 p ..)
+                    uint32_t v[16];
+                    tmemLoad16(tmem + laneBase + 2u * BTC_P + 2u * p0, v);
+                    tmemLoadWait();
+                    if (bDepth) {
 #pragma unroll
                         for (uint32_t q = 0; q < 8; ++q) {
                             if (q >= npj) break;
                             float r0 = __uint_as_float(v[2 * q]), r1 = __uint_as_float(v[2 * q + 1]);
-                            if (norm) { r0 = divShared(r0, rw, rwInv); r1 = divShared(r1, rw, rwInv); } // probesUpdate.glsl:85-86
-                            const float2 prev = unpackRG16F(prevWord[q]);
-                            const float o0 = mixf(r0, prev.x, hysteresis), o1 = mixf(r1, prev.y, hysteresis); // :103
+                            if (normB) { r0 = divShared(r0, rwB, rwInvB); r1 = divShared(r1, rwB, rwInvB); }
+                            const float2 prev = unpackRG16F(prevB[q]);
+                            const float o0 = mixf(r0, prev.x, hysteresis), o1 = mixf(r1, prev.y, hysteresis);
                             const uint32_t word = packRG16Fx2(o0, o1);
                             uint32_t* tileBase = pr.depWork + meta.originD[p0 + q];
-                            tileBase[interior] = word;
+                            tileBase[interiorB] = word;
 #pragma unroll
-                            for (int b = 0; b < 3; ++b) if (b < nb) tileBase[border[b]] = word;   // probesCopyBorders.comp
-                            if (depUnpacked) { float* up = depUnpacked + (size_t(slotBase + slot0 + p0 + q) * 196 + te) * 2; up[0] = o0; up[1] = o1; }
+                            for (int b = 0; b < 3; ++b) if (b < nbB) tileBase[borderB[b]] = word;
+                            if (depUnpacked) { float* up = depUnpacked + (size_t(slotBase + slot0 + p0 + q) * 196 + teB) * 2; up[0] = o0; up[1] = o1; }
                         }
                     }
                 }
-                if (irrWarp) {
+                if (warpHasIrr) { // tile 1, irradiance rows (columns 4 P + 3 p ..)
                     uint32_t v[24];
                     uint32_t a[16], b8[8];
                     tmemLoad16(tmem + laneBase + 4u * BTC_P + 3u * p0, a);
@@ -387,32 +425,30 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
                     for (uint32_t q = 0; q < 8; ++q) {
                         if (q >= npj) break; // warp-uniform
                         float maxChange = 0.0f;
-                        if (isIrr) {
+                        if (bIrr) {
                             float r0 = __uint_as_float(v[3 * q]), r1 = __uint_as_float(v[3 * q + 1]), r2 = __uint_as_float(v[3 * q + 2]);
-                            if (norm) { r0 = divShared(r0, rw, rwInv); r1 = divShared(r1, rw, rwInv); r2 = divShared(r2, rw, rwInv); }
-                            const float3 prev = unpackR11G11B10(prevWord[q]);
+                            if (normB) { r0 = divShared(r0, rwB, rwInvB); r1 = divShared(r1, rwB, rwInvB); r2 = divShared(r2, rwB, rwInvB); }
+                            const float3 prev = unpackR11G11B10(prevB[q]);
                             maxChange = maxS(maxS(fabsf(r0 - prev.x), fabsf(r1 - prev.y)), fabsf(r2 - prev.z));
                             const float o0 = mixf(r0, prev.x, hysteresis), o1 = mixf(r1, prev.y, hysteresis), o2 = mixf(r2, prev.z, hysteresis);
                             const uint32_t word = packR11G11B10(o0, o1, o2);
                             uint32_t* tileBase = pr.irrWork + meta.originI[p0 + q];
-                            tileBase[interior] = word;
+                            tileBase[interiorB] = word;
 #pragma unroll
-                            for (int b = 0; b < 3; ++b) if (b < nb) tileBase[border[b]] = word;
-                            if (irrUnpacked) { float* up = irrUnpacked + (size_t(slotBase + slot0 + p0 + q) * 36 + te) * 3; up[0] = o0; up[1] = o1; up[2] = o2; }
+                            for (int b = 0; b < 3; ++b) if (b < nbB) tileBase[borderB[b]] = word;
+                            if (irrUnpacked) { float* up = irrUnpacked + (size_t(slotBase + slot0 + p0 + q) * 36 + teB) * 3; up[0] = o0; up[1] = o1; up[2] = o2; }
                         }
                         // probesUpdate.glsl:106-107: maximum over the probe's 36 texels (non-negative floats order like their bit patterns)
                         const uint32_t wmax = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(maxChange));
                         if (lane == 0 && wmax) atomicMax(&meta.maxChange[p0 + q], wmax);
                     }
                 }
-#pragma unroll
-                for (uint32_t q = 0; q < 8; ++q) prevWord[q] = nextWord[q];
             }
             // tensor memory is free for the next tile
             tcFenceBefore();
             __syncwarp();
             if (lane == 0) mbarArrive(&barAccEmpty);
-            if (prof && tid == 0) pacc[9] += (unsigned long long)(clock64() - tEpi);
+            if (prof && tid == 0) { const unsigned long long d = (unsigned long long)(clock64() - tEpi); pacc[9] += d; if (it == 0) pacc[13] = d; else if (it == 1) pacc[14] = d; }
             const long long tBar = (prof && tid == 0) ? clock64() : 0;
             namedBarrier(1, BTC_EPI_WARPS * 32u); // (aligned barrier: every lane of the warp must execute the same instruction - no divergent timing wrapper here)
             if (prof && tid == 0) pacc[10] += (unsigned long long)(clock64() - tBar); // every texel of the tile is mixed: maxChange is complete
@@ -434,10 +470,10 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
         }
     }
     if (prof) { // slot owners: TMA lane (0), MMA lane (1-4, 11, 12), first producer thread (5-7), first epilogue thread (8-10)
-        const bool owner[13] = {warp == BTC_TMA_WARP && lane == 0, warp == BTC_MMA_WARP && lane == 0, warp == BTC_MMA_WARP && lane == 0, warp == BTC_MMA_WARP && lane == 0, warp == BTC_MMA_WARP && lane == 0,
-                                tid == BTC_EPI_WARPS * 32u, tid == BTC_EPI_WARPS * 32u, tid == BTC_EPI_WARPS * 32u, tid == 0, tid == 0, tid == 0, warp == BTC_MMA_WARP && lane == 0, warp == BTC_MMA_WARP && lane == 0};
+        const bool owner[16] = {warp == BTC_TMA_WARP && lane == 0, warp == BTC_MMA_WARP && lane == 0, warp == BTC_MMA_WARP && lane == 0, warp == BTC_MMA_WARP && lane == 0, warp == BTC_MMA_WARP && lane == 0,
+                                tid == BTC_EPI_WARPS * 32u, tid == BTC_EPI_WARPS * 32u, tid == BTC_EPI_WARPS * 32u, tid == 0, tid == 0, tid == 0, warp == BTC_MMA_WARP && lane == 0, warp == BTC_MMA_WARP && lane == 0, tid == 0, tid == 0, warp == BTC_MMA_WARP && lane == 0};
 #pragma unroll
-        for (int k = 0; k < 13; ++k) if (owner[k]) prof[blockIdx.x * 16 + k] = pacc[k];
+        for (int k = 0; k < 16; ++k) if (owner[k]) prof[blockIdx.x * 16 + k] = pacc[k];
     }
     tcFenceBefore();
     __syncthreads();
@@ -461,8 +497,9 @@ int blendTcLaunch(vkx_ctx* ctx, const BlendParams& bp, const DeviceProbes& pr, c
                                                                       ctx->debugBuffers ? ctx->dDepUnpacked : nullptr, slotBase, prof, diag); LAUNCH_CHECK(ctx);
     if (prof) { // diagnostics: mean / max cycles per CTA of every instrumented wait (slots: see BTC_TIMED uses)
         cudaStreamSynchronize(st);
-        static const char* names[16] = {"tma: wait emptyA", "mma: wait accEmpty", "mma: wait fullA", "mma: wait fullB", "mma: total", "prod: wait metaFree", "prod: wait emptyB", "prod: convert+arrive", "epi: wait accFull", "epi: drain+mix", "epi: named barrier", "mma: issue 18 MMAs", "mma: commits", "", "", ""};
-        for (int k = 0; k < 13; ++k) { double sum = 0, mx = 0; for (unsigned b = 0; b < grid; ++b) { const double v = double(prof[b * 16 + k]); sum += v; mx = v > mx ? v : mx; } fprintf(stderr, "[blend_tc profile] %-22s mean %10.0f max %10.0f cycles per CTA (%u CTAs, %u probes)\n", names[k], sum / grid, mx, grid, n); }
+        static const char* names[16] = {"tma: wait emptyA", "mma: wait accEmpty", "mma: wait fullA", "mma: wait fullB", "mma: total", "prod: wait metaFree", "prod: wait emptyB", "prod: convert+arrive", "epi: wait accFull", "epi: drain+mix", "epi: named barrier", "mma: issue 18 MMAs", "mma: commits", "epi: drain of tile 0", "epi: drain of tile 1", "mma: first tile issued"};
+        for (int k = 0; k < 16; ++k) { double sum = 0, mx = 0; for (unsigned b = 0; b < grid; ++b) { const double v = double(prof[b * 16 + k]); sum += v; mx = v > mx ? v : mx; } fprintf(stderr, "[blend_tc profile] %-22s mean %10.0f max %10.0f cycles per CTA (%u CTAs, %u probes)\n", names[k], sum / grid, mx, grid, n); }
+        if (getenv("VKX_BLEND_PROFILE")[0] == '2') for (unsigned b = 0; b < grid; b += 12) { fprintf(stderr, "[blend_tc cta %3u]", b); for (int k = 0; k < 16; ++k) fprintf(stderr, " %7llu", prof[b * 16 + k]); fprintf(stderr, "\n"); }
         cudaFree(prof);
     }
     return VKX_OK;

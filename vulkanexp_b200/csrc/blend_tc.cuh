@@ -26,7 +26,7 @@ __device__ __forceinline__ void blendBorderSource(int T, int x, int y, int& sx, 
 // ---- tensor-core blend geometry (blend_tc.cu)
 #define BTC_P 64u            // probes per tile: N = 128 (depth planes) / 192 (colour planes)
 #define BTC_KC 16u           // rays per chunk (two K = 8 TF32 MMAs)
-#define BTC_ASTAGES 4u       // weight chunks in flight (TMA warp -> MMA warp): the bulk copies need ~4 chunk periods of L2 latency
+#define BTC_ASTAGES 2u       // weight chunks in flight (TMA warp -> MMA warp); measured: the MMA warp waits < 3 % of its time for them
 #define BTC_BSTAGES 2u       // ray-data chunks in flight (producer warps -> MMA warp)
 #define BTC_EPI_WARPS 8u     // warps 0..3: accumulator rows of weight tile 0, warps 4..7: weight tile 1 (a warp reads the TMEM lane quarter warp % 4)
 #define BTC_PROD_WARPS 8u    // warps 8..15: ray records -> TF32 hi / lo operand tiles
@@ -55,7 +55,8 @@ __device__ __forceinline__ void blendBorderSource(int T, int x, int y, int& sx, 
 #define BTC_BD_TILE_BYTES (16u * BTC_SBO)                // 128 rows: (probe, d | d^2)
 #define BTC_BC_TILE_BYTES (24u * BTC_SBO)                // 192 rows: (probe, r | g | b)
 #define BTC_B_STAGE_BYTES (2u * BTC_BD_TILE_BYTES + 2u * BTC_BC_TILE_BYTES)
-#define BTC_SMEM_BYTES (BTC_ASTAGES * BTC_A_CHUNK_BYTES + BTC_BSTAGES * BTC_B_STAGE_BYTES)
+#define BTC_PREV_BYTES (BTC_EPI_WARPS * 32u * BTC_P * 4u) // previous texels of a tile: (probes / 2) x 2 texels per epilogue thread
+#define BTC_SMEM_BYTES (BTC_ASTAGES * BTC_A_CHUNK_BYTES + BTC_BSTAGES * BTC_B_STAGE_BYTES + BTC_PREV_BYTES)
 #define BTC_IMAGE_BYTES (size_t(BTC_MAX_CHUNKS) * BTC_A_CHUNK_BYTES)
 
 int blendTcWeights(vkx_ctx* ctx, cudaStream_t st);  // per frame, after k_blend_weights: the A-operand image

@@ -227,9 +227,16 @@ __host__ __device__ inline float unkey(uint32_t k) {
 // ---- atlas texel formats (integer code identical to oracle/packing.h)
 template <int MB>
 __device__ inline uint32_t packUF(float f) {
-    if (!(f > 0.0f)) return 0;
     const uint32_t maxCode = (31u << MB) - 1u;
     uint32_t b = __float_as_uint(f);
+    // Fast path, 2^-14 <= f < 2^16 (a normal number of the target format, or overflow): re-bias the exponent, round to nearest even
+    // by adding half - 1 + lsb below the kept bits (a carry out of the mantissa increments the exponent, as it should), clamp.
+    // Same code as the general path below for every such f.
+    if (b - (113u << 23) < (30u << 23)) {
+        const uint32_t t = b - (112u << 23) + ((1u << (22 - MB)) - 1u) + ((b >> (23 - MB)) & 1u);
+        return min(t >> (23 - MB), maxCode);
+    }
+    if (!(f > 0.0f)) return 0;
     int e = int(b >> 23) - 127;
     uint32_t m = b & 0x7FFFFFu;
     if (e > 15) return maxCode;
