@@ -15,11 +15,14 @@
 //     [0,128), depth tile 1 -> [128,256), tile 1 x colour planes -> [256,448) (only its irradiance rows are read back). One lane of
 //     the MMA warp issues them; tcgen05.commit releases the stage (`empty`) and, after a tile's last chunk, publishes the accumulators
 //     (`accFull`). Producers and TMA run ahead into the next tile while the epilogue drains the accumulators.
-//   * epilogue: eight warps, one accumulator row (= texel) per thread: tcgen05.ld brings the sums of 8 probes at a time, the thread
-//     normalises, mixes with the previous texel of the work atlas (hysteresis), packs and stores the interior texel and the border
-//     texels that copy from it (probesCopyBorders.comp inverted: every border texel has exactly one interior source) straight to
-//     global memory - no shared-memory staging, no block-wide barrier; `accEmpty` hands tensor memory back to the MMA warp. The
-//     per-probe state machine (probesUpdate.glsl:110-119) runs after a barrier among the epilogue warps.
+//   * epilogue: eight warps. A warp reads the TMEM lane quarter warp % 4, so the two warps of a quarter split the tile's probes. While
+//     the tensor core works on the tile they load the previous texels of their (texel, probe) pairs into a private shared-memory
+//     column; when `accFull` arrives each thread reads its accumulator row with tcgen05.ld (8 probes at a time), normalises (exact
+//     quotient through a shared reciprocal), mixes with the previous texel (hysteresis), packs and puts the result back into its
+//     column - no global memory traffic, so tensor memory is handed back (`accEmpty`) after ~7 k cycles. Then all eight warps write
+//     the tile out: 128-bit pieces of atlas rows, border texels taken from the interior texel probesCopyBorders.comp copies them from,
+//     four lanes per 64-byte row = full sectors (scattered 4-byte stores from the accumulator rows measured 100 k cycles per tile),
+//     and the per-probe state machine (probesUpdate.glsl:110-119) runs. This overlaps the next tile's main loop.
 // Accuracy: the split keeps 21 mantissa bits per operand; pre-pack fp32 texels agree with the oracle like the CUDA-core kernel's
 // (tests/test_ddgi_parity.py).
 #include "common.cuh"
@@ -188,7 +191,7 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
         // ------------------------------------------------------------------------------------------ weights: one bulk copy per chunk
         if (lane == 0) {
             uint32_t g = 0; // chunks issued by this CTA so far (stage = g % STAGES, use = g / STAGES)
-            for (uint32_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x)
+            for (uint32_t lt = blockIdx.x; lt < numTiles; lt += gridDim.x)
                 for (uint32_t c = 0; c < chunks; ++c, ++g) {
                     const uint32_t s = g % BTC_ASTAGES, use = g / BTC_ASTAGES;
                     if (use) BTC_TIMED(0, mbarWait(&barEmptyA[s], (use - 1u) & 1u));
@@ -203,7 +206,7 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
             const long long tStart = clock64();
             uint32_t g = 0, it = 0;
             constexpr uint32_t idD = ummaIdesc(2 * BTC_P), idC = ummaIdesc(3 * BTC_P);
-            for (uint32_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x, ++it) {
+            for (uint32_t lt = blockIdx.x; lt < numTiles; lt += gridDim.x, ++it) {
                 if (it) { BTC_TIMED(1, mbarWait(&barAccEmpty, (it - 1u) & 1u)); tcFenceAfter(); } // the epilogue has read the previous tile's accumulators
                 for (uint32_t c = 0; c < chunks; ++c, ++g) {
                     const uint32_t sa = g % BTC_ASTAGES, useA = g / BTC_ASTAGES, sb = g % BTC_BSTAGES, useB = g / BTC_BSTAGES;
@@ -247,11 +250,12 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
         static_assert(EPT == BTC_KC / 4u && BTC_PROD_WARPS * 32u == 4u * BTC_P, "one K core per element");
         const uint32_t myP = pt >> 2, myKq = pt & 3u;
         uint32_t g = 0, it = 0;
-        for (uint32_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x, ++it) {
+        for (uint32_t lt = blockIdx.x; lt < numTiles; lt += gridDim.x, ++it) {
+            const uint32_t tile = (diag & 8u) ? numTiles - 1u - lt : lt; // diagnostics: reversed tile order
             const uint32_t slot0 = tile * BTC_P;
             const uint32_t np = min(uint32_t(BTC_P), bp.count - slot0);
             TileMeta& meta = sMeta[it & 1u];
-            if (it >= 2u) { if (pt == 0) BTC_TIMED(5, mbarWait(&barMetaFree[it & 1u], ((it >> 1) - 1u) & 1u)); else mbarWait(&barMetaFree[it & 1u], ((it >> 1) - 1u) & 1u); } // the epilogue two tiles back is done with this meta block
+            if (it >= 2u) mbarWait(&barMetaFree[it & 1u], ((it >> 1) - 1u) & 1u); // the epilogue two tiles back is done with this meta block
             const float4* myRays = rays + size_t(slot0 + myP) * N;
             auto fetch = [&](uint32_t c, float4 (&rd)[EPT]) {
 #pragma unroll
@@ -326,8 +330,28 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
         const bool warpHasIrr = quarter >= 2u;                    // warp-uniform: irradiance rows 68..103 live in quarters 2 and 3
         const uint32_t* prevAtlasB = bDepth ? pr.depWork : pr.irrWork;
         const uint32_t pBegin = half * (BTC_P / 2u);
+        // Write-out job of this thread (after the drain the staging area holds the tile's new interior texels): 128-bit piece k of a
+        // probe's two atlas tiles, k < 64: row k / 4 of the 16 x 16 depth tile, texels 4 (k % 4) .. + 3; k >= 64: row (k - 64) / 2 of the
+        // 8 x 8 irradiance tile. Border texels take their value from the interior texel probesCopyBorders.comp copies them from
+        // (blendBorderSource). Three probes per pass (240 of the 256 threads); the four lanes of a row write 64 contiguous bytes:
+        // full sectors only (scattered 4-byte stores straight from the accumulator rows took 100 k cycles per tile instead of 17 k).
+        const uint32_t woProbe = tid / 80u, woK = tid % 80u; // woProbe == 3: idle
+        const bool woDepth = woK < 64u;
+        const uint32_t woRow = woDepth ? woK >> 2 : (woK - 64u) >> 1, woQuad = woDepth ? woK & 3u : (woK - 64u) & 1u;
+        uint32_t woRel[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int T = woDepth ? 16 : 8, x = int(4u * woQuad) + j, y = int(woRow);
+            int sx = x, sy = y;
+            if (x == 0 || y == 0 || x == T - 1 || y == T - 1) blendBorderSource(T, x, y, sx, sy);
+            const uint32_t te = uint32_t((sy - 1) * (T - 2) + (sx - 1));
+            // staging slot of an interior texel relative to its probe's block: depth texel te < 128 -> column te of plane A, else column
+            // te - 128 of plane B; irradiance texel ti -> column 68 + ti of plane B (a plane = one word per epilogue thread)
+            woRel[j] = woDepth ? (te < 128u ? te : BTC_EPI_WARPS * 32u + te - 128u) : BTC_EPI_WARPS * 32u + 68u + te;
+        }
         uint32_t it = 0;
-        for (uint32_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x, ++it) {
+        for (uint32_t lt = blockIdx.x; lt < numTiles; lt += gridDim.x, ++it) {
+            const uint32_t tile = (diag & 8u) ? numTiles - 1u - lt : lt; // diagnostics: reversed tile order
             const uint32_t slot0 = tile * BTC_P;
             const uint32_t np = min(uint32_t(BTC_P), bp.count - slot0);
             const uint32_t pEnd = min(np, pBegin + BTC_P / 2u);
@@ -373,8 +397,10 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
                 for (uint32_t q = 0; q < 8; ++q) { prevA[q] = smemPrev[((p0 - pBegin + q) * 2u + 0u) * (BTC_EPI_WARPS * 32u) + tid]; prevB[q] = smemPrev[((p0 - pBegin + q) * 2u + 1u) * (BTC_EPI_WARPS * 32u) + tid]; }
                 { // tile 0: depth texel teA of probes p0 .. p0 + 7 (columns 2 p, 2 p + 1)
                     uint32_t v[16];
+                    const long long tT = (prof && tid == 0) ? clock64() : 0;
                     tmemLoad16(tmem + laneBase + 2u * p0, v);
                     tmemLoadWait();
+                    if (prof && tid == 0) pacc[5] += (unsigned long long)(clock64() - tT);
 #pragma unroll
                     for (uint32_t q = 0; q < 8; ++q) {
                         if (q >= npj) break;
@@ -383,10 +409,7 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
                         const float2 prev = unpackRG16F(prevA[q]);
                         const float o0 = mixf(r0, prev.x, hysteresis), o1 = mixf(r1, prev.y, hysteresis); // :103
                         const uint32_t word = packRG16Fx2(o0, o1);
-                        uint32_t* tileBase = pr.depWork + meta.originD[p0 + q];
-                        tileBase[interiorA] = word;
-#pragma unroll
-                        for (int b = 0; b < 3; ++b) if (b < nbA) tileBase[borderA[b]] = word;   // probesCopyBorders.comp
+                        smemPrev[((p0 - pBegin + q) * 2u + 0u) * (BTC_EPI_WARPS * 32u) + tid] = word; // the new texel replaces the previous one in this thread's staging column
                         if (depUnpacked) { float* up = depUnpacked + (size_t(slotBase + slot0 + p0 + q) * 196 + teA) * 2; up[0] = o0; up[1] = o1; }
                     }
                 }
@@ -403,10 +426,7 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
                             const float2 prev = unpackRG16F(prevB[q]);
                             const float o0 = mixf(r0, prev.x, hysteresis), o1 = mixf(r1, prev.y, hysteresis);
                             const uint32_t word = packRG16Fx2(o0, o1);
-                            uint32_t* tileBase = pr.depWork + meta.originD[p0 + q];
-                            tileBase[interiorB] = word;
-#pragma unroll
-                            for (int b = 0; b < 3; ++b) if (b < nbB) tileBase[borderB[b]] = word;
+                            smemPrev[((p0 - pBegin + q) * 2u + 1u) * (BTC_EPI_WARPS * 32u) + tid] = word;
                             if (depUnpacked) { float* up = depUnpacked + (size_t(slotBase + slot0 + p0 + q) * 196 + teB) * 2; up[0] = o0; up[1] = o1; }
                         }
                     }
@@ -432,10 +452,7 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
                             maxChange = maxS(maxS(fabsf(r0 - prev.x), fabsf(r1 - prev.y)), fabsf(r2 - prev.z));
                             const float o0 = mixf(r0, prev.x, hysteresis), o1 = mixf(r1, prev.y, hysteresis), o2 = mixf(r2, prev.z, hysteresis);
                             const uint32_t word = packR11G11B10(o0, o1, o2);
-                            uint32_t* tileBase = pr.irrWork + meta.originI[p0 + q];
-                            tileBase[interiorB] = word;
-#pragma unroll
-                            for (int b = 0; b < 3; ++b) if (b < nbB) tileBase[borderB[b]] = word;
+                            smemPrev[((p0 - pBegin + q) * 2u + 1u) * (BTC_EPI_WARPS * 32u) + tid] = word;
                             if (irrUnpacked) { float* up = irrUnpacked + (size_t(slotBase + slot0 + p0 + q) * 36 + teB) * 3; up[0] = o0; up[1] = o1; up[2] = o2; }
                         }
                         // probesUpdate.glsl:106-107: maximum over the probe's 36 texels (non-negative floats order like their bit patterns)
@@ -464,14 +481,23 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
                 }
                 pr.stateWork[linearIndex] = stt;
             }
+            if (woProbe < 3u && !(diag & 16u)) {
+                for (uint32_t p = woProbe; p < np; p += 3u) {
+                    // probe p's block: local probe p % 32 of half p / 32 -> threads 128 (p / 32) .. + 127 of both planes
+                    const uint32_t* blk = smemPrev + (p & 31u) * 2u * (BTC_EPI_WARPS * 32u) + (p >> 5) * 128u;
+                    const uint4 w = make_uint4(blk[woRel[0]], blk[woRel[1]], blk[woRel[2]], blk[woRel[3]]);
+                    if (woDepth) *reinterpret_cast<uint4*>(pr.depWork + meta.originD[p] + size_t(woRow) * pr.depW + 4u * woQuad) = w;
+                    else *reinterpret_cast<uint4*>(pr.irrWork + meta.originI[p] + size_t(woRow) * pr.irrW + 4u * woQuad) = w;
+                }
+            }
             if (tid < BTC_P) { meta.outOfRange[tid] = 0u; meta.maxChange[tid] = 0u; }
-            __syncwarp();
+            namedBarrier(3, BTC_EPI_WARPS * 32u); // the staging area and the tile's meta block may be rewritten (next tile's previous texels)
             if (lane == 0) mbarArrive(&barMetaFree[it & 1u]); // release semantics: the zeroes above are visible to the producers that wait
         }
     }
     if (prof) { // slot owners: TMA lane (0), MMA lane (1-4, 11, 12), first producer thread (5-7), first epilogue thread (8-10)
         const bool owner[16] = {warp == BTC_TMA_WARP && lane == 0, warp == BTC_MMA_WARP && lane == 0, warp == BTC_MMA_WARP && lane == 0, warp == BTC_MMA_WARP && lane == 0, warp == BTC_MMA_WARP && lane == 0,
-                                tid == BTC_EPI_WARPS * 32u, tid == BTC_EPI_WARPS * 32u, tid == BTC_EPI_WARPS * 32u, tid == 0, tid == 0, tid == 0, warp == BTC_MMA_WARP && lane == 0, warp == BTC_MMA_WARP && lane == 0, tid == 0, tid == 0, warp == BTC_MMA_WARP && lane == 0};
+                                tid == 0, tid == BTC_EPI_WARPS * 32u, tid == BTC_EPI_WARPS * 32u, tid == 0, tid == 0, tid == 0, warp == BTC_MMA_WARP && lane == 0, warp == BTC_MMA_WARP && lane == 0, tid == 0, tid == 0, warp == BTC_MMA_WARP && lane == 0};
 #pragma unroll
         for (int k = 0; k < 16; ++k) if (owner[k]) prof[blockIdx.x * 16 + k] = pacc[k];
     }
@@ -497,7 +523,7 @@ int blendTcLaunch(vkx_ctx* ctx, const BlendParams& bp, const DeviceProbes& pr, c
                                                                       ctx->debugBuffers ? ctx->dDepUnpacked : nullptr, slotBase, prof, diag); LAUNCH_CHECK(ctx);
     if (prof) { // diagnostics: mean / max cycles per CTA of every instrumented wait (slots: see BTC_TIMED uses)
         cudaStreamSynchronize(st);
-        static const char* names[16] = {"tma: wait emptyA", "mma: wait accEmpty", "mma: wait fullA", "mma: wait fullB", "mma: total", "prod: wait metaFree", "prod: wait emptyB", "prod: convert+arrive", "epi: wait accFull", "epi: drain+mix", "epi: named barrier", "mma: issue 18 MMAs", "mma: commits", "epi: drain of tile 0", "epi: drain of tile 1", "mma: first tile issued"};
+        static const char* names[16] = {"tma: wait emptyA", "mma: wait accEmpty", "mma: wait fullA", "mma: wait fullB", "mma: total", "epi: tmem ld tile0 blk", "prod: wait emptyB", "prod: convert+arrive", "epi: wait accFull", "epi: drain+mix", "epi: named barrier", "mma: issue 18 MMAs", "mma: commits", "epi: drain of tile 0", "epi: drain of tile 1", "mma: first tile issued"};
         for (int k = 0; k < 16; ++k) { double sum = 0, mx = 0; for (unsigned b = 0; b < grid; ++b) { const double v = double(prof[b * 16 + k]); sum += v; mx = v > mx ? v : mx; } fprintf(stderr, "[blend_tc profile] %-22s mean %10.0f max %10.0f cycles per CTA (%u CTAs, %u probes)\n", names[k], sum / grid, mx, grid, n); }
         if (getenv("VKX_BLEND_PROFILE")[0] == '2') for (unsigned b = 0; b < grid; b += 12) { fprintf(stderr, "[blend_tc cta %3u]", b); for (int k = 0; k < 16; ++k) fprintf(stderr, " %7llu", prof[b * 16 + k]); fprintf(stderr, "\n"); }
         cudaFree(prof);
