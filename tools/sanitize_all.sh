@@ -7,14 +7,14 @@ sum=$out/${tag}_sanitizer.txt; : > $sum
 run() { # name, tool, env...
   name=$1; tool=$2; shift 2
   log=$out/${tag}_sanitizer_${name}_${tool}.log
-  env "$@" timeout 900 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_small.py > $log 2>&1
+  env "$@" timeout 420 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_small.py > $log 2>&1
   rc=$?
   echo "$name [$*] $tool: rc=$rc; $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' $log | tail -1); $(grep -c 'sanitize pass ok' $log) pass line(s)" | tee -a $sum
 }
 for tool in memcheck racecheck; do
   run default $tool VKX_PT_POOL=0 VKX_BLEND=tc
-  run pool $tool VKX_PT_POOL=1 VKX_BLEND=tc
-  run simt_defer $tool VKX_PT_POOL=0 VKX_BLEND=simt VKX_PT_DEFER=16 VKX_PT_DEFER_SHADOW=12
+  run pool_simt_defer $tool VKX_PT_POOL=1 VKX_BLEND=simt VKX_PT_DEFER=16 VKX_PT_DEFER_SHADOW=12
 done
-run default initcheck VKX_PT_POOL=1 VKX_BLEND=tc
+run default initcheck VKX_PT_POOL=0 VKX_BLEND=tc
+run default synccheck VKX_PT_POOL=0 VKX_BLEND=tc
 cat $sum

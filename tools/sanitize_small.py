@@ -12,6 +12,7 @@ from vulkanexp_b200.pods import GridInfo, Light, make_camera
 
 flat = scene_format.flatten(synth.make_open_court(columns=2, col_segments=6, col_stacks=1))
 g = Context(0); g.scene_upload(flat); g.bvh_build()
+g.instances_update(flat["instances"]); g.bvh_refit()  # topology-preserving refit kernels
 for rays in (17, 64):
     grid = GridInfo.make(flat["bounds_min"], flat["bounds_max"], (5, 3, 4), rays, hysteresis=0.5)
     g.probes_debug(rays == 17)

@@ -296,6 +296,7 @@ static int allocProbeScratch(vkx_ctx* ctx) {
     CUDA_TRY(ctx, cudaMalloc(&ctx->dShadowVis, maxRays));
     CUDA_TRY(ctx, cudaMalloc(&ctx->dMissQueue, maxRays * 4));
     CUDA_TRY(ctx, cudaMalloc(&ctx->dFrontQueue, maxRays * 4));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->dFrontQueue, 0, maxRays * 4, ctx->stream)); // the sort carries the unused tail (keys all-ones) along: defined values, once
     CUDA_TRY(ctx, cudaMalloc(&ctx->dFrontKeys, maxRays * 4));
     CUDA_TRY(ctx, cudaMalloc(&ctx->dFrontKeysOut, maxRays * 4));
     CUDA_TRY(ctx, cudaMalloc(&ctx->dFrontQueueSorted, maxRays * 4));
