@@ -518,7 +518,7 @@ def main():
                                 "front_hit_fraction": front,
                                 "whole_step": {"bytes_per_primary_ray": b_ray, "achieved": step_gbs, "frac": step_gbs / peak, "what": "SURVEY 8(d) B_ray (node + triangle fetches of the primary and the shadow ray, vertices / material / 16 probe taps per front hit, ray record) x rays / update time"},
                                 "compulsory_hbm_floor_ms": (2208.0 * probes_per_rank + 36e6) / (peak * 1e9) * 1e3,
-                                "operative_bound": dict({"kind": "SM issue slots and warp lane utilisation: the algorithmic bytes above are L1/L2 traffic (the BVH and the atlases live in the 126 MB L2; ncu DRAM throughput 1-6 % of peak), see profiles/"}, **prof.get("_issue", {}).get("k_" + dom, {}))}
+                                "operative_bound": dict({"kind": "SM issue slots and warp lane utilisation: the algorithmic bytes above are L1/L2 traffic (the BVH and the atlases live in the 126 MB L2; ncu DRAM throughput 1-6 % of peak), see profiles/"}, **({"kernels": {k: prof.get("_issue", {}).get(k) for k in (["k_shade_front", "k_shade_miss"] if dom == "shade" else ["k_blend_tc"] if dom == "blend" else ["k_" + dom]) if prof.get("_issue", {}).get(k)}, "rays_per_launch": int(units)}))}
         _emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -12,9 +12,12 @@ KEEP = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
 traffic = {}
+issue = {}
 _tp = os.path.join(ROOT, "profiles", "traffic.json")
 if os.path.exists(_tp):  # kernels captured in earlier sessions keep their entries; this run's captures replace theirs
-    traffic = {k: v for k, v in json.load(open(_tp)).items() if not k.startswith("_")}
+    _old = json.load(open(_tp))
+    traffic = {k: v for k, v in _old.items() if not k.startswith("_")}
+    issue = _old.get("_issue", {})
 for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "prof_%s_k_*.ncu-rep" % tag))):
     kernel = re.search(r"prof_%s_(k_\w+)\.ncu-rep" % tag, rep).group(1)
     traffic_key = kernel[:-len("_alpha")] + "<alpha>" if kernel.endswith("_alpha") else kernel
@@ -33,11 +36,17 @@ for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "prof_%s_k_*.ncu-re
         i = hdr.index(name); v = float(vals[i].replace(",", "")); u = units[i].lower()
         return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
     traffic[traffic_key] = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
+    def plain(name):
+        return float(vals[hdr.index(name)].replace(",", "")) if name in hdr else None
+    issue[traffic_key] = {"issue_slots_busy_pct": plain("smsp__issue_active.avg.pct_of_peak_sustained_active"), "lanes_per_instruction": plain("smsp__thread_inst_executed_per_inst_executed.ratio"),
+                          "warp_instructions": plain("smsp__inst_executed.sum"), "duration_us_under_ncu": plain("gpu__time_duration.sum"), "achieved_occupancy_pct": plain("sm__warps_active.avg.pct_of_peak_sustained_active"),
+                          "dram_throughput_pct_of_peak": plain("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"), "capture": tag}
     print(kernel, vals[hdr.index("gpu__time_duration.sum")], units[hdr.index("gpu__time_duration.sum")], "dram bytes", traffic[traffic_key])
 if "k_shade_front" in traffic and "k_shade_miss" in traffic:
     traffic["k_shade"] = traffic["k_shade_front"] + traffic["k_shade_miss"]
-traffic["_source"] = ("dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full --clock-control none, tools/collect_profiles.sh "
+traffic["_source"] = ("dram__bytes_read.sum + dram__bytes_write.sum per launch (and under _issue: issue-slot utilisation, lanes per warp instruction, warp instructions per launch), ncu --set full --clock-control none, tools/collect_profiles.sh "
                       "(DDGI kernels: cfg2, 16384 probes x 256 rays; screen-space kernels: cfg3 at 3840x2160), summaries in profiles/r01*_ncu_full_*.csv (latest capture: %s)" % tag)
+traffic["_issue"] = issue
 json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
 src = os.path.join(ROOT, "gpurun_out", "launches_%s.csv" % tag)
 if os.path.exists(src):
@@ -45,7 +54,7 @@ if os.path.exists(src):
     open(os.path.join(ROOT, "profiles", "%s_launches_bench.csv" % tag), "w").writelines(lines)
     print("launch list:", len(lines) - 1, "rows")
 # SASS listings of the hot kernels (built objects, no GPU needed)
-objs = {"k_trace_primary": "ddgi.o", "k_trace_shadow": "ddgi.o", "k_blend": "ddgi.o", "k_shade_front": "ddgi_shade.o", "k_shade_miss": "ddgi_shade.o",
+objs = {"k_trace_primary": "ddgi.o", "k_trace_shadow": "ddgi.o", "k_blend": "ddgi.o", "k_blend_tc": "blend_tc.o", "k_classify_hits": "ddgi.o", "k_shade_front": "ddgi_shade.o", "k_shade_miss": "ddgi_shade.o",
         "k_filter_x": "shadow.o", "k_filter_y": "shadow.o", "k_direct_light": "shadow.o", "k_final_gather": "gather.o", "k_reflect_shade": "reflection.o"}
 # template instantiation that ships as the default (name suffix after the kernel name in the mangled symbol)
 inst = {"k_trace_primary": "ILi0E", "k_trace_shadow": "ILi12E", "k_shade_front": "ILb0E", "k_direct_light": "ILb0E", "k_reflect_shade": "ILb0E"}
@@ -54,7 +63,7 @@ for kernel, obj in objs.items():
     blocks = re.split(r"\n\s*Function : ", txt)
     for b in blocks[1:]:
         name = b.split("\n", 1)[0]
-        if re.search(r"\d+%s%s" % (kernel, inst.get(kernel, "(E|I)")), name):
+        if re.search(r"\d+%s%s" % (kernel, inst.get(kernel, r"(E|I|\d)")), name):
             body = [re.sub(r"\s*/\* 0x[0-9a-f]+ \*/\s*$", "", l).rstrip() for l in b.split("\n") if re.match(r"\s+/\*[0-9a-f]{4,}\*/", l)]
             with open(os.path.join(ROOT, "profiles", "%s_sass_%s.txt" % (tag, kernel)), "w") as f:
                 f.write("// cuobjdump -sass %s, function %s (%d instructions)\n" % (obj, name, len(body)) + "\n".join(body) + "\n")
