@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-timeout 90 python tools/profile_step.py 6 | tail -1
-(timeout 600 python -m pytest tests -m gpu -q -x > gpurun_out/r02ab_gputest.log 2>&1; echo "pytest exit $?" >> gpurun_out/r02ab_gputest.log); tail -4 gpurun_out/r02ab_gputest.log
-timeout 120 python tools/diag_parity.py > gpurun_out/r02ab_diag.log 2>&1; grep -E "^frame|texels fp32" gpurun_out/r02ab_diag.log | head -8
+VKX_BLEND_PROFILE=2 timeout 90 python tools/profile_step.py 3 > gpurun_out/r02ac_blend_diag.txt 2>&1; echo "rc=$?"; grep "blend_tc" gpurun_out/r02ac_blend_diag.txt | tail -29 | cut -c1-160 | grep -v "cta  [1-8]"
+for lib in "" _smb5 "" _smb5; do VKX_LIB_PATH=$PWD/vulkanexp_b200/libvkexp_b200$lib.so timeout 90 python tools/profile_step.py 8 | tail -1 | cut -c1-230; done
+(timeout 300 python -m pytest tests/test_ddgi_parity.py tests/test_scheduler_parity.py tests/test_facade.py -m gpu -q -x > gpurun_out/r02ac_gputest.log 2>&1; echo "pytest exit $?" >> gpurun_out/r02ac_gputest.log); tail -4 gpurun_out/r02ac_gputest.log

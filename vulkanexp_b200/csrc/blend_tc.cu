@@ -8,11 +8,12 @@
 //     0..67 and the 36 irradiance texels in rows 68..103). The per-frame table is laid out by k_blend_weight_image as the exact
 //     shared-memory image of the K-major, unswizzled UMMA operand (hi and lo TF32 parts), 16 rays per chunk: the TMA warp brings a
 //     chunk in with one cp.async.bulk (UBLKCP) that completes on the stage's `full` mbarrier.
-//   * B operand = ray data, N = (probe, plane) rows: eight producer warps read the ray records (rgb, depth) once from global memory
-//     (the next chunk's loads are in flight while the current one is converted), clamp and square the depth
-//     (probesUpdate.glsl:74,78-79), split every value into TF32 hi + lo and store both in the same UMMA layout, then arrive on `full`.
+//   * B operand = ray data, N = (plane, probe) rows: eight producer warps read the ray records (rgb, depth) once from global memory
+//     (a thread takes four consecutive rays of one probe; the next two chunks' loads are in flight while one is converted), clamp and
+//     square the depth (probesUpdate.glsl:74,78-79), split every value into TF32 hi + lo and store each plane's K core with one
+//     conflict-free 128-bit store in the same UMMA layout, then arrive on `full`.
 //   * 3xTF32: D += Ahi.Bhi + Ahi.Blo + Alo.Bhi with fp32 accumulation in tensor memory (448 of 512 columns): depth tile 0 -> columns
-//     [0,128), depth tile 1 -> [128,256), tile 1 x colour planes -> [256,448) (only its irradiance rows are read back). One lane of
+//     [0,128) (d of probe p in column p, d^2 in 64 + p), depth tile 1 -> [128,256), tile 1 x colour planes -> [256,448) (only its irradiance rows are read back). One lane of
 //     the MMA warp issues them; tcgen05.commit releases the stage (`empty`) and, after a tile's last chunk, publishes the accumulators
 //     (`accFull`). Producers and TMA run ahead into the next tile while the epilogue drains the accumulators.
 //   * epilogue: eight warps. A warp reads the TMEM lane quarter warp % 4, so the two warps of a quarter split the tile's probes. While
@@ -68,11 +69,6 @@ __device__ __forceinline__ void ummaCommit(uint64_t* bar) { asm volatile("tcgen0
 __device__ __forceinline__ void tmemLoad8(uint32_t addr, uint32_t (&v)[8]) { // this thread's accumulator row (lane of its warp's quarter), 8 consecutive columns
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(addr) : "memory");
-}
-__device__ __forceinline__ void tmemLoad16(uint32_t addr, uint32_t (&v)[16]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]),
-                   "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) : "r"(addr) : "memory");
 }
 __device__ __forceinline__ void mbarArrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smemAddr(bar)) : "memory"); }
 __device__ __forceinline__ void namedBarrier(uint32_t id, uint32_t threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
@@ -243,12 +239,14 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
         }
     } else if (warp >= BTC_EPI_WARPS) {
         // ------------------------------------------------------------------------------------------ producers: ray records -> operand tiles
-        // A thread owns the same (probe, ray-in-core) of every K core: element i of a chunk is probe pt / 4, ray 4 i + pt % 4 (a warp
-        // covers 8 probes x 4 rays per element: conflict-free stores, see tileOffset).
+        // A thread owns one K core (four consecutive rays = 64 contiguous bytes of ray records) of one probe per chunk: probe pt / 4,
+        // core pt % 4. Operand rows are plane-major (depth tile: d of probe p in row p, d^2 in row 64 + p; colour tile: r, g, b in rows
+        // p, 64 + p, 128 + p), so the eight lanes of a quarter-warp (two neighbouring probes x four cores) write 128 contiguous,
+        // swizzled bytes: every 128-bit store is conflict-free, ten stores per thread and chunk instead of forty 32-bit ones.
         const uint32_t pt = tid - BTC_EPI_WARPS * 32u;
-        constexpr uint32_t EPT = BTC_P * BTC_KC / (BTC_PROD_WARPS * 32u); // elements per thread per chunk = K cores per chunk
-        static_assert(EPT == BTC_KC / 4u && BTC_PROD_WARPS * 32u == 4u * BTC_P, "one K core per element");
-        const uint32_t myP = pt >> 2, myKq = pt & 3u;
+        static_assert(BTC_PROD_WARPS * 32u == BTC_P * (BTC_KC / 4u), "one (probe, K core) pair per producer thread");
+        const uint32_t myP = pt >> 2, myCore = pt & 3u;
+        const uint32_t off0 = tileOffset(myP, 4u * myCore), off1 = tileOffset(BTC_P + myP, 4u * myCore), off2 = tileOffset(2u * BTC_P + myP, 4u * myCore);
         uint32_t g = 0, it = 0;
         for (uint32_t lt = blockIdx.x; lt < numTiles; lt += gridDim.x, ++it) {
             const uint32_t tile = (diag & 8u) ? numTiles - 1u - lt : lt; // diagnostics: reversed tile order
@@ -257,15 +255,15 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
             TileMeta& meta = sMeta[it & 1u];
             if (it >= 2u) mbarWait(&barMetaFree[it & 1u], ((it >> 1) - 1u) & 1u); // the epilogue two tiles back is done with this meta block
             const float4* myRays = rays + size_t(slot0 + myP) * N;
-            auto fetch = [&](uint32_t c, float4 (&rd)[EPT]) {
+            auto fetch = [&](uint32_t c, float4 (&rd)[4]) {
 #pragma unroll
-                for (uint32_t i = 0; i < EPT; ++i) {
-                    const uint32_t ray = c * BTC_KC + 4u * i + myKq;
-                    rd[i] = (myP < np && ray < N) ? __ldcs(myRays + ray) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (uint32_t j = 0; j < 4; ++j) {
+                    const uint32_t ray = c * BTC_KC + 4u * myCore + j;
+                    rd[j] = (myP < np && ray < N) ? __ldcs(myRays + ray) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             };
             // the ray records of chunks c + 1 and c + 2 are in flight while chunk c is converted
-            float4 cur[EPT], nxt[EPT], nx2[EPT];
+            float4 cur[4], nxt[4], nx2[4];
             fetch(0, cur);
             if (1u < chunks) fetch(1u, nxt);
             uint32_t outOfRange = 0;
@@ -276,29 +274,32 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
                 const long long tConv = (prof && pt == 0) ? clock64() : 0;
                 unsigned char* bD = smemB + s * BTC_B_STAGE_BYTES;                   // depth planes hi, then lo
                 unsigned char* bC = bD + 2 * BTC_BD_TILE_BYTES;                      // colour planes hi, then lo
+                if (!(diag & 1u)) { // (diagnostics bit 0: no conversion / stores)
+                    float4 dH, dL, d2H, d2L, rH, rL, gH, gL, bH, bL;
+                    float* const dst[10] = {&dH.x, &dL.x, &d2H.x, &d2L.x, &rH.x, &rL.x, &gH.x, &gL.x, &bH.x, &bL.x};
 #pragma unroll
-                for (uint32_t i = 0; i < EPT; ++i) {
-                    if (diag & 1u) { if (cur[i].x == 123.456f) outOfRange++; continue; } // diagnostics: no conversion / stores
-                    const uint32_t k = 4u * i + myKq, ray = c * BTC_KC + k;
-                    float4 rd = cur[i];
-                    if (myP < np && ray < N) {
-                        if (rd.w < 0.0f || rd.w > cellLen) ++outOfRange;                   // probesUpdate.glsl:74
-                        float depth = minS(cellLen, rd.w);                                  // :78-79
-                        if (depth < 0.0f) depth = cellLen;
-                        rd.w = depth;
+                    for (uint32_t j = 0; j < 4; ++j) {
+                        float4 rd = cur[j];
+                        if (myP < np && c * BTC_KC + 4u * myCore + j < N) {
+                            if (rd.w < 0.0f || rd.w > cellLen) ++outOfRange;               // probesUpdate.glsl:74
+                            float depth = minS(cellLen, rd.w);                              // :78-79
+                            if (depth < 0.0f) depth = cellLen;
+                            rd.w = depth;
+                        }
+                        splitTf32(rd.w, dst[0][j], dst[1][j]);
+                        splitTf32(rd.w * rd.w, dst[2][j], dst[3][j]);
+                        splitTf32(rd.x, dst[4][j], dst[5][j]);
+                        splitTf32(rd.y, dst[6][j], dst[7][j]);
+                        splitTf32(rd.z, dst[8][j], dst[9][j]);
                     }
-                    float hi, lo;
-                    const uint32_t od = tileOffset(2u * myP, k), od1 = tileOffset(2u * myP + 1u, k), oc = tileOffset(3u * myP, k);
-                    splitTf32(rd.w, hi, lo);           *reinterpret_cast<float*>(bD + od) = hi;        *reinterpret_cast<float*>(bD + BTC_BD_TILE_BYTES + od) = lo;
-                    splitTf32(rd.w * rd.w, hi, lo);    *reinterpret_cast<float*>(bD + od1) = hi;       *reinterpret_cast<float*>(bD + BTC_BD_TILE_BYTES + od1) = lo;
-                    // colour rows 3p, 3p+1, 3p+2 may cross an 8-row group: address each
-                    splitTf32(rd.x, hi, lo);           *reinterpret_cast<float*>(bC + oc) = hi;        *reinterpret_cast<float*>(bC + BTC_BC_TILE_BYTES + oc) = lo;
-                    const uint32_t oc1 = tileOffset(3u * myP + 1u, k), oc2 = tileOffset(3u * myP + 2u, k);
-                    splitTf32(rd.y, hi, lo);           *reinterpret_cast<float*>(bC + oc1) = hi;       *reinterpret_cast<float*>(bC + BTC_BC_TILE_BYTES + oc1) = lo;
-                    splitTf32(rd.z, hi, lo);           *reinterpret_cast<float*>(bC + oc2) = hi;       *reinterpret_cast<float*>(bC + BTC_BC_TILE_BYTES + oc2) = lo;
+                    *reinterpret_cast<float4*>(bD + off0) = dH;   *reinterpret_cast<float4*>(bD + BTC_BD_TILE_BYTES + off0) = dL;
+                    *reinterpret_cast<float4*>(bD + off1) = d2H;  *reinterpret_cast<float4*>(bD + BTC_BD_TILE_BYTES + off1) = d2L;
+                    *reinterpret_cast<float4*>(bC + off0) = rH;   *reinterpret_cast<float4*>(bC + BTC_BC_TILE_BYTES + off0) = rL;
+                    *reinterpret_cast<float4*>(bC + off1) = gH;   *reinterpret_cast<float4*>(bC + BTC_BC_TILE_BYTES + off1) = gL;
+                    *reinterpret_cast<float4*>(bC + off2) = bH;   *reinterpret_cast<float4*>(bC + BTC_BC_TILE_BYTES + off2) = bL;
                 }
 #pragma unroll
-                for (uint32_t i = 0; i < EPT; ++i) { cur[i] = nxt[i]; nxt[i] = nx2[i]; }
+                for (uint32_t j = 0; j < 4; ++j) { cur[j] = nxt[j]; nxt[j] = nx2[j]; }
                 if (c + 1u == chunks && outOfRange) atomicAdd(&meta.outOfRange[myP], outOfRange); // visible to the epilogue through the arrive below
                 fenceProxyAsync(); // generic-proxy stores -> visible to the tensor core
                 __syncwarp();
@@ -395,16 +396,17 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
                 uint32_t prevA[8], prevB[8];
 #pragma unroll
                 for (uint32_t q = 0; q < 8; ++q) { prevA[q] = smemPrev[((p0 - pBegin + q) * 2u + 0u) * (BTC_EPI_WARPS * 32u) + tid]; prevB[q] = smemPrev[((p0 - pBegin + q) * 2u + 1u) * (BTC_EPI_WARPS * 32u) + tid]; }
-                { // tile 0: depth texel teA of probes p0 .. p0 + 7 (columns 2 p, 2 p + 1)
-                    uint32_t v[16];
+                { // tile 0: depth texel teA of probes p0 .. p0 + 7 (columns p: sum of w d, columns P + p: sum of w d^2)
+                    uint32_t v0[8], v1[8];
                     const long long tT = (prof && tid == 0) ? clock64() : 0;
-                    tmemLoad16(tmem + laneBase + 2u * p0, v);
+                    tmemLoad8(tmem + laneBase + p0, v0);
+                    tmemLoad8(tmem + laneBase + BTC_P + p0, v1);
                     tmemLoadWait();
                     if (prof && tid == 0) pacc[5] += (unsigned long long)(clock64() - tT);
 #pragma unroll
                     for (uint32_t q = 0; q < 8; ++q) {
                         if (q >= npj) break;
-                        float r0 = __uint_as_float(v[2 * q]), r1 = __uint_as_float(v[2 * q + 1]);
+                        float r0 = __uint_as_float(v0[q]), r1 = __uint_as_float(v1[q]);
                         if (normA) { r0 = divShared(r0, rwA, rwInvA); r1 = divShared(r1, rwA, rwInvA); } // probesUpdate.glsl:85-86
                         const float2 prev = unpackRG16F(prevA[q]);
                         const float o0 = mixf(r0, prev.x, hysteresis), o1 = mixf(r1, prev.y, hysteresis); // :103
@@ -413,15 +415,16 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
                         if (depUnpacked) { float* up = depUnpacked + (size_t(slotBase + slot0 + p0 + q) * 196 + teA) * 2; up[0] = o0; up[1] = o1; }
                     }
                 }
-                if (warpHasBDepth) { // tile 1, depth rows (columns 2 P + 2 p ..)
-                    uint32_t v[16];
-                    tmemLoad16(tmem + laneBase + 2u * BTC_P + 2u * p0, v);
+                if (warpHasBDepth) { // tile 1, depth rows (columns 2 P + p and 3 P + p)
+                    uint32_t v0[8], v1[8];
+                    tmemLoad8(tmem + laneBase + 2u * BTC_P + p0, v0);
+                    tmemLoad8(tmem + laneBase + 3u * BTC_P + p0, v1);
                     tmemLoadWait();
                     if (bDepth) {
 #pragma unroll
                         for (uint32_t q = 0; q < 8; ++q) {
                             if (q >= npj) break;
-                            float r0 = __uint_as_float(v[2 * q]), r1 = __uint_as_float(v[2 * q + 1]);
+                            float r0 = __uint_as_float(v0[q]), r1 = __uint_as_float(v1[q]);
                             if (normB) { r0 = divShared(r0, rwB, rwInvB); r1 = divShared(r1, rwB, rwInvB); }
                             const float2 prev = unpackRG16F(prevB[q]);
                             const float o0 = mixf(r0, prev.x, hysteresis), o1 = mixf(r1, prev.y, hysteresis);
@@ -431,22 +434,18 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
                         }
                     }
                 }
-                if (warpHasIrr) { // tile 1, irradiance rows (columns 4 P + 3 p ..)
-                    uint32_t v[24];
-                    uint32_t a[16], b8[8];
-                    tmemLoad16(tmem + laneBase + 4u * BTC_P + 3u * p0, a);
-                    tmemLoad8(tmem + laneBase + 4u * BTC_P + 3u * p0 + 16u, b8);
+                if (warpHasIrr) { // tile 1, irradiance rows (columns 4 P + p: red, 5 P + p: green, 6 P + p: blue)
+                    uint32_t vr[8], vg[8], vb[8];
+                    tmemLoad8(tmem + laneBase + 4u * BTC_P + p0, vr);
+                    tmemLoad8(tmem + laneBase + 5u * BTC_P + p0, vg);
+                    tmemLoad8(tmem + laneBase + 6u * BTC_P + p0, vb);
                     tmemLoadWait();
-#pragma unroll
-                    for (uint32_t q = 0; q < 16; ++q) v[q] = a[q];
-#pragma unroll
-                    for (uint32_t q = 0; q < 8; ++q) v[16 + q] = b8[q];
 #pragma unroll
                     for (uint32_t q = 0; q < 8; ++q) {
                         if (q >= npj) break; // warp-uniform
                         float maxChange = 0.0f;
                         if (bIrr) {
-                            float r0 = __uint_as_float(v[3 * q]), r1 = __uint_as_float(v[3 * q + 1]), r2 = __uint_as_float(v[3 * q + 2]);
+                            float r0 = __uint_as_float(vr[q]), r1 = __uint_as_float(vg[q]), r2 = __uint_as_float(vb[q]);
                             if (normB) { r0 = divShared(r0, rwB, rwInvB); r1 = divShared(r1, rwB, rwInvB); r2 = divShared(r2, rwB, rwInvB); }
                             const float3 prev = unpackR11G11B10(prevB[q]);
                             maxChange = maxS(maxS(fabsf(r0 - prev.x), fabsf(r1 - prev.y)), fabsf(r2 - prev.z));
