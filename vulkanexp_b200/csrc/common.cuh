@@ -97,6 +97,7 @@ struct vkx_ctx {
     uint32_t* dPermList = nullptr;      // multi-chunk updates: probe indices in block order
     uint32_t* dIota = nullptr;          // 0..probeCount-1
     float* dBlendW = nullptr;           // per-frame blend weight table [256][288]
+    bool binAttrSet = false;            // shared-memory opt-in of the counting-sort kernels (per device, like the other attributes)
     float* dBlendImage = nullptr; bool blendTcAttrSet = false; // the same weights as the tensor-core blend's A-operand image (blend_tc.cu)
     std::vector<uint32_t> hLastList;    // the host list currently resident in dIndicesList / dOrder (empty: none), so an unchanged list is not uploaded again
     std::vector<uint32_t> hBlockRank;   // probe linear index -> rank in 2x2x2-block order

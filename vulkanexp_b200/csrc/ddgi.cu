@@ -111,6 +111,113 @@ __global__ void __launch_bounds__(256) k_classify_hits(TraceParams tp, const flo
     }
 }
 
+// ---- front hits grouped by grid cell without a sort library: counting sort with block-private histograms
+// The key of a front hit is its bin = (grid cell of the hit point) >> binShift, at most BIN_MAX bins (64 KB of shared-memory
+// counters). k_bin_count classifies every ray (misses -> sky queue, back faces are final, front hits -> key), counts the keys of
+// BIN_TILE rays at a time in shared memory and adds the block's counts to the global histogram once per block (hit points cluster
+// in few cells: per-ray or per-warp global atomics on the hot cells serialise in L2, the reason an earlier counting sort lost to
+// the radix sort). k_bin_scan turns the histogram into first positions; k_bin_scatter counts each tile again in shared memory (a
+// ray's rank inside its tile's bin is what the shared-memory atomic returns), reserves the tile's range of every non-empty bin with
+// one global atomic, and writes the ray indices. The order inside a bin depends on scheduling; every queue item is shaded
+// independently and results are stored by ray index, so outputs do not.
+#define BIN_TILE 4096u
+#define BIN_MAX 16384u
+__global__ void __launch_bounds__(256) k_bin_count(TraceParams tp, uint32_t numBins, uint32_t binShift, const float4* __restrict__ origins, const float4* __restrict__ dirs,
+                                                   const vkx_hit* __restrict__ hits, uint32_t* __restrict__ missQueue, uint32_t* __restrict__ keys, uint32_t* __restrict__ hist,
+                                                   uint32_t* __restrict__ counters) {
+    extern __shared__ uint32_t sBins[];
+    __shared__ uint32_t sMissBase, sMissCount, sFront;
+    for (uint32_t b = threadIdx.x; b < numBins; b += 256u) sBins[b] = 0u;
+    if (threadIdx.x == 0) sFront = 0u;
+    const uint32_t numTiles = (tp.numRays + BIN_TILE - 1u) / BIN_TILE;
+    uint32_t myFront = 0;
+    for (uint32_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x) { // block-uniform trip count
+        if (threadIdx.x == 0) sMissCount = 0u;
+        __syncthreads();
+        uint32_t missMask = 0, missRank = 0;
+#pragma unroll 4
+        for (uint32_t j = 0; j < BIN_TILE / 256u; ++j) {
+            const uint32_t ri = tile * BIN_TILE + j * 256u + threadIdx.x;
+            uint32_t key = 0xFFFFFFFFu;
+            if (ri < tp.numRays) {
+                const float t = hits[ri].t; const uint32_t prim = hits[ri].primitive;
+                if (prim == 0xFFFFFFFFu) missMask |= 1u << j;
+                else if (!(prim & 0x80000000u)) {
+                    const uint32_t slot = ri / tp.raysPerProbe, ray = ri - slot * tp.raysPerProbe;
+                    const float4 o = __ldg(origins + slot);
+                    const float4 d = __ldg(dirs + ray);
+                    const int cx = min(max(int((o.x + d.x * t - tp.grid.extentMin[0]) * tp.invCell[0]), 0), tp.grid.resolution[0] - 1);
+                    const int cy = min(max(int((o.y + d.y * t - tp.grid.extentMin[1]) * tp.invCell[1]), 0), tp.grid.resolution[1] - 1);
+                    const int cz = min(max(int((o.z + d.z * t - tp.grid.extentMin[2]) * tp.invCell[2]), 0), tp.grid.resolution[2] - 1);
+                    key = uint32_t(cx + tp.grid.resolution[0] * (cy + tp.grid.resolution[1] * cz)) >> binShift;
+                    atomicAdd(&sBins[key], 1u);
+                    ++myFront;
+                }
+                keys[ri] = key;
+            }
+        }
+        // misses of the tile: one reservation per block, positions by (thread, ray) inside the tile
+        const uint32_t nMiss = uint32_t(__popc(missMask));
+        if (nMiss) missRank = atomicAdd(&sMissCount, nMiss);
+        __syncthreads();
+        if (threadIdx.x == 0) sMissBase = sMissCount ? atomicAdd(counters + 3, sMissCount) : 0u;
+        __syncthreads();
+        uint32_t pos = sMissBase + missRank;
+        while (missMask) { const uint32_t j = uint32_t(__ffs(int(missMask))) - 1u; missMask &= missMask - 1u; missQueue[pos++] = tile * BIN_TILE + j * 256u + threadIdx.x; }
+    }
+    if (myFront) atomicAdd(&sFront, myFront);
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < numBins; b += 256u) { const uint32_t c = sBins[b]; if (c) atomicAdd(hist + b, c); }
+    if (threadIdx.x == 0 && sFront) atomicAdd(counters + 4, sFront);
+}
+// exclusive scan of the bin histogram (<= BIN_MAX entries): one block, each thread scans its <= 16 consecutive bins; the loads are
+// unrolled so that all of them are in flight at once (a runtime-bounded loop of global loads took 18 us)
+__global__ void __launch_bounds__(1024) k_bin_scan(uint32_t numBins, const uint32_t* __restrict__ hist, uint32_t* __restrict__ cursor) {
+    __shared__ uint32_t sWarp[32];
+    constexpr uint32_t PER = BIN_MAX / 1024u;
+    const uint32_t first = threadIdx.x * PER;
+    uint32_t v[PER], sum = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < PER; ++k) { v[k] = first + k < numBins ? hist[first + k] : 0u; }
+#pragma unroll
+    for (uint32_t k = 0; k < PER; ++k) sum += v[k];
+    uint32_t incl = sum; // inclusive scan over the block
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (int(threadIdx.x & 31u) >= o) incl += u; }
+    if ((threadIdx.x & 31u) == 31u) sWarp[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32u) {
+        uint32_t w = sWarp[threadIdx.x];
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, w, o); if (int(threadIdx.x) >= o) w += u; }
+        sWarp[threadIdx.x] = w;
+    }
+    __syncthreads();
+    uint32_t run = incl - sum + ((threadIdx.x >> 5) ? sWarp[(threadIdx.x >> 5) - 1u] : 0u);
+#pragma unroll
+    for (uint32_t k = 0; k < PER; ++k) if (first + k < numBins) { cursor[first + k] = run; run += v[k]; }
+}
+__global__ void __launch_bounds__(256) k_bin_scatter(uint32_t numRays, uint32_t numBins, const uint32_t* __restrict__ keys, uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
+    extern __shared__ uint32_t sBins[];
+    const uint32_t numTiles = (numRays + BIN_TILE - 1u) / BIN_TILE;
+    for (uint32_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
+        for (uint32_t b = threadIdx.x; b < numBins; b += 256u) sBins[b] = 0u;
+        __syncthreads();
+        uint32_t key[BIN_TILE / 256u], rank[BIN_TILE / 256u];
+#pragma unroll
+        for (uint32_t j = 0; j < BIN_TILE / 256u; ++j) {
+            const uint32_t ri = tile * BIN_TILE + j * 256u + threadIdx.x;
+            key[j] = ri < numRays ? keys[ri] : 0xFFFFFFFFu;
+            rank[j] = key[j] != 0xFFFFFFFFu ? atomicAdd(&sBins[key[j]], 1u) : 0u;
+        }
+        __syncthreads();
+        for (uint32_t b = threadIdx.x; b < numBins; b += 256u) { const uint32_t c = sBins[b]; if (c) sBins[b] = atomicAdd(cursor + b, c); } // the tile's range of bin b
+        __syncthreads();
+#pragma unroll
+        for (uint32_t j = 0; j < BIN_TILE / 256u; ++j)
+            if (key[j] != 0xFFFFFFFFu) sorted[sBins[key[j]] + rank[j]] = tile * BIN_TILE + j * 256u + threadIdx.x;
+        __syncthreads(); // sBins is cleared by the next tile
+    }
+}
+
 #ifndef PT_DEFER_PRIMARY_DEFAULT
 #define PT_DEFER_PRIMARY_DEFAULT 0 // closest-hit rays lose with deferral: 0.949 ms immediate, 1.038 / 0.995 / 0.978 ms with 8 / 12 / 16
 #endif
@@ -651,23 +758,40 @@ int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* /*unused*/,
 #undef VKX_LAUNCH_PRIMARY
         LAUNCH_CHECK(ctx);
         if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[1], st));
-        // front-hit keys default to all-ones (unused slots sort to the end); then one dense pass fills both queues
-        CUDA_TRY(ctx, cudaMemsetAsync(ctx->dFrontKeys, 0xFF, size_t(numRays) * 4, st));
-        k_classify_hits<<<std::min<unsigned>(divUp(numRays, 256), unsigned(ctx->smCount) * 16u), 256, 0, st>>>(tp, ctx->dOrigins, ctx->dDirs, ctx->dHits, ctx->dMissQueue, ctx->dFrontQueue, ctx->dFrontKeys, ctx->dQueueCount); LAUNCH_CHECK(ctx);
+        // classification: misses -> sky queue, front hits -> key (grid cell of the hit point) for the grouping below
+        static const bool radixSort = [] { const char* e = getenv("VKX_SORT"); return e && !strcmp(e, "radix"); }(); // A/B: the round-1 path (cub::DeviceRadixSort)
+        uint32_t binShift = 0; while (((ctx->probeCount - 1u) >> binShift) + 1u > BIN_MAX) ++binShift;
+        const uint32_t numBins = ((ctx->probeCount - 1u) >> binShift) + 1u;
+        const size_t binBytes = size_t(numBins) * 4;
+        if (radixSort) {
+            CUDA_TRY(ctx, cudaMemsetAsync(ctx->dFrontKeys, 0xFF, size_t(numRays) * 4, st)); // unused slots sort to the end
+            k_classify_hits<<<std::min<unsigned>(divUp(numRays, 256), unsigned(ctx->smCount) * 16u), 256, 0, st>>>(tp, ctx->dOrigins, ctx->dDirs, ctx->dHits, ctx->dMissQueue, ctx->dFrontQueue, ctx->dFrontKeys, ctx->dQueueCount); LAUNCH_CHECK(ctx);
+        } else {
+            if (!ctx->binAttrSet) {
+                CUDA_TRY(ctx, cudaFuncSetAttribute(k_bin_count, cudaFuncAttributeMaxDynamicSharedMemorySize, int(BIN_MAX * 4)));
+                CUDA_TRY(ctx, cudaFuncSetAttribute(k_bin_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, int(BIN_MAX * 4)));
+                ctx->binAttrSet = true;
+            }
+            CUDA_TRY(ctx, cudaMemsetAsync(ctx->dCellHist, 0, binBytes, st));
+            const unsigned binBlocks = std::min<unsigned>(divUp(numRays, BIN_TILE), unsigned(ctx->smCount) * 3u);
+            k_bin_count<<<binBlocks, 256, binBytes, st>>>(tp, numBins, binShift, ctx->dOrigins, ctx->dDirs, ctx->dHits, ctx->dMissQueue, ctx->dFrontKeys, ctx->dCellHist, ctx->dQueueCount); LAUNCH_CHECK(ctx);
+        }
         // The sky kernel only needs the miss queue: it runs on a second stream, concurrently with the sort and the front-hit shading.
         const unsigned shadeBlocks = std::min<unsigned>(divUp(numRays, 128), unsigned(ctx->smCount) * 16u);
         CUDA_TRY(ctx, cudaEventRecord(ctx->auxEvent[0], st));
         CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->auxStream, ctx->auxEvent[0], 0));
         launchShadeMiss(shadeBlocks, ctx->auxStream, sp, ctx->dOrigins, ctx->dDirs, ctx->dMissQueue, ctx->dQueueCount, ctx->dRays); LAUNCH_CHECK(ctx);
         CUDA_TRY(ctx, cudaEventRecord(ctx->auxEvent[1], ctx->auxStream));
-        { // front-hit queue sorted by grid cell (radix sort over just the bits a cell index needs).
-          // A counting sort with a per-cell atomic histogram was slower: hit points cluster in few cells.
+        if (radixSort) { // front-hit queue sorted by grid cell (radix sort over just the bits a cell index needs)
             uint32_t cells = ctx->probeCount, bits = 1; while ((1u << bits) <= cells) ++bits;
             size_t need = 0;
             cub::DeviceRadixSort::SortPairs(nullptr, need, ctx->dFrontKeys, ctx->dFrontKeysOut, ctx->dFrontQueue, ctx->dFrontQueueSorted, int(numRays), 0, int(bits), st);
             if (need > ctx->sortTempBytes) { if (ctx->dSortTemp) cudaFree(ctx->dSortTemp); CUDA_TRY(ctx, cudaMalloc(&ctx->dSortTemp, need)); ctx->sortTempBytes = need; }
             CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->dSortTemp, need, ctx->dFrontKeys, ctx->dFrontKeysOut, ctx->dFrontQueue, ctx->dFrontQueueSorted, int(numRays), 0, int(bits), st));
             ctx->launches += 3;
+        } else { // front-hit queue grouped by bin: first positions, then the scatter (see k_bin_count)
+            k_bin_scan<<<1, 1024, 0, st>>>(numBins, ctx->dCellHist, ctx->dFrontKeysOut); LAUNCH_CHECK(ctx);
+            k_bin_scatter<<<std::min<unsigned>(divUp(numRays, BIN_TILE), unsigned(ctx->smCount) * 3u), 256, binBytes, st>>>(numRays, numBins, ctx->dFrontKeys, ctx->dFrontKeysOut, ctx->dFrontQueueSorted); LAUNCH_CHECK(ctx);
         }
         { int rc = waitGather(ctx); if (rc != VKX_OK) return rc; } // sharded path: the previous frame's atlas all-gather must have landed
         launchShadeFront(shadeBlocks, st, sc, pr, sp, ctx->dOrigins, ctx->dDirs, ctx->dHits, ctx->dFrontQueueSorted, ctx->dQueueCount, ctx->dRays, ctx->dShadowQueue); LAUNCH_CHECK(ctx);
