@@ -222,6 +222,99 @@ def secondary_shadow_pass(device, frames=12):
     return out
 
 
+def cfg5_leg(local, rank, world, torch, dist, light, steps=3, check_rays=16):
+    """BASELINE configs[4] inside the 8-GPU run: the synthetic instanced stress scene (~10 M triangles), 128^3 probes x 256 rays,
+    sharded full-volume updates with the NVLink all-gather inside one timed interval, the gathered atlases of two frames at a reduced
+    ray count compared word for word with a single-GPU run on rank 0, and the 4K sun-shadow pass on the same scene. Collective: every
+    rank calls it; a rank that fails before the first collective makes all ranks return an error record instead of hanging."""
+    from vulkanexp_b200._lib import Context
+    from vulkanexp_b200.pods import make_camera
+
+    dev = torch.device("cuda", local)
+    ok, err, c5, flat5, info = 1, None, None, None, None
+    t0 = time.perf_counter()
+    try:
+        flat5 = scene_format.flatten(synth.make_cfg5())
+        c5 = Context(local); c5.scene_upload(flat5); c5.bvh_build(); info = c5.bvh_info()
+    except Exception as e:
+        ok, err = 0, repr(e)
+    flag = torch.tensor([ok], device="cuda", dtype=torch.int32)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:
+        return {"error": err or "another rank failed to set the scene up"}
+    uid = [Context.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    c5.comm_init(rank, world, uid[0])
+    res = (128, 128, 128)
+    Rs = orientations(steps + 8)
+
+    def init_volume(ctx, rays):
+        g = GridInfo.make(flat5["bounds_min"], flat5["bounds_max"], res, rays, hysteresis=0.0)
+        ctx.probes_init(g); ctx.probes_upload(state=np.ones(g.probe_count, dtype=np.uint32))
+        return g
+
+    def sync_all():
+        dist.barrier(); torch.cuda.synchronize()
+
+    # sharded + gathered == single GPU at the full 128^3 volume (reduced ray count keeps the single-GPU side short)
+    equal = None
+    g16 = init_volume(c5, check_rays)
+    for f, h in enumerate((0.0, 0.6)):
+        g16.hysteresis = h; c5.probes_update_sharded(g16, light, Rs[f], sync=False)
+    got = c5.probes_download()
+    if rank == 0:
+        ref = Context(local); ref.scene_upload(flat5); ref.bvh_build()
+        r16 = init_volume(ref, check_rays)
+        for f, h in enumerate((0.0, 0.6)):
+            r16.hysteresis = h; ref.probes_update(r16, light, Rs[f], None, sync=False)
+        want = ref.probes_download()
+        equal = bool(all(np.array_equal(a, b) for a, b in zip(got[:3], want[:3])))
+        ref.close(); del ref, want
+    del got
+    sync_all()
+    # the named workload
+    grid5 = init_volume(c5, RAYS)
+    stream = torch.cuda.ExternalStream(c5.stream(), device=dev)
+    h = 0.0
+    for w in range(2):
+        grid5.hysteresis = h; c5.probes_update_sharded(grid5, light, Rs[w], sync=False); h = min(0.98, h + 0.4)
+    c5.sync(); sync_all()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for s in range(steps):
+        grid5.hysteresis = h; c5.probes_update_sharded(grid5, light, Rs[2 + s], sync=False)
+    c5.stream_wait_exchange()
+    b.record(stream)
+    c5.sync(); sync_all()
+    t = torch.tensor([a.elapsed_time(b) / steps], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    (ih, iw), (dh, dw) = grid5.atlas_shapes()
+    out = None
+    if rank == 0:
+        rays_total = grid5.probe_count * RAYS
+        out = {"workload": "BASELINE configs[4]: synthetic instanced stress scene, 128x128x128 probes x 256 rays, probe z-slabs x%d" % world, "triangles": int(info.numTriangles), "instances": int(len(flat5["instances"])),
+               "bvh_nodes": int(info.numNodes), "bvh_build_ms": round(float(info.buildMs), 2), "update_ms": ms, "value": rays_total / (ms * 1e-3), "unit": "probe rays/s", "steps": steps,
+               "timing": "one CUDA-event interval over the steps, closed after the last all-gather; max over ranks", "allgather_bytes_per_update": int((ih * iw + dh * dw + grid5.probe_count) * 4),
+               "sharded_equals_single": equal, "check_rays_per_probe": check_rays}
+        try:  # 4K shadows on the same scene (rank 0: the pass is specified for one GPU)
+            W, H = 3840, 2160
+            c5.shadow_set_noise(synth.reference_blue_noise(64)); c5.shadow_init(W, H)
+            lo, hi = np.array(flat5["bounds_min"]), np.array(flat5["bounds_max"])
+            c, ext = (lo + hi) / 2, hi - lo
+            cams = [make_camera((c[0] - 0.3 * ext[0] + 0.01 * ext[0] * f, hi[1] * 0.6 + 10.0, c[2] - 0.3 * ext[2] + 0.008 * ext[2] * f), (c[0] + 0.02 * ext[0] * f, lo[1], c[2]), aspect=W / H, frame_index=f) for f in range(10)]
+            prev, sms = cams[0], []
+            for cam in cams:
+                c5.gbuffer_generate(cam); c5.shadow_frame(cam, prev, light); sms.append(c5.shadow_timings()); prev = cam
+            out["shadow_pass_4k_ms"] = float(np.mean([m["full"] for m in sms[4:]]))
+        except Exception as e:
+            out["shadow_pass_4k_ms"] = repr(e)
+        out["wall_s"] = round(time.perf_counter() - t0, 1)
+    sync_all()
+    c5.close()
+    return out
+
+
 def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -437,6 +530,9 @@ def main():
         single = {"ms_per_step": sms, "value": rays_per_step_total / (sms * 1e-3), "steps": ks, "efficiency_vs_this": (rays_per_step_total / (ms_per_step * 1e-3)) / (n * rays_per_step_total / (sms * 1e-3))}
     if world > 1:
         barrier()
+    cfg5 = None
+    if world == 8 and scaling == "strong" and not args.no_secondary and os.environ.get("VKX_BENCH_CFG5", "1") != "0":
+        cfg5 = cfg5_leg(local, rank, world, torch, dist, light)
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -458,6 +554,8 @@ def main():
             line["sharded_equals_single"] = sharded_equals_single
             if single:
                 line["single_gpu_same_workload"] = single
+            if cfg5 is not None:
+                line["secondary"] = {"cfg5": cfg5}
         if world == 1 and not args.no_secondary:
             try:
                 line["secondary"] = secondary_shadow_pass(local)
