@@ -375,6 +375,11 @@ inline uint32_t intersectNode(const Node80& n, const RayCtx& r, float tmin, floa
 }
 
 // Moeller-Trumbore, fixed op order. Returns true if the triangle plane/edges are hit; t,u,v,det out.
+// Spec v2.1: the barycentric acceptance tests compare the NUMERATORS (sign of det folded in by an exact sign flip) with |det|
+// (0 <= un <= |det|, 0 <= vn, un + vn <= |det|), so rejected candidates - most of them - never pay the division; accepted ones get
+// u, v, t = numerator * (1 / det) as before. (v2 tested the rounded quotients u <= 1, u + v <= 1: the two differ only where a
+// quotient rounds across 1.)
+inline float flipBy(float x, float s) { return u2f(f2u(x) ^ (f2u(s) & 0x80000000u)); } // x if s >= +0, -x if s carries the sign bit
 inline bool intersectTri(const Tri48& tr, const RayCtx& r, float& t, float& u, float& v, float& det) {
     const float* d = r.d; const float* e1 = tr.e1; const float* e2 = tr.e2;
     float px = std::fmaf(d[1], e2[2], -(d[2] * e2[1]));
@@ -382,15 +387,20 @@ inline bool intersectTri(const Tri48& tr, const RayCtx& r, float& t, float& u, f
     float pz = std::fmaf(d[0], e2[1], -(d[1] * e2[0]));
     det = std::fmaf(e1[0], px, std::fmaf(e1[1], py, e1[2] * pz));
     if (det == 0.0f) return false;
-    float inv = 1.0f / det;
+    const float ad = std::fabs(det);
     float tx = r.o[0] - tr.v0[0], ty = r.o[1] - tr.v0[1], tz = r.o[2] - tr.v0[2];
-    u = std::fmaf(tx, px, std::fmaf(ty, py, tz * pz)) * inv;
-    if (!(u >= 0.0f && u <= 1.0f)) return false;
+    const float un = std::fmaf(tx, px, std::fmaf(ty, py, tz * pz));
+    const float uns = flipBy(un, det);
+    if (!(uns >= 0.0f && uns <= ad)) return false;
     float qx = std::fmaf(ty, e1[2], -(tz * e1[1]));
     float qy = std::fmaf(tz, e1[0], -(tx * e1[2]));
     float qz = std::fmaf(tx, e1[1], -(ty * e1[0]));
-    v = std::fmaf(d[0], qx, std::fmaf(d[1], qy, d[2] * qz)) * inv;
-    if (!(v >= 0.0f && u + v <= 1.0f)) return false;
+    const float vn = std::fmaf(d[0], qx, std::fmaf(d[1], qy, d[2] * qz));
+    const float vns = flipBy(vn, det);
+    if (!(vns >= 0.0f && uns + vns <= ad)) return false;
+    const float inv = 1.0f / det;
+    u = un * inv;
+    v = vn * inv;
     t = std::fmaf(e2[0], qx, std::fmaf(e2[1], qy, e2[2] * qz)) * inv;
     return true;
 }

@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE — part of the CPU oracle. Never linked into, imported or called by the product path.
 //
-// Sequential CPU restatement of "BVH spec v2" (v2 = v1 with the per-slot meta bytes replaced by one validity word): the deterministic binned-SAH binary build,
+// Sequential CPU restatement of "BVH spec v2" (v2 = v1 with the per-slot meta bytes replaced by one validity word; v2.1: division-free barycentric acceptance tests): the deterministic binned-SAH binary build,
 // the greedy collapse into 8-wide nodes, the 8-bit child-box quantisation, and the per-ray traversal order.
 // The reference delegates all of this to the Vulkan driver / RT cores (reference src/Renderer.cpp:272-449,
 // 525-642), so nothing here follows reference code: this file *defines* the behaviour the

@@ -104,7 +104,9 @@ __device__ __forceinline__ uint32_t intersectNode(const uint4 w0, const uint4 w1
     return acc & w1.z;
 }
 
-// Moeller-Trumbore with the fixed operation order of oracle/bvh.cpp::intersectTri.
+// Moeller-Trumbore with the fixed operation order of oracle/bvh.cpp::intersectTri (spec v2.1: the barycentric tests compare the
+// sign-adjusted numerators with |det|, the division is paid only by candidates that pass them).
+__device__ __forceinline__ float flipBy(float x, float s) { return __uint_as_float(__float_as_uint(x) ^ (__float_as_uint(s) & 0x80000000u)); }
 __device__ __forceinline__ bool intersectTri(const float4 q0, const float4 q1, const float4 q2, const Ray& r, float& t, float& u, float& v, float& det) {
     const float v0x = q0.x, v0y = q0.y, v0z = q0.z;
     const float e1x = q0.w, e1y = q1.x, e1z = q1.y;
@@ -114,15 +116,20 @@ __device__ __forceinline__ bool intersectTri(const float4 q0, const float4 q1, c
     const float pz = __fmaf_rn(r.dx, e2y, -__fmul_rn(r.dy, e2x));
     det = __fmaf_rn(e1x, px, __fmaf_rn(e1y, py, __fmul_rn(e1z, pz)));
     if (det == 0.0f) return false;
-    const float inv = __fdiv_rn(1.0f, det);
+    const float ad = fabsf(det);
     const float tx = __fsub_rn(r.ox, v0x), ty = __fsub_rn(r.oy, v0y), tz = __fsub_rn(r.oz, v0z);
-    u = __fmul_rn(__fmaf_rn(tx, px, __fmaf_rn(ty, py, __fmul_rn(tz, pz))), inv);
-    if (!(u >= 0.0f && u <= 1.0f)) return false;
+    const float un = __fmaf_rn(tx, px, __fmaf_rn(ty, py, __fmul_rn(tz, pz)));
+    const float uns = flipBy(un, det);
+    if (!(uns >= 0.0f && uns <= ad)) return false;
     const float qx = __fmaf_rn(ty, e1z, -__fmul_rn(tz, e1y));
     const float qy = __fmaf_rn(tz, e1x, -__fmul_rn(tx, e1z));
     const float qz = __fmaf_rn(tx, e1y, -__fmul_rn(ty, e1x));
-    v = __fmul_rn(__fmaf_rn(r.dx, qx, __fmaf_rn(r.dy, qy, __fmul_rn(r.dz, qz))), inv);
-    if (!(v >= 0.0f && __fadd_rn(u, v) <= 1.0f)) return false;
+    const float vn = __fmaf_rn(r.dx, qx, __fmaf_rn(r.dy, qy, __fmul_rn(r.dz, qz)));
+    const float vns = flipBy(vn, det);
+    if (!(vns >= 0.0f && __fadd_rn(uns, vns) <= ad)) return false;
+    const float inv = __fdiv_rn(1.0f, det);
+    u = __fmul_rn(un, inv);
+    v = __fmul_rn(vn, inv);
     t = __fmul_rn(__fmaf_rn(e2x, qx, __fmaf_rn(e2y, qy, __fmul_rn(e2z, qz))), inv);
     return true;
 }
