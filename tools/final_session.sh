@@ -11,7 +11,7 @@ timeout 400 python bench.py > $out/${TAG}_bench.json 2> $out/${TAG}_bench.err; l
 timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > $out/${TAG}_bench_reference.json 2> $out/${TAG}_bench_reference.err; log "bench reference rc=$? $(cut -c1-200 $out/${TAG}_bench_reference.json)"
 timeout 200 python tools/bench_shadow.py > $out/${TAG}_shadow_plain.json 2> $out/${TAG}_shadow_plain.err; log "shadow plain rc=$? $(cut -c1-300 $out/${TAG}_shadow_plain.json)"
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/launches_${TAG}.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-secondary --e2e-steps 2 > $out/${TAG}_bench_under_ncu.log 2>&1; log "ncu launch list rc=$?"
-for k in k_trace_primary k_shade_front k_shade_miss k_trace_shadow k_blend_tc k_classify_hits; do
+for k in k_trace_primary k_shade_front k_shade_miss k_trace_shadow k_blend_tc k_bin_count k_bin_scatter; do
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -f -o $out/prof_${TAG}_$k python tools/profile_step.py 4 > $out/prof_${TAG}_$k.log 2>&1; log "ncu full $k rc=$?"
 done
 log done

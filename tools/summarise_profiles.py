@@ -54,7 +54,7 @@ if os.path.exists(src):
     open(os.path.join(ROOT, "profiles", "%s_launches_bench.csv" % tag), "w").writelines(lines)
     print("launch list:", len(lines) - 1, "rows")
 # SASS listings of the hot kernels (built objects, no GPU needed)
-objs = {"k_trace_primary": "ddgi.o", "k_trace_shadow": "ddgi.o", "k_blend": "ddgi.o", "k_blend_tc": "blend_tc.o", "k_classify_hits": "ddgi.o", "k_shade_front": "ddgi_shade.o", "k_shade_miss": "ddgi_shade.o",
+objs = {"k_trace_primary": "ddgi.o", "k_trace_shadow": "ddgi.o", "k_blend": "ddgi.o", "k_blend_tc": "blend_tc.o", "k_bin_count": "ddgi.o", "k_bin_scatter": "ddgi.o", "k_shade_front": "ddgi_shade.o", "k_shade_miss": "ddgi_shade.o",
         "k_filter_x": "shadow.o", "k_filter_y": "shadow.o", "k_direct_light": "shadow.o", "k_final_gather": "gather.o", "k_reflect_shade": "reflection.o"}
 # template instantiation that ships as the default (name suffix after the kernel name in the mangled symbol)
 inst = {"k_trace_primary": "ILi0E", "k_trace_shadow": "ILi12E", "k_shade_front": "ILb0E", "k_direct_light": "ILb0E", "k_reflect_shade": "ILb0E"}
