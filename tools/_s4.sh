@@ -1,5 +1,4 @@
 mkdir -p gpurun_out
 for i in 1 2; do timeout 90 python tools/profile_step.py 8 | tail -1 | cut -c1-230; done
-(timeout 600 python -m pytest tests -m gpu -q -x > gpurun_out/r02ai_gputest.log 2>&1; echo "pytest exit $?" >> gpurun_out/r02ai_gputest.log); tail -4 gpurun_out/r02ai_gputest.log
-timeout 300 python bench.py --no-cpu-baseline --steps 20 --e2e-steps 20 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read().strip().split('\n')[-1]); print(d['ms_per_step'], d['kernel_ms'], 'cfg4 1gpu', d['secondary']['cfg4_single_gpu']['ms_per_step'], 'shadow4k', d['secondary']['shadow_pass_ms'])"
+(timeout 600 python -m pytest tests/test_ddgi_parity.py tests/test_gather_parity.py tests/test_reflection_parity.py -m gpu -q -x > gpurun_out/r02aj_gputest.log 2>&1; echo "pytest exit $?" >> gpurun_out/r02aj_gputest.log); tail -3 gpurun_out/r02aj_gputest.log
+timeout 120 python tools/diag_parity.py 2>&1 | grep -E "^frame|texels fp32" | head -6

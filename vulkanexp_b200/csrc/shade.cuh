@@ -420,7 +420,9 @@ __device__ inline v3 skyColor(v3 rayOrigin, v3 rayDirection, v3 sunPosition, v3 
             const float cameraAngle = fmaf(rayDirection.x, samplePoint.x, fmaf(rayDirection.y, samplePoint.y, rayDirection.z * samplePoint.z)) * ih;
             const float scatter = fmaf(dpt, skyScaleFast(lightAngle) - skyScaleFast(cameraAngle), startOffset);
             const v3 attenuate = mk3(fastExp(-scatter * kk.x), fastExp(-scatter * kk.y), fastExp(-scatter * kk.z));
-            if (isinf(attenuate.x) || isinf(attenuate.y) || isinf(attenuate.z) || isnan(attenuate.x) || isnan(attenuate.y) || isnan(attenuate.z)) continue;
+            // sky.glsl:103 `if(any(isinf(attenuate)) || any(isnan(attenuate))) continue;` - the components are exponentials (>= 0 or NaN), so
+            // their sum is finite exactly when all three are: one addition chain and one comparison instead of six classifications
+            if (!((attenuate.x + attenuate.y) + attenuate.z < __uint_as_float(0x7F800000u))) continue;
             const float s = dpt * scaledLength;
             color = mk3(fmaf(attenuate.x, s, color.x), fmaf(attenuate.y, s, color.y), fmaf(attenuate.z, s, color.z));
             samplePoint = samplePoint + sampleRay;
