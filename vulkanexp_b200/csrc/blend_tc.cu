@@ -155,7 +155,7 @@ struct TileMeta { uint32_t linear[BTC_P]; uint32_t originD[BTC_P]; uint32_t orig
 
 __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, DeviceProbes pr, const uint32_t* __restrict__ probeIndices, const float4* __restrict__ rays,
                                                              const float* __restrict__ W, const float* __restrict__ image, float* __restrict__ irrUnpacked,
-                                                             float* __restrict__ depUnpacked, uint32_t slotBase, unsigned long long* __restrict__ prof, uint32_t diag) {
+                                                             float* __restrict__ depUnpacked, uint32_t slotBase, unsigned long long* __restrict__ prof) {
     extern __shared__ __align__(1024) unsigned char smem[];
     // weight ring: ASTAGES x [A chunk image (hi t0, hi t1, lo t0, lo t1)]; ray-data ring: BSTAGES x [B depth hi][B depth lo][B colour hi][B colour lo]
     unsigned char* const smemB = smem + BTC_ASTAGES * BTC_A_CHUNK_BYTES;
@@ -191,7 +191,6 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
                 for (uint32_t c = 0; c < chunks; ++c, ++g) {
                     const uint32_t s = g % BTC_ASTAGES, use = g / BTC_ASTAGES;
                     if (use) BTC_TIMED(0, mbarWait(&barEmptyA[s], (use - 1u) & 1u));
-                    if (diag & 2u) { mbarArrive(&barFullA[s]); continue; } // diagnostics: no weight copies
                     mbarExpectTx(&barFullA[s], BTC_A_CHUNK_BYTES);
                     bulkCopyG2S(smem + s * BTC_A_CHUNK_BYTES, reinterpret_cast<const char*>(image) + size_t(c) * BTC_A_CHUNK_BYTES, BTC_A_CHUNK_BYTES, &barFullA[s]);
                 }
@@ -249,7 +248,7 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
         const uint32_t off0 = tileOffset(myP, 4u * myCore), off1 = tileOffset(BTC_P + myP, 4u * myCore), off2 = tileOffset(2u * BTC_P + myP, 4u * myCore);
         uint32_t g = 0, it = 0;
         for (uint32_t lt = blockIdx.x; lt < numTiles; lt += gridDim.x, ++it) {
-            const uint32_t tile = (diag & 8u) ? numTiles - 1u - lt : lt; // diagnostics: reversed tile order
+            const uint32_t tile = lt;
             const uint32_t slot0 = tile * BTC_P;
             const uint32_t np = min(uint32_t(BTC_P), bp.count - slot0);
             TileMeta& meta = sMeta[it & 1u];
@@ -274,7 +273,7 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
                 const long long tConv = (prof && pt == 0) ? clock64() : 0;
                 unsigned char* bD = smemB + s * BTC_B_STAGE_BYTES;                   // depth planes hi, then lo
                 unsigned char* bC = bD + 2 * BTC_BD_TILE_BYTES;                      // colour planes hi, then lo
-                if (!(diag & 1u)) { // (diagnostics bit 0: no conversion / stores)
+                {
                     float4 dH, dL, d2H, d2L, rH, rL, gH, gL, bH, bL;
                     float* const dst[10] = {&dH.x, &dL.x, &d2H.x, &d2L.x, &rH.x, &rL.x, &gH.x, &gL.x, &bH.x, &bL.x};
 #pragma unroll
@@ -352,7 +351,7 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
         }
         uint32_t it = 0;
         for (uint32_t lt = blockIdx.x; lt < numTiles; lt += gridDim.x, ++it) {
-            const uint32_t tile = (diag & 8u) ? numTiles - 1u - lt : lt; // diagnostics: reversed tile order
+            const uint32_t tile = lt;
             const uint32_t slot0 = tile * BTC_P;
             const uint32_t np = min(uint32_t(BTC_P), bp.count - slot0);
             const uint32_t pEnd = min(np, pBegin + BTC_P / 2u);
@@ -391,7 +390,7 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
             __syncwarp(); // reconverge before the warp-aligned tcgen05.ld below
             tcFenceAfter();
             const long long tEpi = (prof && tid == 0) ? clock64() : 0;
-            for (uint32_t p0 = pBegin; p0 < ((diag & 4u) ? 0u : pEnd); p0 += 8u) { // eight probes per pass (diag bit 2: skipped)
+            for (uint32_t p0 = pBegin; p0 < pEnd; p0 += 8u) { // eight probes per pass
                 const uint32_t npj = min(8u, pEnd - p0);
                 uint32_t prevA[8], prevB[8];
 #pragma unroll
@@ -480,7 +479,7 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) k_blend_tc(BlendParams bp, Dev
                 }
                 pr.stateWork[linearIndex] = stt;
             }
-            if (woProbe < 3u && !(diag & 16u)) {
+            if (woProbe < 3u) {
                 for (uint32_t p = woProbe; p < np; p += 3u) {
                     // probe p's block: local probe p % 32 of half p / 32 -> threads 128 (p / 32) .. + 127 of both planes
                     const uint32_t* blk = smemPrev + (p & 31u) * 2u * (BTC_EPI_WARPS * 32u) + (p >> 5) * 128u;
@@ -516,10 +515,9 @@ int blendTcLaunch(vkx_ctx* ctx, const BlendParams& bp, const DeviceProbes& pr, c
     const unsigned grid = std::min<unsigned>(divUp(n, BTC_P), unsigned(ctx->smCount));
     static const bool profile = getenv("VKX_BLEND_PROFILE") != nullptr;
     unsigned long long* prof = nullptr;
-    static const uint32_t diag = [] { const char* e = getenv("VKX_BLEND_DIAG"); return e ? uint32_t(atoi(e)) : 0u; }(); // diagnostics only: results are wrong with any bit set
     if (profile) { CUDA_TRY(ctx, cudaMallocManaged(&prof, size_t(grid) * 16 * sizeof(unsigned long long))); memset(prof, 0, size_t(grid) * 16 * sizeof(unsigned long long)); }
     k_blend_tc<<<grid, BTC_THREADS, BTC_SMEM_BYTES, st>>>(bp, pr, idx, ctx->dRays, ctx->dBlendW, ctx->dBlendImage, ctx->debugBuffers ? ctx->dIrrUnpacked : nullptr,
-                                                                      ctx->debugBuffers ? ctx->dDepUnpacked : nullptr, slotBase, prof, diag); LAUNCH_CHECK(ctx);
+                                                                      ctx->debugBuffers ? ctx->dDepUnpacked : nullptr, slotBase, prof); LAUNCH_CHECK(ctx);
     if (prof) { // diagnostics: mean / max cycles per CTA of every instrumented wait (slots: see BTC_TIMED uses)
         cudaStreamSynchronize(st);
         static const char* names[16] = {"tma: wait emptyA", "mma: wait accEmpty", "mma: wait fullA", "mma: wait fullB", "mma: total", "epi: tmem ld tile0 blk", "prod: wait emptyB", "prod: convert+arrive", "epi: wait accFull", "epi: drain+mix", "epi: named barrier", "mma: issue 18 MMAs", "mma: commits", "epi: drain of tile 0", "epi: drain of tile 1", "mma: first tile issued"};
