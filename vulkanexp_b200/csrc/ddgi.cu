@@ -364,12 +364,19 @@ __global__ void __launch_bounds__(BLEND_COLS) k_blend_weights(float depthSharpne
 __global__ void __launch_bounds__(BLEND_COLS) k_blend_weight_sums(uint32_t N, float* __restrict__ W) {
     float rw = 0.0f;
     uint32_t i = 0;
-    for (; i + 16u <= N; i += 16u) { // sixteen loads in flight, then the additions in ray order (one block: the loop is latency-bound)
-        float w[16];
+    for (; i + 64u <= N; i += 64u) { // 64 loads in flight, then the additions in ray order (one block: the loop is latency-bound, 13 us with 16)
+        float w[64];
 #pragma unroll
-        for (uint32_t k = 0; k < 16u; ++k) w[k] = W[size_t(i + k) * BLEND_COLS + threadIdx.x];
+        for (uint32_t k = 0; k < 64u; ++k) w[k] = W[size_t(i + k) * BLEND_COLS + threadIdx.x];
 #pragma unroll
-        for (uint32_t k = 0; k < 16u; ++k) rw = rw + w[k];
+        for (uint32_t k = 0; k < 64u; ++k) rw = rw + w[k];
+    }
+    for (; i + 8u <= N; i += 8u) {
+        float w[8];
+#pragma unroll
+        for (uint32_t k = 0; k < 8u; ++k) w[k] = W[size_t(i + k) * BLEND_COLS + threadIdx.x];
+#pragma unroll
+        for (uint32_t k = 0; k < 8u; ++k) rw = rw + w[k];
     }
     for (; i < N; ++i) rw = rw + W[size_t(i) * BLEND_COLS + threadIdx.x];
     W[size_t(BLEND_WSUM_ROW) * BLEND_COLS + threadIdx.x] = rw;
