@@ -1,5 +1,5 @@
 import sys, time, os
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from vulkanexp_b200 import scene_format, synth
 from vulkanexp_b200._lib import Context
@@ -8,7 +8,7 @@ from vulkanexp_b200.pods import GridInfo, Light
 flat = scene_format.flatten(synth.make_cfg2())
 grid = GridInfo.make(flat["bounds_min"], flat["bounds_max"], (32,16,32), 256, hysteresis=0.9)
 ctx = Context(0); ctx.scene_upload(flat); ctx.bvh_build(); ctx.probes_init(grid); ctx.probes_upload(state=np.ones(grid.probe_count, dtype=np.uint32))
-gen = OrientationGenerator(); Rs=[gen.next() for _ in range(100)]
+gen = OrientationGenerator(); Rs=[gen.next() for _ in range(256)]
 light = Light.default()
 (ih,iw),(dh,dw)=grid.atlas_shapes()
 outs=[]
@@ -16,7 +16,7 @@ for _ in range(2):
     pin=(torch.empty((ih,iw),dtype=torch.int32).pin_memory(), torch.empty((dh,dw),dtype=torch.int32).pin_memory(), torch.empty(grid.probe_count,dtype=torch.int32).pin_memory())
     outs.append((pin, tuple(t.numpy().view(np.uint32) for t in pin)))
 idx=np.arange(grid.probe_count,dtype=np.uint32)
-def run(mode, K=30):
+def run(mode, K=200):
     for i in range(5): ctx.probes_update(grid, light, Rs[i], None, sync=False)
     ctx.sync(); t0=time.perf_counter(); th=0
     for s in range(K):
