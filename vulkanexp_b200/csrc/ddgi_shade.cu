@@ -3,6 +3,7 @@
 // pbrMetallicRoughness.glsl). Separate translation unit so that its floating-point flags can differ from the traversal and
 // blend kernels; everything that feeds a later traversal (probe origin, hit position) uses explicit _rn intrinsics.
 #include <cstdlib>
+#include <cstring>
 #include "common.cuh"
 #include "shade.cuh"
 #include "ddgi_common.cuh"
@@ -32,11 +33,10 @@ __global__ void __launch_bounds__(128) k_shade_miss(ShadeParams sp, const float4
 #define SHADE_MIN_BLOCKS 6 // resident 128-thread CTAs per SM k_shade_front is compiled for (80 registers)
 #endif
 template <bool TEXTURED>
-__global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade_front(DeviceScene sc, DeviceProbes pr, ShadeParams sp, const float4* __restrict__ origins,
+__global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade_front(DeviceScene sc, DeviceProbes pr, ShadeParams sp, const GridConsts gc, const float4* __restrict__ origins,
                                                      const float4* __restrict__ dirs, const vkx_hit* __restrict__ hits, const uint32_t* __restrict__ frontQueue,
                                                      uint32_t* __restrict__ counters, float4* __restrict__ rays, float4* __restrict__ queue) {
     const uint32_t n = counters[4];
-    const GridConsts gc = makeGridConsts(sp.grid);
     const v3 lightDir = mk3(sp.light.direction[0], sp.light.direction[1], sp.light.direction[2]);
     const v3 lightColor = mk3(sp.light.color[0], sp.light.color[1], sp.light.color[2]);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -85,6 +85,7 @@ void launchShadeFront(unsigned blocks, cudaStream_t st, const DeviceScene& sc, c
         const unsigned long long cap = (unsigned long long)(smCount) * (unsigned long long)(capPerSm);
         if ((unsigned long long)(blocks) > cap) blocks = unsigned(cap);
     }
-    if (sc.numTextures) k_shade_front<true><<<blocks, 128, 0, st>>>(sc, pr, sp, origins, dirs, hits, frontQueue, counters, rays, shadowQueue);
-    else k_shade_front<false><<<blocks, 128, 0, st>>>(sc, pr, sp, origins, dirs, hits, frontQueue, counters, rays, shadowQueue);
+    const GridConsts gc = makeGridConstsHost(sp.grid);
+    if (sc.numTextures) k_shade_front<true><<<blocks, 128, 0, st>>>(sc, pr, sp, gc, origins, dirs, hits, frontQueue, counters, rays, shadowQueue);
+    else k_shade_front<false><<<blocks, 128, 0, st>>>(sc, pr, sp, gc, origins, dirs, hits, frontQueue, counters, rays, shadowQueue);
 }
