@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(128) k_shade_miss(ShadeParams sp, const float4
 // closesthit.glsl:143-288 (NO_REFLECTION) over the dense front-hit queue; appends the shadow rays. TEXTURED: the scene has a texture
 // list (the host picks the variant, so untextured scenes run the kernel without any texture code).
 #ifndef SHADE_MIN_BLOCKS
-#define SHADE_MIN_BLOCKS 6 // resident 128-thread CTAs per SM k_shade_front is compiled for (80 registers)
+#define SHADE_MIN_BLOCKS 7 // resident 128-thread CTAs per SM k_shade_front is compiled for (72 registers; measured on B200, cfg2, shade phase: 6 CTAs 0.834 ms, 7: 0.804, 8: 0.808)
 #endif
 template <bool TEXTURED>
 __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade_front(DeviceScene sc, DeviceProbes pr, ShadeParams sp, const GridConsts gc, const float4* __restrict__ origins,
