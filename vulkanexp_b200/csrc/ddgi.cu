@@ -177,8 +177,12 @@ __global__ void __launch_bounds__(1024) k_bin_scan(uint32_t numBins, const uint3
     constexpr uint32_t PER = BIN_MAX / 1024u;
     const uint32_t first = threadIdx.x * PER;
     uint32_t v[PER], sum = 0;
+    // 128-bit loads: a thread's 16 bins are 64 contiguous bytes; word loads made one SM serve 16 k sector requests (15 us)
 #pragma unroll
-    for (uint32_t k = 0; k < PER; ++k) { v[k] = first + k < numBins ? hist[first + k] : 0u; }
+    for (uint32_t k = 0; k < PER; k += 4u) {
+        if (first + k + 3u < numBins) { const uint4 q = *reinterpret_cast<const uint4*>(hist + first + k); v[k] = q.x; v[k + 1] = q.y; v[k + 2] = q.z; v[k + 3] = q.w; }
+        else { for (uint32_t j = 0; j < 4u; ++j) v[k + j] = first + k + j < numBins ? hist[first + k + j] : 0u; }
+    }
 #pragma unroll
     for (uint32_t k = 0; k < PER; ++k) sum += v[k];
     uint32_t incl = sum; // inclusive scan over the block
@@ -193,7 +197,11 @@ __global__ void __launch_bounds__(1024) k_bin_scan(uint32_t numBins, const uint3
     __syncthreads();
     uint32_t run = incl - sum + ((threadIdx.x >> 5) ? sWarp[(threadIdx.x >> 5) - 1u] : 0u);
 #pragma unroll
-    for (uint32_t k = 0; k < PER; ++k) if (first + k < numBins) { cursor[first + k] = run; run += v[k]; }
+    for (uint32_t k = 0; k < PER; k += 4u) {
+        uint4 q; q.x = run; q.y = q.x + v[k]; q.z = q.y + v[k + 1]; q.w = q.z + v[k + 2]; run = q.w + v[k + 3];
+        if (first + k + 3u < numBins) *reinterpret_cast<uint4*>(cursor + first + k) = q;
+        else { const uint32_t w[4] = {q.x, q.y, q.z, q.w}; for (uint32_t j = 0; j < 4u; ++j) if (first + k + j < numBins) cursor[first + k + j] = w[j]; }
+    }
 }
 __global__ void __launch_bounds__(256) k_bin_scatter(uint32_t numRays, uint32_t numBins, const uint32_t* __restrict__ keys, uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
     extern __shared__ uint32_t sBins[];
@@ -209,7 +217,15 @@ __global__ void __launch_bounds__(256) k_bin_scatter(uint32_t numRays, uint32_t 
             rank[j] = key[j] != 0xFFFFFFFFu ? atomicAdd(&sBins[key[j]], 1u) : 0u;
         }
         __syncthreads();
-        for (uint32_t b = threadIdx.x; b < numBins; b += 256u) { const uint32_t c = sBins[b]; if (c) sBins[b] = atomicAdd(cursor + b, c); } // the tile's range of bin b
+        for (uint32_t b0 = threadIdx.x; b0 < numBins; b0 += 8u * 256u) { // the tile's range of every non-empty bin: eight reservations in flight per thread (one after the other they were a chain of global round trips)
+            uint32_t c[8], base[8];
+#pragma unroll
+            for (uint32_t k = 0; k < 8u; ++k) { const uint32_t b = b0 + k * 256u; c[k] = b < numBins ? sBins[b] : 0u; }
+#pragma unroll
+            for (uint32_t k = 0; k < 8u; ++k) base[k] = c[k] ? atomicAdd(cursor + b0 + k * 256u, c[k]) : 0u;
+#pragma unroll
+            for (uint32_t k = 0; k < 8u; ++k) if (c[k]) sBins[b0 + k * 256u] = base[k];
+        }
         __syncthreads();
 #pragma unroll
         for (uint32_t j = 0; j < BIN_TILE / 256u; ++j)
