@@ -293,7 +293,7 @@ def cfg5_leg(local, rank, world, torch, dist, light, steps=3, check_rays=16):
     out = None
     if rank == 0:
         rays_total = grid5.probe_count * RAYS
-        out = {"workload": "BASELINE configs[4]: synthetic instanced stress scene, 128x128x128 probes x 256 rays, probe z-slabs x%d" % world, "triangles": int(info.numTriangles), "instances": int(len(flat5["instances"])),
+        out = {"workload": "BASELINE configs[4]: synthetic instanced stress scene, 128x128x128 probes x 256 rays, probe z-slices dealt round robin over %d ranks" % world, "triangles": int(info.numTriangles), "instances": int(len(flat5["instances"])),
                "bvh_nodes": int(info.numNodes), "bvh_build_ms": round(float(info.buildMs), 2), "update_ms": ms, "value": rays_total / (ms * 1e-3), "unit": "probe rays/s", "steps": steps,
                "timing": "one CUDA-event interval over the steps, closed after the last all-gather; max over ranks", "allgather_bytes_per_update": int((ih * iw + dh * dw + grid5.probe_count) * 4),
                "sharded_equals_single": equal, "check_rays_per_probe": check_rays}
@@ -482,10 +482,12 @@ def main():
     # ---- end to end through the C ABI with host buffers: every step copies the to-update list + parameters host->device and reads
     # both atlases and the state words back into pinned host memory. The read-back of step s is queued asynchronously
     # (vkx_probes_download_slab_async) and overlaps the tracing of step s+1; all copies have landed before the clock stops.
-    # With N ranks every rank reads back the z-slab it traced, so the job as a whole reads the volume back exactly once per step.
+    # With N ranks every rank reads back the z-slices it traced (vkx_shard_slices), so the job as a whole reads the volume back exactly once per step.
     (ih, iw), (dh, dw) = grid.atlas_shapes()
     ih, dh, nst = ih // n, dh // n, grid.probe_count // n
-    z0, z1 = rank * (grid.resolution[2] // n), (rank + 1) * (grid.resolution[2] // n)
+    from vulkanexp_b200._lib import shard_slices
+    my_slices = shard_slices(grid.resolution[2], n, rank) if n > 1 else [(0, grid.resolution[2])]  # the z-slices this rank traced
+    plane = grid.resolution[0] * grid.resolution[1]
     outs = []
     for _ in range(2):
         pin = (torch.empty((ih, iw), dtype=torch.int32).pin_memory(), torch.empty((dh, dw), dtype=torch.int32).pin_memory(), torch.empty(nst, dtype=torch.int32).pin_memory())
@@ -503,7 +505,12 @@ def main():
             ctx.probes_update_sharded(grid, light, Rs[base + (s % (args.e2e_steps + 8))], sync=False)
         else:
             ctx.probes_update(grid, light, Rs[base + (s % (args.e2e_steps + 8))], idx_np, sync=False)
-        ctx.probes_download_slab_async(z0, z1, outs[s & 1][1])
+        oi, od, ost = outs[s & 1][1]
+        r0 = 0
+        for (z0, z1) in my_slices:  # one read-back per slice group, packed one after the other in the pinned buffers
+            nz = z1 - z0
+            ctx.probes_download_slab_async(z0, z1, (oi[8 * r0:8 * (r0 + nz)], od[16 * r0:16 * (r0 + nz)], ost[r0 * plane:(r0 + nz) * plane]))
+            r0 += nz
     ctx.probes_download_wait()
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps)
@@ -541,7 +548,7 @@ def main():
             "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": name, "probes_per_gpu": probes_per_rank, "rays_per_probe": RAYS, "l2": l2_note,
                        "timing": "per-step CUDA events on the library's stream, summed" if world == 1 else "one CUDA-event interval over all steps on the library's stream, closed after the last all-gather",
-                       "parallelism": ("probe z-slabs x%d, %s" % (n, "blend fused with the atlas exchange over NVLink peer memory (P2P stores + device-side flags)" if exchange == "p2p" else "NCCL all-gather of atlas slabs, deferred behind the next step's primary traversal")) if n > 1 else "single GPU"},
+                       "parallelism": ("probe z-slices dealt round robin over %d ranks, %s" % (n, "blend fused with the atlas exchange over NVLink peer memory (P2P stores + device-side flags)" if exchange == "p2p" else "NCCL all-gather of atlas slabs, deferred behind the next step's primary traversal")) if n > 1 else "single GPU"},
             "full_volume_update_ms": ms_per_step, "grays_per_sec_per_gpu": value / n / 1e9,
             "gpu_launches": int(launches), "clocks": clocks,
             "e2e": {"value": rays_per_step_total / (e2e_ms * 1e-3), "unit": "probe rays/s", "ms_per_step": e2e_ms, "steps": e2e_steps, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

@@ -287,7 +287,7 @@ int vkx_comm_init(vkx_ctx* ctx, int rank, int nranks, const void* id128);
  * sampled atlases waits for all flags on the device - no collective, no host synchronisation. Results are identical. */
 int vkx_comm_p2p_export(vkx_ctx* ctx, void* handle64);
 int vkx_comm_p2p_import(vkx_ctx* ctx, const void* handles /* nranks x 64 bytes, rank order; NULL, 0 = back to NCCL */, int count);
-/* Full-volume update of this rank's z-slab followed by the all-gather of the atlas/state slabs. */
+/* Full-volume update of this rank's z-slices (vkx_shard_slices) followed by the all-gathers of the atlas / state rows. */
 int vkx_probes_update_sharded(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx_light* light,
                               const float orientation[16], int sync);
 /* Partial update of a to-update list on several GPUs (the reference's ProbesPerUpdate / refresh-period scheduling,
@@ -300,10 +300,14 @@ int vkx_probes_update_sharded_list(vkx_ctx* ctx, const vkx_grid_info* grid, cons
 /* Orders the context's stream after a pending atlas exchange (the deferred all-gather of vkx_probes_update_sharded); returns at
  * once. An event recorded on vkx_stream() afterwards completes when the exchange has landed (bench.py times with it). */
 int vkx_stream_wait_exchange(vkx_ctx* ctx);
-/* The sharding arithmetic itself (host only, no context): z-slices [*z0, *z1) of rank `rank` in a full-volume sharded update, and
- * the positions [*first, *first + *n) of a `count`-long to-update list that rank `rank` processes in vkx_probes_update_sharded_list.
- * Return VKX_E_INVALID for rz not divisible by nranks / bad rank. */
-int vkx_shard_slab(uint32_t rz, int nranks, int rank, uint32_t* z0, uint32_t* z1);
+/* The sharding arithmetic itself (host only, no context). Full-volume sharded update: every rank owns *numGroups groups of
+ * *groupSlices consecutive z-slices, dealt round robin (two slices per group = whole 2x2x2 probe blocks, which spreads every region of
+ * the volume over all ranks; an odd number of slices per rank gives one group = one slab); vkx_shard_slices returns group `group` of
+ * rank `rank` as [*z0, *z1). The slices of all ranks in one group are consecutive atlas rows: one all-gather per group. To-update
+ * lists: vkx_shard_range gives the positions [*first, *first + *n) of a `count`-long list that rank `rank` processes in
+ * vkx_probes_update_sharded_list. VKX_E_INVALID for rz not divisible by nranks / bad rank / bad group. */
+int vkx_shard_groups(uint32_t rz, int nranks, uint32_t* groupSlices, uint32_t* numGroups);
+int vkx_shard_slices(uint32_t rz, int nranks, int rank, uint32_t group, uint32_t* z0, uint32_t* z1);
 int vkx_shard_range(uint32_t count, int nranks, int rank, uint32_t* first, uint32_t* n);
 
 /* ---- sun shadows: DirectLight pass ---------------------------------------------------------------------------- */

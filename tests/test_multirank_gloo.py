@@ -1,5 +1,5 @@
 """CPU-only, world_size 2 over gloo: the host-side logic of the two sharded updates, driven by the sharding arithmetic the
-library itself uses (vkx_shard_slab / vkx_shard_range, exported host-only through the C ABI: csrc/api.cu), with the oracle
+library itself uses (vkx_shard_groups / vkx_shard_slices / vkx_shard_range, exported host-only through the C ABI: csrc/api.cu), with the oracle
 standing in for the per-rank device work.
   * full-volume update: z-slab per rank, all-gather of contiguous atlas rows and state words;
   * list update (ProbesPerUpdate scheduling): list positions per rank, all-gather of packed 1296-byte tile records, scatter into
@@ -19,21 +19,26 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 RES, RAYS = (4, 3, 8), 24
 
 
-def test_slab_arithmetic_partitions_the_volume():
-    from vulkanexp_b200._lib import VkxError, shard_slab
+def test_slice_arithmetic_partitions_the_volume():
+    from vulkanexp_b200._lib import VkxError, shard_groups, shard_slices
 
-    for rz in (2, 8, 32, 64, 128, 12):
-        for n in (1, 2, 4, 8):
+    for rz in (2, 8, 32, 64, 128, 12, 3):
+        for n in (1, 2, 3, 4, 8):
             if rz % n:
                 with pytest.raises(VkxError):
-                    shard_slab(rz, n, 0)
+                    shard_groups(rz, n)
                 continue
-            slabs = [shard_slab(rz, n, r) for r in range(n)]
-            assert slabs[0][0] == 0 and slabs[-1][1] == rz
-            assert all(slabs[r][1] == slabs[r + 1][0] for r in range(n - 1))  # consecutive: plain all-gather layout
-            assert len({b - a for a, b in slabs}) == 1                          # equal: ncclAllGather takes one count
+            s, groups = shard_groups(rz, n)
+            assert s * groups * n == rz and (s == 2 or groups == 1)        # pairs of slices (whole 2x2x2 probe blocks), else one slab
+            per_rank = [shard_slices(rz, n, r) for r in range(n)]
+            assert all(len(p) == groups and all(b - a == s for a, b in p) for p in per_rank)  # equal counts: ncclAllGather takes one count
+            for g in range(groups):  # the ranks' slices of one group are consecutive, in rank order: a plain all-gather layout
+                assert per_rank[0][g][0] == g * s * n
+                assert all(per_rank[r][g][1] == per_rank[r + 1][g][0] for r in range(n - 1))
+            covered = sorted(z for p in per_rank for a, b in p for z in range(a, b))
+            assert covered == list(range(rz))                                # every slice exactly once
     with pytest.raises(VkxError):
-        shard_slab(8, 2, 2)
+        shard_slices(8, 2, 2)
 
 
 def test_list_range_arithmetic_covers_every_position_once():
@@ -65,7 +70,7 @@ def _worker(rank, world, port, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from oracle import pyoracle
     from vulkanexp_b200 import scene_format, synth
-    from vulkanexp_b200._lib import shard_range, shard_slab
+    from vulkanexp_b200._lib import shard_groups, shard_range, shard_slices
     from vulkanexp_b200.pods import GridInfo, Light
 
     # rendezvous of an opaque 128-byte id, as bench.py does for ncclUniqueId
@@ -92,13 +97,18 @@ def _worker(rank, world, port, out_dir):
     for frame in range(4):
         R, _ = host.next_orientation()
         grid.hysteresis = 0.3 * frame
-        if frame % 2 == 0:  # ---- full-volume update: own z-slab, all-gather of contiguous rows
-            z0, z1 = shard_slab(rz, world, rank)
-            o.probes_update(grid, light, R, np.arange(z0 * plane, z1 * plane, dtype=np.uint32), 1)
+        if frame % 2 == 0:  # ---- full-volume update: own z-slices, one all-gather of contiguous rows per slice group
+            mine = shard_slices(rz, world, rank)
+            idx = np.concatenate([np.arange(z0 * plane, z1 * plane, dtype=np.uint32) for z0, z1 in mine])
+            o.probes_update(grid, light, R, idx, 1)
             irr, dep, st, _ = o.probes_download()
-            nirr = gather(torch.from_numpy(irr[8 * z0:8 * z1].astype(np.int64))).numpy().astype(np.uint32)
-            ndep = gather(torch.from_numpy(dep[16 * z0:16 * z1].astype(np.int64))).numpy().astype(np.uint32)
-            nst = gather(torch.from_numpy(st[z0 * plane:z1 * plane].astype(np.int64))).numpy().astype(np.uint32)
+            nirr, ndep, nst = irr.copy(), dep.copy(), st.copy()
+            gs, groups = shard_groups(rz, world)
+            for g, (z0, z1) in enumerate(mine):  # group g: rows of the slices [g gs world, (g + 1) gs world), rank order
+                lo, hi = g * gs * world, (g + 1) * gs * world
+                nirr[8 * lo:8 * hi] = gather(torch.from_numpy(irr[8 * z0:8 * z1].astype(np.int64))).numpy().astype(np.uint32)
+                ndep[16 * lo:16 * hi] = gather(torch.from_numpy(dep[16 * z0:16 * z1].astype(np.int64))).numpy().astype(np.uint32)
+                nst[lo * plane:hi * plane] = gather(torch.from_numpy(st[z0 * plane:z1 * plane].astype(np.int64))).numpy().astype(np.uint32)
             o.probes_upload(nirr, ndep, nst)  # publish = swap to the gathered atlases
         else:  # ---- list update: own list positions, all-gather of packed tile records, scatter in list order
             lst = np.random.default_rng(100 + frame).permutation(grid.probe_count).astype(np.uint32)[: 37 + frame]

@@ -43,19 +43,22 @@ for frame in range(4):
 # own-slab read-back queued right behind a sharded update (it reads the rank's work atlases and does not wait for the all-gather):
 # must equal the same rows of the single-GPU atlases, frame after frame, with the next update already queued
 (ih, iw), (dh, dw) = grid.atlas_shapes()
-z0, z1 = rank * (res[2] // world), (rank + 1) * (res[2] // world)
-bufs = [(np.zeros((ih // world, iw), np.uint32), np.zeros((dh // world, dw), np.uint32), np.zeros(grid.probe_count // world, np.uint32)) for _ in range(2)]
+from vulkanexp_b200._lib import shard_slices
+slices = shard_slices(res[2], world, rank)
+bufs = [[(np.zeros((8 * (z1 - z0), iw), np.uint32), np.zeros((16 * (z1 - z0), dw), np.uint32), np.zeros((z1 - z0) * res[0] * res[1], np.uint32)) for (z0, z1) in slices] for _ in range(2)]
 for frame in range(4, 8):
     R = gen.next()
     ctx.probes_update_sharded(grid, light, R, sync=False)
-    ctx.probes_download_slab_async(z0, z1, bufs[frame & 1])
+    for (z0, z1), buf in zip(slices, bufs[frame & 1]):
+        ctx.probes_download_slab_async(z0, z1, buf)
     ref.probes_update(grid, light, R, None)
     ctx.probes_download_wait()
     b = ref.probes_download()
-    got = bufs[frame & 1]
-    same = np.array_equal(got[0], b[0][8 * z0:8 * z1]) and np.array_equal(got[1], b[1][16 * z0:16 * z1]) and np.array_equal(got[2], b[2][z0 * res[0] * res[1]:z1 * res[0] * res[1]])
+    same = True
+    for (z0, z1), got in zip(slices, bufs[frame & 1]):
+        same &= bool(np.array_equal(got[0], b[0][8 * z0:8 * z1]) and np.array_equal(got[1], b[1][16 * z0:16 * z1]) and np.array_equal(got[2], b[2][z0 * res[0] * res[1]:z1 * res[0] * res[1]]))
     ok &= same
-    print("rank %d frame %d: async own-slab read-back == single-GPU rows: %s" % (rank, frame, same), flush=True)
+    print("rank %d frame %d: async own-slice read-back == single-GPU rows: %s" % (rank, frame, same), flush=True)
 a, b = ctx.probes_download(), ref.probes_download()
 same = all(np.array_equal(x, y) for x, y in zip(a[:3], b[:3]))
 ok &= same

@@ -70,13 +70,27 @@ def image_decode(path):
     return out
 
 
-def shard_slab(rz, nranks, rank):
-    """z-slices [z0, z1) of `rank` in a full-volume sharded update (vkx_shard_slab: the arithmetic vkx_probes_update_sharded uses)."""
-    z0, z1 = C.c_uint32(0), C.c_uint32(0)
-    rc = load().vkx_shard_slab(C.c_uint32(rz), C.c_int(nranks), C.c_int(rank), C.byref(z0), C.byref(z1))
+def shard_groups(rz, nranks):
+    """(slices per group, groups per rank) of a full-volume sharded update (vkx_shard_groups)."""
+    s, k = C.c_uint32(), C.c_uint32()
+    rc = load().vkx_shard_groups(C.c_uint32(rz), C.c_int(nranks), C.byref(s), C.byref(k))
     if rc != 0:
-        raise VkxError(rc, "vkx_shard_slab(%d, %d, %d)" % (rz, nranks, rank))
-    return z0.value, z1.value
+        raise VkxError(rc, "vkx_shard_groups(%d, %d)" % (rz, nranks))
+    return s.value, k.value
+
+
+def shard_slices(rz, nranks, rank):
+    """The z-slice ranges [(z0, z1), ...] of `rank` in a full-volume sharded update (vkx_shard_slices: the arithmetic
+    vkx_probes_update_sharded uses), in z order."""
+    _, groups = shard_groups(rz, nranks)
+    out = []
+    for g in range(groups):
+        z0, z1 = C.c_uint32(), C.c_uint32()
+        rc = load().vkx_shard_slices(C.c_uint32(rz), C.c_int(nranks), C.c_int(rank), C.c_uint32(g), C.byref(z0), C.byref(z1))
+        if rc != 0:
+            raise VkxError(rc, "vkx_shard_slices(%d, %d, %d, %d)" % (rz, nranks, rank, g))
+        out.append((z0.value, z1.value))
+    return out
 
 
 def shard_range(count, nranks, rank):

@@ -602,8 +602,13 @@ int vkx_probes_download_slab_async(vkx_ctx* ctx, uint32_t z0, uint32_t z1, uint3
     // After a sharded update the rank's own slab is complete in its work atlases as soon as its blend has run: reading it from there
     // does not have to wait for the all-gather, which stays hidden behind the next frame's traversal. Any other slab comes from the
     // sampled atlases and needs the gather.
-    const uint32_t own = ctx->nranks > 1 ? uint32_t(ctx->grid.resolution[2]) / uint32_t(ctx->nranks) : 0u;
-    const bool fromWork = ctx->shardedLast && (ctx->gatherPending || ctx->p2pPending) && own && z0 >= uint32_t(ctx->rank) * own && z1 <= uint32_t(ctx->rank + 1) * own;
+    bool own = false; // inside one of this rank's slice groups (vkx_shard_slices)?
+    { uint32_t s = 0, K = 0;
+      if (ctx->nranks > 1 && vkx_shard_groups(uint32_t(ctx->grid.resolution[2]), ctx->nranks, &s, &K) == VKX_OK) {
+          const uint32_t g = z0 / (s * uint32_t(ctx->nranks)), lo = g * s * uint32_t(ctx->nranks) + uint32_t(ctx->rank) * s;
+          own = z0 >= lo && z1 <= lo + s;
+      } }
+    const bool fromWork = ctx->shardedLast && (ctx->gatherPending || ctx->p2pPending) && own;
     if (!fromWork) TRY(waitGather(ctx));
     if (!ctx->copyStream) {
         CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
@@ -784,12 +789,12 @@ int vkx_probes_update_sharded(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx
     const size_t irrBytes = size_t(ctx->irrW) * ctx->irrH * 4, depBytes = size_t(ctx->depW) * ctx->depH * 4, stBytes = size_t(ctx->probeCount) * 4;
     if (!ctx->dIrrNext) { // (with peer exchange enabled the next set lives in the shared slab)
         CUDA_TRY(ctx, cudaMalloc(&ctx->dIrrNext, irrBytes)); CUDA_TRY(ctx, cudaMalloc(&ctx->dDepNext, depBytes)); CUDA_TRY(ctx, cudaMalloc(&ctx->dStateNext, stBytes)); }
-    // One chunk per frame: the all-gather of frame f is not waited for at the end of the update but before the first kernel of frame
-    // f+1 that reads the sampled atlases (k_shade_front), so it overlaps frame f+1's primary traversal, which never touches them.
-    // (Measured on 4 GPUs: splitting the slab into chunks to overlap inside the frame cost more in small launches than it hid.)
-    uint32_t slab0 = 0, slab1 = 0;
-    if (vkx_shard_slab(rz, ctx->nranks, ctx->rank, &slab0, &slab1) != VKX_OK) return vkx_fail(ctx, VKX_E_INVALID, "vkx_shard_slab");
-    const uint32_t K = 1, s = slab1 - slab0; // slices per rank
+    // One update per frame over all of the rank's slice groups: the all-gathers of frame f are not waited for at the end of the update
+    // but before the first kernel of frame f+1 that reads the sampled atlases (k_shade_front), so they overlap frame f+1's primary
+    // traversal, which never touches them. (Measured on 4 GPUs: one update per group, to overlap inside the frame, cost more in small
+    // launches than it hid.)
+    uint32_t s = 0, K = 0; // slices per group, groups per rank
+    if (vkx_shard_groups(rz, ctx->nranks, &s, &K) != VKX_OK) return vkx_fail(ctx, VKX_E_INVALID, "vkx_shard_groups");
     ncclComm_t comm = reinterpret_cast<ncclComm_t>(ctx->comm);
     cudaStream_t st = ctx->stream, cs = ctx->commStream;
     const bool p2p = ctx->p2p;
@@ -803,23 +808,28 @@ int vkx_probes_update_sharded(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx
         ctx->blendPeers = pt; ctx->blendToPeers = true;
     } else if (ctx->copyPending && !ctx->copyReadsWork) { CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->commStream, ctx->evCopyDone, 0)); ctx->copyPending = false; } // read-back of the buffers about to be overwritten
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], st));
-    uint32_t total = 0;
-    for (uint32_t k = 0; k < K; ++k) {
-        const uint32_t z0 = k * s * n + slab0; // K = 1: the rank's slab
-        const uint32_t first = z0 * plane, count = s * plane;
-        k_iota_list<<<divUp(count, 256), 256, 0, st>>>(ctx->dIndicesList + total, first, count); LAUNCH_CHECK(ctx);
-        if (!ctx->shardOrderReady) { std::vector<uint32_t> idx(count); for (uint32_t i = 0; i < count; ++i) idx[i] = first + i; TRY(uploadOrder(ctx, idx.data(), count, total, false)); }
-        { int rc = ddgiUpdate(ctx, *light, nullptr, count, total, false); if (rc != VKX_OK) { ctx->blendToPeers = false; return rc; } }
-        total += count;
-        if (p2p) continue;
+    const uint32_t groupProbes = s * plane, total = K * groupProbes;
+    for (uint32_t k = 0; k < K; ++k) { // the rank's to-update list: its slices of every group, in z order
+        const uint32_t first = (k * s * n + uint32_t(ctx->rank) * s) * plane;
+        k_iota_list<<<divUp(groupProbes, 256), 256, 0, st>>>(ctx->dIndicesList + size_t(k) * groupProbes, first, groupProbes); LAUNCH_CHECK(ctx);
+    }
+    if (!ctx->shardOrderReady) {
+        std::vector<uint32_t> idx(total);
+        for (uint32_t k = 0; k < K; ++k) { const uint32_t first = (k * s * n + uint32_t(ctx->rank) * s) * plane; for (uint32_t i = 0; i < groupProbes; ++i) idx[size_t(k) * groupProbes + i] = first + i; }
+        TRY(uploadOrder(ctx, idx.data(), total, 0, false));
+    }
+    { int rc = ddgiUpdate(ctx, *light, nullptr, total, 0, false); if (rc != VKX_OK) { ctx->blendToPeers = false; return rc; } }
+    if (!p2p) {
         CUDA_TRY(ctx, cudaEventRecord(ctx->commEvent, st));
         CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ctx->commEvent, 0));
-        const size_t irrChunk = size_t(8 * s) * ctx->irrW, depChunk = size_t(16 * s) * ctx->depW, stChunk = size_t(s) * plane; // elements per rank
-        const size_t irrOff = size_t(8 * k * s * n) * ctx->irrW, depOff = size_t(16 * k * s * n) * ctx->depW, stOff = size_t(k * s * n) * plane;
+        const size_t irrChunk = size_t(8 * s) * ctx->irrW, depChunk = size_t(16 * s) * ctx->depW, stChunk = size_t(s) * plane; // elements per rank and group
         ncclResult_t r = ncclGroupStart();
-        if (r == ncclSuccess) r = ncclAllGather(ctx->dIrrWork + irrOff + irrChunk * ctx->rank, ctx->dIrrNext + irrOff, irrChunk, ncclUint32, comm, cs);
-        if (r == ncclSuccess) r = ncclAllGather(ctx->dDepWork + depOff + depChunk * ctx->rank, ctx->dDepNext + depOff, depChunk, ncclUint32, comm, cs);
-        if (r == ncclSuccess) r = ncclAllGather(ctx->dStateWork + stOff + stChunk * ctx->rank, ctx->dStateNext + stOff, stChunk, ncclUint32, comm, cs);
+        for (uint32_t k = 0; k < K && r == ncclSuccess; ++k) { // group k: the slices [k s n, (k + 1) s n) of all ranks are consecutive rows
+            const size_t irrOff = size_t(8 * k * s * n) * ctx->irrW, depOff = size_t(16 * k * s * n) * ctx->depW, stOff = size_t(k * s * n) * plane;
+            r = ncclAllGather(ctx->dIrrWork + irrOff + irrChunk * ctx->rank, ctx->dIrrNext + irrOff, irrChunk, ncclUint32, comm, cs);
+            if (r == ncclSuccess) r = ncclAllGather(ctx->dDepWork + depOff + depChunk * ctx->rank, ctx->dDepNext + depOff, depChunk, ncclUint32, comm, cs);
+            if (r == ncclSuccess) r = ncclAllGather(ctx->dStateWork + stOff + stChunk * ctx->rank, ctx->dStateNext + stOff, stChunk, ncclUint32, comm, cs);
+        }
         if (r == ncclSuccess) r = ncclGroupEnd();
         if (r != ncclSuccess) return vkx_fail(ctx, VKX_E_NCCL, "ncclAllGather: %s", ncclGetErrorString(r));
     }
@@ -844,10 +854,22 @@ int vkx_probes_update_sharded(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx
 }
 
 
-int vkx_shard_slab(uint32_t rz, int nranks, int rank, uint32_t* z0, uint32_t* z1) {
-    if (nranks < 1 || rank < 0 || rank >= nranks || !z0 || !z1 || rz % uint32_t(nranks) != 0u) return VKX_E_INVALID;
-    const uint32_t s = rz / uint32_t(nranks);
-    *z0 = uint32_t(rank) * s; *z1 = uint32_t(rank + 1) * s;
+// A rank's z-slices in a sharded full-volume update. The volume is cut into groups of `groupSlices` consecutive slices per rank, dealt
+// round robin: group g of rank r = slices [g s n + r s, g s n + (r + 1) s). With s = 2 (whole 2x2x2 probe blocks) every rank gets a
+// sample of the whole volume instead of one slab, which evens the load (measured on cfg4, 8 ranks: slowest / mean slab 1.069,
+// interleaved 1.036, tools/slab_balance.py), and the slices of all ranks in group g are still consecutive: one all-gather per group
+// and atlas, no packing. An odd number of slices per rank falls back to one slab per rank.
+int vkx_shard_groups(uint32_t rz, int nranks, uint32_t* groupSlices, uint32_t* numGroups) {
+    if (nranks < 1 || !groupSlices || !numGroups || rz == 0u || rz % uint32_t(nranks) != 0u) return VKX_E_INVALID;
+    const uint32_t S = rz / uint32_t(nranks);
+    *groupSlices = (S % 2u == 0u) ? 2u : S;
+    *numGroups = S / *groupSlices;
+    return VKX_OK;
+}
+int vkx_shard_slices(uint32_t rz, int nranks, int rank, uint32_t group, uint32_t* z0, uint32_t* z1) {
+    uint32_t s = 0, K = 0;
+    if (rank < 0 || rank >= nranks || !z0 || !z1 || vkx_shard_groups(rz, nranks, &s, &K) != VKX_OK || group >= K) return VKX_E_INVALID;
+    *z0 = group * s * uint32_t(nranks) + uint32_t(rank) * s; *z1 = *z0 + s;
     return VKX_OK;
 }
 int vkx_shard_range(uint32_t count, int nranks, int rank, uint32_t* first, uint32_t* n) {
