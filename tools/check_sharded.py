@@ -1,5 +1,6 @@
 """Multi-GPU check (run with torchrun, one rank per GPU): the sharded update + NCCL all-gather must give every rank
-atlases identical to a single-GPU update. Prints one line per rank and exits non-zero on mismatch."""
+atlases identical to a single-GPU update. Prints one line per rank and exits non-zero on mismatch. VKX_P2P=1 selects the
+peer-memory exchange, which stores from the CUDA-core blend: run it with VKX_BLEND=simt so that the single-GPU side uses the same kernel."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
