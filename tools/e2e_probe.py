@@ -22,9 +22,13 @@ def run(mode, K=200):
     for s in range(K):
         h0=time.perf_counter()
         ctx.probes_update(grid, light, Rs[5+s], idx if 'list' in mode else None, sync=False)
-        if 'dl' in mode: ctx.probes_download_async(outs[s&1][1])
+        if 'dl' in mode:
+            o = outs[s&1][1]
+            if 'st' in mode: o = (None, None, o[2])
+            elif 'irr' in mode: o = (o[0], None, None)
+            ctx.probes_download_async(o)
         th+=time.perf_counter()-h0
     if 'dl' in mode: ctx.probes_download_wait()
     ctx.sync(); ms=(time.perf_counter()-t0)*1e3/K
     print(mode, 'ms/step %.3f'%ms, 'host enqueue ms/step %.3f'%(th*1e3/K), 'device', ctx.probes_timings()['full'])
-for m in ['null', 'list', 'null+dl', 'list+dl']: run(m)
+for m in ['null', 'null+dl', 'null+dl+st', 'null+dl+irr', 'null', 'null+dl']: run(m)
