@@ -43,11 +43,25 @@ __global__ void k_origin_table(vkx_grid_info grid, const uint32_t* __restrict__ 
     origins[s] = make_float4(o.x, o.y, o.z, 0.0f);
 }
 
+// What a finished primary ray needs next, as one word per ray: a miss goes to the sky queue, a back-face hit is final, a front-face
+// hit is shaded and carries its grouping key = (grid cell of the hit point) >> binShift (scheduling only: rays that shade from the
+// same 8 probes end up in the same warps of k_shade_front, and their shadow rays start close together).
+#define KEY_MISS 0xFFFFFFFFu
+#define KEY_BACK 0xFFFFFFFEu
+__device__ __forceinline__ uint32_t hitKey(const TraceParams& tp, uint32_t binShift, float ox, float oy, float oz, float dx, float dy, float dz, float t, uint32_t prim) {
+    if (prim == 0xFFFFFFFFu) return KEY_MISS;
+    if (prim & 0x80000000u) return KEY_BACK;
+    const int cx = min(max(int((ox + dx * t - tp.grid.extentMin[0]) * tp.invCell[0]), 0), tp.grid.resolution[0] - 1);
+    const int cy = min(max(int((oy + dy * t - tp.grid.extentMin[1]) * tp.invCell[1]), 0), tp.grid.resolution[1] - 1);
+    const int cz = min(max(int((oz + dz * t - tp.grid.extentMin[2]) * tp.invCell[2]), 0), tp.grid.resolution[2] - 1);
+    return uint32_t(cx + tp.grid.resolution[0] * (cy + tp.grid.resolution[1] * cz)) >> binShift;
+}
+
 // Rays are sorted by what they need next when their traversal ends: misses -> sky queue, front-face hits -> shading queue,
 // back-face hits are final (closesthit.glsl:137-141) and written here. The two shading kernels then run on dense queues.
 struct PrimarySrc {
     TraceParams tp; RayMap rm; const float4* origins; const float4* dirs; const float4* invDirs; vkx_hit* hits;
-    float4* rays; uint32_t* missQueue; uint32_t* frontQueue; uint32_t* counters; // counters[3] misses, counters[4] front hits
+    float4* rays;
     uint32_t ri;
     __device__ __forceinline__ bool load(uint32_t item, Ray& r, float& tmin, float& tmax, uint32_t& cullMask) {
         uint32_t slot, ray;
@@ -59,8 +73,10 @@ struct PrimarySrc {
         return true;
     }
     // The hit record only (plus the final value of a back-face hit, closesthit.glsl:137-141). Which queue the ray goes to next is
-    // decided by k_classify_hits: appending here cost a global atomic round trip per finishing ray with the whole warp waiting on
-    // it (16 % of the kernel's stall samples, profiles/r02f_src_k_trace_primary.txt).
+    // decided by the classification pass: appending here cost a global atomic round trip per finishing ray with the whole warp
+    // waiting on it (16 % of the kernel's stall samples, profiles/r02f_src_k_trace_primary.txt), and even computing the ray's
+    // grouping key here (the ray is still in registers) loses: the finishing path runs at ~2 of 32 lanes, so its ~25 instructions
+    // cost 12 warp-instructions per ray (k_trace_primary 0.759 -> 0.794 ms) against one in the dense pass.
     __device__ __forceinline__ void store(uint32_t, const HitRec& h, bool) {
         vkx_hit out; out.t = h.t; out.instance = h.inst; out.primitive = h.prim; out.u = h.u; out.v = h.v;
         hits[ri] = out;
@@ -113,15 +129,16 @@ __global__ void __launch_bounds__(256) k_classify_hits(TraceParams tp, const flo
 
 // ---- front hits grouped by grid cell without a sort library: counting sort with block-private histograms
 // The key of a front hit is its bin = (grid cell of the hit point) >> binShift, at most BIN_MAX bins (64 KB of shared-memory
-// counters). k_bin_count classifies every ray (misses -> sky queue, back faces are final, front hits -> key), counts the keys of
-// BIN_TILE rays at a time in shared memory and adds the block's counts to the global histogram once per block (hit points cluster
-// in few cells: per-ray or per-warp global atomics on the hot cells serialise in L2, the reason an earlier counting sort lost to
-// the radix sort). k_bin_scan turns the histogram into first positions; k_bin_scatter counts each tile again in shared memory (a
-// ray's rank inside its tile's bin is what the shared-memory atomic returns), reserves the tile's range of every non-empty bin with
-// one global atomic, and writes the ray indices. The order inside a bin depends on scheduling; every queue item is shaded
-// independently and results are stored by ray index, so outputs do not.
+// counters). k_bin_count reads the hit records, writes one key word per ray (hitKey), appends the misses of each tile to the
+// sky queue, counts the front hits of BIN_TILE rays at a time in shared memory and adds the block's counts to the global histogram
+// once per block (hit points cluster in few cells: per-ray or per-warp global atomics on the hot cells serialise in L2, the reason
+// an earlier counting sort lost to the radix sort). k_bin_scan turns the histogram into first positions; k_bin_scatter counts each
+// tile again in shared memory (a ray's rank inside its tile's bin is what the shared-memory atomic returns), reserves the tile's
+// range of every bin it touched with one global atomic, and writes the ray indices. The order inside a bin depends on scheduling;
+// every queue item is shaded independently and results are stored by ray index, so outputs do not.
 #define BIN_TILE 4096u
 #define BIN_MAX 16384u
+#define BIN_PER (BIN_TILE / 256u)
 __global__ void __launch_bounds__(256) k_bin_count(TraceParams tp, uint32_t numBins, uint32_t binShift, const float4* __restrict__ origins, const float4* __restrict__ dirs,
                                                    const vkx_hit* __restrict__ hits, uint32_t* __restrict__ missQueue, uint32_t* __restrict__ keys, uint32_t* __restrict__ hist,
                                                    uint32_t* __restrict__ counters) {
@@ -134,27 +151,27 @@ __global__ void __launch_bounds__(256) k_bin_count(TraceParams tp, uint32_t numB
     for (uint32_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x) { // block-uniform trip count
         if (threadIdx.x == 0) sMissCount = 0u;
         __syncthreads();
-        uint32_t missMask = 0, missRank = 0;
-#pragma unroll 4
-        for (uint32_t j = 0; j < BIN_TILE / 256u; ++j) {
+        float t[BIN_PER]; uint32_t prim[BIN_PER];
+#pragma unroll
+        for (uint32_t j = 0; j < BIN_PER; ++j) { // the two words of all the thread's hit records in flight at once (one after the other, behind the branches below, they were a chain of DRAM round trips: 51 us for 84 MB)
             const uint32_t ri = tile * BIN_TILE + j * 256u + threadIdx.x;
-            uint32_t key = 0xFFFFFFFFu;
-            if (ri < tp.numRays) {
-                const float t = hits[ri].t; const uint32_t prim = hits[ri].primitive;
-                if (prim == 0xFFFFFFFFu) missMask |= 1u << j;
-                else if (!(prim & 0x80000000u)) {
-                    const uint32_t slot = ri / tp.raysPerProbe, ray = ri - slot * tp.raysPerProbe;
-                    const float4 o = __ldg(origins + slot);
-                    const float4 d = __ldg(dirs + ray);
-                    const int cx = min(max(int((o.x + d.x * t - tp.grid.extentMin[0]) * tp.invCell[0]), 0), tp.grid.resolution[0] - 1);
-                    const int cy = min(max(int((o.y + d.y * t - tp.grid.extentMin[1]) * tp.invCell[1]), 0), tp.grid.resolution[1] - 1);
-                    const int cz = min(max(int((o.z + d.z * t - tp.grid.extentMin[2]) * tp.invCell[2]), 0), tp.grid.resolution[2] - 1);
-                    key = uint32_t(cx + tp.grid.resolution[0] * (cy + tp.grid.resolution[1] * cz)) >> binShift;
-                    atomicAdd(&sBins[key], 1u);
-                    ++myFront;
-                }
-                keys[ri] = key;
+            const bool in = ri < tp.numRays;
+            t[j] = in ? hits[ri].t : 0.0f; prim[j] = in ? hits[ri].primitive : 0x80000000u; // padding counts as a (final) back face
+        }
+        uint32_t missMask = 0, missRank = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < BIN_PER; ++j) {
+            const uint32_t ri = tile * BIN_TILE + j * 256u + threadIdx.x;
+            const uint32_t slot = ri / tp.raysPerProbe, ray = ri - slot * tp.raysPerProbe;
+            uint32_t key = KEY_BACK;
+            if (prim[j] == 0xFFFFFFFFu) { missMask |= 1u << j; key = KEY_MISS; }
+            else if (!(prim[j] & 0x80000000u)) {
+                const float4 o = __ldg(origins + slot), d = __ldg(dirs + ray);
+                key = hitKey(tp, binShift, o.x, o.y, o.z, d.x, d.y, d.z, t[j], prim[j]);
+                atomicAdd(&sBins[key], 1u);
+                ++myFront;
             }
+            if (ri < tp.numRays) keys[ri] = key;
         }
         // misses of the tile: one reservation per block, positions by (thread, ray) inside the tile
         const uint32_t nMiss = uint32_t(__popc(missMask));
@@ -203,34 +220,44 @@ __global__ void __launch_bounds__(1024) k_bin_scan(uint32_t numBins, const uint3
         else { const uint32_t w[4] = {q.x, q.y, q.z, q.w}; for (uint32_t j = 0; j < 4u; ++j) if (first + k + j < numBins) cursor[first + k + j] = w[j]; }
     }
 }
-__global__ void __launch_bounds__(256) k_bin_scatter(uint32_t numRays, uint32_t numBins, const uint32_t* __restrict__ keys, uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
+// A tile touches few of the bins (4096 rays of 16 probes): instead of sweeping all of them, the thread whose shared-memory atomic
+// returned rank 0 for a bin speaks for it - it reserves the tile's range of that bin (all of a thread's reservations in flight
+// together), leaves the range's start in the bin's counter for the writers, and clears the counter for the next tile afterwards.
+// (The sweep over 16 K counters per tile - 8 dependent rounds of global atomics plus the clear - was most of the 51 us.)
+// Tiles of the scatter are larger than those of the count (SCAT_THREADS x BIN_PER rays): hit points cluster, so every tile reserves a
+// range in the same few hot bins, and those reservations - atomics with a return value on one address - are served one after the
+// other by L2. Measured by leaving phases out (cfg2, under ncu, cold caches): 23 us for the key loads and the shared-memory ranks,
+// + 11 us for the scattered 4-byte stores, + 5-10 us for the reservations; 4096-ray tiles: 59 us, the per-tile sweep before: 53 us.
+#define SCAT_THREADS 1024u
+#define SCAT_TILE (SCAT_THREADS * BIN_PER)
+__global__ void __launch_bounds__(SCAT_THREADS) k_bin_scatter(uint32_t numRays, uint32_t numBins, const uint32_t* __restrict__ keys, uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
     extern __shared__ uint32_t sBins[];
-    const uint32_t numTiles = (numRays + BIN_TILE - 1u) / BIN_TILE;
+    const uint32_t numTiles = (numRays + SCAT_TILE - 1u) / SCAT_TILE;
+    for (uint32_t b = threadIdx.x; b < numBins; b += SCAT_THREADS) sBins[b] = 0u;
+    __syncthreads();
     for (uint32_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
-        for (uint32_t b = threadIdx.x; b < numBins; b += 256u) sBins[b] = 0u;
-        __syncthreads();
-        uint32_t key[BIN_TILE / 256u], rank[BIN_TILE / 256u];
+        uint32_t key[BIN_PER], rank[BIN_PER];
 #pragma unroll
-        for (uint32_t j = 0; j < BIN_TILE / 256u; ++j) {
-            const uint32_t ri = tile * BIN_TILE + j * 256u + threadIdx.x;
-            key[j] = ri < numRays ? keys[ri] : 0xFFFFFFFFu;
-            rank[j] = key[j] != 0xFFFFFFFFu ? atomicAdd(&sBins[key[j]], 1u) : 0u;
+        for (uint32_t j = 0; j < BIN_PER; ++j) {
+            const uint32_t ri = tile * SCAT_TILE + j * SCAT_THREADS + threadIdx.x;
+            key[j] = ri < numRays ? __ldg(keys + ri) : KEY_BACK;
         }
+#pragma unroll
+        for (uint32_t j = 0; j < BIN_PER; ++j) rank[j] = key[j] < KEY_BACK ? atomicAdd(&sBins[key[j]], 1u) : 0xFFFFFFFFu;
         __syncthreads();
-        for (uint32_t b0 = threadIdx.x; b0 < numBins; b0 += 8u * 256u) { // the tile's range of every non-empty bin: eight reservations in flight per thread (one after the other they were a chain of global round trips)
-            uint32_t c[8], base[8];
+        uint32_t lead = 0, base[BIN_PER];
 #pragma unroll
-            for (uint32_t k = 0; k < 8u; ++k) { const uint32_t b = b0 + k * 256u; c[k] = b < numBins ? sBins[b] : 0u; }
+        for (uint32_t j = 0; j < BIN_PER; ++j) if (rank[j] == 0u) { lead |= 1u << j; base[j] = atomicAdd(cursor + key[j], sBins[key[j]]); }
 #pragma unroll
-            for (uint32_t k = 0; k < 8u; ++k) base[k] = c[k] ? atomicAdd(cursor + b0 + k * 256u, c[k]) : 0u;
-#pragma unroll
-            for (uint32_t k = 0; k < 8u; ++k) if (c[k]) sBins[b0 + k * 256u] = base[k];
-        }
+        for (uint32_t j = 0; j < BIN_PER; ++j) if (lead & (1u << j)) sBins[key[j]] = base[j]; // only this thread touches the counter of a bin it leads until the barrier
         __syncthreads();
 #pragma unroll
-        for (uint32_t j = 0; j < BIN_TILE / 256u; ++j)
-            if (key[j] != 0xFFFFFFFFu) sorted[sBins[key[j]] + rank[j]] = tile * BIN_TILE + j * 256u + threadIdx.x;
-        __syncthreads(); // sBins is cleared by the next tile
+        for (uint32_t j = 0; j < BIN_PER; ++j)
+            if (key[j] < KEY_BACK) sorted[sBins[key[j]] + rank[j]] = tile * SCAT_TILE + j * SCAT_THREADS + threadIdx.x;
+        __syncthreads();
+#pragma unroll
+        for (uint32_t j = 0; j < BIN_PER; ++j) if (lead & (1u << j)) sBins[key[j]] = 0u;
+        __syncthreads();
     }
 }
 
@@ -247,9 +274,9 @@ __global__ void __launch_bounds__(256) k_bin_scatter(uint32_t numRays, uint32_t 
 template <int DEFER>
 __global__ void __launch_bounds__(128, PT_MIN_BLOCKS) k_trace_primary(DeviceScene sc, TraceParams tp, RayMap rm, const float4* __restrict__ origins,
                                                        const float4* __restrict__ dirs, const float4* __restrict__ invDirs, vkx_hit* __restrict__ hits, float4* __restrict__ rays,
-                                                       uint32_t* __restrict__ missQueue, uint32_t* __restrict__ frontQueue, uint32_t* __restrict__ counters) {
+                                                       uint32_t* __restrict__ counters) {
     PrimarySrc src; src.tp = tp; src.rm = rm; src.origins = origins; src.dirs = dirs; src.invDirs = invDirs; src.hits = hits; src.ri = 0;
-    src.rays = rays; src.missQueue = missQueue; src.frontQueue = frontQueue; src.counters = counters;
+    src.rays = rays;
     if (DEFER == 0) persistentTrace<false>(sc.nodes, sc.tris, src, rm.numThreads, counters + 1);
     else if (DEFER < 0) persistentTracePF<false>(sc.nodes, sc.tris, src, rm.numThreads, counters + 1);
     else persistentTraceDeferred<false, (DEFER > 0 ? DEFER : 1)>(sc.nodes, sc.tris, src, rm.numThreads, counters + 1);
@@ -772,20 +799,20 @@ int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* /*unused*/,
             }
             poolBlocks = unsigned(ctx->smCount * cached);
         }
-        if (pool) {
-            if (poolStk == 8) k_trace_primary_pool<8><<<poolBlocks, 128, poolBytes, st>>>(sc, tp, rm, ctx->dOrigins, ctx->dDirs, ctx->dInvDirs, ctx->dHits, ctx->dRays, ctx->dQueueCount);
-            else k_trace_primary_pool<12><<<poolBlocks, 128, poolBytes, st>>>(sc, tp, rm, ctx->dOrigins, ctx->dDirs, ctx->dInvDirs, ctx->dHits, ctx->dRays, ctx->dQueueCount);
-        } else
-#define VKX_LAUNCH_PRIMARY(D) k_trace_primary<D><<<persistentBlocks, 128, 0, st>>>(sc, tp, rm, ctx->dOrigins, ctx->dDirs, ctx->dInvDirs, ctx->dHits, ctx->dRays, ctx->dMissQueue, ctx->dFrontQueue, ctx->dQueueCount)
-        switch (deferPrimary) { case -1: VKX_LAUNCH_PRIMARY(-1); break; case 8: VKX_LAUNCH_PRIMARY(8); break; case 12: VKX_LAUNCH_PRIMARY(12); break; case 16: VKX_LAUNCH_PRIMARY(16); break; default: VKX_LAUNCH_PRIMARY(0); }
-#undef VKX_LAUNCH_PRIMARY
-        LAUNCH_CHECK(ctx);
-        if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[1], st));
         // classification: misses -> sky queue, front hits -> key (grid cell of the hit point) for the grouping below
         static const bool radixSort = [] { const char* e = getenv("VKX_SORT"); return e && !strcmp(e, "radix"); }(); // A/B: the round-1 path (cub::DeviceRadixSort)
         uint32_t binShift = 0; while (((ctx->probeCount - 1u) >> binShift) + 1u > BIN_MAX) ++binShift;
         const uint32_t numBins = ((ctx->probeCount - 1u) >> binShift) + 1u;
         const size_t binBytes = size_t(numBins) * 4;
+        if (pool) {
+            if (poolStk == 8) k_trace_primary_pool<8><<<poolBlocks, 128, poolBytes, st>>>(sc, tp, rm, ctx->dOrigins, ctx->dDirs, ctx->dInvDirs, ctx->dHits, ctx->dRays, ctx->dQueueCount);
+            else k_trace_primary_pool<12><<<poolBlocks, 128, poolBytes, st>>>(sc, tp, rm, ctx->dOrigins, ctx->dDirs, ctx->dInvDirs, ctx->dHits, ctx->dRays, ctx->dQueueCount);
+        } else
+#define VKX_LAUNCH_PRIMARY(D) k_trace_primary<D><<<persistentBlocks, 128, 0, st>>>(sc, tp, rm, ctx->dOrigins, ctx->dDirs, ctx->dInvDirs, ctx->dHits, ctx->dRays, ctx->dQueueCount)
+        switch (deferPrimary) { case -1: VKX_LAUNCH_PRIMARY(-1); break; case 8: VKX_LAUNCH_PRIMARY(8); break; case 12: VKX_LAUNCH_PRIMARY(12); break; case 16: VKX_LAUNCH_PRIMARY(16); break; default: VKX_LAUNCH_PRIMARY(0); }
+#undef VKX_LAUNCH_PRIMARY
+        LAUNCH_CHECK(ctx);
+        if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->kev[1], st));
         if (radixSort) {
             CUDA_TRY(ctx, cudaMemsetAsync(ctx->dFrontKeys, 0xFF, size_t(numRays) * 4, st)); // unused slots sort to the end
             k_classify_hits<<<std::min<unsigned>(divUp(numRays, 256), unsigned(ctx->smCount) * 16u), 256, 0, st>>>(tp, ctx->dOrigins, ctx->dDirs, ctx->dHits, ctx->dMissQueue, ctx->dFrontQueue, ctx->dFrontKeys, ctx->dQueueCount); LAUNCH_CHECK(ctx);
@@ -814,7 +841,7 @@ int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* /*unused*/,
             ctx->launches += 3;
         } else { // front-hit queue grouped by bin: first positions, then the scatter (see k_bin_count)
             k_bin_scan<<<1, 1024, 0, st>>>(numBins, ctx->dCellHist, ctx->dFrontKeysOut); LAUNCH_CHECK(ctx);
-            k_bin_scatter<<<std::min<unsigned>(divUp(numRays, BIN_TILE), unsigned(ctx->smCount) * 3u), 256, binBytes, st>>>(numRays, numBins, ctx->dFrontKeys, ctx->dFrontKeysOut, ctx->dFrontQueueSorted); LAUNCH_CHECK(ctx);
+            k_bin_scatter<<<std::min<unsigned>(divUp(numRays, SCAT_TILE), unsigned(ctx->smCount) * 2u), SCAT_THREADS, binBytes, st>>>(numRays, numBins, ctx->dFrontKeys, ctx->dFrontKeysOut, ctx->dFrontQueueSorted); LAUNCH_CHECK(ctx);
         }
         { int rc = waitGather(ctx); if (rc != VKX_OK) return rc; } // sharded path: the previous frame's atlas all-gather must have landed
         launchShadeFront(shadeBlocks, st, sc, pr, sp, ctx->dOrigins, ctx->dDirs, ctx->dHits, ctx->dFrontQueueSorted, ctx->dQueueCount, ctx->dRays, ctx->dShadowQueue); LAUNCH_CHECK(ctx);
