@@ -241,8 +241,11 @@ int vkx_probes_update(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx_light* 
  * rays (optional) = the RGBA32F ray buffer of the last update [count][raysPerProbe] (rgb, depth). NULL skips. */
 int vkx_probes_download(vkx_ctx* ctx, uint32_t* irradiance, uint32_t* depth, uint32_t* state, float* rays,
                         size_t raysCapacityBytes);
-/* Asynchronous read-back: queues the copies behind the last publish on a copy stream and returns; the next update's publish waits
- * for them. Host buffers should be pinned (cudaHostAlloc / torch pin_memory). */
+/* Asynchronous read-back of the sampled atlases as they are at the time of the call. The copies run on a copy stream; on a
+ * single-GPU context they are started by the next update right before its primary traversal (or by vkx_probes_download_wait /
+ * any other writer of the atlases, whichever comes first), so that they overlap one long kernel instead of the update's small
+ * set-up launches; that update's publish waits for them. The host buffers must stay valid until vkx_probes_download_wait returns
+ * and should be pinned (cudaHostAlloc / torch pin_memory). VKX_READBACK=eager queues the copies immediately (A/B). */
 int vkx_probes_download_async(vkx_ctx* ctx, uint32_t* irradiance, uint32_t* depth, uint32_t* state);
 /* Same for the z-slices [z0, z1) only (the contiguous rows one rank of a sharded run owns); pointers address the first copied row. */
 int vkx_probes_download_slab_async(vkx_ctx* ctx, uint32_t z0, uint32_t z1, uint32_t* irradiance, uint32_t* depth, uint32_t* state);

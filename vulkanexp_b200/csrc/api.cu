@@ -30,6 +30,41 @@ static int upload(vkx_ctx* ctx, T** dst, const T* src, size_t n) {
 #define TRY(expr) do { int _rc = (expr); if (_rc != VKX_OK) return _rc; } while (0)
 #define BIND(ctx) do { if (!(ctx)) return VKX_E_INVALID; cudaError_t _e = cudaSetDevice((ctx)->device); if (_e != cudaSuccess) return vkx_fail((ctx), VKX_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(_e)); } while (0)
 
+// Asynchronous read-backs. A request for the sampled atlases of a single-GPU context is only noted (ctx->copyRequests) and queued
+// later: by the next update right before its primary traversal starts (ddgiUpdate), or by whatever needs the copy ordered first
+// (download_wait, any writer of the sampled atlases). Queued right behind the publish, the copy ran while the next update issued its
+// dozen small set-up launches, and every step was ~0.1 ms longer than with the copy alongside the 0.76 ms traversal kernel
+// (tools/e2e_probe.py: the overhead grew with the bytes read back, not with the number of event interlocks). Nothing writes the
+// sampled atlases between the request and that point, so the bytes are the same.
+static int ensureCopyStream(vkx_ctx* ctx) {
+    if (!ctx->copyStream) {
+        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->evPublished, cudaEventDisableTiming));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->evCopyDone, cudaEventDisableTiming));
+    }
+    return VKX_OK;
+}
+int flushCopyRequests(vkx_ctx* ctx) {
+    if (ctx->copyRequests.empty()) return VKX_OK;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->evPublished, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copyStream, ctx->evPublished, 0));
+    for (const auto& op : ctx->copyRequests) CUDA_TRY(ctx, cudaMemcpyAsync(op.dst, op.src, op.bytes, cudaMemcpyDeviceToHost, ctx->copyStream));
+    ctx->copyRequests.clear();
+    CUDA_TRY(ctx, cudaEventRecord(ctx->evCopyDone, ctx->copyStream));
+    ctx->copyPending = true; ctx->copyReadsWork = false;
+    return VKX_OK;
+}
+// Before anything other than an update overwrites the sampled atlases (upload, classification, re-initialisation): the requested
+// read-backs are queued now and the context's stream waits for them.
+static int settleReadBack(vkx_ctx* ctx) {
+    TRY(flushCopyRequests(ctx));
+    if (ctx->copyPending) { CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evCopyDone, 0)); ctx->copyPending = false; ctx->copyReadsWork = false; }
+    return VKX_OK;
+}
+static bool deferReadBack(const vkx_ctx* ctx) {
+    static const bool off = [] { const char* e = getenv("VKX_READBACK"); return e && !strcmp(e, "eager"); }(); // A/B: queue behind the publish as before
+    return !off && ctx->nranks <= 1;
+}
 int waitGather(vkx_ctx* ctx) { // orders the context's stream after a pending exchange (all-gather or peer stores) of the sampled atlases
     if (ctx->gatherPending) { CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->gatherDone, 0)); ctx->gatherPending = false; }
     if (ctx->p2pPending) { ctx->p2pPending = false; int rc = launchP2pWait(ctx); if (rc != VKX_OK) return rc; }
@@ -105,6 +140,7 @@ static void freeShadow(vkx_ctx* ctx) {
 void vkx_destroy(vkx_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    flushCopyRequests(ctx); // requested read-backs still land in the caller's buffers
     cudaStreamSynchronize(ctx->stream);
     if (ctx->comm) ncclCommDestroy(reinterpret_cast<ncclComm_t>(ctx->comm));
     freeProbes(ctx); freeShadow(ctx); freeTextures(ctx);
@@ -311,6 +347,8 @@ static int allocProbeScratch(vkx_ctx* ctx) {
 int vkx_probes_init(vkx_ctx* ctx, const vkx_grid_info* grid) {
     BIND(ctx);
     TRY(checkGrid(ctx, grid));
+    TRY(flushCopyRequests(ctx));
+    if (ctx->copyStream) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copyStream)); // a queued read-back still reads the atlases freed below
     freeProbes(ctx);
     ctx->grid = *grid;
     ctx->probeCount = uint32_t(grid->resolution[0]) * uint32_t(grid->resolution[1]) * uint32_t(grid->resolution[2]);
@@ -392,6 +430,7 @@ int vkx_probes_classify(vkx_ctx* ctx, const float orientation[16]) {
     BIND(ctx);
     if (!ctx->probesReady || !ctx->bvhBuilt) return vkx_fail(ctx, VKX_E_INVALID, "vkx_probes_classify: probes or BVH not ready");
     if (!orientation) return vkx_fail(ctx, VKX_E_INVALID, "null orientation");
+    TRY(settleReadBack(ctx));
     float dirs[512 * 3];
     rayDirections(orientation, 512, float(ctx->grid.raysPerProbe), dirs);
     return ddgiClassify(ctx, dirs);
@@ -559,6 +598,7 @@ int vkx_probes_update_scheduled(vkx_ctx* ctx, const vkx_grid_info* grid, const v
 
 int vkx_probes_download(vkx_ctx* ctx, uint32_t* irradiance, uint32_t* depth, uint32_t* state, float* rays, size_t raysCapacityBytes) {
     BIND(ctx);
+    TRY(flushCopyRequests(ctx));
     TRY(waitGather(ctx));
     if (!ctx->probesReady) return vkx_fail(ctx, VKX_E_INVALID, "probes not initialised");
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -578,21 +618,8 @@ int vkx_probes_download(vkx_ctx* ctx, uint32_t* irradiance, uint32_t* depth, uin
  * publish waits for them. Host buffers should be pinned. vkx_probes_download_wait blocks until the copies have landed. */
 int vkx_probes_download_async(vkx_ctx* ctx, uint32_t* irradiance, uint32_t* depth, uint32_t* state) {
     BIND(ctx);
-    TRY(waitGather(ctx));
     if (!ctx->probesReady) return vkx_fail(ctx, VKX_E_INVALID, "probes not initialised");
-    if (!ctx->copyStream) {
-        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
-        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->evPublished, cudaEventDisableTiming));
-        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->evCopyDone, cudaEventDisableTiming));
-    }
-    CUDA_TRY(ctx, cudaEventRecord(ctx->evPublished, ctx->stream)); // everything queued so far (including the last publish)
-    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copyStream, ctx->evPublished, 0));
-    if (irradiance) CUDA_TRY(ctx, cudaMemcpyAsync(irradiance, ctx->dIrrSampled, size_t(ctx->irrW) * ctx->irrH * 4, cudaMemcpyDeviceToHost, ctx->copyStream));
-    if (depth) CUDA_TRY(ctx, cudaMemcpyAsync(depth, ctx->dDepSampled, size_t(ctx->depW) * ctx->depH * 4, cudaMemcpyDeviceToHost, ctx->copyStream));
-    if (state) CUDA_TRY(ctx, cudaMemcpyAsync(state, ctx->dStateSampled, size_t(ctx->probeCount) * 4, cudaMemcpyDeviceToHost, ctx->copyStream));
-    CUDA_TRY(ctx, cudaEventRecord(ctx->evCopyDone, ctx->copyStream));
-    ctx->copyPending = true; ctx->copyReadsWork = false;
-    return VKX_OK;
+    return vkx_probes_download_slab_async(ctx, 0, uint32_t(ctx->grid.resolution[2]), irradiance, depth, state);
 }
 /* Same for the z-slices [z0, z1) only (contiguous atlas rows [8*z0, 8*z1) / [16*z0, 16*z1) and state words): what one rank of a sharded
  * run owns. Destination pointers address the first copied row. */
@@ -610,31 +637,35 @@ int vkx_probes_download_slab_async(vkx_ctx* ctx, uint32_t z0, uint32_t z1, uint3
       } }
     const bool fromWork = ctx->shardedLast && (ctx->gatherPending || ctx->p2pPending) && own;
     if (!fromWork) TRY(waitGather(ctx));
-    if (!ctx->copyStream) {
-        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
-        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->evPublished, cudaEventDisableTiming));
-        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->evCopyDone, cudaEventDisableTiming));
-    }
+    TRY(ensureCopyStream(ctx));
     const size_t plane = size_t(ctx->grid.resolution[0]) * size_t(ctx->grid.resolution[1]), nz = z1 - z0;
     const uint32_t* irrSrc = fromWork ? ctx->dIrrWork : ctx->dIrrSampled; const uint32_t* depSrc = fromWork ? ctx->dDepWork : ctx->dDepSampled;
     const uint32_t* stSrc = fromWork ? ctx->dStateWork : ctx->dStateSampled;
+    const vkx_ctx::CopyOp ops[3] = {{irradiance, irrSrc + size_t(8 * z0) * ctx->irrW, size_t(8 * nz) * ctx->irrW * 4},
+                                    {depth, depSrc + size_t(16 * z0) * ctx->depW, size_t(16 * nz) * ctx->depW * 4},
+                                    {state, stSrc + size_t(z0) * plane, nz * plane * 4}};
+    if (!fromWork && deferReadBack(ctx)) { // noted; queued by the next update (or by whoever needs it ordered first)
+        for (const auto& op : ops) if (op.dst) ctx->copyRequests.push_back(op);
+        return VKX_OK;
+    }
+    TRY(flushCopyRequests(ctx));
     CUDA_TRY(ctx, cudaEventRecord(ctx->evPublished, ctx->stream));
     CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copyStream, ctx->evPublished, 0));
-    if (irradiance) CUDA_TRY(ctx, cudaMemcpyAsync(irradiance, irrSrc + size_t(8 * z0) * ctx->irrW, size_t(8 * nz) * ctx->irrW * 4, cudaMemcpyDeviceToHost, ctx->copyStream));
-    if (depth) CUDA_TRY(ctx, cudaMemcpyAsync(depth, depSrc + size_t(16 * z0) * ctx->depW, size_t(16 * nz) * ctx->depW * 4, cudaMemcpyDeviceToHost, ctx->copyStream));
-    if (state) CUDA_TRY(ctx, cudaMemcpyAsync(state, stSrc + size_t(z0) * plane, nz * plane * 4, cudaMemcpyDeviceToHost, ctx->copyStream));
+    for (const auto& op : ops) if (op.dst) CUDA_TRY(ctx, cudaMemcpyAsync(op.dst, op.src, op.bytes, cudaMemcpyDeviceToHost, ctx->copyStream));
     CUDA_TRY(ctx, cudaEventRecord(ctx->evCopyDone, ctx->copyStream));
     ctx->copyPending = true; ctx->copyReadsWork = fromWork;
     return VKX_OK;
 }
 int vkx_probes_download_wait(vkx_ctx* ctx) {
     BIND(ctx);
+    TRY(flushCopyRequests(ctx));
     if (ctx->evCopyDone) CUDA_TRY(ctx, cudaEventSynchronize(ctx->evCopyDone));
     return VKX_OK;
 }
 
 int vkx_probes_upload(vkx_ctx* ctx, const uint32_t* irradiance, const uint32_t* depth, const uint32_t* state) {
     BIND(ctx);
+    TRY(settleReadBack(ctx));
     TRY(waitGather(ctx));
     TRY(syncWorkAtlases(ctx)); // a partial upload (e.g. states only) must not leave the other arrays of the work set stale
     if (!ctx->probesReady) return vkx_fail(ctx, VKX_E_INVALID, "probes not initialised");

@@ -124,6 +124,10 @@ struct vkx_ctx {
 
     // asynchronous read-back (vkx_probes_download_async)
     cudaStream_t copyStream = nullptr; cudaEvent_t evPublished = nullptr, evCopyDone = nullptr; bool copyPending = false, copyReadsWork = false; // copyReadsWork: the queued read-back reads the work atlases (own slab of a sharded update)
+    // Read-backs of the sampled atlases that were requested but not queued yet (single-GPU contexts): they are queued right before the
+    // next update's primary traversal starts instead of right behind the publish, see flushCopyRequests (api.cu)
+    struct CopyOp { void* dst; const void* src; size_t bytes; };
+    std::vector<CopyOp> copyRequests;
 
     // on-device scheduler (schedule.cu); the two counters are the reference's s_LoopIndex / _lastUpdateOffset
     uint32_t *dSchedFlags = nullptr, *dSchedPos = nullptr, *dSchedSlotOf = nullptr, *dSchedResult = nullptr, *hSchedResult = nullptr; void* dSchedTemp = nullptr; size_t schedTempBytes = 0;
@@ -181,6 +185,7 @@ static inline unsigned divUp(size_t a, size_t b) { return unsigned((a + b - 1) /
 int bvhBuildDevice(vkx_ctx* ctx);
 int bvhRefitDevice(vkx_ctx* ctx);
 int waitGather(vkx_ctx* ctx); // api.cu
+int flushCopyRequests(vkx_ctx* ctx); // api.cu
 int launchP2pWait(vkx_ctx* ctx);   // ddgi.cu: stream-ordered wait for every rank's tiles of the last sharded update
 int launchP2pSignal(vkx_ctx* ctx); // ddgi.cu
 // ---- ddgi.cu

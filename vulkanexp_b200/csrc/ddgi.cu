@@ -799,6 +799,7 @@ int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* /*unused*/,
             }
             poolBlocks = unsigned(ctx->smCount * cached);
         }
+        if (base == 0) { const int rc = flushCopyRequests(ctx); if (rc != VKX_OK) return rc; } // requested read-backs of the sampled atlases run alongside the traversal (api.cu)
         // classification: misses -> sky queue, front hits -> key (grid cell of the hit point) for the grouping below
         static const bool radixSort = [] { const char* e = getenv("VKX_SORT"); return e && !strcmp(e, "radix"); }(); // A/B: the round-1 path (cub::DeviceRadixSort)
         uint32_t binShift = 0; while (((ctx->probeCount - 1u) >> binShift) + 1u > BIN_MAX) ++binShift;
