@@ -51,7 +51,7 @@ int flushCopyRequests(vkx_ctx* ctx) {
     for (const auto& op : ctx->copyRequests) CUDA_TRY(ctx, cudaMemcpyAsync(op.dst, op.src, op.bytes, cudaMemcpyDeviceToHost, ctx->copyStream));
     ctx->copyRequests.clear();
     CUDA_TRY(ctx, cudaEventRecord(ctx->evCopyDone, ctx->copyStream));
-    ctx->copyPending = true; ctx->copyReadsWork = false;
+    ctx->copyPending = true; ctx->copyReadsWork = ctx->copyRequestsReadWork;
     return VKX_OK;
 }
 // Before anything other than an update overwrites the sampled atlases (upload, classification, re-initialisation): the requested
@@ -61,9 +61,12 @@ static int settleReadBack(vkx_ctx* ctx) {
     if (ctx->copyPending) { CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evCopyDone, 0)); ctx->copyPending = false; ctx->copyReadsWork = false; }
     return VKX_OK;
 }
-static bool deferReadBack(const vkx_ctx* ctx) {
+// Single-GPU contexts: reads of the sampled atlases (next written by the next update's publish). Sharded contexts: reads of the rank's
+// own slices from its work atlases (next written by the next update's blend); other reads there go through the exchange bookkeeping
+// (gather / peer stores into alternating sets) and stay eager.
+static bool deferReadBack(const vkx_ctx* ctx, bool fromWork) {
     static const bool off = [] { const char* e = getenv("VKX_READBACK"); return e && !strcmp(e, "eager"); }(); // A/B: queue behind the publish as before
-    return !off && ctx->nranks <= 1;
+    return !off && (ctx->nranks <= 1 ? !fromWork : (fromWork && !ctx->p2p));
 }
 int waitGather(vkx_ctx* ctx) { // orders the context's stream after a pending exchange (all-gather or peer stores) of the sampled atlases
     if (ctx->gatherPending) { CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->gatherDone, 0)); ctx->gatherPending = false; }
@@ -502,6 +505,7 @@ static int uploadOrder(vkx_ctx* ctx, const uint32_t* probeIndices, uint32_t coun
 static int syncWorkAtlases(vkx_ctx* ctx) {
     if (!ctx->workStale) return VKX_OK;
     { int rc = waitGather(ctx); if (rc != VKX_OK) return rc; }
+    { int rc = settleReadBack(ctx); if (rc != VKX_OK) return rc; } // a read-back of the rank's own slices still reads the work atlases rewritten below
     const size_t irrBytes = size_t(ctx->irrW) * ctx->irrH * 4, depBytes = size_t(ctx->depW) * ctx->depH * 4, stBytes = size_t(ctx->probeCount) * 4;
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dIrrWork, ctx->dIrrSampled, irrBytes, cudaMemcpyDeviceToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dDepWork, ctx->dDepSampled, depBytes, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -644,11 +648,16 @@ int vkx_probes_download_slab_async(vkx_ctx* ctx, uint32_t z0, uint32_t z1, uint3
     const vkx_ctx::CopyOp ops[3] = {{irradiance, irrSrc + size_t(8 * z0) * ctx->irrW, size_t(8 * nz) * ctx->irrW * 4},
                                     {depth, depSrc + size_t(16 * z0) * ctx->depW, size_t(16 * nz) * ctx->depW * 4},
                                     {state, stSrc + size_t(z0) * plane, nz * plane * 4}};
-    if (!fromWork && deferReadBack(ctx)) { // noted; queued by the next update (or by whoever needs it ordered first)
+    if (deferReadBack(ctx, fromWork)) { // noted; queued by the next update (or by whoever needs it ordered first)
+        if (!ctx->copyRequests.empty() && ctx->copyRequestsReadWork != fromWork) TRY(flushCopyRequests(ctx));
         for (const auto& op : ops) if (op.dst) ctx->copyRequests.push_back(op);
+        ctx->copyRequestsReadWork = fromWork;
         return VKX_OK;
     }
     TRY(flushCopyRequests(ctx));
+    if (ctx->copyPending && ctx->copyReadsWork != fromWork) { // one flag says which atlas set the copies in flight read: do not mix the two kinds
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evCopyDone, 0)); ctx->copyPending = false;
+    }
     CUDA_TRY(ctx, cudaEventRecord(ctx->evPublished, ctx->stream));
     CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copyStream, ctx->evPublished, 0));
     for (const auto& op : ops) if (op.dst) CUDA_TRY(ctx, cudaMemcpyAsync(op.dst, op.src, op.bytes, cudaMemcpyDeviceToHost, ctx->copyStream));

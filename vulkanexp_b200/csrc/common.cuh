@@ -127,7 +127,7 @@ struct vkx_ctx {
     // Read-backs of the sampled atlases that were requested but not queued yet (single-GPU contexts): they are queued right before the
     // next update's primary traversal starts instead of right behind the publish, see flushCopyRequests (api.cu)
     struct CopyOp { void* dst; const void* src; size_t bytes; };
-    std::vector<CopyOp> copyRequests;
+    std::vector<CopyOp> copyRequests; bool copyRequestsReadWork = false; // all noted requests read the same atlas set (sampled, or the work set: own slices of a sharded update)
 
     // on-device scheduler (schedule.cu); the two counters are the reference's s_LoopIndex / _lastUpdateOffset
     uint32_t *dSchedFlags = nullptr, *dSchedPos = nullptr, *dSchedSlotOf = nullptr, *dSchedResult = nullptr, *hSchedResult = nullptr; void* dSchedTemp = nullptr; size_t schedTempBytes = 0;
