@@ -759,12 +759,17 @@ int ddgiUpdate(vkx_ctx* ctx, const vkx_light& light, const uint32_t* /*unused*/,
     if (!ctx->traceBlocksPerSm) { int a = 0, b = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_trace_primary<0>, 128, 0); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace_shadow<0>, 128, 0); ctx->traceBlocksPerSm = std::max(1, std::min(a, b)); }
     const unsigned persistentBlocks = unsigned(ctx->smCount * ctx->traceBlocksPerSm);
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
-    k_blend_weights<<<(N + 3u) & ~3u, BLEND_COLS, 0, st>>>(ctx->grid.depthSharpness, N, ctx->dDirs, ctx->dBlendW); LAUNCH_CHECK(ctx);
-    k_blend_weight_sums<<<1, BLEND_COLS, 0, st>>>(N, ctx->dBlendW); LAUNCH_CHECK(ctx);
+    // The frame's blend weights (three small kernels, one of them a single block) are only read by the blend at the end of the
+    // update: they run on the second stream, beside the set-up and the traversal, and are joined together with the sky kernel.
+    cudaStream_t ax = ctx->auxStream;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->auxEvent[0], st)); // after the directions' upload and after the previous update's blend (which reads the tables)
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ax, ctx->auxEvent[0], 0));
+    k_blend_weights<<<(N + 3u) & ~3u, BLEND_COLS, 0, ax>>>(ctx->grid.depthSharpness, N, ctx->dDirs, ctx->dBlendW); LAUNCH_CHECK(ctx);
+    k_blend_weight_sums<<<1, BLEND_COLS, 0, ax>>>(N, ctx->dBlendW); LAUNCH_CHECK(ctx);
     // blend on the tensor cores (blend_tc.cu) unless tiles go straight to peer memory (fused exchange) or VKX_BLEND=simt asks for the CUDA-core kernel
     static const bool blendSimt = [] { const char* e = getenv("VKX_BLEND"); return e && !strcmp(e, "simt"); }();
     const bool blendTc = !blendSimt && !ctx->blendToPeers;
-    if (blendTc) { int rc = blendTcWeights(ctx, st); if (rc != VKX_OK) return rc; }
+    if (blendTc) { int rc = blendTcWeights(ctx, ax); if (rc != VKX_OK) return rc; }
     k_dir_table<<<divUp(N, 128), 128, 0, st>>>(N, ctx->dDirs, ctx->dInvDirs); LAUNCH_CHECK(ctx);
     // One chunk: slots are the caller's list positions (ray/hit buffers are laid out [slot][ray]) and `order` only schedules them.
     // Several chunks: the list is first gathered in block order, a chunk is then a contiguous piece of it with identity order.
