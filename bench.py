@@ -365,9 +365,14 @@ def main():
         uid = [Context.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(rank, world, uid[0])
-        exchange = os.environ.get("VKX_EXCHANGE", "nccl")
+        exchange = os.environ.get("VKX_EXCHANGE", "ce")  # ce (default) | nccl | p2p; ce / p2p fall back to nccl when the peers' atlases cannot be mapped
         if exchange == "p2p":  # VKX_EXCHANGE=p2p: blend fused with the atlas exchange over NVLink peer memory (measured slower than the deferred all-gather at 8 GPUs)
             exchange = "p2p" if ctx.comm_p2p_enable(dist) else "nccl"
+        elif exchange == "ce":  # VKX_EXCHANGE=ce: rows pushed into the peers' atlases by copy engines (no SM takes part: runs beside the next step's traversal)
+            if ctx.comm_p2p_enable(dist):
+                ctx.comm_p2p_mode(1)
+            else:
+                exchange = "nccl"
     else:
         exchange = "none"
     stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
@@ -455,6 +460,16 @@ def main():
     ms_per_step = total_ms / K
     value = rays_per_step_total / (ms_per_step * 1e-3)
 
+    # ---- per-rank update time of the last timed step (the library's own events around one update): how uneven the ranks are
+    rank_update_ms = None
+    if world > 1:
+        tm = ctx.probes_timings()
+        in_loop = {"setup_ms": tm["trace"], "first_chunk_kernels_ms": tm["blend"], "after_first_chunk_ms": tm["publish"], "first_chunk": {k: v for k, v in ctx.probes_kernel_timings().items() if k in ("trace_primary", "shade", "trace_shadow", "blend")}}
+        mine = torch.tensor([tm["full"]], device="cuda", dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        rank_update_ms = [round(float(t.item()), 4) for t in allr]
+
     # ---- per-kernel device times: a separate, untimed pass (vkx_probes_kernel_timings synchronises)
     kt = {"trace_primary": 0.0, "shade": 0.0, "trace_shadow": 0.0, "blend": 0.0}
     shadow_rays = 0
@@ -467,6 +482,12 @@ def main():
             kt[nm] += k[nm]
         shadow_rays = k["shadow_rays"]
     barrier()
+    rank_kernel_sum_ms = None
+    if world > 1:  # the same sum on every rank (first chunk of its update, run alone): how evenly the dealt slices load the ranks
+        mine = torch.tensor([sum(kt.values()) / K], device="cuda", dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        rank_kernel_sum_ms = [round(float(t.item()), 4) for t in allr]
 
     # ---- back-to-back time at N = 1 too (no flush, one interval): what a renderer that updates every frame sees
     b2b_ms = None
@@ -548,12 +569,13 @@ def main():
             "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": name, "probes_per_gpu": probes_per_rank, "rays_per_probe": RAYS, "l2": l2_note,
                        "timing": "per-step CUDA events on the library's stream, summed" if world == 1 else "one CUDA-event interval over all steps on the library's stream, closed after the last all-gather",
-                       "parallelism": ("probe z-slices dealt round robin over %d ranks, %s" % (n, "blend fused with the atlas exchange over NVLink peer memory (P2P stores + device-side flags)" if exchange == "p2p" else "NCCL all-gather of atlas slabs, deferred behind the next step's primary traversal")) if n > 1 else "single GPU"},
+                       "parallelism": ("probe z-slices dealt round robin over %d ranks, %s" % (n, "blend fused with the atlas exchange over NVLink peer memory (P2P stores + device-side flags)" if exchange == "p2p" else "atlas rows pushed to every peer by copy engines over NVLink (IPC-mapped atlases, arrival flags), beside the next step's primary traversal" if exchange == "ce" else "NCCL all-gather of atlas slabs, deferred behind the next step's primary traversal")) if n > 1 else "single GPU"},
             "full_volume_update_ms": ms_per_step, "grays_per_sec_per_gpu": value / n / 1e9,
             "gpu_launches": int(launches), "clocks": clocks,
             "e2e": {"value": rays_per_step_total / (e2e_ms * 1e-3), "unit": "probe rays/s", "ms_per_step": e2e_ms, "steps": e2e_steps, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "what": "vkx_probes_update from host buffers + asynchronous read-back of both atlases and the state words into pinned host memory every step (each rank its own z-slab; read-back of step s overlaps step s+1); byte counts are whole-job", "host_atlas_checksum": checksum},
             "kernel_ms": {k: v / K for k, v in kt.items()},
+            **({"rank_update_ms": rank_update_ms, "rank_kernel_sum_ms": rank_kernel_sum_ms, "last_timed_step_on_rank0": in_loop} if rank_update_ms else {}),
         }
         if b2b_ms is not None:
             line["ms_per_step_back_to_back"] = b2b_ms

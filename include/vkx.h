@@ -290,6 +290,12 @@ int vkx_comm_init(vkx_ctx* ctx, int rank, int nranks, const void* id128);
  * sampled atlases waits for all flags on the device - no collective, no host synchronisation. Results are identical. */
 int vkx_comm_p2p_export(vkx_ctx* ctx, void* handle64);
 int vkx_comm_p2p_import(vkx_ctx* ctx, const void* handles /* nranks x 64 bytes, rank order; NULL, 0 = back to NCCL */, int count);
+/* How the peer-memory exchange moves the rows (every rank must choose the same; default 0 after an import):
+ *   0  the blend kernel stores its tiles straight into every peer (the fused path described above; CUDA-core blend);
+ *   1  the blend writes the rank's own rows locally (tensor-core blend) and copy engines push them to every peer's next set over
+ *      NVLink (strided DMA copies, then the arrival flag as a 4-byte copy in the same stream): no SM takes part in the exchange,
+ *      so it runs beside the next update's persistent traversal kernel, which leaves no room for a collective's thread blocks. */
+int vkx_comm_p2p_mode(vkx_ctx* ctx, int copyEngines);
 /* Full-volume update of this rank's z-slices (vkx_shard_slices) followed by the all-gathers of the atlas / state rows. */
 int vkx_probes_update_sharded(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx_light* light,
                               const float orientation[16], int sync);

@@ -401,6 +401,9 @@ class Context:
         buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
         self._check(self.l.vkx_comm_p2p_import(self.h, buf, C.c_int(len(handles))))
 
+    def comm_p2p_mode(self, copy_engines):
+        self._check(self.l.vkx_comm_p2p_mode(self.h, C.c_int(int(copy_engines))))
+
     def comm_p2p_enable(self, dist):
         """Exchange the IPC handles through torch.distributed and map every peer's atlas slab."""
         try:

@@ -62,11 +62,11 @@ static int settleReadBack(vkx_ctx* ctx) {
     return VKX_OK;
 }
 // Single-GPU contexts: reads of the sampled atlases (next written by the next update's publish). Sharded contexts: reads of the rank's
-// own slices from its work atlases (next written by the next update's blend); other reads there go through the exchange bookkeeping
-// (gather / peer stores into alternating sets) and stay eager.
+// own slices from its work atlases (next written by the next update's blend; not with the fused peer stores, whose blend does not keep
+// the work atlases current); other reads there go through the exchange bookkeeping (gather / alternating sets) and stay eager.
 static bool deferReadBack(const vkx_ctx* ctx, bool fromWork) {
     static const bool off = [] { const char* e = getenv("VKX_READBACK"); return e && !strcmp(e, "eager"); }(); // A/B: queue behind the publish as before
-    return !off && (ctx->nranks <= 1 ? !fromWork : (fromWork && !ctx->p2p));
+    return !off && (ctx->nranks <= 1 ? !fromWork : (fromWork && (!ctx->p2p || ctx->p2pCopy)));
 }
 int waitGather(vkx_ctx* ctx) { // orders the context's stream after a pending exchange (all-gather or peer stores) of the sampled atlases
     if (ctx->gatherPending) { CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->gatherDone, 0)); ctx->gatherPending = false; }
@@ -106,6 +106,8 @@ static void releaseP2p(vkx_ctx* ctx) { // the six atlas pointers live inside the
     cudaDeviceSynchronize();
     for (int r = 0; r < VKX_MAX_RANKS; ++r) { if (ctx->peerSlab[r] && ctx->peerSlab[r] != ctx->p2pSlab) cudaIpcCloseMemHandle(ctx->peerSlab[r]); ctx->peerSlab[r] = nullptr; }
     cudaFree(ctx->p2pSlab); ctx->p2pSlab = nullptr;
+    if (ctx->hFlagRing) { cudaFreeHost(ctx->hFlagRing); ctx->hFlagRing = nullptr; }
+    ctx->p2pCopy = false;
     ctx->dIrrSampled = ctx->dDepSampled = ctx->dStateSampled = ctx->dIrrNext = ctx->dDepNext = ctx->dStateNext = nullptr;
     ctx->p2p = ctx->p2pPending = ctx->blendToPeers = false; ctx->p2pFrame = 0; ctx->p2pSampledSet = 0;
 }
@@ -712,7 +714,12 @@ int vkx_probes_timings(vkx_ctx* ctx, float ms[5]) {
     for (int i = 0; i < 5; ++i) ms[i] = 0.f;
     if (!ctx->lastCount) return VKX_OK;
     CUDA_TRY(ctx, cudaEventElapsedTime(&ms[0], ctx->shardedLast ? ctx->ev[4] : ctx->ev[0], ctx->ev[3]));
-    if (ctx->shardedLast) return VKX_OK; // per-stage split is per chunk in the sharded path; only the total is reported
+    if (ctx->shardedLast) { // per-stage split is per chunk in the sharded path: set-up before the first chunk's traversal, that chunk's kernels, everything after its blend
+        CUDA_TRY(ctx, cudaEventElapsedTime(&ms[1], ctx->ev[4], ctx->kev[0]));
+        CUDA_TRY(ctx, cudaEventElapsedTime(&ms[2], ctx->kev[0], ctx->kev[4]));
+        CUDA_TRY(ctx, cudaEventElapsedTime(&ms[4], ctx->kev[4], ctx->ev[3]));
+        return VKX_OK;
+    }
     CUDA_TRY(ctx, cudaEventElapsedTime(&ms[1], ctx->ev[0], ctx->ev[1]));
     CUDA_TRY(ctx, cudaEventElapsedTime(&ms[2], ctx->ev[1], ctx->ev[2]));
     ms[3] = 0.f; // borders are written by the blend kernel
@@ -758,7 +765,7 @@ int vkx_comm_init(vkx_ctx* ctx, int rank, int nranks, const void* id128) {
     ncclComm_t comm;
     ncclResult_t r = ncclCommInitRank(&comm, nranks, id, rank);
     if (r != ncclSuccess) return vkx_fail(ctx, VKX_E_NCCL, "ncclCommInitRank: %s", ncclGetErrorString(r));
-    ctx->comm = reinterpret_cast<ncclComm*>(comm); ctx->rank = rank; ctx->nranks = nranks;
+    ctx->comm = reinterpret_cast<ncclComm*>(comm); ctx->rank = rank; ctx->nranks = nranks; ctx->shardOrderReady = false;
     if (!ctx->commStream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->commStream, cudaStreamNonBlocking));
     if (!ctx->commEvent) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->commEvent, cudaEventDisableTiming));
     if (!ctx->gatherDone) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->gatherDone, cudaEventDisableTiming));
@@ -809,7 +816,16 @@ int vkx_comm_p2p_import(vkx_ctx* ctx, const void* handles, int count) {
         if (e != cudaSuccess) return vkx_fail(ctx, VKX_E_CUDA, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
         ctx->peerSlab[r] = static_cast<char*>(p);
     }
-    ctx->p2p = true;
+    ctx->p2p = true; ctx->p2pCopy = false;
+    return VKX_OK;
+}
+
+int vkx_comm_p2p_mode(vkx_ctx* ctx, int copyEngines) {
+    BIND(ctx);
+    if (!ctx->p2p) return vkx_fail(ctx, VKX_E_INVALID, "vkx_comm_p2p_mode: import the peer slabs first (vkx_comm_p2p_import)");
+    TRY(waitGather(ctx));
+    if (copyEngines && !ctx->hFlagRing) CUDA_TRY(ctx, cudaHostAlloc(&ctx->hFlagRing, 4096 * sizeof(uint32_t), cudaHostAllocPortable));
+    ctx->p2pCopy = copyEngines != 0;
     return VKX_OK;
 }
 
@@ -837,8 +853,8 @@ int vkx_probes_update_sharded(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx
     if (vkx_shard_groups(rz, ctx->nranks, &s, &K) != VKX_OK) return vkx_fail(ctx, VKX_E_INVALID, "vkx_shard_groups");
     ncclComm_t comm = reinterpret_cast<ncclComm_t>(ctx->comm);
     cudaStream_t st = ctx->stream, cs = ctx->commStream;
-    const bool p2p = ctx->p2p;
-    if (p2p) { // k_blend stores its tiles straight into every rank's next atlas set (NVLink peer memory): no separate exchange step
+    const bool p2p = ctx->p2p, pushCopies = ctx->p2p && ctx->p2pCopy;
+    if (p2p && !pushCopies) { // k_blend stores its tiles straight into every rank's next atlas set (NVLink peer memory): no separate exchange step
         const int nextSet = ctx->p2pSampledSet ^ 1;
         PeerTargets pt{}; pt.n = int(n);
         for (uint32_t r = 0; r < n; ++r) {
@@ -846,14 +862,14 @@ int vkx_probes_update_sharded(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx
             pt.irr[r] = reinterpret_cast<uint32_t*>(base); pt.dep[r] = reinterpret_cast<uint32_t*>(base + ctx->p2pDepOff); pt.state[r] = reinterpret_cast<uint32_t*>(base + ctx->p2pStOff);
         }
         ctx->blendPeers = pt; ctx->blendToPeers = true;
-    } else if (ctx->copyPending && !ctx->copyReadsWork) { CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->commStream, ctx->evCopyDone, 0)); ctx->copyPending = false; } // read-back of the buffers about to be overwritten
+    } else if (!p2p && ctx->copyPending && !ctx->copyReadsWork) { CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->commStream, ctx->evCopyDone, 0)); ctx->copyPending = false; } // read-back of the buffers about to be overwritten
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], st));
     const uint32_t groupProbes = s * plane, total = K * groupProbes;
-    for (uint32_t k = 0; k < K; ++k) { // the rank's to-update list: its slices of every group, in z order
-        const uint32_t first = (k * s * n + uint32_t(ctx->rank) * s) * plane;
-        k_iota_list<<<divUp(groupProbes, 256), 256, 0, st>>>(ctx->dIndicesList + size_t(k) * groupProbes, first, groupProbes); LAUNCH_CHECK(ctx);
-    }
-    if (!ctx->shardOrderReady) {
+    if (!ctx->shardOrderReady) { // the rank's to-update list (its slices of every group, in z order) and its slot order: the same every frame, built once
+        for (uint32_t k = 0; k < K; ++k) {
+            const uint32_t first = (k * s * n + uint32_t(ctx->rank) * s) * plane;
+            k_iota_list<<<divUp(groupProbes, 256), 256, 0, st>>>(ctx->dIndicesList + size_t(k) * groupProbes, first, groupProbes); LAUNCH_CHECK(ctx);
+        }
         std::vector<uint32_t> idx(total);
         for (uint32_t k = 0; k < K; ++k) { const uint32_t first = (k * s * n + uint32_t(ctx->rank) * s) * plane; for (uint32_t i = 0; i < groupProbes; ++i) idx[size_t(k) * groupProbes + i] = first + i; }
         TRY(uploadOrder(ctx, idx.data(), total, 0, false));
@@ -863,8 +879,9 @@ int vkx_probes_update_sharded(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx
         CUDA_TRY(ctx, cudaEventRecord(ctx->commEvent, st));
         CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ctx->commEvent, 0));
         const size_t irrChunk = size_t(8 * s) * ctx->irrW, depChunk = size_t(16 * s) * ctx->depW, stChunk = size_t(s) * plane; // elements per rank and group
+        static const bool dbgNoGather = getenv("VKX_DEBUG_NO_GATHER") != nullptr; // timing experiments only: the atlases of the other ranks stay stale
         ncclResult_t r = ncclGroupStart();
-        for (uint32_t k = 0; k < K && r == ncclSuccess; ++k) { // group k: the slices [k s n, (k + 1) s n) of all ranks are consecutive rows
+        for (uint32_t k = 0; k < K && r == ncclSuccess && !dbgNoGather; ++k) { // group k: the slices [k s n, (k + 1) s n) of all ranks are consecutive rows
             const size_t irrOff = size_t(8 * k * s * n) * ctx->irrW, depOff = size_t(16 * k * s * n) * ctx->depW, stOff = size_t(k * s * n) * plane;
             r = ncclAllGather(ctx->dIrrWork + irrOff + irrChunk * ctx->rank, ctx->dIrrNext + irrOff, irrChunk, ncclUint32, comm, cs);
             if (r == ncclSuccess) r = ncclAllGather(ctx->dDepWork + depOff + depChunk * ctx->rank, ctx->dDepNext + depOff, depChunk, ncclUint32, comm, cs);
@@ -874,7 +891,34 @@ int vkx_probes_update_sharded(vkx_ctx* ctx, const vkx_grid_info* grid, const vkx
         if (r != ncclSuccess) return vkx_fail(ctx, VKX_E_NCCL, "ncclAllGather: %s", ncclGetErrorString(r));
     }
     ctx->shardOrderReady = true;
-    if (p2p) {
+    if (pushCopies) {
+        // Copy engines push this rank's rows of every group into the next set of every rank (its own included): one strided copy per
+        // array and peer (width = the rank's rows of one group, one row of the copy per group). They are ordered after the blend and
+        // run beside the next update's traversal without occupying an SM - the persistent traversal kernel fills every SM to the last
+        // register, so a collective's thread blocks only became resident when it ended (2 GPUs, cfg4: 14.06 ms with the NCCL
+        // all-gather, 13.54 ms with the exchange left out). The arrival flag follows as a 4-byte copy in the same stream; the flag
+        // protocol is the one of the fused path (a rank writes set T only after every rank has raised the previous frame's flag).
+        const int nextSet = ctx->p2pSampledSet ^ 1;
+        CUDA_TRY(ctx, cudaEventRecord(ctx->commEvent, st));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ctx->commEvent, 0));
+        const size_t irrW = size_t(8 * s) * ctx->irrW * 4, depW = size_t(16 * s) * ctx->depW * 4, stW = size_t(s) * plane * 4; // bytes of one rank's rows in one group
+        const size_t own = size_t(ctx->rank);
+        for (uint32_t r = 0; r < n; ++r) {
+            char* base = ctx->peerSlab[r] + size_t(nextSet) * ctx->p2pSetBytes;
+            CUDA_TRY(ctx, cudaMemcpy2DAsync(base + own * irrW, irrW * n, reinterpret_cast<const char*>(ctx->dIrrWork) + own * irrW, irrW * n, irrW, K, cudaMemcpyDeviceToDevice, cs));
+            CUDA_TRY(ctx, cudaMemcpy2DAsync(base + ctx->p2pDepOff + own * depW, depW * n, reinterpret_cast<const char*>(ctx->dDepWork) + own * depW, depW * n, depW, K, cudaMemcpyDeviceToDevice, cs));
+            CUDA_TRY(ctx, cudaMemcpy2DAsync(base + ctx->p2pStOff + own * stW, stW * n, reinterpret_cast<const char*>(ctx->dStateWork) + own * stW, stW * n, stW, K, cudaMemcpyDeviceToDevice, cs));
+        }
+        // peers may overwrite the set a queued read-back still reads as soon as they see this rank's flag: raise it after the copy
+        if (ctx->copyPending && !ctx->copyReadsWork) { CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ctx->evCopyDone, 0)); ctx->copyPending = false; }
+        uint32_t* src = ctx->hFlagRing + (ctx->p2pFrame & 4095u);
+        *src = ctx->p2pFrame + 1u; // the host is never 4096 frames ahead of the device
+        for (uint32_t r = 0; r < n; ++r)
+            CUDA_TRY(ctx, cudaMemcpyAsync(reinterpret_cast<uint32_t*>(ctx->peerSlab[r] + ctx->p2pFlagsOff) + ctx->rank, src, 4, cudaMemcpyDefault, cs));
+        // (the wait of the next reader - waitGather - polls this rank's own flag too: when it has passed, the pushes above have left
+        // the work atlases, which the next blend rewrites)
+        ctx->p2pFrame++; ctx->p2pSampledSet ^= 1; ctx->p2pPending = true;
+    } else if (p2p) {
         ctx->blendToPeers = false;
         // peers may overwrite the set a queued read-back still reads as soon as they see this rank's flag: raise it after the copy
         if (ctx->copyPending && !ctx->copyReadsWork) { CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->evCopyDone, 0)); ctx->copyPending = false; }

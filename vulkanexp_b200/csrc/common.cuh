@@ -141,6 +141,8 @@ struct vkx_ctx {
     // peer-memory exchange (vkx_comm_p2p_export / _import): one slab per rank = atlas set 0 | atlas set 1 | arrival flags | error word,
     // mapped into every peer through CUDA IPC; sampled / next point into the slab
     bool p2p = false, p2pPending = false, blendToPeers = false;
+    bool p2pCopy = false;          // peer exchange by copy engines (vkx_comm_p2p_mode): the blend writes local rows, DMA copies push them to the peers
+    uint32_t* hFlagRing = nullptr; // pinned ring of frame numbers: the source of the arrival-flag copies
     char* p2pSlab = nullptr; char* peerSlab[VKX_MAX_RANKS] = {};
     size_t p2pSetBytes = 0, p2pDepOff = 0, p2pStOff = 0, p2pFlagsOff = 0;
     uint32_t p2pFrame = 0; int p2pSampledSet = 0;
