@@ -1,6 +1,6 @@
 """Multi-GPU check (run with torchrun, one rank per GPU): the sharded update + NCCL all-gather must give every rank
-atlases identical to a single-GPU update. Prints one line per rank and exits non-zero on mismatch. VKX_P2P=1 selects the
-peer-memory exchange, which stores from the CUDA-core blend: run it with VKX_BLEND=simt so that the single-GPU side uses the same kernel."""
+atlases identical to a single-GPU update. Prints one line per rank and exits non-zero on mismatch. VKX_P2P=1 / VKX_P2P=ce select the
+peer-memory exchange (1: fused peer stores from the CUDA-core blend - run it with VKX_BLEND=simt so that the single-GPU side uses the same kernel; ce: copy-engine pushes, tensor-core blend on both sides)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -25,10 +25,12 @@ ctx.probes_upload(state=ones)
 uid = [Context.comm_unique_id() if rank == 0 else None]
 dist.broadcast_object_list(uid, src=0)
 ctx.comm_init(rank, world, uid[0])
-P2P = os.environ.get("VKX_P2P", "0") == "1"
-if P2P:  # blend fused with the atlas exchange over NVLink peer memory instead of the NCCL all-gather
-    ctx.comm_p2p_enable(dist)
-    print("rank %d: peer-memory exchange enabled" % rank, flush=True)
+P2P = os.environ.get("VKX_P2P", "0") in ("1", "ce")  # 1: blend fused with peer stores (compare with VKX_BLEND=simt); ce: copy-engine pushes
+if P2P:  # atlas exchange over NVLink peer memory instead of the NCCL all-gather
+    assert ctx.comm_p2p_enable(dist), "peer atlases could not be mapped"
+    if os.environ["VKX_P2P"] == "ce":
+        ctx.comm_p2p_mode(1)
+    print("rank %d: peer-memory exchange enabled (%s)" % (rank, "copy engines" if os.environ["VKX_P2P"] == "ce" else "fused peer stores"), flush=True)
 ref = Context(local); ref.scene_upload(flat); ref.bvh_build(); ref.probes_init(grid); ref.probes_upload(state=ones)
 gen = OrientationGenerator()
 ok = True
